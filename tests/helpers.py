@@ -1,0 +1,50 @@
+"""Shared test helpers: golden-fixture loading and synthetic Criteo-shaped inputs."""
+import json
+import os
+
+import numpy as np
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name + '.npz'))
+    g = {'sd': {}, 'data': {}, 'out': {}, 'grad': {}}
+    for k in z.files:
+        top, rest = k.split('/', 1)
+        if top == 'meta':
+            g['meta'] = json.loads(bytes(z[k]).decode())
+        else:
+            g[top][rest] = torch.from_numpy(z[k].copy())
+    return g
+
+
+def load_layers():
+    z = np.load(os.path.join(GOLDEN, 'layers.npz'))
+    return {k: torch.from_numpy(z[k].copy()) for k in z.files}
+
+
+def sub_sd(flat, tag):
+    p = tag + '/sd/'
+    return {k[len(p):]: v for k, v in flat.items() if k.startswith(p)}
+
+
+def make_enc(n_sparse, n_dense, vocab):
+    enc = {f'I{i + 1}': {'min': 0.0, 'max': 1.0} for i in range(n_dense)}
+    vs = vocab if isinstance(vocab, (list, tuple)) else [vocab] * n_sparse
+    enc.update({f'C{i + 1}': {'vocab_size': int(vs[i])} for i in range(n_sparse)})
+    return enc
+
+
+def make_batch(enc, B, seed=1029, labels=('label',), device='cpu'):
+    gen = torch.Generator().manual_seed(seed)
+    data = {}
+    for c, d in enc.items():
+        if 'vocab_size' in d:
+            data[c] = torch.randint(0, d['vocab_size'] + 1, (B,), dtype=torch.int64, generator=gen)
+        else:
+            data[c] = torch.rand(B, generator=gen)
+    for l in labels:
+        data[l] = (torch.rand(B, generator=gen) < 0.25).float()
+    return {k: v.to(device) for k, v in data.items()}
