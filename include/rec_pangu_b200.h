@@ -1,0 +1,137 @@
+/* rec_pangu_b200.h — C ABI of librec_pangu_b200.so (sm_100a kernels for the rec_pangu ranking hot path).
+ *
+ * The reference (HaSai666/rec_pangu) has no FFI: its hot path is a chain of ATen calls made from Python
+ * nn.Modules.  Each entry point below replaces one such chain; the cited file:line
+ * is the reference code whose results it must reproduce.  All pointers are raw device pointers unless a
+ * parameter is documented as a host array; `stream` is a cudaStream_t passed as void*; every function
+ * returns 0 on success, a cudaError_t (>0) from the launch, or a negative RPB_ERR_* code.  Nothing here
+ * depends on PyTorch.  There is no CPU implementation behind any of these symbols.
+ *
+ * Layout conventions
+ *   x  : [B, ldx] fp32 row-major "feature row": columns [0, F*D) = the F gathered embedding rows of a sample
+ *        (the reference's [B,F,D] tensor, models/layers/embedding.py:63), columns [F*D, F*D+Nd) = the dense
+ *        features (models/utils.py:122-137), columns up to ldx zero.  ldx % 4 == 0.  This is at once
+ *        `sparse_embedding` (strided view) and `dnn_input` (ranking/deepfm.py:52-58) — the cat is never made.
+ *   W  : nn.Linear layout [N, K] row-major (K contiguous).
+ */
+#ifndef REC_PANGU_B200_H
+#define REC_PANGU_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RPB_MAX_FIELDS 64
+#define RPB_MAX_DENSE 64
+
+#define RPB_ERR_UNSUPPORTED (-1)   /* shape outside what the kernels were built for */
+#define RPB_ERR_BAD_ARG (-2)
+#define RPB_ERR_NO_DRIVER (-3)     /* cuTensorMapEncodeTiled could not be resolved */
+
+/* ABI version; bumped whenever a signature changes. */
+int rpb_version(void);
+/* Last error text for negative codes (static string). */
+const char* rpb_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-table embedding gather (+ dense pack, + FM second order, + LR wide inputs) — one launch.
+ * Replaces EmbeddingLayer.forward (models/layers/embedding.py:49-63: F x aten::embedding + stack),
+ * get_linear_input (models/utils.py:122-137), FM_Layer / InnerProductLayer product_sum_pooling
+ * (models/layers/interaction.py:36-44,225-235) and LR_Layer's second D=1 gather
+ * (models/layers/shallow.py:22-26).
+ * Index semantics are the reference's: int64 row ids, table f has rows[f] = vocab_size+1 rows
+ * (embedding.py:32), id == vocab_size is the OOV row; id < 0 or id >= rows[f] is an error: the kernel
+ * records {1, field, sample, value} into err[0..3] (first error wins) and reads row 0 instead.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct RpbGatherDesc {
+    int32_t B, F, D, Nd;
+    int32_t ldx;                    /* row stride of x in floats, >= F*D+Nd, % 4 == 0 */
+    int32_t ld_lr;                  /* row stride of lr_in in floats (>= F+Nd), 0 if lr_in == NULL */
+    const float* const* tables;     /* host array [F] of device ptrs: table f = float[rows[f]][D] */
+    const int64_t* rows;            /* host array [F] */
+    const int64_t* const* idx;      /* host array [F] of device ptrs int64[B] */
+    const float* const* dense;      /* host array [Nd] of device ptrs float[B]; NULL when Nd == 0 */
+    const float* const* lr_tables;  /* host array [F] of device ptrs float[rows[f]] (D=1 tables) or NULL */
+    float* x;                       /* out [B, ldx] */
+    float* fm;                      /* out [B]: 0.5*sum_d((sum_f e)^2 - sum_f e^2), or NULL */
+    float* fm_s;                    /* out [B, D]: sum_f e (saved for backward), or NULL */
+    float* lr_in;                   /* out [B, ld_lr]: [lr_table_f[idx_f] (F) | dense (Nd)], or NULL */
+    int64_t* err;                   /* device-visible int64[4] error record (see above) */
+} RpbGatherDesc;
+int rpb_gather_fwd(const RpbGatherDesc* d, void* stream);
+
+/* Backward of the gather: scatter-add of per-sample row gradients into per-table gradients
+ * (autograd of aten::embedding = embedding_dense_backward), fused with the FM and LR
+ * backward terms:  gE[b,f,:] = dx[b, f*D:(f+1)*D] + dfm[b]*(fm_s[b,:] - x[b,f,:]);
+ *                  grads[f][idx[f][b], :] += gE[b,f,:];   lr_grads[f][idx[f][b]] += dlr_in[b,f].
+ * grads / lr_grads must be zero-initialised (dense mode) by the caller; additions are fp32 atomics. */
+typedef struct RpbScatterDesc {
+    int32_t B, F, D;
+    int32_t lddx, ldx, ld_dlr;
+    float* const* grads;            /* host array [F] of device ptrs float[rows[f]][D]; entry may be NULL (frozen table) */
+    float* const* lr_grads;         /* host array [F] of device ptrs float[rows[f]] or NULL */
+    const int64_t* rows;            /* host array [F] */
+    const int64_t* const* idx;      /* host array [F] of device ptrs int64[B] */
+    const float* dx;                /* [B, lddx] grad wrt x, or NULL */
+    const float* x;                 /* [B, ldx] forward output (needed iff dfm) */
+    const float* dfm;               /* [B] grad wrt fm, or NULL */
+    const float* fm_s;              /* [B, D] saved sum_f e (needed iff dfm) */
+    const float* dlr_in;            /* [B, ld_dlr] grad wrt lr_in (first F columns used), or NULL */
+} RpbScatterDesc;
+int rpb_gather_bwd(const RpbScatterDesc* d, void* stream);
+
+/* Standalone FM second-order term on any [B,F,D] tensor with row stride lde (floats) between samples:
+ * InnerProductLayer (interaction.py:36-44).  out_sum [B] (product_sum_pooling) and/or out_bi [B,D]
+ * (Bi_interaction_pooling) may be NULL. */
+int rpb_fm_fwd(const float* e, int64_t lde, int B, int F, int D, float* out_sum, float* out_bi, void* stream);
+/* de[b,f,:] (+)= (dsum[b] + dbi[b,:]) * (s[b,:] - e[b,f,:]); accumulate != 0 adds into de. */
+int rpb_fm_bwd(const float* e, int64_t lde, int B, int F, int D, const float* dsum, const float* dbi,
+               float* de, int64_t ldde, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense layers.  nn.Linear + activation of MLP (models/layers/deep.py:62-70).
+ * y[M,N] = act(x[M,K] @ W[N,K]^T + bias[N]);  act: 0 none, 1 relu.
+ * impl: 0 = auto (tcgen05 3xTF32 when the shape qualifies), 1 = SIMT fp32, 2 = tcgen05 3xTF32.
+ * ---------------------------------------------------------------------------------------------- */
+int rpb_linear_fwd(const float* x, int64_t ldx, const float* W, const float* bias, float* y, int64_t ldy,
+                   int M, int N, int K, int act, int impl, void* stream);
+/* dx[M,K] = (dy[M,N] @ W[N,K]) * (mask ? (mask[m,k] > 0) : 1)   — mask = saved post-ReLU input of this
+ * layer, fusing the previous layer's ReLU backward.  dx may be NULL.
+ * dW[N,K] += dy^T @ x,  db[N] += colsum(dy)   (dW/db must be zero-initialised or hold the running sum). */
+int rpb_linear_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* W,
+                   const float* mask, int64_t ldmask, float* dx, int64_t lddx, float* dW, float* db,
+                   int M, int N, int K, int impl, void* stream);
+
+/* Row dot (N=1 linear): out[m] = x[m,:K].w + bias[0] + add0[m] + add1[m] + add2[m]  (NULL addends skipped).
+ * Final Linear(->1) of the MLP plus the logit sum of ranking/deepfm.py:61, xdeepfm.py:69, autoint.py:72-81. */
+int rpb_rowdot_fwd(const float* x, int64_t ldx, const float* w, const float* bias, const float* add0,
+                   const float* add1, const float* add2, float* out, int M, int K, void* stream);
+/* dx[m,k] = dout[m]*w[k] * (mask ? mask[m,k]>0 : 1) (dx may be NULL); dw[k] += sum_m dout[m]*x[m,k]; db[0] += sum dout. */
+int rpb_rowdot_bwd(const float* dout, const float* x, int64_t ldx, const float* w, const float* mask,
+                   int64_t ldmask, float* dx, int64_t lddx, float* dw, float* db, int M, int K, void* stream);
+
+/* pred = sigmoid(logit); loss = mean BCE(pred, label) with log clamped at -100 like ATen
+ * (torch.nn.BCELoss, e.g. ranking/deepfm.py:31,61-63).  eps is added to pred before the BCE
+ * (multi_task/mmoe.py:127-128 uses 1e-6; ranking models 0).  loss_out[0] = scale * mean.  label/loss_out may
+ * be NULL (inference).  work: device int32[2 + 1024*2] scratch owned by the caller, zero-initialised once. */
+int rpb_sigmoid_bce_fwd(const float* logit, const float* label, float* pred, float* loss_out, float eps,
+                        float scale, int M, void* work, void* stream);
+/* dlogit[m] = gloss[0]*scale/M * dBCE/dp * p(1-p), ATen formulas (binary_cross_entropy_backward: denominator
+ * clamped at 1e-12). */
+int rpb_sigmoid_bce_bwd(const float* pred, const float* label, const float* gloss, float eps, float scale,
+                        float* dlogit, int M, void* stream);
+
+/* nn.Dropout of the MLP (models/layers/deep.py:71-72, default p=0.1 for xDeepFM/AutoInt) on a contiguous
+ * buffer of n floats.  keep(i) comes from a counter-based generator keyed by (seed, i), so backward recomputes
+ * the mask instead of storing it.  Train-mode equivalence with torch's Philox stream is statistical
+ * (SURVEY.md §7 hard-part 4).  bwd: dx = dy * keep/(1-p) * (relu_out ? relu_out > 0 : 1). */
+int rpb_dropout_fwd(const float* x, float* y, int64_t n, float p, uint64_t seed, void* stream);
+int rpb_dropout_bwd(const float* dy, const float* relu_out, float* dx, int64_t n, float p, uint64_t seed,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REC_PANGU_B200_H */

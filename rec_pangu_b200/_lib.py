@@ -1,0 +1,83 @@
+"""ctypes binding of librec_pangu_b200.so (the C ABI declared in include/rec_pangu_b200.h).
+
+There is no fallback: if the library cannot be loaded (and cannot be built with nvcc), importing the ops raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'librec_pangu_b200.so')
+ABI_VERSION = 1
+MAX_FIELDS = 64
+MAX_DENSE = 64
+
+_vp = C.c_void_p
+_i32 = C.c_int32
+_i64 = C.c_int64
+_f32 = C.c_float
+
+
+class GatherDesc(C.Structure):
+    _fields_ = [('B', _i32), ('F', _i32), ('D', _i32), ('Nd', _i32), ('ldx', _i32), ('ld_lr', _i32),
+                ('tables', C.POINTER(_vp)), ('rows', C.POINTER(_i64)), ('idx', C.POINTER(_vp)),
+                ('dense', C.POINTER(_vp)), ('lr_tables', C.POINTER(_vp)),
+                ('x', _vp), ('fm', _vp), ('fm_s', _vp), ('lr_in', _vp), ('err', _vp)]
+
+
+class ScatterDesc(C.Structure):
+    _fields_ = [('B', _i32), ('F', _i32), ('D', _i32), ('lddx', _i32), ('ldx', _i32), ('ld_dlr', _i32),
+                ('grads', C.POINTER(_vp)), ('lr_grads', C.POINTER(_vp)), ('rows', C.POINTER(_i64)),
+                ('idx', C.POINTER(_vp)), ('dx', _vp), ('x', _vp), ('dfm', _vp), ('fm_s', _vp), ('dlr_in', _vp)]
+
+
+# name -> (restype, argtypes); must list every symbol of include/rec_pangu_b200.h (tests check this)
+SIGNATURES = {
+    'rpb_version': (C.c_int, []),
+    'rpb_error_string': (C.c_char_p, [C.c_int]),
+    'rpb_gather_fwd': (C.c_int, [C.POINTER(GatherDesc), _vp]),
+    'rpb_gather_bwd': (C.c_int, [C.POINTER(ScatterDesc), _vp]),
+    'rpb_fm_fwd': (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
+    'rpb_fm_bwd': (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _i64, C.c_int, _vp]),
+    'rpb_linear_fwd': (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    'rpb_linear_bwd': (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _vp,
+                                 C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    'rpb_rowdot_fwd': (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
+    'rpb_rowdot_bwd': (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _vp, C.c_int, C.c_int, _vp]),
+    'rpb_sigmoid_bce_fwd': (C.c_int, [_vp, _vp, _vp, _vp, _f32, _f32, C.c_int, _vp, _vp]),
+    'rpb_sigmoid_bce_bwd': (C.c_int, [_vp, _vp, _vp, _f32, _f32, _vp, C.c_int, _vp]),
+    'rpb_dropout_fwd': (C.c_int, [_vp, _vp, _i64, _f32, C.c_uint64, _vp]),
+    'rpb_dropout_bwd': (C.c_int, [_vp, _vp, _vp, _i64, _f32, C.c_uint64, _vp]),
+}
+
+_lib = None
+
+
+class RpbError(RuntimeError):
+    pass
+
+
+def load():
+    """Load (building first if the .so is absent and nvcc exists).  Raises loudly otherwise."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build
+        _build.build(verbose=False)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header / library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    v = lib.rpb_version()
+    if v != ABI_VERSION:
+        raise RpbError(f'librec_pangu_b200.so ABI version {v} != expected {ABI_VERSION}; rebuild with '
+                       f'`python -m rec_pangu_b200.build --force`')
+    _lib = lib
+    return lib
+
+
+def check(code, what):
+    if code != 0:
+        msg = load().rpb_error_string(code).decode()
+        raise RpbError(f'{what} failed: {msg} (code {code})')

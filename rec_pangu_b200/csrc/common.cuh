@@ -1,0 +1,69 @@
+// rec_pangu_b200 — common device/host helpers for the sm_100a kernel library.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rec_pangu_b200.h"
+
+#define RPB_API extern "C" __attribute__((visibility("default")))
+
+#define RPB_LAUNCH_CHECK()                                  \
+    do {                                                    \
+        cudaError_t _e = cudaGetLastError();                \
+        if (_e != cudaSuccess) return (int)_e;              \
+    } while (0)
+
+namespace rpb {
+
+constexpr int kWarp = 32;
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ float4 ldg_f4(const float* p) {
+    return __ldg(reinterpret_cast<const float4*>(p));
+}
+// streaming 128-bit load that does not allocate in L1 (rows are touched once)
+__device__ __forceinline__ float4 ldg_f4_stream(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_f4(float* p, const float4& v) {
+    *reinterpret_cast<float4*>(p) = v;
+}
+// vector reduction: one 16-byte fp32x4 add, no return value (sm_90+)
+__device__ __forceinline__ void red_add_f4(float* p, const float4& v) {
+    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void red_add_f1(float* p, float v) {
+    asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <int LANES>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum for blockDim.x <= 1024, result valid in thread 0
+__device__ __forceinline__ float block_sum(float v, float* smem32) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) smem32[w] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? smem32[threadIdx.x] : 0.f;
+    if (w == 0) v = warp_sum(v);
+    __syncthreads();
+    return v;
+}
+
+}  // namespace rpb

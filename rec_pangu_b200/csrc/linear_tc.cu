@@ -1,0 +1,398 @@
+// tcgen05 / TMEM / TMA dense layer for sm_100a with fp32-grade accuracy ("3xTF32").
+//
+// C[M,N] = epi( A[M,K] . B[N,K]^T ),  A,B fp32 K-major in HBM.  The reference computes this contraction in
+// full fp32 (aten::addmm, models/layers/deep.py:62-70); a single TF32 pass loses ~1e-3 on the logits
+// (SURVEY.md §7 hard-part 2), so every operand is split x = hi + lo with hi = x & 0xFFFFE000 (exact TF32)
+// and three tensor-core products are accumulated in TMEM:  hi*hi + lo*hi + hi*lo  (error ~2^-22 relative).
+//
+// CTA = one 128-row M tile x BLOCK_N (<=256) columns, warp-specialised:
+//   warp 0   : TMA producer — A tile [128 x 32 fp32] and pre-split B_hi/B_lo tiles [BLOCK_N x 32], SWIZZLE_128B
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (kind::tf32, M=128, N=BLOCK_N, K=8)
+//   warps 2-5: split A in shared memory (hi in place, lo to a twin buffer), then the epilogue:
+//              tcgen05.ld 32x32b -> bias / ReLU / ReLU-mask -> global
+// Pipeline barriers per stage: full (TMA landed) -> ready (split done, fenced to the async proxy) ->
+// empty (tcgen05.commit after the stage's 12 MMAs).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace rpb {
+
+constexpr int TC_BLOCK_M = 128;
+constexpr int TC_BLOCK_K = 32;                  // fp32 elements = 128 bytes = one swizzle row
+constexpr int TC_UMMA_K = 8;                    // tf32: 32 bytes per MMA K step
+constexpr int TC_THREADS = 192;
+constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 4;   // 16 KiB
+
+// ---------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}"
+                 :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug traps (sticky CUDA error reported to the host) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    const long long t0 = clock64();
+    uint32_t done = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) break;
+        if (clock64() - t0 > 4000000000ll) { __trap(); }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor, K-major, SWIZZLE_128B: rows are 128 B apart, 8-row groups 1024 B apart
+// (SBO), LBO unused for swizzled K-major layouts (encoded 1), version 1 (Blackwell), layout type 2.
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);            // start address  [0,14)
+    d |= (uint64_t)1 << 16;                                 // LBO (16 B)     [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;                       // SBO (1024 B)   [32,46)
+    d |= (uint64_t)1 << 46;                                 // version = 1    [46,48)
+    d |= (uint64_t)2 << 61;                                 // SWIZZLE_128B   [61,64)
+    return d;
+}
+// Instruction descriptor: D=F32 (bits 4-5 = 1), A=B=TF32 (bits 7-9, 10-12 = 2), K-major A and B (bits 15, 16 = 0),
+// N>>3 in bits 17-22, M>>4 in bits 24-28.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct TcEpilogue {
+    float* C; long long ldc;
+    const float* bias;
+    const float* mask; long long ldmask;
+    int M, N;            // valid extents
+    int relu;
+};
+
+template <int kStages>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+                   const __grid_constant__ CUtensorMap tmBlo, const TcEpilogue ep, int block_n, int num_k_blocks,
+                   uint32_t tmem_cols) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte alignment is required by SWIZZLE_128B; the dynamic smem base is only guaranteed 16 B
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int b_bytes = block_n * TC_BLOCK_K * 4;
+    const int stage_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * stage_bytes);
+    uint64_t* full_bar = bars;
+    uint64_t* ready_bar = bars + kStages;
+    uint64_t* empty_bar = bars + 2 * kStages;
+    uint64_t* tmem_full_bar = bars + 3 * kStages;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * TC_BLOCK_M;
+    const int n0 = blockIdx.y * block_n;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&ready_bar[s], 128); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t tx_bytes = (uint32_t)(TC_A_BYTES + 2 * b_bytes);
+            for (int kb = 0; kb < num_k_blocks; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (uint32_t)((kb / kStages) & 1);
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                uint8_t* st = smem + (size_t)s * stage_bytes;
+                mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+                tma_load_2d(st, &tmA, &full_bar[s], kb * TC_BLOCK_K, m0);
+                tma_load_2d(st + 2 * TC_A_BYTES, &tmBhi, &full_bar[s], kb * TC_BLOCK_K, n0);
+                tma_load_2d(st + 2 * TC_A_BYTES + b_bytes, &tmBlo, &full_bar[s], kb * TC_BLOCK_K, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(TC_BLOCK_M, block_n);
+            for (int kb = 0; kb < num_k_blocks; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (uint32_t)((kb / kStages) & 1);
+                mbar_wait(&ready_bar[s], ph);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint32_t a_lo = a_hi + TC_A_BYTES;
+                const uint32_t b_hi = a_hi + 2 * TC_A_BYTES;
+                const uint32_t b_lo = b_hi + b_bytes;
+#pragma unroll
+                for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
+                    const uint32_t koff = k * TC_UMMA_K * 4;      // 32 B per K step inside the 128 B swizzle row
+                    const uint64_t da_hi = make_kmajor_sw128_desc(a_hi + koff);
+                    const uint64_t da_lo = make_kmajor_sw128_desc(a_lo + koff);
+                    const uint64_t db_hi = make_kmajor_sw128_desc(b_hi + koff);
+                    const uint64_t db_lo = make_kmajor_sw128_desc(b_lo + koff);
+                    umma_tf32(tmem_base, da_lo, db_hi, idesc, (kb > 0 || k > 0) ? 1u : 0u);   // small terms first
+                    umma_tf32(tmem_base, da_hi, db_lo, idesc, 1u);
+                    umma_tf32(tmem_base, da_hi, db_hi, idesc, 1u);
+                }
+                umma_commit(&empty_bar[s]);          // frees the stage once these MMAs have read smem
+            }
+            umma_commit(tmem_full_bar);              // accumulator complete
+        }
+    } else {
+        // ---------------- split warps: A -> (hi, lo)
+        const int t = threadIdx.x - 64;              // 0..127
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+            const int s = kb % kStages;
+            const uint32_t ph = (uint32_t)((kb / kStages) & 1);
+            mbar_wait(&full_bar[s], ph);
+            float4* a = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
+            float4* lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + TC_A_BYTES);
+#pragma unroll
+            for (int i = 0; i < TC_A_BYTES / 16 / 128; ++i) {
+                const int j = t + i * 128;
+                const float4 v = a[j];
+                float4 h, l;
+                h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+                h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+                h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+                h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+                a[j] = h;
+                lo[j] = l;
+            }
+            fence_proxy_async();                     // generic-proxy writes -> visible to the tensor core (async proxy)
+            mbar_arrive(&ready_bar[s]);
+        }
+        // ---------------- epilogue: TMEM -> registers -> global
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const int quarter = warp & 3;                // TMEM lane quarter this warp may access
+        const int row = quarter * 32 + lane;
+        const int m = m0 + row;
+        const bool vec_ok = ((ep.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.C) & 15u) == 0);
+        for (int c0 = 0; c0 < block_n; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+            if (m < ep.M) {
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n = n0 + c0 + j;
+                    float x = __uint_as_float(r[j]);
+                    if (n < ep.N) {
+                        if (ep.bias != nullptr) x += __ldg(ep.bias + n);
+                        if (ep.relu) x = fmaxf(x, 0.f);
+                        if (ep.mask != nullptr) x = (__ldg(ep.mask + (size_t)m * ep.ldmask + n) > 0.f) ? x : 0.f;
+                    }
+                    v[j] = x;
+                }
+                float* crow = ep.C + (size_t)m * ep.ldc + n0 + c0;
+                if (vec_ok && n0 + c0 + 16 <= ep.N) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) stg_f4(crow + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) if (n0 + c0 + j < ep.N) crow[j] = v[j];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+// W[N,K] (row stride ldw) -> hi/lo [Np, Kp] zero padded;  transpose: out[k, n] = W[n, k] (out is [Kout=K rows.., ])
+__global__ void __launch_bounds__(256)
+split_pack_kernel(const float* __restrict__ W, long long ldw, int rows_in, int cols_in, int transpose,
+                  float* __restrict__ hi, float* __restrict__ lo, int Rp, int Cp) {
+    // output is [Rp, Cp]; logical out(r, c) = transpose ? W[c, r] : W[r, c]
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)Rp * Cp) return;
+    const int r = (int)(t / Cp), c = (int)(t % Cp);
+    const int out_rows = transpose ? cols_in : rows_in, out_cols = transpose ? rows_in : cols_in;
+    float v = 0.f;
+    if (r < out_rows && c < out_cols) v = transpose ? __ldg(W + (size_t)c * ldw + r) : __ldg(W + (size_t)r * ldw + c);
+    const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    hi[t] = h;
+    lo[t] = v - h;
+}
+
+// ---------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 tensor [rows, cols] with row stride ld (floats); box = [box_rows, 32 cols], 128 B swizzle, zero OOB fill
+static int make_map(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr) return RPB_ERR_NO_DRIVER;
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : RPB_ERR_BAD_ARG;
+}
+
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+bool tc_shape_ok(const float* A, long long lda, int M, int N, int K) {
+    return M >= 1 && N >= 1 && K >= 1 && (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15u) == 0);
+}
+
+// C[M,N] = epi(A[M,K] . op(W)^T) where op(W) = W [N,K] (transpose_w = 0) or W^T with W stored [K,N]... see callers.
+// Bsrc is given as a [b_rows_in, b_cols_in] row-major matrix (stride ldb); the B operand is [N, K] = Bsrc or Bsrc^T.
+int gemm_tc(const float* A, long long lda, const float* Bsrc, long long ldb, int b_transpose, const TcEpilogue& ep,
+            int M, int N, int K, cudaStream_t st) {
+    if (!tc_shape_ok(A, lda, M, N, K)) return RPB_ERR_UNSUPPORTED;
+    // N tiling: one tile if N <= 256, else tiles of <= 256 columns (multiple of 16)
+    const int n_tiles = ceil_div(N, 256);
+    const int block_n = round_up(ceil_div(N, n_tiles), 16);
+    const int Np = block_n * n_tiles;
+    const int Kp = round_up(K, 4);
+    const int nkb = ceil_div(K, TC_BLOCK_K);
+    float* ws = nullptr;
+    cudaError_t e = cudaMallocAsync(&ws, (size_t)2 * Np * Kp * sizeof(float), st);
+    if (e != cudaSuccess) return (int)e;
+    float* hi = ws;
+    float* lo = ws + (size_t)Np * Kp;
+    const int rows_in = b_transpose ? K : N, cols_in = b_transpose ? N : K;
+    split_pack_kernel<<<ceil_div((long long)Np * Kp, 256), 256, 0, st>>>(Bsrc, ldb, rows_in, cols_in, b_transpose, hi, lo, Np, Kp);
+    CUtensorMap tmA, tmBhi, tmBlo;
+    int rc = make_map(&tmA, A, M, K, lda, TC_BLOCK_M);
+    if (rc == 0) rc = make_map(&tmBhi, hi, Np, Kp, Kp, block_n);
+    if (rc == 0) rc = make_map(&tmBlo, lo, Np, Kp, Kp, block_n);
+    if (rc == 0) {
+        const int b_bytes = block_n * TC_BLOCK_K * 4;
+        const int stage_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
+        uint32_t tmem_cols = 32;
+        while ((int)tmem_cols < block_n) tmem_cols <<= 1;
+        dim3 grid(ceil_div(M, TC_BLOCK_M), n_tiles);
+        auto launch = [&](auto stages_tag) -> int {
+            constexpr int S = decltype(stages_tag)::value;
+            const size_t smem = (size_t)S * stage_bytes + (3 * S + 2) * 8 + 1024;
+            cudaError_t ee = cudaFuncSetAttribute(gemm_tf32x3_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (ee != cudaSuccess) return (int)ee;
+            gemm_tf32x3_kernel<S><<<grid, TC_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, ep, block_n, nkb, tmem_cols);
+            return (int)cudaGetLastError();
+        };
+        // stage count from the shared-memory budget (~200 KiB usable)
+        const int max_stages = (200 * 1024) / stage_bytes;
+        if (max_stages >= 4) rc = launch(std::integral_constant<int, 4>{});
+        else if (max_stages >= 3) rc = launch(std::integral_constant<int, 3>{});
+        else if (max_stages >= 2) rc = launch(std::integral_constant<int, 2>{});
+        else rc = RPB_ERR_UNSUPPORTED;
+    }
+    cudaFreeAsync(ws, st);
+    return rc;
+}
+
+// SIMT implementations (linear_simt.cu)
+int linear_fwd_simt(const float* x, long long ldx, const float* W, const float* bias, float* y, long long ldy,
+                    int M, int N, int K, int act, cudaStream_t st);
+int linear_dx_simt(const float* dy, long long lddy, const float* W, const float* mask, long long ldmask,
+                   float* dx, long long lddx, int M, int N, int K, cudaStream_t st);
+int linear_dw_simt(const float* dy, long long lddy, const float* x, long long ldx, float* dW, float* db,
+                   int M, int N, int K, cudaStream_t st);
+
+}  // namespace rpb
+
+using namespace rpb;
+
+RPB_API int rpb_linear_fwd(const float* x, int64_t ldx, const float* W, const float* bias, float* y, int64_t ldy,
+                           int M, int N, int K, int act, int impl, void* stream) {
+    if (x == nullptr || W == nullptr || y == nullptr || M <= 0 || N <= 0 || K <= 0) return RPB_ERR_BAD_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool tc_ok = tc_shape_ok(x, ldx, M, N, K);
+    if (impl == 2 && !tc_ok) return RPB_ERR_UNSUPPORTED;
+    if (impl == 2 || (impl == 0 && tc_ok && M >= 512)) {
+        TcEpilogue ep{y, ldy, bias, nullptr, 0, M, N, act == 1};
+        return gemm_tc(x, ldx, W, K, 0, ep, M, N, K, st);
+    }
+    return linear_fwd_simt(x, ldx, W, bias, y, ldy, M, N, K, act, st);
+}
+
+RPB_API int rpb_linear_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* W,
+                           const float* mask, int64_t ldmask, float* dx, int64_t lddx, float* dW, float* db,
+                           int M, int N, int K, int impl, void* stream) {
+    if (dy == nullptr || M <= 0 || N <= 0 || K <= 0) return RPB_ERR_BAD_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (dx != nullptr) {
+        if (W == nullptr) return RPB_ERR_BAD_ARG;
+        // dx[M,K] = dy[M,N] @ W[N,K]: the GEMM's reduction dim is N, its output width is K, B operand = W^T [K, N]
+        const bool tc_ok = tc_shape_ok(dy, lddy, M, K, N);
+        if (impl == 2 && !tc_ok) return RPB_ERR_UNSUPPORTED;
+        int rc;
+        if (impl == 2 || (impl == 0 && tc_ok && M >= 512)) {
+            TcEpilogue ep{dx, lddx, nullptr, mask, ldmask, M, K, 0};
+            rc = gemm_tc(dy, lddy, W, K, 1, ep, M, K, N, st);
+        } else {
+            rc = linear_dx_simt(dy, lddy, W, mask, ldmask, dx, lddx, M, N, K, st);
+        }
+        if (rc != 0) return rc;
+    }
+    if (dW != nullptr) {
+        if (x == nullptr) return RPB_ERR_BAD_ARG;
+        const int rc = linear_dw_simt(dy, lddy, x, ldx, dW, db, M, N, K, st);
+        if (rc != 0) return rc;
+    }
+    return 0;
+}

@@ -1,0 +1,53 @@
+"""EmbeddingLayer — same constructor, parameters and state_dict keys as the reference
+(rec_pangu/models/layers/embedding.py:11-71), forward = ONE multi-table gather kernel (rpb_gather_fwd)."""
+from typing import Dict, Optional, Sequence
+
+import torch
+from torch import nn
+
+from ... import ops
+from ..utils import sparse_feature_names, dense_feature_names
+
+
+class EmbeddingLayer(nn.Module):
+    def __init__(self, enc_dict: Dict[str, dict], embedding_dim: int) -> None:
+        super().__init__()
+        self.enc_dict = enc_dict
+        self.embedding_dim = embedding_dim
+        # nn.Embedding modules are parameter containers only (state_dict key
+        # `embedding_layer.<col>.weight`, [vocab_size+1, D], embedding.py:31-34); their forward is never called.
+        self.embedding_layer = nn.ModuleDict()
+        self.emb_feature = []
+        for col in sparse_feature_names(enc_dict):
+            self.emb_feature.append(col)
+            self.embedding_layer.update({col: nn.Embedding(num_embeddings=enc_dict[col]['vocab_size'] + 1,
+                                                           embedding_dim=embedding_dim)})
+        self.dense_feature = dense_feature_names(enc_dict)
+
+    def set_weights(self, col_name: str, embedding_matrix: torch.Tensor, trainable: Optional[bool] = True) -> None:
+        """embedding.py:36-47."""
+        self.embedding_layer[col_name].weight = nn.Parameter(embedding_matrix)
+        if not trainable:
+            self.embedding_layer[col_name].weight.requires_grad = False
+
+    def tables(self):
+        return [self.embedding_layer[c].weight for c in self.emb_feature]
+
+    def feature_row(self, X: Dict[str, torch.Tensor], with_dense: bool = True, want_fm: bool = False,
+                    lr_tables: Optional[Sequence[torch.Tensor]] = None):
+        """Fused entry used by the model forwards: returns (x [B, ldx], fm [B] | None, lr_in | None) where
+        x = [emb_0 | ... | emb_{F-1} | dense_0..dense_{Nd-1} | 0-pad] (see include/rec_pangu_b200.h)."""
+        idx = [X[c] for c in self.emb_feature]
+        dense = [X[c] for c in self.dense_feature] if with_dense else []
+        return ops.gather(self.tables(), idx, dense, lr_tables=lr_tables, want_fm=want_fm)
+
+    def forward(self, X: Dict[str, torch.Tensor], name: Optional[str] = None) -> torch.Tensor:
+        """[B, F, D] (name=None) — embedding.py:58-63; a strided view of the feature row, no stack copy."""
+        if name is None:
+            x, _, _ = self.feature_row(X, with_dense=False)
+            F, D = len(self.emb_feature), self.embedding_dim
+            return x[:, :F * D].view(x.shape[0], F, D)
+        if 'seq' in name:
+            raise NotImplementedError('sequence-feature lookup belongs to the sequence-recall workload (out of scope)')
+        x, _, _ = ops.gather([self.embedding_layer[name].weight], [X[name]])
+        return x[:, :self.embedding_dim].view(x.shape[0], 1, self.embedding_dim)

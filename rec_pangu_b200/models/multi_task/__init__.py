@@ -1,0 +1,17 @@
+"""Multi-task models (reference: rec_pangu/models/multi_task/__init__.py).  MMOE is the north-star config 5."""
+from .mmoe import MMOE
+
+
+def _unported(name):
+    class _Unported:
+        def __init__(self, *args, **kwargs):
+            raise NotImplementedError(f'{name} is not part of the B200 hot-path scope yet (SURVEY.md §8f rank 4)')
+    _Unported.__name__ = name
+    return _Unported
+
+
+AITM = _unported('AITM')
+ESSM = _unported('ESSM')
+MLMMOE = _unported('MLMMOE')
+OMOE = _unported('OMOE')
+ShareBottom = _unported('ShareBottom')

@@ -1,0 +1,10 @@
+"""Ranking models with the reference's names and constructor signatures (rec_pangu/models/ranking/__init__.py)."""
+from .wdl import WDL
+from .deepfm import DeepFM
+from .nfm import NFM
+from .fibinet import FiBiNet
+from .autoint import AutoInt
+from .fm import FM
+from .xdeepfm import xDeepFM
+from .dcn import DCN
+from ._unported import AFM, AFN, AOANet, CCPM, LR, MaskNet

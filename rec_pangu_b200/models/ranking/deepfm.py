@@ -1,0 +1,28 @@
+"""DeepFM — reference: rec_pangu/models/ranking/deepfm.py:13-67."""
+from typing import Dict, List
+
+import torch
+
+from ..base_model import BaseModel
+from ..layers import FM_Layer, MLP
+from ..utils import get_dnn_input_dim
+
+
+class DeepFM(BaseModel):
+    def __init__(self, embedding_dim: int = 32, hidden_units: List[int] = [64, 64, 64],
+                 loss_fun: str = 'torch.nn.BCELoss()', enc_dict: Dict[str, dict] = None):
+        super().__init__(enc_dict, embedding_dim)
+        self.hidden_units = hidden_units
+        self.loss_fun = eval(loss_fun)
+        self.enc_dict = enc_dict
+        self.fm = FM_Layer()
+        self.dnn_input_dim = get_dnn_input_dim(self.enc_dict, self.embedding_dim)
+        self.dnn = MLP(input_dim=self.dnn_input_dim, output_dim=1, hidden_units=self.hidden_units,
+                       hidden_activations='relu', dropout_rates=0)
+        self.reset_parameters()
+
+    def forward(self, data, is_training=True):
+        # one launch: gather 26 rows/sample -> feature row x (= cat(emb.flatten, dense)) + FM second-order term
+        x, fm_out, _ = self.embedding_layer.feature_row(data, with_dense=True, want_fm=True)
+        dnn_output = self.dnn(x, K=self.dnn_input_dim)                  # [B,1]
+        return self._finish(fm_out.unsqueeze(1) + dnn_output, data, is_training)

@@ -1,0 +1,18 @@
+"""FM — reference: rec_pangu/models/ranking/fm.py."""
+from typing import Dict
+
+from ..base_model import BaseModel
+from ..layers import FM_Layer
+
+
+class FM(BaseModel):
+    def __init__(self, embedding_dim: int = 32, loss_fun: str = 'torch.nn.BCELoss()', enc_dict: Dict[str, dict] = None):
+        super().__init__(enc_dict, embedding_dim)
+        self.loss_fun = eval(loss_fun)
+        self.enc_dict = enc_dict
+        self.fm = FM_Layer()
+        self.reset_parameters()
+
+    def forward(self, data, is_training: bool = True):
+        _, fm_out, _ = self.embedding_layer.feature_row(data, with_dense=False, want_fm=True)
+        return self._finish(fm_out.unsqueeze(1), data, is_training)

@@ -1,0 +1,574 @@
+"""Autograd bindings of the sm_100a kernels (C ABI in include/rec_pangu_b200.h, loaded through ctypes).
+
+PyTorch is plumbing here: it owns device memory, the current stream and the autograd tape; every
+numerical step of the hot path is a kernel of librec_pangu_b200.so.  CUDA tensors only — there is no CPU
+fallback, and a missing library raises at first use.
+"""
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import GatherDesc, ScatterDesc, check
+
+__all__ = ['gather', 'fm_interaction', 'mlp_forward', 'sigmoid_bce', 'linear', 'feature_row_stride',
+           'check_index_errors', 'set_gemm_impl', 'get_gemm_impl', 'launch_count', 'reset_launch_count']
+
+_GEMM_IMPL = int(__import__('os').environ.get('RPB_GEMM_IMPL', '0'))   # 0 auto, 1 SIMT fp32, 2 tcgen05 3xTF32
+_LAUNCHES = 0           # number of librec_pangu_b200 kernels launched (bench.py reports it as gpu_launches)
+
+
+def set_gemm_impl(impl: int):
+    global _GEMM_IMPL
+    assert impl in (0, 1, 2)
+    _GEMM_IMPL = impl
+
+
+def get_gemm_impl() -> int:
+    return _GEMM_IMPL
+
+
+def launch_count() -> int:
+    return _LAUNCHES
+
+
+def reset_launch_count():
+    global _LAUNCHES
+    _LAUNCHES = 0
+
+
+def _count(n=1):
+    global _LAUNCHES
+    _LAUNCHES += n
+
+
+def _cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f'rec_pangu_b200: {what} must be a CUDA tensor — the hot path is hand-written sm_100a '
+                           f'CUDA and has no CPU fallback (got device {t.device})')
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _rowmajor(t: torch.Tensor) -> torch.Tensor:
+    """2-D tensor whose last dim is contiguous (row stride arbitrary)."""
+    if t.dim() != 2:
+        t = t.reshape(t.shape[0], -1)
+    if t.stride(1) != 1 or (t.shape[0] > 1 and t.stride(0) < t.shape[1]):
+        t = t.contiguous()
+    return t
+
+
+def feature_row_stride(F: int, D: int, Nd: int) -> int:
+    """Row stride (floats) of the feature-row buffer x: F*D+Nd rounded up to a multiple of 4 (16-byte rows)."""
+    return (F * D + Nd + 3) // 4 * 4
+
+
+# ------------------------------------------------------------------ index error record (pinned, device visible)
+_ERR = {}
+
+
+def _err_record(device) -> torch.Tensor:
+    key = torch.device(device).index or 0
+    if key not in _ERR:
+        _ERR[key] = torch.zeros(4, dtype=torch.int64).pin_memory()
+    return _ERR[key]
+
+
+def check_index_errors(device=None, sync: bool = True):
+    """Raise IndexError if any gather since the last check saw an index outside [0, vocab_size]
+    (the reference raises IndexError from aten::embedding on CPU, models/layers/embedding.py:61-62)."""
+    dev = torch.device(device if device is not None else torch.cuda.current_device())
+    if sync:
+        torch.cuda.synchronize(dev)
+    rec = _err_record(dev)
+    if int(rec[0]) != 0:
+        f, b, v = int(rec[1]), int(rec[2]), int(rec[3])
+        rec.zero_()
+        raise IndexError(f'index out of range in embedding gather: field #{f}, sample {b}, index {v}')
+
+
+# ------------------------------------------------------------------ gather
+class _Gather(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cfg, *tensors):
+        F, Nd, D = cfg['F'], cfg['Nd'], cfg['D']
+        has_lr, want_fm = cfg['has_lr'], cfg['want_fm']
+        tables = tensors[:F]
+        lr_tables = tensors[F:2 * F] if has_lr else ()
+        o = 2 * F if has_lr else F
+        idx = tensors[o:o + F]
+        dense = tensors[o + F:o + F + Nd]
+        dev = tables[0].device
+        B = idx[0].shape[0]
+        ldx = feature_row_stride(F, D, Nd)
+        x = torch.empty((B, ldx), dtype=torch.float32, device=dev)
+        need_grad = cfg['needs_grad']
+        fm = torch.empty((B,), dtype=torch.float32, device=dev) if want_fm else None
+        fm_s = torch.empty((B, D), dtype=torch.float32, device=dev) if (want_fm and need_grad) else None
+        ld_lr = (F + Nd + 3) // 4 * 4 if has_lr else 0
+        lr_in = torch.empty((B, ld_lr), dtype=torch.float32, device=dev) if has_lr else None
+        rows = [int(t.shape[0]) for t in tables]
+
+        d = GatherDesc()
+        d.B, d.F, d.D, d.Nd, d.ldx, d.ld_lr = B, F, D, Nd, ldx, ld_lr
+        t_arr = (C.c_void_p * F)(*[t.data_ptr() for t in tables])
+        r_arr = (C.c_int64 * F)(*rows)
+        i_arr = (C.c_void_p * F)(*[t.data_ptr() for t in idx])
+        d.tables, d.rows, d.idx = t_arr, r_arr, i_arr
+        if Nd:
+            d_arr = (C.c_void_p * Nd)(*[t.data_ptr() for t in dense])
+            d.dense = d_arr
+        if has_lr:
+            l_arr = (C.c_void_p * F)(*[t.data_ptr() for t in lr_tables])
+            d.lr_tables = l_arr
+        d.x, d.fm, d.fm_s, d.lr_in = x.data_ptr(), _ptr(fm), _ptr(fm_s), _ptr(lr_in)
+        d.err = _err_record(dev).data_ptr()
+        check(_lib.load().rpb_gather_fwd(C.byref(d), _stream()), 'rpb_gather_fwd')
+        _count()
+
+        ctx.set_materialize_grads(False)
+        ctx.cfg = cfg
+        ctx.rows = rows
+        ctx.n_in = len(tensors)
+        ctx.save_for_backward(x, fm_s, *idx)
+        outs = [x]
+        if want_fm:
+            outs.append(fm)
+        if has_lr:
+            outs.append(lr_in)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        cfg = ctx.cfg
+        F, Nd, D = cfg['F'], cfg['Nd'], cfg['D']
+        has_lr, want_fm = cfg['has_lr'], cfg['want_fm']
+        x, fm_s, *idx = ctx.saved_tensors
+        gx = gouts[0]
+        k = 1
+        gfm = None
+        glr = None
+        if want_fm:
+            gfm = gouts[k]
+            k += 1
+        if has_lr:
+            glr = gouts[k]
+        B = x.shape[0]
+        dev = x.device
+        tbl_req = ctx.needs_input_grad[1:1 + F]
+        lr_req = ctx.needs_input_grad[1 + F:1 + 2 * F] if has_lr else ()
+
+        grads: List[Optional[torch.Tensor]] = [None] * ctx.n_in
+        g_tables = [torch.zeros((ctx.rows[f], D), dtype=torch.float32, device=dev) if tbl_req[f] else None
+                    for f in range(F)]
+        g_lr = [torch.zeros((ctx.rows[f], 1), dtype=torch.float32, device=dev) if (has_lr and lr_req[f]) else None
+                for f in range(F)]
+        have_any = (gx is not None or gfm is not None) and any(g is not None for g in g_tables)
+        have_lr = glr is not None and any(g is not None for g in g_lr)
+        if have_any or have_lr:
+            d = ScatterDesc()
+            d.B, d.F, d.D = B, F, D
+            if gx is not None:
+                gx = _rowmajor(gx)
+                d.dx, d.lddx = gx.data_ptr(), gx.stride(0)
+            if gfm is not None:
+                gfm = gfm.contiguous()
+                d.dfm, d.x, d.ldx, d.fm_s = gfm.data_ptr(), x.data_ptr(), x.stride(0), fm_s.data_ptr()
+            g_arr = (C.c_void_p * F)(*[g.data_ptr() if g is not None else 0 for g in g_tables])
+            d.grads = g_arr
+            if have_lr:
+                glr = _rowmajor(glr)
+                gl_arr = (C.c_void_p * F)(*[g.data_ptr() if g is not None else 0 for g in g_lr])
+                d.lr_grads, d.dlr_in, d.ld_dlr = gl_arr, glr.data_ptr(), glr.stride(0)
+            r_arr = (C.c_int64 * F)(*ctx.rows)
+            i_arr = (C.c_void_p * F)(*[t.data_ptr() for t in idx])
+            d.rows, d.idx = r_arr, i_arr
+            check(_lib.load().rpb_gather_bwd(C.byref(d), _stream()), 'rpb_gather_bwd')
+            _count()
+        for f in range(F):
+            grads[f] = g_tables[f]
+            if has_lr:
+                grads[F + f] = g_lr[f]
+        return (None, *grads)
+
+
+def gather(tables: Sequence[torch.Tensor], idx: Sequence[torch.Tensor], dense: Sequence[torch.Tensor] = (),
+           lr_tables: Optional[Sequence[torch.Tensor]] = None, want_fm: bool = False):
+    """One-launch multi-table gather.  Returns (x [B, ldx], fm [B] | None, lr_in [B, ld_lr] | None).
+
+    ``x[:, :F*D].view(B, F, D)`` is the reference's ``EmbeddingLayer.forward`` output
+    (models/layers/embedding.py:49-63); ``x[:, :F*D+Nd]`` is ``cat(emb.flatten(1), get_linear_input(...))``.
+    """
+    F = len(tables)
+    if F == 0:
+        raise ValueError('gather needs at least one sparse field')
+    if F > _lib.MAX_FIELDS or len(dense) > _lib.MAX_DENSE:
+        raise NotImplementedError(f'more than {_lib.MAX_FIELDS} sparse or {_lib.MAX_DENSE} dense fields per gather')
+    D = int(tables[0].shape[1])
+    for t in tables:
+        _cuda(t, 'embedding table')
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.shape[1] != D:
+            raise ValueError('embedding tables must be contiguous fp32 [rows, D] with one common D')
+    idx_l = []
+    for t in idx:
+        _cuda(t, 'sparse feature column')
+        t = t.reshape(-1)
+        if t.dtype != torch.int64:          # embedding.py:61: X[col].long()
+            t = t.long()
+        idx_l.append(t.contiguous())
+    B = idx_l[0].shape[0]
+    dense_l = []
+    for t in dense:
+        _cuda(t, 'dense feature column')
+        t = t.reshape(-1)
+        if t.dtype != torch.float32:
+            t = t.float()
+        if t.shape[0] != B:
+            raise ValueError('dense column batch size mismatch')
+        dense_l.append(t.contiguous())
+    has_lr = lr_tables is not None
+    if has_lr:
+        lr_tables = [t if t.is_contiguous() else t.contiguous() for t in lr_tables]
+    needs_grad = torch.is_grad_enabled() and (any(t.requires_grad for t in tables) or
+                                              (has_lr and any(t.requires_grad for t in lr_tables)))
+    cfg = dict(F=F, Nd=len(dense_l), D=D, has_lr=has_lr, want_fm=want_fm, needs_grad=needs_grad)
+    args = list(tables) + (list(lr_tables) if has_lr else []) + idx_l + dense_l
+    outs = _Gather.apply(cfg, *args)
+    x = outs[0]
+    k = 1
+    fm = None
+    lr_in = None
+    if want_fm:
+        fm = outs[k]
+        k += 1
+    if has_lr:
+        lr_in = outs[k]
+    return x, fm, lr_in
+
+
+# ------------------------------------------------------------------ standalone FM on [B,F,D]
+class _FM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, e, mode):
+        B, F, D = e.shape
+        if e.stride(2) != 1 or e.stride(1) != D:
+            e = e.contiguous()
+        out_sum = torch.empty((B, 1), dtype=torch.float32, device=e.device) if mode == 'sum' else None
+        out_bi = torch.empty((B, D), dtype=torch.float32, device=e.device) if mode == 'bi' else None
+        check(_lib.load().rpb_fm_fwd(_ptr(e), e.stride(0), B, F, D, _ptr(out_sum), _ptr(out_bi), _stream()), 'rpb_fm_fwd')
+        _count()
+        ctx.save_for_backward(e)
+        ctx.mode = mode
+        return out_sum if mode == 'sum' else out_bi
+
+    @staticmethod
+    def backward(ctx, g):
+        (e,) = ctx.saved_tensors
+        B, F, D = e.shape
+        g = g.contiguous()
+        de = torch.empty((B, F, D), dtype=torch.float32, device=e.device)
+        dsum = g if ctx.mode == 'sum' else None
+        dbi = g if ctx.mode == 'bi' else None
+        check(_lib.load().rpb_fm_bwd(_ptr(e), e.stride(0), B, F, D, _ptr(dsum), _ptr(dbi), _ptr(de), F * D, 0,
+                                     _stream()), 'rpb_fm_bwd')
+        _count()
+        return de, None
+
+
+def fm_interaction(e: torch.Tensor, mode: str = 'sum') -> torch.Tensor:
+    """InnerProductLayer product_sum_pooling ('sum' -> [B,1]) / Bi_interaction_pooling ('bi' -> [B,D])."""
+    _cuda(e, 'feature_emb')
+    return _FM.apply(e.float(), mode)
+
+
+# ------------------------------------------------------------------ MLP tower
+class _MLP(torch.autograd.Function):
+    """Linear(+ReLU)(+Dropout) x n_hidden [+ Linear(out)] as one autograd node so ReLU backward is fused into
+    the producing GEMM's epilogue (mask = saved activation)."""
+
+    @staticmethod
+    def forward(ctx, cfg, x, *params):
+        n_hidden, has_out, K = cfg['n_hidden'], cfg['has_out'], cfg['K']
+        relu, drops, training, impl = cfg['relu'], cfg['dropout'], cfg['training'], cfg['impl']
+        lib = _lib.load()
+        st = _stream()
+        M = x.shape[0]
+        acts = []          # saved layer inputs: acts[i] = input of hidden layer i (post-ReLU/post-dropout of i-1)
+        pre_drop = []      # pre-dropout ReLU outputs for layers with active dropout (else None)
+        seeds = []
+        h, ldh, kdim = x, x.stride(0), K
+        for i in range(n_hidden):
+            W, b = params[2 * i], params[2 * i + 1]
+            N = W.shape[0]
+            y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+            check(lib.rpb_linear_fwd(_ptr(h), ldh, _ptr(W), _ptr(b), _ptr(y), N, M, N, kdim, 1 if relu[i] else 0,
+                                     impl, st), 'rpb_linear_fwd')
+            _count(2 if impl != 1 else 1)
+            acts.append(h)
+            p = drops[i] if training else 0.0
+            if p > 0.0:
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+                yd = torch.empty_like(y)
+                check(lib.rpb_dropout_fwd(_ptr(y), _ptr(yd), y.numel(), p, seed, st), 'rpb_dropout_fwd')
+                _count()
+                pre_drop.append(y)
+                seeds.append(seed)
+                y = yd
+            else:
+                pre_drop.append(None)
+                seeds.append(0)
+            h, ldh, kdim = y, N, N
+        out = h
+        if has_out:
+            W, b = params[2 * n_hidden], params[2 * n_hidden + 1]
+            N = W.shape[0]
+            out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+            if N == 1:
+                check(lib.rpb_rowdot_fwd(_ptr(h), ldh, _ptr(W), _ptr(b), None, None, None, _ptr(out), M, kdim, st),
+                      'rpb_rowdot_fwd')
+                _count()
+            else:
+                check(lib.rpb_linear_fwd(_ptr(h), ldh, _ptr(W), _ptr(b), _ptr(out), N, M, N, kdim, 0, impl, st),
+                      'rpb_linear_fwd')
+                _count(2 if impl != 1 else 1)
+            acts.append(h)
+        ctx.cfg = cfg
+        ctx.seeds = seeds
+        ctx.n_saved_acts = len(acts)
+        ctx.save_for_backward(*acts, *[t if t is not None else x.new_empty(0) for t in pre_drop], *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        cfg = ctx.cfg
+        n_hidden, has_out, K = cfg['n_hidden'], cfg['has_out'], cfg['K']
+        relu, drops, training, impl = cfg['relu'], cfg['dropout'], cfg['training'], cfg['impl']
+        saved = ctx.saved_tensors
+        na = ctx.n_saved_acts
+        acts = saved[:na]
+        pre_drop = saved[na:na + n_hidden]
+        params = saved[na + n_hidden:]
+        lib = _lib.load()
+        st = _stream()
+        M = acts[0].shape[0]
+        dev = acts[0].device
+        g = _rowmajor(g)
+        gparams: List[Optional[torch.Tensor]] = [None] * len(params)
+        need_dx_input = ctx.needs_input_grad[1]
+
+        def mask_for(layer_in_idx):
+            """Activation mask to fuse when producing the grad of acts[layer_in_idx] (= output of hidden layer-1)."""
+            j = layer_in_idx - 1          # hidden layer that produced this activation
+            if j < 0:
+                return None, False
+            p = drops[j] if training else 0.0
+            if p > 0.0:
+                return None, True         # dropout active: unfused elementwise backward handles ReLU+dropout
+            return (acts[layer_in_idx] if relu[j] else None), False
+
+        def finish_drop(dh, j):
+            """dh = grad wrt dropped output of hidden layer j -> grad wrt its pre-activation."""
+            p = drops[j]
+            out = torch.empty_like(dh)
+            check(lib.rpb_dropout_bwd(_ptr(dh), _ptr(pre_drop[j]) if relu[j] else None, _ptr(out), dh.numel(), p,
+                                      ctx.seeds[j], st), 'rpb_dropout_bwd')
+            _count()
+            return out
+
+        # output layer (always present: the reference only builds MLPs with output_dim=1 on this path)
+        W, b = params[2 * n_hidden], params[2 * n_hidden + 1]
+        N = W.shape[0]
+        hin = acts[n_hidden]
+        kdim = W.shape[1]
+        mask, dropped = mask_for(n_hidden)
+        dx = torch.empty((M, kdim), dtype=torch.float32, device=dev)
+        dW = torch.zeros_like(W)
+        db = torch.zeros_like(b)
+        if N == 1:
+            gcol = g.reshape(-1) if g.stride(0) == 1 else g[:, 0].contiguous()
+            check(lib.rpb_rowdot_bwd(_ptr(gcol), _ptr(hin), hin.stride(0), _ptr(W), _ptr(mask),
+                                     mask.stride(0) if mask is not None else 0, _ptr(dx), dx.stride(0),
+                                     _ptr(dW), _ptr(db), M, kdim, st), 'rpb_rowdot_bwd')
+            _count(2)
+        else:
+            check(lib.rpb_linear_bwd(_ptr(g), g.stride(0), _ptr(hin), hin.stride(0), _ptr(W), _ptr(mask),
+                                     mask.stride(0) if mask is not None else 0, _ptr(dx), dx.stride(0),
+                                     _ptr(dW), _ptr(db), M, N, kdim, impl, st), 'rpb_linear_bwd')
+            _count(3)
+        gparams[2 * n_hidden], gparams[2 * n_hidden + 1] = dW, db
+        dh = dx
+        lddh = dx.stride(0)
+        if dropped:
+            dh = finish_drop(dh, n_hidden - 1)
+
+        for i in range(n_hidden - 1, -1, -1):
+            W, b = params[2 * i], params[2 * i + 1]
+            N, kdim = W.shape[0], (K if i == 0 else W.shape[1])
+            hin = acts[i]
+            need_dx = i > 0 or need_dx_input
+            mask, dropped = mask_for(i)
+            if need_dx:
+                if i == 0:
+                    dx = torch.empty((M, hin.stride(0)), dtype=torch.float32, device=dev)
+                    if hin.stride(0) > kdim:
+                        dx[:, kdim:].zero_()
+                else:
+                    dx = torch.empty((M, kdim), dtype=torch.float32, device=dev)
+            else:
+                dx = None
+            dW = torch.zeros_like(W)
+            db = torch.zeros_like(b) if b is not None else None
+            check(lib.rpb_linear_bwd(_ptr(dh), lddh, _ptr(hin), hin.stride(0), _ptr(W), _ptr(mask),
+                                     mask.stride(0) if mask is not None else 0, _ptr(dx),
+                                     dx.stride(0) if dx is not None else 0, _ptr(dW), _ptr(db), M, N, kdim, impl, st),
+                  'rpb_linear_bwd')
+            _count(3)
+            gparams[2 * i], gparams[2 * i + 1] = dW, db
+            dh = dx
+            lddh = dx.stride(0) if dx is not None else 0
+            if dropped and dh is not None:
+                dh = finish_drop(dh, i - 1)
+        gx = None
+        if need_dx_input and dh is not None:
+            gx = dh if dh.shape[1] == acts[0].shape[1] else dh[:, :acts[0].shape[1]]
+        return (None, gx, *gparams)
+
+
+def mlp_forward(x: torch.Tensor, K: int, weights: Sequence[torch.Tensor], biases: Sequence[Optional[torch.Tensor]],
+                n_hidden: int, has_out: bool, relu: Sequence[bool], dropout: Sequence[float], training: bool,
+                impl: Optional[int] = None) -> torch.Tensor:
+    """MLP.forward (models/layers/deep.py:74-84) on x[:, :K] (x may be a wider, padded feature-row buffer)."""
+    _cuda(x, 'MLP input')
+    x = _rowmajor(x.float() if x.dtype != torch.float32 else x)
+    params = []
+    for W, b in zip(weights, biases):
+        if b is None:
+            raise NotImplementedError('use_bias=False MLP layers')
+        params += [W if W.is_contiguous() else W.contiguous(), b]
+    cfg = dict(n_hidden=n_hidden, has_out=has_out, K=K, relu=list(relu), dropout=list(dropout), training=training,
+               impl=_GEMM_IMPL if impl is None else impl)
+    if not has_out or n_hidden < 1:
+        raise NotImplementedError('MLP needs >= 1 hidden layer and an output layer (deep.py:40-41)')
+    return _MLP.apply(cfg, x, *params)
+
+
+# ------------------------------------------------------------------ single Linear (autograd)
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, K, W, b, impl):
+        M, N = x.shape[0], W.shape[0]
+        y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        lib = _lib.load()
+        if N == 1:
+            check(lib.rpb_rowdot_fwd(_ptr(x), x.stride(0), _ptr(W), _ptr(b), None, None, None, _ptr(y), M, K, _stream()),
+                  'rpb_rowdot_fwd')
+            _count()
+        else:
+            check(lib.rpb_linear_fwd(_ptr(x), x.stride(0), _ptr(W), _ptr(b), _ptr(y), N, M, N, K, 0, impl, _stream()),
+                  'rpb_linear_fwd')
+            _count(2 if impl != 1 else 1)
+        ctx.save_for_backward(x, W)
+        ctx.K, ctx.impl, ctx.has_b = K, impl, b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, W = ctx.saved_tensors
+        K, impl = ctx.K, ctx.impl
+        M, N = x.shape[0], W.shape[0]
+        g = _rowmajor(g)
+        lib = _lib.load()
+        need_dx = ctx.needs_input_grad[0]
+        dx = None
+        if need_dx:
+            dx = torch.empty((M, x.shape[1]), dtype=torch.float32, device=x.device)
+            if x.shape[1] > K:
+                dx[:, K:].zero_()
+        dW = torch.zeros_like(W)
+        db = torch.zeros((N,), dtype=torch.float32, device=x.device) if ctx.has_b else None
+        if N == 1:
+            gcol = g.reshape(-1) if g.stride(0) == 1 else g[:, 0].contiguous()
+            check(lib.rpb_rowdot_bwd(_ptr(gcol), _ptr(x), x.stride(0), _ptr(W), None, 0, _ptr(dx),
+                                     dx.stride(0) if dx is not None else 0, _ptr(dW), _ptr(db), M, K, _stream()),
+                  'rpb_rowdot_bwd')
+            _count(2)
+        else:
+            check(lib.rpb_linear_bwd(_ptr(g), g.stride(0), _ptr(x), x.stride(0), _ptr(W), None, 0, _ptr(dx),
+                                     dx.stride(0) if dx is not None else 0, _ptr(dW), _ptr(db), M, N, K, impl,
+                                     _stream()), 'rpb_linear_bwd')
+            _count(3)
+        return dx, None, dW, db, None
+
+
+def linear(x: torch.Tensor, W: torch.Tensor, b: Optional[torch.Tensor], K: Optional[int] = None,
+           impl: Optional[int] = None) -> torch.Tensor:
+    """nn.Linear on x[:, :K] (K defaults to W.shape[1])."""
+    _cuda(x, 'linear input')
+    x = _rowmajor(x.float() if x.dtype != torch.float32 else x)
+    K = W.shape[1] if K is None else K
+    return _Linear.apply(x, K, W if W.is_contiguous() else W.contiguous(), b, _GEMM_IMPL if impl is None else impl)
+
+
+# ------------------------------------------------------------------ sigmoid + BCE head
+_WORK = {}
+
+
+def _head_work(dev) -> torch.Tensor:
+    key = torch.device(dev).index or 0
+    if key not in _WORK:
+        _WORK[key] = torch.zeros(2 + 1024 * 2, dtype=torch.int32, device=dev)
+    return _WORK[key]
+
+
+class _SigmoidBCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logit, label, eps, scale):
+        M = logit.numel()
+        z = logit.reshape(-1).contiguous()
+        pred = torch.empty((M,), dtype=torch.float32, device=logit.device)
+        loss = torch.empty((), dtype=torch.float32, device=logit.device) if label is not None else None
+        lab = label.reshape(-1).contiguous().float() if label is not None else None
+        check(_lib.load().rpb_sigmoid_bce_fwd(_ptr(z), _ptr(lab), _ptr(pred), _ptr(loss), eps, scale, M,
+                                              _ptr(_head_work(logit.device)), _stream()), 'rpb_sigmoid_bce_fwd')
+        _count()
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(pred, lab if lab is not None else pred.new_empty(0))
+        ctx.eps, ctx.scale, ctx.shape, ctx.has_label = eps, scale, logit.shape, label is not None
+        pred_out = pred.view(logit.shape)
+        if label is None:
+            return pred_out
+        return pred_out, loss
+
+    @staticmethod
+    def backward(ctx, gpred, gloss=None):
+        pred, lab = ctx.saved_tensors
+        M = pred.numel()
+        dlogit = None
+        if ctx.has_label and gloss is not None:
+            dlogit = torch.empty((M,), dtype=torch.float32, device=pred.device)
+            gl = gloss.reshape(1).contiguous().float()
+            check(_lib.load().rpb_sigmoid_bce_bwd(_ptr(pred), _ptr(lab), _ptr(gl), ctx.eps, ctx.scale, _ptr(dlogit), M,
+                                                  _stream()), 'rpb_sigmoid_bce_bwd')
+            _count()
+        if gpred is not None and ctx.needs_input_grad[0]:
+            # someone consumed `pred` directly: sigmoid backward (rare; plain elementwise plumbing)
+            extra = gpred.reshape(-1) * pred * (1.0 - pred)
+            dlogit = extra if dlogit is None else dlogit + extra
+        return (dlogit.view(ctx.shape) if dlogit is not None else None), None, None, None
+
+
+def sigmoid_bce(logit: torch.Tensor, label: Optional[torch.Tensor], eps: float = 0.0, scale: float = 1.0):
+    """pred = sigmoid(logit); loss = scale * mean BCE(pred + eps, label) (torch.nn.BCELoss semantics)."""
+    _cuda(logit, 'logit')
+    if label is None:
+        return _SigmoidBCE.apply(logit, None, eps, scale), None
+    _cuda(label, 'label')
+    return _SigmoidBCE.apply(logit, label, eps, scale)

@@ -1,0 +1,28 @@
+"""tcgen05 / TMEM / TMA dense layer (3xTF32) against float64 and against the fp32 SIMT kernel.
+Named zz so that it runs after every other GPU test file."""
+import pytest
+import torch
+
+from test_kernels_gpu import _check_linear
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('M,N,K,relu', [(128, 64, 32, False), (128, 64, 64, False), (1000, 64, 429, True),
+                                        (4096, 64, 429, True), (257, 64, 64, True), (300, 33, 70, False),
+                                        (512, 390, 100, False), (2048, 256, 512, False), (640, 429, 64, False)])
+def test_linear_tcgen05_forward_backward(M, N, K, relu):
+    _check_linear(M, N, K, relu, impl=2, tol=1e-5)
+
+
+def test_tcgen05_matches_simt_on_deepfm_layer1_shape():
+    from rec_pangu_b200 import ops
+    torch.manual_seed(0)
+    M, N, K = 65536, 64, 429
+    x = torch.zeros(M, 432, device='cuda')
+    x[:, :K] = torch.randn(M, K, device='cuda') * 0.35
+    W = torch.randn(N, K, device='cuda') * (2.0 / K) ** 0.5
+    b = torch.randn(N, device='cuda') * 0.1
+    y1 = ops.linear(x, W, b, K=K, impl=1)
+    y2 = ops.linear(x, W, b, K=K, impl=2)
+    assert (y1 - y2).abs().max().item() < 2e-5

@@ -1,0 +1,162 @@
+"""Kernel micro-benchmarks at BASELINE.json config-2 shape (run on the GPU box; CUDA events, cold-ish L2:
+inputs are rotated over several distinct batches and the tables (1.66 GB) exceed L2)."""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from rec_pangu_b200 import ops
+
+
+def timeit(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    evs = []
+    for i in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn(i) if fn.__code__.co_argcount else fn()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in evs)
+    return ts[len(ts) // 2] * 1e3      # us median
+
+
+def main():
+    B, F, Nd, D, V = 65536, 26, 13, 16, 1_000_000
+    dev = 'cuda'
+    res = {}
+    torch.manual_seed(0)
+    tables = [torch.randn(V + 1, D, device=dev) * 0.35 for _ in range(F)]
+    lrt = [torch.randn(V + 1, 1, device=dev) for _ in range(F)]
+    NB = 4
+    idxs = [[torch.randint(0, V + 1, (B,), device=dev) for _ in range(F)] for _ in range(NB)]
+    dense = [[torch.rand(B, device=dev) for _ in range(Nd)] for _ in range(NB)]
+    cnt = [0]
+
+    def g_plain():
+        i = cnt[0] % NB; cnt[0] += 1
+        return ops.gather(tables, idxs[i], dense[i])
+
+    def g_fm():
+        i = cnt[0] % NB; cnt[0] += 1
+        return ops.gather(tables, idxs[i], dense[i], want_fm=True)
+
+    def g_lr():
+        i = cnt[0] % NB; cnt[0] += 1
+        return ops.gather(tables, idxs[i], dense[i], lr_tables=lrt, want_fm=True)
+
+    with torch.no_grad():
+        for name, fn in (('gather', g_plain), ('gather_fm', g_fm), ('gather_fm_lr', g_lr)):
+            t = timeit(fn)
+            alg = B * (F * (8 + 4 * D) + 4 * Nd + 4)
+            res[name] = {'us': t, 'alg_GBs': alg / t / 1e3, 'copy_GBs': B * (F * (8 + 8 * D) + 8 * Nd) / t / 1e3}
+    # host-side overhead of one gather call
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for _ in range(200):
+            g_fm()
+    torch.cuda.synchronize()
+    res['gather_fm_wall_us_per_call'] = (time.perf_counter() - t0) / 200 * 1e6
+
+    # scatter (dense-grad mode): time only the kernel by reusing pre-zeroed grads
+    x, fm, _ = ops.gather(tables, idxs[0], dense[0], want_fm=True)
+    import ctypes as C
+    from rec_pangu_b200 import _lib
+    lib = _lib.load()
+    grads = [torch.zeros_like(t) for t in tables]
+    dx = torch.randn_like(x)
+    dfm = torch.randn(B, device=dev)
+    fm_s = torch.randn(B, D, device=dev)
+
+    def scatter(i=0):
+        d = _lib.ScatterDesc()
+        d.B, d.F, d.D = B, F, D
+        d.dx, d.lddx = dx.data_ptr(), dx.stride(0)
+        d.dfm, d.x, d.ldx, d.fm_s = dfm.data_ptr(), x.data_ptr(), x.stride(0), fm_s.data_ptr()
+        ga = (C.c_void_p * F)(*[g.data_ptr() for g in grads])
+        ra = (C.c_int64 * F)(*[V + 1] * F)
+        ia = (C.c_void_p * F)(*[t.data_ptr() for t in idxs[i % NB]])
+        d.grads, d.rows, d.idx = ga, ra, ia
+        _lib.check(lib.rpb_gather_bwd(C.byref(d), C.c_void_p(torch.cuda.current_stream().cuda_stream)), 'bwd')
+    t = timeit(scatter)
+    res['scatter_fm'] = {'us': t, 'alg_GBs': B * F * (8 + 4 * D + 4 * D + 8 * D) / t / 1e3}
+    t = timeit(lambda: [g.zero_() for g in grads], iters=5)
+    res['zero_dense_grads_us'] = t
+    del grads
+
+    # dense layers
+    K = F * D + Nd
+    W1 = torch.randn(64, K, device=dev) * (2 / K) ** 0.5
+    b1 = torch.zeros(64, device=dev)
+    W2 = torch.randn(64, 64, device=dev) * 0.17
+    h = torch.randn(B, 64, device=dev)
+    dy = torch.randn(B, 64, device=dev)
+    y = torch.empty(B, 64, device=dev)
+    dxb = torch.empty_like(x)
+    dW = torch.zeros_like(W1)
+    db = torch.zeros(64, device=dev)
+    st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    P = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    for impl, nm in ((1, 'simt'), (2, 'tc')):
+        try:
+            t = timeit(lambda: _lib.check(lib.rpb_linear_fwd(P(x), x.stride(0), P(W1), P(b1), P(y), 64, B, 64, K, 1, impl, st()), 'f'))
+            res[f'linear1_fwd_{nm}'] = {'us': t, 'TFLOPs': 2 * B * 64 * K / t / 1e6}
+            t = timeit(lambda: _lib.check(lib.rpb_linear_fwd(P(h), 64, P(W2), P(b1), P(y), 64, B, 64, 64, 1, impl, st()), 'f'))
+            res[f'linear2_fwd_{nm}'] = {'us': t, 'TFLOPs': 2 * B * 64 * 64 / t / 1e6}
+            t = timeit(lambda: _lib.check(lib.rpb_linear_bwd(P(dy), 64, P(x), x.stride(0), P(W1), None, 0, P(dxb), dxb.stride(0), None, None, B, 64, K, impl, st()), 'b'))
+            res[f'linear1_dx_{nm}'] = {'us': t, 'TFLOPs': 2 * B * 64 * K / t / 1e6}
+        except Exception as e:  # noqa
+            res[f'linear_{nm}_error'] = repr(e)
+            break
+    t = timeit(lambda: _lib.check(lib.rpb_linear_bwd(P(dy), 64, P(x), x.stride(0), P(W1), None, 0, None, 0, P(dW), P(db), B, 64, K, 1, st()), 'b'))
+    res['linear1_dw_simt'] = {'us': t, 'TFLOPs': 2 * B * 64 * K / t / 1e6}
+
+    # whole DeepFM fwd / fwd+bwd through the public model API
+    from rec_pangu_b200.models.ranking import DeepFM
+    enc = {f'I{i + 1}': {'min': 0.0, 'max': 1.0} for i in range(Nd)}
+    enc.update({f'C{i + 1}': {'vocab_size': V} for i in range(F)})
+    del tables, lrt
+    torch.cuda.empty_cache()
+    model = DeepFM.__new__(DeepFM)
+    # fast init: skip kaiming over 416M params on the host; init on device
+    torch.nn.Module.__init__(model)
+    with torch.device('cuda'):
+        model = DeepFM(embedding_dim=D, enc_dict=enc)
+    batches = []
+    for i in range(NB):
+        d = {f'C{j + 1}': idxs[i][j] for j in range(F)}
+        d.update({f'I{j + 1}': dense[i][j] for j in range(Nd)})
+        d['label'] = (torch.rand(B, device=dev) < 0.25).float()
+        batches.append(d)
+    for impl, nm in ((1, 'simt'), (2, 'tc')):
+        if f'linear_{nm}_error' in res or 'linear_tc_error' in res and nm == 'tc':
+            continue
+        ops.set_gemm_impl(impl)
+        model.eval()
+
+        def fwd():
+            i = cnt[0] % NB; cnt[0] += 1
+            with torch.no_grad():
+                return model(batches[i], is_training=False)
+        res[f'deepfm_fwd_{nm}_us'] = timeit(fwd)
+        model.train()
+
+        def fwdbwd():
+            i = cnt[0] % NB; cnt[0] += 1
+            out = model(batches[i])
+            out['loss'].backward()
+            model.zero_grad(set_to_none=True)
+        res[f'deepfm_fwdbwd_densegrad_{nm}_us'] = timeit(fwdbwd, iters=8)
+    print(json.dumps(res, indent=1))
+    os.makedirs('gpurun_out', exist_ok=True)
+    json.dump(res, open('gpurun_out/microbench.json', 'w'), indent=1)
+
+
+if __name__ == '__main__':
+    main()
