@@ -131,6 +131,41 @@ int rpb_dropout_fwd(const float* x, float* y, int64_t n, float p, uint64_t seed,
 int rpb_dropout_bwd(const float* dy, const float* relu_out, float* dx, int64_t n, float p, uint64_t seed,
                     void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * DCN CrossNet, all L (<= 8) layers in one kernel (models/layers/interaction.py:119-141):
+ *   x_{l+1} = x_l + (w_l . x_l) x_0 + b_l.   x0: [B, ldx] (K valid columns), out: [B, ldo] (columns >= K zeroed),
+ * w/bias: host arrays of L device pointers float[K] (CrossInteractionLayer.weight.weight / .bias),
+ * S: [B, L] out, s_l = w_l . x_l saved for backward (may be NULL for inference).  K <= 1024.
+ * bwd: dx0 [B, lddx] may be NULL; dw[l] / db[l] (float[K], may be NULL) are accumulated into (+=). */
+int rpb_crossnet_fwd(const float* x0, int64_t ldx, int K, int L, const float* const* w, const float* const* bias,
+                     float* out, int64_t ldo, float* S, int B, void* stream);
+int rpb_crossnet_bwd(const float* x0, int64_t ldx, int K, int L, const float* const* w, const float* const* bias,
+                     const float* S, const float* dout, int64_t lddo, float* dx0, int64_t lddx,
+                     float* const* dw, float* const* db, int B, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * xDeepFM CIN (models/layers/interaction.py:144-171).  e: [B,F,D] with sample stride lde; units[L];
+ * W[k]: Conv1d weight float[U_k][F*M_k] (M_0 = F, M_k = U_{k-1}), bias[k]: float[U_k];
+ * pooled: [B, ldp] out, columns [sum_{j<k} U_j, +U_k) = sum_d X_{k+1}[b,:,d] (the tensor fed to cin.fc).
+ * Limits: F <= 32, U_k <= 32, L <= 8, D in {8,16,32}, all layers' weights must fit in shared memory.
+ * bwd: de[b,f,:] (+)= dL/dE (accumulate != 0 adds), dW[k]/db[k] are accumulated into (+=). */
+int rpb_cin_fwd(const float* e, int64_t lde, int B, int F, int D, int L, const int32_t* units,
+                const float* const* W, const float* const* bias, float* pooled, int64_t ldp, void* stream);
+int rpb_cin_bwd(const float* e, int64_t lde, int B, int F, int D, int L, const int32_t* units,
+                const float* const* W, const float* const* bias, const float* dpooled, int64_t lddp,
+                float* de, int64_t ldde, int accumulate, float* const* dW, float* const* db, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * AutoInt interacting-layer core (models/layers/attention.py:12-32,63-95) on projected inputs.
+ * qkvr: [B*F, ldq] = X @ [W_q;W_k;W_v;W_res]^T  (Q at column 0, K at H*d, V at 2H*d, R at 3H*d).  When the layer
+ * has no W_res (D == H*d) pass res = X [B*F, ldres] and only Q|K|V in qkvr.
+ * out: [B, F, H*d] = relu(attention(raw-view head regroup, no scale) + residual).   F <= 32, d in {4,8,16}.
+ * bwd: dqkvr [B*F, lddq] receives dQ|dK|dV|dR (dR = ReLU-masked dout, always written). */
+int rpb_autoint_attn_fwd(const float* qkvr, int64_t ldq, const float* res, int64_t ldres, float* out, int B, int F,
+                         int H, int d, void* stream);
+int rpb_autoint_attn_bwd(const float* qkvr, int64_t ldq, int has_res_proj, const float* out, const float* dout,
+                         float* dqkvr, int64_t lddq, int B, int F, int H, int d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,15 @@ SIGNATURES = {
     'rpb_sigmoid_bce_bwd': (C.c_int, [_vp, _vp, _vp, _f32, _f32, _vp, C.c_int, _vp]),
     'rpb_dropout_fwd': (C.c_int, [_vp, _vp, _i64, _f32, C.c_uint64, _vp]),
     'rpb_dropout_bwd': (C.c_int, [_vp, _vp, _vp, _i64, _f32, C.c_uint64, _vp]),
+    'rpb_crossnet_fwd': (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(_vp), _vp, _i64, _vp, C.c_int, _vp]),
+    'rpb_crossnet_bwd': (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(_vp), _vp, _vp, _i64, _vp, _i64,
+                                   C.POINTER(_vp), C.POINTER(_vp), C.c_int, _vp]),
+    'rpb_cin_fwd': (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_i32), C.POINTER(_vp),
+                              C.POINTER(_vp), _vp, _i64, _vp]),
+    'rpb_cin_bwd': (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_i32), C.POINTER(_vp),
+                              C.POINTER(_vp), _vp, _i64, _vp, _i64, C.c_int, C.POINTER(_vp), C.POINTER(_vp), _vp]),
+    'rpb_autoint_attn_fwd': (C.c_int, [_vp, _i64, _vp, _i64, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    'rpb_autoint_attn_bwd': (C.c_int, [_vp, _i64, C.c_int, _vp, _vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
 }
 
 _lib = None

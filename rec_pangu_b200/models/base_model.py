@@ -53,6 +53,7 @@ class BaseModel(nn.Module):
     def _finish(self, logit, data, is_training):
         from .. import ops
         loss_fun = getattr(self, 'loss_fun', None)
+        self._last_logit = logit.detach()      # parity hook: the reference API only returns post-sigmoid `pred`
         fused = isinstance(loss_fun, torch.nn.BCELoss) and loss_fun.reduction == 'mean' and loss_fun.weight is None
         if is_training and fused:
             pred, loss = ops.sigmoid_bce(logit, data['label'])

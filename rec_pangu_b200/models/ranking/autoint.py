@@ -1,4 +1,5 @@
 """AutoInt — reference: rec_pangu/models/ranking/autoint.py:14-88."""
+import torch  # noqa: F401  (loss_fun strings such as "torch.nn.BCELoss()" are eval-ed here, as in the reference)
 from typing import Dict, List
 
 from torch import nn

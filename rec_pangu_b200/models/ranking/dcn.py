@@ -1,5 +1,6 @@
 """DCN — reference: rec_pangu/models/ranking/dcn.py:14-68 (cross network over [emb | dense], then fc; the
 reference builds no deep tower despite the hidden_units kwarg — SURVEY.md App. A-7)."""
+import torch  # noqa: F401  (loss_fun strings such as "torch.nn.BCELoss()" are eval-ed here, as in the reference)
 from typing import Dict, List
 
 from torch import nn

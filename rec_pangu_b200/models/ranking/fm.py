@@ -1,4 +1,5 @@
 """FM — reference: rec_pangu/models/ranking/fm.py."""
+import torch  # noqa: F401  (loss_fun strings such as "torch.nn.BCELoss()" are eval-ed here, as in the reference)
 from typing import Dict
 
 from ..base_model import BaseModel

@@ -1,4 +1,5 @@
 """NFM — reference: rec_pangu/models/ranking/nfm.py (MLP over the bi-interaction pooled [B,D] vector + LR)."""
+import torch  # noqa: F401  (loss_fun strings such as "torch.nn.BCELoss()" are eval-ed here, as in the reference)
 from typing import Dict, List
 
 from ..base_model import BaseModel

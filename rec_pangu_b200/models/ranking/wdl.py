@@ -1,4 +1,5 @@
 """WDL — reference: rec_pangu/models/ranking/wdl.py."""
+import torch  # noqa: F401  (loss_fun strings such as "torch.nn.BCELoss()" are eval-ed here, as in the reference)
 from typing import Dict, List
 
 from ..base_model import BaseModel

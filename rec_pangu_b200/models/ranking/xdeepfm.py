@@ -1,4 +1,5 @@
 """xDeepFM — reference: rec_pangu/models/ranking/xdeepfm.py:13-79 (LR + CIN + MLP with the default Dropout(0.1))."""
+import torch  # noqa: F401  (loss_fun strings such as "torch.nn.BCELoss()" are eval-ed here, as in the reference)
 from typing import Dict, List
 
 from ..base_model import BaseModel

@@ -572,3 +572,137 @@ def sigmoid_bce(logit: torch.Tensor, label: Optional[torch.Tensor], eps: float =
         return _SigmoidBCE.apply(logit, None, eps, scale), None
     _cuda(label, 'label')
     return _SigmoidBCE.apply(logit, label, eps, scale)
+
+
+# ------------------------------------------------------------------ DCN CrossNet
+def _ptr_array(ts):
+    return (C.c_void_p * len(ts))(*[t.data_ptr() if t is not None else 0 for t in ts])
+
+
+class _CrossNet(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x0, K, L, *params):            # params = w_0..w_{L-1} ([1,K] or [K]), b_0..b_{L-1}
+        ws, bs = params[:L], params[L:]
+        B = x0.shape[0]
+        ldo = (K + 3) // 4 * 4
+        out = torch.empty((B, ldo), dtype=torch.float32, device=x0.device)
+        need = any(ctx.needs_input_grad)
+        S = torch.empty((B, L), dtype=torch.float32, device=x0.device) if need else None
+        check(_lib.load().rpb_crossnet_fwd(_ptr(x0), x0.stride(0), K, L, _ptr_array(ws), _ptr_array(bs), _ptr(out), ldo,
+                                           _ptr(S), B, _stream()), 'rpb_crossnet_fwd')
+        _count()
+        ctx.K, ctx.L = K, L
+        ctx.save_for_backward(x0, S, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x0, S, *params = ctx.saved_tensors
+        K, L = ctx.K, ctx.L
+        ws, bs = params[:L], params[L:]
+        B = x0.shape[0]
+        g = _rowmajor(g)
+        dx0 = torch.empty((B, x0.shape[1]), dtype=torch.float32, device=x0.device) if ctx.needs_input_grad[0] else None
+        dws = [torch.zeros_like(w) for w in ws]
+        dbs = [torch.zeros_like(b) for b in bs]
+        check(_lib.load().rpb_crossnet_bwd(_ptr(x0), x0.stride(0), K, L, _ptr_array(ws), _ptr_array(bs), _ptr(S), _ptr(g),
+                                           g.stride(0), _ptr(dx0), dx0.stride(0) if dx0 is not None else 0,
+                                           _ptr_array(dws), _ptr_array(dbs), B, _stream()), 'rpb_crossnet_bwd')
+        _count(5)
+        return (dx0, None, None, *dws, *dbs)
+
+
+def crossnet(x0: torch.Tensor, K: int, weights, biases) -> torch.Tensor:
+    """CrossNet.forward (interaction.py:137-141) on x0[:, :K]; returns [B, round_up(K,4)] (pad columns zero)."""
+    _cuda(x0, 'CrossNet input')
+    x0 = _rowmajor(x0.float() if x0.dtype != torch.float32 else x0)
+    ws = [w if w.is_contiguous() else w.contiguous() for w in weights]
+    return _CrossNet.apply(x0, K, len(ws), *ws, *biases)
+
+
+# ------------------------------------------------------------------ xDeepFM CIN
+class _CIN(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, e, L, *params):                # params = W_0..W_{L-1} ([U,Cin,1]), b_0..b_{L-1}
+        Ws, bs = params[:L], params[L:]
+        B, F, D = e.shape
+        units = [int(w.shape[0]) for w in Ws]
+        tot = sum(units)
+        pooled = torch.empty((B, tot), dtype=torch.float32, device=e.device)
+        u_arr = (C.c_int32 * L)(*units)
+        check(_lib.load().rpb_cin_fwd(_ptr(e), e.stride(0), B, F, D, L, u_arr, _ptr_array(Ws), _ptr_array(bs),
+                                      _ptr(pooled), tot, _stream()), 'rpb_cin_fwd')
+        _count(2)
+        ctx.L, ctx.units = L, units
+        ctx.save_for_backward(e, *params)
+        return pooled
+
+    @staticmethod
+    def backward(ctx, g):
+        e, *params = ctx.saved_tensors
+        L, units = ctx.L, ctx.units
+        Ws, bs = params[:L], params[L:]
+        B, F, D = e.shape
+        g = _rowmajor(g)
+        de = torch.empty((B, F, D), dtype=torch.float32, device=e.device)
+        dWs = [torch.zeros_like(w) for w in Ws]
+        dbs = [torch.zeros_like(b) for b in bs]
+        u_arr = (C.c_int32 * L)(*units)
+        check(_lib.load().rpb_cin_bwd(_ptr(e), e.stride(0), B, F, D, L, u_arr, _ptr_array(Ws), _ptr_array(bs), _ptr(g),
+                                      g.stride(0), _ptr(de), F * D, 0, _ptr_array(dWs), _ptr_array(dbs), _stream()),
+              'rpb_cin_bwd')
+        _count(3)
+        return (de, None, *dWs, *dbs)
+
+
+def cin(e: torch.Tensor, weights, biases) -> torch.Tensor:
+    """CompressedInteractionNet up to the pooled vector [B, sum(units)] (interaction.py:157-169)."""
+    _cuda(e, 'feature_emb')
+    if e.dtype != torch.float32:
+        e = e.float()
+    B, F, D = e.shape
+    if e.stride(2) != 1 or e.stride(1) != D:
+        e = e.contiguous()
+    Ws = [w if w.is_contiguous() else w.contiguous() for w in weights]
+    return _CIN.apply(e, len(Ws), *Ws, *biases)
+
+
+# ------------------------------------------------------------------ AutoInt interacting layer
+class _AutoIntCore(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkvr, res, B, F, H, d):
+        HD = H * d
+        out = torch.empty((B, F, HD), dtype=torch.float32, device=qkvr.device)
+        check(_lib.load().rpb_autoint_attn_fwd(_ptr(qkvr), qkvr.stride(0), _ptr(res), res.stride(0) if res is not None else 0,
+                                               _ptr(out), B, F, H, d, _stream()), 'rpb_autoint_attn_fwd')
+        _count()
+        ctx.dims = (B, F, H, d)
+        ctx.has_res_proj = res is None
+        ctx.save_for_backward(qkvr, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        qkvr, out = ctx.saved_tensors
+        B, F, H, d = ctx.dims
+        HD = H * d
+        g = g.contiguous()
+        dq = torch.empty((B * F, 4 * HD), dtype=torch.float32, device=qkvr.device)
+        check(_lib.load().rpb_autoint_attn_bwd(_ptr(qkvr), qkvr.stride(0), 1 if ctx.has_res_proj else 0, _ptr(out), _ptr(g),
+                                               _ptr(dq), 4 * HD, B, F, H, d, _stream()), 'rpb_autoint_attn_bwd')
+        _count()
+        if ctx.has_res_proj:
+            return dq, None, None, None, None, None
+        return dq[:, :3 * HD], dq[:, 3 * HD:], None, None, None, None
+
+
+def autoint_attention(X: torch.Tensor, Wq, Wk, Wv, Wres, num_heads: int, attention_dim: int) -> torch.Tensor:
+    """MultiHeadSelfAttention.forward (attention.py:98-101) for the AutoInt configuration -> [B, F, H*d].
+    Projections run on the dense-layer GEMM (tcgen05 when the shape qualifies), the attention core in one kernel."""
+    _cuda(X, 'attention input')
+    B, F, D = X.shape
+    Xc = X.float().contiguous().view(B * F, D)          # [B*F, D] matrix for the projection GEMM
+    Wcat = torch.cat([Wq, Wk, Wv] + ([Wres] if Wres is not None else []), dim=0)     # [(3|4)*H*d, D]
+    qkvr = linear(Xc, Wcat, None)
+    res = None if Wres is not None else Xc
+    return _AutoIntCore.apply(qkvr, res, B, F, num_heads, attention_dim)

@@ -239,3 +239,88 @@ def test_sigmoid_bce_matches_aten():
     lr.backward()
     torch.testing.assert_close(l2.cpu(), lr, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(z2.grad.cpu(), zc2.grad, rtol=1e-4, atol=1e-8)
+
+
+def _param_like(t):
+    return t.detach().clone().cuda().requires_grad_(True)
+
+
+@pytest.mark.parametrize('B,K,L', [(300, 429, 3), (65, 70, 1), (1000, 845, 4), (33, 128, 8)])
+def test_crossnet_forward_backward(B, K, L):
+    from rec_pangu_b200.models.layers import CrossNet
+    torch.manual_seed(K)
+    m = CrossNet(K, L)
+    with torch.no_grad():
+        for l in m.cross_net:
+            l.weight.weight.copy_(torch.randn(1, K) * (1.0 / K) ** 0.5)
+            l.bias.copy_(torch.randn(K) * 0.1)
+    sd = {'p.' + k: v.detach().clone().double().requires_grad_(True) for k, v in m.state_dict().items()}
+    m = m.cuda()
+    ld = (K + 3) // 4 * 4
+    xb = torch.zeros(B, ld)
+    xb[:, :K] = torch.randn(B, K)
+    x = xb.cuda().requires_grad_(True)
+    out = m(x, K=K)
+    w = torch.randn(B, K)
+    (out[:, :K] * w.cuda()).sum().backward()
+    xd = xb[:, :K].double().requires_grad_(True)
+    ref = oracle.crossnet(sd, 'p', xd, L)
+    (ref * w.double()).sum().backward()
+    torch.testing.assert_close(out[:, :K].cpu().double(), ref, rtol=1e-5, atol=1e-5)
+    assert torch.count_nonzero(out[:, K:]) == 0
+    torch.testing.assert_close(x.grad[:, :K].cpu().double(), xd.grad, rtol=1e-4, atol=1e-5)
+    for k, p in m.named_parameters():
+        torch.testing.assert_close(p.grad.cpu().double(), sd['p.' + k].grad, rtol=2e-4, atol=2e-4, msg=lambda s: f'{k}: {s}')
+
+
+@pytest.mark.parametrize('B,F,D,units', [(200, 26, 16, [16, 16, 16]), (37, 6, 8, [4, 5, 3]), (64, 10, 32, [8, 20]),
+                                         (50, 32, 16, [32])])
+def test_cin_forward_backward(B, F, D, units):
+    from rec_pangu_b200.models.layers import CompressedInteractionNet
+    torch.manual_seed(F * D)
+    m = CompressedInteractionNet(F, units)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.copy_(torch.randn(p.shape) * (0.3 if p.dim() > 1 else 0.1))
+    sd = {'p.' + k: v.detach().clone().double().requires_grad_(True) for k, v in m.state_dict().items()}
+    m = m.cuda()
+    e0 = torch.randn(B, F, D) * 0.5
+    e = e0.cuda().requires_grad_(True)
+    out = m(e)
+    w = torch.randn(B, 1)
+    (out * w.cuda()).sum().backward()
+    ed = e0.double().requires_grad_(True)
+    ref = oracle.cin(sd, 'p', ed, units)
+    (ref * w.double()).sum().backward()
+    scale = max(1.0, ref.abs().max().item())
+    assert (out.cpu().double() - ref).abs().max().item() <= 2e-5 * scale
+    gs = max(1.0, ed.grad.abs().max().item())
+    assert (e.grad.cpu().double() - ed.grad).abs().max().item() <= 5e-5 * gs
+    for k, p in m.named_parameters():
+        r = sd['p.' + k].grad
+        assert (p.grad.cpu().double() - r).abs().max().item() <= 1e-4 * max(1.0, r.abs().max().item()), k
+
+
+@pytest.mark.parametrize('B,F,D,H,d', [(100, 26, 32, 3, 8), (33, 6, 8, 3, 4), (64, 6, 12, 3, 4), (50, 32, 16, 1, 16)])
+def test_autoint_attention_forward_backward(B, F, D, H, d):
+    from rec_pangu_b200.models.layers import MultiHeadSelfAttention
+    torch.manual_seed(B)
+    m = MultiHeadSelfAttention(D, attention_dim=d, num_heads=H, align_to='output')
+    with torch.no_grad():
+        for p in m.parameters():
+            p.copy_(torch.randn(p.shape) * (1.0 / D) ** 0.5)
+    sd = {'p.' + k: v.detach().clone().double().requires_grad_(True) for k, v in m.state_dict().items()}
+    m = m.cuda()
+    x0 = torch.randn(B, F, D)
+    x = x0.cuda().requires_grad_(True)
+    out = m(x)
+    w = torch.randn(B, F, H * d)
+    (out * w.cuda()).sum().backward()
+    xd = x0.double().requires_grad_(True)
+    ref = oracle.mhsa(sd, 'p', xd, H, d)
+    (ref * w.double()).sum().backward()
+    assert out.shape == ref.shape
+    torch.testing.assert_close(out.cpu().double(), ref, rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(x.grad.cpu().double(), xd.grad, rtol=1e-4, atol=5e-5)
+    for k, p in m.named_parameters():
+        torch.testing.assert_close(p.grad.cpu().double(), sd['p.' + k].grad, rtol=2e-4, atol=2e-4, msg=lambda s: f'{k}: {s}')

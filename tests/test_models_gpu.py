@@ -37,6 +37,7 @@ def test_ranking_model_matches_reference_golden(name):
     ops.check_index_errors()
     assert out['pred'].shape == g['out']['pred'].shape
     assert (_logit(out['pred'].cpu()) - _logit(g['out']['pred'])).abs().max().item() <= 1e-4
+    torch.testing.assert_close(out['pred'].cpu(), g['out']['pred'], rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(out['loss'].cpu(), g['out']['loss'], rtol=1e-5, atol=1e-6)
     grads = dict(model.named_parameters())
     for k, ref in g['grad'].items():
@@ -83,7 +84,8 @@ def test_ranking_model_matches_oracle_criteo_shape(model_name, kw, okw):
     sdr = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
     ref = oracle.MODEL_FORWARDS[model_name](sdr, enc, data_cpu, **okw)
     ref['loss'].backward()
-    dl = (_logit(out['pred'].cpu()) - ref['logit'].double()).abs().max().item()
+    dl = (model._last_logit.cpu().double() - ref['logit'].double()).abs().max().item()
+    torch.testing.assert_close(out['pred'].cpu(), ref['pred'], rtol=1e-5, atol=1e-6)
     assert dl <= 1e-4, f'max |dlogit| = {dl}'
     torch.testing.assert_close(out['loss'].cpu(), ref['loss'], rtol=1e-5, atol=1e-6)
     for k, p in model.named_parameters():

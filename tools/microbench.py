@@ -123,10 +123,7 @@ def main():
     enc.update({f'C{i + 1}': {'vocab_size': V} for i in range(F)})
     del tables, lrt
     torch.cuda.empty_cache()
-    model = DeepFM.__new__(DeepFM)
-    # fast init: skip kaiming over 416M params on the host; init on device
-    torch.nn.Module.__init__(model)
-    with torch.device('cuda'):
+    with torch.device('cuda'):          # init the 416M parameters on the device
         model = DeepFM(embedding_dim=D, enc_dict=enc)
     batches = []
     for i in range(NB):
