@@ -81,6 +81,10 @@ typedef struct RpbScatterDesc {
     const float* dlr_in;            /* [B, ld_dlr] grad wrt lr_in (first F columns used), or NULL */
 } RpbScatterDesc;
 int rpb_gather_bwd(const RpbScatterDesc* d, void* stream);
+/* Sparse zero_grad for persistent dense-grad buffers: grads[f][idx[f][b], :] = 0 and lr_grads[f][idx[f][b]] = 0
+ * for every (b, f) of a previous backward (uses B, F, D, grads, lr_grads, rows, idx of the descriptor only).
+ * Leaves a [rows, D] buffer all-zero again at O(batch) cost instead of the reference's O(vocabulary) zero-fill. */
+int rpb_rows_zero(const RpbScatterDesc* d, void* stream);
 
 /* Standalone FM second-order term on any [B,F,D] tensor with row stride lde (floats) between samples:
  * InnerProductLayer (interaction.py:36-44).  out_sum [B] (product_sum_pooling) and/or out_bi [B,D]

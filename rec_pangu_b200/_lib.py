@@ -36,6 +36,7 @@ SIGNATURES = {
     'rpb_error_string': (C.c_char_p, [C.c_int]),
     'rpb_gather_fwd': (C.c_int, [C.POINTER(GatherDesc), _vp]),
     'rpb_gather_bwd': (C.c_int, [C.POINTER(ScatterDesc), _vp]),
+    'rpb_rows_zero': (C.c_int, [C.POINTER(ScatterDesc), _vp]),
     'rpb_fm_fwd': (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     'rpb_fm_bwd': (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _i64, C.c_int, _vp]),
     'rpb_linear_fwd': (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),

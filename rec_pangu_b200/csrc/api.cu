@@ -1,6 +1,36 @@
 // Library-level entry points.
 #include "common.cuh"
 
+namespace rpb {
+
+// Grow-only per-device scratch buffers (slot = call site).  Kernels of one stream that share a slot are ordered by
+// the stream, so reuse is safe for the single-stream execution model of the reference's training loop.  Growth uses
+// cudaMalloc and therefore must not happen inside CUDA-graph capture: run one eager warm-up step first.
+void* workspace(int slot, size_t bytes, int* err) {
+    constexpr int kMaxDev = 16, kSlots = 8;
+    static void* ptr[kMaxDev][kSlots] = {};
+    static size_t cap[kMaxDev][kSlots] = {};
+    int dev = 0;
+    *err = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess || dev >= kMaxDev || slot >= kSlots) { *err = e != cudaSuccess ? (int)e : RPB_ERR_UNSUPPORTED; return nullptr; }
+    if (cap[dev][slot] < bytes) {
+        if (ptr[dev][slot] != nullptr) {
+            cudaDeviceSynchronize();           // previous users of the old buffer must be done before it is freed
+            cudaFree(ptr[dev][slot]);
+            ptr[dev][slot] = nullptr;
+            cap[dev][slot] = 0;
+        }
+        const size_t want = bytes + bytes / 4 + 4096;
+        e = cudaMalloc(&ptr[dev][slot], want);
+        if (e != cudaSuccess) { *err = (int)e; return nullptr; }
+        cap[dev][slot] = want;
+    }
+    return ptr[dev][slot];
+}
+
+}  // namespace rpb
+
 RPB_API int rpb_version(void) { return 1; }
 
 RPB_API const char* rpb_error_string(int code) {

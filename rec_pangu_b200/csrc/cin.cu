@@ -357,10 +357,10 @@ static int cin_dispatch(int D, int maxu, Fn&& fn) {
 }
 
 static int pack_weights(const CinMeta& meta, const CinPtrs& ptrs, float** Wt_out, float** bias_out, cudaStream_t st) {
-    float* ws = nullptr;
     const size_t bytes = ((size_t)meta.w_total + meta.u_total + 4) * sizeof(float);
-    cudaError_t e = cudaMallocAsync(&ws, bytes, st);
-    if (e != cudaSuccess) return (int)e;
+    int werr = 0;
+    float* ws = static_cast<float*>(workspace(1, bytes, &werr));
+    if (ws == nullptr) return werr;
     cin_pack_kernel<<<dim3(8, meta.L), 256, 0, st>>>(ptrs, meta, ws, ws + meta.w_total);
     *Wt_out = ws;
     *bias_out = ws + meta.w_total;
@@ -383,7 +383,7 @@ RPB_API int rpb_cin_fwd(const float* e, int64_t lde, int B, int F, int D, int L,
     CinPtrs ptrs{};
     for (int k = 0; k < L; ++k) { ptrs.W[k] = W[k]; ptrs.bias[k] = bias[k]; }
     int rc = pack_weights(h.meta, ptrs, &Wt, &bcat, st);
-    if (rc != 0) { if (Wt) cudaFreeAsync(Wt, st); return rc; }
+    if (rc != 0) return rc;
     rc = cin_dispatch(D, maxu, [&](auto dt, auto ut) -> int {
         constexpr int DD = decltype(dt)::value, MU = decltype(ut)::value;
         constexpr int SPC = 256 / DD;
@@ -397,7 +397,6 @@ RPB_API int rpb_cin_fwd(const float* e, int64_t lde, int B, int F, int D, int L,
         cin_fwd_kernel<DD, MU><<<grid, 256, smem, st>>>(e, lde, B, h.meta, Wt, bcat, pooled, (int)ldp);
         return (int)cudaGetLastError();
     });
-    cudaFreeAsync(Wt, st);
     return rc;
 }
 
@@ -417,11 +416,11 @@ RPB_API int rpb_cin_bwd(const float* e, int64_t lde, int B, int F, int D, int L,
         ptrs.dW[k] = dW[k]; ptrs.db[k] = db ? db[k] : nullptr;
     }
     int rc = pack_weights(h.meta, ptrs, &Wt, &bcat, st);
-    if (rc != 0) { if (Wt) cudaFreeAsync(Wt, st); return rc; }
-    float* spill = nullptr;
+    if (rc != 0) return rc;
     const size_t per = (size_t)B * h.meta.u_total * D;
-    cudaError_t e1 = cudaMallocAsync(&spill, (2 * per) * sizeof(float), st);
-    if (e1 != cudaSuccess) { cudaFreeAsync(Wt, st); return (int)e1; }
+    int werr = 0;
+    float* spill = static_cast<float*>(workspace(2, (2 * per) * sizeof(float), &werr));
+    if (spill == nullptr) return werr;
     float* Gout = spill;
     float* Xout = spill + per;
     rc = cin_dispatch(D, maxu, [&](auto dt, auto ut) -> int {
@@ -455,7 +454,5 @@ RPB_API int rpb_cin_bwd(const float* e, int64_t lde, int B, int F, int D, int L,
         if (maxfm <= 768) return launch(std::integral_constant<int, 3>{});
         return launch(std::integral_constant<int, 4>{});
     });
-    cudaFreeAsync(spill, st);
-    cudaFreeAsync(Wt, st);
     return rc;
 }

@@ -17,6 +17,8 @@ namespace rpb {
 
 constexpr int kWarp = 32;
 
+void* workspace(int slot, size_t bytes, int* err);   // api.cu
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 __device__ __forceinline__ float4 ldg_f4(const float* p) {

@@ -176,9 +176,9 @@ RPB_API int rpb_crossnet_bwd(const float* x0, int64_t ldx, int K, int L, const f
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     // workspace: C [B, 2L] | T [2L, K] | tb [2L] | csum [K]
     const size_t nC = (size_t)B * 2 * L, nT = (size_t)2 * L * K;
-    float* ws = nullptr;
-    cudaError_t e = cudaMallocAsync(&ws, (nC + nT + 2 * L + K + 8) * sizeof(float), st);
-    if (e != cudaSuccess) return (int)e;
+    int werr = 0;
+    float* ws = static_cast<float*>(workspace(3, (nC + nT + 2 * L + K + 8) * sizeof(float), &werr));
+    if (ws == nullptr) return werr;
     float* C = ws; float* T = ws + nC; float* tb = T + nT; float* csum = tb + 2 * L;
     cudaMemsetAsync(T, 0, (nT + 2 * L + K) * sizeof(float), st);
     int rc = cn_dispatch((int)max((int64_t)K, dx0 ? lddx : 0), [&](auto t) -> int {
@@ -198,6 +198,5 @@ RPB_API int rpb_crossnet_bwd(const float* x0, int64_t ldx, int K, int L, const f
             rc = (int)cudaGetLastError();
         }
     }
-    cudaFreeAsync(ws, st);
     return rc;
 }

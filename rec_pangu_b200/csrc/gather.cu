@@ -213,6 +213,24 @@ gather_bwd_kernel(const __grid_constant__ ScatterParams p) {
     }
 }
 
+// Sparse zero_grad: clear exactly the rows touched by a previous backward (persistent dense-grad buffers).
+template <int VEC, int LPR>
+__global__ void __launch_bounds__(256)
+rows_zero_kernel(const __grid_constant__ ScatterParams p) {
+    const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = (int)(gt / LPR), l = (int)(gt % LPR);
+    if (b >= p.B) return;
+    const bool lane_on = l < p.D / VEC;
+    Vec<VEC> z;
+    z.zero();
+    for (int f = 0; f < p.F; ++f) {
+        long long v = __ldg(p.idx[f] + b);
+        if ((unsigned long long)v >= (unsigned long long)p.rows[f]) v = 0;
+        if (lane_on && p.grads[f] != nullptr) z.store(p.grads[f] + (size_t)v * p.D + l * VEC);
+        if ((f % LPR) == l && p.lr_grads[f] != nullptr) p.lr_grads[f][v] = 0.f;
+    }
+}
+
 // ---------------------------------------------------------------- standalone FM on a [B,F,D] tensor
 template <int VEC, int LPR>
 __global__ void __launch_bounds__(256)
@@ -358,6 +376,28 @@ RPB_API int rpb_gather_bwd(const RpbScatterDesc* d, void* stream) {
         constexpr int VEC = decltype(vec)::value, LPR = decltype(lpr)::value;
         const int grid = ceil_div((long long)p.B * LPR, 256);
         gather_bwd_kernel<VEC, LPR, 8><<<grid, 256, 0, st>>>(p);
+        RPB_LAUNCH_CHECK();
+        return 0;
+    });
+}
+
+RPB_API int rpb_rows_zero(const RpbScatterDesc* d, void* stream) {
+    if (d == nullptr || d->B <= 0 || d->F <= 0 || d->D <= 0) return RPB_ERR_BAD_ARG;
+    if (d->F > RPB_MAX_FIELDS) return RPB_ERR_UNSUPPORTED;
+    ScatterParams p{};
+    bool aligned = true;
+    for (int f = 0; f < d->F; ++f) {
+        p.grads[f] = d->grads ? d->grads[f] : nullptr;
+        p.lr_grads[f] = d->lr_grads ? d->lr_grads[f] : nullptr;
+        p.idx[f] = reinterpret_cast<const long long*>(d->idx[f]);
+        p.rows[f] = d->rows[f];
+        if (p.grads[f]) aligned = aligned && is_aligned16(p.grads[f]);
+    }
+    p.B = d->B; p.F = d->F; p.D = d->D;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    return dispatch_shape(d->D, aligned, [&](auto vec, auto lpr) -> int {
+        constexpr int VEC = decltype(vec)::value, LPR = decltype(lpr)::value;
+        rows_zero_kernel<VEC, LPR><<<ceil_div((long long)p.B * LPR, 256), 256, 0, st>>>(p);
         RPB_LAUNCH_CHECK();
         return 0;
     });

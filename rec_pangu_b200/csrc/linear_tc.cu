@@ -309,9 +309,9 @@ int gemm_tc(const float* A, long long lda, const float* Bsrc, long long ldb, int
     const int Np = block_n * n_tiles;
     const int Kp = round_up(K, 4);
     const int nkb = ceil_div(K, TC_BLOCK_K);
-    float* ws = nullptr;
-    cudaError_t e = cudaMallocAsync(&ws, (size_t)2 * Np * Kp * sizeof(float), st);
-    if (e != cudaSuccess) return (int)e;
+    int werr = 0;
+    float* ws = static_cast<float*>(workspace(0, (size_t)2 * Np * Kp * sizeof(float), &werr));
+    if (ws == nullptr) return werr;
     float* hi = ws;
     float* lo = ws + (size_t)Np * Kp;
     const int rows_in = b_transpose ? K : N, cols_in = b_transpose ? N : K;
@@ -341,7 +341,6 @@ int gemm_tc(const float* A, long long lda, const float* Bsrc, long long ldb, int
         else if (max_stages >= 2) rc = launch(std::integral_constant<int, 2>{});
         else rc = RPB_ERR_UNSUPPORTED;
     }
-    cudaFreeAsync(ws, st);
     return rc;
 }
 

@@ -49,6 +49,20 @@ class BaseModel(nn.Module):
         self.embedding_layer.set_weights(col_name=col_name, embedding_matrix=embeddings.to(old.device),
                                          trainable=trainable)
 
+    def set_grad_mode(self, mode: str):
+        """'dense' (reference-identical fresh dense table grads) or 'persistent' (see EmbeddingLayer.grad_mode)."""
+        assert mode in ('dense', 'persistent')
+        for m in self.modules():
+            if isinstance(m, EmbeddingLayer):
+                m.grad_mode = mode
+        return self
+
+    def zero_grad(self, set_to_none: bool = True):
+        for m in self.modules():
+            if isinstance(m, EmbeddingLayer):
+                m.clean_grads()
+        super().zero_grad(set_to_none=set_to_none)
+
     # ---- shared head: sigmoid + loss (ranking models: `y_pred.sigmoid()` + `self.loss_fun(...)`)
     def _finish(self, logit, data, is_training):
         from .. import ops

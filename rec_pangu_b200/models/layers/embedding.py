@@ -23,6 +23,11 @@ class EmbeddingLayer(nn.Module):
             self.embedding_layer.update({col: nn.Embedding(num_embeddings=enc_dict[col]['vocab_size'] + 1,
                                                            embedding_dim=embedding_dim)})
         self.dense_feature = dense_feature_names(enc_dict)
+        # 'dense': backward returns fresh zero-filled [rows, D] grads exactly like nn.Embedding (reference behaviour);
+        # 'persistent': grads live in persistent buffers that are re-zeroed sparsely (ops.GradStore) — same .grad
+        # contents, O(batch) instead of O(vocabulary) traffic per step.
+        self.grad_mode = 'dense'
+        self._grad_store = ops.GradStore()
 
     def set_weights(self, col_name: str, embedding_matrix: torch.Tensor, trainable: Optional[bool] = True) -> None:
         """embedding.py:36-47."""
@@ -39,7 +44,12 @@ class EmbeddingLayer(nn.Module):
         x = [emb_0 | ... | emb_{F-1} | dense_0..dense_{Nd-1} | 0-pad] (see include/rec_pangu_b200.h)."""
         idx = [X[c] for c in self.emb_feature]
         dense = [X[c] for c in self.dense_feature] if with_dense else []
-        return ops.gather(self.tables(), idx, dense, lr_tables=lr_tables, want_fm=want_fm)
+        return ops.gather(self.tables(), idx, dense, lr_tables=lr_tables, want_fm=want_fm,
+                          grad_store=self._grad_store if self.grad_mode == 'persistent' else None)
+
+    def clean_grads(self):
+        """Sparse re-zero of the persistent grad buffers (no-op in 'dense' mode)."""
+        self._grad_store.clean()
 
     def forward(self, X: Dict[str, torch.Tensor], name: Optional[str] = None) -> torch.Tensor:
         """[B, F, D] (name=None) — embedding.py:58-63; a strided view of the feature row, no stack copy."""

@@ -12,7 +12,7 @@ import torch
 from . import _lib
 from ._lib import GatherDesc, ScatterDesc, check
 
-__all__ = ['gather', 'fm_interaction', 'mlp_forward', 'sigmoid_bce', 'linear', 'feature_row_stride',
+__all__ = ['GradStore', 'gather', 'fm_interaction', 'mlp_forward', 'sigmoid_bce', 'linear', 'feature_row_stride',
            'check_index_errors', 'set_gemm_impl', 'get_gemm_impl', 'launch_count', 'reset_launch_count']
 
 _GEMM_IMPL = int(__import__('os').environ.get('RPB_GEMM_IMPL', '0'))   # 0 auto, 1 SIMT fp32, 2 tcgen05 3xTF32
@@ -95,6 +95,49 @@ def check_index_errors(device=None, sync: bool = True):
         raise IndexError(f'index out of range in embedding gather: field #{f}, sample {b}, index {v}')
 
 
+# ------------------------------------------------------------------ persistent dense-grad buffers
+class GradStore:
+    """Persistent [rows, D] gradient buffers for embedding tables ('persistent' grad mode).
+
+    The reference's backward materialises a zero-filled dense grad per table every step (embedding_dense_backward,
+    SURVEY.md K14: 1.66 GB of zero-fill at config 2).  Here each table owns one buffer that is all-zero between
+    steps: backward scatter-adds into it and publishes it as ``param.grad`` (a dense tensor with exactly the
+    reference's content, so torch.optim.Adam(model.parameters()) still works), and ``clean()`` — called from
+    ``BaseModel.zero_grad()`` or lazily by the next backward — re-zeroes only the rows the batch touched."""
+
+    def __init__(self):
+        self.buffers = {}          # id(param) -> tensor
+        self.pending = []          # list of (grads, lr_grads, rows, idx tensors, D)
+
+    def buffer(self, param: torch.Tensor) -> torch.Tensor:
+        b = self.buffers.get(id(param))
+        if b is None or b.shape != param.shape or b.device != param.device:
+            b = torch.zeros_like(param)
+            self.buffers[id(param)] = b
+        return b
+
+    def clean(self):
+        for grads, lr_grads, rows, idx, D in self.pending:
+            F = len(idx)
+            d = ScatterDesc()
+            d.B, d.F, d.D = idx[0].shape[0], F, D
+            g_arr = _ptr_list(grads)
+            d.grads = g_arr
+            if lr_grads is not None:
+                l_arr = _ptr_list(lr_grads)
+                d.lr_grads = l_arr
+            r_arr = (C.c_int64 * F)(*rows)
+            i_arr = _ptr_list(idx)
+            d.rows, d.idx = r_arr, i_arr
+            check(_lib.load().rpb_rows_zero(C.byref(d), _stream()), 'rpb_rows_zero')
+            _count()
+        self.pending = []
+
+
+def _ptr_list(ts):
+    return (C.c_void_p * len(ts))(*[t.data_ptr() if t is not None else 0 for t in ts])
+
+
 # ------------------------------------------------------------------ gather
 class _Gather(torch.autograd.Function):
     @staticmethod
@@ -138,6 +181,7 @@ class _Gather(torch.autograd.Function):
         ctx.cfg = cfg
         ctx.rows = rows
         ctx.n_in = len(tensors)
+        ctx.params = (tables, lr_tables)       # Parameter objects (persistent grad mode publishes .grad itself)
         ctx.save_for_backward(x, fm_s, *idx)
         outs = [x]
         if want_fm:
@@ -167,10 +211,20 @@ class _Gather(torch.autograd.Function):
         lr_req = ctx.needs_input_grad[1 + F:1 + 2 * F] if has_lr else ()
 
         grads: List[Optional[torch.Tensor]] = [None] * ctx.n_in
-        g_tables = [torch.zeros((ctx.rows[f], D), dtype=torch.float32, device=dev) if tbl_req[f] else None
+        store = cfg.get('grad_store')
+        tables, lr_tables = ctx.params
+        if store is not None:
+            trainable = [tables[f] for f in range(F) if tbl_req[f]] + \
+                        ([lr_tables[f] for f in range(F) if lr_req[f]] if has_lr else [])
+            if store.pending and all(t.grad is None for t in trainable):
+                store.clean()                  # grads were dropped (optimizer.zero_grad): start from all-zero buffers
+            g_tables = [store.buffer(tables[f]) if tbl_req[f] else None for f in range(F)]
+            g_lr = [store.buffer(lr_tables[f]) if (has_lr and lr_req[f]) else None for f in range(F)]
+        else:
+            g_tables = [torch.zeros((ctx.rows[f], D), dtype=torch.float32, device=dev) if tbl_req[f] else None
+                        for f in range(F)]
+            g_lr = [torch.zeros((ctx.rows[f], 1), dtype=torch.float32, device=dev) if (has_lr and lr_req[f]) else None
                     for f in range(F)]
-        g_lr = [torch.zeros((ctx.rows[f], 1), dtype=torch.float32, device=dev) if (has_lr and lr_req[f]) else None
-                for f in range(F)]
         have_any = (gx is not None or gfm is not None) and any(g is not None for g in g_tables)
         have_lr = glr is not None and any(g is not None for g in g_lr)
         if have_any or have_lr:
@@ -193,6 +247,18 @@ class _Gather(torch.autograd.Function):
             d.rows, d.idx = r_arr, i_arr
             check(_lib.load().rpb_gather_bwd(C.byref(d), _stream()), 'rpb_gather_bwd')
             _count()
+        if store is not None:
+            store.pending.append((g_tables, g_lr if has_lr else None, ctx.rows, list(idx), D))
+            for f in range(F):
+                for prm, buf in ((tables[f], g_tables[f]), (lr_tables[f] if has_lr else None, g_lr[f])):
+                    if buf is None:
+                        continue
+                    if prm.grad is None:
+                        prm.grad = buf             # publish the dense grad (same content as the reference's)
+                    elif prm.grad is not buf:
+                        raise RuntimeError("embedding table .grad was replaced externally; persistent grad mode "
+                                           "needs model.zero_grad() / set grad_mode='dense'")
+            return (None, *grads)
         for f in range(F):
             grads[f] = g_tables[f]
             if has_lr:
@@ -201,7 +267,8 @@ class _Gather(torch.autograd.Function):
 
 
 def gather(tables: Sequence[torch.Tensor], idx: Sequence[torch.Tensor], dense: Sequence[torch.Tensor] = (),
-           lr_tables: Optional[Sequence[torch.Tensor]] = None, want_fm: bool = False):
+           lr_tables: Optional[Sequence[torch.Tensor]] = None, want_fm: bool = False,
+           grad_store: Optional['GradStore'] = None):
     """One-launch multi-table gather.  Returns (x [B, ldx], fm [B] | None, lr_in [B, ld_lr] | None).
 
     ``x[:, :F*D].view(B, F, D)`` is the reference's ``EmbeddingLayer.forward`` output
@@ -239,7 +306,8 @@ def gather(tables: Sequence[torch.Tensor], idx: Sequence[torch.Tensor], dense: S
         lr_tables = [t if t.is_contiguous() else t.contiguous() for t in lr_tables]
     needs_grad = torch.is_grad_enabled() and (any(t.requires_grad for t in tables) or
                                               (has_lr and any(t.requires_grad for t in lr_tables)))
-    cfg = dict(F=F, Nd=len(dense_l), D=D, has_lr=has_lr, want_fm=want_fm, needs_grad=needs_grad)
+    cfg = dict(F=F, Nd=len(dense_l), D=D, has_lr=has_lr, want_fm=want_fm, needs_grad=needs_grad,
+               grad_store=grad_store)
     args = list(tables) + (list(lr_tables) if has_lr else []) + idx_l + dense_l
     outs = _Gather.apply(cfg, *args)
     x = outs[0]
