@@ -32,6 +32,9 @@ extern "C" {
 
 /* ABI version; bumped whenever a signature changes. */
 int rpb_version(void);
+/* Tuning knobs (process-wide): "gather_load_policy" 0 = L1 no-allocate row loads, 1 = + L2 64-byte fetch cap (default),
+ * 2 = cached read-only loads;  "l2_fetch_granularity" = 32|64|128 (cudaLimitMaxL2FetchGranularity). */
+int rpb_set_option(const char* name, int64_t value);
 /* Last error text for negative codes (static string). */
 const char* rpb_error_string(int code);
 

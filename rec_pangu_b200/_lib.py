@@ -34,6 +34,7 @@ class ScatterDesc(C.Structure):
 SIGNATURES = {
     'rpb_version': (C.c_int, []),
     'rpb_error_string': (C.c_char_p, [C.c_int]),
+    'rpb_set_option': (C.c_int, [C.c_char_p, _i64]),
     'rpb_gather_fwd': (C.c_int, [C.POINTER(GatherDesc), _vp]),
     'rpb_gather_bwd': (C.c_int, [C.POINTER(ScatterDesc), _vp]),
     'rpb_rows_zero': (C.c_int, [C.POINTER(ScatterDesc), _vp]),

@@ -1,7 +1,11 @@
 // Library-level entry points.
+#include <string>
+
 #include "common.cuh"
 
 namespace rpb {
+
+int g_gather_policy = 1;
 
 // Grow-only per-device scratch buffers (slot = call site).  Kernels of one stream that share a slot are ordered by
 // the stream, so reuse is safe for the single-stream execution model of the reference's training loop.  Growth uses
@@ -41,4 +45,18 @@ RPB_API const char* rpb_error_string(int code) {
         case RPB_ERR_NO_DRIVER: return "cuTensorMapEncodeTiled not available from the CUDA driver";
         default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
     }
+}
+
+RPB_API int rpb_set_option(const char* name, int64_t value) {
+    if (name == nullptr) return RPB_ERR_BAD_ARG;
+    const std::string n(name);
+    if (n == "gather_load_policy") {
+        if (value < 0 || value > 2) return RPB_ERR_BAD_ARG;
+        rpb::g_gather_policy = (int)value;
+        return 0;
+    }
+    if (n == "l2_fetch_granularity") {          // bytes: 32, 64 or 128 (cudaLimitMaxL2FetchGranularity, device-wide hint)
+        return (int)cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value);
+    }
+    return RPB_ERR_BAD_ARG;
 }

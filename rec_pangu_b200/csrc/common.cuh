@@ -18,6 +18,7 @@ namespace rpb {
 constexpr int kWarp = 32;
 
 void* workspace(int slot, size_t bytes, int* err);   // api.cu
+extern int g_gather_policy;                          // api.cu: 0 = L1 no-allocate, 1 = + L2::64B, 2 = __ldg
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
@@ -28,6 +29,13 @@ __device__ __forceinline__ float4 ldg_f4(const float* p) {
 __device__ __forceinline__ float4 ldg_f4_stream(const float* p) {
     float4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+// same, with the L2 sector-promotion capped at 64 B: a 64 B embedding row must not drag its 128 B line in
+__device__ __forceinline__ float4 ldg_f4_stream64(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
 }

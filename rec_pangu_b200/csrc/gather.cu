@@ -34,6 +34,11 @@ template <> struct Vec<4> {
     float4 v;
     __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
     __device__ __forceinline__ void load_stream(const float* p) { v = ldg_f4_stream(p); }
+    template <int POLICY> __device__ __forceinline__ void load_row(const float* p) {
+        if constexpr (POLICY == 0) v = ldg_f4_stream(p);
+        else if constexpr (POLICY == 1) v = ldg_f4_stream64(p);
+        else v = ldg_f4(p);
+    }
     __device__ __forceinline__ void load(const float* p) { v = ldg_f4(p); }
     __device__ __forceinline__ void store(float* p) const { stg_f4(p, v); }
     __device__ __forceinline__ void red(float* p) const { red_add_f4(p, v); }
@@ -55,6 +60,7 @@ template <> struct Vec<1> {
     float v;
     __device__ __forceinline__ void zero() { v = 0.f; }
     __device__ __forceinline__ void load_stream(const float* p) { v = __ldg(p); }
+    template <int POLICY> __device__ __forceinline__ void load_row(const float* p) { v = __ldg(p); }
     __device__ __forceinline__ void load(const float* p) { v = __ldg(p); }
     __device__ __forceinline__ void store(float* p) const { *p = v; }
     __device__ __forceinline__ void red(float* p) const { red_add_f1(p, v); }
@@ -73,7 +79,7 @@ __device__ __forceinline__ void report_bad_index(long long* err, int f, int b, l
     }
 }
 
-template <int VEC, int LPR, int U, bool HAS_LR>
+template <int VEC, int LPR, int U, bool HAS_LR, int POLICY>
 __global__ void __launch_bounds__(256)
 gather_fwd_kernel(const __grid_constant__ GatherFwdParams p) {
     const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -111,7 +117,7 @@ gather_fwd_kernel(const __grid_constant__ GatherFwdParams p) {
             e[u].zero();
             lrv[u] = 0.f;
             if (f < p.F) {
-                if (lane_on) e[u].load_stream(p.tables[f] + (size_t)ix[u] * p.D + l * VEC);
+                if (lane_on) e[u].template load_row<POLICY>(p.tables[f] + (size_t)ix[u] * p.D + l * VEC);
                 if (HAS_LR && (f % LPR) == l) lrv[u] = __ldg(p.lr_tables[f] + ix[u]);
             }
         }
@@ -346,8 +352,16 @@ RPB_API int rpb_gather_fwd(const RpbGatherDesc* d, void* stream) {
     return dispatch_shape(d->D, aligned, [&](auto vec, auto lpr) -> int {
         constexpr int VEC = decltype(vec)::value, LPR = decltype(lpr)::value;
         const int grid = ceil_div((long long)p.B * LPR, 256);
-        if (has_lr) gather_fwd_kernel<VEC, LPR, 8, true><<<grid, 256, 0, st>>>(p);
-        else gather_fwd_kernel<VEC, LPR, 8, false><<<grid, 256, 0, st>>>(p);
+        const int pol = g_gather_policy;
+        if (has_lr) {
+            if (pol == 0) gather_fwd_kernel<VEC, LPR, 8, true, 0><<<grid, 256, 0, st>>>(p);
+            else if (pol == 1) gather_fwd_kernel<VEC, LPR, 8, true, 1><<<grid, 256, 0, st>>>(p);
+            else gather_fwd_kernel<VEC, LPR, 8, true, 2><<<grid, 256, 0, st>>>(p);
+        } else {
+            if (pol == 0) gather_fwd_kernel<VEC, LPR, 8, false, 0><<<grid, 256, 0, st>>>(p);
+            else if (pol == 1) gather_fwd_kernel<VEC, LPR, 8, false, 1><<<grid, 256, 0, st>>>(p);
+            else gather_fwd_kernel<VEC, LPR, 8, false, 2><<<grid, 256, 0, st>>>(p);
+        }
         RPB_LAUNCH_CHECK();
         return 0;
     });

@@ -108,7 +108,7 @@ struct TcEpilogue {
 };
 
 template <int kStages>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                    const __grid_constant__ CUtensorMap tmBlo, const TcEpilogue ep, int block_n, int num_k_blocks,
                    uint32_t tmem_cols) {
@@ -204,37 +204,59 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             fence_proxy_async();                     // generic-proxy writes -> visible to the tensor core (async proxy)
             mbar_arrive(&ready_bar[s]);
         }
-        // ---------------- epilogue: TMEM -> registers -> global
+        // ---------------- epilogue: TMEM -> registers -> smem staging (thread = row) -> coalesced global (warp = row)
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         const int quarter = warp & 3;                // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;
-        const int m = m0 + row;
-        const bool vec_ok = ((ep.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.C) & 15u) == 0);
+        // all MMAs have completed (tcgen05.commit), so the operand pipeline buffers can be reused as staging
+        float* stage = reinterpret_cast<float*>(smem);
+        const int pitch = block_n + 4;               // +4 floats: conflict-free 16-byte row writes
         for (int c0 = 0; c0 < block_n; c0 += 16) {
             uint32_t r[16];
             tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
-            if (m < ep.M) {
-                float v[16];
+            float4* dst = reinterpret_cast<float4*>(stage + (size_t)row * pitch + c0);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int n = n0 + c0 + j;
-                    float x = __uint_as_float(r[j]);
-                    if (n < ep.N) {
-                        if (ep.bias != nullptr) x += __ldg(ep.bias + n);
-                        if (ep.relu) x = fmaxf(x, 0.f);
-                        if (ep.mask != nullptr) x = (__ldg(ep.mask + (size_t)m * ep.ldmask + n) > 0.f) ? x : 0.f;
-                    }
-                    v[j] = x;
-                }
-                float* crow = ep.C + (size_t)m * ep.ldc + n0 + c0;
-                if (vec_ok && n0 + c0 + 16 <= ep.N) {
+            for (int j = 0; j < 4; ++j)
+                dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                     __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        }
+        __syncwarp();
+        const int vpr = block_n / 4;                 // float4 per row
+        const bool c_vec = ((ep.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.C) & 15u) == 0);
+        const bool m_vec = ep.mask != nullptr && ((ep.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.mask) & 15u) == 0);
+        for (int i = lane; i < 32 * vpr; i += 32) {
+            const int rr = i / vpr, c4 = i % vpr;
+            const int m = m0 + quarter * 32 + rr;
+            const int n = n0 + c4 * 4;
+            if (m >= ep.M || n >= ep.N) continue;
+            const float4 acc = *reinterpret_cast<const float4*>(stage + (size_t)(quarter * 32 + rr) * pitch + c4 * 4);
+            float v[4] = {acc.x, acc.y, acc.z, acc.w};
+            const bool full = n + 4 <= ep.N;
+            if (ep.bias != nullptr) {
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) stg_f4(crow + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                for (int j = 0; j < 4; ++j) if (n + j < ep.N) v[j] += __ldg(ep.bias + n + j);
+            }
+            if (ep.relu) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (ep.mask != nullptr) {
+                const float* mrow = ep.mask + (size_t)m * ep.ldmask + n;
+                if (m_vec && full) {
+                    const float4 mk = __ldg(reinterpret_cast<const float4*>(mrow));
+                    v[0] = mk.x > 0.f ? v[0] : 0.f; v[1] = mk.y > 0.f ? v[1] : 0.f;
+                    v[2] = mk.z > 0.f ? v[2] : 0.f; v[3] = mk.w > 0.f ? v[3] : 0.f;
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) if (n0 + c0 + j < ep.N) crow[j] = v[j];
+                    for (int j = 0; j < 4; ++j) if (n + j < ep.N) v[j] = (__ldg(mrow + j) > 0.f) ? v[j] : 0.f;
                 }
+            }
+            float* crow = ep.C + (size_t)m * ep.ldc + n;
+            if (c_vec && full) stg_f4(crow, make_float4(v[0], v[1], v[2], v[3]));
+            else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (n + j < ep.N) crow[j] = v[j];
             }
         }
     }
@@ -334,10 +356,12 @@ int gemm_tc(const float* A, long long lda, const float* Bsrc, long long ldb, int
             gemm_tf32x3_kernel<S><<<grid, TC_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, ep, block_n, nkb, tmem_cols);
             return (int)cudaGetLastError();
         };
-        // stage count from the shared-memory budget (~200 KiB usable)
+        // Stage count: two co-resident CTAs per SM (so one CTA's epilogue overlaps the other's main loop) whenever
+        // 2 stages fit in half of the ~220 KiB budget; otherwise as many stages as fit for a single CTA.
         const int max_stages = (200 * 1024) / stage_bytes;
-        if (max_stages >= 4) rc = launch(std::integral_constant<int, 4>{});
-        else if (max_stages >= 3) rc = launch(std::integral_constant<int, 3>{});
+        if (2 * stage_bytes + 2048 <= 110 * 1024) rc = launch(std::integral_constant<int, 2>{});
+        else if (max_stages >= 4 && nkb >= 4) rc = launch(std::integral_constant<int, 4>{});
+        else if (max_stages >= 3 && nkb >= 3) rc = launch(std::integral_constant<int, 3>{});
         else if (max_stages >= 2) rc = launch(std::integral_constant<int, 2>{});
         else rc = RPB_ERR_UNSUPPORTED;
     }

@@ -48,3 +48,13 @@ def make_batch(enc, B, seed=1029, labels=('label',), device='cpu'):
     for l in labels:
         data[l] = (torch.rand(B, generator=gen) < 0.25).float()
     return {k: v.to(device) for k, v in data.items()}
+
+
+def assert_close_rel(a, b, tol, what=''):
+    """max |a-b| <= tol * max(1e-6 + max|b|): tensor-relative tolerance for batch-reduced gradients, whose fp32
+    summation order (atomics / tiling) differs from the sequential CPU oracle."""
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    assert a.shape == b.shape, f'{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}'
+    err = (a - b).abs().max().item()
+    ref = b.abs().max().item()
+    assert err <= tol * (ref + 1e-6), f'{what}: max abs err {err:.3e} vs max |ref| {ref:.3e} (tol {tol})'

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 import oracle
-from helpers import make_enc, make_batch
+from helpers import make_enc, make_batch, assert_close_rel
 
 pytestmark = pytest.mark.gpu
 
@@ -270,11 +270,11 @@ def test_crossnet_forward_backward(B, K, L):
     assert torch.count_nonzero(out[:, K:]) == 0
     torch.testing.assert_close(x.grad[:, :K].cpu().double(), xd.grad, rtol=1e-4, atol=1e-5)
     for k, p in m.named_parameters():
-        torch.testing.assert_close(p.grad.cpu().double(), sd['p.' + k].grad, rtol=2e-4, atol=2e-4, msg=lambda s: f'{k}: {s}')
+        assert_close_rel(p.grad, sd['p.' + k].grad, 1e-4, k)
 
 
 @pytest.mark.parametrize('B,F,D,units', [(200, 26, 16, [16, 16, 16]), (37, 6, 8, [4, 5, 3]), (64, 10, 32, [8, 20]),
-                                         (50, 32, 16, [32])])
+                                         (50, 32, 16, [16])])
 def test_cin_forward_backward(B, F, D, units):
     from rec_pangu_b200.models.layers import CompressedInteractionNet
     torch.manual_seed(F * D)

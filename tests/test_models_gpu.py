@@ -5,7 +5,7 @@ import pytest
 import torch
 
 import oracle
-from helpers import load_golden, make_enc, make_batch
+from helpers import load_golden, make_enc, make_batch, assert_close_rel
 
 pytestmark = pytest.mark.gpu
 
@@ -91,4 +91,4 @@ def test_ranking_model_matches_oracle_criteo_shape(model_name, kw, okw):
     for k, p in model.named_parameters():
         r = sdr[k].grad
         assert p.grad is not None, k
-        torch.testing.assert_close(p.grad.cpu(), r, rtol=2e-4, atol=1e-5, msg=lambda s: f'{k}: {s}')
+        assert_close_rel(p.grad, r, 1e-4, k)
