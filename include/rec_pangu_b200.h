@@ -173,6 +173,33 @@ int rpb_autoint_attn_fwd(const float* qkvr, int64_t ldq, const float* res, int64
 int rpb_autoint_attn_bwd(const float* qkvr, int64_t ldq, int has_res_proj, const float* out, const float* dout,
                          float* dqkvr, int64_t lddq, int B, int F, int H, int d, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * MMOE (models/multi_task/mmoe.py:86-112).
+ * rpb_matmul_kn_*: y[M,N] = x[M,K] @ Wkn[K,N] + bias[N] with the weight stored [K,N] (row stride ldw) like the
+ * reference's `experts` [hid, Hh, E] viewed as [hid, Hh*E] and `gates[t]` [hid, E]; einsum('ij,jkl->ikl') and
+ * einsum('ab,bc->ac') of mmoe.py:86,92 become one GEMM over the column-concatenated weight.
+ * bwd: dx = dy @ Wkn^T (may be NULL), dWkn += x^T dy, db += colsum(dy) (each may be NULL). */
+int rpb_matmul_kn_fwd(const float* x, int64_t ldx, const float* Wkn, int64_t ldw, const float* bias, float* y,
+                      int64_t ldy, int M, int N, int K, int impl, void* stream);
+int rpb_matmul_kn_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* Wkn, int64_t ldw,
+                      float* dx, int64_t lddx, float* dWkn, float* db, int M, int N, int K, int impl, void* stream);
+/* eo: [B, ld] = [experts_out (Hh*E, column k*E+l) | gate logits (T*E)].  gate[b, t*E+l] = softmax_l(logits_t)
+ * (mmoe.py:95), out[t, b, k] = sum_l eo[b, k*E+l] * gate[b, t*E+l] (mmoe.py:99-104).  E <= 32.
+ * bwd writes deo [B, ldd] for all Hh*E + T*E columns (pad columns zeroed). */
+int rpb_mmoe_combine_fwd(const float* eo, int64_t ld, int B, int Hh, int E, int T, float* out, float* gate, void* stream);
+int rpb_mmoe_combine_bwd(const float* eo, int64_t ld, const float* gate, const float* dout, int B, int Hh, int E, int T,
+                         float* deo, int64_t ldd, void* stream);
+/* BatchNorm1d of the task towers (mmoe.py:54-56) on a contiguous [M,N] activation.
+ * rpb_bn_stats: sum[n] += sum_m x, sumsq[n] += sum_m x^2 (zero-initialised by the caller; mean/var formed on [N]).
+ * rpb_bn_apply: y = (x - mean) * invstd * gamma + beta.
+ * rpb_bn_bwd: dbeta += colsum(dy), dgamma += colsum(dy * xhat) (zero-initialised by the caller);
+ *             dx = gamma*invstd*(dy - dbeta/M - xhat*dgamma/M) when use_batch_stats, else gamma*invstd*dy. */
+int rpb_bn_stats(const float* x, int M, int N, float* sum, float* sumsq, void* stream);
+int rpb_bn_apply(const float* x, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                 float* y, int M, int N, void* stream);
+int rpb_bn_bwd(const float* dy, const float* x, const float* mean, const float* invstd, const float* gamma,
+               float* dx, float* dgamma, float* dbeta, int M, int N, int use_batch_stats, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

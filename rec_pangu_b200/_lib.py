@@ -56,6 +56,14 @@ SIGNATURES = {
                               C.POINTER(_vp), _vp, _i64, _vp]),
     'rpb_cin_bwd': (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_i32), C.POINTER(_vp),
                               C.POINTER(_vp), _vp, _i64, _vp, _i64, C.c_int, C.POINTER(_vp), C.POINTER(_vp), _vp]),
+    'rpb_matmul_kn_fwd': (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    'rpb_matmul_kn_bwd': (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, _vp]),
+    'rpb_mmoe_combine_fwd': (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
+    'rpb_mmoe_combine_bwd': (C.c_int, [_vp, _i64, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _i64, _vp]),
+    'rpb_bn_stats': (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    'rpb_bn_apply': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
+    'rpb_bn_bwd': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     'rpb_autoint_attn_fwd': (C.c_int, [_vp, _i64, _vp, _i64, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     'rpb_autoint_attn_bwd': (C.c_int, [_vp, _i64, C.c_int, _vp, _vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
 }

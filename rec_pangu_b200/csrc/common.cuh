@@ -20,6 +20,15 @@ constexpr int kWarp = 32;
 void* workspace(int slot, size_t bytes, int* err);   // api.cu
 extern int g_gather_policy;                          // api.cu: 0 = L1 no-allocate, 1 = + L2::64B, 2 = __ldg
 
+// epilogue descriptor of the tcgen05 GEMM (linear_tc.cu)
+struct TcEpilogue {
+    float* C; long long ldc;
+    const float* bias;
+    const float* mask; long long ldmask;
+    int M, N;            // valid extents
+    int relu;
+};
+
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 __device__ __forceinline__ float4 ldg_f4(const float* p) {

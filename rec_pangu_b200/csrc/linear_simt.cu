@@ -215,6 +215,24 @@ int linear_dx_simt(const float* dy, long long lddy, const float* W, const float*
     return 0;
 }
 
+// y[M,N] = x[M,K] @ Wkn[K,N] + bias   (weights stored [K,N], row stride ldw)
+int sgemm_kn_simt(const float* x, long long ldx, const float* Wkn, long long ldw, const float* bias, float* y,
+                  long long ldy, int M, int N, int K, cudaStream_t st) {
+    dim3 grid(ceil_div(M, BM), ceil_div(N, BN));
+    sgemm_kernel<false><<<grid, 256, 0, st>>>(x, ldx, Wkn, ldw, bias, nullptr, 0, y, ldy, M, N, K, 0);
+    RPB_LAUNCH_CHECK();
+    return 0;
+}
+
+// y[M,N] = x[M,K] @ Wnk[N,K]^T   (row stride ldw)
+int sgemm_nk_simt(const float* x, long long ldx, const float* Wnk, long long ldw, float* y, long long ldy, int M, int N,
+                  int K, cudaStream_t st) {
+    dim3 grid(ceil_div(M, BM), ceil_div(N, BN));
+    sgemm_kernel<true><<<grid, 256, 0, st>>>(x, ldx, Wnk, ldw, nullptr, nullptr, 0, y, ldy, M, N, K, 0);
+    RPB_LAUNCH_CHECK();
+    return 0;
+}
+
 int linear_dw_simt(const float* dy, long long lddy, const float* x, long long ldx, float* dW, float* db,
                    int M, int N, int K, cudaStream_t st) {
     const int tiles = ceil_div(K, 64) * ceil_div(N, 64);

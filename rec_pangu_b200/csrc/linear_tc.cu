@@ -99,14 +99,6 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-struct TcEpilogue {
-    float* C; long long ldc;
-    const float* bias;
-    const float* mask; long long ldmask;
-    int M, N;            // valid extents
-    int relu;
-};
-
 template <int kStages>
 __global__ void __launch_bounds__(TC_THREADS)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,

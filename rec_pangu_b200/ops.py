@@ -774,3 +774,152 @@ def autoint_attention(X: torch.Tensor, Wq, Wk, Wv, Wres, num_heads: int, attenti
     qkvr = linear(Xc, Wcat, None)
     res = None if Wres is not None else Xc
     return _AutoIntCore.apply(qkvr, res, B, F, num_heads, attention_dim)
+
+
+# ------------------------------------------------------------------ MMOE pieces
+class _MatmulKN(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, K, Wkn, bias, impl):
+        M, N = x.shape[0], Wkn.shape[1]
+        ldy = (N + 3) // 4 * 4
+        y = torch.empty((M, ldy), dtype=torch.float32, device=x.device)
+        if ldy > N:
+            y[:, N:].zero_()
+        check(_lib.load().rpb_matmul_kn_fwd(_ptr(x), x.stride(0), _ptr(Wkn), Wkn.stride(0), _ptr(bias), _ptr(y), ldy, M, N, K,
+                                            impl, _stream()), 'rpb_matmul_kn_fwd')
+        _count(2 if impl != 1 else 1)
+        ctx.save_for_backward(x, Wkn)
+        ctx.K, ctx.impl, ctx.has_b = K, impl, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, Wkn = ctx.saved_tensors
+        K, impl = ctx.K, ctx.impl
+        M, N = x.shape[0], Wkn.shape[1]
+        g = _rowmajor(g)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((M, x.shape[1]), dtype=torch.float32, device=x.device)
+            if x.shape[1] > K:
+                dx[:, K:].zero_()
+        dW = torch.zeros_like(Wkn)
+        db = torch.zeros((N,), dtype=torch.float32, device=x.device) if ctx.has_b else None
+        check(_lib.load().rpb_matmul_kn_bwd(_ptr(g), g.stride(0), _ptr(x), x.stride(0), _ptr(Wkn), Wkn.stride(0), _ptr(dx),
+                                            dx.stride(0) if dx is not None else 0, _ptr(dW), _ptr(db), M, N, K, impl,
+                                            _stream()), 'rpb_matmul_kn_bwd')
+        _count(4)
+        return dx, None, dW, db, None
+
+
+def matmul_kn(x: torch.Tensor, Wkn: torch.Tensor, bias: Optional[torch.Tensor], K: Optional[int] = None,
+              impl: Optional[int] = None) -> torch.Tensor:
+    """x[:, :K] @ Wkn[K, N] + bias -> [M, round_up(N,4)] (pad columns zero)."""
+    _cuda(x, 'matmul input')
+    x = _rowmajor(x.float() if x.dtype != torch.float32 else x)
+    K = Wkn.shape[0] if K is None else K
+    return _MatmulKN.apply(x, K, Wkn if Wkn.is_contiguous() else Wkn.contiguous(), bias,
+                           _GEMM_IMPL if impl is None else impl)
+
+
+class _MMOECombine(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, eo, Hh, E, T):
+        B = eo.shape[0]
+        out = torch.empty((T, B, Hh), dtype=torch.float32, device=eo.device)
+        gate = torch.empty((B, T * E), dtype=torch.float32, device=eo.device)
+        check(_lib.load().rpb_mmoe_combine_fwd(_ptr(eo), eo.stride(0), B, Hh, E, T, _ptr(out), _ptr(gate), _stream()),
+              'rpb_mmoe_combine_fwd')
+        _count()
+        ctx.dims = (Hh, E, T)
+        ctx.save_for_backward(eo, gate)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        eo, gate = ctx.saved_tensors
+        Hh, E, T = ctx.dims
+        B = eo.shape[0]
+        g = g.contiguous()
+        deo = torch.empty_like(eo)
+        check(_lib.load().rpb_mmoe_combine_bwd(_ptr(eo), eo.stride(0), _ptr(gate), _ptr(g), B, Hh, E, T, _ptr(deo),
+                                               deo.stride(0), _stream()), 'rpb_mmoe_combine_bwd')
+        _count()
+        return deo, None, None, None
+
+
+def mmoe_combine(eo: torch.Tensor, Hh: int, E: int, T: int) -> torch.Tensor:
+    """Gate softmax + gated sum over experts (mmoe.py:90-104): eo [B, >= Hh*E + T*E] -> [T, B, Hh]."""
+    _cuda(eo, 'experts_out')
+    return _MMOECombine.apply(_rowmajor(eo), Hh, E, T)
+
+
+class _BatchNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, training, momentum, eps):
+        M, N = x.shape
+        lib, st = _lib.load(), _stream()
+        if training:
+            stats = torch.zeros((2, N), dtype=torch.float32, device=x.device)
+            check(lib.rpb_bn_stats(_ptr(x), M, N, _ptr(stats[0]), _ptr(stats[1]), st), 'rpb_bn_stats')
+            _count()
+            mean = stats[0] / M
+            var = (stats[1] / M - mean * mean).clamp_min_(0.0)           # biased (normalisation) variance; [N]-sized plumbing
+            with torch.no_grad():
+                running_mean.mul_(1 - momentum).add_(mean, alpha=momentum)
+                running_var.mul_(1 - momentum).add_(var * (M / max(M - 1, 1)), alpha=momentum)
+        else:
+            mean, var = running_mean, running_var
+        invstd = torch.rsqrt(var + eps)
+        y = torch.empty_like(x)
+        check(lib.rpb_bn_apply(_ptr(x), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(beta), _ptr(y), M, N, st), 'rpb_bn_apply')
+        _count()
+        ctx.save_for_backward(x, gamma, mean.contiguous(), invstd)
+        ctx.training = training
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, gamma, mean, invstd = ctx.saved_tensors
+        M, N = x.shape
+        g = g.contiguous()
+        dx = torch.empty_like(x)
+        dgb = torch.zeros((2, N), dtype=torch.float32, device=x.device)
+        check(_lib.load().rpb_bn_bwd(_ptr(g), _ptr(x), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(dx), _ptr(dgb[0]),
+                                     _ptr(dgb[1]), M, N, 1 if ctx.training else 0, _stream()), 'rpb_bn_bwd')
+        _count(2)
+        return dx, dgb[0], dgb[1], None, None, None, None, None
+
+
+def batch_norm(x: torch.Tensor, bn: torch.nn.BatchNorm1d, training: bool) -> torch.Tensor:
+    """nn.BatchNorm1d (mmoe.py:54-56) on a contiguous [M, N] CUDA tensor; updates running stats in training mode."""
+    _cuda(x, 'batch-norm input')
+    if training and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    return _BatchNorm.apply(x.contiguous(), bn.weight, bn.bias, bn.running_mean, bn.running_var, training,
+                            bn.momentum if bn.momentum is not None else 0.1, bn.eps)
+
+
+class _Dropout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p, seed):
+        y = torch.empty_like(x)
+        check(_lib.load().rpb_dropout_fwd(_ptr(x), _ptr(y), x.numel(), p, seed, _stream()), 'rpb_dropout_fwd')
+        _count()
+        ctx.p, ctx.seed = p, seed
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        dx = torch.empty_like(g)
+        check(_lib.load().rpb_dropout_bwd(_ptr(g), None, _ptr(dx), g.numel(), ctx.p, ctx.seed, _stream()), 'rpb_dropout_bwd')
+        _count()
+        return dx, None, None
+
+
+def dropout(x: torch.Tensor, p: float, training: bool) -> torch.Tensor:
+    """nn.Dropout (counter-based mask, recomputed in backward)."""
+    if not training or p <= 0.0:
+        return x
+    return _Dropout.apply(x.contiguous(), float(p), int(torch.randint(0, 2 ** 62, (1,)).item()))
