@@ -189,19 +189,15 @@ def run_ours(args):
     model.set_grad_mode('persistent')
     model.train()
 
-    # data-parallel replicas: dense (MLP) grads are all-reduced inside the step; see DESIGN.md §multi-GPU
-    dense_params = [p for n, p in model.named_parameters() if not n.startswith('embedding_layer.')]
-    post = None
+    # N > 1: batch-parallel ranks, tables row-sharded over the GPUs in NVLink peer memory (the lookup and
+    # the gradient scatter cross NVLink inside the gather/scatter kernels), dense grads summed with one NCCL all-reduce.
+    post, loss_scale, st = None, 1.0, None
     if world > 1:
-        flat = torch.zeros(sum(p.numel() for p in dense_params), device=dev)
-
-        def post():
-            off = 0
-            for p in dense_params:
-                flat[off:off + p.numel()].copy_(p.grad.reshape(-1))
-                off += p.numel()
-            dist.all_reduce(flat)
-            flat.mul_(1.0 / world)
+        from rec_pangu_b200 import dist as rdist
+        st = rdist.shard_model_tables(model)
+        torch.cuda.empty_cache()
+        bucket = rdist.DenseGradBucket([p for n, p in model.named_parameters() if not n.startswith('embedding_layer.')])
+        post, loss_scale = bucket.all_reduce, 1.0 / world
 
     NB = 4
     gen = torch.Generator(device=dev).manual_seed(SEED + rank)
@@ -214,13 +210,13 @@ def run_ours(args):
     launch_mode = 'cuda_graph' if use_graph else 'eager'
     try:
         for cb in cbs:
-            steps_g.append(GraphedStep(model, cb, post=post, use_graph=use_graph))
+            steps_g.append(GraphedStep(model, cb, post=post, use_graph=use_graph, loss_scale=loss_scale))
     except Exception as e:      # capture not possible: time the eager path instead (still the same kernels)
         if rank == 0:
             print(f'[bench] CUDA-graph capture failed ({e!r}); falling back to eager launches', file=sys.stderr)
         launch_mode = 'eager'
         torch.cuda.synchronize()
-        steps_g = [GraphedStep(model, cb, post=post, use_graph=False) for cb in cbs]
+        steps_g = [GraphedStep(model, cb, post=post, use_graph=False, loss_scale=loss_scale) for cb in cbs]
     ops.check_index_errors(dev)
     launches_per_step = steps_g[0].launches_per_step
 
@@ -273,34 +269,37 @@ def run_ours(args):
     e2e = {'value': world * B * args.steps / (ms_e2e * 1e-3), 'unit': 'samples/s', 'h2d_bytes_per_step': h2d,
            'd2h_bytes_per_step': 4, 'loss': lossv}
 
-    # ---------------- roofline of the dominant memory kernel: the fused gather+FM forward (rpb_gather_fwd)
-    tables = model.embedding_layer.tables()
-    gg = []
-    with torch.no_grad():
-        for cb in cbs:
-            d = cb.as_dict()
-            idx = [d[c] for c in model.embedding_layer.emb_feature]
-            dn = [d[c] for c in model.embedding_layer.dense_feature]
-            ops.gather(tables, idx, dn, want_fm=True)
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+    roofline = None
+    if world == 1:
+        # ---------------- roofline of the dominant memory kernel: the fused gather+FM forward (rpb_gather_fwd)
+        tables = model.embedding_layer.tables()
+        gg = []
+        with torch.no_grad():
+            for cb in cbs:
+                d = cb.as_dict()
+                idx = [d[c] for c in model.embedding_layer.emb_feature]
+                dn = [d[c] for c in model.embedding_layer.dense_feature]
                 ops.gather(tables, idx, dn, want_fm=True)
-            gg.append(g)
-    for i in range(3):
-        gg[i % NB].replay()
-    torch.cuda.synchronize()
-    e0.record()
-    for i in range(args.steps):
-        gg[i % NB].replay()
-    e1.record()
-    torch.cuda.synchronize()
-    us_gather = e0.elapsed_time(e1) * 1e3 / args.steps
-    peak, peak_src = measured_peaks()
-    achieved = ALG_BYTES_PER_SAMPLE * B / (us_gather * 1e-6) / 1e9
-    roofline = {'kernel': 'gather_fwd_kernel (multi-table gather + dense pack + FM second order)', 'bound': 'hbm',
-                'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
-                'us_per_launch': us_gather, 'alg_bytes_per_launch': ALG_BYTES_PER_SAMPLE * B, 'peak_source': peak_src}
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    ops.gather(tables, idx, dn, want_fm=True)
+                gg.append(g)
+        for i in range(3):
+            gg[i % NB].replay()
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(args.steps):
+            gg[i % NB].replay()
+        e1.record()
+        torch.cuda.synchronize()
+        us_gather = e0.elapsed_time(e1) * 1e3 / args.steps
+        peak, peak_src = measured_peaks()
+        achieved = ALG_BYTES_PER_SAMPLE * B / (us_gather * 1e-6) / 1e9
+        roofline = {'kernel': 'gather_fwd_kernel (multi-table gather + dense pack + FM second order)', 'bound': 'hbm',
+                    'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                    'us_per_launch': us_gather, 'alg_bytes_per_launch': ALG_BYTES_PER_SAMPLE * B, 'peak_source': peak_src}
+
 
     line = {
         'metric': 'DeepFM samples/sec (forward+backward hot path)', 'value': value, 'unit': 'samples/s',
@@ -308,10 +307,11 @@ def run_ours(args):
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': 'DeepFM criteo-shape: 26 sparse x 1M-row tables (D=16) + 13 dense, MLP 64-64-64, '
                                'fwd + bwd (dense per-table grads, sparse re-zero), BASELINE.json configs[1]',
-                   'batch_per_gpu': B, 'global_batch': B * world, 'parallelism': f'dp{world}' if world > 1 else 'single',
+                   'batch_per_gpu': B, 'global_batch': B * world, 'parallelism': (f'dp{world}: batch-parallel ranks, tables row-sharded in NVLink peer memory (fused P2P gather/scatter), '
+                                   f'dense grads NCCL all-reduce') if world > 1 else 'single',
                    'launch': launch_mode, 'l2': 'inputs larger than L2: 4 rotating batches over 1.66 GB of tables',
                    'gemm': {0: 'auto(tcgen05 3xTF32)', 1: 'simt fp32', 2: 'tcgen05 3xTF32'}[ops.get_gemm_impl()],
-                   'grad_mode': 'persistent'},
+                   'grad_mode': 'persistent' if world == 1 else 'sharded'},
         'e2e': e2e, 'gpu_launches': launches_per_step * args.steps, 'clocks': clocks, 'roofline': roofline,
     }
     if rank == 0:

@@ -33,7 +33,8 @@ extern "C" {
 /* ABI version; bumped whenever a signature changes. */
 int rpb_version(void);
 /* Tuning knobs (process-wide): "gather_load_policy" 0 = L1 no-allocate row loads, 1 = + L2 64-byte fetch cap (default),
- * 2 = cached read-only loads;  "l2_fetch_granularity" = 32|64|128 (cudaLimitMaxL2FetchGranularity). */
+ * 2 = cached read-only loads, 3 = measurement-only (no x write);  "gather_kernel" 0 = shared-memory tile + bulk
+ * store (default), 1 = direct stores;  "l2_fetch_granularity" = 32|64|128 (cudaLimitMaxL2FetchGranularity). */
 int rpb_set_option(const char* name, int64_t value);
 /* Last error text for negative codes (static string). */
 const char* rpb_error_string(int code);
@@ -62,6 +63,13 @@ typedef struct RpbGatherDesc {
     float* fm_s;                    /* out [B, D]: sum_f e (saved for backward), or NULL */
     float* lr_in;                   /* out [B, ld_lr]: [lr_table_f[idx_f] (F) | dense (Nd)], or NULL */
     int64_t* err;                   /* device-visible int64[4] error record (see above) */
+    /* Row-sharded tables over G GPUs of one NVLink domain (BASELINE.json config 5): owner = id mod G, local row =
+     * id div G.  shard_tab is a DEVICE array [F*G] of shard base pointers, entry f*G+g = rank g's shard of table f
+     * (float[ceil(rows[f]/G)][D]) mapped into this process (NVLink peer memory); the kernel reads remote rows
+     * directly, so the lookup all-to-all is fused into the gather.  G <= 1: unsharded, `tables` is used.
+     * rows[] stay the GLOBAL row counts (bounds check).  LR tables are not supported together with sharding. */
+    int32_t G;
+    const float* const* shard_tab;
 } RpbGatherDesc;
 int rpb_gather_fwd(const RpbGatherDesc* d, void* stream);
 
@@ -82,6 +90,10 @@ typedef struct RpbScatterDesc {
     const float* dfm;               /* [B] grad wrt fm, or NULL */
     const float* fm_s;              /* [B, D] saved sum_f e (needed iff dfm) */
     const float* dlr_in;            /* [B, ld_dlr] grad wrt lr_in (first F columns used), or NULL */
+    /* Row-sharded gradient buffers (see RpbGatherDesc.G): DEVICE array [F*G] of grad-shard base pointers; remote
+     * shards receive fp32 vector reductions over NVLink.  G <= 1: `grads` is used. */
+    int32_t G;
+    float* const* grad_shard_tab;
 } RpbScatterDesc;
 int rpb_gather_bwd(const RpbScatterDesc* d, void* stream);
 /* Sparse zero_grad for persistent dense-grad buffers: grads[f][idx[f][b], :] = 0 and lr_grads[f][idx[f][b]] = 0

@@ -7,7 +7,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'librec_pangu_b200.so')
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_FIELDS = 64
 MAX_DENSE = 64
 
@@ -21,13 +21,14 @@ class GatherDesc(C.Structure):
     _fields_ = [('B', _i32), ('F', _i32), ('D', _i32), ('Nd', _i32), ('ldx', _i32), ('ld_lr', _i32),
                 ('tables', C.POINTER(_vp)), ('rows', C.POINTER(_i64)), ('idx', C.POINTER(_vp)),
                 ('dense', C.POINTER(_vp)), ('lr_tables', C.POINTER(_vp)),
-                ('x', _vp), ('fm', _vp), ('fm_s', _vp), ('lr_in', _vp), ('err', _vp)]
+                ('x', _vp), ('fm', _vp), ('fm_s', _vp), ('lr_in', _vp), ('err', _vp), ('G', _i32), ('shard_tab', _vp)]
 
 
 class ScatterDesc(C.Structure):
     _fields_ = [('B', _i32), ('F', _i32), ('D', _i32), ('lddx', _i32), ('ldx', _i32), ('ld_dlr', _i32),
                 ('grads', C.POINTER(_vp)), ('lr_grads', C.POINTER(_vp)), ('rows', C.POINTER(_i64)),
-                ('idx', C.POINTER(_vp)), ('dx', _vp), ('x', _vp), ('dfm', _vp), ('fm_s', _vp), ('dlr_in', _vp)]
+                ('idx', C.POINTER(_vp)), ('dx', _vp), ('x', _vp), ('dfm', _vp), ('fm_s', _vp), ('dlr_in', _vp),
+                ('G', _i32), ('grad_shard_tab', _vp)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/rec_pangu_b200.h (tests check this)

@@ -6,6 +6,7 @@
 namespace rpb {
 
 int g_gather_policy = 1;
+int g_gather_kernel = 0;
 
 // Grow-only per-device scratch buffers (slot = call site).  Kernels of one stream that share a slot are ordered by
 // the stream, so reuse is safe for the single-stream execution model of the reference's training loop.  Growth uses
@@ -35,7 +36,7 @@ void* workspace(int slot, size_t bytes, int* err) {
 
 }  // namespace rpb
 
-RPB_API int rpb_version(void) { return 1; }
+RPB_API int rpb_version(void) { return 2; }
 
 RPB_API const char* rpb_error_string(int code) {
     switch (code) {
@@ -51,8 +52,13 @@ RPB_API int rpb_set_option(const char* name, int64_t value) {
     if (name == nullptr) return RPB_ERR_BAD_ARG;
     const std::string n(name);
     if (n == "gather_load_policy") {
-        if (value < 0 || value > 2) return RPB_ERR_BAD_ARG;
+        if (value < 0 || value > 3) return RPB_ERR_BAD_ARG;   // 3 = measurement-only variant without the x write
         rpb::g_gather_policy = (int)value;
+        return 0;
+    }
+    if (n == "gather_kernel") {
+        if (value < 0 || value > 1) return RPB_ERR_BAD_ARG;
+        rpb::g_gather_kernel = (int)value;
         return 0;
     }
     if (n == "l2_fetch_granularity") {          // bytes: 32, 64 or 128 (cudaLimitMaxL2FetchGranularity, device-wide hint)

@@ -26,8 +26,20 @@ struct GatherFwdParams {
     float* fm_s;
     float* lr_in;
     long long* err;
-    int B, F, D, Nd, ldx, ld_lr;
+    const float* const* shard_tab;     // device array [F*G] of shard base pointers (row-sharded tables), or nullptr
+    int B, F, D, Nd, ldx, ld_lr, G;
 };
+
+// Row-sharded tables (owner = id mod G, local row = id div G; oracle/index_routing.py::shard_route): the shard of
+// another GPU is read directly through its NVLink peer mapping — the lookup "all-to-all" is fused into the gather.
+__device__ __forceinline__ const float* table_row(const GatherFwdParams& p, int f, long long ix, int D) {
+    if (p.G > 1) {
+        const unsigned u = (unsigned)ix, g = (unsigned)p.G;
+        const float* base = reinterpret_cast<const float*>(__ldg(reinterpret_cast<const unsigned long long*>(p.shard_tab) + (size_t)f * g + (u % g)));
+        return base + (size_t)(u / g) * D;
+    }
+    return p.tables[f] + (size_t)ix * D;
+}
 
 template <int VEC> struct Vec;
 template <> struct Vec<4> {
@@ -36,7 +48,7 @@ template <> struct Vec<4> {
     __device__ __forceinline__ void load_stream(const float* p) { v = ldg_f4_stream(p); }
     template <int POLICY> __device__ __forceinline__ void load_row(const float* p) {
         if constexpr (POLICY == 0) v = ldg_f4_stream(p);
-        else if constexpr (POLICY == 1) v = ldg_f4_stream64(p);
+        else if constexpr (POLICY == 1 || POLICY == 3) v = ldg_f4_stream64(p);
         else v = ldg_f4(p);
     }
     __device__ __forceinline__ void load(const float* p) { v = ldg_f4(p); }
@@ -117,7 +129,7 @@ gather_fwd_kernel(const __grid_constant__ GatherFwdParams p) {
             e[u].zero();
             lrv[u] = 0.f;
             if (f < p.F) {
-                if (lane_on) e[u].template load_row<POLICY>(p.tables[f] + (size_t)ix[u] * p.D + l * VEC);
+                if (lane_on) e[u].template load_row<POLICY>(table_row(p, f, ix[u], p.D) + l * VEC);
                 if (HAS_LR && (f % LPR) == l) lrv[u] = __ldg(p.lr_tables[f] + ix[u]);
             }
         }
@@ -125,7 +137,7 @@ gather_fwd_kernel(const __grid_constant__ GatherFwdParams p) {
         for (int u = 0; u < U; ++u) {
             const int f = f0 + u;
             if (f < p.F) {
-                if (lane_on && valid) e[u].store(xrow + f * p.D + l * VEC);
+                if (lane_on && valid && POLICY != 3) e[u].store(xrow + f * p.D + l * VEC);   // 3 = experiment: no x write
                 s.add(e[u]);
                 q.add_sq(e[u]);
                 if (HAS_LR && valid && (f % LPR) == l) p.lr_in[(size_t)b * p.ld_lr + f] = lrv[u];
@@ -151,6 +163,100 @@ gather_fwd_kernel(const __grid_constant__ GatherFwdParams p) {
     }
 }
 
+
+// ---------------------------------------------------------------- tile variant (default): staged through shared memory
+// CTA = 128 threads = S samples (S = 128/LPR).  (1) the [F x S] index tile is fetched with fully coalesced 8-byte
+// loads into shared memory (one exposed latency instead of one per field chunk), (2) every lane then has U independent
+// 16-byte row loads in flight per chunk, rows are written into a shared-memory copy of the output tile, (3) the tile —
+// S complete feature rows, contiguous in x — leaves with ONE asynchronous bulk copy (cp.async.bulk, the TMA engine),
+// so the 113 MB of x writes cost no LSU issue slots and no partial-line traffic.
+__device__ __forceinline__ void bulk_store_tile(float* gdst, const float* ssrc, unsigned bytes) {
+    const unsigned saddr = (unsigned)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(saddr), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+template <int LPR, int U, bool HAS_LR>
+__global__ void __launch_bounds__(128)
+gather_fwd_tile_kernel(const __grid_constant__ GatherFwdParams p) {
+    constexpr int S = 128 / LPR;
+    extern __shared__ __align__(128) unsigned char tile_raw[];
+    float* xs = reinterpret_cast<float*>(tile_raw);                         // [S][ldx]
+    long long* is = reinterpret_cast<long long*>(tile_raw + (size_t)S * p.ldx * sizeof(float));   // [F][S]
+    const int tid = threadIdx.x;
+    const int b0 = blockIdx.x * S;
+    const int ns = min(S, p.B - b0);
+
+    for (int i = tid; i < p.F * S; i += 128) {
+        const int f = i / S, s = i % S;
+        long long v = 0;
+        if (s < ns) {
+            v = __ldg(p.idx[f] + b0 + s);
+            if ((unsigned long long)v >= (unsigned long long)p.rows[f]) { report_bad_index(p.err, f, b0 + s, v); v = 0; }
+        }
+        is[i] = v;
+    }
+    const int FD = p.F * p.D;
+    for (int i = tid; i < p.Nd * S; i += 128) {
+        const int j = i / S, s = i % S;
+        const float dv = (s < ns) ? __ldg(p.dense[j] + b0 + s) : 0.f;
+        xs[(size_t)s * p.ldx + FD + j] = dv;
+        if (HAS_LR && s < ns) p.lr_in[(size_t)(b0 + s) * p.ld_lr + p.F + j] = dv;
+    }
+    for (int i = tid; i < (p.ldx - FD - p.Nd) * S; i += 128) {
+        const int j = i / S, s = i % S;
+        xs[(size_t)s * p.ldx + FD + p.Nd + j] = 0.f;
+    }
+    __syncthreads();
+
+    const int s = tid / LPR, l = tid % LPR;
+    const bool valid = s < ns;
+    const int b = b0 + (valid ? s : 0);
+    const bool lane_on = l < p.D / 4;
+    float* xrow = xs + (size_t)s * p.ldx;
+    Vec<4> sum, sq;
+    sum.zero(); sq.zero();
+    for (int f0 = 0; f0 < p.F; f0 += U) {
+        Vec<4> e[U];
+        float lrv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int f = f0 + u;
+            e[u].zero();
+            lrv[u] = 0.f;
+            if (f < p.F) {
+                const long long ix = is[f * S + s];
+                if (lane_on) e[u].template load_row<1>(table_row(p, f, ix, p.D) + l * 4);
+                if (HAS_LR && (f % LPR) == l) lrv[u] = __ldg(p.lr_tables[f] + ix);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int f = f0 + u;
+            if (f < p.F) {
+                if (lane_on) *reinterpret_cast<float4*>(xrow + f * p.D + l * 4) = e[u].v;
+                sum.add(e[u]);
+                sq.add_sq(e[u]);
+                if (HAS_LR && valid && (f % LPR) == l) p.lr_in[(size_t)b * p.ld_lr + f] = lrv[u];
+            }
+        }
+    }
+    if (valid) {
+        if (HAS_LR) for (int j = p.F + p.Nd + l; j < p.ld_lr; j += LPR) p.lr_in[(size_t)b * p.ld_lr + j] = 0.f;
+        if (p.fm_s != nullptr && lane_on) sum.store(p.fm_s + (size_t)b * p.D + l * 4);
+    }
+    if (p.fm != nullptr) {
+        float t = lane_on ? sum.sq_minus(sq) : 0.f;
+        t = group_sum<LPR>(t);
+        if (valid && l == 0) p.fm[b] = 0.5f * t;
+    }
+    // publish the tile: generic-proxy smem writes -> async proxy, then one bulk copy of ns complete rows
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) bulk_store_tile(p.x + (size_t)b0 * p.ldx, xs, (unsigned)((size_t)ns * p.ldx * sizeof(float)));
+}
+
 struct ScatterParams {
     float* grads[RPB_MAX_FIELDS];
     float* lr_grads[RPB_MAX_FIELDS];
@@ -161,8 +267,18 @@ struct ScatterParams {
     const float* dfm;
     const float* fm_s;
     const float* dlr_in;
-    int B, F, D, lddx, ldx, ld_dlr;
+    float* const* grad_shard_tab;      // device array [F*G] of grad-shard base pointers, or nullptr
+    int B, F, D, lddx, ldx, ld_dlr, G;
 };
+
+__device__ __forceinline__ float* grad_row(const ScatterParams& p, int f, long long ix, int D) {
+    if (p.G > 1) {
+        const unsigned u = (unsigned)ix, g = (unsigned)p.G;
+        float* base = reinterpret_cast<float*>(__ldg(reinterpret_cast<const unsigned long long*>(p.grad_shard_tab) + (size_t)f * g + (u % g)));
+        return base + (size_t)(u / g) * D;
+    }
+    return p.grads[f] != nullptr ? p.grads[f] + (size_t)ix * D : nullptr;
+}
 
 template <int VEC, int LPR, int U>
 __global__ void __launch_bounds__(256)
@@ -211,7 +327,10 @@ gather_bwd_kernel(const __grid_constant__ ScatterParams p) {
         for (int u = 0; u < U; ++u) {
             const int f = f0 + u;
             if (f < p.F) {
-                if (lane_on && p.grads[f] != nullptr) g[u].red(p.grads[f] + (size_t)ix[u] * p.D + l * VEC);
+                if (lane_on) {
+                    float* gr = grad_row(p, f, ix[u], p.D);
+                    if (gr != nullptr) g[u].red(gr + l * VEC);
+                }
                 if (p.dlr_in != nullptr && (f % LPR) == l && p.lr_grads[f] != nullptr)
                     red_add_f1(p.lr_grads[f] + ix[u], __ldg(p.dlr_in + (size_t)b * p.ld_dlr + f));
             }
@@ -232,7 +351,10 @@ rows_zero_kernel(const __grid_constant__ ScatterParams p) {
     for (int f = 0; f < p.F; ++f) {
         long long v = __ldg(p.idx[f] + b);
         if ((unsigned long long)v >= (unsigned long long)p.rows[f]) v = 0;
-        if (lane_on && p.grads[f] != nullptr) z.store(p.grads[f] + (size_t)v * p.D + l * VEC);
+        if (lane_on) {
+            float* gr = grad_row(p, f, v, p.D);
+            if (gr != nullptr) z.store(gr + l * VEC);
+        }
         if ((f % LPR) == l && p.lr_grads[f] != nullptr) p.lr_grads[f][v] = 0.f;
     }
 }
@@ -336,23 +458,41 @@ RPB_API int rpb_gather_fwd(const RpbGatherDesc* d, void* stream) {
     GatherFwdParams p{};
     bool aligned = (d->ldx % 4 == 0) && is_aligned16(d->x) && (d->fm_s == nullptr || is_aligned16(d->fm_s));
     for (int f = 0; f < d->F; ++f) {
-        p.tables[f] = d->tables[f];
+        p.tables[f] = d->tables ? d->tables[f] : nullptr;
         p.idx[f] = reinterpret_cast<const long long*>(d->idx[f]);
         p.rows[f] = d->rows[f];
         p.lr_tables[f] = d->lr_tables ? d->lr_tables[f] : nullptr;
-        aligned = aligned && is_aligned16(d->tables[f]);
+        if (d->G <= 1) aligned = aligned && is_aligned16(d->tables[f]);
+        if (d->G > 1 && d->rows[f] > 0xFFFFFFFFll) return RPB_ERR_UNSUPPORTED;
     }
     for (int j = 0; j < d->Nd; ++j) p.dense[j] = d->dense[j];
     p.x = d->x; p.fm = d->fm; p.fm_s = d->fm_s; p.lr_in = d->lr_tables ? d->lr_in : nullptr;
     p.err = reinterpret_cast<long long*>(d->err);
     p.B = d->B; p.F = d->F; p.D = d->D; p.Nd = d->Nd; p.ldx = d->ldx; p.ld_lr = d->ld_lr;
+    p.G = d->G > 1 ? d->G : 1;
+    p.shard_tab = d->shard_tab;
+    if (p.G > 1 && (d->shard_tab == nullptr || d->lr_tables != nullptr)) return RPB_ERR_BAD_ARG;
     if (d->lr_tables && (d->lr_in == nullptr || d->ld_lr < d->F + d->Nd)) return RPB_ERR_BAD_ARG;
     const bool has_lr = d->lr_tables != nullptr;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     return dispatch_shape(d->D, aligned, [&](auto vec, auto lpr) -> int {
         constexpr int VEC = decltype(vec)::value, LPR = decltype(lpr)::value;
-        const int grid = ceil_div((long long)p.B * LPR, 256);
         const int pol = g_gather_policy;
+        if constexpr (VEC == 4 && LPR <= 16) {
+            constexpr int S = 128 / LPR;
+            const size_t smem = (size_t)S * p.ldx * sizeof(float) + (size_t)p.F * S * sizeof(long long);
+            if (g_gather_kernel == 0 && pol == 1 && smem <= 100 * 1024) {
+                auto launch = [&](auto kern) -> int {
+                    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    if (e != cudaSuccess) return (int)e;
+                    kern<<<ceil_div(p.B, S), 128, smem, st>>>(p);
+                    return (int)cudaGetLastError();
+                };
+                if (p.F % 13 == 0) return has_lr ? launch(gather_fwd_tile_kernel<LPR, 13, true>) : launch(gather_fwd_tile_kernel<LPR, 13, false>);
+                return has_lr ? launch(gather_fwd_tile_kernel<LPR, 8, true>) : launch(gather_fwd_tile_kernel<LPR, 8, false>);
+            }
+        }
+        const int grid = ceil_div((long long)p.B * LPR, 256);
         if (has_lr) {
             if (pol == 0) gather_fwd_kernel<VEC, LPR, 8, true, 0><<<grid, 256, 0, st>>>(p);
             else if (pol == 1) gather_fwd_kernel<VEC, LPR, 8, true, 1><<<grid, 256, 0, st>>>(p);
@@ -360,7 +500,8 @@ RPB_API int rpb_gather_fwd(const RpbGatherDesc* d, void* stream) {
         } else {
             if (pol == 0) gather_fwd_kernel<VEC, LPR, 8, false, 0><<<grid, 256, 0, st>>>(p);
             else if (pol == 1) gather_fwd_kernel<VEC, LPR, 8, false, 1><<<grid, 256, 0, st>>>(p);
-            else gather_fwd_kernel<VEC, LPR, 8, false, 2><<<grid, 256, 0, st>>>(p);
+            else if (pol == 2) gather_fwd_kernel<VEC, LPR, 8, false, 2><<<grid, 256, 0, st>>>(p);
+            else gather_fwd_kernel<VEC, LPR, 8, false, 3><<<grid, 256, 0, st>>>(p);
         }
         RPB_LAUNCH_CHECK();
         return 0;
@@ -385,6 +526,9 @@ RPB_API int rpb_gather_bwd(const RpbScatterDesc* d, void* stream) {
     p.dx = d->dx; p.x = d->x; p.dfm = d->dfm; p.fm_s = d->fm_s;
     p.dlr_in = d->lr_grads ? d->dlr_in : nullptr;
     p.B = d->B; p.F = d->F; p.D = d->D; p.lddx = d->lddx; p.ldx = d->ldx; p.ld_dlr = d->ld_dlr;
+    p.G = d->G > 1 ? d->G : 1;
+    p.grad_shard_tab = d->grad_shard_tab;
+    if (p.G > 1 && d->grad_shard_tab == nullptr) return RPB_ERR_BAD_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     return dispatch_shape(d->D, aligned, [&](auto vec, auto lpr) -> int {
         constexpr int VEC = decltype(vec)::value, LPR = decltype(lpr)::value;
@@ -408,6 +552,9 @@ RPB_API int rpb_rows_zero(const RpbScatterDesc* d, void* stream) {
         if (p.grads[f]) aligned = aligned && is_aligned16(p.grads[f]);
     }
     p.B = d->B; p.F = d->F; p.D = d->D;
+    p.G = d->G > 1 ? d->G : 1;
+    p.grad_shard_tab = d->grad_shard_tab;
+    if (p.G > 1 && d->grad_shard_tab == nullptr) return RPB_ERR_BAD_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     return dispatch_shape(d->D, aligned, [&](auto vec, auto lpr) -> int {
         constexpr int VEC = decltype(vec)::value, LPR = decltype(lpr)::value;

@@ -121,10 +121,14 @@ mmoe_combine_fwd_kernel(const float* __restrict__ eo, long long ld, int B, int H
         const float sum = warp_sum(ex);
         const float g = ex / sum;
         if (lane < E) gate[(size_t)b * T * E + t * E + lane] = g;
-        for (int k = lane; k < Hh; k += 32) {
+        for (int k0 = 0; k0 < Hh; k0 += 32) {          // warp-uniform trip count: the shuffles below need all lanes
+            const int k = k0 + lane;
             float acc = 0.f;
-            for (int l = 0; l < E; ++l) acc = fmaf(__ldg(row + k * E + l), __shfl_sync(0xffffffffu, g, l), acc);
-            out[((size_t)t * B + b) * Hh + k] = acc;
+            for (int l = 0; l < E; ++l) {
+                const float gl = __shfl_sync(0xffffffffu, g, l);
+                if (k < Hh) acc = fmaf(__ldg(row + k * E + l), gl, acc);
+            }
+            if (k < Hh) out[((size_t)t * B + b) * Hh + k] = acc;
         }
     }
 }

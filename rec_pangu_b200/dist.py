@@ -1,0 +1,161 @@
+"""Multi-GPU execution of the hot path: one process per GPU (torchrun), NCCL for the plumbing collectives,
+row-sharded embedding tables in NVLink peer memory for the lookup.
+
+Design.  The reference is single-device; the path shards on the batch axis and on
+table rows:
+
+* batch: every rank runs the model on its own B samples (weak scaling); dense (MLP / interaction) gradients are
+  averaged with one NCCL all-reduce over a flat bucket;
+* tables: each table is ROW-SHARDED over the G GPUs (owner = id mod G, local row = id div G — the integer contract of
+  oracle/index_routing.py).  Shards live in symmetric memory (torch.distributed._symmetric_memory: CUDA VMM + NVLink
+  peer mappings), so the gather kernel reads a remote row with a plain load over NVLink and the scatter kernel adds a
+  remote gradient row with a vector reduction over NVLink: the index/row all-to-all of a classical sharded lookup is
+  FUSED into the gather/scatter kernels — no bucketing, no host-visible counts, no separate collective.  NVSwitch gives
+  every peer full bandwidth, so the uniform `mod G` placement is also the load-balanced one.
+* the only synchronisation is a device-side barrier (NCCL all-reduce of one word on the compute stream) after backward
+  (all remote gradient adds have landed) and after zero_grad / optimizer (tables and grad shards are consistent again).
+"""
+import os
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend: Optional[str] = None) -> (int, int, int):
+    """(rank, world, local_rank) from torchrun's environment; initialises the default process group if needed."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+        kw = {}
+        if backend == 'nccl':
+            torch.cuda.set_device(local)
+            kw['device_id'] = torch.device('cuda', local)
+        dist.init_process_group(backend, **kw)
+    return rank, world, local
+
+
+def shard_rows(rows: int, world: int) -> int:
+    """Rows per shard (identical on every rank; the tail of the last shards is padding)."""
+    return (rows + world - 1) // world
+
+
+def local_slice(full: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    """Rows owned by `rank` under owner = id mod G: full[rank::G], zero-padded to shard_rows."""
+    sl = full[rank::world]
+    n = shard_rows(full.shape[0], world)
+    if sl.shape[0] < n:
+        sl = torch.cat([sl, sl.new_zeros((n - sl.shape[0],) + tuple(sl.shape[1:]))], dim=0)
+    return sl.contiguous()
+
+
+def unshard(shards: List[torch.Tensor], rows: int) -> torch.Tensor:
+    """Inverse of local_slice over all ranks' shards -> the full [rows, D] table (for state_dict round trips)."""
+    world = len(shards)
+    out = shards[0].new_empty((rows,) + tuple(shards[0].shape[1:]))
+    for r, s in enumerate(shards):
+        n = len(range(r, rows, world))
+        out[r::world] = s[:n]
+    return out
+
+
+class DenseGradBucket:
+    """Flat bucket for the non-embedding parameters: copy grads in, one all-reduce(sum), copy back.
+
+    Convention for data-parallel steps: every rank back-propagates ``loss / world`` (its loss is the mean over its own
+    batch), so that summed gradients — both these dense ones and the table gradients that the scatter kernel adds
+    straight into the owners' shards — equal the gradient of the mean loss over the global batch."""
+
+    def __init__(self, params: List[torch.nn.Parameter], group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device if self.params else 'cpu'
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+
+    def all_reduce(self, average: bool = False):
+        if self.world == 1 or not self.params:
+            return
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            if p.grad is not None:
+                self.flat[off:off + n].copy_(p.grad.reshape(-1))
+            else:
+                self.flat[off:off + n].zero_()
+            off += n
+        dist.all_reduce(self.flat, group=self.group)
+        if average:
+            self.flat.mul_(1.0 / self.world)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            if p.grad is not None:
+                p.grad.copy_(self.flat[off:off + n].view_as(p.grad))
+            off += n
+
+
+class ShardedTables:
+    """Row-sharded embedding tables + gradient shards of one EmbeddingLayer in symmetric (peer-mapped) memory."""
+
+    def __init__(self, emb_layer, group=None, full_tables: Optional[Dict[str, torch.Tensor]] = None):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.cols = list(emb_layer.emb_feature)
+        self.D = emb_layer.embedding_dim
+        dev = torch.device('cuda', torch.cuda.current_device())
+        self.rows = [int(emb_layer.enc_dict[c]['vocab_size']) + 1 for c in self.cols]
+        F, G = len(self.cols), self.world
+        self.weights, self.grads, self._handles = [], [], []
+        w_ptrs = torch.zeros(F * G, dtype=torch.int64)
+        g_ptrs = torch.zeros(F * G, dtype=torch.int64)
+        for f, c in enumerate(self.cols):
+            n = shard_rows(self.rows[f], G)
+            w = symm.empty((n, self.D), dtype=torch.float32, device=dev)
+            g = symm.empty((n, self.D), dtype=torch.float32, device=dev)
+            hw = symm.rendezvous(w, self.group)
+            hg = symm.rendezvous(g, self.group)
+            src = full_tables[c] if full_tables is not None else emb_layer.embedding_layer[c].weight.data
+            w.copy_(local_slice(src.to(dev), self.rank, G))
+            g.zero_()
+            for r in range(G):
+                w_ptrs[f * G + r] = int(hw.buffer_ptrs[r])
+                g_ptrs[f * G + r] = int(hg.buffer_ptrs[r])
+            self.weights.append(w)
+            self.grads.append(g)
+            self._handles += [hw, hg]
+        self.w_tab = w_ptrs.to(dev)
+        self.g_tab = g_ptrs.to(dev)
+        self._one = torch.zeros(1, device=dev)
+        self.pending = []            # idx lists of backward passes whose touched grad rows still need re-zeroing
+        self.barrier()
+
+    def barrier(self):
+        """Device-side barrier on the current stream (graph-capturable)."""
+        dist.all_reduce(self._one, group=self.group)
+
+    def full_table(self, f: int) -> torch.Tensor:
+        """All-gather the shards of table f and re-interleave them (checkpointing / tests)."""
+        shards = [torch.empty_like(self.weights[f]) for _ in range(self.world)]
+        dist.all_gather(shards, self.weights[f], group=self.group)
+        return unshard(shards, self.rows[f])
+
+    def full_grad(self, f: int) -> torch.Tensor:
+        shards = [torch.empty_like(self.grads[f]) for _ in range(self.world)]
+        dist.all_gather(shards, self.grads[f], group=self.group)
+        return unshard(shards, self.rows[f])
+
+
+def shard_model_tables(model, group=None) -> ShardedTables:
+    """Convert `model.embedding_layer` to row-sharded peer-memory tables (every rank must hold identical full tables
+    when this is called, e.g. same seed).  The full tables are released afterwards."""
+    emb = model.embedding_layer
+    st = ShardedTables(emb, group)
+    emb.attach_shards(st)
+    return st

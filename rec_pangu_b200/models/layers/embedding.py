@@ -28,6 +28,15 @@ class EmbeddingLayer(nn.Module):
         # contents, O(batch) instead of O(vocabulary) traffic per step.
         self.grad_mode = 'dense'
         self._grad_store = ops.GradStore()
+        self._shards = None                # dist.ShardedTables when the tables are row-sharded over several GPUs
+
+    def attach_shards(self, st):
+        """Switch to row-sharded tables in NVLink peer memory (rec_pangu_b200.dist.shard_model_tables): each
+        nn.Embedding container now holds only this rank's shard [ceil(rows/G), D] as its Parameter."""
+        self._shards = st
+        for f, c in enumerate(self.emb_feature):
+            trainable = self.embedding_layer[c].weight.requires_grad
+            self.embedding_layer[c].weight = nn.Parameter(st.weights[f], requires_grad=trainable)
 
     def set_weights(self, col_name: str, embedding_matrix: torch.Tensor, trainable: Optional[bool] = True) -> None:
         """embedding.py:36-47."""
@@ -44,12 +53,18 @@ class EmbeddingLayer(nn.Module):
         x = [emb_0 | ... | emb_{F-1} | dense_0..dense_{Nd-1} | 0-pad] (see include/rec_pangu_b200.h)."""
         idx = [X[c] for c in self.emb_feature]
         dense = [X[c] for c in self.dense_feature] if with_dense else []
+        if self._shards is not None:
+            if lr_tables is not None:
+                raise NotImplementedError('LR (D=1) tables together with row-sharded embedding tables')
+            return ops.gather_sharded(self._shards, self.tables(), idx, dense, want_fm=want_fm)
         return ops.gather(self.tables(), idx, dense, lr_tables=lr_tables, want_fm=want_fm,
                           grad_store=self._grad_store if self.grad_mode == 'persistent' else None)
 
     def clean_grads(self):
         """Sparse re-zero of the persistent grad buffers (no-op in 'dense' mode)."""
         self._grad_store.clean()
+        if self._shards is not None:
+            ops.sharded_clean(self._shards)
 
     def forward(self, X: Dict[str, torch.Tensor], name: Optional[str] = None) -> torch.Tensor:
         """[B, F, D] (name=None) — embedding.py:58-63; a strided view of the feature row, no stack copy."""

@@ -12,7 +12,7 @@ import torch
 from . import _lib
 from ._lib import GatherDesc, ScatterDesc, check
 
-__all__ = ['GradStore', 'gather', 'fm_interaction', 'mlp_forward', 'sigmoid_bce', 'linear', 'feature_row_stride',
+__all__ = ['GradStore', 'gather', 'gather_sharded', 'sharded_clean', 'fm_interaction', 'mlp_forward', 'sigmoid_bce', 'linear', 'feature_row_stride',
            'check_index_errors', 'set_gemm_impl', 'get_gemm_impl', 'launch_count', 'reset_launch_count']
 
 _GEMM_IMPL = int(__import__('os').environ.get('RPB_GEMM_IMPL', '0'))   # 0 auto, 1 SIMT fp32, 2 tcgen05 3xTF32
@@ -320,6 +320,104 @@ def gather(tables: Sequence[torch.Tensor], idx: Sequence[torch.Tensor], dense: S
     if has_lr:
         lr_in = outs[k]
     return x, fm, lr_in
+
+
+class _GatherSharded(torch.autograd.Function):
+    """Gather over row-sharded tables in NVLink peer memory (dist.ShardedTables).  Gradients are reduced straight into
+    the owners' gradient shards by the scatter kernel; after the device barrier each local shard's .grad is published."""
+
+    @staticmethod
+    def forward(ctx, st, want_fm, n_idx, *tensors):
+        F, D, G = len(st.cols), st.D, st.world
+        params = tensors[:F]                       # local shard Parameters (autograd anchors)
+        idx = tensors[F:F + n_idx]
+        dense = tensors[F + n_idx:]
+        Nd = len(dense)
+        dev = idx[0].device
+        B = idx[0].shape[0]
+        ldx = feature_row_stride(F, D, Nd)
+        x = torch.empty((B, ldx), dtype=torch.float32, device=dev)
+        need_grad = any(p.requires_grad for p in params) and torch.is_grad_enabled()
+        fm = torch.empty((B,), dtype=torch.float32, device=dev) if want_fm else None
+        fm_s = torch.empty((B, D), dtype=torch.float32, device=dev) if (want_fm and need_grad) else None
+        d = GatherDesc()
+        d.B, d.F, d.D, d.Nd, d.ldx, d.ld_lr = B, F, D, Nd, ldx, 0
+        r_arr = (C.c_int64 * F)(*st.rows)
+        i_arr = _ptr_list(idx)
+        d.rows, d.idx = r_arr, i_arr
+        if Nd:
+            d_arr = _ptr_list(dense)
+            d.dense = d_arr
+        d.x, d.fm, d.fm_s = x.data_ptr(), _ptr(fm), _ptr(fm_s)
+        d.err = _err_record(dev).data_ptr()
+        d.G, d.shard_tab = G, st.w_tab.data_ptr()
+        check(_lib.load().rpb_gather_fwd(C.byref(d), _stream()), 'rpb_gather_fwd(sharded)')
+        _count()
+        ctx.set_materialize_grads(False)
+        ctx.st, ctx.want_fm, ctx.params = st, want_fm, params
+        ctx.n_inputs = 3 + len(tensors)
+        ctx.save_for_backward(x, fm_s, *idx)
+        return (x, fm) if want_fm else (x,)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        st = ctx.st
+        x, fm_s, *idx = ctx.saved_tensors
+        gx = gouts[0]
+        gfm = gouts[1] if ctx.want_fm else None
+        F, D, G = len(st.cols), st.D, st.world
+        if gx is not None or gfm is not None:
+            d = ScatterDesc()
+            d.B, d.F, d.D = x.shape[0], F, D
+            if gx is not None:
+                gx = _rowmajor(gx)
+                d.dx, d.lddx = gx.data_ptr(), gx.stride(0)
+            if gfm is not None:
+                gfm = gfm.contiguous()
+                d.dfm, d.x, d.ldx, d.fm_s = gfm.data_ptr(), x.data_ptr(), x.stride(0), fm_s.data_ptr()
+            r_arr = (C.c_int64 * F)(*st.rows)
+            i_arr = _ptr_list(idx)
+            d.rows, d.idx = r_arr, i_arr
+            d.G, d.grad_shard_tab = G, st.g_tab.data_ptr()
+            check(_lib.load().rpb_gather_bwd(C.byref(d), _stream()), 'rpb_gather_bwd(sharded)')
+            _count()
+        st.pending.append(list(idx))
+        st.barrier()                                  # every rank's remote gradient adds have landed
+        for p, g in zip(ctx.params, st.grads):
+            if p.requires_grad:
+                p.grad = g
+        return (None,) * ctx.n_inputs
+
+
+def gather_sharded(st, params, idx: Sequence[torch.Tensor], dense: Sequence[torch.Tensor] = (), want_fm: bool = False):
+    """Row-sharded counterpart of `gather` (no LR tables).  Returns (x, fm | None, None)."""
+    idx_l = []
+    for t in idx:
+        _cuda(t, 'sparse feature column')
+        t = t.reshape(-1)
+        if t.dtype != torch.int64:
+            t = t.long()
+        idx_l.append(t.contiguous())
+    dense_l = [t.reshape(-1).float().contiguous() for t in dense]
+    outs = _GatherSharded.apply(st, want_fm, len(idx_l), *params, *idx_l, *dense_l)
+    return outs[0], (outs[1] if want_fm else None), None
+
+
+def sharded_clean(st):
+    """Sparse re-zero of the gradient shards for the rows this rank's pending batches touched, then a barrier."""
+    F = len(st.cols)
+    for idx in st.pending:
+        d = ScatterDesc()
+        d.B, d.F, d.D = idx[0].shape[0], F, st.D
+        r_arr = (C.c_int64 * F)(*st.rows)
+        i_arr = _ptr_list(idx)
+        d.rows, d.idx = r_arr, i_arr
+        d.G, d.grad_shard_tab = st.world, st.g_tab.data_ptr()
+        check(_lib.load().rpb_rows_zero(C.byref(d), _stream()), 'rpb_rows_zero(sharded)')
+        _count()
+    if st.pending:
+        st.barrier()
+    st.pending = []
 
 
 # ------------------------------------------------------------------ standalone FM on [B,F,D]

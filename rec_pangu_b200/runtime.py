@@ -64,8 +64,9 @@ class GraphedStep:
     output tensors."""
 
     def __init__(self, model: torch.nn.Module, batch: ColumnarBatch, post: Optional[Callable[[], None]] = None,
-                 warmup: int = 3, use_graph: bool = True):
+                 warmup: int = 3, use_graph: bool = True, loss_scale: float = 1.0):
         self.model, self.batch, self.post = model, batch, post
+        self.loss_scale = loss_scale           # data parallel: back-propagate loss / world (dist.DenseGradBucket)
         self.data = batch.as_dict()
         self.graph = None
         self.loss = self.pred = None
@@ -90,7 +91,7 @@ class GraphedStep:
 
     def _eager(self):
         out = self.model(self.data)
-        out['loss'].backward()
+        (out['loss'] if self.loss_scale == 1.0 else out['loss'] * self.loss_scale).backward()
         if self.post is not None:
             self.post()
         self.model.zero_grad(set_to_none=True)
