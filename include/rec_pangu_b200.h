@@ -212,6 +212,21 @@ int rpb_bn_apply(const float* x, const float* mean, const float* invstd, const f
 int rpb_bn_bwd(const float* dy, const float* x, const float* mean, const float* invstd, const float* gamma,
                float* dx, float* dgamma, float* dbeta, int M, int N, int use_batch_stats, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * FiBiNet interaction (ranking/fibinet.py:59-66): SENET_Layer (interaction.py:238-251) + BilinearInteractionLayer
+ * 'field_interaction' (interaction.py:55-81) applied to the raw and the SENET-reweighted embeddings with the SAME
+ * weights, written straight into the MLP input row
+ *   comb[b] = [ bilinear(E) (P*D) | bilinear(SENET(E)) (P*D) | dense (Nd) | 0-pad ],  P = F(F-1)/2 (combinations order).
+ * x: feature row [B, ldx] (embeddings then dense);  W1: [R, F], W2: [F, R] (excitation.0/.2 weights, no bias);
+ * Wb: [P, D, D] stacked bilinear_layer.<p>.weight;  A: [B, F] out — SENET weights saved for backward.
+ * Limits: 2 <= F <= 32, D in {8,16,32}, R <= D.
+ * bwd: dx [B, lddx] (embedding columns; the rest zero) is written; dW1/dW2/dWb are accumulated into (+=). */
+int rpb_fibinet_fwd(const float* x, int64_t ldx, int B, int F, int D, int Nd, const float* W1, int R,
+                    const float* W2, const float* Wb, float* comb, int64_t ldc, float* A, void* stream);
+int rpb_fibinet_bwd(const float* x, int64_t ldx, int B, int F, int D, const float* W1, int R, const float* W2,
+                    const float* Wb, const float* A, const float* dcomb, int64_t lddc, float* dx, int64_t lddx,
+                    float* dW1, float* dW2, float* dWb, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,9 @@ SIGNATURES = {
     'rpb_bn_stats': (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     'rpb_bn_apply': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     'rpb_bn_bwd': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+    'rpb_fibinet_fwd': (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _i64, _vp, _vp]),
+    'rpb_fibinet_bwd': (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _i64, _vp, _i64,
+                                  _vp, _vp, _vp, _vp]),
     'rpb_autoint_attn_fwd': (C.c_int, [_vp, _i64, _vp, _i64, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     'rpb_autoint_attn_bwd': (C.c_int, [_vp, _i64, C.c_int, _vp, _vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
 }

@@ -1021,3 +1021,61 @@ def dropout(x: torch.Tensor, p: float, training: bool) -> torch.Tensor:
     if not training or p <= 0.0:
         return x
     return _Dropout.apply(x.contiguous(), float(p), int(torch.randint(0, 2 ** 62, (1,)).item()))
+
+
+# ------------------------------------------------------------------ FiBiNet: SENET + bilinear (both passes) fused
+class _FiBiNet(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, F, D, Nd, W1, W2, Wb):
+        B = x.shape[0]
+        P = F * (F - 1) // 2
+        K = 2 * P * D + Nd
+        ldc = (K + 3) // 4 * 4
+        comb = torch.empty((B, ldc), dtype=torch.float32, device=x.device)
+        A = torch.empty((B, F), dtype=torch.float32, device=x.device)
+        R = W1.shape[0]
+        check(_lib.load().rpb_fibinet_fwd(_ptr(x), x.stride(0), B, F, D, Nd, _ptr(W1), R, _ptr(W2), _ptr(Wb), _ptr(comb), ldc,
+                                          _ptr(A), _stream()), 'rpb_fibinet_fwd')
+        _count()
+        ctx.dims = (F, D, Nd)
+        ctx.save_for_backward(x, A, W1, W2, Wb)
+        return comb
+
+    @staticmethod
+    def backward(ctx, g):
+        x, A, W1, W2, Wb = ctx.saved_tensors
+        F, D, Nd = ctx.dims
+        B = x.shape[0]
+        g = _rowmajor(g)
+        dx = torch.empty((B, x.shape[1]), dtype=torch.float32, device=x.device)
+        dW1, dW2, dWb = torch.zeros_like(W1), torch.zeros_like(W2), torch.zeros_like(Wb)
+        check(_lib.load().rpb_fibinet_bwd(_ptr(x), x.stride(0), B, F, D, _ptr(W1), W1.shape[0], _ptr(W2), _ptr(Wb), _ptr(A),
+                                          _ptr(g), g.stride(0), _ptr(dx), dx.stride(0), _ptr(dW1), _ptr(dW2), _ptr(dWb),
+                                          _stream()), 'rpb_fibinet_bwd')
+        _count(3)
+        return dx, None, None, None, dW1, dW2, dWb
+
+
+def fibinet_interaction(x: torch.Tensor, F: int, D: int, Nd: int, W1: torch.Tensor, W2: torch.Tensor,
+                        Wb: torch.Tensor) -> torch.Tensor:
+    """[bilinear(E) | bilinear(SENET(E)) | dense] MLP input of FiBiNet (fibinet.py:59-66) from the feature row x."""
+    _cuda(x, 'feature row')
+    return _FiBiNet.apply(_rowmajor(x), F, D, Nd, W1.contiguous(), W2.contiguous(), Wb.contiguous())
+
+
+def senet(e: torch.Tensor, W1: torch.Tensor, W2: torch.Tensor) -> torch.Tensor:
+    raise NotImplementedError('standalone SENET_Layer.forward: use FiBiNet (fused rpb_fibinet_* kernels)')
+
+
+def bilinear(e: torch.Tensor, Wb: torch.Tensor) -> torch.Tensor:
+    """Standalone BilinearInteractionLayer('field_interaction').forward -> [B, P, D] through the fused FiBiNet kernel
+    (zero excitation weights switch the SENET branch off; its half of the output row is ignored)."""
+    _cuda(e, 'feature_emb')
+    B, F, D = e.shape
+    x = e.float().contiguous().view(B, F * D)
+    R = max(1, F // 3)
+    W1 = torch.zeros((R, F), dtype=torch.float32, device=e.device)
+    W2 = torch.zeros((F, R), dtype=torch.float32, device=e.device)
+    P = F * (F - 1) // 2
+    comb = _FiBiNet.apply(x, F, D, 0, W1, W2, Wb.contiguous())
+    return comb[:, :P * D].reshape(B, P, D)

@@ -324,3 +324,54 @@ def test_autoint_attention_forward_backward(B, F, D, H, d):
     torch.testing.assert_close(x.grad.cpu().double(), xd.grad, rtol=1e-4, atol=5e-5)
     for k, p in m.named_parameters():
         torch.testing.assert_close(p.grad.cpu().double(), sd['p.' + k].grad, rtol=2e-4, atol=2e-4, msg=lambda s: f'{k}: {s}')
+
+
+@pytest.mark.parametrize('B,F,D', [(100, 26, 16), (33, 6, 8), (40, 7, 32)])
+def test_bilinear_layer_forward_backward(B, F, D):
+    from rec_pangu_b200.models.layers import BilinearInteractionLayer
+    torch.manual_seed(F)
+    m = BilinearInteractionLayer(F, D, 'field_interaction')
+    sd = {'p.' + k: v.detach().clone().double().requires_grad_(True) for k, v in m.state_dict().items()}
+    m = m.cuda()
+    e0 = torch.randn(B, F, D)
+    e = e0.cuda().requires_grad_(True)
+    out = m(e)
+    w = torch.randn(out.shape)
+    (out * w.cuda()).sum().backward()
+    ed = e0.double().requires_grad_(True)
+    ref = oracle.bilinear_field_interaction(sd, 'p', ed)
+    (ref * w.double()).sum().backward()
+    torch.testing.assert_close(out.cpu().double(), ref, rtol=1e-4, atol=1e-5)
+    assert_close_rel(e.grad, ed.grad, 1e-4, 'dE')
+    for k, p in m.named_parameters():
+        assert_close_rel(p.grad, sd['p.' + k].grad, 1e-4, k)
+
+
+def test_layers_match_reference_golden_on_gpu():
+    """The committed reference-layer outputs (tests/golden/layers.npz) through the CUDA layers."""
+    from helpers import load_layers, sub_sd
+    from rec_pangu_b200.models import layers as L
+    G = load_layers()
+    e, x, e2 = G['in/e'].cuda(), G['in/x'].cuda(), G['in/e2'].cuda()
+    Fn, D = e.shape[1], e.shape[2]
+    tol = dict(rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(L.FM_Layer().cuda()(e).cpu(), G['fm/out'], **tol)
+    torch.testing.assert_close(L.InnerProductLayer(output='Bi_interaction_pooling')(e).cpu(), G['bi/out'], **tol)
+    m = L.MLP(input_dim=x.shape[1], output_dim=1, hidden_units=[16, 8], hidden_activations='relu', dropout_rates=0)
+    m.load_state_dict(sub_sd(G, 'mlp'))
+    torch.testing.assert_close(m.cuda()(x).cpu(), G['mlp/out'], **tol)
+    c = L.CrossNet(x.shape[1], 3)
+    c.load_state_dict(sub_sd(G, 'crossnet'))
+    torch.testing.assert_close(c.cuda()(x)[:, :x.shape[1]].cpu(), G['crossnet/out'], **tol)
+    ci = L.CompressedInteractionNet(Fn, [4, 5, 3])
+    ci.load_state_dict(sub_sd(G, 'cin'))
+    torch.testing.assert_close(ci.cuda()(e).cpu(), G['cin/out'], **tol)
+    bl = L.BilinearInteractionLayer(Fn, D, 'field_interaction')
+    bl.load_state_dict(sub_sd(G, 'bilinear'))
+    torch.testing.assert_close(bl.cuda()(e).cpu(), G['bilinear/out'], **tol)
+    a = L.MultiHeadSelfAttention(D, attention_dim=4, num_heads=3, align_to='output')
+    a.load_state_dict(sub_sd(G, 'mhsa'))
+    torch.testing.assert_close(a.cuda()(e).cpu(), G['mhsa/out'], **tol)
+    a2 = L.MultiHeadSelfAttention(12, attention_dim=4, num_heads=3, align_to='output')
+    a2.load_state_dict(sub_sd(G, 'mhsa_nores'))
+    torch.testing.assert_close(a2.cuda()(e2).cpu(), G['mhsa_nores/out'], **tol)
