@@ -169,32 +169,48 @@ rowdot_dx_kernel(const float* __restrict__ dout, const float* __restrict__ w, co
     dx[(size_t)m * lddx + k] = v;
 }
 
-// dw[k] += sum_m dout[m] x[m,k]; db += sum_m dout[m].  grid (ceil(K/256), slabs); thread owns one k.
+// dw[k] += sum_m dout[m] x[m,k]; db += sum_m dout[m].  Warp per row (coalesced 128-byte row segments), each lane keeps
+// K/32 partial sums in registers over the rows of its warp, then one block reduction through shared memory.
+template <int NJ>
 __global__ void __launch_bounds__(256)
 rowdot_dw_kernel(const float* __restrict__ dout, const float* __restrict__ x, long long ldx,
-                 float* __restrict__ dw, float* __restrict__ db, int M, int K, int slab) {
-    __shared__ float ds[256];
-    __shared__ float red[32];
-    const int k = blockIdx.x * 256 + threadIdx.x;
-    const int mbeg = blockIdx.y * slab, mend = min(M, mbeg + slab);
-    float acc = 0.f, dsum = 0.f;
-    for (int m0 = mbeg; m0 < mend; m0 += 256) {
-        const int mm = m0 + threadIdx.x;
-        const float dv = (mm < mend) ? __ldg(dout + mm) : 0.f;
-        ds[threadIdx.x] = dv;
-        dsum += dv;
-        __syncthreads();
-        const int cnt = min(256, mend - m0);
-        if (k < K) {
-#pragma unroll 4
-            for (int r = 0; r < cnt; ++r) acc = fmaf(ds[r], __ldg(x + (size_t)(m0 + r) * ldx + k), acc);
+                 float* __restrict__ dw, float* __restrict__ db, int M, int K) {
+    __shared__ float part[8][32 * NJ + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float acc[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) acc[j] = 0.f;
+    float dsum = 0.f;
+    for (long long m = (long long)blockIdx.x * 8 + warp; m < M; m += (long long)gridDim.x * 8) {
+        const float d = __ldg(dout + m);
+        dsum += d;
+        const float* row = x + (size_t)m * ldx;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int k = lane + 32 * j;
+            if (k < K) acc[j] = fmaf(d, __ldg(row + k), acc[j]);
         }
-        __syncthreads();
     }
-    if (k < K) red_add_f1(dw + k, acc);
-    if (db != nullptr && blockIdx.x == 0) {
-        const float t = block_sum(dsum, red);
-        if (threadIdx.x == 0) red_add_f1(db, t);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) part[warp][lane + 32 * j] = acc[j];
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += 256) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += part[w][k];
+        red_add_f1(dw + k, s);
+    }
+    if (db != nullptr) {
+        // every lane of a warp accumulated the same dsum; take lane 0 of each warp
+        __syncthreads();
+        if (lane == 0) part[warp][0] = dsum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) s += part[w][0];
+            red_add_f1(db, s);
+        }
     }
 }
 
@@ -271,12 +287,12 @@ RPB_API int rpb_rowdot_bwd(const float* dout, const float* x, int64_t ldx, const
     }
     if (dw != nullptr) {
         if (x == nullptr) return RPB_ERR_BAD_ARG;
-        const int kt = ceil_div(K, 256);
-        int slabs = max(1, min(ceil_div(M, 256), ceil_div(148 * 4, kt)));
-        int slab = ceil_div(M, slabs);
-        slab = ((slab + 255) / 256) * 256;
-        slabs = ceil_div(M, slab);
-        rowdot_dw_kernel<<<dim3(kt, slabs), 256, 0, st>>>(dout, x, ldx, dw, db, M, K, slab);
+        const int grid = min(ceil_div(M, 8), 148 * 4);
+        const int nj = ceil_div(K, 32);
+        if (nj <= 2) rowdot_dw_kernel<2><<<grid, 256, 0, st>>>(dout, x, ldx, dw, db, M, K);
+        else if (nj <= 8) rowdot_dw_kernel<8><<<grid, 256, 0, st>>>(dout, x, ldx, dw, db, M, K);
+        else if (nj <= 32) rowdot_dw_kernel<32><<<grid, 256, 0, st>>>(dout, x, ldx, dw, db, M, K);
+        else return RPB_ERR_UNSUPPORTED;
         RPB_LAUNCH_CHECK();
     }
     return 0;

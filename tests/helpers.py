@@ -50,11 +50,18 @@ def make_batch(enc, B, seed=1029, labels=('label',), device='cpu'):
     return {k: v.to(device) for k, v in data.items()}
 
 
-def assert_close_rel(a, b, tol, what=''):
-    """max |a-b| <= tol * max(1e-6 + max|b|): tensor-relative tolerance for batch-reduced gradients, whose fp32
-    summation order (atomics / tiling) differs from the sequential CPU oracle."""
+def assert_close_rel(a, b, tol, what='', atol=1e-7, outlier_frac=0.0):
+    """|a-b| <= tol * max|b| + atol element-wise, for batch-reduced gradients whose fp32 summation order (atomics /
+    tiling) differs from the sequential CPU oracle.  `outlier_frac` tolerates a small fraction of elements beyond the
+    bound: on large random batches a ReLU pre-activation (or a saturated sigmoid) within fp32 noise of its kink takes
+    the other branch on the GPU than on the CPU, which changes that ONE sample's whole gradient contribution — an
+    ill-conditioning of the reference's own formulation, not a kernel error."""
     a, b = a.detach().cpu().double(), b.detach().cpu().double()
     assert a.shape == b.shape, f'{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}'
-    err = (a - b).abs().max().item()
     ref = b.abs().max().item()
-    assert err <= tol * (ref + 1e-6), f'{what}: max abs err {err:.3e} vs max |ref| {ref:.3e} (tol {tol})'
+    bad = ((a - b).abs() > tol * ref + atol)
+    nbad = int(bad.sum().item())
+    allowed = int(outlier_frac * a.numel())
+    err = (a - b).abs().max().item()
+    assert nbad <= allowed, (f'{what}: {nbad} of {a.numel()} elements beyond tol (allowed {allowed}); '
+                             f'max abs err {err:.3e} vs max |ref| {ref:.3e} (tol {tol})')
