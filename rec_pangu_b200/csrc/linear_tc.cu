@@ -257,6 +257,150 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
 }
 
+// ---------------------------------------------------------------------------------- weight gradient on tcgen05
+// dW[n,k] += sum_m dy[m,n] * x[m,k]: the reduction runs over the SAMPLES, so both operands are MN-major (their
+// contiguous dimension is the output dimension): A = x^T tile [128 k-columns x 64 samples], B = dy^T [block_n x 64
+// samples].  TMA brings [64 rows x 32 floats] SWIZZLE_128B boxes; in the MN-major canonical layout one box is one
+// 32-float MN chunk (chunks LBO = 8 KiB apart) of eight 8-sample K groups (SBO = 1 KiB apart), one group per MMA.
+// Each CTA reduces one slab of samples for one 128-column tile of dW^T in TMEM and adds it to dW with fp32 reductions.
+constexpr int WG_ROWS = 64;                                  // samples per stage
+constexpr int WG_BOX_BYTES = WG_ROWS * 128;                  // one [64 x 32 fp32] box = 8 KiB
+
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);            // start address
+    d |= (uint64_t)(WG_BOX_BYTES >> 4) << 16;               // LBO: next 32-float chunk along M/N
+    d |= (uint64_t)(1024 >> 4) << 32;                       // SBO: next 8-sample group along K
+    d |= (uint64_t)1 << 46;                                 // version = 1
+    d |= (uint64_t)2 << 61;                                 // SWIZZLE_128B
+    return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int m, int n) {
+    return make_idesc_tf32(m, n) | (1u << 15) | (1u << 16);  // A and B are MN-major
+}
+
+template <int kStages>
+__global__ void __launch_bounds__(TC_THREADS)
+wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDy,
+                    float* __restrict__ dW, int N, int K, int M, int block_n, int slab, uint32_t tmem_cols) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int a_bytes = 4 * WG_BOX_BYTES;                    // 128 k-columns = 4 chunks
+    const int b_chunks = block_n / 32;
+    const int b_bytes = b_chunks * WG_BOX_BYTES;
+    const int stage_bytes = 2 * a_bytes + 2 * b_bytes;       // [A hi | A lo | B hi | B lo]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * stage_bytes);
+    uint64_t* full_bar = bars;
+    uint64_t* ready_bar = bars + kStages;
+    uint64_t* empty_bar = bars + 2 * kStages;
+    uint64_t* tmem_full_bar = bars + 3 * kStages;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k0 = blockIdx.x * 128;                         // dW column tile
+    const int mbeg = blockIdx.y * slab;
+    const int mend = min(M, mbeg + slab);
+    const int num_kb = (mend - mbeg + WG_ROWS - 1) / WG_ROWS;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&ready_bar[s], 128); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t tx_bytes = (uint32_t)(a_bytes + b_bytes);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (uint32_t)((kb / kStages) & 1);
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                uint8_t* st = smem + (size_t)s * stage_bytes;
+                const int m0 = mbeg + kb * WG_ROWS;
+                mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+                for (int c = 0; c < 4; ++c) tma_load_2d(st + c * WG_BOX_BYTES, &tmX, &full_bar[s], k0 + 32 * c, m0);
+                for (int c = 0; c < b_chunks; ++c)
+                    tma_load_2d(st + 2 * a_bytes + c * WG_BOX_BYTES, &tmDy, &full_bar[s], 32 * c, m0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32_mn(128, block_n);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % kStages;
+                const uint32_t ph = (uint32_t)((kb / kStages) & 1);
+                mbar_wait(&ready_bar[s], ph);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint32_t a_lo = a_hi + a_bytes;
+                const uint32_t b_hi = a_hi + 2 * a_bytes;
+                const uint32_t b_lo = b_hi + b_bytes;
+#pragma unroll
+                for (int g = 0; g < WG_ROWS / TC_UMMA_K; ++g) {
+                    const uint32_t koff = g * 1024;                         // one 8-sample K group
+                    const uint64_t da_hi = make_mnmajor_sw128_desc(a_hi + koff), da_lo = make_mnmajor_sw128_desc(a_lo + koff);
+                    const uint64_t db_hi = make_mnmajor_sw128_desc(b_hi + koff), db_lo = make_mnmajor_sw128_desc(b_lo + koff);
+                    umma_tf32(tmem_base, da_lo, db_hi, idesc, (kb > 0 || g > 0) ? 1u : 0u);
+                    umma_tf32(tmem_base, da_hi, db_lo, idesc, 1u);
+                    umma_tf32(tmem_base, da_hi, db_hi, idesc, 1u);
+                }
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(tmem_full_bar);
+        }
+    } else {
+        const int t = threadIdx.x - 64;
+        const int a_vec = a_bytes / 16, b_vec = b_bytes / 16;
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % kStages;
+            const uint32_t ph = (uint32_t)((kb / kStages) & 1);
+            mbar_wait(&full_bar[s], ph);
+            float4* a = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
+            float4* alo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + a_bytes);
+            float4* b = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + 2 * a_bytes);
+            float4* blo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + 2 * a_bytes + b_bytes);
+            for (int j = t; j < a_vec + b_vec; j += 128) {
+                float4* src = j < a_vec ? a + j : b + (j - a_vec);
+                float4* dlo = j < a_vec ? alo + j : blo + (j - a_vec);
+                const float4 v = *src;
+                float4 h, l;
+                h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+                h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+                h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+                h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+                *src = h;
+                *dlo = l;
+            }
+            fence_proxy_async();
+            mbar_arrive(&ready_bar[s]);
+        }
+        // epilogue: TMEM lane = dW column k0+row, TMEM column = output row n
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const int quarter = warp & 3;
+        const int k = k0 + quarter * 32 + lane;
+        for (int c0 = 0; c0 < block_n; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+            if (k < K) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n = c0 + j;
+                    if (n < N) red_add_f1(dW + (size_t)n * K + k, __uint_as_float(r[j]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+}
+
 // W[N,K] (row stride ldw) -> hi/lo [Np, Kp] zero padded;  transpose: out[k, n] = W[n, k] (out is [Kout=K rows.., ])
 __global__ void __launch_bounds__(256)
 split_pack_kernel(const float* __restrict__ W, long long ldw, int rows_in, int cols_in, int transpose,
@@ -360,6 +504,40 @@ int gemm_tc(const float* A, long long lda, const float* Bsrc, long long ldb, int
     return rc;
 }
 
+
+// dW[N,K] += dy[M,N]^T @ x[M,K] on tensor cores (see wgrad_tf32x3_kernel).  Returns RPB_ERR_UNSUPPORTED when the
+// operands do not satisfy the TMA constraints (16-byte aligned rows) or N > 256.
+int wgrad_tc(const float* dy, long long lddy, const float* x, long long ldx, float* dW, int M, int N, int K, cudaStream_t st) {
+    if ((lddy % 4) != 0 || (ldx % 4) != 0 || (reinterpret_cast<uintptr_t>(dy) & 15u) || (reinterpret_cast<uintptr_t>(x) & 15u))
+        return RPB_ERR_UNSUPPORTED;
+    const int block_n = round_up(N, 32);
+    if (block_n > 256) return RPB_ERR_UNSUPPORTED;
+    CUtensorMap tmX, tmDy;
+    int rc = make_map(&tmX, x, M, K, ldx, WG_ROWS);
+    if (rc == 0) rc = make_map(&tmDy, dy, M, N, lddy, WG_ROWS);
+    if (rc != 0) return rc;
+    const int ktiles = ceil_div(K, 128);
+    int slabs = max(1, min(ceil_div(M, WG_ROWS), (148 * 2) / ktiles));
+    int slab = round_up(ceil_div(M, slabs), WG_ROWS);
+    slabs = ceil_div(M, slab);
+    const int stage_bytes = 2 * 4 * WG_BOX_BYTES + 2 * (block_n / 32) * WG_BOX_BYTES;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < block_n) tmem_cols <<= 1;
+    auto launch = [&](auto stages_tag) -> int {
+        constexpr int S = decltype(stages_tag)::value;
+        const size_t smem = (size_t)S * stage_bytes + (3 * S + 2) * 8 + 1024;
+        cudaError_t ee = cudaFuncSetAttribute(wgrad_tf32x3_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (ee != cudaSuccess) return (int)ee;
+        wgrad_tf32x3_kernel<S><<<dim3(ktiles, slabs), TC_THREADS, smem, st>>>(tmX, tmDy, dW, N, K, M, block_n, slab, tmem_cols);
+        return (int)cudaGetLastError();
+    };
+    const int max_stages = (200 * 1024) / stage_bytes;
+    if (max_stages >= 2) return launch(std::integral_constant<int, 2>{});
+    return RPB_ERR_UNSUPPORTED;
+}
+
+void colsum_launch(const float* x, long long ldx, float* out, int M, int K, cudaStream_t st);   // mmoe.cu
+
 // SIMT implementations (linear_simt.cu)
 int linear_fwd_simt(const float* x, long long ldx, const float* W, const float* bias, float* y, long long ldy,
                     int M, int N, int K, int act, cudaStream_t st);
@@ -406,7 +584,13 @@ RPB_API int rpb_linear_bwd(const float* dy, int64_t lddy, const float* x, int64_
     }
     if (dW != nullptr) {
         if (x == nullptr) return RPB_ERR_BAD_ARG;
-        const int rc = linear_dw_simt(dy, lddy, x, ldx, dW, db, M, N, K, st);
+        int rc = RPB_ERR_UNSUPPORTED;
+        if (impl == 2 || (impl == 0 && M >= 2048 && g_wgrad_tc)) {
+            rc = wgrad_tc(dy, lddy, x, ldx, dW, M, N, K, st);
+            if (rc == 0 && db != nullptr) colsum_launch(dy, lddy, db, M, N, st);
+            if (rc != 0 && rc != RPB_ERR_UNSUPPORTED) return rc;
+        }
+        if (rc != 0) rc = linear_dw_simt(dy, lddy, x, ldx, dW, db, M, N, K, st);
         if (rc != 0) return rc;
     }
     return 0;

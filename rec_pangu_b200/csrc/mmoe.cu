@@ -166,6 +166,14 @@ mmoe_combine_bwd_kernel(const float* __restrict__ eo, long long ld, const float*
     for (int j = Hh * E + T * E + lane; j < ldd; j += 32) drow[j] = 0.f;
 }
 
+static void stats_grid(int M, int K, dim3& grid, int& slab);
+
+void colsum_launch(const float* x, long long ldx, float* out, int M, int K, cudaStream_t st) {
+    dim3 grid; int slab;
+    stats_grid(M, K, grid, slab);
+    colstats_kernel<<<grid, dim3(32, 8), 0, st>>>(x, ldx, out, nullptr, M, K, slab);
+}
+
 static void stats_grid(int M, int K, dim3& grid, int& slab) {
     const int kt = ceil_div(K, 32);
     int slabs = max(1, min(ceil_div(M, 64), (148 * 8) / kt));

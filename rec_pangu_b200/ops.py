@@ -327,7 +327,7 @@ class _GatherSharded(torch.autograd.Function):
     the owners' gradient shards by the scatter kernel; after the device barrier each local shard's .grad is published."""
 
     @staticmethod
-    def forward(ctx, st, want_fm, n_idx, *tensors):
+    def forward(ctx, st, want_fm, n_idx, need_grad, *tensors):
         F, D, G = len(st.cols), st.D, st.world
         params = tensors[:F]                       # local shard Parameters (autograd anchors)
         idx = tensors[F:F + n_idx]
@@ -337,7 +337,6 @@ class _GatherSharded(torch.autograd.Function):
         B = idx[0].shape[0]
         ldx = feature_row_stride(F, D, Nd)
         x = torch.empty((B, ldx), dtype=torch.float32, device=dev)
-        need_grad = any(p.requires_grad for p in params) and torch.is_grad_enabled()
         fm = torch.empty((B,), dtype=torch.float32, device=dev) if want_fm else None
         fm_s = torch.empty((B, D), dtype=torch.float32, device=dev) if (want_fm and need_grad) else None
         d = GatherDesc()
@@ -355,7 +354,7 @@ class _GatherSharded(torch.autograd.Function):
         _count()
         ctx.set_materialize_grads(False)
         ctx.st, ctx.want_fm, ctx.params = st, want_fm, params
-        ctx.n_inputs = 3 + len(tensors)
+        ctx.n_inputs = 4 + len(tensors)
         ctx.save_for_backward(x, fm_s, *idx)
         return (x, fm) if want_fm else (x,)
 
@@ -399,7 +398,8 @@ def gather_sharded(st, params, idx: Sequence[torch.Tensor], dense: Sequence[torc
             t = t.long()
         idx_l.append(t.contiguous())
     dense_l = [t.reshape(-1).float().contiguous() for t in dense]
-    outs = _GatherSharded.apply(st, want_fm, len(idx_l), *params, *idx_l, *dense_l)
+    need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    outs = _GatherSharded.apply(st, want_fm, len(idx_l), need_grad, *params, *idx_l, *dense_l)
     return outs[0], (outs[1] if want_fm else None), None
 
 
