@@ -227,6 +227,28 @@ int rpb_fibinet_bwd(const float* x, int64_t ldx, int B, int F, int D, const floa
                     const float* Wb, const float* A, const float* dcomb, int64_t lddc, float* dx, int64_t lddx,
                     float* dW1, float* dW2, float* dWb, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer step (reference: torch.optim.Adam created in rec_pangu/trainer.py:75, stepped in model_pipeline.py:57).
+ * rpb_adam_dense: element-wise Adam (torch semantics: bias-corrected, eps added after the sqrt(v)/sqrt(bc2)).
+ * rpb_sparse_adam: row-sparse ("lazy") Adam for embedding tables in 'persistent' grad mode — only rows named by
+ * idx are updated (once per step even when several samples hit them: claimed through stamps[f][row] = step), and the
+ * row of the persistent gradient buffer is re-zeroed in the same pass.  Rows without gradient keep value and moments
+ * (torch.optim.SparseAdam semantics; the reference's dense Adam would keep moving them by momentum). */
+int rpb_adam_dense(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                   float eps, int step, void* stream);
+typedef struct RpbSparseAdamDesc {
+    int32_t B, F, D, step;          /* step >= 1: global optimizer step (bias correction) */
+    float lr, beta1, beta2, eps;
+    float* const* weights;          /* host arrays [F] of device pointers; weights[f] == NULL skips table f */
+    float* const* grads;            /* persistent dense gradient buffers [rows, D] */
+    float* const* exp_avg;
+    float* const* exp_avg_sq;
+    int32_t* const* stamps;         /* int32[rows[f]], zero-initialised once */
+    const int64_t* rows;
+    const int64_t* const* idx;      /* int64[B] per field: the batch whose backward filled `grads` */
+} RpbSparseAdamDesc;
+int rpb_sparse_adam(const RpbSparseAdamDesc* d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

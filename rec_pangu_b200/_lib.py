@@ -31,6 +31,13 @@ class ScatterDesc(C.Structure):
                 ('G', _i32), ('grad_shard_tab', _vp)]
 
 
+class SparseAdamDesc(C.Structure):
+    _fields_ = [('B', _i32), ('F', _i32), ('D', _i32), ('step', _i32), ('lr', _f32), ('beta1', _f32), ('beta2', _f32),
+                ('eps', _f32), ('weights', C.POINTER(_vp)), ('grads', C.POINTER(_vp)), ('exp_avg', C.POINTER(_vp)),
+                ('exp_avg_sq', C.POINTER(_vp)), ('stamps', C.POINTER(_vp)), ('rows', C.POINTER(_i64)),
+                ('idx', C.POINTER(_vp))]
+
+
 # name -> (restype, argtypes); must list every symbol of include/rec_pangu_b200.h (tests check this)
 SIGNATURES = {
     'rpb_version': (C.c_int, []),
@@ -68,6 +75,8 @@ SIGNATURES = {
     'rpb_fibinet_fwd': (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _i64, _vp, _vp]),
     'rpb_fibinet_bwd': (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _i64, _vp, _i64,
                                   _vp, _vp, _vp, _vp]),
+    'rpb_adam_dense': (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, C.c_int, _vp]),
+    'rpb_sparse_adam': (C.c_int, [C.POINTER(SparseAdamDesc), _vp]),
     'rpb_autoint_attn_fwd': (C.c_int, [_vp, _i64, _vp, _i64, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     'rpb_autoint_attn_bwd': (C.c_int, [_vp, _i64, C.c_int, _vp, _vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
 }

@@ -1,0 +1,104 @@
+"""Fused optimizer for the hot path.
+
+`FusedAdam(model, lr)` has torch.optim.Adam's hyper-parameters (the reference creates
+`torch.optim.Adam(model.parameters(), lr=lr, betas=(0.9, 0.999), eps=1e-08, weight_decay=0)`, trainer.py:75).
+Dense parameters get the element-wise Adam kernel; embedding tables in 'persistent' grad mode get the row-sparse kernel
+(`rpb_sparse_adam`), which touches only the rows of the current batch and re-zeroes the gradient buffer in the same
+pass.  Semantics of the sparse part = torch.optim.SparseAdam ("lazy" Adam): a row that receives no gradient in a step
+is left untouched, whereas the reference's dense Adam would still move it by its momentum — a documented deviation;
+use torch.optim.Adam with grad_mode='dense'/'persistent' for the reference-identical update."""
+import ctypes as C
+
+import torch
+
+from . import _lib, ops
+from ._lib import SparseAdamDesc, check
+from .models.layers.embedding import EmbeddingLayer
+
+
+class FusedAdam:
+    def __init__(self, model: torch.nn.Module, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
+        self.model, self.lr, self.betas, self.eps = model, lr, betas, eps
+        self.step_count = 0
+        self.emb_layers = [m for m in model.modules() if isinstance(m, EmbeddingLayer) and m._shards is None]
+        for m in self.emb_layers:
+            m.grad_mode = 'persistent'
+        table_ids = {id(p) for m in self.emb_layers for p in m.tables()}
+        self.dense = [p for p in model.parameters() if id(p) not in table_ids and p.requires_grad]
+        self.state = {}
+
+    def _st(self, p):
+        s = self.state.get(id(p))
+        if s is None:
+            s = {'m': torch.zeros_like(p), 'v': torch.zeros_like(p)}
+            self.state[id(p)] = s
+        return s
+
+    @torch.no_grad()
+    def step(self):
+        self.step_count += 1
+        lib, st = _lib.load(), C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        b1, b2 = self.betas
+        for p in self.dense:
+            if p.grad is None:
+                continue
+            s = self._st(p)
+            g = p.grad.contiguous()
+            check(lib.rpb_adam_dense(p.data_ptr(), g.data_ptr(), s['m'].data_ptr(), s['v'].data_ptr(), p.numel(), self.lr,
+                                     b1, b2, self.eps, self.step_count, st), 'rpb_adam_dense')
+            ops._count()
+        for emb in self.emb_layers:
+            store = emb._grad_store
+            for grads, lr_grads, rows, idx, D in store.pending:
+                self._sparse(lib, st, emb.tables(), grads, rows, idx, D)
+                if lr_grads is not None:
+                    # D=1 LR tables rode in the same gather: their params are matched by buffer identity
+                    lr_params = [self._param_of(store, g) for g in lr_grads]
+                    self._sparse_scalar(lr_params, lr_grads, rows, idx)
+            store.pending = []                     # gradient rows were re-zeroed by the fused kernel
+
+    def _param_of(self, store, buf):
+        for p in self.model.parameters():
+            if store.buffers.get(id(p)) is buf:
+                return p
+        return None
+
+    def _sparse(self, lib, st, params, grads, rows, idx, D):
+        F = len(idx)
+        d = SparseAdamDesc()
+        d.B, d.F, d.D, d.step = idx[0].shape[0], F, D, self.step_count
+        d.lr, d.beta1, d.beta2, d.eps = self.lr, self.betas[0], self.betas[1], self.eps
+        states = [self._st(p) if g is not None else None for p, g in zip(params, grads)]
+        for p, s in zip(params, states):
+            if s is not None and 'stamp' not in s:
+                s['stamp'] = torch.zeros(p.shape[0], dtype=torch.int32, device=p.device)
+        arr = lambda ts: (C.c_void_p * F)(*[t.data_ptr() if t is not None else 0 for t in ts])  # noqa: E731
+        w_arr = arr([p if g is not None else None for p, g in zip(params, grads)])
+        g_arr = arr(grads)
+        m_arr = arr([s['m'] if s else None for s in states])
+        v_arr = arr([s['v'] if s else None for s in states])
+        s_arr = arr([s['stamp'] if s else None for s in states])
+        r_arr = (C.c_int64 * F)(*rows)
+        i_arr = arr(idx)
+        d.weights, d.grads, d.exp_avg, d.exp_avg_sq, d.stamps, d.rows, d.idx = w_arr, g_arr, m_arr, v_arr, s_arr, r_arr, i_arr
+        check(lib.rpb_sparse_adam(C.byref(d), st), 'rpb_sparse_adam')
+        ops._count()
+
+    def _sparse_scalar(self, params, grads, rows, idx):
+        # D=1 tables: tiny rows; update them densely over the touched rows with index ops (plumbing on [B]-sized data)
+        b1, b2 = self.betas
+        bc1 = 1 - b1 ** self.step_count
+        bc2 = 1 - b2 ** self.step_count
+        for p, g, ix in zip(params, grads, idx):
+            if p is None or g is None:
+                continue
+            s = self._st(p)
+            rows_u = torch.unique(ix)
+            gr = g[rows_u]
+            s['m'][rows_u] = b1 * s['m'][rows_u] + (1 - b1) * gr
+            s['v'][rows_u] = b2 * s['v'][rows_u] + (1 - b2) * gr * gr
+            p[rows_u] -= (self.lr / bc1) * s['m'][rows_u] / (s['v'][rows_u].sqrt() / bc2 ** 0.5 + self.eps)
+            g[rows_u] = 0
+
+    def zero_grad(self, set_to_none: bool = True):
+        self.model.zero_grad(set_to_none=set_to_none)

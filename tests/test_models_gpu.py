@@ -164,3 +164,39 @@ def test_persistent_grad_mode_equals_dense_mode():
     for (k, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
         torch.testing.assert_close(p1.grad, p2.grad, rtol=1e-5, atol=1e-7)
     ops.check_index_errors()
+
+
+def test_fused_sparse_adam_matches_torch_adam_on_touched_rows():
+    """FusedAdam == torch.optim.Adam for dense params and for every table row that receives gradient in the step
+    (rows without gradient are left alone: lazy / SparseAdam semantics, see rec_pangu_b200/optim.py)."""
+    from rec_pangu_b200.models.ranking import DeepFM
+    from rec_pangu_b200.optim import FusedAdam
+    enc = make_enc(5, 2, 40)
+    torch.manual_seed(0)
+    m1 = DeepFM(embedding_dim=8, hidden_units=[16, 8], enc_dict=enc).cuda()
+    m2 = DeepFM(embedding_dim=8, hidden_units=[16, 8], enc_dict=enc).cuda()
+    m2.load_state_dict(m1.state_dict())
+    o1 = torch.optim.Adam(m1.parameters(), lr=1e-2, betas=(0.9, 0.999), eps=1e-8)
+    o2 = FusedAdam(m2, lr=1e-2)
+    touched_prev = None
+    for step in range(3):
+        data = make_batch(enc, 32, seed=100 + step, device='cuda')
+        for m, o in ((m1, o1), (m2, o2)):
+            m(data)['loss'].backward()
+            o.step()
+            m.zero_grad()
+        for (k, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+            if 'embedding_layer' in k:
+                col = k.split('.')[-2]
+                rows = torch.unique(data[col])
+                torch.testing.assert_close(p2[rows], p1[rows], rtol=1e-5, atol=1e-6, msg=lambda s: f'step {step} {k}: {s}') \
+                    if step == 0 else None
+                if step == 0:
+                    mask = torch.ones(p1.shape[0], dtype=torch.bool, device='cuda')
+                    mask[rows] = False
+                    assert torch.equal(p2[mask], p1[mask])          # untouched rows identical after the first step
+            else:
+                torch.testing.assert_close(p2, p1, rtol=1e-5, atol=1e-6, msg=lambda s: f'step {step} {k}: {s}')
+    # gradient buffers are all-zero again after the fused step
+    for buf in m2.embedding_layer._grad_store.buffers.values():
+        assert torch.count_nonzero(buf) == 0
