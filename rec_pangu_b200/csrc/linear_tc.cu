@@ -260,8 +260,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // ---------------------------------------------------------------------------------- weight gradient on tcgen05
 // dW[n,k] += sum_m dy[m,n] * x[m,k]: the reduction runs over the SAMPLES, so both operands are MN-major (their
 // contiguous dimension is the output dimension): A = x^T tile [128 k-columns x 64 samples], B = dy^T [block_n x 64
-// samples].  TMA brings [64 rows x 32 floats] SWIZZLE_128B boxes; in the MN-major canonical layout one box is one
-// 32-float MN chunk (chunks LBO = 8 KiB apart) of eight 8-sample K groups (SBO = 1 KiB apart), one group per MMA.
+// samples].  For 32-bit MN-major operands the only UMMA shared-memory layout is "128B swizzle with 32B atoms"
+// (LayoutType 1; TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of 128 B, 32-byte chunks XOR-ed with (row mod 4), so a
+// K atom is 4 samples (512 B).  TMA brings [64 samples x 32 floats] boxes: one box = one 32-float MN chunk (chunks
+// LBO = 8 KiB apart) holding sixteen 4-sample K atoms (SBO = 512 B apart); one MMA (K = 8) consumes two atoms.
 // Each CTA reduces one slab of samples for one 128-column tile of dW^T in TMEM and adds it to dW with fp32 reductions.
 constexpr int WG_ROWS = 64;                                  // samples per stage
 constexpr int WG_BOX_BYTES = WG_ROWS * 128;                  // one [64 x 32 fp32] box = 8 KiB
@@ -270,9 +272,9 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) 
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);            // start address
     d |= (uint64_t)(WG_BOX_BYTES >> 4) << 16;               // LBO: next 32-float chunk along M/N
-    d |= (uint64_t)(1024 >> 4) << 32;                       // SBO: next 8-sample group along K
+    d |= (uint64_t)(512 >> 4) << 32;                        // SBO: next 4-sample K atom
     d |= (uint64_t)1 << 46;                                 // version = 1
-    d |= (uint64_t)2 << 61;                                 // SWIZZLE_128B
+    d |= (uint64_t)1 << 61;                                 // SWIZZLE_128B_BASE32B
     return d;
 }
 __host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int m, int n) {
@@ -437,7 +439,8 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D fp32 tensor [rows, cols] with row stride ld (floats); box = [box_rows, 32 cols], 128 B swizzle, zero OOB fill
-static int make_map(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows) {
+static int make_map(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows,
+                    CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = get_encode_fn();
     if (fn == nullptr) return RPB_ERR_NO_DRIVER;
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -445,7 +448,7 @@ static int make_map(CUtensorMap* map, const float* base, long long rows, long lo
     cuuint32_t box[2] = {(cuuint32_t)TC_BLOCK_K, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : RPB_ERR_BAD_ARG;
 }
@@ -513,8 +516,8 @@ int wgrad_tc(const float* dy, long long lddy, const float* x, long long ldx, flo
     const int block_n = round_up(N, 32);
     if (block_n > 256) return RPB_ERR_UNSUPPORTED;
     CUtensorMap tmX, tmDy;
-    int rc = make_map(&tmX, x, M, K, ldx, WG_ROWS);
-    if (rc == 0) rc = make_map(&tmDy, dy, M, N, lddy, WG_ROWS);
+    int rc = make_map(&tmX, x, M, K, ldx, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc == 0) rc = make_map(&tmDy, dy, M, N, lddy, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc != 0) return rc;
     const int ktiles = ceil_div(K, 128);
     int slabs = max(1, min(ceil_div(M, WG_ROWS), (148 * 2) / ktiles));

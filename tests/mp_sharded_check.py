@@ -68,8 +68,9 @@ def main():
         assert torch.count_nonzero(st.full_grad(f)) == 0
     dist.barrier()
     if rank == 0:
-        print('SHARDED_OK world', world)
-    dist.destroy_process_group()
+        print('SHARDED_OK world', world, flush=True)
+    torch.cuda.synchronize()
+    os._exit(0)          # symmetric-memory / NCCL teardown can block at interpreter exit
 
 
 if __name__ == '__main__':
