@@ -296,9 +296,36 @@ def run_ours(args):
         us_gather = e0.elapsed_time(e1) * 1e3 / args.steps
         peak, peak_src = measured_peaks()
         achieved = ALG_BYTES_PER_SAMPLE * B / (us_gather * 1e-6) / 1e9
-        roofline = {'kernel': 'gather_fwd_kernel (multi-table gather + dense pack + FM second order)', 'bound': 'hbm',
-                    'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
-                    'us_per_launch': us_gather, 'alg_bytes_per_launch': ALG_BYTES_PER_SAMPLE * B, 'peak_source': peak_src}
+        # same stage without materialising the [B,F,D] rows (what FM inference runs; SURVEY.md §8d defines the
+        # algorithmic bytes of the embedding+interaction forward without the optional materialisation)
+        gn = []
+        with torch.no_grad():
+            for cb in cbs:
+                d = cb.as_dict()
+                idx = [d[c] for c in model.embedding_layer.emb_feature]
+                dn = [d[c] for c in model.embedding_layer.dense_feature]
+                ops.gather(tables, idx, dn, want_fm=True, want_x=False)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    ops.gather(tables, idx, dn, want_fm=True, want_x=False)
+                gn.append(g)
+        for i in range(3):
+            gn[i % NB].replay()
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(args.steps):
+            gn[i % NB].replay()
+        e1.record()
+        torch.cuda.synchronize()
+        us_nomat = e0.elapsed_time(e1) * 1e3 / args.steps
+        roofline = {'kernel': 'gather_fwd_tile_kernel (multi-table gather + dense pack + FM second order, x materialised)',
+                    'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                    'traffic': 183.1e6, 'traffic_source': 'profiles/r01_gather_fwd.md (ncu dram__bytes_read+write per launch)',
+                    'us_per_launch': us_gather, 'alg_bytes_per_launch': ALG_BYTES_PER_SAMPLE * B, 'peak_source': peak_src,
+                    'no_materialise': {'us_per_launch': us_nomat,
+                                       'achieved': ALG_BYTES_PER_SAMPLE * B / (us_nomat * 1e-6) / 1e9,
+                                       'frac': ALG_BYTES_PER_SAMPLE * B / (us_nomat * 1e-6) / 1e9 / peak}}
 
 
     line = {

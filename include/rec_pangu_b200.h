@@ -58,7 +58,7 @@ typedef struct RpbGatherDesc {
     const int64_t* const* idx;      /* host array [F] of device ptrs int64[B] */
     const float* const* dense;      /* host array [Nd] of device ptrs float[B]; NULL when Nd == 0 */
     const float* const* lr_tables;  /* host array [F] of device ptrs float[rows[f]] (D=1 tables) or NULL */
-    float* x;                       /* out [B, ldx] */
+    float* x;                       /* out [B, ldx]; may be NULL when only fm / lr_in are consumed (FM inference) */
     float* fm;                      /* out [B]: 0.5*sum_d((sum_f e)^2 - sum_f e^2), or NULL */
     float* fm_s;                    /* out [B, D]: sum_f e (saved for backward), or NULL */
     float* lr_in;                   /* out [B, ld_lr]: [lr_table_f[idx_f] (F) | dense (Nd)], or NULL */

@@ -137,7 +137,7 @@ gather_fwd_kernel(const __grid_constant__ GatherFwdParams p) {
         for (int u = 0; u < U; ++u) {
             const int f = f0 + u;
             if (f < p.F) {
-                if (lane_on && valid && POLICY != 3) e[u].store(xrow + f * p.D + l * VEC);   // 3 = experiment: no x write
+                if (lane_on && valid && POLICY != 3 && p.x != nullptr) e[u].store(xrow + f * p.D + l * VEC);   // x == NULL: FM-only consumers
                 s.add(e[u]);
                 q.add_sq(e[u]);
                 if (HAS_LR && valid && (f % LPR) == l) p.lr_in[(size_t)b * p.ld_lr + f] = lrv[u];
@@ -149,10 +149,10 @@ gather_fwd_kernel(const __grid_constant__ GatherFwdParams p) {
         const int FD = p.F * p.D;
         for (int j = l; j < p.Nd; j += LPR) {
             const float dv = __ldg(p.dense[j] + b);
-            xrow[FD + j] = dv;
+            if (p.x != nullptr) xrow[FD + j] = dv;
             if (HAS_LR) p.lr_in[(size_t)b * p.ld_lr + p.F + j] = dv;
         }
-        for (int j = FD + p.Nd + l; j < p.ldx; j += LPR) xrow[j] = 0.f;
+        if (p.x != nullptr) for (int j = FD + p.Nd + l; j < p.ldx; j += LPR) xrow[j] = 0.f;
         if (HAS_LR) for (int j = p.F + p.Nd + l; j < p.ld_lr; j += LPR) p.lr_in[(size_t)b * p.ld_lr + j] = 0.f;
         if (p.fm_s != nullptr && lane_on) s.store(p.fm_s + (size_t)b * p.D + l * VEC);
     }
@@ -452,11 +452,12 @@ static inline bool is_aligned16(const void* p) { return (reinterpret_cast<uintpt
 using namespace rpb;
 
 RPB_API int rpb_gather_fwd(const RpbGatherDesc* d, void* stream) {
-    if (d == nullptr || d->B <= 0 || d->F <= 0 || d->D <= 0 || d->x == nullptr) return RPB_ERR_BAD_ARG;
+    if (d == nullptr || d->B <= 0 || d->F <= 0 || d->D <= 0) return RPB_ERR_BAD_ARG;
+    if (d->x == nullptr && d->fm == nullptr && d->lr_in == nullptr) return RPB_ERR_BAD_ARG;      // nothing to produce
     if (d->F > RPB_MAX_FIELDS || d->Nd > RPB_MAX_DENSE || d->Nd < 0) return RPB_ERR_UNSUPPORTED;
-    if (d->ldx < d->F * d->D + d->Nd) return RPB_ERR_BAD_ARG;
+    if (d->x != nullptr && d->ldx < d->F * d->D + d->Nd) return RPB_ERR_BAD_ARG;
     GatherFwdParams p{};
-    bool aligned = (d->ldx % 4 == 0) && is_aligned16(d->x) && (d->fm_s == nullptr || is_aligned16(d->fm_s));
+    bool aligned = (d->x == nullptr || ((d->ldx % 4 == 0) && is_aligned16(d->x))) && (d->fm_s == nullptr || is_aligned16(d->fm_s));
     for (int f = 0; f < d->F; ++f) {
         p.tables[f] = d->tables ? d->tables[f] : nullptr;
         p.idx[f] = reinterpret_cast<const long long*>(d->idx[f]);
@@ -481,7 +482,7 @@ RPB_API int rpb_gather_fwd(const RpbGatherDesc* d, void* stream) {
         if constexpr (VEC == 4 && LPR <= 16) {
             constexpr int S = 128 / LPR;
             const size_t smem = (size_t)S * p.ldx * sizeof(float) + (size_t)p.F * S * sizeof(long long);
-            if (g_gather_kernel == 0 && pol == 1 && smem <= 100 * 1024) {
+            if (g_gather_kernel == 0 && pol == 1 && smem <= 100 * 1024 && p.x != nullptr) {
                 auto launch = [&](auto kern) -> int {
                     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                     if (e != cudaSuccess) return (int)e;

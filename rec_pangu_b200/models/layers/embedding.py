@@ -48,7 +48,7 @@ class EmbeddingLayer(nn.Module):
         return [self.embedding_layer[c].weight for c in self.emb_feature]
 
     def feature_row(self, X: Dict[str, torch.Tensor], with_dense: bool = True, want_fm: bool = False,
-                    lr_tables: Optional[Sequence[torch.Tensor]] = None):
+                    lr_tables: Optional[Sequence[torch.Tensor]] = None, want_x: bool = True):
         """Fused entry used by the model forwards: returns (x [B, ldx], fm [B] | None, lr_in | None) where
         x = [emb_0 | ... | emb_{F-1} | dense_0..dense_{Nd-1} | 0-pad] (see include/rec_pangu_b200.h)."""
         idx = [X[c] for c in self.emb_feature]
@@ -58,7 +58,7 @@ class EmbeddingLayer(nn.Module):
                 raise NotImplementedError('LR (D=1) tables together with row-sharded embedding tables')
             return ops.gather_sharded(self._shards, self.tables(), idx, dense, want_fm=want_fm)
         return ops.gather(self.tables(), idx, dense, lr_tables=lr_tables, want_fm=want_fm,
-                          grad_store=self._grad_store if self.grad_mode == 'persistent' else None)
+                          grad_store=self._grad_store if self.grad_mode == 'persistent' else None, want_x=want_x)
 
     def clean_grads(self):
         """Sparse re-zero of the persistent grad buffers (no-op in 'dense' mode)."""

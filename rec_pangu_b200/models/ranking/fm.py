@@ -15,5 +15,6 @@ class FM(BaseModel):
         self.reset_parameters()
 
     def forward(self, data, is_training: bool = True):
-        _, fm_out, _ = self.embedding_layer.feature_row(data, with_dense=False, want_fm=True)
+        # FM consumes only the second-order sum: in inference the [B,F,D] rows are never written to HBM (want_x=False)
+        _, fm_out, _ = self.embedding_layer.feature_row(data, with_dense=False, want_fm=True, want_x=False)
         return self._finish(fm_out.unsqueeze(1), data, is_training)

@@ -152,7 +152,7 @@ class _Gather(torch.autograd.Function):
         dev = tables[0].device
         B = idx[0].shape[0]
         ldx = feature_row_stride(F, D, Nd)
-        x = torch.empty((B, ldx), dtype=torch.float32, device=dev)
+        x = torch.empty((B, ldx), dtype=torch.float32, device=dev) if cfg.get('want_x', True) else None
         need_grad = cfg['needs_grad']
         fm = torch.empty((B,), dtype=torch.float32, device=dev) if want_fm else None
         fm_s = torch.empty((B, D), dtype=torch.float32, device=dev) if (want_fm and need_grad) else None
@@ -172,7 +172,7 @@ class _Gather(torch.autograd.Function):
         if has_lr:
             l_arr = (C.c_void_p * F)(*[t.data_ptr() for t in lr_tables])
             d.lr_tables = l_arr
-        d.x, d.fm, d.fm_s, d.lr_in = x.data_ptr(), _ptr(fm), _ptr(fm_s), _ptr(lr_in)
+        d.x, d.fm, d.fm_s, d.lr_in = _ptr(x), _ptr(fm), _ptr(fm_s), _ptr(lr_in)
         d.err = _err_record(dev).data_ptr()
         check(_lib.load().rpb_gather_fwd(C.byref(d), _stream()), 'rpb_gather_fwd')
         _count()
@@ -183,7 +183,7 @@ class _Gather(torch.autograd.Function):
         ctx.n_in = len(tensors)
         ctx.params = (tables, lr_tables)       # Parameter objects (persistent grad mode publishes .grad itself)
         ctx.save_for_backward(x, fm_s, *idx)
-        outs = [x]
+        outs = [x if x is not None else torch.empty(0, device=dev)]
         if want_fm:
             outs.append(fm)
         if has_lr:
@@ -268,7 +268,7 @@ class _Gather(torch.autograd.Function):
 
 def gather(tables: Sequence[torch.Tensor], idx: Sequence[torch.Tensor], dense: Sequence[torch.Tensor] = (),
            lr_tables: Optional[Sequence[torch.Tensor]] = None, want_fm: bool = False,
-           grad_store: Optional['GradStore'] = None):
+           grad_store: Optional['GradStore'] = None, want_x: bool = True):
     """One-launch multi-table gather.  Returns (x [B, ldx], fm [B] | None, lr_in [B, ld_lr] | None).
 
     ``x[:, :F*D].view(B, F, D)`` is the reference's ``EmbeddingLayer.forward`` output
@@ -306,8 +306,10 @@ def gather(tables: Sequence[torch.Tensor], idx: Sequence[torch.Tensor], dense: S
         lr_tables = [t if t.is_contiguous() else t.contiguous() for t in lr_tables]
     needs_grad = torch.is_grad_enabled() and (any(t.requires_grad for t in tables) or
                                               (has_lr and any(t.requires_grad for t in lr_tables)))
+    if not want_x and (needs_grad or not (want_fm or has_lr)):
+        want_x = True                  # backward (and any consumer of the rows) needs the materialised feature row
     cfg = dict(F=F, Nd=len(dense_l), D=D, has_lr=has_lr, want_fm=want_fm, needs_grad=needs_grad,
-               grad_store=grad_store)
+               grad_store=grad_store, want_x=want_x)
     args = list(tables) + (list(lr_tables) if has_lr else []) + idx_l + dense_l
     outs = _Gather.apply(cfg, *args)
     x = outs[0]

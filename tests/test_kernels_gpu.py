@@ -375,3 +375,18 @@ def test_layers_match_reference_golden_on_gpu():
     a2 = L.MultiHeadSelfAttention(12, attention_dim=4, num_heads=3, align_to='output')
     a2.load_state_dict(sub_sd(G, 'mhsa_nores'))
     torch.testing.assert_close(a2.cuda()(e2).cpu(), G['mhsa_nores/out'], **tol)
+
+
+def test_gather_without_materialisation_matches():
+    """FM-only consumers (FM inference) skip the [B,F,D] write: fm must equal the materialising launch's fm."""
+    from rec_pangu_b200 import ops
+    enc = make_enc(26, 13, 500)
+    data = make_batch(enc, 3000, device='cuda')
+    tabs = _tables(enc, 16)
+    cols, dcols = oracle.sparse_cols(enc), oracle.dense_cols(enc)
+    with torch.no_grad():
+        x, fm, _ = ops.gather([tabs[c] for c in cols], [data[c] for c in cols], [data[c] for c in dcols], want_fm=True)
+        x2, fm2, _ = ops.gather([tabs[c] for c in cols], [data[c] for c in cols], [data[c] for c in dcols], want_fm=True,
+                                want_x=False)
+    assert x2.numel() == 0
+    torch.testing.assert_close(fm2, fm, rtol=1e-6, atol=1e-6)
