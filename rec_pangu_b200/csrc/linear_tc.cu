@@ -257,16 +257,203 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
 }
 
+// ---------------------------------------------------------------------------------- persistent GEMM (v2)
+// Same math as gemm_tf32x3_kernel, restructured so that nothing on the tensor-core critical path waits for HBM:
+//   * persistent CTAs (one per SM) walk the tile list; the k-block counter runs across tiles so the rings never drain;
+//   * a deep RAW ring (kRaw stages: TMA destination for the fp32 A tile and the pre-split B hi/lo chunks) decouples the
+//     ~1-2 us load latency from the 2-stage OPERAND ring (A hi / A lo produced by the split warps);
+//   * the accumulator is double-buffered in TMEM (2 x block_n columns) and drained by four dedicated epilogue warps,
+//     so tile i's epilogue (bias / ReLU / mask / global stores) overlaps tile i+1's main loop.
+// Warps: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2-5 = split, 6-9 = epilogue (TMEM lane quarter = warp & 3).
+constexpr int V2_THREADS = 320;
+constexpr int V2_OP_STAGES = 2;
+
+template <int kRaw>
+__global__ void __launch_bounds__(V2_THREADS, 1)
+gemm_tf32x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+                      const __grid_constant__ CUtensorMap tmBlo, const TcEpilogue ep, int block_n, int num_k_blocks,
+                      int m_tiles, int n_tiles, uint32_t tmem_cols) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int b_bytes = block_n * TC_BLOCK_K * 4;
+    const int raw_bytes = TC_A_BYTES + 2 * b_bytes;                    // [A raw | B hi | B lo]
+    uint8_t* raw_base = smem;
+    uint8_t* op_base = smem + (size_t)kRaw * raw_bytes;                // [A hi | A lo] x V2_OP_STAGES
+    uint64_t* bars = reinterpret_cast<uint64_t*>(op_base + (size_t)V2_OP_STAGES * 2 * TC_A_BYTES);
+    uint64_t* full_raw = bars;                     // [kRaw]  TMA landed
+    uint64_t* empty_raw = bars + kRaw;             // [kRaw]  MMAs that read B of this stage are done
+    uint64_t* ready_op = bars + 2 * kRaw;          // [2]     split done
+    uint64_t* empty_op = ready_op + V2_OP_STAGES;  // [2]     MMAs that read A hi/lo of this stage are done
+    uint64_t* tmem_full = empty_op + V2_OP_STAGES; // [2]
+    uint64_t* tmem_empty = tmem_full + 2;          // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = m_tiles * n_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kRaw; ++s) { mbar_init(&full_raw[s], 1); mbar_init(&empty_raw[s], 1); }
+        for (int s = 0; s < V2_OP_STAGES; ++s) { mbar_init(&ready_op[s], 128); mbar_init(&empty_op[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t tx_bytes = (uint32_t)raw_bytes;
+            uint32_t g = 0;                                              // global k-block counter
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles) * TC_BLOCK_M, n0 = (tile % n_tiles) * block_n;
+                for (int kb = 0; kb < num_k_blocks; ++kb, ++g) {
+                    const int s = g % kRaw;
+                    mbar_wait(&empty_raw[s], ((g / kRaw) & 1u) ^ 1u);
+                    uint8_t* st = raw_base + (size_t)s * raw_bytes;
+                    mbar_arrive_expect_tx(&full_raw[s], tx_bytes);
+                    tma_load_2d(st, &tmA, &full_raw[s], kb * TC_BLOCK_K, m0);
+                    tma_load_2d(st + TC_A_BYTES, &tmBhi, &full_raw[s], kb * TC_BLOCK_K, n0);
+                    tma_load_2d(st + TC_A_BYTES + b_bytes, &tmBlo, &full_raw[s], kb * TC_BLOCK_K, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(TC_BLOCK_M, block_n);
+            uint32_t g = 0, t = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+                const uint32_t acc = t & 1u;
+                mbar_wait(&tmem_empty[acc], ((t >> 1) & 1u) ^ 1u);       // epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * (uint32_t)block_n;
+                for (int kb = 0; kb < num_k_blocks; ++kb, ++g) {
+                    const int s = g % kRaw, o = g % V2_OP_STAGES;
+                    mbar_wait(&ready_op[o], (g / V2_OP_STAGES) & 1u);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(op_base + (size_t)o * 2 * TC_A_BYTES);
+                    const uint32_t a_lo = a_hi + TC_A_BYTES;
+                    const uint32_t b_hi = smem_u32(raw_base + (size_t)s * raw_bytes + TC_A_BYTES);
+                    const uint32_t b_lo = b_hi + b_bytes;
+#pragma unroll
+                    for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
+                        const uint32_t koff = k * TC_UMMA_K * 4;
+                        const uint64_t da_hi = make_kmajor_sw128_desc(a_hi + koff), da_lo = make_kmajor_sw128_desc(a_lo + koff);
+                        const uint64_t db_hi = make_kmajor_sw128_desc(b_hi + koff), db_lo = make_kmajor_sw128_desc(b_lo + koff);
+                        umma_tf32(d_tmem, da_lo, db_hi, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        umma_tf32(d_tmem, da_hi, db_lo, idesc, 1u);
+                        umma_tf32(d_tmem, da_hi, db_hi, idesc, 1u);
+                    }
+                    umma_commit(&empty_op[o]);
+                    umma_commit(&empty_raw[s]);
+                }
+                umma_commit(&tmem_full[acc]);
+            }
+        }
+    } else if (warp < 6) {
+        // ---------------- split warps: raw A -> (hi, lo) operand stage
+        const int tid = threadIdx.x - 64;
+        uint32_t g = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int kb = 0; kb < num_k_blocks; ++kb, ++g) {
+                const int s = g % kRaw, o = g % V2_OP_STAGES;
+                mbar_wait(&full_raw[s], (g / kRaw) & 1u);
+                mbar_wait(&empty_op[o], ((g / V2_OP_STAGES) & 1u) ^ 1u);
+                const float4* src = reinterpret_cast<const float4*>(raw_base + (size_t)s * raw_bytes);
+                float4* hi = reinterpret_cast<float4*>(op_base + (size_t)o * 2 * TC_A_BYTES);
+                float4* lo = reinterpret_cast<float4*>(op_base + (size_t)o * 2 * TC_A_BYTES + TC_A_BYTES);
+#pragma unroll
+                for (int i = 0; i < TC_A_BYTES / 16 / 128; ++i) {
+                    const int j = tid + i * 128;
+                    const float4 v = src[j];
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+                    hi[j] = h;
+                    lo[j] = l;
+                }
+                fence_proxy_async();
+                mbar_arrive(&ready_op[o]);
+            }
+        }
+    } else {
+        // ---------------- epilogue warps: TMEM -> registers -> global (thread = output row), overlapped with the next tile
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const bool c_vec = ((ep.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.C) & 15u) == 0);
+        const bool m_vec = ep.mask != nullptr && ((ep.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.mask) & 15u) == 0);
+        uint32_t t = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+            const int m0 = (tile / n_tiles) * TC_BLOCK_M, n0 = (tile % n_tiles) * block_n;
+            const uint32_t acc = t & 1u;
+            mbar_wait(&tmem_full[acc], (t >> 1) & 1u);
+            tc_fence_after();
+            const int m = m0 + row;
+            for (int c0 = 0; c0 < block_n; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(tmem_base + acc * (uint32_t)block_n + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+                if (m < ep.M && n0 + c0 < ep.N) {
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+                    const int n = n0 + c0;
+                    const bool full = n + 16 <= ep.N;
+                    if (ep.bias != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) if (n + j < ep.N) v[j] += __ldg(ep.bias + n + j);
+                    }
+                    if (ep.relu) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                    }
+                    if (ep.mask != nullptr) {
+                        const float* mrow = ep.mask + (size_t)m * ep.ldmask + n;
+                        if (m_vec && full) {
+#pragma unroll
+                            for (int j4 = 0; j4 < 4; ++j4) {
+                                const float4 mk = __ldg(reinterpret_cast<const float4*>(mrow) + j4);
+                                v[4 * j4] = mk.x > 0.f ? v[4 * j4] : 0.f; v[4 * j4 + 1] = mk.y > 0.f ? v[4 * j4 + 1] : 0.f;
+                                v[4 * j4 + 2] = mk.z > 0.f ? v[4 * j4 + 2] : 0.f; v[4 * j4 + 3] = mk.w > 0.f ? v[4 * j4 + 3] : 0.f;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) if (n + j < ep.N) v[j] = (__ldg(mrow + j) > 0.f) ? v[j] : 0.f;
+                        }
+                    }
+                    float* crow = ep.C + (size_t)m * ep.ldc + n;
+                    if (c_vec && full) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) stg_f4(crow + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) if (n + j < ep.N) crow[j] = v[j];
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+}
+
 // ---------------------------------------------------------------------------------- weight gradient on tcgen05
 // dW[n,k] += sum_m dy[m,n] * x[m,k]: the reduction runs over the SAMPLES, so both operands are MN-major (their
-// contiguous dimension is the output dimension): A = x^T tile [128 k-columns x 64 samples], B = dy^T [block_n x 64
+// contiguous dimension is the output dimension): A = x^T tile [128 k-columns x 32 samples], B = dy^T [block_n x 32
 // samples].  For 32-bit MN-major operands the only UMMA shared-memory layout is "128B swizzle with 32B atoms"
 // (LayoutType 1; TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of 128 B, 32-byte chunks XOR-ed with (row mod 4), so a
-// K atom is 4 samples (512 B).  TMA brings [64 samples x 32 floats] boxes: one box = one 32-float MN chunk (chunks
-// LBO = 8 KiB apart) holding sixteen 4-sample K atoms (SBO = 512 B apart); one MMA (K = 8) consumes two atoms.
+// K atom is 4 samples (512 B).  TMA brings [32 samples x 32 floats] boxes: one box = one 32-float MN chunk (chunks
+// LBO = 4 KiB apart) holding eight 4-sample K atoms (SBO = 512 B apart); one MMA (K = 8) consumes two atoms.
 // Each CTA reduces one slab of samples for one 128-column tile of dW^T in TMEM and adds it to dW with fp32 reductions.
-constexpr int WG_ROWS = 64;                                  // samples per stage
-constexpr int WG_BOX_BYTES = WG_ROWS * 128;                  // one [64 x 32 fp32] box = 8 KiB
+constexpr int WG_ROWS = 32;                                  // samples per stage (4 stages in flight hide the TMA latency)
+constexpr int WG_BOX_BYTES = WG_ROWS * 128;                  // one [32 samples x 32 fp32] box = 4 KiB
 
 __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -481,6 +668,31 @@ int gemm_tc(const float* A, long long lda, const float* Bsrc, long long ldb, int
     int rc = make_map(&tmA, A, M, K, lda, TC_BLOCK_M);
     if (rc == 0) rc = make_map(&tmBhi, hi, Np, Kp, Kp, block_n);
     if (rc == 0) rc = make_map(&tmBlo, lo, Np, Kp, Kp, block_n);
+    if (rc == 0 && g_gemm_v2) {
+        const int b_bytes = block_n * TC_BLOCK_K * 4;
+        const int raw_bytes = TC_A_BYTES + 2 * b_bytes;
+        const int op_bytes = V2_OP_STAGES * 2 * TC_A_BYTES;
+        uint32_t tmem_cols = 32;
+        while ((int)tmem_cols < 2 * block_n) tmem_cols <<= 1;
+        const int m_tiles = ceil_div(M, TC_BLOCK_M);
+        const int budget = 226 * 1024 - op_bytes - 1024 - 256;
+        const int max_raw = budget / raw_bytes;
+        if (tmem_cols <= 512 && max_raw >= 2) {
+            const int grid = min(m_tiles * n_tiles, 148);
+            auto launch = [&](auto raw_tag) -> int {
+                constexpr int R = decltype(raw_tag)::value;
+                const size_t smem = (size_t)R * raw_bytes + op_bytes + (2 * R + 2 * V2_OP_STAGES + 4 + 1) * 8 + 1024;
+                cudaError_t ee = cudaFuncSetAttribute(gemm_tf32x3_v2_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (ee != cudaSuccess) return (int)ee;
+                gemm_tf32x3_v2_kernel<R><<<grid, V2_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, ep, block_n, nkb, m_tiles, n_tiles, tmem_cols);
+                return (int)cudaGetLastError();
+            };
+            if (max_raw >= 5) return launch(std::integral_constant<int, 5>{});
+            if (max_raw >= 4) return launch(std::integral_constant<int, 4>{});
+            if (max_raw >= 3) return launch(std::integral_constant<int, 3>{});
+            return launch(std::integral_constant<int, 2>{});
+        }
+    }
     if (rc == 0) {
         const int b_bytes = block_n * TC_BLOCK_K * 4;
         const int stage_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
@@ -535,6 +747,8 @@ int wgrad_tc(const float* dy, long long lddy, const float* x, long long ldx, flo
         return (int)cudaGetLastError();
     };
     const int max_stages = (200 * 1024) / stage_bytes;
+    if (max_stages >= 4) return launch(std::integral_constant<int, 4>{});
+    if (max_stages >= 3) return launch(std::integral_constant<int, 3>{});
     if (max_stages >= 2) return launch(std::integral_constant<int, 2>{});
     return RPB_ERR_UNSUPPORTED;
 }
