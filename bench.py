@@ -245,20 +245,44 @@ def run_ours(args):
         ms = float(t.item())
     value = world * B * args.steps / (ms * 1e-3)
 
-    # ---------------- e2e: host (pinned) buffers -> H2D -> step -> D2H loss, every step
-    cb0, st0 = cbs[0], steps_g[0]
-    cb0.fill_host({k: v.cpu() for k, v in cb0.as_dict().items()})
-    h2d = 0
-    for _ in range(max(3, args.warmup)):
-        h2d = cb0.h2d()
-        st0.replay()
-        float(st0.loss.item())
+    # ---------------- e2e: every step's inputs start in pinned HOST memory: H2D (3 copies) -> step -> D2H read of the loss.
+    # Double-buffered: the copy of batch i+1 runs on a copy stream while batch i computes (each batch is still copied
+    # exactly once per step inside the timed region).
+    for cb in cbs[:2]:
+        if cb.h_idx is None:
+            cb.h_idx = torch.zeros_like(cb.idx, device='cpu').pin_memory()
+            cb.h_dns = torch.zeros_like(cb.dns, device='cpu').pin_memory()
+            cb.h_lab = torch.zeros_like(cb.lab, device='cpu').pin_memory()
+        cb.h_idx.copy_(cb.idx)
+        cb.h_dns.copy_(cb.dns)
+        cb.h_lab.copy_(cb.lab)
+    main_stream = torch.cuda.current_stream()
+    copy_stream = torch.cuda.Stream()
+    ev_copied = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_done = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def e2e_loop(n):
+        h2d_bytes, lossv = 0, 0.0
+        with torch.cuda.stream(copy_stream):
+            h2d_bytes = cbs[0].h2d()
+            ev_copied[0].record(copy_stream)
+        for i in range(n):
+            cur, nxt = i % 2, (i + 1) % 2
+            if i >= 1:
+                copy_stream.wait_event(ev_done[nxt])            # buffer `nxt` was last read by step i-1
+            with torch.cuda.stream(copy_stream):
+                cbs[nxt].h2d()
+                ev_copied[nxt].record(copy_stream)
+            main_stream.wait_event(ev_copied[cur])
+            steps_g[cur].replay()
+            ev_done[cur].record(main_stream)
+            lossv = float(steps_g[cur].loss.item())              # D2H read of the step's result
+        return h2d_bytes, lossv
+
+    e2e_loop(max(3, args.warmup))
     barrier()
     e0.record()
-    for _ in range(args.steps):
-        cb0.h2d()
-        st0.replay()
-        lossv = float(st0.loss.item())                      # D2H read of the step's result
+    h2d, lossv = e2e_loop(args.steps)
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
@@ -267,7 +291,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t.item())
     e2e = {'value': world * B * args.steps / (ms_e2e * 1e-3), 'unit': 'samples/s', 'h2d_bytes_per_step': h2d,
-           'd2h_bytes_per_step': 4, 'loss': lossv}
+           'd2h_bytes_per_step': 4, 'loss': lossv, 'overlap': 'H2D of batch i+1 on a copy stream during step i'}
 
     roofline = None
     if world == 1:

@@ -531,6 +531,12 @@ class _MLP(torch.autograd.Function):
         g = _rowmajor(g)
         gparams: List[Optional[torch.Tensor]] = [None] * len(params)
         need_dx_input = ctx.needs_input_grad[1]
+        # one zero-fill for every dW/db of the tower (the kernels accumulate into them)
+        flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
+        zviews, off = [], 0
+        for p in params:
+            zviews.append(flat[off:off + p.numel()].view(p.shape))
+            off += p.numel()
 
         def mask_for(layer_in_idx):
             """Activation mask to fuse when producing the grad of acts[layer_in_idx] (= output of hidden layer-1)."""
@@ -558,8 +564,8 @@ class _MLP(torch.autograd.Function):
         kdim = W.shape[1]
         mask, dropped = mask_for(n_hidden)
         dx = torch.empty((M, kdim), dtype=torch.float32, device=dev)
-        dW = torch.zeros_like(W)
-        db = torch.zeros_like(b)
+        dW = zviews[2 * n_hidden]
+        db = zviews[2 * n_hidden + 1]
         if N == 1:
             gcol = g.reshape(-1) if g.stride(0) == 1 else g[:, 0].contiguous()
             check(lib.rpb_rowdot_bwd(_ptr(gcol), _ptr(hin), hin.stride(0), _ptr(W), _ptr(mask),
@@ -592,8 +598,8 @@ class _MLP(torch.autograd.Function):
                     dx = torch.empty((M, kdim), dtype=torch.float32, device=dev)
             else:
                 dx = None
-            dW = torch.zeros_like(W)
-            db = torch.zeros_like(b) if b is not None else None
+            dW = zviews[2 * i]
+            db = zviews[2 * i + 1]
             check(lib.rpb_linear_bwd(_ptr(dh), lddh, _ptr(hin), hin.stride(0), _ptr(W), _ptr(mask),
                                      mask.stride(0) if mask is not None else 0, _ptr(dx),
                                      dx.stride(0) if dx is not None else 0, _ptr(dW), _ptr(db), M, N, kdim, impl, st),
