@@ -201,12 +201,14 @@ gather_fwd_tile_kernel(const __grid_constant__ GatherFwdParams p) {
     for (int i = tid; i < p.Nd * S; i += 128) {
         const int j = i / S, s = i % S;
         const float dv = (s < ns) ? __ldg(p.dense[j] + b0 + s) : 0.f;
-        xs[(size_t)s * p.ldx + FD + j] = dv;
+        if (p.x != nullptr) xs[(size_t)s * p.ldx + FD + j] = dv;
         if (HAS_LR && s < ns) p.lr_in[(size_t)(b0 + s) * p.ld_lr + p.F + j] = dv;
     }
-    for (int i = tid; i < (p.ldx - FD - p.Nd) * S; i += 128) {
-        const int j = i / S, s = i % S;
-        xs[(size_t)s * p.ldx + FD + p.Nd + j] = 0.f;
+    if (p.x != nullptr) {
+        for (int i = tid; i < (p.ldx - FD - p.Nd) * S; i += 128) {
+            const int j = i / S, s = i % S;
+            xs[(size_t)s * p.ldx + FD + p.Nd + j] = 0.f;
+        }
     }
     __syncthreads();
 
@@ -235,7 +237,7 @@ gather_fwd_tile_kernel(const __grid_constant__ GatherFwdParams p) {
         for (int u = 0; u < U; ++u) {
             const int f = f0 + u;
             if (f < p.F) {
-                if (lane_on) *reinterpret_cast<float4*>(xrow + f * p.D + l * 4) = e[u].v;
+                if (lane_on && p.x != nullptr) *reinterpret_cast<float4*>(xrow + f * p.D + l * 4) = e[u].v;
                 sum.add(e[u]);
                 sq.add_sq(e[u]);
                 if (HAS_LR && valid && (f % LPR) == l) p.lr_in[(size_t)b * p.ld_lr + f] = lrv[u];
@@ -252,6 +254,7 @@ gather_fwd_tile_kernel(const __grid_constant__ GatherFwdParams p) {
         if (valid && l == 0) p.fm[b] = 0.5f * t;
     }
     // publish the tile: generic-proxy smem writes -> async proxy, then one bulk copy of ns complete rows
+    if (p.x == nullptr) return;                 // FM-only consumers: nothing to materialise
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     if (tid == 0) bulk_store_tile(p.x + (size_t)b0 * p.ldx, xs, (unsigned)((size_t)ns * p.ldx * sizeof(float)));
@@ -470,6 +473,7 @@ RPB_API int rpb_gather_fwd(const RpbGatherDesc* d, void* stream) {
     p.x = d->x; p.fm = d->fm; p.fm_s = d->fm_s; p.lr_in = d->lr_tables ? d->lr_in : nullptr;
     p.err = reinterpret_cast<long long*>(d->err);
     p.B = d->B; p.F = d->F; p.D = d->D; p.Nd = d->Nd; p.ldx = d->ldx; p.ld_lr = d->ld_lr;
+    if (d->x == nullptr) p.ldx = 0;            // no tile rows to stage
     p.G = d->G > 1 ? d->G : 1;
     p.shard_tab = d->shard_tab;
     if (p.G > 1 && (d->shard_tab == nullptr || d->lr_tables != nullptr)) return RPB_ERR_BAD_ARG;
@@ -482,7 +486,7 @@ RPB_API int rpb_gather_fwd(const RpbGatherDesc* d, void* stream) {
         if constexpr (VEC == 4 && LPR <= 16) {
             constexpr int S = 128 / LPR;
             const size_t smem = (size_t)S * p.ldx * sizeof(float) + (size_t)p.F * S * sizeof(long long);
-            if (g_gather_kernel == 0 && pol == 1 && smem <= 100 * 1024 && p.x != nullptr) {
+            if (g_gather_kernel == 0 && pol == 1 && smem <= 100 * 1024) {
                 auto launch = [&](auto kern) -> int {
                     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                     if (e != cudaSuccess) return (int)e;

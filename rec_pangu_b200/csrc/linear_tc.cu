@@ -272,27 +272,33 @@ template <int kRaw>
 __global__ void __launch_bounds__(V2_THREADS, 1)
 gemm_tf32x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                       const __grid_constant__ CUtensorMap tmBlo, const TcEpilogue ep, int block_n, int num_k_blocks,
-                      int m_tiles, int n_tiles, uint32_t tmem_cols) {
+                      int m_tiles, int n_tiles, uint32_t tmem_cols, int b_resident) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int b_bytes = block_n * TC_BLOCK_K * 4;
-    const int raw_bytes = TC_A_BYTES + 2 * b_bytes;                    // [A raw | B hi | B lo]
+    // b_resident (n_tiles == 1 and the whole pre-split weight fits): B hi/lo of every k-block is loaded ONCE per CTA
+    // and stays in shared memory for all of its tiles; the raw ring then carries only A and is released by the split
+    // warps themselves.  Otherwise each raw stage is [A raw | B hi | B lo] and is released by the MMA commit.
+    const int raw_bytes = b_resident ? TC_A_BYTES : TC_A_BYTES + 2 * b_bytes;
     uint8_t* raw_base = smem;
     uint8_t* op_base = smem + (size_t)kRaw * raw_bytes;                // [A hi | A lo] x V2_OP_STAGES
-    uint64_t* bars = reinterpret_cast<uint64_t*>(op_base + (size_t)V2_OP_STAGES * 2 * TC_A_BYTES);
+    uint8_t* bres_base = op_base + (size_t)V2_OP_STAGES * 2 * TC_A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bres_base + (b_resident ? (size_t)num_k_blocks * 2 * b_bytes : 0));
     uint64_t* full_raw = bars;                     // [kRaw]  TMA landed
     uint64_t* empty_raw = bars + kRaw;             // [kRaw]  MMAs that read B of this stage are done
     uint64_t* ready_op = bars + 2 * kRaw;          // [2]     split done
     uint64_t* empty_op = ready_op + V2_OP_STAGES;  // [2]     MMAs that read A hi/lo of this stage are done
     uint64_t* tmem_full = empty_op + V2_OP_STAGES; // [2]
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* b_full = tmem_empty + 2;             // [1]     resident B landed
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = m_tiles * n_tiles;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kRaw; ++s) { mbar_init(&full_raw[s], 1); mbar_init(&empty_raw[s], 1); }
+        for (int s = 0; s < kRaw; ++s) { mbar_init(&full_raw[s], 1); mbar_init(&empty_raw[s], b_resident ? 128 : 1); }
+        mbar_init(b_full, 1);
         for (int s = 0; s < V2_OP_STAGES; ++s) { mbar_init(&ready_op[s], 128); mbar_init(&empty_op[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
         fence_barrier_init();
@@ -307,6 +313,13 @@ gemm_tf32x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         if (lane == 0) {
             const uint32_t tx_bytes = (uint32_t)raw_bytes;
             uint32_t g = 0;                                              // global k-block counter
+            if (b_resident && blockIdx.x < num_tiles) {
+                mbar_arrive_expect_tx(b_full, (uint32_t)(num_k_blocks * 2 * b_bytes));
+                for (int kb = 0; kb < num_k_blocks; ++kb) {
+                    tma_load_2d(bres_base + (size_t)kb * 2 * b_bytes, &tmBhi, b_full, kb * TC_BLOCK_K, 0);
+                    tma_load_2d(bres_base + (size_t)kb * 2 * b_bytes + b_bytes, &tmBlo, b_full, kb * TC_BLOCK_K, 0);
+                }
+            }
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m0 = (tile / n_tiles) * TC_BLOCK_M, n0 = (tile % n_tiles) * block_n;
                 for (int kb = 0; kb < num_k_blocks; ++kb, ++g) {
@@ -315,8 +328,10 @@ gemm_tf32x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     uint8_t* st = raw_base + (size_t)s * raw_bytes;
                     mbar_arrive_expect_tx(&full_raw[s], tx_bytes);
                     tma_load_2d(st, &tmA, &full_raw[s], kb * TC_BLOCK_K, m0);
-                    tma_load_2d(st + TC_A_BYTES, &tmBhi, &full_raw[s], kb * TC_BLOCK_K, n0);
-                    tma_load_2d(st + TC_A_BYTES + b_bytes, &tmBlo, &full_raw[s], kb * TC_BLOCK_K, n0);
+                    if (!b_resident) {
+                        tma_load_2d(st + TC_A_BYTES, &tmBhi, &full_raw[s], kb * TC_BLOCK_K, n0);
+                        tma_load_2d(st + TC_A_BYTES + b_bytes, &tmBlo, &full_raw[s], kb * TC_BLOCK_K, n0);
+                    }
                 }
             }
         }
@@ -324,6 +339,7 @@ gemm_tf32x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(TC_BLOCK_M, block_n);
             uint32_t g = 0, t = 0;
+            if (b_resident && blockIdx.x < num_tiles) mbar_wait(b_full, 0);
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
                 const uint32_t acc = t & 1u;
                 mbar_wait(&tmem_empty[acc], ((t >> 1) & 1u) ^ 1u);       // epilogue drained this accumulator
@@ -335,7 +351,8 @@ gemm_tf32x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     tc_fence_after();
                     const uint32_t a_hi = smem_u32(op_base + (size_t)o * 2 * TC_A_BYTES);
                     const uint32_t a_lo = a_hi + TC_A_BYTES;
-                    const uint32_t b_hi = smem_u32(raw_base + (size_t)s * raw_bytes + TC_A_BYTES);
+                    const uint32_t b_hi = b_resident ? smem_u32(bres_base + (size_t)kb * 2 * b_bytes)
+                                                     : smem_u32(raw_base + (size_t)s * raw_bytes + TC_A_BYTES);
                     const uint32_t b_lo = b_hi + b_bytes;
 #pragma unroll
                     for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
@@ -347,7 +364,7 @@ gemm_tf32x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                         umma_tf32(d_tmem, da_hi, db_hi, idesc, 1u);
                     }
                     umma_commit(&empty_op[o]);
-                    umma_commit(&empty_raw[s]);
+                    if (!b_resident) umma_commit(&empty_raw[s]);
                 }
                 umma_commit(&tmem_full[acc]);
             }
@@ -378,6 +395,7 @@ gemm_tf32x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 }
                 fence_proxy_async();
                 mbar_arrive(&ready_op[o]);
+                if (b_resident) mbar_arrive(&empty_raw[s]);              // the raw A tile has been consumed
             }
         }
     } else {
@@ -670,23 +688,28 @@ int gemm_tc(const float* A, long long lda, const float* Bsrc, long long ldb, int
     if (rc == 0) rc = make_map(&tmBlo, lo, Np, Kp, Kp, block_n);
     if (rc == 0 && g_gemm_v2) {
         const int b_bytes = block_n * TC_BLOCK_K * 4;
-        const int raw_bytes = TC_A_BYTES + 2 * b_bytes;
         const int op_bytes = V2_OP_STAGES * 2 * TC_A_BYTES;
+        const int bres_bytes = nkb * 2 * b_bytes;
+        const int b_resident = (n_tiles == 1 && bres_bytes <= 72 * 1024) ? 1 : 0;
+        const int raw_bytes = b_resident ? TC_A_BYTES : TC_A_BYTES + 2 * b_bytes;
         uint32_t tmem_cols = 32;
         while ((int)tmem_cols < 2 * block_n) tmem_cols <<= 1;
         const int m_tiles = ceil_div(M, TC_BLOCK_M);
-        const int budget = 226 * 1024 - op_bytes - 1024 - 256;
+        const int budget = 226 * 1024 - op_bytes - (b_resident ? bres_bytes : 0) - 1024 - 256;
         const int max_raw = budget / raw_bytes;
         if (tmem_cols <= 512 && max_raw >= 2) {
             const int grid = min(m_tiles * n_tiles, 148);
             auto launch = [&](auto raw_tag) -> int {
                 constexpr int R = decltype(raw_tag)::value;
-                const size_t smem = (size_t)R * raw_bytes + op_bytes + (2 * R + 2 * V2_OP_STAGES + 4 + 1) * 8 + 1024;
+                const size_t smem = (size_t)R * raw_bytes + op_bytes + (b_resident ? bres_bytes : 0) +
+                                    (2 * R + 2 * V2_OP_STAGES + 4 + 2) * 8 + 1024;
                 cudaError_t ee = cudaFuncSetAttribute(gemm_tf32x3_v2_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (ee != cudaSuccess) return (int)ee;
-                gemm_tf32x3_v2_kernel<R><<<grid, V2_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, ep, block_n, nkb, m_tiles, n_tiles, tmem_cols);
+                gemm_tf32x3_v2_kernel<R><<<grid, V2_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, ep, block_n, nkb, m_tiles, n_tiles,
+                                                                        tmem_cols, b_resident);
                 return (int)cudaGetLastError();
             };
+            if (max_raw >= 6) return launch(std::integral_constant<int, 6>{});
             if (max_raw >= 5) return launch(std::integral_constant<int, 5>{});
             if (max_raw >= 4) return launch(std::integral_constant<int, 4>{});
             if (max_raw >= 3) return launch(std::integral_constant<int, 3>{});

@@ -26,3 +26,30 @@ def test_tcgen05_matches_simt_on_deepfm_layer1_shape():
     y1 = ops.linear(x, W, b, K=K, impl=1)
     y2 = ops.linear(x, W, b, K=K, impl=2)
     assert (y1 - y2).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize('M,N,K,relu', [(1000, 64, 429, True), (640, 428, 64, False)])
+def test_linear_tcgen05_v1_kernel_still_correct(M, N, K, relu):
+    """The one-tile-per-CTA kernel (gemm_v2 = 0) stays available as a cross-check of the persistent kernel."""
+    from rec_pangu_b200 import _lib
+    lib = _lib.load()
+    assert lib.rpb_set_option(b'gemm_v2', 0) == 0
+    try:
+        _check_linear(M, N, K, relu, impl=2, tol=1e-5)
+    finally:
+        lib.rpb_set_option(b'gemm_v2', 1)
+
+
+def test_persistent_gemm_many_tiles_and_resident_weights():
+    """More tiles than SMs (persistent loop, TMEM double buffering) with resident (K=64) and streamed (K=429) weights."""
+    from rec_pangu_b200 import ops
+    torch.manual_seed(1)
+    for M, N, K in ((148 * 128 * 3 + 77, 64, 64), (148 * 128 * 2 + 5, 64, 429), (40000, 224, 64)):
+        ld = (K + 3) // 4 * 4
+        x = torch.zeros(M, ld, device='cuda')
+        x[:, :K] = torch.randn(M, K, device='cuda')
+        W = torch.randn(N, K, device='cuda') / K ** 0.5
+        b = torch.randn(N, device='cuda')
+        y1 = ops.linear(x, W, b, K=K, impl=1)
+        y2 = ops.linear(x, W, b, K=K, impl=2)
+        assert (y1 - y2).abs().max().item() < 3e-5, (M, N, K)
