@@ -123,6 +123,14 @@ int rpb_linear_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, c
                    const float* mask, int64_t ldmask, float* dx, int64_t lddx, float* dW, float* db,
                    int M, int N, int K, int impl, void* stream);
 
+/* First-layer dx GEMM fused with the gradient scatter: computes dx = dy[M,N] @ W[N,K] tile by tile on tcgen05 and, in
+ * the epilogue, adds dx[m, f*D:(f+1)*D] + dfm[m]*(fm_s[m,:] - x[m, f*D:(f+1)*D]) straight into grads[f][idx[f][m], :]
+ * (fields of RpbScatterDesc: B (= M), F, D, grads, rows, idx, x, ldx, dfm, fm_s; dx / lddx / LR fields are ignored,
+ * sharded tables unsupported).  dx is never written to HBM.  Returns RPB_ERR_UNSUPPORTED when the persistent tcgen05
+ * kernel cannot take the shape (the caller then runs rpb_linear_bwd + rpb_gather_bwd). */
+int rpb_linear_dx_scatter(const float* dy, int64_t lddy, const float* W, int M, int N, int K,
+                          const RpbScatterDesc* d, void* stream);
+
 /* Row dot (N=1 linear): out[m] = x[m,:K].w + bias[0] + add0[m] + add1[m] + add2[m]  (NULL addends skipped).
  * Final Linear(->1) of the MLP plus the logit sum of ranking/deepfm.py:61, xdeepfm.py:69, autoint.py:72-81. */
 int rpb_rowdot_fwd(const float* x, int64_t ldx, const float* w, const float* bias, const float* add0,

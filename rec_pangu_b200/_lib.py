@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(_HERE, 'librec_pangu_b200.so')
 ABI_VERSION = 2
 MAX_FIELDS = 64
 MAX_DENSE = 64
+ERR_UNSUPPORTED = -1
 
 _vp = C.c_void_p
 _i32 = C.c_int32
@@ -51,6 +52,7 @@ SIGNATURES = {
     'rpb_linear_fwd': (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     'rpb_linear_bwd': (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _vp,
                                  C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    'rpb_linear_dx_scatter': (C.c_int, [_vp, _i64, _vp, C.c_int, C.c_int, C.c_int, C.POINTER(ScatterDesc), _vp]),
     'rpb_rowdot_fwd': (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     'rpb_rowdot_bwd': (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _vp, C.c_int, C.c_int, _vp]),
     'rpb_sigmoid_bce_fwd': (C.c_int, [_vp, _vp, _vp, _vp, _f32, _f32, C.c_int, _vp, _vp]),

@@ -23,6 +23,20 @@ extern int g_gemm_v2;                                // api.cu: 1 = persistent G
 extern int g_wgrad_tc;                               // api.cu: 1 = tcgen05 weight-gradient kernel in auto mode
 extern int g_gather_policy;                          // api.cu: 0 = L1 no-allocate, 1 = + L2::64B, 2 = __ldg
 
+// Fused scatter epilogue of the layer-1 dx GEMM: instead of writing dx[M, F*D+Nd] the epilogue adds every sample's
+// per-field gradient row straight into the table gradients,
+//   grads[f][idx[f][m], :] += dx[m, f*D:(f+1)*D] + dfm[m] * (fm_s[m, :] - x[m, f*D:(f+1)*D]),
+// i.e. rpb_gather_bwd runs inside the GEMM epilogue and the 113 MB dx round trip through HBM disappears.
+struct TcScatter {
+    float* grads[RPB_MAX_FIELDS];
+    const long long* idx[RPB_MAX_FIELDS];
+    long long rows[RPB_MAX_FIELDS];
+    const float* x; long long ldx;       // forward feature rows (FM term), may be null when dfm is null
+    const float* dfm;                    // [M] or null
+    const float* fm_s;                   // [M, D] or null
+    int F, D, enabled;
+};
+
 // epilogue descriptor of the tcgen05 GEMM (linear_tc.cu)
 struct TcEpilogue {
     float* C; long long ldc;
@@ -30,6 +44,7 @@ struct TcEpilogue {
     const float* mask; long long ldmask;
     int M, N;            // valid extents
     int relu;
+    const TcScatter* sc; // host pointer (copied into the kernel parameter when enabled), else null
 };
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -272,7 +272,8 @@ template <int kRaw>
 __global__ void __launch_bounds__(V2_THREADS, 1)
 gemm_tf32x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                       const __grid_constant__ CUtensorMap tmBlo, const TcEpilogue ep, int block_n, int num_k_blocks,
-                      int m_tiles, int n_tiles, uint32_t tmem_cols, int b_resident) {
+                      int m_tiles, int n_tiles, uint32_t tmem_cols, int b_resident,
+                      const __grid_constant__ TcScatter sc) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int b_bytes = block_n * TC_BLOCK_K * 4;
@@ -414,7 +415,33 @@ gemm_tf32x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             for (int c0 = 0; c0 < block_n; c0 += 16) {
                 uint32_t r[16];
                 tmem_ld16(tmem_base + acc * (uint32_t)block_n + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
-                if (m < ep.M && n0 + c0 < ep.N) {
+                if (sc.enabled) {
+                    // ---- fused scatter-add of the table gradients (see TcScatter)
+                    if (m < ep.M) {
+                        const int FD = sc.F * sc.D;
+                        const float cfm = sc.dfm != nullptr ? __ldg(sc.dfm + m) : 0.f;
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const int n4 = n0 + c0 + 4 * j4;
+                            if (n4 < FD) {
+                                const int f = n4 / sc.D, d = n4 - f * sc.D;
+                                if (sc.grads[f] != nullptr) {
+                                    long long ix = __ldg(sc.idx[f] + m);
+                                    if ((unsigned long long)ix >= (unsigned long long)sc.rows[f]) ix = 0;
+                                    float4 gv = make_float4(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1]),
+                                                            __uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3]));
+                                    if (sc.dfm != nullptr) {
+                                        const float4 e = ldg_f4_stream(sc.x + (size_t)m * sc.ldx + n4);
+                                        const float4 sv = ldg_f4(sc.fm_s + (size_t)m * sc.D + d);
+                                        gv.x = fmaf(cfm, sv.x - e.x, gv.x); gv.y = fmaf(cfm, sv.y - e.y, gv.y);
+                                        gv.z = fmaf(cfm, sv.z - e.z, gv.z); gv.w = fmaf(cfm, sv.w - e.w, gv.w);
+                                    }
+                                    red_add_f4(sc.grads[f] + (size_t)ix * sc.D + d, gv);
+                                }
+                            }
+                        }
+                    }
+                } else if (m < ep.M && n0 + c0 < ep.N) {
                     float v[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
@@ -705,8 +732,9 @@ int gemm_tc(const float* A, long long lda, const float* Bsrc, long long ldb, int
                                     (2 * R + 2 * V2_OP_STAGES + 4 + 2) * 8 + 1024;
                 cudaError_t ee = cudaFuncSetAttribute(gemm_tf32x3_v2_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (ee != cudaSuccess) return (int)ee;
+                static const TcScatter no_scatter{};
                 gemm_tf32x3_v2_kernel<R><<<grid, V2_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, ep, block_n, nkb, m_tiles, n_tiles,
-                                                                        tmem_cols, b_resident);
+                                                                        tmem_cols, b_resident, ep.sc != nullptr ? *ep.sc : no_scatter);
                 return (int)cudaGetLastError();
             };
             if (max_raw >= 6) return launch(std::integral_constant<int, 6>{});
@@ -716,6 +744,7 @@ int gemm_tc(const float* A, long long lda, const float* Bsrc, long long ldb, int
             return launch(std::integral_constant<int, 2>{});
         }
     }
+    if (rc == 0 && ep.sc != nullptr) return RPB_ERR_UNSUPPORTED;       // the fused scatter epilogue exists in the v2 kernel only
     if (rc == 0) {
         const int b_bytes = block_n * TC_BLOCK_K * 4;
         const int stage_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
@@ -797,7 +826,7 @@ RPB_API int rpb_linear_fwd(const float* x, int64_t ldx, const float* W, const fl
     const bool tc_ok = tc_shape_ok(x, ldx, M, N, K);
     if (impl == 2 && !tc_ok) return RPB_ERR_UNSUPPORTED;
     if (impl == 2 || (impl == 0 && tc_ok && M >= 512)) {
-        TcEpilogue ep{y, ldy, bias, nullptr, 0, M, N, act == 1};
+        TcEpilogue ep{y, ldy, bias, nullptr, 0, M, N, act == 1, nullptr};
         return gemm_tc(x, ldx, W, K, 0, ep, M, N, K, st);
     }
     return linear_fwd_simt(x, ldx, W, bias, y, ldy, M, N, K, act, st);
@@ -815,7 +844,7 @@ RPB_API int rpb_linear_bwd(const float* dy, int64_t lddy, const float* x, int64_
         if (impl == 2 && !tc_ok) return RPB_ERR_UNSUPPORTED;
         int rc;
         if (impl == 2 || (impl == 0 && tc_ok && M >= 512)) {
-            TcEpilogue ep{dx, lddx, nullptr, mask, ldmask, M, K, 0};
+            TcEpilogue ep{dx, lddx, nullptr, mask, ldmask, M, K, 0, nullptr};
             rc = gemm_tc(dy, lddy, W, K, 1, ep, M, K, N, st);
         } else {
             rc = linear_dx_simt(dy, lddy, W, mask, ldmask, dx, lddx, M, N, K, st);
@@ -834,4 +863,25 @@ RPB_API int rpb_linear_bwd(const float* dy, int64_t lddy, const float* x, int64_
         if (rc != 0) return rc;
     }
     return 0;
+}
+
+// dx GEMM of the first MLP layer fused with the embedding-gradient scatter (TcScatter): dx is never written.
+RPB_API int rpb_linear_dx_scatter(const float* dy, int64_t lddy, const float* W, int M, int N, int K,
+                                  const RpbScatterDesc* d, void* stream) {
+    if (dy == nullptr || W == nullptr || d == nullptr || M <= 0 || N <= 0 || K <= 0) return RPB_ERR_BAD_ARG;
+    if (d->B != M || d->F > RPB_MAX_FIELDS || d->F * d->D > K || (d->D % 4) != 0 || d->G > 1) return RPB_ERR_UNSUPPORTED;
+    if (d->dfm != nullptr && (d->x == nullptr || d->fm_s == nullptr || (d->ldx % 4) != 0)) return RPB_ERR_BAD_ARG;
+    if (!g_gemm_v2 || !tc_shape_ok(dy, lddy, M, K, N)) return RPB_ERR_UNSUPPORTED;
+    TcScatter sc{};
+    for (int f = 0; f < d->F; ++f) {
+        sc.grads[f] = d->grads ? d->grads[f] : nullptr;
+        sc.idx[f] = reinterpret_cast<const long long*>(d->idx[f]);
+        sc.rows[f] = d->rows[f];
+        if (sc.grads[f] != nullptr && (reinterpret_cast<uintptr_t>(sc.grads[f]) & 15u)) return RPB_ERR_UNSUPPORTED;
+    }
+    sc.x = d->x; sc.ldx = d->ldx; sc.dfm = d->dfm; sc.fm_s = d->fm_s; sc.F = d->F; sc.D = d->D; sc.enabled = 1;
+    TcEpilogue ep{nullptr, 0, nullptr, nullptr, 0, M, K, 0, &sc};
+    // only the embedding columns matter: output width = F*D (the dense-feature columns of dx have no consumer)
+    ep.N = d->F * d->D;
+    return gemm_tc(dy, lddy, W, K, 1, ep, M, d->F * d->D, N, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -193,7 +193,7 @@ RPB_API int rpb_matmul_kn_fwd(const float* x, int64_t ldx, const float* Wkn, int
     const bool tc_ok = tc_shape_ok(x, ldx, M, N, K);
     if (impl == 2 && !tc_ok) return RPB_ERR_UNSUPPORTED;
     if (impl == 2 || (impl == 0 && tc_ok && M >= 512)) {
-        TcEpilogue ep{y, ldy, bias, nullptr, 0, M, N, 0};
+        TcEpilogue ep{y, ldy, bias, nullptr, 0, M, N, 0, nullptr};
         return gemm_tc(x, ldx, Wkn, ldw, 1, ep, M, N, K, st);      // B operand [N,K] = Wkn^T
     }
     return sgemm_kn_simt(x, ldx, Wkn, ldw, bias, y, ldy, M, N, K, st);
@@ -211,7 +211,7 @@ RPB_API int rpb_matmul_kn_bwd(const float* dy, int64_t lddy, const float* x, int
         const bool tc_ok = tc_shape_ok(dy, lddy, M, K, N);
         if (impl == 2 && !tc_ok) return RPB_ERR_UNSUPPORTED;
         if (impl == 2 || (impl == 0 && tc_ok && M >= 512)) {
-            TcEpilogue ep{dx, lddx, nullptr, nullptr, 0, M, K, 0};
+            TcEpilogue ep{dx, lddx, nullptr, nullptr, 0, M, K, 0, nullptr};
             rc = gemm_tc(dy, lddy, Wkn, ldw, 0, ep, M, K, N, st);
         } else {
             rc = sgemm_nk_simt(dy, lddy, Wkn, ldw, dx, lddx, M, K, N, st);

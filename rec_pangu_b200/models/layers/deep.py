@@ -58,6 +58,15 @@ class MLP(nn.Module):
             raise NotImplementedError('MLP output_activation is not used by the ranking hot path')
         self.net = nn.Sequential(*layers)      # same module indices as the reference => same state_dict keys
 
+    def layer_params(self):
+        """(weights, biases, relu flags, dropout rates) in layer order, for fused model-level kernels."""
+        Ws = [self.net[i].weight for i, _, _ in self._plan]
+        bs = [self.net[i].bias for i, _, _ in self._plan]
+        if self._out_idx is not None:
+            Ws.append(self.net[self._out_idx].weight)
+            bs.append(self.net[self._out_idx].bias)
+        return Ws, bs, [r for _, r, _ in self._plan], [p for _, _, p in self._plan]
+
     def forward(self, x: torch.Tensor, K: Optional[int] = None) -> torch.Tensor:
         """x: [B, >=input_dim]; only the first ``K`` (= input_dim) columns are read, so the padded feature row from
         EmbeddingLayer.feature_row can be passed without a cat/copy."""

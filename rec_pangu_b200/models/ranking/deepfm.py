@@ -22,7 +22,18 @@ class DeepFM(BaseModel):
         self.reset_parameters()
 
     def forward(self, data, is_training=True):
-        # one launch: gather 26 rows/sample -> feature row x (= cat(emb.flatten, dense)) + FM second-order term
-        x, fm_out, _ = self.embedding_layer.feature_row(data, with_dense=True, want_fm=True)
+        emb = self.embedding_layer
+        if emb._shards is None and self.dnn._out_idx is not None:
+            # whole body as one fused autograd node (ops.deepfm_core): gather+FM in one launch, MLP on tcgen05, the
+            # logit sum folded into the last row-dot, and in backward the layer-1 dx GEMM scatters the embedding
+            # gradients from its epilogue (no dx round trip through HBM)
+            from ... import ops
+            Ws, bs, relu, drops = self.dnn.layer_params()
+            logit = ops.deepfm_core(emb.tables(), [data[c] for c in emb.emb_feature], [data[c] for c in emb.dense_feature],
+                                    Ws, bs, n_hidden=len(relu), relu=relu, dropout=drops, training=self.training,
+                                    grad_store=emb._grad_store if emb.grad_mode == 'persistent' else None)
+            return self._finish(logit, data, is_training)
+        # row-sharded tables: one launch gathers 26 rows/sample over NVLink -> feature row x + FM second-order term
+        x, fm_out, _ = emb.feature_row(data, with_dense=True, want_fm=True)
         dnn_output = self.dnn(x, K=self.dnn_input_dim)                  # [B,1]
         return self._finish(fm_out.unsqueeze(1) + dnn_output, data, is_training)

@@ -12,7 +12,7 @@ import torch
 from . import _lib
 from ._lib import GatherDesc, ScatterDesc, check
 
-__all__ = ['GradStore', 'gather', 'gather_sharded', 'sharded_clean', 'fm_interaction', 'mlp_forward', 'sigmoid_bce', 'linear', 'feature_row_stride',
+__all__ = ['GradStore', 'deepfm_core', 'gather', 'gather_sharded', 'sharded_clean', 'fm_interaction', 'mlp_forward', 'sigmoid_bce', 'linear', 'feature_row_stride',
            'check_index_errors', 'set_gemm_impl', 'get_gemm_impl', 'launch_count', 'reset_launch_count']
 
 _GEMM_IMPL = int(__import__('os').environ.get('RPB_GEMM_IMPL', '0'))   # 0 auto, 1 SIMT fp32, 2 tcgen05 3xTF32
@@ -458,56 +458,170 @@ def fm_interaction(e: torch.Tensor, mode: str = 'sum') -> torch.Tensor:
 
 
 # ------------------------------------------------------------------ MLP tower
+def _mlp_fwd(cfg, x, params, addend=None):
+    """Forward of Linear(+ReLU)(+Dropout) x n_hidden + Linear(out).  `addend` ([M]) is added to a 1-wide output inside
+    the final row-dot kernel (DeepFM: logit = fm + dnn).  Returns (out, acts, pre_drop, seeds)."""
+    n_hidden, K = cfg['n_hidden'], cfg['K']
+    relu, drops, training, impl = cfg['relu'], cfg['dropout'], cfg['training'], cfg['impl']
+    lib = _lib.load()
+    st = _stream()
+    M = x.shape[0]
+    acts = []          # acts[i] = input of hidden layer i (post-ReLU/post-dropout of i-1); acts[n_hidden] = last hidden out
+    pre_drop = []      # pre-dropout ReLU outputs for layers with active dropout (else None)
+    seeds = []
+    h, ldh, kdim = x, x.stride(0), K
+    for i in range(n_hidden):
+        W, b = params[2 * i], params[2 * i + 1]
+        N = W.shape[0]
+        y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+        check(lib.rpb_linear_fwd(_ptr(h), ldh, _ptr(W), _ptr(b), _ptr(y), N, M, N, kdim, 1 if relu[i] else 0,
+                                 impl, st), 'rpb_linear_fwd')
+        _count(2 if impl != 1 else 1)
+        acts.append(h)
+        p = drops[i] if training else 0.0
+        if p > 0.0:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            yd = torch.empty_like(y)
+            check(lib.rpb_dropout_fwd(_ptr(y), _ptr(yd), y.numel(), p, seed, st), 'rpb_dropout_fwd')
+            _count()
+            pre_drop.append(y)
+            seeds.append(seed)
+            y = yd
+        else:
+            pre_drop.append(None)
+            seeds.append(0)
+        h, ldh, kdim = y, N, N
+    W, b = params[2 * n_hidden], params[2 * n_hidden + 1]
+    N = W.shape[0]
+    out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    if N == 1:
+        check(lib.rpb_rowdot_fwd(_ptr(h), ldh, _ptr(W), _ptr(b), _ptr(addend), None, None, _ptr(out), M, kdim, st),
+              'rpb_rowdot_fwd')
+        _count()
+    else:
+        if addend is not None:
+            raise NotImplementedError('addend with a multi-column MLP output')
+        check(lib.rpb_linear_fwd(_ptr(h), ldh, _ptr(W), _ptr(b), _ptr(out), N, M, N, kdim, 0, impl, st),
+              'rpb_linear_fwd')
+        _count(2 if impl != 1 else 1)
+    acts.append(h)
+    return out, acts, pre_drop, seeds
+
+
+def _mlp_bwd(cfg, acts, pre_drop, seeds, params, g, need_dx_input, layer0_hook=None):
+    """Backward of _mlp_fwd.  Returns (gx | None, gparams).  `layer0_hook(dh, lddh, W0) -> bool`, when given, consumes the
+    pre-activation gradient of the first layer instead of the dx GEMM (fused dx + scatter); False = not handled."""
+    n_hidden, K = cfg['n_hidden'], cfg['K']
+    relu, drops, training, impl = cfg['relu'], cfg['dropout'], cfg['training'], cfg['impl']
+    lib = _lib.load()
+    st = _stream()
+    M = acts[0].shape[0]
+    dev = acts[0].device
+    g = _rowmajor(g)
+    gparams: List[Optional[torch.Tensor]] = [None] * len(params)
+    # one zero-fill for every dW/db of the tower (the kernels accumulate into them)
+    flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
+    zviews, off = [], 0
+    for p in params:
+        zviews.append(flat[off:off + p.numel()].view(p.shape))
+        off += p.numel()
+
+    def mask_for(layer_in_idx):
+        """Activation mask to fuse when producing the grad of acts[layer_in_idx] (= output of hidden layer-1)."""
+        j = layer_in_idx - 1          # hidden layer that produced this activation
+        if j < 0:
+            return None, False
+        p = drops[j] if training else 0.0
+        if p > 0.0:
+            return None, True         # dropout active: unfused elementwise backward handles ReLU+dropout
+        return (acts[layer_in_idx] if relu[j] else None), False
+
+    def finish_drop(dh, j):
+        """dh = grad wrt dropped output of hidden layer j -> grad wrt its pre-activation."""
+        p = drops[j]
+        out = torch.empty_like(dh)
+        check(lib.rpb_dropout_bwd(_ptr(dh), _ptr(pre_drop[j]) if relu[j] else None, _ptr(out), dh.numel(), p,
+                                  seeds[j], st), 'rpb_dropout_bwd')
+        _count()
+        return out
+
+    # output layer (always present: the reference only builds MLPs with output_dim=1 on this path)
+    W, b = params[2 * n_hidden], params[2 * n_hidden + 1]
+    N = W.shape[0]
+    hin = acts[n_hidden]
+    kdim = W.shape[1]
+    mask, dropped = mask_for(n_hidden)
+    dx = torch.empty((M, kdim), dtype=torch.float32, device=dev)
+    dW = zviews[2 * n_hidden]
+    db = zviews[2 * n_hidden + 1]
+    if N == 1:
+        gcol = g.reshape(-1) if g.stride(0) == 1 else g[:, 0].contiguous()
+        check(lib.rpb_rowdot_bwd(_ptr(gcol), _ptr(hin), hin.stride(0), _ptr(W), _ptr(mask),
+                                 mask.stride(0) if mask is not None else 0, _ptr(dx), dx.stride(0),
+                                 _ptr(dW), _ptr(db), M, kdim, st), 'rpb_rowdot_bwd')
+        _count(2)
+    else:
+        check(lib.rpb_linear_bwd(_ptr(g), g.stride(0), _ptr(hin), hin.stride(0), _ptr(W), _ptr(mask),
+                                 mask.stride(0) if mask is not None else 0, _ptr(dx), dx.stride(0),
+                                 _ptr(dW), _ptr(db), M, N, kdim, impl, st), 'rpb_linear_bwd')
+        _count(3)
+    gparams[2 * n_hidden], gparams[2 * n_hidden + 1] = dW, db
+    dh = dx
+    lddh = dx.stride(0)
+    if dropped:
+        dh = finish_drop(dh, n_hidden - 1)
+
+    for i in range(n_hidden - 1, -1, -1):
+        W, b = params[2 * i], params[2 * i + 1]
+        N, kdim = W.shape[0], (K if i == 0 else W.shape[1])
+        hin = acts[i]
+        need_dx = i > 0 or need_dx_input
+        mask, dropped = mask_for(i)
+        dW = zviews[2 * i]
+        db = zviews[2 * i + 1]
+        if i == 0 and layer0_hook is not None:
+            # parameter gradients only; dx is consumed by the hook (fused dx GEMM + embedding-gradient scatter)
+            check(lib.rpb_linear_bwd(_ptr(dh), lddh, _ptr(hin), hin.stride(0), _ptr(W), None, 0, None, 0, _ptr(dW), _ptr(db),
+                                     M, N, kdim, impl, st), 'rpb_linear_bwd')
+            _count(2)
+            gparams[0], gparams[1] = dW, db
+            if layer0_hook(dh, lddh, W):
+                return None, gparams
+            dW = db = None                       # not handled: fall through and compute dx the plain way
+            need_dx = True
+        if need_dx:
+            if i == 0:
+                dx = torch.empty((M, hin.stride(0)), dtype=torch.float32, device=dev)
+                if hin.stride(0) > kdim:
+                    dx[:, kdim:].zero_()
+            else:
+                dx = torch.empty((M, kdim), dtype=torch.float32, device=dev)
+        else:
+            dx = None
+        check(lib.rpb_linear_bwd(_ptr(dh), lddh, _ptr(hin), hin.stride(0), _ptr(W), _ptr(mask),
+                                 mask.stride(0) if mask is not None else 0, _ptr(dx),
+                                 dx.stride(0) if dx is not None else 0, _ptr(dW), _ptr(db), M, N, kdim, impl, st),
+              'rpb_linear_bwd')
+        _count(3)
+        if dW is not None:
+            gparams[2 * i], gparams[2 * i + 1] = dW, db
+        dh = dx
+        lddh = dx.stride(0) if dx is not None else 0
+        if dropped and dh is not None:
+            dh = finish_drop(dh, i - 1)
+    gx = None
+    if dh is not None:
+        gx = dh if dh.shape[1] == acts[0].shape[1] else dh[:, :acts[0].shape[1]]
+    return gx, gparams
+
+
 class _MLP(torch.autograd.Function):
-    """Linear(+ReLU)(+Dropout) x n_hidden [+ Linear(out)] as one autograd node so ReLU backward is fused into
-    the producing GEMM's epilogue (mask = saved activation)."""
+    """Linear(+ReLU)(+Dropout) x n_hidden + Linear(out) as one autograd node so ReLU backward is fused into the
+    producing GEMM's epilogue (mask = saved activation)."""
 
     @staticmethod
     def forward(ctx, cfg, x, *params):
-        n_hidden, has_out, K = cfg['n_hidden'], cfg['has_out'], cfg['K']
-        relu, drops, training, impl = cfg['relu'], cfg['dropout'], cfg['training'], cfg['impl']
-        lib = _lib.load()
-        st = _stream()
-        M = x.shape[0]
-        acts = []          # saved layer inputs: acts[i] = input of hidden layer i (post-ReLU/post-dropout of i-1)
-        pre_drop = []      # pre-dropout ReLU outputs for layers with active dropout (else None)
-        seeds = []
-        h, ldh, kdim = x, x.stride(0), K
-        for i in range(n_hidden):
-            W, b = params[2 * i], params[2 * i + 1]
-            N = W.shape[0]
-            y = torch.empty((M, N), dtype=torch.float32, device=x.device)
-            check(lib.rpb_linear_fwd(_ptr(h), ldh, _ptr(W), _ptr(b), _ptr(y), N, M, N, kdim, 1 if relu[i] else 0,
-                                     impl, st), 'rpb_linear_fwd')
-            _count(2 if impl != 1 else 1)
-            acts.append(h)
-            p = drops[i] if training else 0.0
-            if p > 0.0:
-                seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-                yd = torch.empty_like(y)
-                check(lib.rpb_dropout_fwd(_ptr(y), _ptr(yd), y.numel(), p, seed, st), 'rpb_dropout_fwd')
-                _count()
-                pre_drop.append(y)
-                seeds.append(seed)
-                y = yd
-            else:
-                pre_drop.append(None)
-                seeds.append(0)
-            h, ldh, kdim = y, N, N
-        out = h
-        if has_out:
-            W, b = params[2 * n_hidden], params[2 * n_hidden + 1]
-            N = W.shape[0]
-            out = torch.empty((M, N), dtype=torch.float32, device=x.device)
-            if N == 1:
-                check(lib.rpb_rowdot_fwd(_ptr(h), ldh, _ptr(W), _ptr(b), None, None, None, _ptr(out), M, kdim, st),
-                      'rpb_rowdot_fwd')
-                _count()
-            else:
-                check(lib.rpb_linear_fwd(_ptr(h), ldh, _ptr(W), _ptr(b), _ptr(out), N, M, N, kdim, 0, impl, st),
-                      'rpb_linear_fwd')
-                _count(2 if impl != 1 else 1)
-            acts.append(h)
+        out, acts, pre_drop, seeds = _mlp_fwd(cfg, x, params)
         ctx.cfg = cfg
         ctx.seeds = seeds
         ctx.n_saved_acts = len(acts)
@@ -517,103 +631,155 @@ class _MLP(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         cfg = ctx.cfg
-        n_hidden, has_out, K = cfg['n_hidden'], cfg['has_out'], cfg['K']
-        relu, drops, training, impl = cfg['relu'], cfg['dropout'], cfg['training'], cfg['impl']
+        n_hidden = cfg['n_hidden']
         saved = ctx.saved_tensors
         na = ctx.n_saved_acts
         acts = saved[:na]
         pre_drop = saved[na:na + n_hidden]
         params = saved[na + n_hidden:]
-        lib = _lib.load()
-        st = _stream()
-        M = acts[0].shape[0]
-        dev = acts[0].device
-        g = _rowmajor(g)
-        gparams: List[Optional[torch.Tensor]] = [None] * len(params)
-        need_dx_input = ctx.needs_input_grad[1]
-        # one zero-fill for every dW/db of the tower (the kernels accumulate into them)
-        flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
-        zviews, off = [], 0
-        for p in params:
-            zviews.append(flat[off:off + p.numel()].view(p.shape))
-            off += p.numel()
+        gx, gparams = _mlp_bwd(cfg, acts, pre_drop, ctx.seeds, params, g, ctx.needs_input_grad[1])
+        return (None, gx if ctx.needs_input_grad[1] else None, *gparams)
 
-        def mask_for(layer_in_idx):
-            """Activation mask to fuse when producing the grad of acts[layer_in_idx] (= output of hidden layer-1)."""
-            j = layer_in_idx - 1          # hidden layer that produced this activation
-            if j < 0:
-                return None, False
-            p = drops[j] if training else 0.0
-            if p > 0.0:
-                return None, True         # dropout active: unfused elementwise backward handles ReLU+dropout
-            return (acts[layer_in_idx] if relu[j] else None), False
 
-        def finish_drop(dh, j):
-            """dh = grad wrt dropped output of hidden layer j -> grad wrt its pre-activation."""
-            p = drops[j]
-            out = torch.empty_like(dh)
-            check(lib.rpb_dropout_bwd(_ptr(dh), _ptr(pre_drop[j]) if relu[j] else None, _ptr(out), dh.numel(), p,
-                                      ctx.seeds[j], st), 'rpb_dropout_bwd')
-            _count()
-            return out
+class _DeepFMCore(torch.autograd.Function):
+    """Whole DeepFM body as ONE autograd node: gather(+FM) -> MLP -> logit = fm + dnn (ranking/deepfm.py:52-61).
+    Knowing both consumers of the gathered rows lets backward run the layer-1 dx GEMM with the scatter epilogue
+    (rpb_linear_dx_scatter): dx + dlogit*(s - e) is added straight into the table gradients, dx never reaches HBM."""
 
-        # output layer (always present: the reference only builds MLPs with output_dim=1 on this path)
-        W, b = params[2 * n_hidden], params[2 * n_hidden + 1]
-        N = W.shape[0]
-        hin = acts[n_hidden]
-        kdim = W.shape[1]
-        mask, dropped = mask_for(n_hidden)
-        dx = torch.empty((M, kdim), dtype=torch.float32, device=dev)
-        dW = zviews[2 * n_hidden]
-        db = zviews[2 * n_hidden + 1]
-        if N == 1:
-            gcol = g.reshape(-1) if g.stride(0) == 1 else g[:, 0].contiguous()
-            check(lib.rpb_rowdot_bwd(_ptr(gcol), _ptr(hin), hin.stride(0), _ptr(W), _ptr(mask),
-                                     mask.stride(0) if mask is not None else 0, _ptr(dx), dx.stride(0),
-                                     _ptr(dW), _ptr(db), M, kdim, st), 'rpb_rowdot_bwd')
-            _count(2)
+    @staticmethod
+    def forward(ctx, cfg, gcfg, *tensors):
+        F, Nd = gcfg['F'], gcfg['Nd']
+        tables, idx, dense = tensors[:F], tensors[F:2 * F], tensors[2 * F:2 * F + Nd]
+        params = tensors[2 * F + Nd:]
+        need_grad = gcfg['needs_grad']
+        x, fm, fm_s, rows = _gather_fwd_raw(tables, idx, dense, want_fm=True, need_grad=need_grad)
+        logit, acts, pre_drop, seeds = _mlp_fwd(cfg, x, params, addend=fm)
+        ctx.set_materialize_grads(False)
+        ctx.cfg, ctx.gcfg, ctx.seeds, ctx.rows = cfg, gcfg, seeds, rows
+        ctx.tables = tables
+        ctx.n_saved_acts = len(acts)
+        ctx.n_inputs = 2 + len(tensors)
+        ctx.save_for_backward(fm_s, *idx, *acts, *[t if t is not None else x.new_empty(0) for t in pre_drop], *params)
+        return logit
+
+    @staticmethod
+    def backward(ctx, g):
+        cfg, gcfg = ctx.cfg, ctx.gcfg
+        F, Nd, D = gcfg['F'], gcfg['Nd'], gcfg['D']
+        n_hidden = cfg['n_hidden']
+        saved = ctx.saved_tensors
+        fm_s = saved[0]
+        idx = list(saved[1:1 + F])
+        na = ctx.n_saved_acts
+        acts = saved[1 + F:1 + F + na]
+        pre_drop = saved[1 + F + na:1 + F + na + n_hidden]
+        params = saved[1 + F + na + n_hidden:]
+        x = acts[0]
+        dev = x.device
+        tables = ctx.tables
+        tbl_req = ctx.needs_input_grad[2:2 + F]
+        store = gcfg.get('grad_store')
+        if store is not None:
+            trainable = [tables[f] for f in range(F) if tbl_req[f]]
+            if store.pending and all(t.grad is None for t in trainable):
+                store.clean()
+            g_tables = [store.buffer(tables[f]) if tbl_req[f] else None for f in range(F)]
         else:
-            check(lib.rpb_linear_bwd(_ptr(g), g.stride(0), _ptr(hin), hin.stride(0), _ptr(W), _ptr(mask),
-                                     mask.stride(0) if mask is not None else 0, _ptr(dx), dx.stride(0),
-                                     _ptr(dW), _ptr(db), M, N, kdim, impl, st), 'rpb_linear_bwd')
-            _count(3)
-        gparams[2 * n_hidden], gparams[2 * n_hidden + 1] = dW, db
-        dh = dx
-        lddh = dx.stride(0)
-        if dropped:
-            dh = finish_drop(dh, n_hidden - 1)
+            g_tables = [torch.zeros((ctx.rows[f], D), dtype=torch.float32, device=dev) if tbl_req[f] else None for f in range(F)]
+        dlogit = g.reshape(-1).contiguous()                       # = dL/dfm as well (logit = fm + dnn)
 
-        for i in range(n_hidden - 1, -1, -1):
-            W, b = params[2 * i], params[2 * i + 1]
-            N, kdim = W.shape[0], (K if i == 0 else W.shape[1])
-            hin = acts[i]
-            need_dx = i > 0 or need_dx_input
-            mask, dropped = mask_for(i)
-            if need_dx:
-                if i == 0:
-                    dx = torch.empty((M, hin.stride(0)), dtype=torch.float32, device=dev)
-                    if hin.stride(0) > kdim:
-                        dx[:, kdim:].zero_()
-                else:
-                    dx = torch.empty((M, kdim), dtype=torch.float32, device=dev)
-            else:
-                dx = None
-            dW = zviews[2 * i]
-            db = zviews[2 * i + 1]
-            check(lib.rpb_linear_bwd(_ptr(dh), lddh, _ptr(hin), hin.stride(0), _ptr(W), _ptr(mask),
-                                     mask.stride(0) if mask is not None else 0, _ptr(dx),
-                                     dx.stride(0) if dx is not None else 0, _ptr(dW), _ptr(db), M, N, kdim, impl, st),
-                  'rpb_linear_bwd')
-            _count(3)
-            gparams[2 * i], gparams[2 * i + 1] = dW, db
-            dh = dx
-            lddh = dx.stride(0) if dx is not None else 0
-            if dropped and dh is not None:
-                dh = finish_drop(dh, i - 1)
-        gx = None
-        if need_dx_input and dh is not None:
-            gx = dh if dh.shape[1] == acts[0].shape[1] else dh[:, :acts[0].shape[1]]
-        return (None, gx, *gparams)
+        def desc(dx=None):
+            d = ScatterDesc()
+            d.B, d.F, d.D = x.shape[0], F, D
+            if dx is not None:
+                d.dx, d.lddx = dx.data_ptr(), dx.stride(0)
+            d.dfm, d.x, d.ldx, d.fm_s = dlogit.data_ptr(), x.data_ptr(), x.stride(0), fm_s.data_ptr()
+            d._keep = (_ptr_list(g_tables), (C.c_int64 * F)(*ctx.rows), _ptr_list(idx))
+            d.grads, d.rows, d.idx = d._keep
+            return d
+
+        def hook(dh, lddh, W0):
+            d = desc()
+            rc = _lib.load().rpb_linear_dx_scatter(_ptr(dh), lddh, _ptr(W0), x.shape[0], W0.shape[0], cfg['K'], C.byref(d),
+                                                   _stream())
+            if rc == _lib.ERR_UNSUPPORTED:
+                return False
+            check(rc, 'rpb_linear_dx_scatter')
+            _count(2)
+            return True
+
+        any_tbl = any(t is not None for t in g_tables)
+        gx, gparams = _mlp_bwd(cfg, acts, pre_drop, ctx.seeds, params, g, any_tbl, layer0_hook=hook if any_tbl else None)
+        if gx is not None and any_tbl:                            # hook declined: plain scatter of dx + FM term
+            gx = _rowmajor(gx)
+            d = desc(gx)
+            check(_lib.load().rpb_gather_bwd(C.byref(d), _stream()), 'rpb_gather_bwd')
+            _count()
+        out: List[Optional[torch.Tensor]] = [None] * ctx.n_inputs
+        if store is not None:
+            store.pending.append((g_tables, None, ctx.rows, idx, D))
+            for f in range(F):
+                if g_tables[f] is None:
+                    continue
+                if tables[f].grad is None:
+                    tables[f].grad = g_tables[f]
+                elif tables[f].grad is not g_tables[f]:
+                    raise RuntimeError("embedding table .grad was replaced externally; persistent grad mode needs "
+                                       "model.zero_grad() / set grad_mode='dense'")
+        else:
+            for f in range(F):
+                out[2 + f] = g_tables[f]
+        base = 2 + 2 * F + Nd
+        for i, gp in enumerate(gparams):
+            out[base + i] = gp
+        return tuple(out)
+
+
+def _gather_fwd_raw(tables, idx, dense, want_fm, need_grad):
+    """One gather launch outside autograd bookkeeping: returns (x, fm, fm_s, rows)."""
+    F, Nd, D = len(tables), len(dense), int(tables[0].shape[1])
+    dev = tables[0].device
+    B = idx[0].shape[0]
+    ldx = feature_row_stride(F, D, Nd)
+    x = torch.empty((B, ldx), dtype=torch.float32, device=dev)
+    fm = torch.empty((B,), dtype=torch.float32, device=dev) if want_fm else None
+    fm_s = torch.empty((B, D), dtype=torch.float32, device=dev) if (want_fm and need_grad) else None
+    rows = [int(t.shape[0]) for t in tables]
+    d = GatherDesc()
+    d.B, d.F, d.D, d.Nd, d.ldx, d.ld_lr = B, F, D, Nd, ldx, 0
+    keep = (_ptr_list(tables), (C.c_int64 * F)(*rows), _ptr_list(idx))
+    d.tables, d.rows, d.idx = keep
+    if Nd:
+        dk = _ptr_list(dense)
+        d.dense = dk
+    d.x, d.fm, d.fm_s = x.data_ptr(), _ptr(fm), _ptr(fm_s)
+    d.err = _err_record(dev).data_ptr()
+    check(_lib.load().rpb_gather_fwd(C.byref(d), _stream()), 'rpb_gather_fwd')
+    _count()
+    return x, fm, fm_s, rows
+
+
+def deepfm_core(tables, idx, dense, weights, biases, n_hidden, relu, dropout, training, grad_store=None,
+                impl: Optional[int] = None) -> torch.Tensor:
+    """logit [B,1] of DeepFM (FM second order + MLP over [emb | dense]) as one fused autograd node."""
+    F = len(tables)
+    D = int(tables[0].shape[1])
+    for t in tables:
+        _cuda(t, 'embedding table')
+    idx_l = []
+    for t in idx:
+        _cuda(t, 'sparse feature column')
+        t = t.reshape(-1)
+        idx_l.append((t if t.dtype == torch.int64 else t.long()).contiguous())
+    dense_l = [t.reshape(-1).float().contiguous() for t in dense]
+    params = []
+    for W, b in zip(weights, biases):
+        params += [W if W.is_contiguous() else W.contiguous(), b]
+    needs_grad = torch.is_grad_enabled() and (any(t.requires_grad for t in tables) or any(p.requires_grad for p in params))
+    cfg = dict(n_hidden=n_hidden, has_out=True, K=F * D + len(dense_l), relu=list(relu), dropout=list(dropout),
+               training=training, impl=_GEMM_IMPL if impl is None else impl)
+    gcfg = dict(F=F, Nd=len(dense_l), D=D, needs_grad=needs_grad, grad_store=grad_store)
+    return _DeepFMCore.apply(cfg, gcfg, *tables, *idx_l, *dense_l, *params)
 
 
 def mlp_forward(x: torch.Tensor, K: int, weights: Sequence[torch.Tensor], biases: Sequence[Optional[torch.Tensor]],
