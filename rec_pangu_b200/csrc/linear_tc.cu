@@ -264,8 +264,34 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 //     ~1-2 us load latency from the 2-stage OPERAND ring (A hi / A lo produced by the split warps);
 //   * the accumulator is double-buffered in TMEM (2 x block_n columns) and drained by four dedicated epilogue warps,
 //     so tile i's epilogue (bias / ReLU / mask / global stores) overlaps tile i+1's main loop.
-// Warps: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2-5 = split, 6-9 = epilogue (TMEM lane quarter = warp & 3).
-constexpr int V2_THREADS = 320;
+// Warps: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2-5 = split, 6-13 = epilogue: two warps per TMEM lane quarter
+// 4x4 transpose of float4 "elements" across each group of 4 lanes.  In: r[4i..4i+3] = element i of this lane's row
+// (lane & 3 = row within the group).  Out: r[4j..4j+3] = element (lane & 3) of row j.  Two butterfly stages, 16 SHFL.
+__device__ __forceinline__ void transpose4x4(uint32_t (&r)[16], int q) {
+    const bool b0 = (q & 1) != 0, b1 = (q & 2) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; i += 2) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t send = b0 ? r[4 * i + c] : r[4 * (i + 1) + c];
+            const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 1);
+            if (b0) r[4 * i + c] = recv; else r[4 * (i + 1) + c] = recv;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t send = b1 ? r[4 * i + c] : r[4 * (i + 2) + c];
+            const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, 2);
+            if (b1) r[4 * i + c] = recv; else r[4 * (i + 2) + c] = recv;
+        }
+    }
+}
+
+// (quarter = warp & 3), which take alternate 16-column chunks of the accumulator.
+constexpr int V2_THREADS = 448;
+constexpr int V2_EPI_WARPS = 8;
 constexpr int V2_OP_STAGES = 2;
 
 template <int kRaw>
@@ -301,7 +327,7 @@ gemm_tf32x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         for (int s = 0; s < kRaw; ++s) { mbar_init(&full_raw[s], 1); mbar_init(&empty_raw[s], b_resident ? 128 : 1); }
         mbar_init(b_full, 1);
         for (int s = 0; s < V2_OP_STAGES; ++s) { mbar_init(&ready_op[s], 128); mbar_init(&empty_op[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], V2_EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr, tmem_cols);
@@ -402,6 +428,7 @@ gemm_tf32x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     } else {
         // ---------------- epilogue warps: TMEM -> registers -> global (thread = output row), overlapped with the next tile
         const int quarter = warp & 3;
+        const int half = (warp - 6) >> 2;              // which of the quarter's two warps: chunks half, half+2, ...
         const int row = quarter * 32 + lane;
         const bool c_vec = ((ep.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.C) & 15u) == 0);
         const bool m_vec = ep.mask != nullptr && ((ep.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.mask) & 15u) == 0);
@@ -409,39 +436,80 @@ gemm_tf32x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
             const int m0 = (tile / n_tiles) * TC_BLOCK_M, n0 = (tile % n_tiles) * block_n;
             const uint32_t acc = t & 1u;
-            mbar_wait(&tmem_full[acc], (t >> 1) & 1u);
-            tc_fence_after();
             const int m = m0 + row;
-            for (int c0 = 0; c0 < block_n; c0 += 16) {
-                uint32_t r[16];
-                tmem_ld16(tmem_base + acc * (uint32_t)block_n + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
-                if (sc.enabled) {
-                    // ---- fused scatter-add of the table gradients (see TcScatter)
-                    if (m < ep.M) {
-                        const int FD = sc.F * sc.D;
-                        const float cfm = sc.dfm != nullptr ? __ldg(sc.dfm + m) : 0.f;
+            if (sc.enabled) {
+                // ---- fused scatter-add of the table gradients (see TcScatter).
+                // TMEM hands each lane 16 consecutive columns of ITS row; a 4x4 float4 transpose inside every group of
+                // 4 lanes (transpose4x4) turns that into "4 lanes cover 64 contiguous bytes of one row" for 4 rows, so
+                // x loads and table-gradient reductions are whole 64-byte requests instead of 16-byte fragments.
+                // Everything that does not depend on the accumulator (row ids, forward rows e) is fetched BEFORE the
+                // accumulator is awaited, two 16-column chunks at a time, to overlap the random-access latency with
+                // the main loop of this tile.
+                const int FD = sc.F * sc.D;
+                const int q = lane & 3;
+                const int mb = m0 + quarter * 32 + (lane >> 2) * 4;     // first of this lane group's 4 rows
+                float cf[4];
 #pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) {
-                            const int n4 = n0 + c0 + 4 * j4;
-                            if (n4 < FD) {
-                                const int f = n4 / sc.D, d = n4 - f * sc.D;
-                                if (sc.grads[f] != nullptr) {
-                                    long long ix = __ldg(sc.idx[f] + m);
-                                    if ((unsigned long long)ix >= (unsigned long long)sc.rows[f]) ix = 0;
-                                    float4 gv = make_float4(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1]),
-                                                            __uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3]));
+                for (int j = 0; j < 4; ++j) cf[j] = (sc.dfm != nullptr && mb + j < ep.M) ? __ldg(sc.dfm + mb + j) : 0.f;
+                bool waited = false;
+                for (int c0 = half * 16; c0 < block_n; c0 += 64) {
+                    long long ix[2][4];
+                    float4 e[2][4];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int n4 = n0 + c0 + 32 * u + 4 * q;
+                        const bool colok = c0 + 32 * u < block_n && n4 < FD;
+                        const int f = colok ? n4 / sc.D : 0;
+                        const bool live = colok && sc.grads[f] != nullptr;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            ix[u][j] = -1;
+                            e[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (live && mb + j < ep.M) {
+                                long long v = __ldg(sc.idx[f] + mb + j);
+                                if ((unsigned long long)v >= (unsigned long long)sc.rows[f]) v = 0;
+                                ix[u][j] = v;
+                                if (sc.dfm != nullptr) e[u][j] = ldg_f4_stream(sc.x + (size_t)(mb + j) * sc.ldx + n4);
+                            }
+                        }
+                    }
+                    if (!waited) { mbar_wait(&tmem_full[acc], (t >> 1) & 1u); tc_fence_after(); waited = true; }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        if (c0 + 32 * u < block_n) {            // warp-uniform
+                            uint32_t r[16];
+                            tmem_ld16(tmem_base + acc * (uint32_t)block_n + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c0 + 32 * u), r);
+                            transpose4x4(r, q);                 // r[4j..4j+3] = columns 4q..4q+3 of row mb + j
+                            const int n4 = n0 + c0 + 32 * u + 4 * q;
+                            const int f = n4 < FD ? n4 / sc.D : 0, d = n4 - f * sc.D;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                if (ix[u][j] >= 0) {
+                                    float4 gv = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                            __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
                                     if (sc.dfm != nullptr) {
-                                        const float4 e = ldg_f4_stream(sc.x + (size_t)m * sc.ldx + n4);
-                                        const float4 sv = ldg_f4(sc.fm_s + (size_t)m * sc.D + d);
-                                        gv.x = fmaf(cfm, sv.x - e.x, gv.x); gv.y = fmaf(cfm, sv.y - e.y, gv.y);
-                                        gv.z = fmaf(cfm, sv.z - e.z, gv.z); gv.w = fmaf(cfm, sv.w - e.w, gv.w);
+                                        const float4 sv = ldg_f4(sc.fm_s + (size_t)(mb + j) * sc.D + d);
+                                        gv.x = fmaf(cf[j], sv.x - e[u][j].x, gv.x); gv.y = fmaf(cf[j], sv.y - e[u][j].y, gv.y);
+                                        gv.z = fmaf(cf[j], sv.z - e[u][j].z, gv.z); gv.w = fmaf(cf[j], sv.w - e[u][j].w, gv.w);
                                     }
-                                    red_add_f4(sc.grads[f] + (size_t)ix * sc.D + d, gv);
+                                    red_add_f4(sc.grads[f] + (size_t)ix[u][j] * sc.D + d, gv);
                                 }
                             }
                         }
                     }
-                } else if (m < ep.M && n0 + c0 < ep.N) {
+                }
+                if (!waited) { mbar_wait(&tmem_full[acc], (t >> 1) & 1u); tc_fence_after(); }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                continue;
+            }
+            mbar_wait(&tmem_full[acc], (t >> 1) & 1u);
+            tc_fence_after();
+            for (int c0 = half * 16; c0 < block_n; c0 += 32) {
+                uint32_t r[16];
+                tmem_ld16(tmem_base + acc * (uint32_t)block_n + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+                if (m < ep.M && n0 + c0 < ep.N) {
                     float v[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);

@@ -16,6 +16,9 @@ __all__ = ['GradStore', 'deepfm_core', 'gather', 'gather_sharded', 'sharded_clea
            'check_index_errors', 'set_gemm_impl', 'get_gemm_impl', 'launch_count', 'reset_launch_count']
 
 _GEMM_IMPL = int(__import__('os').environ.get('RPB_GEMM_IMPL', '0'))   # 0 auto, 1 SIMT fp32, 2 tcgen05 3xTF32
+# DeepFM backward: 1 = layer-1 dx GEMM scatters table gradients from its epilogue (rpb_linear_dx_scatter),
+# 0 = dx GEMM to HBM followed by rpb_gather_bwd.  Both are bit-for-bit the same sums in a different add order.
+FUSED_DX_SCATTER = int(__import__('os').environ.get('RPB_DX_SCATTER', '1'))
 _LAUNCHES = 0           # number of librec_pangu_b200 kernels launched (bench.py reports it as gpu_launches)
 
 
@@ -709,7 +712,7 @@ class _DeepFMCore(torch.autograd.Function):
             return True
 
         any_tbl = any(t is not None for t in g_tables)
-        gx, gparams = _mlp_bwd(cfg, acts, pre_drop, ctx.seeds, params, g, any_tbl, layer0_hook=hook if any_tbl else None)
+        gx, gparams = _mlp_bwd(cfg, acts, pre_drop, ctx.seeds, params, g, any_tbl, layer0_hook=hook if (any_tbl and FUSED_DX_SCATTER) else None)
         if gx is not None and any_tbl:                            # hook declined: plain scatter of dx + FM term
             gx = _rowmajor(gx)
             d = desc(gx)
