@@ -34,8 +34,14 @@ extern "C" {
 int rpb_version(void);
 /* Tuning knobs (process-wide): "gather_load_policy" 0 = L1 no-allocate row loads, 1 = + L2 64-byte fetch cap (default),
  * 2 = cached read-only loads, 3 = measurement-only (no x write);  "gather_kernel" 0 = shared-memory tile + bulk
- * store (default), 1 = direct stores;  "l2_fetch_granularity" = 32|64|128 (cudaLimitMaxL2FetchGranularity). */
+ * store (default), 1 = direct stores;  "l2_fetch_granularity" = 32|64|128 (cudaLimitMaxL2FetchGranularity);
+ * "gemm_v2" 1 = persistent tcgen05 GEMM (default), 0 = one tile per CTA;  "gemm_a_tmem" 1 = the split A operand lives in
+ * tensor memory (TS-mode MMA, default), 0 = in shared memory;  "gemm_stack_n" 1 = layers of <= 64 outputs multiply by
+ * [B hi ; B lo] as one operand (default);  "wgrad_tc" 1 = tcgen05 weight gradient (default). */
 int rpb_set_option(const char* name, int64_t value);
+/* Diagnostics for the persistent tcgen05 GEMM: per-role stall cycles of CTA 0 of the last launch (see linear_tc.cu);
+ * out16 may be NULL; `enable` switches the counters on/off for subsequent launches (synchronous, not graph-safe). */
+int rpb_debug_tc_trace(uint64_t* out16, int enable);
 /* Last error text for negative codes (static string). */
 const char* rpb_error_string(int code);
 

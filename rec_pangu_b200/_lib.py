@@ -44,6 +44,7 @@ SIGNATURES = {
     'rpb_version': (C.c_int, []),
     'rpb_error_string': (C.c_char_p, [C.c_int]),
     'rpb_set_option': (C.c_int, [C.c_char_p, _i64]),
+    'rpb_debug_tc_trace': (C.c_int, [C.POINTER(C.c_uint64), C.c_int]),
     'rpb_gather_fwd': (C.c_int, [C.POINTER(GatherDesc), _vp]),
     'rpb_gather_bwd': (C.c_int, [C.POINTER(ScatterDesc), _vp]),
     'rpb_rows_zero': (C.c_int, [C.POINTER(ScatterDesc), _vp]),

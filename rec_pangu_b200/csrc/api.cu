@@ -9,6 +9,8 @@ int g_gather_policy = 1;
 int g_gather_kernel = 0;
 int g_wgrad_tc = 1;
 int g_gemm_v2 = 1;
+int g_gemm_a_tmem = 1;
+int g_gemm_stack_n = 1;
 
 // Grow-only per-device scratch buffers (slot = call site).  Kernels of one stream that share a slot are ordered by
 // the stream, so reuse is safe for the single-stream execution model of the reference's training loop.  Growth uses
@@ -59,6 +61,8 @@ RPB_API int rpb_set_option(const char* name, int64_t value) {
         return 0;
     }
     if (n == "gemm_v2") { rpb::g_gemm_v2 = value != 0; return 0; }
+    if (n == "gemm_a_tmem") { rpb::g_gemm_a_tmem = value != 0; return 0; }
+    if (n == "gemm_stack_n") { rpb::g_gemm_stack_n = value != 0; return 0; }
     if (n == "wgrad_tc") { rpb::g_wgrad_tc = value != 0; return 0; }
     if (n == "gather_kernel") {
         if (value < 0 || value > 1) return RPB_ERR_BAD_ARG;

@@ -71,6 +71,22 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                  :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand in tensor memory (TS mode): lane = row of the M=128 tile, one 32-bit column per k.
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+                 "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                    "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+                    "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+                    "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
@@ -265,6 +281,16 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 //   * the accumulator is double-buffered in TMEM (2 x block_n columns) and drained by four dedicated epilogue warps,
 //     so tile i's epilogue (bias / ReLU / mask / global stores) overlaps tile i+1's main loop.
 // Warps: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2-5 = split, 6-13 = epilogue: two warps per TMEM lane quarter
+// (quarter = warp & 3), which take alternate 16-column chunks of the accumulator.
+//
+// Operand placement (a_stages): tcgen05.mma reads BOTH operands of an SS-mode instruction from shared memory — 6 KiB per
+// 128x64x8 tf32 MMA, and three MMAs per K step for the 3xTF32 products.  Together with the TMA writes and the split
+// warps' own traffic that is ~150 KiB of shared-memory traffic per 32-wide k-block, and ncu shows the narrow layers
+// (N = 64) bound by exactly that, at half the tensor-pipe rate (tools/exp/exp_mma.cu: 65 cycles per 128x64x8 MMA alone,
+// ~128 in the SS pipeline).  With a_stages > 0 the split warps therefore write A hi / A lo straight into TENSOR MEMORY
+// (tcgen05.st, lane = tile row, column = k) and the MMAs take A from TMEM (TS mode): shared memory then only carries
+// the raw A tile once and the B chunks.  TMEM columns: [acc 0 | acc 1 | a_stages x (A hi 32 | A lo 32)].
+
 // 4x4 transpose of float4 "elements" across each group of 4 lanes.  In: r[4i..4i+3] = element i of this lane's row
 // (lane & 3 = row within the group).  Out: r[4j..4j+3] = element (lane & 3) of row j.  Two butterfly stages, 16 SHFL.
 __device__ __forceinline__ void transpose4x4(uint32_t (&r)[16], int q) {
@@ -289,16 +315,21 @@ __device__ __forceinline__ void transpose4x4(uint32_t (&r)[16], int q) {
     }
 }
 
-// (quarter = warp & 3), which take alternate 16-column chunks of the accumulator.
+// Diagnostics (rpb_debug_tc_trace): per-role stall cycles of CTA 0 of the last v2 launch.
+__device__ int g_tc_trace_on = 0;
+__device__ unsigned long long g_tc_trace[16];
+#define TC_TRACE_T() (trace ? clock64() : 0ll)
+
 constexpr int V2_THREADS = 448;
 constexpr int V2_EPI_WARPS = 8;
-constexpr int V2_OP_STAGES = 2;
+constexpr int V2_OP_STAGES = 2;       // shared-memory operand ring (SS mode)
+constexpr int V2_MAX_OP = 4;          // tensor-memory operand ring (TS mode): up to 4 stages of 64 columns
 
 template <int kRaw>
 __global__ void __launch_bounds__(V2_THREADS, 1)
 gemm_tf32x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                       const __grid_constant__ CUtensorMap tmBlo, const TcEpilogue ep, int block_n, int num_k_blocks,
-                      int m_tiles, int n_tiles, uint32_t tmem_cols, int b_resident,
+                      int m_tiles, int n_tiles, uint32_t tmem_cols, int b_resident, int a_stages, int stack_n,
                       const __grid_constant__ TcScatter sc) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -309,24 +340,33 @@ gemm_tf32x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int raw_bytes = b_resident ? TC_A_BYTES : TC_A_BYTES + 2 * b_bytes;
     uint8_t* raw_base = smem;
     uint8_t* op_base = smem + (size_t)kRaw * raw_bytes;                // [A hi | A lo] x V2_OP_STAGES
-    uint8_t* bres_base = op_base + (size_t)V2_OP_STAGES * 2 * TC_A_BYTES;
+    const int n_op = a_stages > 0 ? a_stages : V2_OP_STAGES;          // operand ring depth (TMEM or shared memory)
+    // stack_n (narrow layers, TS mode): B hi and B lo are adjacent in shared memory, so ONE descriptor of N = 2*block_n rows
+    // covers both and one MMA yields a.b_hi in columns [0, block_n) and a.b_lo in [block_n, 2*block_n) of the accumulator.
+    // A 128 x N x 8 tf32 MMA costs max(64, N/2) cycles (tools/exp/exp_mma.cu), i.e. N = 128 is as cheap as N = 64: the
+    // k-step needs two MMAs (a_hi, a_lo) instead of three, and the epilogue adds the two accumulator halves.
+    const uint32_t acc_stride = (uint32_t)(stack_n ? 2 * block_n : block_n);
+    const uint32_t a_col = (2u * acc_stride + 31u) & ~31u;             // TS mode: first TMEM column of the A ring
+    uint8_t* bres_base = op_base + (a_stages > 0 ? 0 : (size_t)V2_OP_STAGES * 2 * TC_A_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(bres_base + (b_resident ? (size_t)num_k_blocks * 2 * b_bytes : 0));
     uint64_t* full_raw = bars;                     // [kRaw]  TMA landed
     uint64_t* empty_raw = bars + kRaw;             // [kRaw]  MMAs that read B of this stage are done
-    uint64_t* ready_op = bars + 2 * kRaw;          // [2]     split done
-    uint64_t* empty_op = ready_op + V2_OP_STAGES;  // [2]     MMAs that read A hi/lo of this stage are done
-    uint64_t* tmem_full = empty_op + V2_OP_STAGES; // [2]
+    uint64_t* ready_op = bars + 2 * kRaw;          // [<=4]   split done
+    uint64_t* empty_op = ready_op + V2_MAX_OP;     // [<=4]   MMAs that read A hi/lo of this stage are done
+    uint64_t* tmem_full = empty_op + V2_MAX_OP;    // [2]
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
     uint64_t* b_full = tmem_empty + 2;             // [1]     resident B landed
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = m_tiles * n_tiles;
+    const bool trace = g_tc_trace_on != 0 && blockIdx.x == 0;
+    const long long t_start = TC_TRACE_T();
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kRaw; ++s) { mbar_init(&full_raw[s], 1); mbar_init(&empty_raw[s], b_resident ? 128 : 1); }
         mbar_init(b_full, 1);
-        for (int s = 0; s < V2_OP_STAGES; ++s) { mbar_init(&ready_op[s], 128); mbar_init(&empty_op[s], 1); }
+        for (int s = 0; s < V2_MAX_OP; ++s) { mbar_init(&ready_op[s], 128); mbar_init(&empty_op[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], V2_EPI_WARPS); }
         fence_barrier_init();
     }
@@ -340,6 +380,7 @@ gemm_tf32x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         if (lane == 0) {
             const uint32_t tx_bytes = (uint32_t)raw_bytes;
             uint32_t g = 0;                                              // global k-block counter
+            long long w_raw = 0;
             if (b_resident && blockIdx.x < num_tiles) {
                 mbar_arrive_expect_tx(b_full, (uint32_t)(num_k_blocks * 2 * b_bytes));
                 for (int kb = 0; kb < num_k_blocks; ++kb) {
@@ -351,7 +392,9 @@ gemm_tf32x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 const int m0 = (tile / n_tiles) * TC_BLOCK_M, n0 = (tile % n_tiles) * block_n;
                 for (int kb = 0; kb < num_k_blocks; ++kb, ++g) {
                     const int s = g % kRaw;
+                    const long long c0 = TC_TRACE_T();
                     mbar_wait(&empty_raw[s], ((g / kRaw) & 1u) ^ 1u);
+                    w_raw += TC_TRACE_T() - c0;
                     uint8_t* st = raw_base + (size_t)s * raw_bytes;
                     mbar_arrive_expect_tx(&full_raw[s], tx_bytes);
                     tma_load_2d(st, &tmA, &full_raw[s], kb * TC_BLOCK_K, m0);
@@ -361,51 +404,110 @@ gemm_tf32x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     }
                 }
             }
+            if (trace) { g_tc_trace[1] = (unsigned long long)w_raw; g_tc_trace[10] = g; }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(TC_BLOCK_M, block_n);
             uint32_t g = 0, t = 0;
+            long long w_ready = 0, w_acc = 0, w_issue = 0;
             if (b_resident && blockIdx.x < num_tiles) mbar_wait(b_full, 0);
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
                 const uint32_t acc = t & 1u;
+                const long long c0 = TC_TRACE_T();
                 mbar_wait(&tmem_empty[acc], ((t >> 1) & 1u) ^ 1u);       // epilogue drained this accumulator
+                w_acc += TC_TRACE_T() - c0;
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * (uint32_t)block_n;
+                const uint32_t d_tmem = tmem_base + acc * acc_stride;
                 for (int kb = 0; kb < num_k_blocks; ++kb, ++g) {
-                    const int s = g % kRaw, o = g % V2_OP_STAGES;
-                    mbar_wait(&ready_op[o], (g / V2_OP_STAGES) & 1u);
+                    const int s = g % kRaw, o = g % n_op;
+                    const long long c1 = TC_TRACE_T();
+                    mbar_wait(&ready_op[o], (g / n_op) & 1u);
+                    const long long c2 = TC_TRACE_T();
+                    w_ready += c2 - c1;
                     tc_fence_after();
                     const uint32_t a_hi = smem_u32(op_base + (size_t)o * 2 * TC_A_BYTES);
                     const uint32_t a_lo = a_hi + TC_A_BYTES;
                     const uint32_t b_hi = b_resident ? smem_u32(bres_base + (size_t)kb * 2 * b_bytes)
                                                      : smem_u32(raw_base + (size_t)s * raw_bytes + TC_A_BYTES);
                     const uint32_t b_lo = b_hi + b_bytes;
+                    if (stack_n) {
+                        const uint32_t ta_hi = tmem_base + a_col + (uint32_t)o * 64u, ta_lo = ta_hi + 32u;
+                        const uint32_t idesc2 = make_idesc_tf32(TC_BLOCK_M, 2 * block_n);
 #pragma unroll
-                    for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
-                        const uint32_t koff = k * TC_UMMA_K * 4;
-                        const uint64_t da_hi = make_kmajor_sw128_desc(a_hi + koff), da_lo = make_kmajor_sw128_desc(a_lo + koff);
-                        const uint64_t db_hi = make_kmajor_sw128_desc(b_hi + koff), db_lo = make_kmajor_sw128_desc(b_lo + koff);
-                        umma_tf32(d_tmem, da_lo, db_hi, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                        umma_tf32(d_tmem, da_hi, db_lo, idesc, 1u);
-                        umma_tf32(d_tmem, da_hi, db_hi, idesc, 1u);
+                        for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
+                            const uint64_t db = make_kmajor_sw128_desc(b_hi + k * TC_UMMA_K * 4);       // [B hi ; B lo]
+                            umma_tf32_ts(d_tmem, ta_lo + k * TC_UMMA_K, db, idesc2, (kb > 0 || k > 0) ? 1u : 0u);
+                            umma_tf32_ts(d_tmem, ta_hi + k * TC_UMMA_K, db, idesc2, 1u);
+                        }
+                    } else if (a_stages > 0) {
+                        const uint32_t ta_hi = tmem_base + a_col + (uint32_t)o * 64u, ta_lo = ta_hi + 32u;
+#pragma unroll
+                        for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
+                            const uint32_t koff = k * TC_UMMA_K * 4;
+                            const uint64_t db_hi = make_kmajor_sw128_desc(b_hi + koff), db_lo = make_kmajor_sw128_desc(b_lo + koff);
+                            umma_tf32_ts(d_tmem, ta_lo + k * TC_UMMA_K, db_hi, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                            umma_tf32_ts(d_tmem, ta_hi + k * TC_UMMA_K, db_lo, idesc, 1u);
+                            umma_tf32_ts(d_tmem, ta_hi + k * TC_UMMA_K, db_hi, idesc, 1u);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
+                            const uint32_t koff = k * TC_UMMA_K * 4;
+                            const uint64_t da_hi = make_kmajor_sw128_desc(a_hi + koff), da_lo = make_kmajor_sw128_desc(a_lo + koff);
+                            const uint64_t db_hi = make_kmajor_sw128_desc(b_hi + koff), db_lo = make_kmajor_sw128_desc(b_lo + koff);
+                            umma_tf32(d_tmem, da_lo, db_hi, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                            umma_tf32(d_tmem, da_hi, db_lo, idesc, 1u);
+                            umma_tf32(d_tmem, da_hi, db_hi, idesc, 1u);
+                        }
                     }
                     umma_commit(&empty_op[o]);
                     if (!b_resident) umma_commit(&empty_raw[s]);
+                    w_issue += TC_TRACE_T() - c2;
                 }
                 umma_commit(&tmem_full[acc]);
             }
+            if (trace) { g_tc_trace[2] = (unsigned long long)w_ready; g_tc_trace[3] = (unsigned long long)w_acc; g_tc_trace[4] = (unsigned long long)w_issue; }
         }
     } else if (warp < 6) {
         // ---------------- split warps: raw A -> (hi, lo) operand stage
         const int tid = threadIdx.x - 64;
         uint32_t g = 0;
+        long long w_full = 0, w_eop = 0, w_work = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             for (int kb = 0; kb < num_k_blocks; ++kb, ++g) {
-                const int s = g % kRaw, o = g % V2_OP_STAGES;
+                const int s = g % kRaw, o = g % n_op;
+                const long long c0 = TC_TRACE_T();
                 mbar_wait(&full_raw[s], (g / kRaw) & 1u);
-                mbar_wait(&empty_op[o], ((g / V2_OP_STAGES) & 1u) ^ 1u);
+                const long long c1 = TC_TRACE_T();
+                mbar_wait(&empty_op[o], ((g / n_op) & 1u) ^ 1u);
+                const long long c2 = TC_TRACE_T();
+                w_full += c1 - c0; w_eop += c2 - c1;
                 const float4* src = reinterpret_cast<const float4*>(raw_base + (size_t)s * raw_bytes);
+                if (a_stages > 0) {
+                    // TS mode: this thread owns tile row (warp & 3) * 32 + lane — the TMEM lane its warp may write.
+                    // The raw tile is SWIZZLE_128B: 16-byte unit j of row r sits at unit j ^ (r & 7).
+                    tc_fence_after();
+                    const int r = (warp & 3) * 32 + lane;
+                    uint32_t h[32], l[32];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 v = src[r * 8 + (j ^ (r & 7))];
+                        h[4 * j + 0] = __float_as_uint(v.x) & 0xFFFFE000u; l[4 * j + 0] = __float_as_uint(v.x - __uint_as_float(h[4 * j + 0]));
+                        h[4 * j + 1] = __float_as_uint(v.y) & 0xFFFFE000u; l[4 * j + 1] = __float_as_uint(v.y - __uint_as_float(h[4 * j + 1]));
+                        h[4 * j + 2] = __float_as_uint(v.z) & 0xFFFFE000u; l[4 * j + 2] = __float_as_uint(v.z - __uint_as_float(h[4 * j + 2]));
+                        h[4 * j + 3] = __float_as_uint(v.w) & 0xFFFFE000u; l[4 * j + 3] = __float_as_uint(v.w - __uint_as_float(h[4 * j + 3]));
+                    }
+                    const uint32_t ta = tmem_base + a_col + (uint32_t)o * 64u + ((uint32_t)((warp & 3) * 32) << 16);
+                    tmem_st32(ta, h);
+                    tmem_st32(ta + 32u, l);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(&ready_op[o]);
+                    if (b_resident) mbar_arrive(&empty_raw[s]);
+                    w_work += TC_TRACE_T() - c2;
+                    continue;
+                }
                 float4* hi = reinterpret_cast<float4*>(op_base + (size_t)o * 2 * TC_A_BYTES);
                 float4* lo = reinterpret_cast<float4*>(op_base + (size_t)o * 2 * TC_A_BYTES + TC_A_BYTES);
 #pragma unroll
@@ -423,8 +525,10 @@ gemm_tf32x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 fence_proxy_async();
                 mbar_arrive(&ready_op[o]);
                 if (b_resident) mbar_arrive(&empty_raw[s]);              // the raw A tile has been consumed
+                w_work += TC_TRACE_T() - c2;
             }
         }
+        if (trace && tid == 0) { g_tc_trace[5] = (unsigned long long)w_full; g_tc_trace[6] = (unsigned long long)w_eop; g_tc_trace[7] = (unsigned long long)w_work; }
     } else {
         // ---------------- epilogue warps: TMEM -> registers -> global (thread = output row), overlapped with the next tile
         const int quarter = warp & 3;
@@ -478,7 +582,7 @@ gemm_tf32x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     for (int u = 0; u < 2; ++u) {
                         if (c0 + 32 * u < block_n) {            // warp-uniform
                             uint32_t r[16];
-                            tmem_ld16(tmem_base + acc * (uint32_t)block_n + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c0 + 32 * u), r);
+                            tmem_ld16(tmem_base + acc * acc_stride + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c0 + 32 * u), r);
                             transpose4x4(r, q);                 // r[4j..4j+3] = columns 4q..4q+3 of row mb + j
                             const int n4 = n0 + c0 + 32 * u + 4 * q;
                             const int f = n4 < FD ? n4 / sc.D : 0, d = n4 - f * sc.D;
@@ -504,15 +608,19 @@ gemm_tf32x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                 continue;
             }
+            const long long e0 = TC_TRACE_T();
             mbar_wait(&tmem_full[acc], (t >> 1) & 1u);
+            const long long e1 = TC_TRACE_T();
             tc_fence_after();
             for (int c0 = half * 16; c0 < block_n; c0 += 32) {
                 uint32_t r[16];
-                tmem_ld16(tmem_base + acc * (uint32_t)block_n + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+                tmem_ld16(tmem_base + acc * acc_stride + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+                uint32_t r2[16];
+                if (stack_n) tmem_ld16(tmem_base + acc * acc_stride + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(block_n + c0), r2);
                 if (m < ep.M && n0 + c0 < ep.N) {
                     float v[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+                    for (int j = 0; j < 16; ++j) v[j] = stack_n ? __uint_as_float(r2[j]) + __uint_as_float(r[j]) : __uint_as_float(r[j]);
                     const int n = n0 + c0;
                     const bool full = n + 16 <= ep.N;
                     if (ep.bias != nullptr) {
@@ -550,11 +658,16 @@ gemm_tf32x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (trace && warp == 6 && lane == 0) {
+                g_tc_trace[8] += (unsigned long long)(e1 - e0);
+                g_tc_trace[9] += (unsigned long long)(TC_TRACE_T() - e1);
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+    if (trace && threadIdx.x == 0) g_tc_trace[0] = (unsigned long long)(clock64() - t_start);
 }
 
 // ---------------------------------------------------------------------------------- weight gradient on tcgen05
@@ -783,12 +896,18 @@ int gemm_tc(const float* A, long long lda, const float* Bsrc, long long ldb, int
     if (rc == 0) rc = make_map(&tmBlo, lo, Np, Kp, Kp, block_n);
     if (rc == 0 && g_gemm_v2) {
         const int b_bytes = block_n * TC_BLOCK_K * 4;
-        const int op_bytes = V2_OP_STAGES * 2 * TC_A_BYTES;
+        // TS mode (A hi/lo in tensor memory) whenever two accumulators leave room for >= 2 operand stages of 64 columns;
+        // the fused scatter epilogue keeps the SS pipeline (its 2 x 208 accumulator columns fill TMEM).
+        const int stack_n = (g_gemm_a_tmem && g_gemm_stack_n && ep.sc == nullptr && n_tiles == 1 && block_n <= 64) ? 1 : 0;
+        const int acc_cols = round_up((stack_n ? 4 : 2) * block_n, 32);
+        int a_stages = 0;
+        if (g_gemm_a_tmem && ep.sc == nullptr && acc_cols + 2 * 64 <= 512) a_stages = min(V2_MAX_OP, (512 - acc_cols) / 64);
+        const int op_bytes = a_stages > 0 ? 0 : V2_OP_STAGES * 2 * TC_A_BYTES;
         const int bres_bytes = nkb * 2 * b_bytes;
         const int b_resident = (n_tiles == 1 && bres_bytes <= 72 * 1024) ? 1 : 0;
         const int raw_bytes = b_resident ? TC_A_BYTES : TC_A_BYTES + 2 * b_bytes;
         uint32_t tmem_cols = 32;
-        while ((int)tmem_cols < 2 * block_n) tmem_cols <<= 1;
+        while ((int)tmem_cols < (a_stages > 0 ? acc_cols + 64 * a_stages : 2 * block_n)) tmem_cols <<= 1;
         const int m_tiles = ceil_div(M, TC_BLOCK_M);
         const int budget = 226 * 1024 - op_bytes - (b_resident ? bres_bytes : 0) - 1024 - 256;
         const int max_raw = budget / raw_bytes;
@@ -797,12 +916,13 @@ int gemm_tc(const float* A, long long lda, const float* Bsrc, long long ldb, int
             auto launch = [&](auto raw_tag) -> int {
                 constexpr int R = decltype(raw_tag)::value;
                 const size_t smem = (size_t)R * raw_bytes + op_bytes + (b_resident ? bres_bytes : 0) +
-                                    (2 * R + 2 * V2_OP_STAGES + 4 + 2) * 8 + 1024;
+                                    (2 * R + 2 * V2_MAX_OP + 4 + 2) * 8 + 1024;
                 cudaError_t ee = cudaFuncSetAttribute(gemm_tf32x3_v2_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (ee != cudaSuccess) return (int)ee;
                 static const TcScatter no_scatter{};
                 gemm_tf32x3_v2_kernel<R><<<grid, V2_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, ep, block_n, nkb, m_tiles, n_tiles,
-                                                                        tmem_cols, b_resident, ep.sc != nullptr ? *ep.sc : no_scatter);
+                                                                        tmem_cols, b_resident, a_stages, stack_n,
+                                                                        ep.sc != nullptr ? *ep.sc : no_scatter);
                 return (int)cudaGetLastError();
             };
             if (max_raw >= 6) return launch(std::integral_constant<int, 6>{});
@@ -934,6 +1054,23 @@ RPB_API int rpb_linear_bwd(const float* dy, int64_t lddy, const float* x, int64_
 }
 
 // dx GEMM of the first MLP layer fused with the embedding-gradient scatter (TcScatter): dx is never written.
+// Diagnostics: enable/disable the per-role stall counters of the persistent GEMM and read them back (16 x u64, cycles of
+// CTA 0 of the LAST launch: [0] kernel, [1] producer waits for a free raw stage, [2] MMA issuer waits for operands,
+// [3] MMA issuer waits for a drained accumulator, [4] MMA issue, [5] split waits for TMA, [6] split waits for a free
+// operand stage, [7] split work, [8] epilogue waits for the accumulator, [9] epilogue work, [10] k-blocks).
+RPB_API int rpb_debug_tc_trace(uint64_t* out16, int enable) {
+    int on = enable != 0;
+    cudaError_t e = cudaSuccess;
+    if (out16 != nullptr) {
+        e = cudaMemcpyFromSymbol(out16, g_tc_trace, sizeof(unsigned long long) * 16);
+        if (e != cudaSuccess) return (int)e;
+    }
+    static const unsigned long long zeros[16] = {};
+    e = cudaMemcpyToSymbol(g_tc_trace, zeros, sizeof(zeros));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_tc_trace_on, &on, sizeof(int));
+    return (int)e;
+}
+
 RPB_API int rpb_linear_dx_scatter(const float* dy, int64_t lddy, const float* W, int M, int N, int K,
                                   const RpbScatterDesc* d, void* stream) {
     if (dy == nullptr || W == nullptr || d == nullptr || M <= 0 || N <= 0 || K <= 0) return RPB_ERR_BAD_ARG;

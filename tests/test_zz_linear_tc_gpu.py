@@ -53,3 +53,18 @@ def test_persistent_gemm_many_tiles_and_resident_weights():
         y1 = ops.linear(x, W, b, K=K, impl=1)
         y2 = ops.linear(x, W, b, K=K, impl=2)
         assert (y1 - y2).abs().max().item() < 3e-5, (M, N, K)
+
+
+@pytest.mark.parametrize('option', [b'gemm_a_tmem', b'gemm_stack_n'])
+@pytest.mark.parametrize('M,N,K,relu', [(1000, 64, 429, True), (4096, 128, 64, False), (148 * 128 * 2 + 5, 64, 429, True),
+                                        (300, 36, 70, False)])
+def test_linear_tcgen05_operand_modes_still_correct(M, N, K, relu, option):
+    """gemm_a_tmem = 0 keeps the split A operand in shared memory (SS-mode MMA) instead of tensor memory (TS mode);
+    gemm_stack_n = 0 issues three N = block_n MMAs per k-step instead of two against the stacked [B hi ; B lo] operand."""
+    from rec_pangu_b200 import _lib
+    lib = _lib.load()
+    assert lib.rpb_set_option(option, 0) == 0
+    try:
+        _check_linear(M, N, K, relu, impl=2, tol=1e-5)
+    finally:
+        lib.rpb_set_option(option, 1)
