@@ -697,7 +697,7 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int m, int n) {
 template <int kStages>
 __global__ void __launch_bounds__(TC_THREADS)
 wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDy,
-                    float* __restrict__ dW, int N, int K, int M, int block_n, int slab, uint32_t tmem_cols) {
+                    float* __restrict__ dW, int N, int K, int M, int block_n, int slab, uint32_t tmem_cols, int stack_n, int raw_hi) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int a_bytes = 4 * WG_BOX_BYTES;                    // 128 k-columns = 4 chunks
@@ -716,6 +716,8 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const int mbeg = blockIdx.y * slab;
     const int mend = min(M, mbeg + slab);
     const int num_kb = (mend - mbeg + WG_ROWS - 1) / WG_ROWS;
+    const bool trace = g_tc_trace_on != 0 && blockIdx.x == 0 && blockIdx.y == 0;
+    const long long t_start = TC_TRACE_T();
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&ready_bar[s], 128); mbar_init(&empty_bar[s], 1); }
@@ -731,10 +733,14 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     if (warp == 0) {
         if (lane == 0) {
             const uint32_t tx_bytes = (uint32_t)(a_bytes + b_bytes);
+            long long w_raw = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % kStages;
                 const uint32_t ph = (uint32_t)((kb / kStages) & 1);
+                const long long c0 = TC_TRACE_T();
                 mbar_wait(&empty_bar[s], ph ^ 1u);
+                w_raw += TC_TRACE_T() - c0;
+                if (trace && kb == num_kb - 1) { g_tc_trace[1] = (unsigned long long)w_raw; g_tc_trace[10] = (unsigned long long)num_kb; }
                 uint8_t* st = smem + (size_t)s * stage_bytes;
                 const int m0 = mbeg + kb * WG_ROWS;
                 mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
@@ -745,11 +751,17 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32_mn(128, block_n);
+            // stack_n: [B hi ; B lo] (adjacent 32-float chunks, LBO apart) as ONE operand of 2*block_n columns — two MMAs per
+            // 8-sample group instead of three; accumulator columns [0, block_n) = a.b_hi, [block_n, 2*block_n) = a.b_lo.
+            const uint32_t idesc = make_idesc_tf32_mn(128, stack_n ? 2 * block_n : block_n);
+            long long w_ready = 0, w_issue = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % kStages;
                 const uint32_t ph = (uint32_t)((kb / kStages) & 1);
+                const long long c1 = TC_TRACE_T();
                 mbar_wait(&ready_bar[s], ph);
+                const long long c2 = TC_TRACE_T();
+                w_ready += c2 - c1;
                 tc_fence_after();
                 const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
                 const uint32_t a_lo = a_hi + a_bytes;
@@ -760,53 +772,93 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                     const uint32_t koff = g * 1024;                         // one 8-sample K group
                     const uint64_t da_hi = make_mnmajor_sw128_desc(a_hi + koff), da_lo = make_mnmajor_sw128_desc(a_lo + koff);
                     const uint64_t db_hi = make_mnmajor_sw128_desc(b_hi + koff), db_lo = make_mnmajor_sw128_desc(b_lo + koff);
+                    if (stack_n) {
+                        umma_tf32(tmem_base, da_lo, db_hi, idesc, (kb > 0 || g > 0) ? 1u : 0u);
+                        umma_tf32(tmem_base, da_hi, db_hi, idesc, 1u);
+                        continue;
+                    }
                     umma_tf32(tmem_base, da_lo, db_hi, idesc, (kb > 0 || g > 0) ? 1u : 0u);
                     umma_tf32(tmem_base, da_hi, db_lo, idesc, 1u);
                     umma_tf32(tmem_base, da_hi, db_hi, idesc, 1u);
                 }
                 umma_commit(&empty_bar[s]);
+                w_issue += TC_TRACE_T() - c2;
             }
             umma_commit(tmem_full_bar);
+            if (trace) { g_tc_trace[2] = (unsigned long long)w_ready; g_tc_trace[4] = (unsigned long long)w_issue; }
         }
     } else {
         const int t = threadIdx.x - 64;
-        const int a_vec = a_bytes / 16, b_vec = b_bytes / 16;
+        const int b_vec = b_bytes / 16;
+        long long w_full = 0, w_work = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
             const int s = kb % kStages;
             const uint32_t ph = (uint32_t)((kb / kStages) & 1);
+            const long long c0 = TC_TRACE_T();
             mbar_wait(&full_bar[s], ph);
+            const long long c1 = TC_TRACE_T();
+            w_full += c1 - c0;
             float4* a = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
             float4* alo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + a_bytes);
             float4* b = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + 2 * a_bytes);
             float4* blo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + 2 * a_bytes + b_bytes);
-            for (int j = t; j < a_vec + b_vec; j += 128) {
-                float4* src = j < a_vec ? a + j : b + (j - a_vec);
-                float4* dlo = j < a_vec ? alo + j : blo + (j - a_vec);
-                const float4 v = *src;
-                float4 h, l;
-                h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-                h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-                h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-                h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-                *src = h;
-                *dlo = l;
+            // all loads of a batch are issued before the first dependent store (the straightforward one-vector-per-iteration
+            // loop ran at ~125 cycles per vector and made the split warps the bottleneck of the whole kernel)
+            {
+                float4 v[8];                                     // A: 4 chunks x 4 KiB = 1024 vectors = 8 per thread
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = a[t + 128 * i];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(v[i].x) & 0xFFFFE000u); l.x = v[i].x - h.x;
+                    h.y = __uint_as_float(__float_as_uint(v[i].y) & 0xFFFFE000u); l.y = v[i].y - h.y;
+                    h.z = __uint_as_float(__float_as_uint(v[i].z) & 0xFFFFE000u); l.z = v[i].z - h.z;
+                    h.w = __uint_as_float(__float_as_uint(v[i].w) & 0xFFFFE000u); l.w = v[i].w - h.w;
+                    if (!raw_hi) a[t + 128 * i] = h;
+                    alo[t + 128 * i] = l;
+                }
+            }
+            for (int j0 = 0; j0 < b_vec; j0 += 512) {           // B: b_chunks x 256 vectors, 4 per thread per pass
+                float4 v[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) if (j0 + t + 128 * i < b_vec) v[i] = b[j0 + t + 128 * i];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (j0 + t + 128 * i < b_vec) {
+                        float4 h, l;
+                        h.x = __uint_as_float(__float_as_uint(v[i].x) & 0xFFFFE000u); l.x = v[i].x - h.x;
+                        h.y = __uint_as_float(__float_as_uint(v[i].y) & 0xFFFFE000u); l.y = v[i].y - h.y;
+                        h.z = __uint_as_float(__float_as_uint(v[i].z) & 0xFFFFE000u); l.z = v[i].z - h.z;
+                        h.w = __uint_as_float(__float_as_uint(v[i].w) & 0xFFFFE000u); l.w = v[i].w - h.w;
+                        if (!raw_hi) b[j0 + t + 128 * i] = h;
+                        blo[j0 + t + 128 * i] = l;
+                    }
+                }
             }
             fence_proxy_async();
             mbar_arrive(&ready_bar[s]);
+            w_work += TC_TRACE_T() - c1;
         }
         // epilogue: TMEM lane = dW column k0+row, TMEM column = output row n
+        const long long e0 = TC_TRACE_T();
         mbar_wait(tmem_full_bar, 0);
+        const long long e1 = TC_TRACE_T();
+        if (trace && t == 0) { g_tc_trace[5] = (unsigned long long)w_full; g_tc_trace[7] = (unsigned long long)w_work; g_tc_trace[8] = (unsigned long long)(e1 - e0); }
         tc_fence_after();
         const int quarter = warp & 3;
         const int k = k0 + quarter * 32 + lane;
         for (int c0 = 0; c0 < block_n; c0 += 16) {
             uint32_t r[16];
             tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+            uint32_t r2[16];
+            if (stack_n) tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(block_n + c0), r2);
             if (k < K) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const int n = c0 + j;
-                    if (n < N) red_add_f1(dW + (size_t)n * K + k, __uint_as_float(r[j]));
+                    const float v = stack_n ? __uint_as_float(r2[j]) + __uint_as_float(r[j]) : __uint_as_float(r[j]);
+                    if (n < N) red_add_f1(dW + (size_t)n * K + k, v);
                 }
             }
         }
@@ -814,6 +866,7 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     tc_fence_before();
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+    if (trace && threadIdx.x == 0) g_tc_trace[0] = (unsigned long long)(clock64() - t_start);
 }
 
 // W[N,K] (row stride ldw) -> hi/lo [Np, Kp] zero padded;  transpose: out[k, n] = W[n, k] (out is [Kout=K rows.., ])
@@ -965,8 +1018,15 @@ int gemm_tc(const float* A, long long lda, const float* Bsrc, long long ldb, int
 int wgrad_tc(const float* dy, long long lddy, const float* x, long long ldx, float* dW, int M, int N, int K, cudaStream_t st) {
     if ((lddy % 4) != 0 || (ldx % 4) != 0 || (reinterpret_cast<uintptr_t>(dy) & 15u) || (reinterpret_cast<uintptr_t>(x) & 15u))
         return RPB_ERR_UNSUPPORTED;
+    if (N > 256) {                                   // wide layers (MMOE experts): one launch per 256-column slice of dy
+        for (int n0 = 0; n0 < N; n0 += 256) {
+            const int rc = wgrad_tc(dy + n0, lddy, x, ldx, dW + (size_t)n0 * K, M, min(256, N - n0), K, st);
+            if (rc != 0) return rc;
+        }
+        return 0;
+    }
     const int block_n = round_up(N, 32);
-    if (block_n > 256) return RPB_ERR_UNSUPPORTED;
+    const int stack_n = (g_gemm_stack_n && block_n <= 64) ? 1 : 0;
     CUtensorMap tmX, tmDy;
     int rc = make_map(&tmX, x, M, K, ldx, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc == 0) rc = make_map(&tmDy, dy, M, N, lddy, WG_ROWS, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
@@ -977,13 +1037,13 @@ int wgrad_tc(const float* dy, long long lddy, const float* x, long long ldx, flo
     slabs = ceil_div(M, slab);
     const int stage_bytes = 2 * 4 * WG_BOX_BYTES + 2 * (block_n / 32) * WG_BOX_BYTES;
     uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < block_n) tmem_cols <<= 1;
+    while ((int)tmem_cols < (stack_n ? 2 * block_n : block_n)) tmem_cols <<= 1;
     auto launch = [&](auto stages_tag) -> int {
         constexpr int S = decltype(stages_tag)::value;
         const size_t smem = (size_t)S * stage_bytes + (3 * S + 2) * 8 + 1024;
         cudaError_t ee = cudaFuncSetAttribute(wgrad_tf32x3_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (ee != cudaSuccess) return (int)ee;
-        wgrad_tf32x3_kernel<S><<<dim3(ktiles, slabs), TC_THREADS, smem, st>>>(tmX, tmDy, dW, N, K, M, block_n, slab, tmem_cols);
+        wgrad_tf32x3_kernel<S><<<dim3(ktiles, slabs), TC_THREADS, smem, st>>>(tmX, tmDy, dW, N, K, M, block_n, slab, tmem_cols, stack_n, g_tf32_raw_hi);
         return (int)cudaGetLastError();
     };
     const int max_stages = (200 * 1024) / stage_bytes;

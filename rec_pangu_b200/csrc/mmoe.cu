@@ -14,6 +14,7 @@ namespace rpb {
 int gemm_tc(const float* A, long long lda, const float* Bsrc, long long ldb, int b_transpose, const TcEpilogue& ep,
             int M, int N, int K, cudaStream_t st);
 bool tc_shape_ok(const float* A, long long lda, int M, int N, int K);
+int wgrad_tc(const float* dy, long long lddy, const float* x, long long ldx, float* dW, int M, int N, int K, cudaStream_t st);
 int linear_dw_simt(const float* dy, long long lddy, const float* x, long long ldx, float* dW, float* db,
                    int M, int N, int K, cudaStream_t st);
 int sgemm_kn_simt(const float* x, long long ldx, const float* Wkn, long long ldw, const float* bias, float* y,
@@ -221,7 +222,12 @@ RPB_API int rpb_matmul_kn_bwd(const float* dy, int64_t lddy, const float* x, int
     if (dWkn != nullptr) {
         if (x == nullptr) return RPB_ERR_BAD_ARG;
         // dWkn[k,n] += sum_m x[m,k] dy[m,n]  == wgrad with the roles of x and dy swapped (output [K, N], row stride N)
-        rc = linear_dw_simt(x, ldx, dy, lddy, dWkn, nullptr, M, K, N, st);
+        rc = RPB_ERR_UNSUPPORTED;
+        if (impl == 2 || (impl == 0 && M >= 2048 && g_wgrad_tc)) {
+            rc = wgrad_tc(x, ldx, dy, lddy, dWkn, M, K, N, st);                 // tcgen05, sliced over K > 256
+            if (rc != 0 && rc != RPB_ERR_UNSUPPORTED) return rc;
+        }
+        if (rc != 0) rc = linear_dw_simt(x, ldx, dy, lddy, dWkn, nullptr, M, K, N, st);
         if (rc != 0) return rc;
     }
     if (db != nullptr) {

@@ -39,3 +39,33 @@ if __name__ == '__main__':
     for a in (1, 0):
         run(65536, 64, 429, 432, a)
         run(65536, 64, 64, 64, a)
+
+
+def run_wgrad(M, N, K, ldx):
+    lib = _lib.load()
+    x = torch.zeros(M, ldx, device='cuda')
+    x[:, :K] = torch.randn(M, K, device='cuda')
+    dy = torch.randn(M, N, device='cuda')
+    W = torch.randn(N, K, device='cuda')
+    dW = torch.zeros(N, K, device='cuda')
+    st = torch.cuda.current_stream().cuda_stream
+
+    def call():
+        return lib.rpb_linear_bwd(dy.data_ptr(), N, x.data_ptr(), ldx, W.data_ptr(), None, 0, None, 0, dW.data_ptr(), None,
+                                  M, N, K, 2, st)
+    for _ in range(3):
+        assert call() == 0
+    torch.cuda.synchronize()
+    lib.rpb_debug_tc_trace(None, 1)
+    assert call() == 0
+    torch.cuda.synchronize()
+    out = (C.c_uint64 * 16)()
+    lib.rpb_debug_tc_trace(out, 0)
+    print(f'wgrad M={M} N={N} K={K}')
+    for n, v in zip(NAMES, out):
+        print(f'   {n:22s} {v:10d}')
+
+
+if __name__ == '__main__':
+    run_wgrad(65536, 64, 429, 432)
+    run_wgrad(65536, 64, 64, 64)
