@@ -156,6 +156,44 @@ int rpb_sigmoid_bce_fwd(const float* logit, const float* label, float* pred, flo
 int rpb_sigmoid_bce_bwd(const float* pred, const float* label, const float* gloss, float eps, float scale,
                         float* dlogit, int M, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * MLP tower tail: the n_tail (0..RPB_TOWER_MAX_TAIL) square H x H hidden layers that follow the first layer, the
+ * Linear(H -> 1) output layer, the logit sum, the sigmoid and the mean BCE in ONE launch (models/layers/deep.py:62-84
+ * with ReLU after every hidden layer and dropout inactive; ranking/deepfm.py:57-63 for `fm + dnn`, sigmoid, BCELoss).
+ * Exact fp32 FMAs on a shared-memory resident activation tile; H must be 64.
+ *   h[l] = relu(h[l-1] @ W[l]^T + b[l])   (h[-1] = h1, the post-ReLU output of layer 1, row stride ldh1)
+ *   logit = h[n_tail-1] . w_out + b_out[0] (+ addend);  pred = sigmoid(logit);  loss = scale * mean BCE(pred + eps, label)
+ * W, b, h are HOST arrays of n_tail device pointers; h[l] is [M, H] contiguous (saved for backward).  pred / label /
+ * loss may be NULL (loss needs label, pred and work: the same int32[2 + 2048] scratch as rpb_sigmoid_bce_fwd). */
+#define RPB_TOWER_MAX_TAIL 4
+typedef struct RpbTowerFwdDesc {
+    int32_t M, H, n_tail;
+    const float* h1; int64_t ldh1;
+    const float* const* W; const float* const* b; float* const* h;
+    const float* w_out; const float* b_out; const float* addend;
+    float* logit; const float* label; float* pred; float* loss;
+    float eps, scale;
+    void* work;
+} RpbTowerFwdDesc;
+int rpb_tower_tail_fwd(const RpbTowerFwdDesc* d, void* stream);
+/* Backward of rpb_tower_tail_fwd.  hin: HOST array of n_tail+1 device pointers, hin[0] = h1 (row stride ldh1),
+ * hin[j] = h[j-1] ([M, H] contiguous).  dlogit[m] = dlogit_in[m] when given, else gloss[0]*scale/M * dBCE/dp * p(1-p)
+ * from (pred, label) with ATen's clamps (gloss NULL = 1); it is written to dlogit_out when non-NULL.
+ * dz: HOST array of n_tail+1 device pointers, out [M, H]: dz[j] = gradient wrt the pre-activation that produced hin[j]
+ * (dz[0] feeds the first layer's weight-gradient and dx kernels, dz[j] with hin[j-1] gives dW[j-1]).
+ * db (HOST array of n_tail+1 device pointers or NULL, entries may be NULL): db[j] += colsum(dz[j]);
+ * dw_out[H] += sum_m dlogit[m] * hin[n_tail][m, :];  db_out[0] += sum_m dlogit[m]. */
+typedef struct RpbTowerBwdDesc {
+    int32_t M, H, n_tail;
+    const float* const* hin; int64_t ldh1;
+    const float* const* W; const float* w_out;
+    float* const* dz; float* const* db;
+    float* dw_out; float* db_out;
+    const float* pred; const float* label; const float* gloss; float eps, scale;
+    const float* dlogit_in; float* dlogit_out;
+} RpbTowerBwdDesc;
+int rpb_tower_tail_bwd(const RpbTowerBwdDesc* d, void* stream);
+
 /* nn.Dropout of the MLP (models/layers/deep.py:71-72, default p=0.1 for xDeepFM/AutoInt) on a contiguous
  * buffer of n floats.  keep(i) comes from a counter-based generator keyed by (seed, i), so backward recomputes
  * the mask instead of storing it.  Train-mode equivalence with torch's Philox stream is statistical

@@ -7,7 +7,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'librec_pangu_b200.so')
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_FIELDS = 64
 MAX_DENSE = 64
 ERR_UNSUPPORTED = -1
@@ -39,6 +39,20 @@ class SparseAdamDesc(C.Structure):
                 ('idx', C.POINTER(_vp))]
 
 
+class TowerFwdDesc(C.Structure):
+    _fields_ = [('M', _i32), ('H', _i32), ('n_tail', _i32), ('h1', _vp), ('ldh1', _i64),
+                ('W', C.POINTER(_vp)), ('b', C.POINTER(_vp)), ('h', C.POINTER(_vp)),
+                ('w_out', _vp), ('b_out', _vp), ('addend', _vp), ('logit', _vp), ('label', _vp), ('pred', _vp),
+                ('loss', _vp), ('eps', _f32), ('scale', _f32), ('work', _vp)]
+
+
+class TowerBwdDesc(C.Structure):
+    _fields_ = [('M', _i32), ('H', _i32), ('n_tail', _i32), ('hin', C.POINTER(_vp)), ('ldh1', _i64),
+                ('W', C.POINTER(_vp)), ('w_out', _vp), ('dz', C.POINTER(_vp)), ('db', C.POINTER(_vp)),
+                ('dw_out', _vp), ('db_out', _vp), ('pred', _vp), ('label', _vp), ('gloss', _vp),
+                ('eps', _f32), ('scale', _f32), ('dlogit_in', _vp), ('dlogit_out', _vp)]
+
+
 # name -> (restype, argtypes); must list every symbol of include/rec_pangu_b200.h (tests check this)
 SIGNATURES = {
     'rpb_version': (C.c_int, []),
@@ -58,6 +72,8 @@ SIGNATURES = {
     'rpb_rowdot_bwd': (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _vp, C.c_int, C.c_int, _vp]),
     'rpb_sigmoid_bce_fwd': (C.c_int, [_vp, _vp, _vp, _vp, _f32, _f32, C.c_int, _vp, _vp]),
     'rpb_sigmoid_bce_bwd': (C.c_int, [_vp, _vp, _vp, _f32, _f32, _vp, C.c_int, _vp]),
+    'rpb_tower_tail_fwd': (C.c_int, [C.POINTER(TowerFwdDesc), _vp]),
+    'rpb_tower_tail_bwd': (C.c_int, [C.POINTER(TowerBwdDesc), _vp]),
     'rpb_dropout_fwd': (C.c_int, [_vp, _vp, _i64, _f32, C.c_uint64, _vp]),
     'rpb_dropout_bwd': (C.c_int, [_vp, _vp, _vp, _i64, _f32, C.c_uint64, _vp]),
     'rpb_crossnet_fwd': (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(_vp), _vp, _i64, _vp, C.c_int, _vp]),

@@ -41,7 +41,7 @@ void* workspace(int slot, size_t bytes, int* err) {
 
 }  // namespace rpb
 
-RPB_API int rpb_version(void) { return 2; }
+RPB_API int rpb_version(void) { return 3; }
 
 RPB_API const char* rpb_error_string(int code) {
     switch (code) {

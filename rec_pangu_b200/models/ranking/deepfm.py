@@ -29,10 +29,17 @@ class DeepFM(BaseModel):
             # gradients from its epilogue (no dx round trip through HBM)
             from ... import ops
             Ws, bs, relu, drops = self.dnn.layer_params()
-            logit = ops.deepfm_core(emb.tables(), [data[c] for c in emb.emb_feature], [data[c] for c in emb.dense_feature],
-                                    Ws, bs, n_hidden=len(relu), relu=relu, dropout=drops, training=self.training,
-                                    grad_store=emb._grad_store if emb.grad_mode == 'persistent' else None)
-            return self._finish(logit, data, is_training)
+            fused_loss = (is_training and 'label' in data and isinstance(self.loss_fun, torch.nn.BCELoss)
+                          and self.loss_fun.reduction == 'mean' and self.loss_fun.weight is None)
+            res = ops.deepfm_core(emb.tables(), [data[c] for c in emb.emb_feature], [data[c] for c in emb.dense_feature],
+                                  Ws, bs, n_hidden=len(relu), relu=relu, dropout=drops, training=self.training,
+                                  grad_store=emb._grad_store if emb.grad_mode == 'persistent' else None,
+                                  label=data['label'] if fused_loss else None)
+            if isinstance(res, tuple):             # sigmoid + BCE came out of the kernel that finished the MLP
+                logit, pred, loss = res
+                self._last_logit = logit.detach()
+                return {'pred': pred, 'loss': loss}
+            return self._finish(res, data, is_training)
         # row-sharded tables: one launch gathers 26 rows/sample over NVLink -> feature row x + FM second-order term
         x, fm_out, _ = emb.feature_row(data, with_dense=True, want_fm=True)
         dnn_output = self.dnn(x, K=self.dnn_input_dim)                  # [B,1]

@@ -10,7 +10,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import GatherDesc, ScatterDesc, check
+from ._lib import GatherDesc, ScatterDesc, TowerFwdDesc, TowerBwdDesc, check
 
 __all__ = ['GradStore', 'deepfm_core', 'gather', 'gather_sharded', 'sharded_clean', 'fm_interaction', 'mlp_forward', 'sigmoid_bce', 'linear', 'feature_row_stride',
            'check_index_errors', 'set_gemm_impl', 'get_gemm_impl', 'launch_count', 'reset_launch_count']
@@ -19,6 +19,9 @@ _GEMM_IMPL = int(__import__('os').environ.get('RPB_GEMM_IMPL', '0'))   # 0 auto,
 # DeepFM backward: 1 = layer-1 dx GEMM scatters table gradients from its epilogue (rpb_linear_dx_scatter),
 # 0 = dx GEMM to HBM followed by rpb_gather_bwd.  Both are bit-for-bit the same sums in a different add order.
 FUSED_DX_SCATTER = int(__import__('os').environ.get('RPB_DX_SCATTER', '1'))
+# MLP tower tail (rpb_tower_tail_fwd/bwd): 1 = every 64-wide hidden layer after the first, the Linear(64->1) output, the
+# logit sum and (DeepFM) sigmoid + BCE run as ONE fp32 kernel per direction; 0 = one GEMM / row-dot / head kernel each.
+TOWER_TAIL = int(__import__('os').environ.get('RPB_TOWER_TAIL', '1'))
 _LAUNCHES = 0           # number of librec_pangu_b200 kernels launched (bench.py reports it as gpu_launches)
 
 
@@ -618,13 +621,135 @@ def _mlp_bwd(cfg, acts, pre_drop, seeds, params, g, need_dx_input, layer0_hook=N
     return gx, gparams
 
 
+def _tower_ok(cfg, params) -> bool:
+    """True when the MLP is Linear(K->64)+ReLU, n_tail x [Linear(64->64)+ReLU], Linear(64->1) with dropout inactive:
+    the shape rpb_tower_tail_* is built for (DeepFM/xDeepFM/AutoInt/FiBiNet/WDL defaults, deep.py:36-41)."""
+    if not TOWER_TAIL or not cfg.get('has_out', True):
+        return False
+    n_hidden = cfg['n_hidden']
+    if n_hidden < 1 or n_hidden - 1 > 4 or len(params) != 2 * n_hidden + 2:
+        return False
+    for i in range(n_hidden):
+        if not cfg['relu'][i] or (cfg['training'] and cfg['dropout'][i] > 0.0):
+            return False
+        W, b = params[2 * i], params[2 * i + 1]
+        if b is None or W.shape[0] != 64 or (i > 0 and W.shape[1] != 64):
+            return False
+    Wo, bo = params[2 * n_hidden], params[2 * n_hidden + 1]
+    return bo is not None and Wo.shape[0] == 1 and Wo.shape[1] == 64
+
+
+def _tower_fwd(cfg, x, params, addend=None, head=None):
+    """Layer 1 on the tcgen05 GEMM, everything after it in rpb_tower_tail_fwd.  head = (label [M], eps, scale) also
+    yields pred [M,1] and the mean-BCE loss from the same launch.  Returns (logit [M,1], acts, pred | None, loss | None)."""
+    n_hidden, K, impl = cfg['n_hidden'], cfg['K'], cfg['impl']
+    lib = _lib.load()
+    st = _stream()
+    M, dev = x.shape[0], x.device
+    y1 = torch.empty((M, 64), dtype=torch.float32, device=dev)
+    check(lib.rpb_linear_fwd(_ptr(x), x.stride(0), _ptr(params[0]), _ptr(params[1]), _ptr(y1), 64, M, 64, K, 1, impl, st),
+          'rpb_linear_fwd')
+    _count(2 if impl != 1 else 1)
+    n_tail = n_hidden - 1
+    hs = [torch.empty((M, 64), dtype=torch.float32, device=dev) for _ in range(n_tail)]
+    logit = torch.empty((M, 1), dtype=torch.float32, device=dev)
+    d = TowerFwdDesc()
+    d.M, d.H, d.n_tail = M, 64, n_tail
+    d.h1, d.ldh1 = y1.data_ptr(), 64
+    keep = None
+    if n_tail:
+        keep = (_ptr_list([params[2 * (l + 1)] for l in range(n_tail)]),
+                _ptr_list([params[2 * (l + 1) + 1] for l in range(n_tail)]), _ptr_list(hs))
+        d.W, d.b, d.h = keep
+    d.w_out, d.b_out = params[2 * n_hidden].data_ptr(), params[2 * n_hidden + 1].data_ptr()
+    d.addend = addend.data_ptr() if addend is not None else None
+    d.logit = logit.data_ptr()
+    pred = loss = None
+    if head is not None:
+        label, eps, scale = head
+        pred = torch.empty((M, 1), dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        d.label, d.pred, d.loss = label.data_ptr(), pred.data_ptr(), loss.data_ptr()
+        d.eps, d.scale = eps, scale
+        d.work = _head_work(dev).data_ptr()
+    check(lib.rpb_tower_tail_fwd(C.byref(d), st), 'rpb_tower_tail_fwd')
+    _count()
+    del keep
+    return logit, [x, y1] + hs, pred, loss
+
+
+def _tower_bwd(cfg, acts, params, dlogit_in=None, head=None, gloss=None, need_dx_input=False, layer0_hook=None):
+    """Backward of _tower_fwd.  dlogit comes from `dlogit_in` ([M]) or is formed in the kernel from head = (pred, label,
+    eps, scale) and gloss (0-dim tensor or None = 1).  Returns (gx | None, gparams, dlogit [M])."""
+    n_hidden, K, impl = cfg['n_hidden'], cfg['K'], cfg['impl']
+    lib = _lib.load()
+    st = _stream()
+    x = acts[0]
+    M, dev = x.shape[0], x.device
+    n_tail = n_hidden - 1
+    flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
+    zviews, off = [], 0
+    for p in params:
+        zviews.append(flat[off:off + p.numel()].view(p.shape))
+        off += p.numel()
+    dzs = [torch.empty((M, 64), dtype=torch.float32, device=dev) for _ in range(n_hidden)]
+    dlogit = torch.empty((M,), dtype=torch.float32, device=dev)
+    d = TowerBwdDesc()
+    d.M, d.H, d.n_tail = M, 64, n_tail
+    hin = list(acts[1:1 + n_hidden])
+    keep = [_ptr_list(hin), _ptr_list(dzs), _ptr_list([zviews[2 * j + 1] for j in range(n_hidden)])]
+    d.hin, d.dz, d.db = keep
+    d.ldh1 = hin[0].stride(0)
+    if n_tail:
+        keep.append(_ptr_list([params[2 * (l + 1)] for l in range(n_tail)]))
+        d.W = keep[-1]
+    d.w_out = params[2 * n_hidden].data_ptr()
+    d.dw_out, d.db_out = zviews[2 * n_hidden].data_ptr(), zviews[2 * n_hidden + 1].data_ptr()
+    if dlogit_in is not None:
+        d.dlogit_in = dlogit_in.data_ptr()
+    else:
+        pred, label, eps, scale = head
+        d.pred, d.label, d.eps, d.scale = pred.data_ptr(), label.data_ptr(), eps, scale
+        if gloss is not None:
+            gl = gloss.reshape(1).contiguous().float()
+            d.gloss = gl.data_ptr()
+    d.dlogit_out = dlogit.data_ptr()
+    check(lib.rpb_tower_tail_bwd(C.byref(d), st), 'rpb_tower_tail_bwd')
+    _count()
+    # weight gradients (bias gradients came out of the tower kernel): dW_i = dz_i^T . input_i
+    for i in range(n_hidden - 1, -1, -1):
+        kdim = K if i == 0 else 64
+        check(lib.rpb_linear_bwd(_ptr(dzs[i]), 64, _ptr(acts[i]), acts[i].stride(0), None, None, 0, None, 0,
+                                 _ptr(zviews[2 * i]), None, M, 64, kdim, impl, st), 'rpb_linear_bwd')
+        _count()
+    gparams = list(zviews)
+    if layer0_hook is not None and layer0_hook(dzs[0], 64, params[0], dlogit):
+        return None, gparams, dlogit
+    gx = None
+    if need_dx_input or layer0_hook is not None:
+        gx = torch.empty((M, x.stride(0)), dtype=torch.float32, device=dev)
+        if x.stride(0) > K:
+            gx[:, K:].zero_()
+        check(lib.rpb_linear_bwd(_ptr(dzs[0]), 64, None, 0, _ptr(params[0]), None, 0, _ptr(gx), gx.stride(0), None, None,
+                                 M, 64, K, impl, st), 'rpb_linear_bwd')
+        _count(2 if impl != 1 else 1)
+        if gx.shape[1] != x.shape[1]:
+            gx = gx[:, :x.shape[1]]
+    return gx, gparams, dlogit
+
+
 class _MLP(torch.autograd.Function):
     """Linear(+ReLU)(+Dropout) x n_hidden + Linear(out) as one autograd node so ReLU backward is fused into the
     producing GEMM's epilogue (mask = saved activation)."""
 
     @staticmethod
     def forward(ctx, cfg, x, *params):
-        out, acts, pre_drop, seeds = _mlp_fwd(cfg, x, params)
+        ctx.tower = _tower_ok(cfg, params)
+        if ctx.tower:
+            out, acts, _, _ = _tower_fwd(cfg, x, params)
+            pre_drop, seeds = [None] * cfg['n_hidden'], [0] * cfg['n_hidden']
+        else:
+            out, acts, pre_drop, seeds = _mlp_fwd(cfg, x, params)
         ctx.cfg = cfg
         ctx.seeds = seeds
         ctx.n_saved_acts = len(acts)
@@ -640,7 +765,11 @@ class _MLP(torch.autograd.Function):
         acts = saved[:na]
         pre_drop = saved[na:na + n_hidden]
         params = saved[na + n_hidden:]
-        gx, gparams = _mlp_bwd(cfg, acts, pre_drop, ctx.seeds, params, g, ctx.needs_input_grad[1])
+        if ctx.tower:
+            gx, gparams, _ = _tower_bwd(cfg, acts, params, dlogit_in=g.reshape(-1).contiguous(),
+                                        need_dx_input=ctx.needs_input_grad[1])
+        else:
+            gx, gparams = _mlp_bwd(cfg, acts, pre_drop, ctx.seeds, params, g, ctx.needs_input_grad[1])
         return (None, gx if ctx.needs_input_grad[1] else None, *gparams)
 
 
@@ -653,20 +782,32 @@ class _DeepFMCore(torch.autograd.Function):
     def forward(ctx, cfg, gcfg, *tensors):
         F, Nd = gcfg['F'], gcfg['Nd']
         tables, idx, dense = tensors[:F], tensors[F:2 * F], tensors[2 * F:2 * F + Nd]
-        params = tensors[2 * F + Nd:]
+        label = tensors[-1] if gcfg['has_label'] else None
+        params = tensors[2 * F + Nd:len(tensors) - (1 if gcfg['has_label'] else 0)]
         need_grad = gcfg['needs_grad']
         x, fm, fm_s, rows = _gather_fwd_raw(tables, idx, dense, want_fm=True, need_grad=need_grad)
-        logit, acts, pre_drop, seeds = _mlp_fwd(cfg, x, params, addend=fm)
+        ctx.tower = gcfg['tower']
+        pred = loss = None
+        if ctx.tower:
+            head = (label, 0.0, 1.0) if label is not None else None
+            logit, acts, pred, loss = _tower_fwd(cfg, x, params, addend=fm, head=head)
+            pre_drop, seeds = [None] * cfg['n_hidden'], [0] * cfg['n_hidden']
+        else:
+            logit, acts, pre_drop, seeds = _mlp_fwd(cfg, x, params, addend=fm)
         ctx.set_materialize_grads(False)
         ctx.cfg, ctx.gcfg, ctx.seeds, ctx.rows = cfg, gcfg, seeds, rows
         ctx.tables = tables
         ctx.n_saved_acts = len(acts)
         ctx.n_inputs = 2 + len(tensors)
-        ctx.save_for_backward(fm_s, *idx, *acts, *[t if t is not None else x.new_empty(0) for t in pre_drop], *params)
+        extra = [pred, label] if pred is not None else []
+        ctx.n_extra = len(extra)
+        ctx.save_for_backward(fm_s, *idx, *acts, *[t if t is not None else x.new_empty(0) for t in pre_drop], *params, *extra)
+        if pred is not None:
+            return logit, pred, loss
         return logit
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, g, g_pred=None, g_loss=None):
         cfg, gcfg = ctx.cfg, ctx.gcfg
         F, Nd, D = gcfg['F'], gcfg['Nd'], gcfg['D']
         n_hidden = cfg['n_hidden']
@@ -676,7 +817,8 @@ class _DeepFMCore(torch.autograd.Function):
         na = ctx.n_saved_acts
         acts = saved[1 + F:1 + F + na]
         pre_drop = saved[1 + F + na:1 + F + na + n_hidden]
-        params = saved[1 + F + na + n_hidden:]
+        params = saved[1 + F + na + n_hidden:len(saved) - ctx.n_extra]
+        pred, label = (saved[-2], saved[-1]) if ctx.n_extra else (None, None)
         x = acts[0]
         dev = x.device
         tables = ctx.tables
@@ -689,20 +831,19 @@ class _DeepFMCore(torch.autograd.Function):
             g_tables = [store.buffer(tables[f]) if tbl_req[f] else None for f in range(F)]
         else:
             g_tables = [torch.zeros((ctx.rows[f], D), dtype=torch.float32, device=dev) if tbl_req[f] else None for f in range(F)]
-        dlogit = g.reshape(-1).contiguous()                       # = dL/dfm as well (logit = fm + dnn)
 
-        def desc(dx=None):
+        def desc(dlogit, dx=None):
             d = ScatterDesc()
             d.B, d.F, d.D = x.shape[0], F, D
             if dx is not None:
                 d.dx, d.lddx = dx.data_ptr(), dx.stride(0)
-            d.dfm, d.x, d.ldx, d.fm_s = dlogit.data_ptr(), x.data_ptr(), x.stride(0), fm_s.data_ptr()
-            d._keep = (_ptr_list(g_tables), (C.c_int64 * F)(*ctx.rows), _ptr_list(idx))
-            d.grads, d.rows, d.idx = d._keep
+            d.dfm, d.x, d.ldx, d.fm_s = dlogit.data_ptr(), x.data_ptr(), x.stride(0), fm_s.data_ptr()   # dL/dfm = dlogit
+            d._keep = (_ptr_list(g_tables), (C.c_int64 * F)(*ctx.rows), _ptr_list(idx), dlogit)
+            d.grads, d.rows, d.idx = d._keep[:3]
             return d
 
-        def hook(dh, lddh, W0):
-            d = desc()
+        def hook(dh, lddh, W0, dlogit):
+            d = desc(dlogit)
             rc = _lib.load().rpb_linear_dx_scatter(_ptr(dh), lddh, _ptr(W0), x.shape[0], W0.shape[0], cfg['K'], C.byref(d),
                                                    _stream())
             if rc == _lib.ERR_UNSUPPORTED:
@@ -712,10 +853,33 @@ class _DeepFMCore(torch.autograd.Function):
             return True
 
         any_tbl = any(t is not None for t in g_tables)
-        gx, gparams = _mlp_bwd(cfg, acts, pre_drop, ctx.seeds, params, g, any_tbl, layer0_hook=hook if (any_tbl and FUSED_DX_SCATTER) else None)
+        use_hook = any_tbl and FUSED_DX_SCATTER
+        if ctx.tower:
+            # dlogit: formed inside the tower kernel from (pred, label, g_loss) unless someone also consumed logit / pred
+            dl_in = None
+            if g is not None or g_pred is not None or pred is None:
+                dl_in = torch.zeros((x.shape[0],), dtype=torch.float32, device=dev)
+                if g is not None:
+                    dl_in += g.reshape(-1)
+                if g_pred is not None:
+                    dl_in += g_pred.reshape(-1) * pred.reshape(-1) * (1.0 - pred.reshape(-1))
+                if g_loss is not None:
+                    dl = torch.empty_like(dl_in)
+                    gl = g_loss.reshape(1).contiguous().float()
+                    check(_lib.load().rpb_sigmoid_bce_bwd(_ptr(pred), _ptr(label), _ptr(gl), 0.0, 1.0, _ptr(dl),
+                                                          x.shape[0], _stream()), 'rpb_sigmoid_bce_bwd')
+                    _count()
+                    dl_in += dl
+            gx, gparams, dlogit = _tower_bwd(cfg, acts, params, dlogit_in=dl_in,
+                                             head=(pred, label, 0.0, 1.0) if dl_in is None else None, gloss=g_loss,
+                                             need_dx_input=any_tbl, layer0_hook=hook if use_hook else None)
+        else:
+            dlogit = g.reshape(-1).contiguous()
+            gx, gparams = _mlp_bwd(cfg, acts, pre_drop, ctx.seeds, params, g, any_tbl,
+                                   layer0_hook=(lambda dh, lddh, W0: hook(dh, lddh, W0, dlogit)) if use_hook else None)
         if gx is not None and any_tbl:                            # hook declined: plain scatter of dx + FM term
             gx = _rowmajor(gx)
-            d = desc(gx)
+            d = desc(dlogit, gx)
             check(_lib.load().rpb_gather_bwd(C.byref(d), _stream()), 'rpb_gather_bwd')
             _count()
         out: List[Optional[torch.Tensor]] = [None] * ctx.n_inputs
@@ -763,8 +927,10 @@ def _gather_fwd_raw(tables, idx, dense, want_fm, need_grad):
 
 
 def deepfm_core(tables, idx, dense, weights, biases, n_hidden, relu, dropout, training, grad_store=None,
-                impl: Optional[int] = None) -> torch.Tensor:
-    """logit [B,1] of DeepFM (FM second order + MLP over [emb | dense]) as one fused autograd node."""
+                impl: Optional[int] = None, label: Optional[torch.Tensor] = None):
+    """logit [B,1] of DeepFM (FM second order + MLP over [emb | dense]) as one fused autograd node.  With `label` ([B]
+    fp32) and a tower-shaped MLP (see _tower_ok) the node also yields sigmoid(logit) and the mean BCE from the same
+    launch that finishes the MLP: returns (logit, pred [B,1], loss) instead of logit."""
     F = len(tables)
     D = int(tables[0].shape[1])
     for t in tables:
@@ -781,8 +947,14 @@ def deepfm_core(tables, idx, dense, weights, biases, n_hidden, relu, dropout, tr
     needs_grad = torch.is_grad_enabled() and (any(t.requires_grad for t in tables) or any(p.requires_grad for p in params))
     cfg = dict(n_hidden=n_hidden, has_out=True, K=F * D + len(dense_l), relu=list(relu), dropout=list(dropout),
                training=training, impl=_GEMM_IMPL if impl is None else impl)
-    gcfg = dict(F=F, Nd=len(dense_l), D=D, needs_grad=needs_grad, grad_store=grad_store)
-    return _DeepFMCore.apply(cfg, gcfg, *tables, *idx_l, *dense_l, *params)
+    tower = _tower_ok(cfg, params)
+    extra = []
+    if label is not None and tower:
+        _cuda(label, 'label')
+        extra = [label.reshape(-1).float().contiguous()]
+    gcfg = dict(F=F, Nd=len(dense_l), D=D, needs_grad=needs_grad, grad_store=grad_store, tower=tower,
+                has_label=bool(extra))
+    return _DeepFMCore.apply(cfg, gcfg, *tables, *idx_l, *dense_l, *params, *extra)
 
 
 def mlp_forward(x: torch.Tensor, K: int, weights: Sequence[torch.Tensor], biases: Sequence[Optional[torch.Tensor]],

@@ -1,0 +1,133 @@
+"""GPU parity tests of the fused MLP tower tail (rpb_tower_tail_fwd / rpb_tower_tail_bwd through the C ABI) against
+the oracle's MLP (oracle/restatement.py::mlp, models/layers/deep.py:62-84) + torch.nn.BCELoss on the CPU."""
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _mlp(K, hidden, seed=0):
+    from rec_pangu_b200.models.layers import MLP
+    torch.manual_seed(seed)
+    m = MLP(input_dim=K, output_dim=1, hidden_units=hidden, hidden_activations='relu', dropout_rates=0).cuda()
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() == 1:
+                p.copy_(torch.randn_like(p) * 0.1)
+    return m
+
+
+@pytest.mark.parametrize('M,K,hidden', [(700, 429, [64, 64, 64]), (64, 32, [64]), (1, 16, [64, 64]),
+                                        (4097, 100, [64, 64, 64, 64, 64]), (333, 429, [64, 64])])
+def test_tower_mlp_matches_oracle(M, K, hidden):
+    """MLP.forward/backward through the tower kernels (dlogit handed in by autograd) vs the CPU oracle."""
+    from rec_pangu_b200 import ops
+    assert ops.TOWER_TAIL == 1
+    m = _mlp(K, hidden)
+    ld = (K + 3) // 4 * 4
+    x = torch.zeros(M, ld, device='cuda')
+    x[:, :K] = torch.randn(M, K, device='cuda')
+    x.requires_grad_(True)
+    n0 = ops.launch_count()
+    out = m(x, K=K)
+    n_fwd = ops.launch_count() - n0
+    assert n_fwd <= 3, f'tower forward should be layer-1 GEMM (+weight split) + ONE tail kernel, saw {n_fwd} launches'
+    w = torch.randn(M, 1, device='cuda')
+    (out * w).sum().backward()
+    sd = {'p.' + k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    xc = x.detach().cpu()[:, :K].clone().requires_grad_(True)
+    ref = oracle.mlp(sd, 'p', xc, len(hidden), 2)
+    (ref * w.cpu()).sum().backward()
+    torch.testing.assert_close(out.cpu(), ref, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(x.grad.cpu()[:, :K], xc.grad, rtol=1e-4, atol=1e-5)
+    assert torch.count_nonzero(x.grad[:, K:]) == 0
+    for k, p in m.named_parameters():
+        r = sd['p.' + k].grad
+        tol = 1e-4 * max(1.0, r.abs().max().item())
+        assert (p.grad.cpu() - r).abs().max().item() <= tol, k
+
+
+def test_tower_equals_layerwise_path():
+    """RPB_TOWER_TAIL=0 (one GEMM / row-dot kernel per layer, 3xTF32) and the fused fp32 tail agree."""
+    from rec_pangu_b200 import ops
+    m = _mlp(429, [64, 64, 64], seed=3)
+    x = torch.zeros(5000, 432, device='cuda')
+    x[:, :429] = torch.randn(5000, 429, device='cuda')
+    res = []
+    for flag in (1, 0):
+        ops.TOWER_TAIL = flag
+        try:
+            xi = x.clone().requires_grad_(True)
+            out = m(xi, K=429)
+            out.sum().backward()
+            res.append((out.detach().clone(), xi.grad.clone(), [p.grad.clone() for p in m.parameters()]))
+            m.zero_grad()
+        finally:
+            ops.TOWER_TAIL = 1
+    torch.testing.assert_close(res[0][0], res[1][0], rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(res[0][1], res[1][1], rtol=1e-4, atol=2e-5)
+    for a, b in zip(res[0][2], res[1][2]):
+        assert (a - b).abs().max().item() <= 1e-4 * max(1.0, b.abs().max().item())
+
+
+@pytest.mark.parametrize('B', [2048, 777])
+def test_deepfm_fused_head_matches_oracle(B):
+    """DeepFM with sigmoid + BCE produced by the tower kernel (label passed into ops.deepfm_core): pred, loss, logit and
+    every gradient vs the oracle; the loss gradient scale comes in through autograd (loss * 0.5)."""
+    from helpers import make_enc, make_batch, assert_close_rel
+    from rec_pangu_b200 import ops
+    from rec_pangu_b200.models.ranking import DeepFM
+    enc = make_enc(26, 13, 500)
+    torch.manual_seed(1029)
+    model = DeepFM(embedding_dim=16, hidden_units=[64, 64, 64], enc_dict=enc)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if 'embedding_layer' in n:
+                p.mul_(0.25)
+            elif p.dim() == 1:
+                p.copy_(torch.randn(p.shape) * 0.05)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.cuda().train()
+    data_cpu = make_batch(enc, B, seed=7)
+    data = {k: v.cuda() for k, v in data_cpu.items()}
+    n0 = ops.launch_count()
+    out = model(data)
+    assert ops.launch_count() - n0 <= 4          # gather, weight split + layer-1 GEMM, tower tail (incl. sigmoid + BCE)
+    (out['loss'] * 0.5).backward()
+    ops.check_index_errors()
+    sdr = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    ref = oracle.deepfm(sdr, enc, data_cpu, hidden_units=(64, 64, 64))
+    (ref['loss'] * 0.5).backward()
+    assert out['pred'].shape == ref['pred'].shape
+    assert (model._last_logit.cpu().double() - ref['logit'].double()).abs().max().item() <= 1e-4
+    torch.testing.assert_close(out['pred'].cpu(), ref['pred'], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(out['loss'].cpu(), ref['loss'], rtol=1e-5, atol=1e-6)
+    for k, p in model.named_parameters():
+        assert p.grad is not None, k
+        assert_close_rel(p.grad, sdr[k].grad, 1e-3, k, outlier_frac=0.02)
+    # the un-fused path (inference head) gives the same probabilities bit for bit
+    with torch.no_grad():
+        out2 = model(data, is_training=False)
+    assert torch.equal(out2['pred'], out['pred'])
+
+
+def test_deepfm_pred_consumer_gets_gradient():
+    """A caller that differentiates `pred` (not only `loss`) still gets the right gradient from the fused node."""
+    from helpers import make_enc, make_batch
+    from rec_pangu_b200.models.ranking import DeepFM
+    enc = make_enc(4, 2, 50)
+    torch.manual_seed(5)
+    model = DeepFM(embedding_dim=8, hidden_units=[64, 64], enc_dict=enc)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.cuda().train()
+    data_cpu = make_batch(enc, 300, seed=3)
+    out = model({k: v.cuda() for k, v in data_cpu.items()})
+    (out['loss'] + out['pred'].sum() * 0.01).backward()
+    sdr = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    ref = oracle.deepfm(sdr, enc, data_cpu, hidden_units=(64, 64))
+    (ref['loss'] + ref['pred'].sum() * 0.01).backward()
+    for k, p in model.named_parameters():
+        r = sdr[k].grad
+        assert (p.grad.cpu() - r).abs().max().item() <= 1e-4 * max(1.0, r.abs().max().item()), k
