@@ -176,6 +176,13 @@ typedef struct RpbTowerFwdDesc {
     void* work;
 } RpbTowerFwdDesc;
 int rpb_tower_tail_fwd(const RpbTowerFwdDesc* d, void* stream);
+/* The first layer and the tail in ONE launch: h1 = relu(x[M,K] @ W1[64,K]^T + b1) on the persistent tcgen05 GEMM
+ * (3xTF32), whose epilogue warps then run rpb_tower_tail_fwd's tile routine on every finished 128-sample tile while
+ * the tensor pipe works on the next ones — h1 goes to HBM once (d->h1, an OUTPUT here, saved for backward) and is never
+ * read back.  Needs n_tail >= 1 and M >= 512; returns RPB_ERR_UNSUPPORTED otherwise (the caller then launches
+ * rpb_linear_fwd + rpb_tower_tail_fwd). */
+int rpb_linear_tower_fwd(const float* x, int64_t ldx, const float* W1, const float* b1, int K,
+                         const RpbTowerFwdDesc* d, void* stream);
 /* Backward of rpb_tower_tail_fwd.  hin: HOST array of n_tail+1 device pointers, hin[0] = h1 (row stride ldh1),
  * hin[j] = h[j-1] ([M, H] contiguous).  dlogit[m] = dlogit_in[m] when given, else gloss[0]*scale/M * dBCE/dp * p(1-p)
  * from (pred, label) with ATen's clamps (gloss NULL = 1); it is written to dlogit_out when non-NULL.

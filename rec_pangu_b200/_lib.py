@@ -73,6 +73,7 @@ SIGNATURES = {
     'rpb_sigmoid_bce_fwd': (C.c_int, [_vp, _vp, _vp, _vp, _f32, _f32, C.c_int, _vp, _vp]),
     'rpb_sigmoid_bce_bwd': (C.c_int, [_vp, _vp, _vp, _f32, _f32, _vp, C.c_int, _vp]),
     'rpb_tower_tail_fwd': (C.c_int, [C.POINTER(TowerFwdDesc), _vp]),
+    'rpb_linear_tower_fwd': (C.c_int, [_vp, _i64, _vp, _vp, C.c_int, C.POINTER(TowerFwdDesc), _vp]),
     'rpb_tower_tail_bwd': (C.c_int, [C.POINTER(TowerBwdDesc), _vp]),
     'rpb_dropout_fwd': (C.c_int, [_vp, _vp, _i64, _f32, C.c_uint64, _vp]),
     'rpb_dropout_bwd': (C.c_int, [_vp, _vp, _vp, _i64, _f32, C.c_uint64, _vp]),

@@ -40,6 +40,8 @@ struct TcScatter {
     int F, D, enabled;
 };
 
+struct TowerFwdParams;   // tower_tile.cuh
+
 // epilogue descriptor of the tcgen05 GEMM (linear_tc.cu)
 struct TcEpilogue {
     float* C; long long ldc;
@@ -48,6 +50,9 @@ struct TcEpilogue {
     int M, N;            // valid extents
     int relu;
     const TcScatter* sc; // host pointer (copied into the kernel parameter when enabled), else null
+    // host pointer or null: run the rest of the MLP tower (tower_tile.cuh) on every finished 64-wide tile from the epilogue
+    // warps; C then receives h1 as usual and the tail's outputs (h[l], logit, pred, loss) come from the same launch
+    const TowerFwdParams* tail;
 };
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -15,6 +15,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "tower_tile.cuh"
 
 namespace rpb {
 
@@ -122,7 +123,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                    uint32_t tmem_cols) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment is required by SWIZZLE_128B; the dynamic smem base is only guaranteed 16 B
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the pointer in the shared address space (LDS/STS, not generic LD/ST)
     const int b_bytes = block_n * TC_BLOCK_K * 4;
     const int stage_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * stage_bytes);
@@ -330,9 +331,9 @@ __global__ void __launch_bounds__(V2_THREADS, 1)
 gemm_tf32x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                       const __grid_constant__ CUtensorMap tmBlo, const TcEpilogue ep, int block_n, int num_k_blocks,
                       int m_tiles, int n_tiles, uint32_t tmem_cols, int b_resident, int a_stages, int stack_n,
-                      const __grid_constant__ TcScatter sc) {
+                      const __grid_constant__ TcScatter sc, const __grid_constant__ TowerFwdParams tw) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the pointer in the shared address space (LDS/STS, not generic LD/ST)
     const int b_bytes = block_n * TC_BLOCK_K * 4;
     // b_resident (n_tiles == 1 and the whole pre-split weight fits): B hi/lo of every k-block is loaded ONCE per CTA
     // and stays in shared memory for all of its tiles; the raw ring then carries only A and is released by the split
@@ -357,6 +358,11 @@ gemm_tf32x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
     uint64_t* b_full = tmem_empty + 2;             // [1]     resident B landed
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_full + 1);
+    // fused tower tail (tw.enabled): [As: 128 x TW_LDA | Bs: n_tail x 64 x 64 | loss partials: 256] floats after the barriers
+    // (`bars` is 1024-byte aligned: every region before it is a multiple of 1 KiB; 2*kRaw + 13 barrier slots + the TMEM address)
+    float* tw_As = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + (((2 * kRaw + 2 * V2_MAX_OP + 5) * 8 + 4 + 15) & ~15));
+    float* tw_Bs = tw_As + TC_BLOCK_M * TW_LDA;
+    float* tw_loss = tw_Bs + tw.n_tail * TW_H * TW_H;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = m_tiles * n_tiles;
@@ -536,11 +542,58 @@ gemm_tf32x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const int row = quarter * 32 + lane;
         const bool c_vec = ((ep.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.C) & 15u) == 0);
         const bool m_vec = ep.mask != nullptr && ((ep.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.mask) & 15u) == 0);
+        // ---- fused tower tail: the 8 epilogue warps are one 256-thread team (named barrier 1) that owns tw_As / tw_Bs
+        const int et = threadIdx.x - 6 * 32;
+        auto epi_sync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+        float4 tw_wo = make_float4(0.f, 0.f, 0.f, 0.f);
+        float tw_bo = 0.f, tw_loss_acc = 0.f;
+        if (tw.enabled) {
+            tower_load_weights_t<V2_EPI_WARPS * 32>(tw, tw_Bs, et);
+            tw_wo = ldg_f4(tw.w_out + (et & 15) * 4);
+            tw_bo = tw.b_out != nullptr ? __ldg(tw.b_out) : 0.f;
+        }
         uint32_t t = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
             const int m0 = (tile / n_tiles) * TC_BLOCK_M, n0 = (tile % n_tiles) * block_n;
             const uint32_t acc = t & 1u;
             const int m = m0 + row;
+            if (tw.enabled) {
+                // layer-1 epilogue (stacked accumulator: a.b_hi + a.b_lo, bias, ReLU) -> h1 to HBM and into tw_As, then
+                // the accumulator is handed back and the tail layers / head run on CUDA cores while the tensor pipe is
+                // already busy with the next tiles (host guarantees block_n == 64, stack_n, bias, relu)
+                const long long q0 = TC_TRACE_T();
+                mbar_wait(&tmem_full[acc], (t >> 1) & 1u);
+                tc_fence_after();
+                const long long q1 = TC_TRACE_T();
+                epi_sync();                            // previous tile's activations fully consumed (weights visible)
+                for (int c0 = half * 16; c0 < TW_H; c0 += 32) {
+                    uint32_t r[16], r2[16];
+                    tmem_ld16(tmem_base + acc * acc_stride + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+                    tmem_ld16(tmem_base + acc * acc_stride + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(TW_H + c0), r2);
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        v[j] = fmaxf(__uint_as_float(r2[j]) + __uint_as_float(r[j]) + __ldg(ep.bias + c0 + j), 0.f);
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 q4 = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        if (m < ep.M) stg_f4(ep.C + (size_t)m * ep.ldc + c0 + j, q4);
+                        *reinterpret_cast<float4*>(tw_As + row * TW_LDA + c0 + j) = q4;
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                epi_sync();
+                const long long q2 = TC_TRACE_T();
+                tower_tail_tile_fwd<V2_EPI_WARPS * 32>(tw, tw_As, tw_Bs, m0, et, tw_wo, tw_bo, tw_loss_acc, epi_sync);
+                if (trace && warp == 6 && lane == 0) {
+                    g_tc_trace[8] += (unsigned long long)(q1 - q0);           // waiting for the accumulator
+                    g_tc_trace[9] += (unsigned long long)(q2 - q1);           // layer-1 epilogue (TMEM -> HBM + smem)
+                    g_tc_trace[11] += (unsigned long long)(TC_TRACE_T() - q2); // tail layers + head
+                }
+                continue;
+            }
             if (sc.enabled) {
                 // ---- fused scatter-add of the table gradients (see TcScatter).
                 // TMEM hands each lane 16 consecutive columns of ITS row; a 4x4 float4 transpose inside every group of
@@ -663,10 +716,36 @@ gemm_tf32x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 g_tc_trace[9] += (unsigned long long)(TC_TRACE_T() - e1);
             }
         }
+        if (tw.enabled && tw.loss != nullptr) tw_loss[et] = tw_loss_acc;
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+    if (tw.enabled && tw.loss != nullptr && warp == 0) {
+        // deterministic mean BCE: fixed-order sum of the 256 epilogue partials -> per-CTA partial -> the last CTA to
+        // finish adds the per-CTA partials in index order (same scheme as head.cu / tower.cu)
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < V2_EPI_WARPS; ++i) s += tw_loss[lane + 32 * i];
+        s = warp_sum(s);
+        unsigned int last = 0;
+        if (lane == 0) {
+            tw.partials[blockIdx.x] = s;
+            __threadfence();
+            last = (atomicAdd(tw.counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            __threadfence();
+            float tot = 0.f;
+            for (int i = lane; i < (int)gridDim.x; i += 32) tot += ((volatile float*)tw.partials)[i];
+            tot = warp_sum(tot);
+            if (lane == 0) {
+                tw.loss[0] = tw.scale * (tot / (float)tw.M);
+                *tw.counter = 0u;
+            }
+        }
+    }
     if (trace && threadIdx.x == 0) g_tc_trace[0] = (unsigned long long)(clock64() - t_start);
 }
 
@@ -699,7 +778,7 @@ __global__ void __launch_bounds__(TC_THREADS)
 wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDy,
                     float* __restrict__ dW, int N, int K, int M, int block_n, int slab, uint32_t tmem_cols, int stack_n, int raw_hi) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the pointer in the shared address space (LDS/STS, not generic LD/ST)
     const int a_bytes = 4 * WG_BOX_BYTES;                    // 128 k-columns = 4 chunks
     const int b_chunks = block_n / 32;
     const int b_bytes = b_chunks * WG_BOX_BYTES;
@@ -957,25 +1036,36 @@ int gemm_tc(const float* A, long long lda, const float* Bsrc, long long ldb, int
         if (g_gemm_a_tmem && ep.sc == nullptr && acc_cols + 2 * 64 <= 512) a_stages = min(V2_MAX_OP, (512 - acc_cols) / 64);
         const int op_bytes = a_stages > 0 ? 0 : V2_OP_STAGES * 2 * TC_A_BYTES;
         const int bres_bytes = nkb * 2 * b_bytes;
-        const int b_resident = (n_tiles == 1 && bres_bytes <= 72 * 1024) ? 1 : 0;
-        const int raw_bytes = b_resident ? TC_A_BYTES : TC_A_BYTES + 2 * b_bytes;
+        const int raw_bytes_nores = TC_A_BYTES + 2 * b_bytes;
+        // fused tower tail: needs the stacked TS-mode accumulator of a single 64-wide tile with bias + ReLU
+        const bool tail = ep.tail != nullptr;
+        if (tail && !(stack_n && a_stages > 0 && n_tiles == 1 && block_n == TW_H && N == TW_H && ep.relu && ep.bias != nullptr &&
+                      ep.C != nullptr && ep.mask == nullptr && (ep.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.C) & 15u) == 0))
+            return RPB_ERR_UNSUPPORTED;
+        const int tail_bytes = tail ? (TC_BLOCK_M * TW_LDA + ep.tail->n_tail * TW_H * TW_H + 256) * 4 + 64 : 0;
+        const int b_resident = (n_tiles == 1 && bres_bytes <= 72 * 1024 &&
+                                (!tail || 226 * 1024 - bres_bytes - 1280 - tail_bytes >= 3 * TC_A_BYTES)) ? 1 : 0;
+        const int raw_bytes = b_resident ? TC_A_BYTES : raw_bytes_nores;
         uint32_t tmem_cols = 32;
         while ((int)tmem_cols < (a_stages > 0 ? acc_cols + 64 * a_stages : 2 * block_n)) tmem_cols <<= 1;
         const int m_tiles = ceil_div(M, TC_BLOCK_M);
-        const int budget = 226 * 1024 - op_bytes - (b_resident ? bres_bytes : 0) - 1024 - 256;
+        const int budget = 226 * 1024 - op_bytes - (b_resident ? bres_bytes : 0) - 1024 - 256 - tail_bytes;
         const int max_raw = budget / raw_bytes;
+        if (tail && (tmem_cols > 512 || max_raw < 2)) return RPB_ERR_UNSUPPORTED;
         if (tmem_cols <= 512 && max_raw >= 2) {
             const int grid = min(m_tiles * n_tiles, 148);
             auto launch = [&](auto raw_tag) -> int {
                 constexpr int R = decltype(raw_tag)::value;
                 const size_t smem = (size_t)R * raw_bytes + op_bytes + (b_resident ? bres_bytes : 0) +
-                                    (2 * R + 2 * V2_MAX_OP + 4 + 2) * 8 + 1024;
+                                    (2 * R + 2 * V2_MAX_OP + 4 + 2) * 8 + 1024 + tail_bytes;
                 cudaError_t ee = cudaFuncSetAttribute(gemm_tf32x3_v2_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (ee != cudaSuccess) return (int)ee;
                 static const TcScatter no_scatter{};
+                static const TowerFwdParams no_tail{};
                 gemm_tf32x3_v2_kernel<R><<<grid, V2_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, ep, block_n, nkb, m_tiles, n_tiles,
                                                                         tmem_cols, b_resident, a_stages, stack_n,
-                                                                        ep.sc != nullptr ? *ep.sc : no_scatter);
+                                                                        ep.sc != nullptr ? *ep.sc : no_scatter,
+                                                                        tail ? *ep.tail : no_tail);
                 return (int)cudaGetLastError();
             };
             if (max_raw >= 6) return launch(std::integral_constant<int, 6>{});
@@ -985,7 +1075,7 @@ int gemm_tc(const float* A, long long lda, const float* Bsrc, long long ldb, int
             return launch(std::integral_constant<int, 2>{});
         }
     }
-    if (rc == 0 && ep.sc != nullptr) return RPB_ERR_UNSUPPORTED;       // the fused scatter epilogue exists in the v2 kernel only
+    if (rc == 0 && (ep.sc != nullptr || ep.tail != nullptr)) return RPB_ERR_UNSUPPORTED;   // fused epilogues exist in the v2 kernel only
     if (rc == 0) {
         const int b_bytes = block_n * TC_BLOCK_K * 4;
         const int stage_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
@@ -1111,6 +1201,18 @@ RPB_API int rpb_linear_bwd(const float* dy, int64_t lddy, const float* x, int64_
         if (rc != 0) return rc;
     }
     return 0;
+}
+
+// Layer-1 GEMM fused with the rest of the tower (see TcEpilogue::tail): one launch from the feature row to the loss.
+RPB_API int rpb_linear_tower_fwd(const float* x, int64_t ldx, const float* W1, const float* b1, int K,
+                                 const RpbTowerFwdDesc* d, void* stream) {
+    if (x == nullptr || W1 == nullptr || b1 == nullptr || d == nullptr || K <= 0) return RPB_ERR_BAD_ARG;
+    TowerFwdParams p{};
+    const int prc = tower_fwd_params(d, &p);
+    if (prc != 0) return prc;
+    if (d->n_tail < 1 || d->M < 512 || !g_gemm_v2 || !tc_shape_ok(x, ldx, d->M, TW_H, K)) return RPB_ERR_UNSUPPORTED;
+    TcEpilogue ep{const_cast<float*>(d->h1), d->ldh1, b1, nullptr, 0, d->M, TW_H, 1, nullptr, &p};
+    return gemm_tc(x, ldx, W1, K, 0, ep, d->M, TW_H, K, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // dx GEMM of the first MLP layer fused with the embedding-gradient scatter (TcScatter): dx is never written.

@@ -13,26 +13,12 @@
 // Backward is the mirror image: dlogit from (pred, label) -> masked outer product with w_out -> per layer
 // dz_{l-1} = (dz_l . W_l) * (h_{l-1} > 0), with the bias gradients (column sums), dw_out and db_out accumulated on
 // the way; the dz tiles are written for the weight-gradient kernels and for the layer-1 dx + scatter GEMM.
-#include "common.cuh"
+#include "tower_tile.cuh"
 
 namespace rpb {
 
-constexpr int TW_H = 64;                 // hidden width this kernel is built for
-constexpr int TW_ROWS = 64;              // samples per tile
+constexpr int TW_ROWS = 64;              // samples per tile of the standalone kernels
 constexpr int TW_THREADS = 128;          // 8 row groups x 16 column groups
-constexpr int TW_LDA = TW_H + 4;         // padded activation row: conflict-free float4 rows
-constexpr int TW_MAX_TAIL = RPB_TOWER_MAX_TAIL;
-constexpr int TW_MAX_GRID = 2048;        // loss partials live in the caller's work buffer (2048 floats)
-
-struct TowerFwdParams {
-    const float* h1; long long ldh1;
-    const float* W[TW_MAX_TAIL]; const float* b[TW_MAX_TAIL];
-    float* h[TW_MAX_TAIL];
-    const float* w_out; const float* b_out; const float* addend;
-    float* logit; const float* label; float* pred; float* loss;
-    float eps, scale; unsigned int* counter; float* partials;
-    int M, n_tail;
-};
 
 struct TowerBwdParams {
     const float* hin[TW_MAX_TAIL + 1]; long long ldh1;       // hin[0] = h1 (row stride ldh1), hin[j>0] row stride 64
@@ -44,30 +30,6 @@ struct TowerBwdParams {
     int M, n_tail;
 };
 
-// acc[i][c] += sum_k As[ty + 8 i][k] * Bs[k][tx * 4 + c]     (As row stride TW_LDA, Bs row stride TW_H)
-__device__ __forceinline__ void tile_fma(const float* __restrict__ As, const float* __restrict__ Bs, int ty, int tx,
-                                         float (&acc)[8][4]) {
-#pragma unroll 4
-    for (int k0 = 0; k0 < TW_H; k0 += 4) {
-        float4 a[8], b[4];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(As + (ty + 8 * i) * TW_LDA + k0);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float4*>(Bs + (k0 + j) * TW_H + tx * 4);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float av[4] = {a[i].x, a[i].y, a[i].z, a[i].w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                acc[i][0] = fmaf(av[j], b[j].x, acc[i][0]);
-                acc[i][1] = fmaf(av[j], b[j].y, acc[i][1]);
-                acc[i][2] = fmaf(av[j], b[j].z, acc[i][2]);
-                acc[i][3] = fmaf(av[j], b[j].w, acc[i][3]);
-            }
-        }
-    }
-}
-
 __global__ void __launch_bounds__(TW_THREADS, 4)
 tower_tail_fwd_kernel(const TowerFwdParams p) {
     extern __shared__ __align__(16) float tw_smem[];
@@ -75,17 +37,9 @@ tower_tail_fwd_kernel(const TowerFwdParams p) {
     float* Bs = tw_smem + TW_ROWS * TW_LDA;           // [n_tail][k][n] = W_l[n][k]
     __shared__ float red[32];
     __shared__ bool is_last;
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int tid = threadIdx.x, tx = tid & 15;
 
-    // transposed weight load: consecutive lanes take consecutive output rows n, so the four scalar stores of a float4
-    // (k..k+3 of row n) land in consecutive banks (the naive "coalesced read, strided store" is a 32-way bank conflict)
-    for (int l = 0; l < p.n_tail; ++l)
-        for (int i = tid; i < TW_H * TW_H / 4; i += TW_THREADS) {
-            const int n = i & 63, k4 = i >> 6;
-            const float4 v = ldg_f4(p.W[l] + n * TW_H + k4 * 4);
-            float* dst = Bs + l * TW_H * TW_H + (k4 * 4) * TW_H + n;
-            dst[0] = v.x; dst[TW_H] = v.y; dst[2 * TW_H] = v.z; dst[3 * TW_H] = v.w;
-        }
+    tower_load_weights_t<TW_THREADS>(p, Bs, tid);
     const float4 wo = ldg_f4(p.w_out + tx * 4);
     const float bo = p.b_out != nullptr ? __ldg(p.b_out) : 0.f;
     float loss_acc = 0.f;
@@ -102,57 +56,7 @@ tower_tail_fwd_kernel(const TowerFwdParams p) {
             *reinterpret_cast<float4*>(As + r * TW_LDA + c4 * 4) = v;
         }
         __syncthreads();
-        for (int l = 0; l < p.n_tail; ++l) {
-            float acc[8][4];
-            const float4 bv = ldg_f4(p.b[l] + tx * 4);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { acc[i][0] = bv.x; acc[i][1] = bv.y; acc[i][2] = bv.z; acc[i][3] = bv.w; }
-            tile_fma(As, Bs + l * TW_H * TW_H, ty, tx, acc);
-            __syncthreads();                          // every thread has finished reading the layer input
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 v = make_float4(fmaxf(acc[i][0], 0.f), fmaxf(acc[i][1], 0.f), fmaxf(acc[i][2], 0.f),
-                                             fmaxf(acc[i][3], 0.f));
-                const int r = ty + 8 * i;
-                if (m0 + r < p.M) stg_f4(p.h[l] + (size_t)(m0 + r) * TW_H + tx * 4, v);
-                *reinterpret_cast<float4*>(As + r * TW_LDA + tx * 4) = v;
-            }
-            __syncthreads();
-        }
-        // head: logit = h_last . w_out + b_out (+ addend); 16 lanes share a row
-        float part[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float4 v = *reinterpret_cast<const float4*>(As + (ty + 8 * i) * TW_LDA + tx * 4);
-            part[i] = fmaf(v.x, wo.x, fmaf(v.y, wo.y, fmaf(v.z, wo.z, v.w * wo.w)));
-        }
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) part[i] += __shfl_xor_sync(0xffffffffu, part[i], o);
-        }
-        if (tx == 0) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int m = m0 + ty + 8 * i;
-                if (m < p.M) {
-                    float z = part[i] + bo;
-                    if (p.addend != nullptr) z += __ldg(p.addend + m);
-                    p.logit[m] = z;
-                    if (p.pred != nullptr) {
-                        const float q = 1.f / (1.f + expf(-z));
-                        p.pred[m] = q;
-                        if (p.label != nullptr) {
-                            const float y = __ldg(p.label + m);
-                            const float pe = q + p.eps;
-                            const float l1 = fmaxf(logf(pe), -100.f);
-                            const float l0 = fmaxf(logf(1.f - pe), -100.f);
-                            loss_acc += -(y * l1 + (1.f - y) * l0);
-                        }
-                    }
-                }
-            }
-        }
+        tower_tail_tile_fwd<TW_THREADS>(p, As, Bs, m0, tid, wo, bo, loss_acc, [] { __syncthreads(); });
     }
     if (p.loss == nullptr) return;
     // deterministic mean: per-CTA partial, the last CTA to finish adds them in index order (same as head.cu)
@@ -254,7 +158,7 @@ tower_tail_bwd_kernel(const TowerBwdParams p) {
             float acc[8][4];
 #pragma unroll
             for (int i = 0; i < 8; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; acc[i][2] = 0.f; acc[i][3] = 0.f; }
-            tile_fma(As, Bs + j * TW_H * TW_H, ty, tx, acc);
+            tile_fma<TW_THREADS / 16>(As, Bs + j * TW_H * TW_H, ty, tx, acc);
             __syncthreads();                          // dz_{j+1} fully consumed
             const float* hj = p.hin[j];
             const long long ld = j == 0 ? p.ldh1 : (long long)TW_H;
@@ -294,11 +198,23 @@ tower_tail_bwd_kernel(const TowerBwdParams p) {
 
 static bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
 
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+        n = min(n, TW_MAX_GRID / 4);
+    }
+    return n;
+}
+
 }  // namespace rpb
 
 using namespace rpb;
 
-RPB_API int rpb_tower_tail_fwd(const RpbTowerFwdDesc* d, void* stream) {
+namespace rpb {
+int tower_fwd_params(const RpbTowerFwdDesc* d, TowerFwdParams* out) {
     if (d == nullptr || d->M <= 0 || d->h1 == nullptr || d->w_out == nullptr || d->logit == nullptr) return RPB_ERR_BAD_ARG;
     if (d->H != TW_H || d->n_tail < 0 || d->n_tail > TW_MAX_TAIL || (d->ldh1 % 4) != 0 || !aligned16(d->h1) || !aligned16(d->w_out))
         return RPB_ERR_UNSUPPORTED;
@@ -316,14 +232,24 @@ RPB_API int rpb_tower_tail_fwd(const RpbTowerFwdDesc* d, void* stream) {
     p.eps = d->eps; p.scale = d->scale;
     p.counter = reinterpret_cast<unsigned int*>(d->work);
     p.partials = reinterpret_cast<float*>(d->work) + 2;
-    p.M = d->M; p.n_tail = d->n_tail;
+    p.M = d->M; p.n_tail = d->n_tail; p.enabled = 1;
+    *out = p;
+    return 0;
+}
+}  // namespace rpb
+
+RPB_API int rpb_tower_tail_fwd(const RpbTowerFwdDesc* d, void* stream) {
+    TowerFwdParams p{};
+    const int rc = tower_fwd_params(d, &p);
+    if (rc != 0) return rc;
     const size_t smem = (size_t)(TW_ROWS * TW_LDA + d->n_tail * TW_H * TW_H) * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(tower_tail_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)      // 4 CTAs x ~50 KiB per SM only fit with the L1/shared split at its shared-memory maximum
         e = cudaFuncSetAttribute(tower_tail_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
     const int tiles = ceil_div(d->M, TW_ROWS);
-    tower_tail_fwd_kernel<<<min(tiles, TW_MAX_GRID), TW_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    // persistent: 4 CTAs per SM walk the tile list, so the transposed weight load is paid once per CTA
+    tower_tail_fwd_kernel<<<min(tiles, 4 * sm_count()), TW_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     RPB_LAUNCH_CHECK();
     return 0;
 }
@@ -356,7 +282,7 @@ RPB_API int rpb_tower_tail_bwd(const RpbTowerBwdDesc* d, void* stream) {
         e = cudaFuncSetAttribute(tower_tail_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
     const int tiles = ceil_div(d->M, TW_ROWS);
-    tower_tail_bwd_kernel<<<min(tiles, TW_MAX_GRID), TW_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    tower_tail_bwd_kernel<<<min(tiles, 4 * sm_count()), TW_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     RPB_LAUNCH_CHECK();
     return 0;
 }

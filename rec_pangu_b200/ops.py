@@ -22,6 +22,8 @@ FUSED_DX_SCATTER = int(__import__('os').environ.get('RPB_DX_SCATTER', '1'))
 # MLP tower tail (rpb_tower_tail_fwd/bwd): 1 = every 64-wide hidden layer after the first, the Linear(64->1) output, the
 # logit sum and (DeepFM) sigmoid + BCE run as ONE fp32 kernel per direction; 0 = one GEMM / row-dot / head kernel each.
 TOWER_TAIL = int(__import__('os').environ.get('RPB_TOWER_TAIL', '1'))
+# 1 = the tail runs inside the epilogue of the layer-1 tcgen05 GEMM (rpb_linear_tower_fwd), 0 = as its own kernel
+FUSED_TOWER_EPILOGUE = int(__import__('os').environ.get('RPB_TOWER_EPILOGUE', '1'))
 _LAUNCHES = 0           # number of librec_pangu_b200 kernels launched (bench.py reports it as gpu_launches)
 
 
@@ -647,9 +649,6 @@ def _tower_fwd(cfg, x, params, addend=None, head=None):
     st = _stream()
     M, dev = x.shape[0], x.device
     y1 = torch.empty((M, 64), dtype=torch.float32, device=dev)
-    check(lib.rpb_linear_fwd(_ptr(x), x.stride(0), _ptr(params[0]), _ptr(params[1]), _ptr(y1), 64, M, 64, K, 1, impl, st),
-          'rpb_linear_fwd')
-    _count(2 if impl != 1 else 1)
     n_tail = n_hidden - 1
     hs = [torch.empty((M, 64), dtype=torch.float32, device=dev) for _ in range(n_tail)]
     logit = torch.empty((M, 1), dtype=torch.float32, device=dev)
@@ -672,8 +671,19 @@ def _tower_fwd(cfg, x, params, addend=None, head=None):
         d.label, d.pred, d.loss = label.data_ptr(), pred.data_ptr(), loss.data_ptr()
         d.eps, d.scale = eps, scale
         d.work = _head_work(dev).data_ptr()
-    check(lib.rpb_tower_tail_fwd(C.byref(d), st), 'rpb_tower_tail_fwd')
-    _count()
+    # one launch from the feature row to the loss when the layer-1 GEMM can host the tail in its epilogue
+    rc = _lib.ERR_UNSUPPORTED
+    if FUSED_TOWER_EPILOGUE and impl != 1:
+        rc = lib.rpb_linear_tower_fwd(_ptr(x), x.stride(0), _ptr(params[0]), _ptr(params[1]), K, C.byref(d), st)
+        if rc != _lib.ERR_UNSUPPORTED:
+            check(rc, 'rpb_linear_tower_fwd')
+            _count(2)
+    if rc == _lib.ERR_UNSUPPORTED:
+        check(lib.rpb_linear_fwd(_ptr(x), x.stride(0), _ptr(params[0]), _ptr(params[1]), _ptr(y1), 64, M, 64, K, 1, impl, st),
+              'rpb_linear_fwd')
+        _count(2 if impl != 1 else 1)
+        check(lib.rpb_tower_tail_fwd(C.byref(d), st), 'rpb_tower_tail_fwd')
+        _count()
     del keep
     return logit, [x, y1] + hs, pred, loss
 

@@ -131,3 +131,40 @@ def test_deepfm_pred_consumer_gets_gradient():
     for k, p in model.named_parameters():
         r = sdr[k].grad
         assert (p.grad.cpu() - r).abs().max().item() <= 1e-4 * max(1.0, r.abs().max().item()), k
+
+
+@pytest.mark.parametrize('M,K,hidden', [(5000, 429, [64, 64, 64]), (37893, 429, [64, 64, 64]), (512, 40, [64, 64]),
+                                        (20000, 429, [64, 64, 64, 64, 64])])
+def test_tower_in_gemm_epilogue_equals_standalone_tail(M, K, hidden):
+    """rpb_linear_tower_fwd (tail run by the epilogue warps of the layer-1 tcgen05 GEMM) vs rpb_linear_fwd +
+    rpb_tower_tail_fwd: same arithmetic per element, so activations, logit, pred and loss agree bit for bit."""
+    from rec_pangu_b200 import ops
+    m = _mlp(K, hidden, seed=11)
+    Ws, bs, relu, drops = m.layer_params()
+    params = []
+    for W, b in zip(Ws, bs):
+        params += [W.detach(), b.detach()]
+    ld = (K + 3) // 4 * 4
+    x = torch.zeros(M, ld, device='cuda')
+    x[:, :K] = torch.randn(M, K, device='cuda')
+    addend = torch.randn(M, device='cuda')
+    label = (torch.rand(M, device='cuda') < 0.3).float()
+    cfg = dict(n_hidden=len(hidden), has_out=True, K=K, relu=relu, dropout=drops, training=False, impl=0)
+    res = []
+    for flag in (1, 0):
+        ops.FUSED_TOWER_EPILOGUE = flag
+        try:
+            n0 = ops.launch_count()
+            logit, acts, pred, loss = ops._tower_fwd(cfg, x, params, addend=addend, head=(label, 0.0, 1.0))
+            res.append((logit, acts, pred, loss, ops.launch_count() - n0))
+        finally:
+            ops.FUSED_TOWER_EPILOGUE = 1
+    torch.cuda.synchronize()
+    assert res[0][4] == 2 and res[1][4] == 3          # (weight split + fused GEMM) vs (split + GEMM + tail kernel)
+    assert torch.equal(res[0][0], res[1][0])
+    for a, b in zip(res[0][1], res[1][1]):
+        assert torch.equal(a, b)
+    assert torch.equal(res[0][2], res[1][2])
+    torch.testing.assert_close(res[0][3], res[1][3], rtol=1e-6, atol=1e-7)     # loss: different partial-sum grouping
+    ref = torch.nn.functional.binary_cross_entropy(torch.sigmoid(res[0][0].double().squeeze(1)), label.double())
+    torch.testing.assert_close(res[0][3].double(), ref, rtol=1e-5, atol=1e-6)
