@@ -295,6 +295,18 @@ int rpb_fibinet_bwd(const float* x, int64_t ldx, int B, int F, int D, const floa
  * (torch.optim.SparseAdam semantics; the reference's dense Adam would keep moving them by momentum). */
 int rpb_adam_dense(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                    float eps, int step, void* stream);
+/* The same update for up to RPB_ADAM_MAX_TENSORS dense parameters in ONE launch (host arrays of `count` device
+ * pointers / element counts).  step_dev: optional DEVICE int32 holding the step number; when non-NULL it overrides
+ * `step`, so a training step captured into a CUDA graph keeps the right bias correction across replays. */
+#define RPB_ADAM_MAX_TENSORS 32
+typedef struct RpbAdamMultiDesc {
+    int32_t count, step;
+    float lr, beta1, beta2, eps;
+    float* const* params; const float* const* grads; float* const* exp_avg; float* const* exp_avg_sq;
+    const int64_t* numel;
+    const int32_t* step_dev;
+} RpbAdamMultiDesc;
+int rpb_adam_multi(const RpbAdamMultiDesc* d, void* stream);
 typedef struct RpbSparseAdamDesc {
     int32_t B, F, D, step;          /* step >= 1: global optimizer step (bias correction) */
     float lr, beta1, beta2, eps;
@@ -305,6 +317,7 @@ typedef struct RpbSparseAdamDesc {
     int32_t* const* stamps;         /* int32[rows[f]], zero-initialised once */
     const int64_t* rows;
     const int64_t* const* idx;      /* int64[B] per field: the batch whose backward filled `grads` */
+    const int32_t* step_dev;        /* optional DEVICE int32 step number (overrides `step`; see rpb_adam_multi) */
 } RpbSparseAdamDesc;
 int rpb_sparse_adam(const RpbSparseAdamDesc* d, void* stream);
 

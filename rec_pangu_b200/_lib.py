@@ -7,10 +7,11 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'librec_pangu_b200.so')
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_FIELDS = 64
 MAX_DENSE = 64
 ERR_UNSUPPORTED = -1
+ADAM_MAX_TENSORS = 32
 
 _vp = C.c_void_p
 _i32 = C.c_int32
@@ -36,7 +37,13 @@ class SparseAdamDesc(C.Structure):
     _fields_ = [('B', _i32), ('F', _i32), ('D', _i32), ('step', _i32), ('lr', _f32), ('beta1', _f32), ('beta2', _f32),
                 ('eps', _f32), ('weights', C.POINTER(_vp)), ('grads', C.POINTER(_vp)), ('exp_avg', C.POINTER(_vp)),
                 ('exp_avg_sq', C.POINTER(_vp)), ('stamps', C.POINTER(_vp)), ('rows', C.POINTER(_i64)),
-                ('idx', C.POINTER(_vp))]
+                ('idx', C.POINTER(_vp)), ('step_dev', _vp)]
+
+
+class AdamMultiDesc(C.Structure):
+    _fields_ = [('count', _i32), ('step', _i32), ('lr', _f32), ('beta1', _f32), ('beta2', _f32), ('eps', _f32),
+                ('params', C.POINTER(_vp)), ('grads', C.POINTER(_vp)), ('exp_avg', C.POINTER(_vp)),
+                ('exp_avg_sq', C.POINTER(_vp)), ('numel', C.POINTER(_i64)), ('step_dev', _vp)]
 
 
 class TowerFwdDesc(C.Structure):
@@ -96,6 +103,7 @@ SIGNATURES = {
     'rpb_fibinet_bwd': (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _i64, _vp, _i64,
                                   _vp, _vp, _vp, _vp]),
     'rpb_adam_dense': (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, C.c_int, _vp]),
+    'rpb_adam_multi': (C.c_int, [C.POINTER(AdamMultiDesc), _vp]),
     'rpb_sparse_adam': (C.c_int, [C.POINTER(SparseAdamDesc), _vp]),
     'rpb_autoint_attn_fwd': (C.c_int, [_vp, _i64, _vp, _i64, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     'rpb_autoint_attn_bwd': (C.c_int, [_vp, _i64, C.c_int, _vp, _vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),

@@ -1136,7 +1136,7 @@ int wgrad_tc(const float* dy, long long lddy, const float* x, long long ldx, flo
         wgrad_tf32x3_kernel<S><<<dim3(ktiles, slabs), TC_THREADS, smem, st>>>(tmX, tmDy, dW, N, K, M, block_n, slab, tmem_cols, stack_n, g_tf32_raw_hi);
         return (int)cudaGetLastError();
     };
-    const int max_stages = (200 * 1024) / stage_bytes;
+    const int max_stages = min((200 * 1024) / stage_bytes, g_wgrad_stages);
     if (max_stages >= 4) return launch(std::integral_constant<int, 4>{});
     if (max_stages >= 3) return launch(std::integral_constant<int, 3>{});
     if (max_stages >= 2) return launch(std::integral_constant<int, 2>{});

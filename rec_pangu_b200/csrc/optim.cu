@@ -12,6 +12,14 @@ namespace rpb {
 
 struct AdamHyper { float lr, b1, b2, eps, bc1, bc2_sqrt; };   // bc1 = 1 - b1^t, bc2_sqrt = sqrt(1 - b2^t)
 
+__host__ __device__ inline AdamHyper make_hyper(float lr, float b1, float b2, float eps, int step) {
+    AdamHyper h;
+    h.lr = lr; h.b1 = b1; h.b2 = b2; h.eps = eps;
+    h.bc1 = 1.f - powf(b1, (float)step);
+    h.bc2_sqrt = sqrtf(1.f - powf(b2, (float)step));
+    return h;
+}
+
 __device__ __forceinline__ void adam_update(float& p, float& m, float& v, float g, const AdamHyper& h) {
     m = h.b1 * m + (1.f - h.b1) * g;
     v = h.b2 * v + (1.f - h.b2) * g * g;
@@ -19,14 +27,26 @@ __device__ __forceinline__ void adam_update(float& p, float& m, float& v, float 
     p -= (h.lr / h.bc1) * (m / denom);
 }
 
+// Up to RPB_ADAM_MAX_TENSORS dense parameters in one launch: block b works on tensor t with blk0[t] <= b < blk0[t+1].
+// step_dev (device int32, may be null): the step number is read on the device, so a captured CUDA graph of the
+// training step keeps counting (bias correction) across replays.
+struct AdamMultiParams {
+    float* p[RPB_ADAM_MAX_TENSORS]; const float* g[RPB_ADAM_MAX_TENSORS];
+    float* m[RPB_ADAM_MAX_TENSORS]; float* v[RPB_ADAM_MAX_TENSORS];
+    long long n[RPB_ADAM_MAX_TENSORS]; int blk0[RPB_ADAM_MAX_TENSORS + 1];
+    int count; AdamHyper h; const int* step_dev;
+};
+
 __global__ void __launch_bounds__(256)
-adam_dense_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                  long long n, AdamHyper h) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float pp = p[i], mm = m[i], vv = v[i];
-    adam_update(pp, mm, vv, g[i], h);
-    p[i] = pp; m[i] = mm; v[i] = vv;
+adam_multi_kernel(const __grid_constant__ AdamMultiParams q) {
+    int t = 0;
+    while (t + 1 < q.count && (int)blockIdx.x >= q.blk0[t + 1]) ++t;
+    const long long i = (long long)(blockIdx.x - q.blk0[t]) * blockDim.x + threadIdx.x;
+    if (i >= q.n[t]) return;
+    const AdamHyper h = q.step_dev != nullptr ? make_hyper(q.h.lr, q.h.b1, q.h.b2, q.h.eps, *q.step_dev) : q.h;
+    float pp = q.p[t][i], mm = q.m[t][i], vv = q.v[t][i];
+    adam_update(pp, mm, vv, q.g[t][i], h);
+    q.p[t][i] = pp; q.m[t][i] = mm; q.v[t][i] = vv;
 }
 
 struct SparseAdamParams {
@@ -39,6 +59,7 @@ struct SparseAdamParams {
     long long rows[RPB_MAX_FIELDS];
     int B, F, D, step;
     AdamHyper h;
+    const int* step_dev;
 };
 
 // LPR lanes own one (sample, field) occurrence at a time; lane 0 claims the row for this step with an atomic
@@ -47,6 +68,8 @@ template <int LPR>
 __global__ void __launch_bounds__(256)
 sparse_adam_kernel(const __grid_constant__ SparseAdamParams p) {
     const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int step = p.step_dev != nullptr ? *p.step_dev : p.step;
+    const AdamHyper hy = p.step_dev != nullptr ? make_hyper(p.h.lr, p.h.b1, p.h.b2, p.h.eps, step) : p.h;
     const int b_raw = (int)(gt / LPR), l = (int)(gt % LPR);
     const bool valid = b_raw < p.B;
     const int b = valid ? b_raw : p.B - 1;
@@ -56,7 +79,7 @@ sparse_adam_kernel(const __grid_constant__ SparseAdamParams p) {
         long long row = __ldg(p.idx[f] + b);
         if ((unsigned long long)row >= (unsigned long long)p.rows[f]) row = 0;
         int claimed = 0;
-        if (l == 0 && valid) claimed = (atomicExch(p.stamp[f] + row, p.step) != p.step) ? 1 : 0;
+        if (l == 0 && valid) claimed = (atomicExch(p.stamp[f] + row, step) != step) ? 1 : 0;
         claimed = __shfl_sync(0xffffffffu, claimed, (threadIdx.x & 31) / LPR * LPR);
         if (claimed && l < DV) {
             const size_t off = (size_t)row * p.D + l * 4;
@@ -64,8 +87,8 @@ sparse_adam_kernel(const __grid_constant__ SparseAdamParams p) {
             float4 w = *reinterpret_cast<const float4*>(p.w[f] + off);
             float4 m = *reinterpret_cast<const float4*>(p.m[f] + off);
             float4 v = *reinterpret_cast<const float4*>(p.v[f] + off);
-            adam_update(w.x, m.x, v.x, g.x, p.h); adam_update(w.y, m.y, v.y, g.y, p.h);
-            adam_update(w.z, m.z, v.z, g.z, p.h); adam_update(w.w, m.w, v.w, g.w, p.h);
+            adam_update(w.x, m.x, v.x, g.x, hy); adam_update(w.y, m.y, v.y, g.y, hy);
+            adam_update(w.z, m.z, v.z, g.z, hy); adam_update(w.w, m.w, v.w, g.w, hy);
             *reinterpret_cast<float4*>(p.w[f] + off) = w;
             *reinterpret_cast<float4*>(p.m[f] + off) = m;
             *reinterpret_cast<float4*>(p.v[f] + off) = v;
@@ -78,25 +101,39 @@ sparse_adam_kernel(const __grid_constant__ SparseAdamParams p) {
 
 using namespace rpb;
 
-static AdamHyper make_hyper(float lr, float b1, float b2, float eps, int step) {
-    AdamHyper h;
-    h.lr = lr; h.b1 = b1; h.b2 = b2; h.eps = eps;
-    h.bc1 = 1.f - powf(b1, (float)step);
-    h.bc2_sqrt = sqrtf(1.f - powf(b2, (float)step));
-    return h;
-}
-
 RPB_API int rpb_adam_dense(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                            float eps, int step, void* stream) {
     if (p == nullptr || g == nullptr || m == nullptr || v == nullptr || n <= 0 || step < 1) return RPB_ERR_BAD_ARG;
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    adam_dense_kernel<<<ceil_div(n, 256), 256, 0, st>>>(p, g, m, v, n, make_hyper(lr, beta1, beta2, eps, step));
+    RpbAdamMultiDesc d{};
+    float* pp[1] = {p}; const float* gg[1] = {g}; float* mm[1] = {m}; float* vv[1] = {v}; int64_t nn[1] = {n};
+    d.count = 1; d.params = pp; d.grads = gg; d.exp_avg = mm; d.exp_avg_sq = vv; d.numel = nn;
+    d.lr = lr; d.beta1 = beta1; d.beta2 = beta2; d.eps = eps; d.step = step; d.step_dev = nullptr;
+    return rpb_adam_multi(&d, stream);
+}
+
+RPB_API int rpb_adam_multi(const RpbAdamMultiDesc* d, void* stream) {
+    if (d == nullptr || d->count <= 0 || (d->step_dev == nullptr && d->step < 1)) return RPB_ERR_BAD_ARG;
+    if (d->count > RPB_ADAM_MAX_TENSORS) return RPB_ERR_UNSUPPORTED;
+    AdamMultiParams q{};
+    int blocks = 0;
+    for (int t = 0; t < d->count; ++t) {
+        if (d->params[t] == nullptr || d->grads[t] == nullptr || d->exp_avg[t] == nullptr || d->exp_avg_sq[t] == nullptr || d->numel[t] <= 0)
+            return RPB_ERR_BAD_ARG;
+        q.p[t] = d->params[t]; q.g[t] = d->grads[t]; q.m[t] = d->exp_avg[t]; q.v[t] = d->exp_avg_sq[t]; q.n[t] = d->numel[t];
+        q.blk0[t] = blocks;
+        blocks += ceil_div(d->numel[t], 256);
+    }
+    q.blk0[d->count] = blocks;
+    q.count = d->count;
+    q.h = make_hyper(d->lr, d->beta1, d->beta2, d->eps, d->step_dev != nullptr ? 1 : d->step);
+    q.step_dev = d->step_dev;
+    adam_multi_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(q);
     RPB_LAUNCH_CHECK();
     return 0;
 }
 
 RPB_API int rpb_sparse_adam(const RpbSparseAdamDesc* d, void* stream) {
-    if (d == nullptr || d->B <= 0 || d->F <= 0 || d->D <= 0 || d->step < 1) return RPB_ERR_BAD_ARG;
+    if (d == nullptr || d->B <= 0 || d->F <= 0 || d->D <= 0 || (d->step_dev == nullptr && d->step < 1)) return RPB_ERR_BAD_ARG;
     if (d->F > RPB_MAX_FIELDS || d->D % 4 != 0 || d->D > 128) return RPB_ERR_UNSUPPORTED;
     SparseAdamParams p{};
     for (int f = 0; f < d->F; ++f) {
@@ -106,7 +143,8 @@ RPB_API int rpb_sparse_adam(const RpbSparseAdamDesc* d, void* stream) {
         p.rows[f] = d->rows[f];
     }
     p.B = d->B; p.F = d->F; p.D = d->D; p.step = d->step;
-    p.h = make_hyper(d->lr, d->beta1, d->beta2, d->eps, d->step);
+    p.step_dev = d->step_dev;
+    p.h = make_hyper(d->lr, d->beta1, d->beta2, d->eps, d->step_dev != nullptr ? 1 : d->step);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int dv = d->D / 4;
     auto launch = [&](auto lt) -> int {

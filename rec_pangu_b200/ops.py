@@ -24,6 +24,18 @@ FUSED_DX_SCATTER = int(__import__('os').environ.get('RPB_DX_SCATTER', '1'))
 TOWER_TAIL = int(__import__('os').environ.get('RPB_TOWER_TAIL', '1'))
 # 1 = the tail runs inside the epilogue of the layer-1 tcgen05 GEMM (rpb_linear_tower_fwd), 0 = as its own kernel
 FUSED_TOWER_EPILOGUE = int(__import__('os').environ.get('RPB_TOWER_EPILOGUE', '1'))
+# 1 = the tower's small weight-gradient kernels run on a side stream concurrently with the layer-1 one
+PARALLEL_WGRAD = int(__import__('os').environ.get('RPB_PARALLEL_WGRAD', '1'))
+_SIDE = {}
+
+
+def _side_stream(dev) -> 'torch.cuda.Stream':
+    key = torch.device(dev).index or 0
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=dev)
+    return _SIDE[key]
+
+
 _LAUNCHES = 0           # number of librec_pangu_b200 kernels launched (bench.py reports it as gpu_launches)
 
 
@@ -726,12 +738,29 @@ def _tower_bwd(cfg, acts, params, dlogit_in=None, head=None, gloss=None, need_dx
     d.dlogit_out = dlogit.data_ptr()
     check(lib.rpb_tower_tail_bwd(C.byref(d), st), 'rpb_tower_tail_bwd')
     _count()
-    # weight gradients (bias gradients came out of the tower kernel): dW_i = dz_i^T . input_i
-    for i in range(n_hidden - 1, -1, -1):
+    # weight gradients (bias gradients came out of the tower kernel): dW_i = dz_i^T . input_i.  They only READ the dz
+    # tiles, so the small 64x64 ones run on a side stream next to the layer-1 one (fork / join with events; the pattern
+    # is capturable into the step's CUDA graph) instead of three latency-bound launches back to back.
+    def wgrad(i):
         kdim = K if i == 0 else 64
         check(lib.rpb_linear_bwd(_ptr(dzs[i]), 64, _ptr(acts[i]), acts[i].stride(0), None, None, 0, None, 0,
-                                 _ptr(zviews[2 * i]), None, M, 64, kdim, impl, st), 'rpb_linear_bwd')
+                                 _ptr(zviews[2 * i]), None, M, 64, kdim, impl, _stream()), 'rpb_linear_bwd')
         _count()
+
+    if n_tail and PARALLEL_WGRAD:
+        main, side = torch.cuda.current_stream(), _side_stream(dev)
+        fork, join = torch.cuda.Event(), torch.cuda.Event()
+        fork.record(main)
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            for i in range(n_hidden - 1, 0, -1):
+                wgrad(i)
+            join.record(side)
+        wgrad(0)
+        main.wait_event(join)
+    else:
+        for i in range(n_hidden - 1, -1, -1):
+            wgrad(i)
     gparams = list(zviews)
     if layer0_hook is not None and layer0_hook(dzs[0], 64, params[0], dlogit):
         return None, gparams, dlogit

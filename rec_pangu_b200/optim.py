@@ -12,7 +12,7 @@ import ctypes as C
 import torch
 
 from . import _lib, ops
-from ._lib import SparseAdamDesc, check
+from ._lib import AdamMultiDesc, SparseAdamDesc, check
 from .models.layers.embedding import EmbeddingLayer
 
 
@@ -20,6 +20,7 @@ class FusedAdam:
     def __init__(self, model: torch.nn.Module, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
         self.model, self.lr, self.betas, self.eps = model, lr, betas, eps
         self.step_count = 0
+        self.step_dev = None                       # device int32 step counter (graph-replay safe)
         self.emb_layers = [m for m in model.modules() if isinstance(m, EmbeddingLayer) and m._shards is None]
         for m in self.emb_layers:
             m.grad_mode = 'persistent'
@@ -36,16 +37,31 @@ class FusedAdam:
 
     @torch.no_grad()
     def step(self):
+        """One optimizer step.  The step number lives on the device (`self.step_dev`, incremented on the stream), so the
+        whole step — including its bias correction and the per-step row stamps — can be captured into a CUDA graph and
+        replayed."""
         self.step_count += 1
         lib, st = _lib.load(), C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        b1, b2 = self.betas
-        for p in self.dense:
-            if p.grad is None:
-                continue
-            s = self._st(p)
-            g = p.grad.contiguous()
-            check(lib.rpb_adam_dense(p.data_ptr(), g.data_ptr(), s['m'].data_ptr(), s['v'].data_ptr(), p.numel(), self.lr,
-                                     b1, b2, self.eps, self.step_count, st), 'rpb_adam_dense')
+        live = [p for p in self.dense if p.grad is not None]
+        if self.step_dev is None and (live or self.emb_layers):
+            dev = live[0].device if live else next(self.model.parameters()).device
+            self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        if self.step_dev is not None:
+            self.step_dev.add_(1)
+        for c0 in range(0, len(live), _lib.ADAM_MAX_TENSORS):
+            chunk = live[c0:c0 + _lib.ADAM_MAX_TENSORS]
+            n = len(chunk)
+            states = [self._st(p) for p in chunk]
+            grads = [p.grad.contiguous() for p in chunk]
+            arr = lambda ts: (C.c_void_p * n)(*[t.data_ptr() for t in ts])  # noqa: E731
+            keep = (arr(chunk), arr(grads), arr([s['m'] for s in states]), arr([s['v'] for s in states]),
+                    (C.c_int64 * n)(*[p.numel() for p in chunk]), grads)
+            d = AdamMultiDesc()
+            d.count, d.step = n, self.step_count
+            d.lr, d.beta1, d.beta2, d.eps = self.lr, self.betas[0], self.betas[1], self.eps
+            d.params, d.grads, d.exp_avg, d.exp_avg_sq, d.numel = keep[:5]
+            d.step_dev = self.step_dev.data_ptr()
+            check(lib.rpb_adam_multi(C.byref(d), st), 'rpb_adam_multi')
             ops._count()
         for emb in self.emb_layers:
             store = emb._grad_store
@@ -81,6 +97,7 @@ class FusedAdam:
         r_arr = (C.c_int64 * F)(*rows)
         i_arr = arr(idx)
         d.weights, d.grads, d.exp_avg, d.exp_avg_sq, d.stamps, d.rows, d.idx = w_arr, g_arr, m_arr, v_arr, s_arr, r_arr, i_arr
+        d.step_dev = self.step_dev.data_ptr()
         check(lib.rpb_sparse_adam(C.byref(d), st), 'rpb_sparse_adam')
         ops._count()
 

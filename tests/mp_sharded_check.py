@@ -13,20 +13,20 @@ from rec_pangu_b200 import dist as rdist, ops
 from rec_pangu_b200.models.ranking import DeepFM
 
 
-def main():
-    rank, world, local = rdist.init_from_env('nccl')
-    dev = torch.device('cuda', local)
+def check(rank, world, dev, hidden):
+    """hidden = [16, 8]: layer-by-layer MLP kernels; [64, 64]: the fused tower-tail kernels (single-GPU reference with the
+    loss fused into the DeepFM core node, sharded model through MLP + the separate sigmoid/BCE head)."""
     enc = make_enc(6, 3, [101, 57, 33, 200, 17, 64])
     B = 96
     torch.manual_seed(7)
-    ref = DeepFM(embedding_dim=8, hidden_units=[16, 8], enc_dict=enc)
+    ref = DeepFM(embedding_dim=8, hidden_units=hidden, enc_dict=enc)
     with torch.no_grad():
         for n, p in ref.named_parameters():
             if 'embedding_layer' in n:
                 p.mul_(0.3)
     sd = {k: v.clone() for k, v in ref.state_dict().items()}
     ref = ref.to(dev)
-    model = DeepFM(embedding_dim=8, hidden_units=[16, 8], enc_dict=enc)
+    model = DeepFM(embedding_dim=8, hidden_units=hidden, enc_dict=enc)
     model.load_state_dict(sd)
     model = model.to(dev)
     st = rdist.shard_model_tables(model)
@@ -67,6 +67,13 @@ def main():
     for f in range(len(st.cols)):
         assert torch.count_nonzero(st.full_grad(f)) == 0
     dist.barrier()
+
+
+def main():
+    rank, world, local = rdist.init_from_env('nccl')
+    dev = torch.device('cuda', local)
+    for hidden in ([16, 8], [64, 64]):
+        check(rank, world, dev, hidden)
     if rank == 0:
         print('SHARDED_OK world', world, flush=True)
     torch.cuda.synchronize()

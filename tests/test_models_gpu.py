@@ -201,3 +201,34 @@ def test_fused_sparse_adam_matches_torch_adam_on_touched_rows():
     # gradient buffers are all-zero again after the fused step
     for buf in m2.embedding_layer._grad_store.buffers.values():
         assert torch.count_nonzero(buf) == 0
+
+
+def test_fused_adam_inside_cuda_graph_keeps_counting_steps():
+    """A captured training step (GraphedStep with FusedAdam as `post`) replays with the right bias correction and row
+    stamps: 3 eager warm-up steps + 2 replays == 5 eager steps (the step number lives on the device)."""
+    from rec_pangu_b200.models.ranking import DeepFM
+    from rec_pangu_b200.optim import FusedAdam
+    from rec_pangu_b200.runtime import ColumnarBatch, GraphedStep
+    enc = make_enc(6, 3, 200)
+    torch.manual_seed(3)
+    m1 = DeepFM(embedding_dim=16, hidden_units=[64, 64], enc_dict=enc).cuda()
+    m2 = DeepFM(embedding_dim=16, hidden_units=[64, 64], enc_dict=enc).cuda()
+    m2.load_state_dict(m1.state_dict())
+    for m in (m1, m2):
+        m.set_grad_mode('persistent')
+        m.train()
+    data = make_batch(enc, 1024, seed=5, device='cuda')
+    cb = ColumnarBatch(enc, 1024, device='cuda', pinned_host=False)
+    cb.load_device(data)
+    o1, o2 = FusedAdam(m1, lr=1e-2), FusedAdam(m2, lr=1e-2)
+    gs = GraphedStep(m1, cb, post=o1.step, warmup=3, use_graph=True)
+    gs.replay()
+    gs.replay()
+    torch.cuda.synchronize()
+    assert int(o1.step_dev.item()) == 5
+    for _ in range(5):
+        m2(data)['loss'].backward()
+        o2.step()
+        m2.zero_grad()
+    for (k, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        torch.testing.assert_close(p1, p2, rtol=1e-4, atol=1e-5, msg=lambda s: f'{k}: {s}')
