@@ -18,7 +18,7 @@ __all__ = [
     "sparse_cols", "dense_cols", "embedding_layer", "get_linear_input", "fm_layer",
     "bi_interaction", "mlp", "lr_layer", "crossnet", "cin", "senet", "bilinear_field_interaction",
     "mhsa", "bce_mean", "deepfm", "xdeepfm", "autoint", "dcn", "fibinet", "fm", "wdl", "nfm", "mmoe",
-    "MODEL_FORWARDS",
+    "sharebottom", "omoe", "mlmmoe", "MODEL_FORWARDS",
 ]
 
 
@@ -255,7 +255,64 @@ def mmoe(sd, enc_dict, data, gates: List[torch.Tensor], gates_bias: List[torch.T
     return out
 
 
+def _task_towers(sd, tower_inputs, data, is_training, hidden_dim, bn_training, eps=0.0, bn_eps=1e-5):
+    """The per-task tower + weighted-BCE block shared by ShareBottom / OMOE / MLMMOE (sharebottom.py:69-92, omoe.py:82-107,
+    mlmmoe.py:118-143): Linear -> BatchNorm1d -> Dropout (identity here) per hidden layer, Linear(->1), Sigmoid;
+    loss = sum_t (1/T) BCE(pred_t, task{t}_label) — no +1e-6 (that is MMOE only)."""
+    T = len(tower_inputs)
+    out, loss = {}, 0
+    for t in range(T):
+        x = tower_inputs[t]
+        p = f"task_{t + 1}_dnn"
+        for j in range(len(hidden_dim)):
+            x = F.linear(x, sd[f"{p}.ctr_hidden_{j}.weight"], sd[f"{p}.ctr_hidden_{j}.bias"])
+            x = F.batch_norm(x, sd[f"{p}.ctr_batchnorm_{j}.running_mean"].clone(),
+                             sd[f"{p}.ctr_batchnorm_{j}.running_var"].clone(),
+                             sd[f"{p}.ctr_batchnorm_{j}.weight"], sd[f"{p}.ctr_batchnorm_{j}.bias"],
+                             training=bn_training, momentum=0.1, eps=bn_eps)
+        x = torch.sigmoid(F.linear(x, sd[f"{p}.task_last_layer.weight"], sd[f"{p}.task_last_layer.bias"]))
+        out[f'task{t + 1}_pred'] = x
+        if is_training:
+            loss = loss + (1.0 / T) * F.binary_cross_entropy(x.squeeze(-1) + eps if eps else x.squeeze(-1),
+                                                             data[f'task{t + 1}_label'])
+    if is_training:
+        out['loss'] = loss
+    return out
+
+
+def sharebottom(sd, enc_dict, data, is_training=True, num_task=2, hidden_units=(128, 64), bn_training: bool = False):
+    """ShareBottom.forward/.loss (models/multi_task/sharebottom.py:54-92): every task tower reads the same
+    cat(embeddings.flatten(1), dense) row."""
+    _, hidden = _emb_dense(sd, enc_dict, data)
+    return _task_towers(sd, [hidden] * num_task, data, is_training, hidden_units, bn_training)
+
+
+def omoe(sd, enc_dict, data, is_training=True, num_task=2, hidden_dim=(128, 64), bn_training: bool = False):
+    """OMOE.forward/.loss (models/multi_task/omoe.py:58-107): experts einsum + bias (omoe.py:73-74), ONE parameter-only
+    gate softmax(dim=0) shared by all tasks (omoe.py:79-80)."""
+    _, hidden = _emb_dense(sd, enc_dict, data)
+    experts_out = torch.einsum('ij,jkl->ikl', hidden, sd["experts"]) + sd["experts_bias"]
+    gate = torch.softmax(sd["gate"], dim=0)
+    gate_out = torch.einsum('abc,cd->abd', experts_out, gate).squeeze(-1)
+    return _task_towers(sd, [gate_out] * num_task, data, is_training, hidden_dim, bn_training)
+
+
+def mlmmoe(sd, enc_dict, data, level_gates: List[torch.Tensor], gates: List[torch.Tensor], gates_bias: List[torch.Tensor],
+           is_training=True, num_task=2, hidden_dim=(128, 64), bn_training: bool = False):
+    """MLMMOE.forward/.loss (models/multi_task/mlmmoe.py:74-143): experts (mlmmoe.py:90-91), parameter-only second-level
+    gates (mlmmoe.py:96-102), per-task input gates (mlmmoe.py:104-110) and the gated sum (mlmmoe.py:112-117).  The three
+    gate lists are unregistered python lists in the reference and are passed explicitly."""
+    _, hidden = _emb_dense(sd, enc_dict, data)
+    experts_out = torch.einsum('ij,jkl->ikl', hidden, sd["experts"]) + sd["experts_bias"]
+    level_out = torch.cat([torch.einsum('abc,cd->abd', experts_out, torch.softmax(g, dim=0)) for g in level_gates], dim=-1)
+    outs = []
+    for g, gb in zip(gates, gates_bias):
+        gate = torch.softmax(hidden @ g + gb, dim=-1)
+        outs.append(torch.sum(level_out * gate.unsqueeze(1), dim=2))
+    return _task_towers(sd, outs[:num_task], data, is_training, hidden_dim, bn_training)
+
+
 MODEL_FORWARDS = {
     'DeepFM': deepfm, 'xDeepFM': xdeepfm, 'AutoInt': autoint, 'DCN': dcn, 'FiBiNet': fibinet,
-    'FM': fm, 'WDL': wdl, 'NFM': nfm, 'MMOE': mmoe,
+    'FM': fm, 'WDL': wdl, 'NFM': nfm, 'MMOE': mmoe, 'ShareBottom': sharebottom, 'OMOE': omoe, 'MLMMOE': mlmmoe,
 }

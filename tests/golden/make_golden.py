@@ -30,7 +30,7 @@ sys.path.insert(0, '/root/reference')
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 from rec_pangu.models.ranking import DeepFM, xDeepFM, AutoInt, DCN, FiBiNet, FM, WDL, NFM  # noqa: E402
-from rec_pangu.models.multi_task import MMOE  # noqa: E402
+from rec_pangu.models.multi_task import MMOE, ShareBottom, OMOE, MLMMOE  # noqa: E402
 from rec_pangu.models.layers import (FM_Layer, MLP, CrossNet, CompressedInteractionNet, SENET_Layer,  # noqa: E402
                                      BilinearInteractionLayer, MultiHeadSelfAttention, InnerProductLayer)
 
@@ -129,6 +129,37 @@ def run_mmoe(name, bn_training, seed=1029):
                'kwargs': {'mmoe_hidden_dim': 16, 'hidden_dim': [16, 8], 'dropouts': [0.0, 0.0]}, 'D': 8})
 
 
+def run_multitask(name, ctor, kwargs, bn_training, list_attrs=(), seed=1029):
+    """ShareBottom / OMOE / MLMMOE (multi_task/{sharebottom,omoe,mlmmoe}.py).  `list_attrs`: unregistered python lists of
+    Parameters (MLMMOE's level_gates / gates / gates_bias) saved next to the state_dict with their gradients."""
+    torch.manual_seed(seed)
+    gen = torch.Generator().manual_seed(seed)
+    enc = make_enc(4, 2, [17, 50, 97, 9])
+    model = ctor(embedding_dim=8, enc_dict=enc, **kwargs)
+    with torch.no_grad():
+        for k, p in model.named_parameters():
+            if p.dim() == 1:
+                p.copy_(torch.randn(p.shape, generator=gen) * 0.1 + (1.0 if 'batchnorm' in k and 'weight' in k else 0.0))
+            elif k in ('experts', 'experts_bias'):
+                p.mul_(0.3)                       # normal_(0,1) experts over a 34-wide input saturate the sigmoid
+        for k, b in model.named_buffers():
+            if 'running_mean' in k:
+                b.copy_(torch.randn(b.shape, generator=gen) * 0.1)
+            if 'running_var' in k:
+                b.copy_(torch.rand(b.shape, generator=gen) + 0.5)
+    model.train(bn_training)
+    sd_before = {k: v.clone() for k, v in model.state_dict().items()}
+    data = make_batch(enc, 48, gen, labels=('task1_label', 'task2_label'))
+    out = model(data)
+    out['loss'].backward()
+    extra = {}
+    for a in list_attrs:
+        extra.update({f'{a}.{i}': g for i, g in enumerate(getattr(model, a))})
+    model.load_state_dict(sd_before)
+    save(name, model, enc, data, out, extra_sd=extra,
+         meta={'model': ctor.__name__, 'bn_training': bn_training, 'kwargs': kwargs, 'D': 8, 'list_attrs': list(list_attrs)})
+
+
 def run_layers(seed=7):
     torch.manual_seed(seed)
     gen = torch.Generator().manual_seed(seed)
@@ -168,7 +199,20 @@ def run_layers(seed=7):
     print('layers saved')
 
 
+def run_multitask_all():
+    tw = {'dropouts': [0.0, 0.0]}
+    for bn in (False, True):
+        sfx = '_train' if bn else '_eval'
+        run_multitask('sharebottom' + sfx, ShareBottom, dict(hidden_units=[16, 8], **tw), bn)
+        run_multitask('omoe' + sfx, OMOE, dict(omoe_hidden_dim=16, hidden_dim=[16, 8], **tw), bn)
+        run_multitask('mlmmoe' + sfx, MLMMOE, dict(mmoe_hidden_dim=16, hidden_dim=[16, 8], device='cpu', **tw), bn,
+                      list_attrs=('level_gates', 'gates', 'gates_bias'))
+
+
 if __name__ == '__main__':
+    if '--only-multitask' in sys.argv:            # ShareBottom / OMOE / MLMMOE fixtures only (added after the first set)
+        run_multitask_all()
+        sys.exit(0)
     run_layers()
     run_model('deepfm', DeepFM, {'hidden_units': [16, 8]})
     run_model('deepfm_d16', DeepFM, {'hidden_units': [32, 16, 8]}, n_sparse=7, n_dense=4, D=16, B=40)
@@ -182,3 +226,4 @@ if __name__ == '__main__':
     run_model('nfm', NFM, {'hidden_units': [16, 8]})
     run_mmoe('mmoe_eval', bn_training=False)
     run_mmoe('mmoe_train', bn_training=True)
+    run_multitask_all()
