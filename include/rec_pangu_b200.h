@@ -107,6 +107,11 @@ int rpb_gather_bwd(const RpbScatterDesc* d, void* stream);
  * Leaves a [rows, D] buffer all-zero again at O(batch) cost instead of the reference's O(vocabulary) zero-fill. */
 int rpb_rows_zero(const RpbScatterDesc* d, void* stream);
 
+/* Hashed-id encoder for tables too large for the reference's sorted-unique vocabulary map (dataset/base_dataset.py:57-61,92),
+ * BASELINE.json config 5: out[i] = splitmix64(raw[i]) mod vocab_size, int64 in [0, vocab_size) — row vocab_size stays
+ * the OOV slot.  Integer contract restated in oracle/index_routing.py::hash_to_row (bit-exact).  In place allowed. */
+int rpb_hash_to_row(const int64_t* raw, int64_t* out, int64_t n, int64_t vocab_size, void* stream);
+
 /* Standalone FM second-order term on any [B,F,D] tensor with row stride lde (floats) between samples:
  * InnerProductLayer (interaction.py:36-44).  out_sum [B] (product_sum_pooling) and/or out_bi [B,D]
  * (Bi_interaction_pooling) may be NULL. */

@@ -7,7 +7,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'librec_pangu_b200.so')
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_FIELDS = 64
 MAX_DENSE = 64
 ERR_UNSUPPORTED = -1
@@ -69,6 +69,7 @@ SIGNATURES = {
     'rpb_gather_fwd': (C.c_int, [C.POINTER(GatherDesc), _vp]),
     'rpb_gather_bwd': (C.c_int, [C.POINTER(ScatterDesc), _vp]),
     'rpb_rows_zero': (C.c_int, [C.POINTER(ScatterDesc), _vp]),
+    'rpb_hash_to_row': (C.c_int, [_vp, _vp, _i64, _i64, _vp]),
     'rpb_fm_fwd': (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     'rpb_fm_bwd': (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _i64, C.c_int, _vp]),
     'rpb_linear_fwd': (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),

@@ -12,7 +12,7 @@ import torch
 from . import _lib
 from ._lib import GatherDesc, ScatterDesc, TowerFwdDesc, TowerBwdDesc, check
 
-__all__ = ['GradStore', 'deepfm_core', 'gather', 'gather_sharded', 'sharded_clean', 'fm_interaction', 'mlp_forward', 'sigmoid_bce', 'linear', 'feature_row_stride',
+__all__ = ['GradStore', 'hash_to_row', 'deepfm_core', 'gather', 'gather_sharded', 'sharded_clean', 'fm_interaction', 'mlp_forward', 'sigmoid_bce', 'linear', 'feature_row_stride',
            'check_index_errors', 'set_gemm_impl', 'get_gemm_impl', 'launch_count', 'reset_launch_count']
 
 _GEMM_IMPL = int(__import__('os').environ.get('RPB_GEMM_IMPL', '0'))   # 0 auto, 1 SIMT fp32, 2 tcgen05 3xTF32
@@ -452,6 +452,20 @@ def sharded_clean(st):
     if st.pending:
         st.barrier()
     st.pending = []
+
+
+def hash_to_row(raw: torch.Tensor, vocab_size: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Hashed-id encoder (config 5): row = splitmix64(raw) mod vocab_size for an int64 CUDA tensor of raw ids.  The
+    result addresses rows [0, vocab_size) of a [vocab_size + 1, D] table; row vocab_size stays the OOV slot."""
+    _cuda(raw, 'raw id column')
+    if raw.dtype != torch.int64:
+        raise TypeError(f'hash_to_row expects int64 ids, got {raw.dtype}')
+    raw = raw.contiguous()
+    if out is None:
+        out = torch.empty_like(raw)
+    check(_lib.load().rpb_hash_to_row(_ptr(raw), _ptr(out), raw.numel(), int(vocab_size), _stream()), 'rpb_hash_to_row')
+    _count()
+    return out
 
 
 # ------------------------------------------------------------------ standalone FM on [B,F,D]
