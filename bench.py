@@ -265,7 +265,14 @@ def run_ours(args):
     ev_copied = [torch.cuda.Event(), torch.cuda.Event()]
     ev_done = [torch.cuda.Event(), torch.cuda.Event()]
 
+    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()          # D2H landing zone of the per-step loss
+    ev_loss = [torch.cuda.Event(), torch.cuda.Event()]
+
     def e2e_loop(n):
+        """Every step: H2D of its batch from pinned memory (3 copies), the graph replay, and a D2H copy of its loss that the
+        host reads.  The loss of step i is read while step i+1 runs (async metrics: the copy is queued right behind the
+        step, the host waits for its event one iteration later), so the device never idles on a host round trip; the last
+        loss is read before the timed region closes."""
         h2d_bytes, lossv = 0, 0.0
         with torch.cuda.stream(copy_stream):
             h2d_bytes = cbs[0].h2d()
@@ -280,7 +287,13 @@ def run_ours(args):
             main_stream.wait_event(ev_copied[cur])
             steps_g[cur].replay()
             ev_done[cur].record(main_stream)
-            lossv = float(steps_g[cur].loss.item())              # D2H read of the step's result
+            loss_host[cur:cur + 1].copy_(steps_g[cur].loss.reshape(1), non_blocking=True)     # D2H of this step's result
+            ev_loss[cur].record(main_stream)
+            if i >= 1:
+                ev_loss[nxt].synchronize()                       # loss of step i-1 has landed
+                lossv = float(loss_host[nxt])
+        ev_loss[(n - 1) % 2].synchronize()
+        lossv = float(loss_host[(n - 1) % 2])
         return h2d_bytes, lossv
 
     e2e_loop(max(3, args.warmup))
@@ -295,7 +308,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = float(t.item())
     e2e = {'value': world * B * args.steps / (ms_e2e * 1e-3), 'unit': 'samples/s', 'h2d_bytes_per_step': h2d,
-           'd2h_bytes_per_step': 4, 'loss': lossv, 'overlap': 'H2D of batch i+1 on a copy stream during step i'}
+           'd2h_bytes_per_step': 4, 'loss': lossv, 'overlap': 'H2D of batch i+1 on a copy stream during step i; loss of step i read by the host during step i+1'}
 
     roofline = None
     if world == 1:
@@ -349,7 +362,7 @@ def run_ours(args):
         us_nomat = e0.elapsed_time(e1) * 1e3 / args.steps
         roofline = {'kernel': 'gather_fwd_tile_kernel (multi-table gather + dense pack + FM second order, x materialised)',
                     'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                    'traffic': 183.1e6, 'traffic_source': 'profiles/r01_gather_fwd.md (ncu dram__bytes_read+write per launch)',
+                    'traffic': 185.7e6, 'traffic_source': 'profiles/r01_deepfm_step_ncu_full.md (ncu --set full: dram__bytes_read 125.3 MB + write 60.4 MB per launch)',
                     'us_per_launch': us_gather, 'alg_bytes_per_launch': ALG_BYTES_PER_SAMPLE * B, 'peak_source': peak_src,
                     'no_materialise': {'us_per_launch': us_nomat,
                                        'achieved': ALG_BYTES_PER_SAMPLE * B / (us_nomat * 1e-6) / 1e9,

@@ -92,16 +92,58 @@ __device__ __forceinline__ void colsum_add(float4* row, int lane, float s0, floa
     }
 }
 
-__global__ void __launch_bounds__(TW_THREADS, 4)
+// 16-byte asynchronous global -> shared copy (zero-fill when `valid` is false)
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, bool valid) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int bytes = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Latency plan (the first version spent most of its time on exposed global loads — ncu: long-scoreboard stalls
+// dominated): the top activation tile of the NEXT tile is copied into Hs with cp.async while the current tile's layers
+// run, its (pred, label) / dlogit values are loaded one tile ahead into registers, and the ReLU-mask tile of each
+// hidden layer is loaded into registers BEFORE that layer's FMA block.  3 CTAs per SM (register budget 170).
+__global__ void __launch_bounds__(TW_THREADS, 3)
 tower_tail_bwd_kernel(const TowerBwdParams p) {
     extern __shared__ __align__(16) float tw_smem[];
     float* As = tw_smem;                              // [TW_ROWS][TW_LDA]: dz of the layer above
-    float* Bs = tw_smem + TW_ROWS * TW_LDA;           // [n_tail][n][k] = W_l[n][k]
+    float* Hs = As + TW_ROWS * TW_LDA;                // [TW_ROWS][TW_LDA]: top activation tile (prefetched)
+    float* Bs = Hs + TW_ROWS * TW_LDA;                // [n_tail][n][k] = W_l[n][k]
     // column sums (bias gradients, dw_out): one private row per warp, so no atomics: [j] = db[j], [TW_MAX_TAIL + 1] = dw_out
     __shared__ float4 cs[TW_MAX_TAIL + 2][TW_THREADS / 32][TW_H / 4];
     __shared__ float dbo_s;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, warp = tid >> 5, lane = tid & 31;
+    const int tiles = (p.M + TW_ROWS - 1) / TW_ROWS;
+    const float* htop = p.hin[p.n_tail];
+    const long long ldtop = p.n_tail == 0 ? p.ldh1 : (long long)TW_H;
 
+    auto prefetch_top = [&](int tile) {               // Hs <- rows of the top activation of `tile`
+        const int m0 = tile * TW_ROWS;
+#pragma unroll
+        for (int i = 0; i < TW_ROWS * 16 / TW_THREADS; ++i) {
+            const int e = tid + i * TW_THREADS, r = e >> 4, c4 = e & 15;
+            const bool ok = m0 + r < p.M;
+            cp_async16(Hs + r * TW_LDA + c4 * 4, htop + (size_t)(ok ? m0 + r : 0) * ldtop + c4 * 4, ok);
+        }
+    };
+    // (q, y) = (pred, label) or (dlogit_in, unused) of this thread's 8 rows, one tile ahead
+    float qn[8], yn[8];
+    auto load_dl_inputs = [&](int tile) {
+        const int m0 = tile * TW_ROWS;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int m = m0 + ty + 8 * i;
+            qn[i] = 0.f; yn[i] = 0.f;
+            if (m < p.M) {
+                if (p.dlogit_in != nullptr) qn[i] = __ldg(p.dlogit_in + m);
+                else { qn[i] = __ldg(p.pred + m); yn[i] = __ldg(p.label + m); }
+            }
+        }
+    };
+
+    prefetch_top(blockIdx.x);
+    load_dl_inputs(blockIdx.x);
     for (int l = 0; l < p.n_tail; ++l)
         for (int i = tid; i < TW_H * TW_H / 4; i += TW_THREADS)
             reinterpret_cast<float4*>(Bs + l * TW_H * TW_H)[i] = __ldg(reinterpret_cast<const float4*>(p.W[l]) + i);
@@ -110,40 +152,40 @@ tower_tail_bwd_kernel(const TowerBwdParams p) {
     if (tid == 0) dbo_s = 0.f;
     const float4 wo = ldg_f4(p.w_out + tx * 4);
     const float gscale = (p.gloss != nullptr ? __ldg(p.gloss) : 1.f) * p.scale / (float)p.M;
-    const int tiles = (p.M + TW_ROWS - 1) / TW_ROWS;
     float dbo = 0.f;
 
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int m0 = tile * TW_ROWS;
-        __syncthreads();
+        float dl[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (p.dlogit_in != nullptr) {
+                dl[i] = qn[i];
+            } else {
+                // ATen binary_cross_entropy_backward (denominator clamped at 1e-12) x sigmoid backward
+                const float pe = qn[i] + p.eps;
+                dl[i] = gscale * (pe - yn[i]) / fmaxf((1.f - pe) * pe, 1e-12f) * qn[i] * (1.f - qn[i]);
+            }
+        }
+        cp_async_wait_all();
+        __syncthreads();                              // Hs landed; the previous tile is done with As
         // ---- output layer: dz_top[r, n] = dlogit[r] * w_out[n] * (h_top[r, n] > 0)
         {
             const int j = p.n_tail;
-            const float* hj = p.hin[j];
-            const long long ld = j == 0 ? p.ldh1 : (long long)TW_H;
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int r = ty + 8 * i, m = m0 + r;
                 float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (m < p.M) {
-                    float dl;
-                    if (p.dlogit_in != nullptr) {
-                        dl = __ldg(p.dlogit_in + m);
-                    } else {
-                        // ATen binary_cross_entropy_backward (denominator clamped at 1e-12) x sigmoid backward
-                        const float q = __ldg(p.pred + m), y = __ldg(p.label + m);
-                        const float pe = q + p.eps;
-                        dl = gscale * (pe - y) / fmaxf((1.f - pe) * pe, 1e-12f) * q * (1.f - q);
-                    }
                     if (tx == 0) {
-                        if (p.dlogit_out != nullptr) p.dlogit_out[m] = dl;
-                        dbo += dl;
+                        if (p.dlogit_out != nullptr) p.dlogit_out[m] = dl[i];
+                        dbo += dl[i];
                     }
-                    const float4 hv = ldg_f4_stream(hj + (size_t)m * ld + tx * 4);
-                    w0 = fmaf(dl, hv.x, w0); w1 = fmaf(dl, hv.y, w1); w2 = fmaf(dl, hv.z, w2); w3 = fmaf(dl, hv.w, w3);
-                    d.x = hv.x > 0.f ? dl * wo.x : 0.f; d.y = hv.y > 0.f ? dl * wo.y : 0.f;
-                    d.z = hv.z > 0.f ? dl * wo.z : 0.f; d.w = hv.w > 0.f ? dl * wo.w : 0.f;
+                    const float4 hv = *reinterpret_cast<const float4*>(Hs + r * TW_LDA + tx * 4);
+                    w0 = fmaf(dl[i], hv.x, w0); w1 = fmaf(dl[i], hv.y, w1); w2 = fmaf(dl[i], hv.z, w2); w3 = fmaf(dl[i], hv.w, w3);
+                    d.x = hv.x > 0.f ? dl[i] * wo.x : 0.f; d.y = hv.y > 0.f ? dl[i] * wo.y : 0.f;
+                    d.z = hv.z > 0.f ? dl[i] * wo.z : 0.f; d.w = hv.w > 0.f ? dl[i] * wo.w : 0.f;
                     s0 += d.x; s1 += d.y; s2 += d.z; s3 += d.w;
                     stg_f4(p.dz[j] + (size_t)m * TW_H + tx * 4, d);
                 }
@@ -152,25 +194,35 @@ tower_tail_bwd_kernel(const TowerBwdParams p) {
             colsum_add(cs[j][warp], lane, s0, s1, s2, s3);
             colsum_add(cs[TW_MAX_TAIL + 1][warp], lane, w0, w1, w2, w3);
         }
-        __syncthreads();
+        __syncthreads();                              // As complete, Hs fully consumed
+        if (tile + (int)gridDim.x < tiles) {          // next tile's inputs fly while this tile's layers run
+            prefetch_top(tile + gridDim.x);
+            load_dl_inputs(tile + gridDim.x);
+        }
         // ---- hidden tail layers, top down: dz_j = (dz_{j+1} . W_j) * (hin[j] > 0)
         for (int j = p.n_tail - 1; j >= 0; --j) {
+            const float* hj = p.hin[j];
+            const long long ld = j == 0 ? p.ldh1 : (long long)TW_H;
+            float4 hv[8];                             // ReLU-mask tile, requested before the FMA block that hides it
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int m = m0 + ty + 8 * i;
+                hv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (m < p.M) hv[i] = ldg_f4_stream(hj + (size_t)m * ld + tx * 4);
+            }
             float acc[8][4];
 #pragma unroll
             for (int i = 0; i < 8; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; acc[i][2] = 0.f; acc[i][3] = 0.f; }
             tile_fma<TW_THREADS / 16>(As, Bs + j * TW_H * TW_H, ty, tx, acc);
             __syncthreads();                          // dz_{j+1} fully consumed
-            const float* hj = p.hin[j];
-            const long long ld = j == 0 ? p.ldh1 : (long long)TW_H;
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int r = ty + 8 * i, m = m0 + r;
                 float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (m < p.M) {
-                    const float4 hv = ldg_f4_stream(hj + (size_t)m * ld + tx * 4);
-                    d.x = hv.x > 0.f ? acc[i][0] : 0.f; d.y = hv.y > 0.f ? acc[i][1] : 0.f;
-                    d.z = hv.z > 0.f ? acc[i][2] : 0.f; d.w = hv.w > 0.f ? acc[i][3] : 0.f;
+                    d.x = hv[i].x > 0.f ? acc[i][0] : 0.f; d.y = hv[i].y > 0.f ? acc[i][1] : 0.f;
+                    d.z = hv[i].z > 0.f ? acc[i][2] : 0.f; d.w = hv[i].w > 0.f ? acc[i][3] : 0.f;
                     s0 += d.x; s1 += d.y; s2 += d.z; s3 += d.w;
                     stg_f4(p.dz[j] + (size_t)m * TW_H + tx * 4, d);
                 }
@@ -180,6 +232,7 @@ tower_tail_bwd_kernel(const TowerBwdParams p) {
             __syncthreads();
         }
     }
+    cp_async_wait_all();
     if (tx == 0 && dbo != 0.f) atomicAdd(&dbo_s, dbo);
     __syncthreads();
     if (tid < TW_H) {
@@ -276,13 +329,13 @@ RPB_API int rpb_tower_tail_bwd(const RpbTowerBwdDesc* d, void* stream) {
     p.pred = d->pred; p.label = d->label; p.gloss = d->gloss; p.eps = d->eps; p.scale = d->scale;
     p.dlogit_in = d->dlogit_in; p.dlogit_out = d->dlogit_out;
     p.M = d->M; p.n_tail = d->n_tail;
-    const size_t smem = (size_t)(TW_ROWS * TW_LDA + d->n_tail * TW_H * TW_H) * sizeof(float);
+    const size_t smem = (size_t)(2 * TW_ROWS * TW_LDA + d->n_tail * TW_H * TW_H) * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(tower_tail_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)      // 4 CTAs x ~50 KiB per SM only fit with the L1/shared split at its shared-memory maximum
         e = cudaFuncSetAttribute(tower_tail_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
     const int tiles = ceil_div(d->M, TW_ROWS);
-    tower_tail_bwd_kernel<<<min(tiles, 4 * sm_count()), TW_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    tower_tail_bwd_kernel<<<min(tiles, 3 * sm_count()), TW_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     RPB_LAUNCH_CHECK();
     return 0;
 }
