@@ -391,6 +391,54 @@ def run_ours(args):
                       'gpu_launches_per_step': tsteps[0].launches_per_step, 'loss_after': float(tsteps[0].loss.item())}
         del tsteps, opt
 
+    # ---------------- secondary legs (N = 1 only): Zipf(1.05)-distributed ids and stock PyTorch eager on the
+    # same GPU (the oracle's functional restatement of the reference forward run on CUDA tensors = the "existing Blackwell
+    # path" a user of the reference gets from `.to('cuda')`: F separate embedding lookups + stack + cat + addmm chain, dense
+    # [V+1, D] table gradients from autograd)
+    zipf = eager_gpu = None
+    if world == 1 and not args.no_extras:
+        import numpy as np
+        rng = np.random.default_rng(SEED)
+        zsteps = []
+        for i in range(2):
+            cb = ColumnarBatch(enc, B, device=dev, pinned_host=False)
+            d = synth_batch(enc, B, gen, device=dev)
+            for c in cb.sparse:
+                d[c] = torch.from_numpy(((rng.zipf(1.05, B) - 1) % (CFG['V'] + 1)).astype('int64')).to(dev)
+            cb.load_device(d)
+            zsteps.append(GraphedStep(model, cb, use_graph=use_graph))
+        for i in range(3):
+            zsteps[i % 2].replay()
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(args.steps):
+            zsteps[i % 2].replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_z = e0.elapsed_time(e1)
+        zipf = {'value': B * args.steps / (ms_z * 1e-3), 'unit': 'samples/s', 'ms_per_step': ms_z / args.steps,
+                'ids': 'zipf(1.05) - 1 mod (V+1) per field'}
+        del zsteps
+        import oracle
+        sd = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+        dd = cbs[0].as_dict()
+        n_e = 5
+        for it in range(2 + n_e):
+            if it == 2:
+                torch.cuda.synchronize()
+                e0.record()
+            out = oracle.deepfm(sd, enc, dd, hidden_units=tuple(CFG['hidden']))
+            out['loss'].backward()
+            for v in sd.values():
+                v.grad = None
+        e1.record()
+        torch.cuda.synchronize()
+        ms_e = e0.elapsed_time(e1)
+        eager_gpu = {'value': B * n_e / (ms_e * 1e-3), 'unit': 'samples/s', 'ms_per_step': ms_e / n_e,
+                     'what': 'stock PyTorch eager ops of the reference forward + autograd backward on the same B200 (fp32)'}
+        del sd, out
+        torch.cuda.empty_cache()
+
     line = {
         'metric': 'DeepFM samples/sec (forward+backward hot path)', 'value': value, 'unit': 'samples/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
@@ -403,7 +451,7 @@ def run_ours(args):
                    'gemm': {0: 'auto(tcgen05 3xTF32)', 1: 'simt fp32', 2: 'tcgen05 3xTF32'}[ops.get_gemm_impl()],
                    'grad_mode': 'persistent' if world == 1 else 'sharded'},
         'e2e': e2e, 'gpu_launches': launches_per_step * args.steps, 'clocks': clocks, 'roofline': roofline,
-        'train_step': train_step,
+        'train_step': train_step, 'zipf_ids': zipf, 'torch_eager_gpu_baseline': eager_gpu,
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
@@ -430,6 +478,7 @@ def main():
     ap.add_argument('--eager', action='store_true', help='time eager launches instead of CUDA-graph replays')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-train-step', action='store_true', help='skip the secondary forward+backward+optimizer timing')
+    ap.add_argument('--no-extras', action='store_true', help='skip the Zipf-id and stock-PyTorch-eager-GPU secondary timings')
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     if args.impl == 'reference':

@@ -161,6 +161,15 @@ int rpb_sigmoid_bce_fwd(const float* logit, const float* label, float* pred, flo
 int rpb_sigmoid_bce_bwd(const float* pred, const float* label, const float* gloss, float eps, float scale,
                         float* dlogit, int M, void* stream);
 
+/* ESSM head (multi_task/essm.py:50-75): click = sigmoid(z1), conv = sigmoid(z2),
+ * loss[0] = mean BCE(click*conv, y2) + w_ctr * mean BCE(click, y1)  (the reference feeds the PRODUCT to its loss while
+ * reporting conv as task2_pred; w_ctr = 0.5).  y1 / y2 / loss_out may be NULL (inference).  work as rpb_sigmoid_bce_fwd.
+ * bwd: dz1, dz2 = gloss[0] * dloss/dz (gloss NULL = 1), ATen clamps. */
+int rpb_essm_head_fwd(const float* z1, const float* z2, const float* y1, const float* y2, float* click, float* conv,
+                      float* loss_out, float w_ctr, int M, void* work, void* stream);
+int rpb_essm_head_bwd(const float* click, const float* conv, const float* y1, const float* y2, const float* gloss,
+                      float w_ctr, float* dz1, float* dz2, int M, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * MLP tower tail: the n_tail (0..RPB_TOWER_MAX_TAIL) square H x H hidden layers that follow the first layer, the
  * Linear(H -> 1) output layer, the logit sum, the sigmoid and the mean BCE in ONE launch (models/layers/deep.py:62-84

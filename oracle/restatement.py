@@ -18,7 +18,7 @@ __all__ = [
     "sparse_cols", "dense_cols", "embedding_layer", "get_linear_input", "fm_layer",
     "bi_interaction", "mlp", "lr_layer", "crossnet", "cin", "senet", "bilinear_field_interaction",
     "mhsa", "bce_mean", "deepfm", "xdeepfm", "autoint", "dcn", "fibinet", "fm", "wdl", "nfm", "mmoe",
-    "sharebottom", "omoe", "mlmmoe", "MODEL_FORWARDS",
+    "sharebottom", "omoe", "mlmmoe", "essm", "MODEL_FORWARDS",
 ]
 
 
@@ -312,7 +312,23 @@ def mlmmoe(sd, enc_dict, data, level_gates: List[torch.Tensor], gates: List[torc
     return _task_towers(sd, outs[:num_task], data, is_training, hidden_dim, bn_training)
 
 
+def essm(sd, enc_dict, data, is_training=True, hidden_dim=(128, 64), dropouts=(0.2, 0.2), w_ctr=0.5):
+    """ESSM.forward/.loss (models/multi_task/essm.py:38-75): two MLPs over the flattened embeddings (no dense part),
+    click / conversion = sigmoid; loss = BCE(click*conversion, task2_label) + 0.5 * BCE(click, task1_label) — the product
+    is what the reference hands to its loss as `conversion` (essm.py:52-56).  Dropout is identity (eval)."""
+    hidden = embedding_layer(sd, "embedding_layer", enc_dict, data).flatten(start_dim=1)
+    stride = 3 if any(p > 0 for p in dropouts) else 2
+    click = torch.sigmoid(mlp(sd, "ctr_layer", hidden, len(hidden_dim), stride))
+    conversion = torch.sigmoid(mlp(sd, "cvr_layer", hidden, len(hidden_dim), stride))
+    out = {'task1_pred': click, 'task2_pred': conversion}
+    if is_training:
+        pctrcvr = click * conversion
+        out['loss'] = F.binary_cross_entropy(pctrcvr.squeeze(-1), data['task2_label']) + \
+            w_ctr * F.binary_cross_entropy(click.squeeze(-1), data['task1_label'])
+    return out
+
+
 MODEL_FORWARDS = {
     'DeepFM': deepfm, 'xDeepFM': xdeepfm, 'AutoInt': autoint, 'DCN': dcn, 'FiBiNet': fibinet,
-    'FM': fm, 'WDL': wdl, 'NFM': nfm, 'MMOE': mmoe, 'ShareBottom': sharebottom, 'OMOE': omoe, 'MLMMOE': mlmmoe,
+    'FM': fm, 'WDL': wdl, 'NFM': nfm, 'MMOE': mmoe, 'ShareBottom': sharebottom, 'OMOE': omoe, 'MLMMOE': mlmmoe, 'ESSM': essm,
 }

@@ -7,7 +7,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'librec_pangu_b200.so')
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_FIELDS = 64
 MAX_DENSE = 64
 ERR_UNSUPPORTED = -1
@@ -80,6 +80,8 @@ SIGNATURES = {
     'rpb_rowdot_bwd': (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _vp, C.c_int, C.c_int, _vp]),
     'rpb_sigmoid_bce_fwd': (C.c_int, [_vp, _vp, _vp, _vp, _f32, _f32, C.c_int, _vp, _vp]),
     'rpb_sigmoid_bce_bwd': (C.c_int, [_vp, _vp, _vp, _f32, _f32, _vp, C.c_int, _vp]),
+    'rpb_essm_head_fwd': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, C.c_int, _vp, _vp]),
+    'rpb_essm_head_bwd': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, C.c_int, _vp]),
     'rpb_tower_tail_fwd': (C.c_int, [C.POINTER(TowerFwdDesc), _vp]),
     'rpb_linear_tower_fwd': (C.c_int, [_vp, _i64, _vp, _vp, C.c_int, C.POINTER(TowerFwdDesc), _vp]),
     'rpb_tower_tail_bwd': (C.c_int, [C.POINTER(TowerBwdDesc), _vp]),

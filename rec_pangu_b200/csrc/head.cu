@@ -61,6 +61,62 @@ sigmoid_bce_bwd_kernel(const float* __restrict__ pred, const float* __restrict__
     dlogit[m] = dp * p * (1.f - p);                  // sigmoid backward
 }
 
+// ESSM head (multi_task/essm.py:50-75): click = sigmoid(z1), conversion = sigmoid(z2), pctrcvr = click * conversion,
+// loss = mean BCE(pctrcvr, y2) + w * mean BCE(click, y1) — the reference passes the PRODUCT as the "conversion" argument of
+// its loss (essm.py:56,69-73) while reporting sigmoid(z2) as task2_pred.  Same ATen clamps as above.
+__global__ void __launch_bounds__(256)
+essm_head_fwd_kernel(const float* __restrict__ z1, const float* __restrict__ z2, const float* __restrict__ y1,
+                     const float* __restrict__ y2, float* __restrict__ click, float* __restrict__ conv,
+                     float* __restrict__ loss_out, float w, int M, unsigned int* counter, float* partials) {
+    __shared__ float red[32];
+    __shared__ bool is_last;
+    float acc = 0.f;
+    for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
+        const float c = 1.f / (1.f + expf(-__ldg(z1 + m)));
+        const float v = 1.f / (1.f + expf(-__ldg(z2 + m)));
+        click[m] = c;
+        conv[m] = v;
+        if (loss_out != nullptr) {
+            const float p = c * v, t1 = __ldg(y1 + m), t2 = __ldg(y2 + m);
+            acc += -(t2 * fmaxf(logf(p), -100.f) + (1.f - t2) * fmaxf(logf(1.f - p), -100.f));
+            acc += -w * (t1 * fmaxf(logf(c), -100.f) + (1.f - t1) * fmaxf(logf(1.f - c), -100.f));
+        }
+    }
+    if (loss_out == nullptr) return;
+    const float t = block_sum(acc, red);
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = t;
+        __threadfence();
+        const unsigned int done = atomicAdd(counter, 1u);
+        is_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        float s = 0.f;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) s += ((volatile float*)partials)[i];
+        s = block_sum(s, red);
+        if (threadIdx.x == 0) {
+            loss_out[0] = s / (float)M;
+            *counter = 0u;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+essm_head_bwd_kernel(const float* __restrict__ click, const float* __restrict__ conv, const float* __restrict__ y1,
+                     const float* __restrict__ y2, const float* __restrict__ gloss, float w, float* __restrict__ dz1,
+                     float* __restrict__ dz2, int M) {
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const float g = (gloss != nullptr ? __ldg(gloss) : 1.f) / (float)M;
+    const float c = __ldg(click + m), v = __ldg(conv + m), p = c * v;
+    const float dp = g * (p - __ldg(y2 + m)) / fmaxf((1.f - p) * p, 1e-12f);
+    const float dc = dp * v + w * g * (c - __ldg(y1 + m)) / fmaxf((1.f - c) * c, 1e-12f);
+    dz1[m] = dc * c * (1.f - c);
+    dz2[m] = dp * c * v * (1.f - v);
+}
+
 // counter-based RNG: keep(i) = u(seed, i) >= p, u uniform in [0,1) from splitmix64; recomputed in backward
 __device__ __forceinline__ float uniform01(unsigned long long seed, unsigned long long i) {
     unsigned long long z = seed + (i + 1ull) * 0x9E3779B97F4A7C15ull;
@@ -129,6 +185,28 @@ RPB_API int rpb_sigmoid_bce_bwd(const float* pred, const float* label, const flo
     if (pred == nullptr || label == nullptr || dlogit == nullptr || M <= 0) return RPB_ERR_BAD_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     sigmoid_bce_bwd_kernel<<<ceil_div(M, 256), 256, 0, st>>>(pred, label, gloss, eps, scale, dlogit, M);
+    RPB_LAUNCH_CHECK();
+    return 0;
+}
+
+RPB_API int rpb_essm_head_fwd(const float* z1, const float* z2, const float* y1, const float* y2, float* click,
+                              float* conv, float* loss_out, float w_ctr, int M, void* work, void* stream) {
+    if (z1 == nullptr || z2 == nullptr || click == nullptr || conv == nullptr || M <= 0) return RPB_ERR_BAD_ARG;
+    if (loss_out != nullptr && (y1 == nullptr || y2 == nullptr || work == nullptr)) return RPB_ERR_BAD_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int grid = min(kHeadMaxBlocks, ceil_div(M, 256));
+    essm_head_fwd_kernel<<<grid, 256, 0, st>>>(z1, z2, y1, y2, click, conv, loss_out, w_ctr, M,
+                                               reinterpret_cast<unsigned int*>(work), reinterpret_cast<float*>(work) + 2);
+    RPB_LAUNCH_CHECK();
+    return 0;
+}
+
+RPB_API int rpb_essm_head_bwd(const float* click, const float* conv, const float* y1, const float* y2, const float* gloss,
+                              float w_ctr, float* dz1, float* dz2, int M, void* stream) {
+    if (click == nullptr || conv == nullptr || y1 == nullptr || y2 == nullptr || dz1 == nullptr || dz2 == nullptr || M <= 0)
+        return RPB_ERR_BAD_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    essm_head_bwd_kernel<<<ceil_div(M, 256), 256, 0, st>>>(click, conv, y1, y2, gloss, w_ctr, dz1, dz2, M);
     RPB_LAUNCH_CHECK();
     return 0;
 }

@@ -1,9 +1,10 @@
 """Multi-task models (reference: rec_pangu/models/multi_task/__init__.py).  MMOE is the north-star config 5; ShareBottom,
-OMOE and MLMMOE reuse its kernels (gather, [K,N] GEMM, gate-softmax/combine, BatchNorm towers, sigmoid+BCE)."""
+OMOE, MLMMOE and ESSM reuse its kernels (gather, [K,N] GEMM, gate-softmax/combine, BatchNorm towers, sigmoid+BCE)."""
 from .mmoe import MMOE
 from .sharebottom import ShareBottom
 from .omoe import OMOE
 from .mlmmoe import MLMMOE
+from .essm import ESSM
 
 
 def _unported(name):
@@ -15,4 +16,3 @@ def _unported(name):
 
 
 AITM = _unported('AITM')
-ESSM = _unported('ESSM')

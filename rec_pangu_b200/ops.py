@@ -12,7 +12,7 @@ import torch
 from . import _lib
 from ._lib import GatherDesc, ScatterDesc, TowerFwdDesc, TowerBwdDesc, check
 
-__all__ = ['GradStore', 'hash_to_row', 'deepfm_core', 'gather', 'gather_sharded', 'sharded_clean', 'fm_interaction', 'mlp_forward', 'sigmoid_bce', 'linear', 'feature_row_stride',
+__all__ = ['GradStore', 'hash_to_row', 'essm_head', 'deepfm_core', 'gather', 'gather_sharded', 'sharded_clean', 'fm_interaction', 'mlp_forward', 'sigmoid_bce', 'linear', 'feature_row_stride',
            'check_index_errors', 'set_gemm_impl', 'get_gemm_impl', 'launch_count', 'reset_launch_count']
 
 _GEMM_IMPL = int(__import__('os').environ.get('RPB_GEMM_IMPL', '0'))   # 0 auto, 1 SIMT fp32, 2 tcgen05 3xTF32
@@ -1152,6 +1152,52 @@ def sigmoid_bce(logit: torch.Tensor, label: Optional[torch.Tensor], eps: float =
         return _SigmoidBCE.apply(logit, None, eps, scale), None
     _cuda(label, 'label')
     return _SigmoidBCE.apply(logit, label, eps, scale)
+
+
+class _ESSMHead(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z1, z2, y1, y2, w):
+        M = z1.numel()
+        a, b = z1.reshape(-1).contiguous(), z2.reshape(-1).contiguous()
+        click = torch.empty((M,), dtype=torch.float32, device=z1.device)
+        conv = torch.empty_like(click)
+        has_label = y1 is not None
+        loss = torch.empty((), dtype=torch.float32, device=z1.device) if has_label else None
+        t1 = y1.reshape(-1).contiguous().float() if has_label else None
+        t2 = y2.reshape(-1).contiguous().float() if has_label else None
+        check(_lib.load().rpb_essm_head_fwd(_ptr(a), _ptr(b), _ptr(t1), _ptr(t2), _ptr(click), _ptr(conv), _ptr(loss), w, M,
+                                            _ptr(_head_work(z1.device)), _stream()), 'rpb_essm_head_fwd')
+        _count()
+        ctx.set_materialize_grads(False)
+        ctx.w, ctx.shape, ctx.has_label = w, z1.shape, has_label
+        if has_label:
+            ctx.save_for_backward(click, conv, t1, t2)
+        c_out, v_out = click.view(z1.shape), conv.view(z2.shape)
+        ctx.mark_non_differentiable(c_out, v_out)
+        return (c_out, v_out, loss) if has_label else (c_out, v_out)
+
+    @staticmethod
+    def backward(ctx, gc, gv, gloss=None):
+        if not ctx.has_label or gloss is None:
+            return None, None, None, None, None
+        click, conv, t1, t2 = ctx.saved_tensors
+        M = click.numel()
+        dz1, dz2 = torch.empty_like(click), torch.empty_like(click)
+        gl = gloss.reshape(1).contiguous().float()
+        check(_lib.load().rpb_essm_head_bwd(_ptr(click), _ptr(conv), _ptr(t1), _ptr(t2), _ptr(gl), ctx.w, _ptr(dz1), _ptr(dz2),
+                                            M, _stream()), 'rpb_essm_head_bwd')
+        _count()
+        return dz1.view(ctx.shape), dz2.view(ctx.shape), None, None, None
+
+
+def essm_head(z1: torch.Tensor, z2: torch.Tensor, y1: Optional[torch.Tensor] = None, y2: Optional[torch.Tensor] = None,
+              w_ctr: float = 0.5):
+    """ESSM head (multi_task/essm.py:50-75): (click, conversion[, loss]) with click = sigmoid(z1), conversion = sigmoid(z2),
+    loss = mean BCE(click * conversion, y2) + w_ctr * mean BCE(click, y1).  The predictions are outputs only (gradients
+    flow through the loss)."""
+    _cuda(z1, 'ctr logit')
+    _cuda(z2, 'cvr logit')
+    return _ESSMHead.apply(z1, z2, y1, y2, float(w_ctr))
 
 
 # ------------------------------------------------------------------ DCN CrossNet

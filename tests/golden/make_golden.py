@@ -30,7 +30,7 @@ sys.path.insert(0, '/root/reference')
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 from rec_pangu.models.ranking import DeepFM, xDeepFM, AutoInt, DCN, FiBiNet, FM, WDL, NFM  # noqa: E402
-from rec_pangu.models.multi_task import MMOE, ShareBottom, OMOE, MLMMOE  # noqa: E402
+from rec_pangu.models.multi_task import MMOE, ShareBottom, OMOE, MLMMOE, ESSM  # noqa: E402
 from rec_pangu.models.layers import (FM_Layer, MLP, CrossNet, CompressedInteractionNet, SENET_Layer,  # noqa: E402
                                      BilinearInteractionLayer, MultiHeadSelfAttention, InnerProductLayer)
 
@@ -199,7 +199,26 @@ def run_layers(seed=7):
     print('layers saved')
 
 
+def run_essm(seed=1029):
+    """ESSM (multi_task/essm.py), eval mode (its MLPs carry Dropout(0.2) modules)."""
+    torch.manual_seed(seed)
+    gen = torch.Generator().manual_seed(seed)
+    enc = make_enc(4, 2, [17, 50, 97, 9])
+    kwargs = {'hidden_dim': [16, 8], 'dropouts': [0.2, 0.2]}
+    model = ESSM(embedding_dim=8, enc_dict=enc, device='cpu', **kwargs)
+    with torch.no_grad():
+        for k, p in model.named_parameters():
+            if p.dim() == 1:
+                p.copy_(torch.randn(p.shape, generator=gen) * 0.1)
+    model.eval()
+    data = make_batch(enc, 48, gen, labels=('task1_label', 'task2_label'))
+    out = model(data)
+    out['loss'].backward()
+    save('essm', model, enc, data, out, meta={'model': 'ESSM', 'kwargs': kwargs, 'D': 8})
+
+
 def run_multitask_all():
+    run_essm()
     tw = {'dropouts': [0.0, 0.0]}
     for bn in (False, True):
         sfx = '_train' if bn else '_eval'

@@ -172,6 +172,31 @@ def test_multitask_family_matches_reference_golden(name):
     assert set(out2.keys()) == {'task1_pred', 'task2_pred'}
 
 
+def test_essm_matches_reference_golden():
+    """ESSM (multi_task/essm.py): two MLP towers + the entire-space loss head kernel vs the reference fixture."""
+    from rec_pangu_b200.models.multi_task import ESSM
+    g = load_golden('essm')
+    m = g['meta']
+    model = ESSM(embedding_dim=m['D'], enc_dict=m['enc_dict'], device='cpu', **m['kwargs'])
+    assert set(model.state_dict().keys()) == set(g['sd'].keys())
+    model.load_state_dict(g['sd'])
+    model = model.cuda().eval()
+    data = {k: v.cuda() for k, v in g['data'].items()}
+    out = model(data)
+    (out['loss'] * 2.0).backward()
+    for k in ('task1_pred', 'task2_pred'):
+        assert out[k].shape == g['out'][k].shape
+        torch.testing.assert_close(out[k].cpu(), g['out'][k], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(out['loss'].cpu(), g['out']['loss'], rtol=1e-5, atol=1e-6)
+    grads = dict(model.named_parameters())
+    for k, ref in g['grad'].items():
+        assert grads[k].grad is not None, k
+        assert_close_rel(grads[k].grad, 2.0 * ref, 2e-4, k)
+    out2 = model(data, is_training=False)
+    assert set(out2.keys()) == {'task1_pred', 'task2_pred'}
+    assert torch.equal(out2['task1_pred'], out['task1_pred']) and torch.equal(out2['task2_pred'], out['task2_pred'])
+
+
 def test_persistent_grad_mode_equals_dense_mode():
     from rec_pangu_b200.models.ranking import DeepFM
     from rec_pangu_b200 import ops
