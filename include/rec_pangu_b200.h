@@ -284,6 +284,15 @@ int rpb_bn_apply(const float* x, const float* mean, const float* invstd, const f
                  float* y, int M, int N, void* stream);
 int rpb_bn_bwd(const float* dy, const float* x, const float* mean, const float* invstd, const float* gamma,
                float* dx, float* dgamma, float* dbeta, int M, int N, int use_batch_stats, void* stream);
+/* The two halves of rpb_bn_bwd, for batch statistics that span several GPUs (BatchNorm1d needs cross-GPU
+ * batch statistics for parity with the single-process reference): rpb_bn_bwd_stats accumulates the LOCAL column sums
+ * (these are also the parameter gradients of this rank's samples), the caller all-reduces them, rpb_bn_bwd_dx applies
+ * dx = gamma*invstd*(dy - dbeta_sum*inv_count - xhat*dgamma_sum*inv_count) with inv_count = 1 / (global sample count). */
+int rpb_bn_bwd_stats(const float* dy, const float* x, const float* mean, const float* invstd, float* dgamma,
+                     float* dbeta, int M, int N, void* stream);
+int rpb_bn_bwd_dx(const float* dy, const float* x, const float* mean, const float* invstd, const float* gamma,
+                  const float* dgamma_sum, const float* dbeta_sum, float* dx, int M, int N, float inv_count,
+                  int use_batch_stats, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * FiBiNet interaction (ranking/fibinet.py:59-66): SENET_Layer (interaction.py:238-251) + BilinearInteractionLayer

@@ -7,7 +7,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'librec_pangu_b200.so')
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_FIELDS = 64
 MAX_DENSE = 64
 ERR_UNSUPPORTED = -1
@@ -102,6 +102,8 @@ SIGNATURES = {
     'rpb_bn_stats': (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     'rpb_bn_apply': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     'rpb_bn_bwd': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+    'rpb_bn_bwd_stats': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
+    'rpb_bn_bwd_dx': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _f32, C.c_int, _vp]),
     'rpb_fibinet_fwd': (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _i64, _vp, _vp]),
     'rpb_fibinet_bwd': (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _i64, _vp, _i64,
                                   _vp, _vp, _vp, _vp]),

@@ -42,7 +42,7 @@ void* workspace(int slot, size_t bytes, int* err) {
 
 }  // namespace rpb
 
-RPB_API int rpb_version(void) { return 6; }
+RPB_API int rpb_version(void) { return 7; }
 
 RPB_API const char* rpb_error_string(int code) {
     switch (code) {

@@ -278,15 +278,32 @@ RPB_API int rpb_bn_apply(const float* x, const float* mean, const float* invstd,
     return 0;
 }
 
+RPB_API int rpb_bn_bwd_stats(const float* dy, const float* x, const float* mean, const float* invstd, float* dgamma,
+                             float* dbeta, int M, int N, void* stream) {
+    if (dy == nullptr || x == nullptr || mean == nullptr || invstd == nullptr || dgamma == nullptr || dbeta == nullptr || M <= 0)
+        return RPB_ERR_BAD_ARG;
+    dim3 grid; int slab;
+    stats_grid(M, N, grid, slab);
+    bn_bwd_stats_kernel<<<grid, dim3(32, 8), 0, reinterpret_cast<cudaStream_t>(stream)>>>(dy, x, mean, invstd, dbeta, dgamma, M, N, slab);
+    RPB_LAUNCH_CHECK();
+    return 0;
+}
+
+RPB_API int rpb_bn_bwd_dx(const float* dy, const float* x, const float* mean, const float* invstd, const float* gamma,
+                          const float* dgamma_sum, const float* dbeta_sum, float* dx, int M, int N, float inv_count,
+                          int use_batch_stats, void* stream) {
+    if (dy == nullptr || x == nullptr || dx == nullptr || gamma == nullptr || invstd == nullptr || M <= 0) return RPB_ERR_BAD_ARG;
+    if (use_batch_stats && (dgamma_sum == nullptr || dbeta_sum == nullptr || mean == nullptr)) return RPB_ERR_BAD_ARG;
+    bn_bwd_dx_kernel<<<ceil_div((long long)M * N, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        dy, x, mean, invstd, gamma, dbeta_sum, dgamma_sum, dx, (long long)M * N, N, inv_count, use_batch_stats);
+    RPB_LAUNCH_CHECK();
+    return 0;
+}
+
 RPB_API int rpb_bn_bwd(const float* dy, const float* x, const float* mean, const float* invstd, const float* gamma,
                        float* dx, float* dgamma, float* dbeta, int M, int N, int use_batch_stats, void* stream) {
     if (dy == nullptr || x == nullptr || dx == nullptr || dgamma == nullptr || dbeta == nullptr || M <= 0) return RPB_ERR_BAD_ARG;
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    dim3 grid; int slab;
-    stats_grid(M, N, grid, slab);
-    bn_bwd_stats_kernel<<<grid, dim3(32, 8), 0, st>>>(dy, x, mean, invstd, dbeta, dgamma, M, N, slab);
-    bn_bwd_dx_kernel<<<ceil_div((long long)M * N, 256), 256, 0, st>>>(dy, x, mean, invstd, gamma, dbeta, dgamma, dx,
-                                                                    (long long)M * N, N, 1.f / (float)M, use_batch_stats);
-    RPB_LAUNCH_CHECK();
-    return 0;
+    int rc = rpb_bn_bwd_stats(dy, x, mean, invstd, dgamma, dbeta, M, N, stream);
+    if (rc == 0) rc = rpb_bn_bwd_dx(dy, x, mean, invstd, gamma, dgamma, dbeta, dx, M, N, 1.f / (float)M, use_batch_stats, stream);
+    return rc;
 }

@@ -152,6 +152,14 @@ class ShardedTables:
         return unshard(shards, self.rows[f])
 
 
+def enable_sync_batchnorm(group=None, enabled: bool = True):
+    """BatchNorm1d layers of the hot path (multi-task towers) normalise with the statistics of the GLOBAL batch: the
+    [sum | sum of squares | count] vector in forward and the [dgamma | dbeta] column sums in backward are all-reduced over
+    `group` (needed for parity with the single-process reference under data parallelism)."""
+    from . import ops
+    ops.SYNC_BN_GROUP = (group if group is not None else dist.group.WORLD) if enabled else None
+
+
 def shard_model_tables(model, group=None) -> ShardedTables:
     """Convert `model.embedding_layer` to row-sharded peer-memory tables (every rank must hold identical full tables
     when this is called, e.g. same seed).  The full tables are released afterwards."""

@@ -1412,20 +1412,33 @@ def mmoe_combine(eo: torch.Tensor, Hh: int, E: int, T: int) -> torch.Tensor:
     return _MMOECombine.apply(_rowmajor(eo), Hh, E, T)
 
 
+# Process group over which BatchNorm batch statistics are shared (None = per-process statistics, the single-GPU case).
+# Set by rec_pangu_b200.dist.enable_sync_batchnorm(); with it the data-parallel towers normalise with the statistics of
+# the GLOBAL batch, i.e. exactly what the single-process reference computes on the concatenated batch.
+SYNC_BN_GROUP = None
+
+
 class _BatchNorm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, running_mean, running_var, training, momentum, eps):
         M, N = x.shape
         lib, st = _lib.load(), _stream()
+        group = SYNC_BN_GROUP if training else None
+        count = float(M)
         if training:
-            stats = torch.zeros((2, N), dtype=torch.float32, device=x.device)
-            check(lib.rpb_bn_stats(_ptr(x), M, N, _ptr(stats[0]), _ptr(stats[1]), st), 'rpb_bn_stats')
+            stats = torch.zeros((2 * N + 1,), dtype=torch.float32, device=x.device)
+            check(lib.rpb_bn_stats(_ptr(x), M, N, _ptr(stats[:N]), _ptr(stats[N:2 * N]), st), 'rpb_bn_stats')
             _count()
-            mean = stats[0] / M
-            var = (stats[1] / M - mean * mean).clamp_min_(0.0)           # biased (normalisation) variance; [N]-sized plumbing
+            if group is not None:
+                import torch.distributed as dist
+                stats[2 * N] = float(M)
+                dist.all_reduce(stats, group=group)                  # sums, sums of squares and the sample count
+                count = float(M) * dist.get_world_size(group)        # equal per-rank batches (weak scaling)
+            mean = stats[:N] / count
+            var = (stats[N:2 * N] / count - mean * mean).clamp_min_(0.0)     # biased (normalisation) variance; [N]-sized plumbing
             with torch.no_grad():
                 running_mean.mul_(1 - momentum).add_(mean, alpha=momentum)
-                running_var.mul_(1 - momentum).add_(var * (M / max(M - 1, 1)), alpha=momentum)
+                running_var.mul_(1 - momentum).add_(var * (count / max(count - 1, 1)), alpha=momentum)
         else:
             mean, var = running_mean, running_var
         invstd = torch.rsqrt(var + eps)
@@ -1433,7 +1446,7 @@ class _BatchNorm(torch.autograd.Function):
         check(lib.rpb_bn_apply(_ptr(x), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(beta), _ptr(y), M, N, st), 'rpb_bn_apply')
         _count()
         ctx.save_for_backward(x, gamma, mean.contiguous(), invstd)
-        ctx.training = training
+        ctx.training, ctx.group, ctx.count = training, group, count
         return y
 
     @staticmethod
@@ -1441,11 +1454,23 @@ class _BatchNorm(torch.autograd.Function):
         x, gamma, mean, invstd = ctx.saved_tensors
         M, N = x.shape
         g = g.contiguous()
+        lib, st = _lib.load(), _stream()
         dx = torch.empty_like(x)
-        dgb = torch.zeros((2, N), dtype=torch.float32, device=x.device)
-        check(_lib.load().rpb_bn_bwd(_ptr(g), _ptr(x), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(dx), _ptr(dgb[0]),
-                                     _ptr(dgb[1]), M, N, 1 if ctx.training else 0, _stream()), 'rpb_bn_bwd')
+        dgb = torch.zeros((2, N), dtype=torch.float32, device=x.device)        # [dgamma ; dbeta] of THIS rank's samples
+        if ctx.group is None:
+            check(lib.rpb_bn_bwd(_ptr(g), _ptr(x), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(dx), _ptr(dgb[0]),
+                                 _ptr(dgb[1]), M, N, 1 if ctx.training else 0, st), 'rpb_bn_bwd')
+            _count(2)
+            return dx, dgb[0], dgb[1], None, None, None, None, None
+        import torch.distributed as dist
+        check(lib.rpb_bn_bwd_stats(_ptr(g), _ptr(x), _ptr(mean), _ptr(invstd), _ptr(dgb[0]), _ptr(dgb[1]), M, N, st),
+              'rpb_bn_bwd_stats')
+        tot = dgb.clone()
+        dist.all_reduce(tot, group=ctx.group)                                  # column sums over the global batch
+        check(lib.rpb_bn_bwd_dx(_ptr(g), _ptr(x), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(tot[0]), _ptr(tot[1]), _ptr(dx),
+                                M, N, 1.0 / ctx.count, 1, st), 'rpb_bn_bwd_dx')
         _count(2)
+        # parameter gradients stay the local sums: the dense-gradient all-reduce (dist.DenseGradBucket) adds the ranks
         return dx, dgb[0], dgb[1], None, None, None, None, None
 
 

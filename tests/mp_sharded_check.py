@@ -69,11 +69,68 @@ def check(rank, world, dev, hidden):
     dist.barrier()
 
 
+def check_mmoe_sync_bn(rank, world, dev):
+    """MMOE in train mode (BatchNorm towers use BATCH statistics): data-parallel ranks with cross-GPU statistics
+    (dist.enable_sync_batchnorm) == the single-process model on the concatenated batch."""
+    from rec_pangu_b200.models.multi_task import MMOE
+    enc = make_enc(5, 2, [101, 57, 33, 200, 17])
+    B = 64
+    kw = dict(embedding_dim=8, enc_dict=enc, mmoe_hidden_dim=16, hidden_dim=[16, 8], dropouts=[0.0, 0.0], device='cpu')
+    torch.manual_seed(11)
+    ref = MMOE(**kw)
+    with torch.no_grad():
+        for n, p in ref.named_parameters():
+            if 'embedding_layer' in n:
+                p.mul_(0.3)
+            elif n in ('experts', 'experts_bias'):
+                p.mul_(0.3)
+    sd = {k: v.clone() for k, v in ref.state_dict().items()}
+    gates = [g.detach().clone() for g in ref.gates]
+    gates_bias = [g.detach().clone() for g in ref.gates_bias]
+    model = MMOE(**kw)
+    model.load_state_dict(sd)
+    with torch.no_grad():
+        for i in range(2):
+            model.gates[i].copy_(gates[i])
+            model.gates_bias[i].copy_(gates_bias[i])
+    ref, model = ref.to(dev).train(), model.to(dev).train()
+    st = rdist.shard_model_tables(model)
+    bucket = rdist.DenseGradBucket([p for n, p in model.named_parameters() if not n.startswith('embedding_layer.')])
+    full = make_batch(enc, B * world, seed=9, labels=('task1_label', 'task2_label'), device=dev)
+    mine = {k: v[rank * B:(rank + 1) * B].contiguous() for k, v in full.items()}
+    rdist.enable_sync_batchnorm(enabled=False)
+    ro = ref(full)
+    ro['loss'].backward()
+    rdist.enable_sync_batchnorm()
+    out = model(mine)
+    (out['loss'] / world).backward()
+    bucket.all_reduce()
+    rdist.enable_sync_batchnorm(enabled=False)
+    ops.check_index_errors(dev)
+    for k in ('task1_pred', 'task2_pred'):
+        torch.testing.assert_close(out[k], ro[k][rank * B:(rank + 1) * B], rtol=1e-4, atol=1e-5, msg=lambda s: f'{k}: {s}')
+    ref_grads = {n: p.grad for n, p in ref.named_parameters()}
+    for n, p in model.named_parameters():
+        if not n.startswith('embedding_layer.'):
+            r = ref_grads[n]
+            err = (p.grad - r).abs().max().item()
+            assert err <= 2e-4 * max(1e-6, r.abs().max().item()) + 1e-7, (n, err)
+    for k, v in model.state_dict().items():
+        if 'running_mean' in k or 'running_var' in k:
+            torch.testing.assert_close(v, ref.state_dict()[k], rtol=1e-4, atol=1e-6, msg=lambda s: f'{k}: {s}')
+    g_full = st.full_grad(2)
+    r_full = ref.embedding_layer.embedding_layer['C3'].weight.grad
+    assert (g_full - r_full).abs().max().item() <= 2e-4 * max(1e-6, r_full.abs().max().item()) + 1e-8
+    model.zero_grad()
+    dist.barrier()
+
+
 def main():
     rank, world, local = rdist.init_from_env('nccl')
     dev = torch.device('cuda', local)
     for hidden in ([16, 8], [64, 64]):
         check(rank, world, dev, hidden)
+    check_mmoe_sync_bn(rank, world, dev)
     if rank == 0:
         print('SHARDED_OK world', world, flush=True)
     torch.cuda.synchronize()
