@@ -38,13 +38,25 @@ class RankTrainer:
 
     def fit(self, model, train_loader, valid_loader: Optional = None, epoch: int = 10, lr: float = 1e-3,
             device: torch.device = torch.device('cpu'), use_earlystopping: bool = False, max_patience: int = 999,
-            monitor_metric: Optional[str] = None, lr_scheduler_type: str = "", scheduler_params: Optional[dict] = {}):
+            monitor_metric: Optional[str] = None, lr_scheduler_type: str = "", scheduler_params: Optional[dict] = {},
+            optimizer_type: str = 'adam'):
+        """Same arguments as the reference (trainer.py:51-61) plus `optimizer_type`: 'adam' = torch.optim.Adam over the dense
+        gradients exactly as the reference (trainer.py:75), 'fused_adam' = rec_pangu_b200.optim.FusedAdam (row-sparse Adam
+        on the touched table rows, dense parameters in one launch; lazy-Adam semantics on untouched rows)."""
         if self.use_wandb:
             import wandb
             wandb.init(**self.wandb_config)
         device = _compute_device(device)
         model = model.to(device)
-        optimizer = torch.optim.Adam(model.parameters(), lr=lr, betas=(0.9, 0.999), eps=1e-08, weight_decay=0)
+        if optimizer_type == 'fused_adam':
+            if lr_scheduler_type != "":
+                raise ValueError('lr schedulers drive torch.optim optimizers; use optimizer_type="adam" with a scheduler')
+            from .optim import FusedAdam
+            optimizer = FusedAdam(model, lr=lr, betas=(0.9, 0.999), eps=1e-08)
+        elif optimizer_type == 'adam':
+            optimizer = torch.optim.Adam(model.parameters(), lr=lr, betas=(0.9, 0.999), eps=1e-08, weight_decay=0)
+        else:
+            raise ValueError(f'Unknown optimizer_type: {optimizer_type}')
         if lr_scheduler_type == 'StepLR':
             scheduler = lr_scheduler.StepLR(optimizer, **scheduler_params)
         elif lr_scheduler_type == 'ExponentialLR':

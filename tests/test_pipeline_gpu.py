@@ -65,3 +65,49 @@ def test_multitask_flow_mmoe(tmp_path):
     assert set(m.keys()) == {'test_task1_roc_auc_score', 'test_task1_log_loss', 'test_task2_roc_auc_score', 'test_task2_log_loss'}
     preds = trainer.predict_dataframe(model, df[:380], enc, schema, device=torch.device('cuda'))
     assert len(preds) == 2 and len(preds[0]) == 380
+
+
+def test_batch_stager_packs_columns_and_survives_reuse():
+    """model_pipeline._to_device: one pinned staging buffer + one H2D copy per dtype; device views of consecutive batches
+    stay intact while they are in use (double buffering), values are bit-identical to per-key .to(device)."""
+    from rec_pangu_b200.model_pipeline import _BatchStager
+    st = _BatchStager()
+    dev = torch.device('cuda', torch.cuda.current_device())
+    g = torch.Generator().manual_seed(0)
+    batches = []
+    for b in range(5):
+        n = 512 if b < 4 else 77                                     # last batch is ragged
+        d = {f's{i}': torch.randint(0, 1000, (n,), generator=g) for i in range(6)}
+        d.update({f'd{i}': torch.rand(n, generator=g) for i in range(3)})
+        d['label'] = (torch.rand(n, generator=g) < 0.3).float()
+        batches.append(d)
+    prev = None
+    for d in batches:
+        ref = {k: v.clone() for k, v in d.items()}
+        out = st(dict(d), dev)
+        assert list(out.keys()) == list(ref.keys())
+        for k in ref:
+            assert out[k].is_cuda and out[k].dtype == ref[k].dtype and torch.equal(out[k].cpu(), ref[k])
+        if prev is not None:                                          # the previous batch's views were not overwritten
+            for k in prev[1]:
+                assert torch.equal(prev[0][k].cpu(), prev[1][k])
+        prev = (out, ref)
+    # two int64 columns of one batch are rows of ONE device buffer
+    o = st({k: v for k, v in batches[0].items()}, dev)
+    assert o['s1'].data_ptr() - o['s0'].data_ptr() == 512 * 8
+
+
+def test_trainer_with_fused_adam(tmp_path):
+    from rec_pangu.dataset import get_dataloader
+    from rec_pangu.models.ranking import DeepFM
+    from rec_pangu.trainer import RankTrainer
+    df, schema = _frame()
+    train_loader, valid_loader, _, enc_dict = get_dataloader(df[:240], df[:270], df[:285], schema, batch_size=512)
+    torch.manual_seed(0)
+    model = DeepFM(embedding_dim=8, enc_dict=enc_dict)
+    trainer = RankTrainer(num_task=1, model_ckpt_dir=str(tmp_path))
+    m = trainer.fit(model, train_loader, valid_loader, epoch=12, lr=1e-2, device=torch.device('cuda'), optimizer_type='fused_adam')
+    assert m['roc_auc_score'] > 0.7
+    with pytest.raises(ValueError):
+        trainer.fit(model, train_loader, valid_loader, epoch=1, optimizer_type='fused_adam', lr_scheduler_type='StepLR',
+                    scheduler_params={'step_size': 1})
