@@ -197,6 +197,15 @@ int rpb_tower_tail_fwd(const RpbTowerFwdDesc* d, void* stream);
  * rpb_linear_fwd + rpb_tower_tail_fwd). */
 int rpb_linear_tower_fwd(const float* x, int64_t ldx, const float* W1, const float* b1, int K,
                          const RpbTowerFwdDesc* d, void* stream);
+/* DeepFM forward in ONE launch (ranking/deepfm.py:41-67): the gather + dense pack + FM second order of rpb_gather_fwd, the
+ * layer-1 GEMM and rpb_tower_tail_fwd, overlapped inside one persistent tcgen05 kernel — the GEMM's operand warps fetch
+ * their own table rows with cp.async (the random-row DRAM latency hides behind the tensor / tail work of the previous
+ * k-blocks) and the FM term is formed from the registers that feed the MMAs.  Uses of `g`: B, F, D (= 16), Nd, tables,
+ * rows, idx, dense, err; x / fm / fm_s are OPTIONAL outputs (x and fm_s only when backward needs them; ldx as for
+ * rpb_gather_fwd).  `d` as for rpb_linear_tower_fwd (d->h1 is an output, d->addend is ignored: the FM term is added inside).
+ * Needs D == 16, an even F, unsharded tables, n_tail >= 1, M >= 512; RPB_ERR_UNSUPPORTED otherwise (the caller then runs
+ * rpb_gather_fwd + rpb_linear_tower_fwd). */
+int rpb_deepfm_fwd_fused(const RpbGatherDesc* g, const float* W1, const float* b1, const RpbTowerFwdDesc* d, void* stream);
 /* Backward of rpb_tower_tail_fwd.  hin: HOST array of n_tail+1 device pointers, hin[0] = h1 (row stride ldh1),
  * hin[j] = h[j-1] ([M, H] contiguous).  dlogit[m] = dlogit_in[m] when given, else gloss[0]*scale/M * dBCE/dp * p(1-p)
  * from (pred, label) with ATen's clamps (gloss NULL = 1); it is written to dlogit_out when non-NULL.

@@ -7,7 +7,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'librec_pangu_b200.so')
-ABI_VERSION = 7
+ABI_VERSION = 8
 MAX_FIELDS = 64
 MAX_DENSE = 64
 ERR_UNSUPPORTED = -1
@@ -84,6 +84,7 @@ SIGNATURES = {
     'rpb_essm_head_bwd': (C.c_int, [_vp, _vp, _vp, _vp, _vp, _f32, _vp, _vp, C.c_int, _vp]),
     'rpb_tower_tail_fwd': (C.c_int, [C.POINTER(TowerFwdDesc), _vp]),
     'rpb_linear_tower_fwd': (C.c_int, [_vp, _i64, _vp, _vp, C.c_int, C.POINTER(TowerFwdDesc), _vp]),
+    'rpb_deepfm_fwd_fused': (C.c_int, [C.POINTER(GatherDesc), _vp, _vp, C.POINTER(TowerFwdDesc), _vp]),
     'rpb_tower_tail_bwd': (C.c_int, [C.POINTER(TowerBwdDesc), _vp]),
     'rpb_dropout_fwd': (C.c_int, [_vp, _vp, _i64, _f32, C.c_uint64, _vp]),
     'rpb_dropout_bwd': (C.c_int, [_vp, _vp, _vp, _i64, _f32, C.c_uint64, _vp]),

@@ -8,6 +8,7 @@ namespace rpb {
 int g_gather_policy = 1;
 int g_gather_kernel = 0;
 int g_wgrad_tc = 1;
+int g_scatter_reverse = 1;
 int g_wgrad_stages = 2;     // 2 stages = 2 CTAs per SM: measured faster than 4 stages x 1 CTA (16.9 vs 22.6 us on the 64x64 layers)
 int g_gemm_v2 = 1;
 int g_gemm_a_tmem = 1;
@@ -42,7 +43,7 @@ void* workspace(int slot, size_t bytes, int* err) {
 
 }  // namespace rpb
 
-RPB_API int rpb_version(void) { return 7; }
+RPB_API int rpb_version(void) { return 8; }
 
 RPB_API const char* rpb_error_string(int code) {
     switch (code) {
@@ -67,6 +68,7 @@ RPB_API int rpb_set_option(const char* name, int64_t value) {
     if (n == "gemm_stack_n") { rpb::g_gemm_stack_n = value != 0; return 0; }
     if (n == "tf32_raw_hi") { rpb::g_tf32_raw_hi = value != 0; return 0; }
     if (n == "wgrad_tc") { rpb::g_wgrad_tc = value != 0; return 0; }
+    if (n == "scatter_reverse") { rpb::g_scatter_reverse = value != 0; return 0; }
     if (n == "wgrad_stages") { if (value < 2 || value > 4) return RPB_ERR_BAD_ARG; rpb::g_wgrad_stages = (int)value; return 0; }
     if (n == "gather_kernel") {
         if (value < 0 || value > 1) return RPB_ERR_BAD_ARG;

@@ -23,6 +23,7 @@ extern int g_gemm_v2;                                // api.cu: 1 = persistent G
 extern int g_gemm_a_tmem;                            // api.cu: 1 = v2 GEMM keeps the split A operand in tensor memory (TS-mode MMA)
 extern int g_gemm_stack_n;                           // api.cu: 1 = narrow layers run [B hi ; B lo] as one N = 2*block_n operand
 extern int g_tf32_raw_hi;                            // api.cu: 1 = feed unmasked fp32 as the tf32 'hi' operand (the tensor core ignores the low 13 mantissa bits)
+extern int g_scatter_reverse;                        // api.cu: 1 = fused dx+scatter GEMM walks the sample tiles back to front
 extern int g_wgrad_stages;                           // api.cu: pipeline depth of the tcgen05 weight-gradient kernel (2..4)
 extern int g_wgrad_tc;                               // api.cu: 1 = tcgen05 weight-gradient kernel in auto mode
 extern int g_gather_policy;                          // api.cu: 0 = L1 no-allocate, 1 = + L2::64B, 2 = __ldg

@@ -1,0 +1,408 @@
+// DeepFM forward in ONE kernel: embedding gather -> FM second order -> layer-1 GEMM (tcgen05, 3xTF32) -> tower tail ->
+// logit = fm + dnn -> sigmoid -> BCE (reference: ranking/deepfm.py:41-67 = EmbeddingLayer.forward embedding.py:49-63,
+// get_linear_input utils.py:122-137, FM_Layer interaction.py:225-235, MLP deep.py:62-84, BCELoss).
+//
+// The separate kernels spend 77 us gathering 1.7 M table rows into the feature row x, then 79 us re-reading x for the
+// layer-1 GEMM (profiles/r01_deepfm_step_ncu_full.md): the gather waits on DRAM row activations with the SMs idle, the
+// GEMM is bound by tensor / shared-memory work with DRAM idle.  Here the two overlap: the four "split" warps of the
+// persistent GEMM (thread = sample row) fetch their own rows straight from the tables with cp.async into a private ring
+// of shared-memory stages — FG_LA k-blocks (= 2 fields x 64 B per sample each) in flight per thread, ~80 KB per SM —
+// and then do what they did before: split fp32 -> (hi, lo) into tensor memory for the TS-mode MMAs.  Because a thread
+// only ever reads the bytes it requested, the A operand needs no mbarriers at all (cp.async groups), and the FM sums
+// fall out of registers the thread already holds.  x is written from those registers only when backward needs it.
+//
+// Warps: 0 = TMA producer for the pre-split weight k-blocks, 1 = MMA issuer (+TMEM alloc), 2-5 = gather + split,
+// 6-13 = epilogue + tower tail (tower_tile.cuh) as in gemm_tf32x3_v2_kernel.
+#include "tc_ptx.cuh"
+#include "tower_tile.cuh"
+
+namespace rpb {
+
+constexpr int FG_THREADS = 448;
+constexpr int FG_EPI_WARPS = 8;
+constexpr int FG_LB = 3;                  // weight ring depth (16 KiB stages: [B hi ; B lo] of one k-block)
+constexpr int FG_OP = 4;                  // tensor-memory operand ring (64 columns per stage: A hi 32 | A lo 32)
+constexpr int FG_ROW = TC_BLOCK_K + 4;    // floats per staged row: 144 B, conflict-free float4 reads with thread = row
+constexpr int FG_N = 64;                  // layer-1 width
+constexpr int FG_FM_BUF = 4;              // per-tile FM values handed from the split warps to the tail (see kernel)
+constexpr int FG_B_BYTES = 2 * FG_N * TC_BLOCK_K * 4;
+
+struct FusedFwdParams {
+    const float* tables[RPB_MAX_FIELDS];
+    const long long* idx[RPB_MAX_FIELDS];
+    long long rows[RPB_MAX_FIELDS];
+    const float* dense[RPB_MAX_DENSE];
+    float* x; long long ldx;              // optional materialised feature row (backward needs it)
+    float* fm; float* fm_s;               // optional outputs: FM term [M], sum_f e [M, 16]
+    long long* err;
+    float* h1; long long ldh1; const float* bias1;
+    int M, F, Nd, nkb, nkb_emb;
+};
+
+__device__ __forceinline__ void fg_cp16(float* dst, const float* src, bool valid) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_u32(dst)), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void fg_cp8(void* dst, const void* src, bool valid) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(smem_u32(dst)), "l"(src), "r"(valid ? 8 : 0) : "memory");
+}
+__device__ __forceinline__ void fg_cp4(float* dst, const float* src, bool valid) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(smem_u32(dst)), "l"(src), "r"(valid ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ void fg_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void fg_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+__device__ __forceinline__ void fg_bad_index(long long* err, int f, int b, long long ix) {
+    if (err != nullptr) {
+        unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long*>(err), 0ull, 1ull);
+        if (old == 0ull) { err[1] = f; err[2] = b; err[3] = ix; __threadfence_system(); }
+    }
+}
+
+template <int LA>
+__global__ void __launch_bounds__(FG_THREADS, 1)
+deepfm_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
+                        const __grid_constant__ FusedFwdParams p, const __grid_constant__ TowerFwdParams tw, int m_tiles) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* b_base = smem;                                                   // FG_LB x 16 KiB, 1 KiB aligned (SWIZZLE_128B)
+    float* a_base = reinterpret_cast<float*>(b_base + FG_LB * FG_B_BYTES);    // LA x 128 rows x FG_ROW floats
+    long long* id_base = reinterpret_cast<long long*>(a_base + LA * TC_BLOCK_M * FG_ROW);   // LA x 128 x 2 ids
+    uint64_t* bars = reinterpret_cast<uint64_t*>(id_base + LA * TC_BLOCK_M * 2);
+    uint64_t* full_b = bars;                       // [FG_LB]  weight k-block landed
+    uint64_t* empty_b = full_b + FG_LB;            // [FG_LB]  MMAs that read it are done
+    uint64_t* ready_op = empty_b + FG_LB;          // [FG_OP]  A hi/lo of a k-block are in tensor memory
+    uint64_t* empty_op = ready_op + FG_OP;         // [FG_OP]
+    uint64_t* tmem_full = empty_op + FG_OP;        // [2]
+    uint64_t* tmem_empty = tmem_full + 2;          // [2]
+    uint64_t* fm_ready = tmem_empty + 2;           // [FG_FM_BUF]  FM values of a tile written
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(fm_ready + FG_FM_BUF);
+    float* fm_tile = reinterpret_cast<float*>(tmem_ptr + 4);                  // [FG_FM_BUF][128]
+    float* tw_As = fm_tile + FG_FM_BUF * TC_BLOCK_M;                          // 16-byte aligned: every block above is
+    float* tw_Bs = tw_As + TC_BLOCK_M * TW_LDA;
+    float* tw_loss = tw_Bs + tw.n_tail * TW_H * TW_H;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = p.nkb;
+    const int my_tiles = ((int)blockIdx.x < m_tiles) ? (m_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const uint32_t G = (uint32_t)my_tiles * (uint32_t)nkb;                    // k-blocks this CTA walks
+    constexpr uint32_t ACC_STRIDE = 2 * FG_N;                                 // stacked accumulator: [a.b_hi | a.b_lo]
+    constexpr uint32_t A_COL = 2 * ACC_STRIDE;                                // first TMEM column of the operand ring
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < FG_LB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
+        for (int s = 0; s < FG_OP; ++s) { mbar_init(&ready_op[s], 128); mbar_init(&empty_op[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], FG_EPI_WARPS); }
+        for (int s = 0; s < FG_FM_BUF; ++s) mbar_init(&fm_ready[s], 128);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ---------------- weight producer: [B hi ; B lo] of every k-block through a FG_LB-deep ring
+        if (lane == 0) {
+            for (uint32_t g = 0; g < G; ++g) {
+                const int s = g % FG_LB, kb = g % nkb;
+                mbar_wait(&empty_b[s], ((g / FG_LB) & 1u) ^ 1u);
+                uint8_t* st = b_base + (size_t)s * FG_B_BYTES;
+                mbar_arrive_expect_tx(&full_b[s], (uint32_t)FG_B_BYTES);
+                tma_load_2d(st, &tmBhi, &full_b[s], kb * TC_BLOCK_K, 0);
+                tma_load_2d(st + FG_B_BYTES / 2, &tmBlo, &full_b[s], kb * TC_BLOCK_K, 0);
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer: per k-step two TS-mode MMAs (a_lo, a_hi) against the stacked 128-row weight operand
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(TC_BLOCK_M, 2 * FG_N);
+            uint32_t g = 0;
+            for (int t = 0; t < my_tiles; ++t) {
+                const uint32_t acc = (uint32_t)t & 1u;
+                mbar_wait(&tmem_empty[acc], (((uint32_t)t >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int s = g % FG_LB, o = g % FG_OP;
+                    mbar_wait(&full_b[s], (g / FG_LB) & 1u);
+                    mbar_wait(&ready_op[o], (g / FG_OP) & 1u);
+                    tc_fence_after();
+                    const uint32_t b_addr = smem_u32(b_base + (size_t)s * FG_B_BYTES);
+                    const uint32_t ta_hi = tmem_base + A_COL + (uint32_t)o * 64u, ta_lo = ta_hi + 32u;
+#pragma unroll
+                    for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
+                        const uint64_t db = make_kmajor_sw128_desc(b_addr + k * TC_UMMA_K * 4);
+                        umma_tf32_ts(d_tmem, ta_lo + k * TC_UMMA_K, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        umma_tf32_ts(d_tmem, ta_hi + k * TC_UMMA_K, db, idesc, 1u);
+                    }
+                    umma_commit(&empty_op[o]);
+                    umma_commit(&empty_b[s]);
+                }
+                umma_commit(&tmem_full[acc]);
+            }
+        }
+    } else if (warp < 6) {
+        // ---------------- gather + split warps: thread = sample row of the tile (= its TMEM lane)
+        const int r = (warp & 3) * 32 + lane;
+        const int K_emb_cols = p.F * 16;
+        // issue(gi): request the table rows (or dense columns) of k-block gi into A stage gi % LA, and the ids of
+        // k-block gi + LA - 1 into the id FIFO; one cp.async group per call, empty past the end so the counts stay uniform
+        auto issue = [&](uint32_t gi) {
+            if (gi < G) {
+                const uint32_t tl = gi / (uint32_t)nkb;
+                const int kb = (int)(gi - tl * (uint32_t)nkb);
+                const int m = ((int)blockIdx.x + (int)tl * (int)gridDim.x) * TC_BLOCK_M + r;
+                const bool ok = m < p.M;
+                float* dst = a_base + ((gi % LA) * TC_BLOCK_M + r) * FG_ROW;
+                if (kb < p.nkb_emb) {
+                    const long long* ids = id_base + ((gi % LA) * TC_BLOCK_M + r) * 2;
+                    long long i0 = ids[0], i1 = ids[1];
+                    const int f0 = 2 * kb;
+                    if (ok) {
+                        if ((unsigned long long)i0 >= (unsigned long long)p.rows[f0]) { fg_bad_index(p.err, f0, m, i0); i0 = 0; }
+                        if ((unsigned long long)i1 >= (unsigned long long)p.rows[f0 + 1]) { fg_bad_index(p.err, f0 + 1, m, i1); i1 = 0; }
+                    } else { i0 = 0; i1 = 0; }
+                    const float* s0 = p.tables[f0] + (size_t)i0 * 16;
+                    const float* s1 = p.tables[f0 + 1] + (size_t)i1 * 16;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { fg_cp16(dst + 4 * j, s0 + 4 * j, ok); fg_cp16(dst + 16 + 4 * j, s1 + 4 * j, ok); }
+                } else {
+                    const int c0 = kb * TC_BLOCK_K - K_emb_cols;             // first dense column of this k-block
+#pragma unroll 4
+                    for (int j = 0; j < TC_BLOCK_K; ++j) {
+                        const int c = c0 + j;
+                        if (c < p.Nd) fg_cp4(dst + j, p.dense[c] + (ok ? m : 0), ok);
+                        else dst[j] = 0.f;
+                    }
+                }
+            }
+            const uint32_t gj = gi + (uint32_t)(LA - 1);
+            if (gj < G) {
+                const uint32_t tl = gj / (uint32_t)nkb;
+                const int kb = (int)(gj - tl * (uint32_t)nkb);
+                const int m = ((int)blockIdx.x + (int)tl * (int)gridDim.x) * TC_BLOCK_M + r;
+                if (kb < p.nkb_emb) {
+                    long long* ids = id_base + ((gj % LA) * TC_BLOCK_M + r) * 2;
+                    const bool ok = m < p.M;
+                    fg_cp8(ids, p.idx[2 * kb] + (ok ? m : 0), ok);
+                    fg_cp8(ids + 1, p.idx[2 * kb + 1] + (ok ? m : 0), ok);
+                }
+            }
+            fg_commit();
+        };
+        // prologue: ids of the first LA-1 k-blocks with plain loads, then LA-1 groups in flight
+        for (uint32_t gi = 0; gi + 1 < (uint32_t)LA && gi < G; ++gi) {
+            const uint32_t tl = gi / (uint32_t)nkb;
+            const int kb = (int)(gi - tl * (uint32_t)nkb);
+            const int m = ((int)blockIdx.x + (int)tl * (int)gridDim.x) * TC_BLOCK_M + r;
+            long long* ids = id_base + ((gi % LA) * TC_BLOCK_M + r) * 2;
+            const bool ok = kb < p.nkb_emb && m < p.M;
+            ids[0] = ok ? __ldg(p.idx[2 * kb] + m) : 0;
+            ids[1] = ok ? __ldg(p.idx[2 * kb + 1] + m) : 0;
+        }
+        for (uint32_t gi = 0; gi + 1 < (uint32_t)LA; ++gi) issue(gi);
+
+        float fs[16];                                   // sum_f e of this sample, and the sum of squares
+        float fq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) fs[j] = 0.f;
+        uint32_t g = 0;
+        for (int t = 0; t < my_tiles; ++t) {
+            const int m = ((int)blockIdx.x + t * (int)gridDim.x) * TC_BLOCK_M + r;
+            for (int kb = 0; kb < nkb; ++kb, ++g) {
+                fg_wait<LA - 2>();                      // group g has landed: A(g) and the ids of k-block g + LA - 1
+                issue(g + (uint32_t)(LA - 1));
+                const int o = g % FG_OP;
+                mbar_wait(&empty_op[o], ((g / FG_OP) & 1u) ^ 1u);
+                tc_fence_after();
+                const float4* src = reinterpret_cast<const float4*>(a_base + ((g % LA) * TC_BLOCK_M + r) * FG_ROW);
+                float4 v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = src[j];
+                if (p.x != nullptr && m < p.M) {        // materialise the feature row (training): 128 B per k-block
+                    float* xr = p.x + (size_t)m * p.ldx + kb * TC_BLOCK_K;
+                    const int nv = min(8, ((int)p.ldx - kb * TC_BLOCK_K) >> 2);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) if (j < nv) stg_f4(xr + 4 * j, v[j]);
+                }
+                if (kb < p.nkb_emb) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 a = v[j], b = v[4 + j];
+                        fs[4 * j + 0] += a.x + b.x; fs[4 * j + 1] += a.y + b.y; fs[4 * j + 2] += a.z + b.z; fs[4 * j + 3] += a.w + b.w;
+                        fq = fmaf(a.x, a.x, fq); fq = fmaf(a.y, a.y, fq); fq = fmaf(a.z, a.z, fq); fq = fmaf(a.w, a.w, fq);
+                        fq = fmaf(b.x, b.x, fq); fq = fmaf(b.y, b.y, fq); fq = fmaf(b.z, b.z, fq); fq = fmaf(b.w, b.w, fq);
+                    }
+                }
+                uint32_t h[32], l[32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 q = v[j];
+                    h[4 * j + 0] = __float_as_uint(q.x) & 0xFFFFE000u; l[4 * j + 0] = __float_as_uint(q.x - __uint_as_float(h[4 * j + 0]));
+                    h[4 * j + 1] = __float_as_uint(q.y) & 0xFFFFE000u; l[4 * j + 1] = __float_as_uint(q.y - __uint_as_float(h[4 * j + 1]));
+                    h[4 * j + 2] = __float_as_uint(q.z) & 0xFFFFE000u; l[4 * j + 2] = __float_as_uint(q.z - __uint_as_float(h[4 * j + 2]));
+                    h[4 * j + 3] = __float_as_uint(q.w) & 0xFFFFE000u; l[4 * j + 3] = __float_as_uint(q.w - __uint_as_float(h[4 * j + 3]));
+                }
+                const uint32_t ta = tmem_base + A_COL + (uint32_t)o * 64u + ((uint32_t)((warp & 3) * 32) << 16);
+                tmem_st32(ta, h);
+                tmem_st32(ta + 32u, l);
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&ready_op[o]);
+            }
+            // FM second order of this sample: 0.5 * (sum_d s_d^2 - sum_{f,d} e^2); handed to the tail through shared memory
+            float ss = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) ss = fmaf(fs[j], fs[j], ss);
+            const float fmv = 0.5f * (ss - fq);
+            fm_tile[(t % FG_FM_BUF) * TC_BLOCK_M + r] = fmv;
+            if (m < p.M) {
+                if (p.fm != nullptr) p.fm[m] = fmv;
+                if (p.fm_s != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        stg_f4(p.fm_s + (size_t)m * 16 + 4 * j, make_float4(fs[4 * j], fs[4 * j + 1], fs[4 * j + 2], fs[4 * j + 3]));
+                }
+            }
+            mbar_arrive(&fm_ready[t % FG_FM_BUF]);
+            fq = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) fs[j] = 0.f;
+        }
+        fg_wait<0>();
+    } else {
+        // ---------------- epilogue warps: layer-1 epilogue -> h1 (HBM + shared memory) -> tower tail (tower_tile.cuh)
+        const int quarter = warp & 3;
+        const int half = (warp - 6) >> 2;
+        const int row = quarter * 32 + lane;
+        const int et = threadIdx.x - 6 * 32;
+        auto epi_sync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+        tower_load_weights_t<FG_EPI_WARPS * 32>(tw, tw_Bs, et);
+        const float4 tw_wo = ldg_f4(tw.w_out + (et & 15) * 4);
+        const float tw_bo = tw.b_out != nullptr ? __ldg(tw.b_out) : 0.f;
+        float loss_acc = 0.f;
+        for (int t = 0; t < my_tiles; ++t) {
+            const int m0 = ((int)blockIdx.x + t * (int)gridDim.x) * TC_BLOCK_M;
+            const uint32_t acc = (uint32_t)t & 1u;
+            const int m = m0 + row;
+            mbar_wait(&tmem_full[acc], ((uint32_t)t >> 1) & 1u);
+            tc_fence_after();
+            epi_sync();                                // previous tile's activations fully consumed (weights visible)
+            for (int c0 = half * 16; c0 < FG_N; c0 += 32) {
+                uint32_t a0[16], a1[16];
+                tmem_ld16(tmem_base + acc * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, a0);
+                tmem_ld16(tmem_base + acc * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(FG_N + c0), a1);
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    v[j] = fmaxf(__uint_as_float(a1[j]) + __uint_as_float(a0[j]) + __ldg(p.bias1 + c0 + j), 0.f);
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 q4 = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    if (m < p.M) stg_f4(p.h1 + (size_t)m * p.ldh1 + c0 + j, q4);
+                    *reinterpret_cast<float4*>(tw_As + row * TW_LDA + c0 + j) = q4;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            mbar_wait(&fm_ready[t % FG_FM_BUF], ((uint32_t)t / FG_FM_BUF) & 1u);
+            epi_sync();
+            tower_tail_tile_fwd<FG_EPI_WARPS * 32>(tw, tw_As, tw_Bs, m0, et, tw_wo, tw_bo, loss_acc, epi_sync,
+                                                   fm_tile + (t % FG_FM_BUF) * TC_BLOCK_M);
+        }
+        if (tw.loss != nullptr) tw_loss[et] = loss_acc;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+    if (tw.loss != nullptr && warp == 0) {
+        // deterministic mean BCE: 256 epilogue partials -> per-CTA partial -> the last CTA adds them in index order
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < FG_EPI_WARPS; ++i) s += tw_loss[lane + 32 * i];
+        s = warp_sum(s);
+        unsigned int last = 0;
+        if (lane == 0) {
+            tw.partials[blockIdx.x] = s;
+            __threadfence();
+            last = (atomicAdd(tw.counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            __threadfence();
+            float tot = 0.f;
+            for (int i = lane; i < (int)gridDim.x; i += 32) tot += ((volatile float*)tw.partials)[i];
+            tot = warp_sum(tot);
+            if (lane == 0) {
+                tw.loss[0] = tw.scale * (tot / (float)tw.M);
+                *tw.counter = 0u;
+            }
+        }
+    }
+}
+
+static size_t fg_smem_bytes(int la, int n_tail) {
+    return (size_t)FG_LB * FG_B_BYTES + (size_t)la * TC_BLOCK_M * FG_ROW * 4 + (size_t)la * TC_BLOCK_M * 16 +
+           (2 * FG_LB + 2 * FG_OP + 4 + FG_FM_BUF) * 8 + 16 + FG_FM_BUF * TC_BLOCK_M * 4 +
+           (size_t)(TC_BLOCK_M * TW_LDA + n_tail * TW_H * TW_H + 256) * 4 + 1024;
+}
+
+}  // namespace rpb
+
+using namespace rpb;
+
+RPB_API int rpb_deepfm_fwd_fused(const RpbGatherDesc* g, const float* W1, const float* b1, const RpbTowerFwdDesc* d,
+                                 void* stream) {
+    if (g == nullptr || d == nullptr || W1 == nullptr || b1 == nullptr) return RPB_ERR_BAD_ARG;
+    TowerFwdParams tw{};
+    const int prc = tower_fwd_params(d, &tw);
+    if (prc != 0) return prc;
+    if (g->B != d->M || g->tables == nullptr || g->rows == nullptr || g->idx == nullptr || (g->Nd > 0 && g->dense == nullptr))
+        return RPB_ERR_BAD_ARG;
+    // shapes this kernel is built for: 64-byte rows, an even number of fields (one k-block = two fields), unsharded tables
+    if (g->D != 16 || g->F < 2 || (g->F & 1) || g->F > RPB_MAX_FIELDS || g->Nd > RPB_MAX_DENSE || g->G > 1 || g->lr_tables != nullptr ||
+        g->lr_in != nullptr || d->n_tail < 1 || d->M < 512 || !g_gemm_v2 || (d->ldh1 & 3) != 0)
+        return RPB_ERR_UNSUPPORTED;
+    const int K = g->F * 16 + g->Nd;
+    if (g->x != nullptr && (g->ldx < ((K + 3) / 4) * 4 || (g->ldx & 3) != 0 || (reinterpret_cast<uintptr_t>(g->x) & 15u))) return RPB_ERR_BAD_ARG;
+    if (g->fm_s != nullptr && (reinterpret_cast<uintptr_t>(g->fm_s) & 15u)) return RPB_ERR_UNSUPPORTED;
+    FusedFwdParams p{};
+    for (int f = 0; f < g->F; ++f) {
+        if (g->tables[f] == nullptr || g->idx[f] == nullptr || (reinterpret_cast<uintptr_t>(g->tables[f]) & 15u) ||
+            (reinterpret_cast<uintptr_t>(g->idx[f]) & 7u))
+            return RPB_ERR_UNSUPPORTED;
+        p.tables[f] = g->tables[f];
+        p.idx[f] = reinterpret_cast<const long long*>(g->idx[f]);
+        p.rows[f] = g->rows[f];
+    }
+    for (int j = 0; j < g->Nd; ++j) {
+        if (g->dense[j] == nullptr) return RPB_ERR_BAD_ARG;
+        p.dense[j] = g->dense[j];
+    }
+    p.x = g->x; p.ldx = g->ldx; p.fm = g->fm; p.fm_s = g->fm_s; p.err = reinterpret_cast<long long*>(g->err);
+    p.h1 = const_cast<float*>(d->h1); p.ldh1 = d->ldh1; p.bias1 = b1;
+    p.M = d->M; p.F = g->F; p.Nd = g->Nd;
+    p.nkb_emb = g->F / 2;
+    p.nkb = p.nkb_emb + ceil_div(g->Nd, TC_BLOCK_K);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CUtensorMap tmBhi, tmBlo;
+    int rc = tc_prepare_weight(W1, K, FG_N, K, &tmBhi, &tmBlo, st);
+    if (rc != 0) return rc;
+    const int m_tiles = ceil_div(d->M, TC_BLOCK_M);
+    const int grid = min(m_tiles, 148);
+    auto launch = [&](auto la_tag) -> int {
+        constexpr int LA = decltype(la_tag)::value;
+        const size_t smem = fg_smem_bytes(LA, d->n_tail);
+        cudaError_t e = cudaFuncSetAttribute(deepfm_fwd_fused_kernel<LA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        deepfm_fwd_fused_kernel<LA><<<grid, FG_THREADS, smem, st>>>(tmBhi, tmBlo, p, tw, m_tiles);
+        return (int)cudaGetLastError();
+    };
+    const size_t cap = 227 * 1024;
+    if (fg_smem_bytes(5, d->n_tail) <= cap) return launch(std::integral_constant<int, 5>{});
+    if (fg_smem_bytes(4, d->n_tail) <= cap) return launch(std::integral_constant<int, 4>{});
+    if (fg_smem_bytes(3, d->n_tail) <= cap) return launch(std::integral_constant<int, 3>{});
+    return RPB_ERR_UNSUPPORTED;
+}

@@ -63,10 +63,12 @@ __device__ __forceinline__ void tower_load_weights_t(const TowerFwdParams& p, fl
 
 // One tile of the forward tail.  On entry As holds the post-ReLU layer-1 tile (rows m0 .. m0+NT/2-1, zero beyond M) and
 // the caller has synchronised the NT threads; `sync()` is a barrier over exactly those NT threads.  Runs the n_tail
-// hidden layers (h[l] -> HBM, activations stay in As), then logit / pred / BCE term of each row.
+// hidden layers (h[l] -> HBM, activations stay in As), then logit / pred / BCE term of each row.  `addend_local`, when
+// given, replaces p.addend: NT/2 floats indexed by the row inside the tile (shared memory).
 template <int NT, class Sync>
 __device__ __forceinline__ void tower_tail_tile_fwd(const TowerFwdParams& p, float* As, const float* Bs, int m0, int tid,
-                                                    const float4 wo, const float bo, float& loss_acc, Sync sync) {
+                                                    const float4 wo, const float bo, float& loss_acc, Sync sync,
+                                                    const float* addend_local = nullptr) {
     constexpr int RG = NT / 16;
     const int tx = tid & 15, ty = tid >> 4;
     for (int l = 0; l < p.n_tail; ++l) {
@@ -106,7 +108,8 @@ __device__ __forceinline__ void tower_tail_tile_fwd(const TowerFwdParams& p, flo
     const int m = m0 + ty + RG * tx;
     if (tx < 8 && m < p.M) {
         float z = mine + bo;
-        if (p.addend != nullptr) z += __ldg(p.addend + m);
+        if (addend_local != nullptr) z += addend_local[ty + RG * tx];      // per-tile addend in shared memory (fused kernel)
+        else if (p.addend != nullptr) z += __ldg(p.addend + m);
         p.logit[m] = z;
         if (p.pred != nullptr) {
             const float q = 1.f / (1.f + expf(-z));

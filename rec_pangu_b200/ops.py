@@ -36,6 +36,8 @@ def _side_stream(dev) -> 'torch.cuda.Stream':
     return _SIDE[key]
 
 
+# 1 = DeepFM forward as ONE kernel: the layer-1 GEMM gathers its own operand rows (rpb_deepfm_fwd_fused)
+FUSED_GATHER_GEMM = int(__import__('os').environ.get('RPB_FUSED_GATHER_GEMM', '1'))
 _LAUNCHES = 0           # number of librec_pangu_b200 kernels launched (bench.py reports it as gpu_launches)
 
 
@@ -726,6 +728,57 @@ def _tower_fwd(cfg, x, params, addend=None, head=None):
     return logit, [x, y1] + hs, pred, loss
 
 
+def _deepfm_fused_fwd(cfg, tables, idx, dense, params, head, need_grad):
+    """rpb_deepfm_fwd_fused: gather + FM + layer 1 + tower tail (+ sigmoid/BCE) in one launch.  Returns None when the
+    shape is outside what that kernel takes, else (logit, acts, pred, loss, fm_s, rows) like _gather_fwd_raw + _tower_fwd."""
+    F, Nd, D = len(tables), len(dense), int(tables[0].shape[1])
+    M = idx[0].shape[0]
+    n_hidden = cfg['n_hidden']
+    n_tail = n_hidden - 1
+    if D != 16 or (F & 1) or n_tail < 1 or M < 512:
+        return None
+    lib, st, dev = _lib.load(), _stream(), tables[0].device
+    ldx = feature_row_stride(F, D, Nd)
+    x = torch.empty((M, ldx), dtype=torch.float32, device=dev) if need_grad else None
+    fm_s = torch.empty((M, D), dtype=torch.float32, device=dev) if need_grad else None
+    rows = [int(t.shape[0]) for t in tables]
+    g = GatherDesc()
+    g.B, g.F, g.D, g.Nd, g.ldx, g.ld_lr = M, F, D, Nd, ldx, 0
+    keep = [_ptr_list(tables), (C.c_int64 * F)(*rows), _ptr_list(idx)]
+    g.tables, g.rows, g.idx = keep
+    if Nd:
+        keep.append(_ptr_list(dense))
+        g.dense = keep[-1]
+    g.x, g.fm_s = _ptr(x), _ptr(fm_s)
+    g.err = _err_record(dev).data_ptr()
+    y1 = torch.empty((M, 64), dtype=torch.float32, device=dev)
+    hs = [torch.empty((M, 64), dtype=torch.float32, device=dev) for _ in range(n_tail)]
+    logit = torch.empty((M, 1), dtype=torch.float32, device=dev)
+    d = TowerFwdDesc()
+    d.M, d.H, d.n_tail = M, 64, n_tail
+    d.h1, d.ldh1 = y1.data_ptr(), 64
+    keep += [_ptr_list([params[2 * (l + 1)] for l in range(n_tail)]),
+             _ptr_list([params[2 * (l + 1) + 1] for l in range(n_tail)]), _ptr_list(hs)]
+    d.W, d.b, d.h = keep[-3:]
+    d.w_out, d.b_out = params[2 * n_hidden].data_ptr(), params[2 * n_hidden + 1].data_ptr()
+    d.logit = logit.data_ptr()
+    pred = loss = None
+    if head is not None:
+        label, eps, scale = head
+        pred = torch.empty((M, 1), dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        d.label, d.pred, d.loss = label.data_ptr(), pred.data_ptr(), loss.data_ptr()
+        d.eps, d.scale = eps, scale
+        d.work = _head_work(dev).data_ptr()
+    rc = lib.rpb_deepfm_fwd_fused(C.byref(g), _ptr(params[0]), _ptr(params[1]), C.byref(d), st)
+    if rc == _lib.ERR_UNSUPPORTED:
+        return None
+    check(rc, 'rpb_deepfm_fwd_fused')
+    _count(2)
+    del keep
+    return logit, [x, y1] + hs, pred, loss, fm_s, rows
+
+
 def _tower_bwd(cfg, acts, params, dlogit_in=None, head=None, gloss=None, need_dx_input=False, layer0_hook=None):
     """Backward of _tower_fwd.  dlogit comes from `dlogit_in` ([M]) or is formed in the kernel from head = (pred, label,
     eps, scale) and gloss (0-dim tensor or None = 1).  Returns (gx | None, gparams, dlogit [M])."""
@@ -850,15 +903,24 @@ class _DeepFMCore(torch.autograd.Function):
         label = tensors[-1] if gcfg['has_label'] else None
         params = tensors[2 * F + Nd:len(tensors) - (1 if gcfg['has_label'] else 0)]
         need_grad = gcfg['needs_grad']
-        x, fm, fm_s, rows = _gather_fwd_raw(tables, idx, dense, want_fm=True, need_grad=need_grad)
         ctx.tower = gcfg['tower']
         pred = loss = None
-        if ctx.tower:
-            head = (label, 0.0, 1.0) if label is not None else None
-            logit, acts, pred, loss = _tower_fwd(cfg, x, params, addend=fm, head=head)
+        fused = None
+        head = (label, 0.0, 1.0) if label is not None else None
+        if ctx.tower and FUSED_GATHER_GEMM and cfg['impl'] != 1:
+            fused = _deepfm_fused_fwd(cfg, tables, idx, dense, params, head, need_grad)
+        if fused is not None:                          # gather + FM + layer 1 + tail + loss: one kernel
+            logit, acts, pred, loss, fm_s, rows = fused
             pre_drop, seeds = [None] * cfg['n_hidden'], [0] * cfg['n_hidden']
+            x = acts[0] if acts[0] is not None else logit.new_empty(0)
+            acts[0] = x
         else:
-            logit, acts, pre_drop, seeds = _mlp_fwd(cfg, x, params, addend=fm)
+            x, fm, fm_s, rows = _gather_fwd_raw(tables, idx, dense, want_fm=True, need_grad=need_grad)
+            if ctx.tower:
+                logit, acts, pred, loss = _tower_fwd(cfg, x, params, addend=fm, head=head)
+                pre_drop, seeds = [None] * cfg['n_hidden'], [0] * cfg['n_hidden']
+            else:
+                logit, acts, pre_drop, seeds = _mlp_fwd(cfg, x, params, addend=fm)
         ctx.set_materialize_grads(False)
         ctx.cfg, ctx.gcfg, ctx.seeds, ctx.rows = cfg, gcfg, seeds, rows
         ctx.tables = tables

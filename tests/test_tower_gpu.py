@@ -168,3 +168,64 @@ def test_tower_in_gemm_epilogue_equals_standalone_tail(M, K, hidden):
     torch.testing.assert_close(res[0][3], res[1][3], rtol=1e-6, atol=1e-7)     # loss: different partial-sum grouping
     ref = torch.nn.functional.binary_cross_entropy(torch.sigmoid(res[0][0].double().squeeze(1)), label.double())
     torch.testing.assert_close(res[0][3].double(), ref, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('B,F,Nd,hidden', [(4096, 26, 13, [64, 64, 64]), (5000, 26, 13, [64, 64]), (1300, 4, 0, [64, 64, 64]),
+                                           (2048, 6, 40, [64, 64, 64, 64])])
+def test_deepfm_one_kernel_forward_equals_separate_kernels(B, F, Nd, hidden):
+    """rpb_deepfm_fwd_fused (gather + FM + layer 1 + tail + loss in one launch, operand rows fetched with cp.async by the
+    GEMM's split warps) vs rpb_gather_fwd + rpb_linear_tower_fwd: the feature row is a pure copy (bit exact), layer 1 sees
+    the same operands (bit exact), the FM term is summed in another order (1e-5), gradients agree."""
+    from helpers import make_enc, make_batch
+    from rec_pangu_b200 import ops
+    from rec_pangu_b200.models.ranking import DeepFM
+    enc = make_enc(F, Nd, 3000)
+    torch.manual_seed(2)
+    model = DeepFM(embedding_dim=16, hidden_units=hidden, enc_dict=enc)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if 'embedding_layer' in n:
+                p.mul_(0.25)
+            elif p.dim() == 1:
+                p.copy_(torch.randn(p.shape) * 0.05)
+    model = model.cuda().train()
+    data = make_batch(enc, B, seed=21, device='cuda')
+    res = []
+    for flag in (1, 0):
+        ops.FUSED_GATHER_GEMM = flag
+        try:
+            model.zero_grad()
+            n0 = ops.launch_count()
+            out = model(data)
+            nl = ops.launch_count() - n0
+            out['loss'].backward()
+            ops.check_index_errors()
+            grads = {n: p.grad.clone() for n, p in model.named_parameters()}
+            res.append((out['pred'].detach().clone(), out['loss'].detach().clone(), model._last_logit.clone(), grads, nl))
+        finally:
+            ops.FUSED_GATHER_GEMM = 1
+    assert res[0][4] == 2 and res[1][4] == 3            # (split + fused kernel) vs (gather, split + GEMM-with-tail)
+    torch.testing.assert_close(res[0][2], res[1][2], rtol=1e-5, atol=2e-5)
+    torch.testing.assert_close(res[0][0], res[1][0], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(res[0][1], res[1][1], rtol=1e-5, atol=1e-6)
+    for n in res[0][3]:
+        a, b = res[0][3][n], res[1][3][n]
+        assert (a - b).abs().max().item() <= 2e-4 * max(1e-6, b.abs().max().item()) + 1e-7, n
+    # inference (no autograd): no feature row is materialised, same probabilities
+    with torch.no_grad():
+        p_fused = model(data, is_training=False)['pred']
+    torch.testing.assert_close(p_fused, res[0][0], rtol=1e-6, atol=1e-7)
+
+
+def test_deepfm_one_kernel_reports_bad_index():
+    from helpers import make_enc, make_batch
+    from rec_pangu_b200 import ops
+    from rec_pangu_b200.models.ranking import DeepFM
+    enc = make_enc(4, 2, 100)
+    model = DeepFM(embedding_dim=16, hidden_units=[64, 64], enc_dict=enc).cuda()
+    data = make_batch(enc, 1024, seed=1, device='cuda')
+    data['C3'][517] = 101 + 5                          # one past the OOV row and beyond
+    with torch.no_grad():
+        model(data, is_training=False)
+    with pytest.raises(IndexError):
+        ops.check_index_errors()
