@@ -206,6 +206,9 @@ int rpb_linear_tower_fwd(const float* x, int64_t ldx, const float* W1, const flo
  * Needs D == 16, an even F, unsharded tables, n_tail >= 1, M >= 512; RPB_ERR_UNSUPPORTED otherwise (the caller then runs
  * rpb_gather_fwd + rpb_linear_tower_fwd). */
 int rpb_deepfm_fwd_fused(const RpbGatherDesc* g, const float* W1, const float* b1, const RpbTowerFwdDesc* d, void* stream);
+/* Per-role stall cycles of CTA 0 of the last rpb_deepfm_fwd_fused launch (same protocol as rpb_debug_tc_trace; see
+ * deepfm_fused.cu for the 12 counters). */
+int rpb_debug_fused_trace(uint64_t* out16, int enable);
 /* Backward of rpb_tower_tail_fwd.  hin: HOST array of n_tail+1 device pointers, hin[0] = h1 (row stride ldh1),
  * hin[j] = h[j-1] ([M, H] contiguous).  dlogit[m] = dlogit_in[m] when given, else gloss[0]*scale/M * dBCE/dp * p(1-p)
  * from (pred, label) with ATen's clamps (gloss NULL = 1); it is written to dlogit_out when non-NULL.

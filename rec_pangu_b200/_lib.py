@@ -85,6 +85,7 @@ SIGNATURES = {
     'rpb_tower_tail_fwd': (C.c_int, [C.POINTER(TowerFwdDesc), _vp]),
     'rpb_linear_tower_fwd': (C.c_int, [_vp, _i64, _vp, _vp, C.c_int, C.POINTER(TowerFwdDesc), _vp]),
     'rpb_deepfm_fwd_fused': (C.c_int, [C.POINTER(GatherDesc), _vp, _vp, C.POINTER(TowerFwdDesc), _vp]),
+    'rpb_debug_fused_trace': (C.c_int, [C.POINTER(C.c_uint64), C.c_int]),
     'rpb_tower_tail_bwd': (C.c_int, [C.POINTER(TowerBwdDesc), _vp]),
     'rpb_dropout_fwd': (C.c_int, [_vp, _vp, _i64, _f32, C.c_uint64, _vp]),
     'rpb_dropout_bwd': (C.c_int, [_vp, _vp, _vp, _i64, _f32, C.c_uint64, _vp]),

@@ -39,8 +39,10 @@ struct FusedFwdParams {
     int M, F, Nd, nkb, nkb_emb;
 };
 
+// table rows: 16-byte pieces of a 64-byte row; the L2 fetch is capped at 64 B so that a row does not drag the other half
+// of its 128-byte line in (without the cap ncu showed 231 MB read for 126 MB of rows + ids)
 __device__ __forceinline__ void fg_cp16(float* dst, const float* src, bool valid) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_u32(dst)), "l"(src), "r"(valid ? 16 : 0) : "memory");
+    asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16, %2;" :: "r"(smem_u32(dst)), "l"(src), "r"(valid ? 16 : 0) : "memory");
 }
 __device__ __forceinline__ void fg_cp8(void* dst, const void* src, bool valid) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(smem_u32(dst)), "l"(src), "r"(valid ? 8 : 0) : "memory");
@@ -57,6 +59,14 @@ __device__ __forceinline__ void fg_bad_index(long long* err, int f, int b, long 
         if (old == 0ull) { err[1] = f; err[2] = b; err[3] = ix; __threadfence_system(); }
     }
 }
+
+// Diagnostics (rpb_debug_fused_trace): cycles of CTA 0 of the last launch — [0] kernel, [1] split: cp.async wait,
+// [2] split: wait for a free TMEM operand slot, [3] split: work, [4] MMA: wait weights, [5] MMA: wait operands,
+// [6] MMA: wait accumulator, [7] MMA: issue, [8] epilogue: wait accumulator, [9] epilogue: layer-1 part + wait FM,
+// [10] epilogue: tail, [11] weight producer: wait free stage.
+__device__ int g_fg_trace_on = 0;
+__device__ unsigned long long g_fg_trace[16];
+#define FG_T() (trace ? clock64() : 0ll)
 
 template <int LA>
 __global__ void __launch_bounds__(FG_THREADS, 1)
@@ -100,13 +110,19 @@ deepfm_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    const bool trace = g_fg_trace_on != 0 && blockIdx.x == 0;
+    const long long t_start = FG_T();
 
     if (warp == 0) {
         // ---------------- weight producer: [B hi ; B lo] of every k-block through a FG_LB-deep ring
         if (lane == 0) {
+            long long w_b = 0;
             for (uint32_t g = 0; g < G; ++g) {
                 const int s = g % FG_LB, kb = g % nkb;
+                const long long c0 = FG_T();
                 mbar_wait(&empty_b[s], ((g / FG_LB) & 1u) ^ 1u);
+                w_b += FG_T() - c0;
+                if (trace && g + 1 == G) g_fg_trace[11] = (unsigned long long)w_b;
                 uint8_t* st = b_base + (size_t)s * FG_B_BYTES;
                 mbar_arrive_expect_tx(&full_b[s], (uint32_t)FG_B_BYTES);
                 tma_load_2d(st, &tmBhi, &full_b[s], kb * TC_BLOCK_K, 0);
@@ -118,15 +134,22 @@ deepfm_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_
         if (lane == 0) {
             const uint32_t idesc = make_idesc_tf32(TC_BLOCK_M, 2 * FG_N);
             uint32_t g = 0;
+            long long w_fb = 0, w_op = 0, w_acc = 0, w_is = 0;
             for (int t = 0; t < my_tiles; ++t) {
                 const uint32_t acc = (uint32_t)t & 1u;
+                const long long c0 = FG_T();
                 mbar_wait(&tmem_empty[acc], (((uint32_t)t >> 1) & 1u) ^ 1u);
+                w_acc += FG_T() - c0;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
                 for (int kb = 0; kb < nkb; ++kb, ++g) {
                     const int s = g % FG_LB, o = g % FG_OP;
+                    const long long c1 = FG_T();
                     mbar_wait(&full_b[s], (g / FG_LB) & 1u);
+                    const long long c2 = FG_T();
                     mbar_wait(&ready_op[o], (g / FG_OP) & 1u);
+                    const long long c3 = FG_T();
+                    w_fb += c2 - c1; w_op += c3 - c2;
                     tc_fence_after();
                     const uint32_t b_addr = smem_u32(b_base + (size_t)s * FG_B_BYTES);
                     const uint32_t ta_hi = tmem_base + A_COL + (uint32_t)o * 64u, ta_lo = ta_hi + 32u;
@@ -138,37 +161,46 @@ deepfm_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_
                     }
                     umma_commit(&empty_op[o]);
                     umma_commit(&empty_b[s]);
+                    w_is += FG_T() - c3;
                 }
                 umma_commit(&tmem_full[acc]);
             }
+            if (trace) { g_fg_trace[4] = (unsigned long long)w_fb; g_fg_trace[5] = (unsigned long long)w_op; g_fg_trace[6] = (unsigned long long)w_acc; g_fg_trace[7] = (unsigned long long)w_is; }
         }
     } else if (warp < 6) {
         // ---------------- gather + split warps: thread = sample row of the tile (= its TMEM lane)
         const int r = (warp & 3) * 32 + lane;
         const int K_emb_cols = p.F * 16;
-        // issue(gi): request the table rows (or dense columns) of k-block gi into A stage gi % LA, and the ids of
-        // k-block gi + LA - 1 into the id FIFO; one cp.async group per call, empty past the end so the counts stay uniform
-        auto issue = [&](uint32_t gi) {
+        // issue(): request the table rows (or dense columns) of the next un-requested k-block `gi` into A stage gi % LA, and
+        // the ids of k-block gi + LA - 1 into the id FIFO; one cp.async group per call (empty past the end, so the group
+        // counts stay uniform).  Row requests are made COOPERATIVELY by the warp: 4 consecutive lanes fetch the four 16-byte
+        // pieces of one 64-byte row, so a warp instruction is 8 whole-row requests instead of 32 quarter-row ones (the
+        // thread = row mapping cost ~2 k cycles of LSU time per k-block: tools/exp/trace_fused.py).  A warp therefore reads
+        // ids and writes stage rows of its OWN 32 rows only, and __syncwarp() is the only synchronisation the A path needs.
+        const int wrow0 = (warp & 3) * 32;               // first tile row of this warp
+        uint32_t gi = 0; int i_kb = 0, i_t = 0;          // next k-block to request: global index, k-block, local tile
+        uint32_t gj = (uint32_t)(LA - 1); int j_kb = (LA - 1) % nkb, j_t = (LA - 1) / nkb;     // next ids to request
+        auto issue = [&]() {
+            __syncwarp();
             if (gi < G) {
-                const uint32_t tl = gi / (uint32_t)nkb;
-                const int kb = (int)(gi - tl * (uint32_t)nkb);
-                const int m = ((int)blockIdx.x + (int)tl * (int)gridDim.x) * TC_BLOCK_M + r;
-                const bool ok = m < p.M;
-                float* dst = a_base + ((gi % LA) * TC_BLOCK_M + r) * FG_ROW;
-                if (kb < p.nkb_emb) {
-                    const long long* ids = id_base + ((gi % LA) * TC_BLOCK_M + r) * 2;
-                    long long i0 = ids[0], i1 = ids[1];
-                    const int f0 = 2 * kb;
-                    if (ok) {
-                        if ((unsigned long long)i0 >= (unsigned long long)p.rows[f0]) { fg_bad_index(p.err, f0, m, i0); i0 = 0; }
-                        if ((unsigned long long)i1 >= (unsigned long long)p.rows[f0 + 1]) { fg_bad_index(p.err, f0 + 1, m, i1); i1 = 0; }
-                    } else { i0 = 0; i1 = 0; }
-                    const float* s0 = p.tables[f0] + (size_t)i0 * 16;
-                    const float* s1 = p.tables[f0 + 1] + (size_t)i1 * 16;
+                const int mt = ((int)blockIdx.x + i_t * (int)gridDim.x) * TC_BLOCK_M;
+                const int slot = (int)(gi % LA);
+                if (i_kb < p.nkb_emb) {
+                    const int piece = lane & 3;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) { fg_cp16(dst + 4 * j, s0 + 4 * j, ok); fg_cp16(dst + 16 + 4 * j, s1 + 4 * j, ok); }
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = wrow0 + (i & 3) * 8 + (lane >> 2), fsel = i >> 2, f = 2 * i_kb + fsel;
+                        const bool ok = mt + row < p.M;
+                        long long id = id_base[(slot * TC_BLOCK_M + row) * 2 + fsel];
+                        if (!ok) id = 0;
+                        else if ((unsigned long long)id >= (unsigned long long)p.rows[f]) { if (piece == 0) fg_bad_index(p.err, f, mt + row, id); id = 0; }
+                        fg_cp16(a_base + (slot * TC_BLOCK_M + row) * FG_ROW + fsel * 16 + piece * 4, p.tables[f] + (size_t)id * 16 + piece * 4, ok);
+                    }
                 } else {
-                    const int c0 = kb * TC_BLOCK_K - K_emb_cols;             // first dense column of this k-block
+                    const int m = mt + r;
+                    const bool ok = m < p.M;
+                    float* dst = a_base + (slot * TC_BLOCK_M + r) * FG_ROW;
+                    const int c0 = i_kb * TC_BLOCK_K - K_emb_cols;           // first dense column of this k-block
 #pragma unroll 4
                     for (int j = 0; j < TC_BLOCK_K; ++j) {
                         const int c = c0 + j;
@@ -177,54 +209,64 @@ deepfm_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_
                     }
                 }
             }
-            const uint32_t gj = gi + (uint32_t)(LA - 1);
-            if (gj < G) {
-                const uint32_t tl = gj / (uint32_t)nkb;
-                const int kb = (int)(gj - tl * (uint32_t)nkb);
-                const int m = ((int)blockIdx.x + (int)tl * (int)gridDim.x) * TC_BLOCK_M + r;
-                if (kb < p.nkb_emb) {
-                    long long* ids = id_base + ((gj % LA) * TC_BLOCK_M + r) * 2;
-                    const bool ok = m < p.M;
-                    fg_cp8(ids, p.idx[2 * kb] + (ok ? m : 0), ok);
-                    fg_cp8(ids + 1, p.idx[2 * kb + 1] + (ok ? m : 0), ok);
-                }
+            if (gj < G && j_kb < p.nkb_emb) {
+                const int m = ((int)blockIdx.x + j_t * (int)gridDim.x) * TC_BLOCK_M + r;
+                long long* ids = id_base + ((int)(gj % LA) * TC_BLOCK_M + r) * 2;
+                const bool ok = m < p.M;
+                fg_cp8(ids, p.idx[2 * j_kb] + (ok ? m : 0), ok);
+                fg_cp8(ids + 1, p.idx[2 * j_kb + 1] + (ok ? m : 0), ok);
             }
             fg_commit();
+            ++gi; if (++i_kb == nkb) { i_kb = 0; ++i_t; }
+            ++gj; if (++j_kb == nkb) { j_kb = 0; ++j_t; }
         };
         // prologue: ids of the first LA-1 k-blocks with plain loads, then LA-1 groups in flight
-        for (uint32_t gi = 0; gi + 1 < (uint32_t)LA && gi < G; ++gi) {
-            const uint32_t tl = gi / (uint32_t)nkb;
-            const int kb = (int)(gi - tl * (uint32_t)nkb);
-            const int m = ((int)blockIdx.x + (int)tl * (int)gridDim.x) * TC_BLOCK_M + r;
-            long long* ids = id_base + ((gi % LA) * TC_BLOCK_M + r) * 2;
-            const bool ok = kb < p.nkb_emb && m < p.M;
-            ids[0] = ok ? __ldg(p.idx[2 * kb] + m) : 0;
-            ids[1] = ok ? __ldg(p.idx[2 * kb + 1] + m) : 0;
+        {
+            int kb = 0, tl = 0;
+            for (uint32_t q = 0; q + 1 < (uint32_t)LA && q < G; ++q) {
+                const int m = ((int)blockIdx.x + tl * (int)gridDim.x) * TC_BLOCK_M + r;
+                long long* ids = id_base + ((int)(q % LA) * TC_BLOCK_M + r) * 2;
+                const bool ok = kb < p.nkb_emb && m < p.M;
+                ids[0] = ok ? __ldg(p.idx[2 * kb] + m) : 0;
+                ids[1] = ok ? __ldg(p.idx[2 * kb + 1] + m) : 0;
+                if (++kb == nkb) { kb = 0; ++tl; }
+            }
         }
-        for (uint32_t gi = 0; gi + 1 < (uint32_t)LA; ++gi) issue(gi);
+        for (int q = 0; q + 1 < LA; ++q) issue();
 
         float fs[16];                                   // sum_f e of this sample, and the sum of squares
         float fq = 0.f;
 #pragma unroll
         for (int j = 0; j < 16; ++j) fs[j] = 0.f;
         uint32_t g = 0;
+        long long w_cp = 0, w_eo = 0, w_wk = 0;
         for (int t = 0; t < my_tiles; ++t) {
             const int m = ((int)blockIdx.x + t * (int)gridDim.x) * TC_BLOCK_M + r;
             for (int kb = 0; kb < nkb; ++kb, ++g) {
+                const long long c0 = FG_T();
                 fg_wait<LA - 2>();                      // group g has landed: A(g) and the ids of k-block g + LA - 1
-                issue(g + (uint32_t)(LA - 1));
+                const long long c1 = FG_T();
+                issue();                                // k-block g + LA - 1 (starts with a __syncwarp: rows of group g visible warp-wide)
                 const int o = g % FG_OP;
+                const long long c2 = FG_T();
                 mbar_wait(&empty_op[o], ((g / FG_OP) & 1u) ^ 1u);
+                const long long c3 = FG_T();
+                w_cp += c1 - c0; w_eo += c3 - c2; w_wk += c2 - c1;
                 tc_fence_after();
                 const float4* src = reinterpret_cast<const float4*>(a_base + ((g % LA) * TC_BLOCK_M + r) * FG_ROW);
                 float4 v[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = src[j];
-                if (p.x != nullptr && m < p.M) {        // materialise the feature row (training): 128 B per k-block
-                    float* xr = p.x + (size_t)m * p.ldx + kb * TC_BLOCK_K;
+                if (p.x != nullptr) {                   // materialise the feature row (training): 8 lanes write one row's 128 B
+                    const int mt = m - r, piece = lane & 7;
                     const int nv = min(8, ((int)p.ldx - kb * TC_BLOCK_K) >> 2);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) if (j < nv) stg_f4(xr + 4 * j, v[j]);
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = wrow0 + i * 4 + (lane >> 3);
+                        if (piece < nv && mt + row < p.M)
+                            stg_f4(p.x + (size_t)(mt + row) * p.ldx + kb * TC_BLOCK_K + piece * 4,
+                                   *reinterpret_cast<const float4*>(a_base + ((g % LA) * TC_BLOCK_M + row) * FG_ROW + piece * 4));
+                    }
                 }
                 if (kb < p.nkb_emb) {
 #pragma unroll
@@ -250,6 +292,7 @@ deepfm_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(&ready_op[o]);
+                w_wk += FG_T() - c3;
             }
             // FM second order of this sample: 0.5 * (sum_d s_d^2 - sum_{f,d} e^2); handed to the tail through shared memory
             float ss = 0.f;
@@ -271,6 +314,7 @@ deepfm_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_
             for (int j = 0; j < 16; ++j) fs[j] = 0.f;
         }
         fg_wait<0>();
+        if (trace && r == 0) { g_fg_trace[1] = (unsigned long long)w_cp; g_fg_trace[2] = (unsigned long long)w_eo; g_fg_trace[3] = (unsigned long long)w_wk; }
     } else {
         // ---------------- epilogue warps: layer-1 epilogue -> h1 (HBM + shared memory) -> tower tail (tower_tile.cuh)
         const int quarter = warp & 3;
@@ -286,8 +330,10 @@ deepfm_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_
             const int m0 = ((int)blockIdx.x + t * (int)gridDim.x) * TC_BLOCK_M;
             const uint32_t acc = (uint32_t)t & 1u;
             const int m = m0 + row;
+            const long long q0 = FG_T();
             mbar_wait(&tmem_full[acc], ((uint32_t)t >> 1) & 1u);
             tc_fence_after();
+            const long long q1 = FG_T();
             epi_sync();                                // previous tile's activations fully consumed (weights visible)
             for (int c0 = half * 16; c0 < FG_N; c0 += 32) {
                 uint32_t a0[16], a1[16];
@@ -309,14 +355,20 @@ deepfm_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             mbar_wait(&fm_ready[t % FG_FM_BUF], ((uint32_t)t / FG_FM_BUF) & 1u);
             epi_sync();
+            const long long q2 = FG_T();
             tower_tail_tile_fwd<FG_EPI_WARPS * 32>(tw, tw_As, tw_Bs, m0, et, tw_wo, tw_bo, loss_acc, epi_sync,
                                                    fm_tile + (t % FG_FM_BUF) * TC_BLOCK_M);
+            if (trace && et == 0) {
+                g_fg_trace[8] += (unsigned long long)(q1 - q0); g_fg_trace[9] += (unsigned long long)(q2 - q1);
+                g_fg_trace[10] += (unsigned long long)(FG_T() - q2);
+            }
         }
         if (tw.loss != nullptr) tw_loss[et] = loss_acc;
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+    if (trace && threadIdx.x == 0) g_fg_trace[0] = (unsigned long long)(clock64() - t_start);
     if (tw.loss != nullptr && warp == 0) {
         // deterministic mean BCE: 256 epilogue partials -> per-CTA partial -> the last CTA adds them in index order
         float s = 0.f;
@@ -352,6 +404,19 @@ static size_t fg_smem_bytes(int la, int n_tail) {
 }  // namespace rpb
 
 using namespace rpb;
+
+RPB_API int rpb_debug_fused_trace(uint64_t* out16, int enable) {
+    int on = enable != 0;
+    cudaError_t e = cudaSuccess;
+    if (out16 != nullptr) {
+        e = cudaMemcpyFromSymbol(out16, g_fg_trace, sizeof(unsigned long long) * 16);
+        if (e != cudaSuccess) return (int)e;
+    }
+    static const unsigned long long zeros[16] = {};
+    e = cudaMemcpyToSymbol(g_fg_trace, zeros, sizeof(zeros));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_fg_trace_on, &on, sizeof(int));
+    return (int)e;
+}
 
 RPB_API int rpb_deepfm_fwd_fused(const RpbGatherDesc* g, const float* W1, const float* b1, const RpbTowerFwdDesc* d,
                                  void* stream) {
