@@ -17,7 +17,7 @@ import torch.nn.functional as F
 __all__ = [
     "sparse_cols", "dense_cols", "embedding_layer", "get_linear_input", "fm_layer",
     "bi_interaction", "mlp", "lr_layer", "crossnet", "cin", "senet", "bilinear_field_interaction",
-    "mhsa", "bce_mean", "deepfm", "xdeepfm", "autoint", "dcn", "fibinet", "fm", "wdl", "nfm", "mmoe",
+    "mhsa", "bce_mean", "deepfm", "xdeepfm", "autoint", "dcn", "fibinet", "afm", "fm", "wdl", "nfm", "mmoe",
     "sharebottom", "omoe", "mlmmoe", "essm", "MODEL_FORWARDS",
 ]
 
@@ -328,7 +328,13 @@ def essm(sd, enc_dict, data, is_training=True, hidden_dim=(128, 64), dropouts=(0
     return out
 
 
+def afm(sd, enc_dict, data, is_training=True, hidden_units=(64, 64, 64)):
+    """AFM.forward (models/ranking/afm.py:38-67) — the same statements as FiBiNet.forward (fibinet.py:46-77)."""
+    return fibinet(sd, enc_dict, data, is_training=is_training, hidden_units=hidden_units)
+
+
 MODEL_FORWARDS = {
+    'AFM': afm,
     'DeepFM': deepfm, 'xDeepFM': xdeepfm, 'AutoInt': autoint, 'DCN': dcn, 'FiBiNet': fibinet,
     'FM': fm, 'WDL': wdl, 'NFM': nfm, 'MMOE': mmoe, 'ShareBottom': sharebottom, 'OMOE': omoe, 'MLMMOE': mlmmoe, 'ESSM': essm,
 }

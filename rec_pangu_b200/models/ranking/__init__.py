@@ -7,4 +7,5 @@ from .autoint import AutoInt
 from .fm import FM
 from .xdeepfm import xDeepFM
 from .dcn import DCN
-from ._unported import AFM, AFN, AOANet, CCPM, LR, MaskNet
+from .afm import AFM
+from ._unported import AFN, AOANet, CCPM, LR, MaskNet

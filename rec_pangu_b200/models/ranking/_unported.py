@@ -1,4 +1,4 @@
-"""Reference ranking classes that are outside the north-star hot path (AFM, AFN, AOANet,
+"""Reference ranking classes that are outside the north-star hot path (AFN, AOANet,
 CCPM, MaskNet, LR are not named by BASELINE.json's north_star).  The names exist so that
 `from rec_pangu.models.ranking import ...` lines in the reference's examples import unchanged; constructing one
 fails loudly instead of silently running a non-B200 path."""
@@ -9,12 +9,11 @@ def _unported(name):
         def __init__(self, *args, **kwargs):
             raise NotImplementedError(
                 f'{name} is not part of the B200 hot-path scope (SURVEY.md §8); use one of WDL, DeepFM, NFM, '
-                f'FiBiNet, AutoInt, FM, xDeepFM, DCN')
+                f'FiBiNet, AFM, AutoInt, FM, xDeepFM, DCN')
     _Unported.__name__ = name
     return _Unported
 
 
-AFM = _unported('AFM')
 AFN = _unported('AFN')
 AOANet = _unported('AOANet')
 CCPM = _unported('CCPM')

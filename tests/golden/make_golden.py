@@ -29,7 +29,7 @@ sys.path.insert(0, '/root/reference')
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
-from rec_pangu.models.ranking import DeepFM, xDeepFM, AutoInt, DCN, FiBiNet, FM, WDL, NFM  # noqa: E402
+from rec_pangu.models.ranking import DeepFM, xDeepFM, AutoInt, DCN, FiBiNet, FM, WDL, NFM, AFM  # noqa: E402
 from rec_pangu.models.multi_task import MMOE, ShareBottom, OMOE, MLMMOE, ESSM  # noqa: E402
 from rec_pangu.models.layers import (FM_Layer, MLP, CrossNet, CompressedInteractionNet, SENET_Layer,  # noqa: E402
                                      BilinearInteractionLayer, MultiHeadSelfAttention, InnerProductLayer)
@@ -232,6 +232,9 @@ if __name__ == '__main__':
     if '--only-multitask' in sys.argv:            # ShareBottom / OMOE / MLMMOE fixtures only (added after the first set)
         run_multitask_all()
         sys.exit(0)
+    if '--only-afm' in sys.argv:                  # AFM fixture only (added after the first set)
+        run_model('afm', AFM, {'hidden_units': [16, 8]}, n_sparse=5, n_dense=2, seed=2029)
+        sys.exit(0)
     run_layers()
     run_model('deepfm', DeepFM, {'hidden_units': [16, 8]})
     run_model('deepfm_d16', DeepFM, {'hidden_units': [32, 16, 8]}, n_sparse=7, n_dense=4, D=16, B=40)
@@ -240,6 +243,7 @@ if __name__ == '__main__':
     run_model('autoint_l2', AutoInt, {'dnn_hidden_units': [16], 'num_heads': 2, 'attention_dim': 4, 'attention_layers': 2})
     run_model('dcn', DCN, {'crossing_layers': 3})
     run_model('fibinet', FiBiNet, {'hidden_units': [16, 8]}, n_sparse=6)
+    run_model('afm', AFM, {'hidden_units': [16, 8]}, n_sparse=5, n_dense=2, seed=2029)
     run_model('fm', FM, {})
     run_model('wdl', WDL, {'hidden_units': [16, 8]})
     run_model('nfm', NFM, {'hidden_units': [16, 8]})

@@ -34,6 +34,7 @@ def test_constructor_signatures_match_reference():
         'AutoInt': ['embedding_dim', 'dnn_hidden_units', 'attention_layers', 'num_heads', 'attention_dim', 'loss_fun', 'enc_dict'],
         'DCN': ['embedding_dim', 'hidden_units', 'crossing_layers', 'loss_fun', 'enc_dict'],
         'FiBiNet': ['embedding_dim', 'hidden_units', 'loss_fun', 'enc_dict'],
+        'AFM': ['embedding_dim', 'hidden_units', 'loss_fun', 'enc_dict'],
         'FM': ['embedding_dim', 'loss_fun', 'enc_dict'],
         'WDL': ['embedding_dim', 'hidden_units', 'loss_fun', 'enc_dict'],
         'NFM': ['embedding_dim', 'hidden_units', 'loss_fun', 'enc_dict'],
@@ -45,7 +46,7 @@ def test_constructor_signatures_match_reference():
         assert sig.parameters['loss_fun'].default == 'torch.nn.BCELoss()'
 
 
-@pytest.mark.parametrize('name', ['deepfm', 'deepfm_d16', 'fm', 'wdl', 'nfm', 'dcn', 'xdeepfm', 'autoint', 'autoint_l2', 'fibinet'])
+@pytest.mark.parametrize('name', ['deepfm', 'deepfm_d16', 'fm', 'wdl', 'nfm', 'dcn', 'xdeepfm', 'autoint', 'autoint_l2', 'fibinet', 'afm'])
 def test_state_dict_contract_matches_reference(name):
     """Same keys and shapes as the reference's state_dict (so reference checkpoints load and vice versa)."""
     from rec_pangu_b200.models import ranking

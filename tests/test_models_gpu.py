@@ -21,7 +21,7 @@ def _logit(p):
     return torch.log(p) - torch.log1p(-p)
 
 
-RANKING_GOLDEN = ['deepfm', 'deepfm_d16', 'fm', 'wdl', 'nfm', 'dcn', 'xdeepfm', 'autoint', 'autoint_l2', 'fibinet']
+RANKING_GOLDEN = ['deepfm', 'deepfm_d16', 'fm', 'wdl', 'nfm', 'dcn', 'xdeepfm', 'autoint', 'autoint_l2', 'fibinet', 'afm']
 
 
 @pytest.mark.parametrize('name', RANKING_GOLDEN)
