@@ -491,7 +491,8 @@ def run_ours(args):
                                    f'dense grads NCCL all-reduce') if world > 1 else 'single',
                    'launch': launch_mode, 'l2': 'inputs larger than L2: 4 rotating batches over 1.66 GB of tables',
                    'gemm': {0: 'auto(tcgen05 3xTF32)', 1: 'simt fp32', 2: 'tcgen05 3xTF32'}[ops.get_gemm_impl()],
-                   'grad_mode': 'persistent' if world == 1 else 'sharded'},
+                   'grad_mode': 'persistent' if world == 1 else 'sharded',
+                   'sharded_fused_core': bool(ops.SHARDED_FUSED) if world > 1 else None},
         'e2e': e2e, 'gpu_launches': launches_per_step * args.steps, 'clocks': clocks, 'roofline': roofline,
         'train_step': train_step, 'zipf_ids': zipf, 'torch_eager_gpu_baseline': eager_gpu,
     }

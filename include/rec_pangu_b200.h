@@ -136,8 +136,9 @@ int rpb_linear_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, c
 
 /* First-layer dx GEMM fused with the gradient scatter: computes dx = dy[M,N] @ W[N,K] tile by tile on tcgen05 and, in
  * the epilogue, adds dx[m, f*D:(f+1)*D] + dfm[m]*(fm_s[m,:] - x[m, f*D:(f+1)*D]) straight into grads[f][idx[f][m], :]
- * (fields of RpbScatterDesc: B (= M), F, D, grads, rows, idx, x, ldx, dfm, fm_s; dx / lddx / LR fields are ignored,
- * sharded tables unsupported).  dx is never written to HBM.  Returns RPB_ERR_UNSUPPORTED when the persistent tcgen05
+ * (fields of RpbScatterDesc: B (= M), F, D, grads, rows, idx, x, ldx, dfm, fm_s, G, grad_shard_tab; dx / lddx / LR
+ * fields are ignored).  With G > 1 the reductions go to the owners' gradient shards (local HBM or NVLink peer memory)
+ * and grads[f] != NULL only marks table f as trainable.  dx is never written to HBM.  Returns RPB_ERR_UNSUPPORTED when the persistent tcgen05
  * kernel cannot take the shape (the caller then runs rpb_linear_bwd + rpb_gather_bwd). */
 int rpb_linear_dx_scatter(const float* dy, int64_t lddy, const float* W, int M, int N, int K,
                           const RpbScatterDesc* d, void* stream);
@@ -203,7 +204,8 @@ int rpb_linear_tower_fwd(const float* x, int64_t ldx, const float* W1, const flo
  * k-blocks) and the FM term is formed from the registers that feed the MMAs.  Uses of `g`: B, F, D (= 16), Nd, tables,
  * rows, idx, dense, err; x / fm / fm_s are OPTIONAL outputs (x and fm_s only when backward needs them; ldx as for
  * rpb_gather_fwd).  `d` as for rpb_linear_tower_fwd (d->h1 is an output, d->addend is ignored: the FM term is added inside).
- * Needs D == 16, an even F, unsharded tables, n_tail >= 1, M >= 512; RPB_ERR_UNSUPPORTED otherwise (the caller then runs
+ * Row-sharded tables (g->G > 1, g->shard_tab): the same row requests go to the owner's shard, local or over NVLink.
+ * Needs D == 16, an even F, n_tail >= 1, M >= 512; RPB_ERR_UNSUPPORTED otherwise (the caller then runs
  * rpb_gather_fwd + rpb_linear_tower_fwd). */
 int rpb_deepfm_fwd_fused(const RpbGatherDesc* g, const float* W1, const float* b1, const RpbTowerFwdDesc* d, void* stream);
 /* Per-role stall cycles of CTA 0 of the last rpb_deepfm_fwd_fused launch (same protocol as rpb_debug_tc_trace; see

@@ -40,6 +40,11 @@ struct TcScatter {
     const float* dfm;                    // [M] or null
     const float* fm_s;                   // [M, D] or null
     int F, D, enabled;
+    // row-sharded gradient buffers (RpbScatterDesc.G / grad_shard_tab): owner = id mod G, local row = id div G, entry
+    // f*G+g of the DEVICE array = rank g's gradient shard of table f; remote shards take the reductions over NVLink.
+    // G <= 1: `grads` holds the buffers.  With G > 1 grads[f] is only the "table f is trainable" flag.
+    int G;
+    float* const* grad_shard_tab;
 };
 
 struct TowerFwdParams;   // tower_tile.cuh

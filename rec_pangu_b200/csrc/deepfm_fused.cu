@@ -37,6 +37,10 @@ struct FusedFwdParams {
     long long* err;
     float* h1; long long ldh1; const float* bias1;
     int M, F, Nd, nkb, nkb_emb;
+    // row-sharded tables (RpbGatherDesc.G / shard_tab): owner = id mod G, local row = id div G; entry f*G+g of the DEVICE
+    // array = rank g's shard of table f, local or mapped over NVLink (the row request is the same cp.async either way)
+    int G;
+    const float* const* shard_tab;
 };
 
 // table rows: 16-byte pieces of a 64-byte row; the L2 fetch is capped at 64 B so that a row does not drag the other half
@@ -68,7 +72,7 @@ __device__ int g_fg_trace_on = 0;
 __device__ unsigned long long g_fg_trace[16];
 #define FG_T() (trace ? clock64() : 0ll)
 
-template <int LA>
+template <int LA, bool SHARDED>
 __global__ void __launch_bounds__(FG_THREADS, 1)
 deepfm_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
                         const __grid_constant__ FusedFwdParams p, const __grid_constant__ TowerFwdParams tw, int m_tiles) {
@@ -194,7 +198,15 @@ deepfm_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_
                         long long id = id_base[(slot * TC_BLOCK_M + row) * 2 + fsel];
                         if (!ok) id = 0;
                         else if ((unsigned long long)id >= (unsigned long long)p.rows[f]) { if (piece == 0) fg_bad_index(p.err, f, mt + row, id); id = 0; }
-                        fg_cp16(a_base + (slot * TC_BLOCK_M + row) * FG_ROW + fsel * 16 + piece * 4, p.tables[f] + (size_t)id * 16 + piece * 4, ok);
+                        const float* src;
+                        if constexpr (SHARDED) {
+                            const unsigned iu = (unsigned)id, gg = (unsigned)p.G;
+                            const float* base = reinterpret_cast<const float*>(__ldg(reinterpret_cast<const unsigned long long*>(p.shard_tab) + (size_t)f * gg + (iu % gg)));
+                            src = base + (size_t)(iu / gg) * 16 + piece * 4;
+                        } else {
+                            src = p.tables[f] + (size_t)id * 16 + piece * 4;
+                        }
+                        fg_cp16(a_base + (slot * TC_BLOCK_M + row) * FG_ROW + fsel * 16 + piece * 4, src, ok);
                     }
                 } else {
                     const int m = mt + r;
@@ -424,10 +436,12 @@ RPB_API int rpb_deepfm_fwd_fused(const RpbGatherDesc* g, const float* W1, const 
     TowerFwdParams tw{};
     const int prc = tower_fwd_params(d, &tw);
     if (prc != 0) return prc;
-    if (g->B != d->M || g->tables == nullptr || g->rows == nullptr || g->idx == nullptr || (g->Nd > 0 && g->dense == nullptr))
+    if (g->B != d->M || (g->tables == nullptr && g->G <= 1) || g->rows == nullptr || g->idx == nullptr || (g->Nd > 0 && g->dense == nullptr))
         return RPB_ERR_BAD_ARG;
-    // shapes this kernel is built for: 64-byte rows, an even number of fields (one k-block = two fields), unsharded tables
-    if (g->D != 16 || g->F < 2 || (g->F & 1) || g->F > RPB_MAX_FIELDS || g->Nd > RPB_MAX_DENSE || g->G > 1 || g->lr_tables != nullptr ||
+    // shapes this kernel is built for: 64-byte rows, an even number of fields (one k-block = two fields)
+    const bool sharded = g->G > 1;
+    if (sharded && g->shard_tab == nullptr) return RPB_ERR_BAD_ARG;
+    if (g->D != 16 || g->F < 2 || (g->F & 1) || g->F > RPB_MAX_FIELDS || g->Nd > RPB_MAX_DENSE || g->lr_tables != nullptr ||
         g->lr_in != nullptr || d->n_tail < 1 || d->M < 512 || !g_gemm_v2 || (d->ldh1 & 3) != 0)
         return RPB_ERR_UNSUPPORTED;
     const int K = g->F * 16 + g->Nd;
@@ -435,10 +449,9 @@ RPB_API int rpb_deepfm_fwd_fused(const RpbGatherDesc* g, const float* W1, const 
     if (g->fm_s != nullptr && (reinterpret_cast<uintptr_t>(g->fm_s) & 15u)) return RPB_ERR_UNSUPPORTED;
     FusedFwdParams p{};
     for (int f = 0; f < g->F; ++f) {
-        if (g->tables[f] == nullptr || g->idx[f] == nullptr || (reinterpret_cast<uintptr_t>(g->tables[f]) & 15u) ||
-            (reinterpret_cast<uintptr_t>(g->idx[f]) & 7u))
-            return RPB_ERR_UNSUPPORTED;
-        p.tables[f] = g->tables[f];
+        if (g->idx[f] == nullptr || (reinterpret_cast<uintptr_t>(g->idx[f]) & 7u)) return RPB_ERR_UNSUPPORTED;
+        if (!sharded && (g->tables[f] == nullptr || (reinterpret_cast<uintptr_t>(g->tables[f]) & 15u))) return RPB_ERR_UNSUPPORTED;
+        p.tables[f] = sharded ? nullptr : g->tables[f];
         p.idx[f] = reinterpret_cast<const long long*>(g->idx[f]);
         p.rows[f] = g->rows[f];
     }
@@ -449,6 +462,8 @@ RPB_API int rpb_deepfm_fwd_fused(const RpbGatherDesc* g, const float* W1, const 
     p.x = g->x; p.ldx = g->ldx; p.fm = g->fm; p.fm_s = g->fm_s; p.err = reinterpret_cast<long long*>(g->err);
     p.h1 = const_cast<float*>(d->h1); p.ldh1 = d->ldh1; p.bias1 = b1;
     p.M = d->M; p.F = g->F; p.Nd = g->Nd;
+    p.G = sharded ? g->G : 1;
+    p.shard_tab = sharded ? g->shard_tab : nullptr;
     p.nkb_emb = g->F / 2;
     p.nkb = p.nkb_emb + ceil_div(g->Nd, TC_BLOCK_K);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -460,9 +475,15 @@ RPB_API int rpb_deepfm_fwd_fused(const RpbGatherDesc* g, const float* W1, const 
     auto launch = [&](auto la_tag) -> int {
         constexpr int LA = decltype(la_tag)::value;
         const size_t smem = fg_smem_bytes(LA, d->n_tail);
-        cudaError_t e = cudaFuncSetAttribute(deepfm_fwd_fused_kernel<LA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (sharded) {
+            cudaError_t e = cudaFuncSetAttribute(deepfm_fwd_fused_kernel<LA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            deepfm_fwd_fused_kernel<LA, true><<<grid, FG_THREADS, smem, st>>>(tmBhi, tmBlo, p, tw, m_tiles);
+            return (int)cudaGetLastError();
+        }
+        cudaError_t e = cudaFuncSetAttribute(deepfm_fwd_fused_kernel<LA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        deepfm_fwd_fused_kernel<LA><<<grid, FG_THREADS, smem, st>>>(tmBhi, tmBlo, p, tw, m_tiles);
+        deepfm_fwd_fused_kernel<LA, false><<<grid, FG_THREADS, smem, st>>>(tmBhi, tmBlo, p, tw, m_tiles);
         return (int)cudaGetLastError();
     };
     const size_t cap = 227 * 1024;

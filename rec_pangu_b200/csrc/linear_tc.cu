@@ -230,7 +230,7 @@ constexpr int V2_EPI_WARPS = 8;
 constexpr int V2_OP_STAGES = 2;       // shared-memory operand ring (SS mode)
 constexpr int V2_MAX_OP = 4;          // tensor-memory operand ring (TS mode): up to 4 stages of 64 columns
 
-template <int kRaw>
+template <int kRaw, bool kShardedScatter>
 __global__ void __launch_bounds__(V2_THREADS, 1)
 gemm_tf32x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                       const __grid_constant__ CUtensorMap tmBlo, const TcEpilogue ep, int block_n, int num_k_blocks,
@@ -555,7 +555,15 @@ gemm_tf32x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                                         gv.x = fmaf(cf[j], sv.x - e[u][j].x, gv.x); gv.y = fmaf(cf[j], sv.y - e[u][j].y, gv.y);
                                         gv.z = fmaf(cf[j], sv.z - e[u][j].z, gv.z); gv.w = fmaf(cf[j], sv.w - e[u][j].w, gv.w);
                                     }
-                                    red_add_f4(sc.grads[f] + (size_t)ix[u][j] * sc.D + d, gv);
+                                    float* grow;
+                                    if constexpr (kShardedScatter) {   // row-sharded gradients: owner = id mod G, local row = id div G
+                                        const unsigned iu = (unsigned)ix[u][j], gg = (unsigned)sc.G;
+                                        float* base = reinterpret_cast<float*>(__ldg(reinterpret_cast<const unsigned long long*>(sc.grad_shard_tab) + (size_t)f * gg + (iu % gg)));
+                                        grow = base + (size_t)(iu / gg) * sc.D + d;
+                                    } else {
+                                        grow = sc.grads[f] + (size_t)ix[u][j] * sc.D + d;
+                                    }
+                                    red_add_f4(grow, gv);
                                 }
                             }
                         }
@@ -964,14 +972,21 @@ int gemm_tc(const float* A, long long lda, const float* Bsrc, long long ldb, int
                 constexpr int R = decltype(raw_tag)::value;
                 const size_t smem = (size_t)R * raw_bytes + op_bytes + (b_resident ? bres_bytes : 0) +
                                     (2 * R + 2 * V2_MAX_OP + 4 + 2) * 8 + 1024 + tail_bytes;
-                cudaError_t ee = cudaFuncSetAttribute(gemm_tf32x3_v2_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                if (ee != cudaSuccess) return (int)ee;
                 static const TcScatter no_scatter{};
                 static const TowerFwdParams no_tail{};
-                gemm_tf32x3_v2_kernel<R><<<grid, V2_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, ep, block_n, nkb, m_tiles, n_tiles,
-                                                                        tmem_cols, b_resident, a_stages, stack_n,
-                                                                        ep.sc != nullptr ? *ep.sc : no_scatter,
-                                                                        tail ? *ep.tail : no_tail);
+                if (ep.sc != nullptr && ep.sc->G > 1) {          // scatter epilogue into row-sharded gradient buffers
+                    cudaError_t es = cudaFuncSetAttribute(gemm_tf32x3_v2_kernel<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    if (es != cudaSuccess) return (int)es;
+                    gemm_tf32x3_v2_kernel<R, true><<<grid, V2_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, ep, block_n, nkb, m_tiles, n_tiles,
+                                                                                  tmem_cols, b_resident, a_stages, stack_n, *ep.sc, no_tail);
+                    return (int)cudaGetLastError();
+                }
+                cudaError_t ee = cudaFuncSetAttribute(gemm_tf32x3_v2_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (ee != cudaSuccess) return (int)ee;
+                gemm_tf32x3_v2_kernel<R, false><<<grid, V2_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, ep, block_n, nkb, m_tiles, n_tiles,
+                                                                               tmem_cols, b_resident, a_stages, stack_n,
+                                                                               ep.sc != nullptr ? *ep.sc : no_scatter,
+                                                                               tail ? *ep.tail : no_tail);
                 return (int)cudaGetLastError();
             };
             if (max_raw >= 6) return launch(std::integral_constant<int, 6>{});
@@ -1157,7 +1172,9 @@ RPB_API int rpb_debug_tc_trace(uint64_t* out16, int enable) {
 RPB_API int rpb_linear_dx_scatter(const float* dy, int64_t lddy, const float* W, int M, int N, int K,
                                   const RpbScatterDesc* d, void* stream) {
     if (dy == nullptr || W == nullptr || d == nullptr || M <= 0 || N <= 0 || K <= 0) return RPB_ERR_BAD_ARG;
-    if (d->B != M || d->F > RPB_MAX_FIELDS || d->F * d->D > K || (d->D % 4) != 0 || d->G > 1) return RPB_ERR_UNSUPPORTED;
+    if (d->B != M || d->F > RPB_MAX_FIELDS || d->F * d->D > K || (d->D % 4) != 0) return RPB_ERR_UNSUPPORTED;
+    const bool sharded = d->G > 1;
+    if (sharded && d->grad_shard_tab == nullptr) return RPB_ERR_BAD_ARG;
     if (d->dfm != nullptr && (d->x == nullptr || d->fm_s == nullptr || (d->ldx % 4) != 0)) return RPB_ERR_BAD_ARG;
     if (!g_gemm_v2 || !tc_shape_ok(dy, lddy, M, K, N)) return RPB_ERR_UNSUPPORTED;
     TcScatter sc{};
@@ -1168,6 +1185,8 @@ RPB_API int rpb_linear_dx_scatter(const float* dy, int64_t lddy, const float* W,
         if (sc.grads[f] != nullptr && (reinterpret_cast<uintptr_t>(sc.grads[f]) & 15u)) return RPB_ERR_UNSUPPORTED;
     }
     sc.x = d->x; sc.ldx = d->ldx; sc.dfm = d->dfm; sc.fm_s = d->fm_s; sc.F = d->F; sc.D = d->D;
+    sc.G = sharded ? d->G : 1;
+    sc.grad_shard_tab = sharded ? d->grad_shard_tab : nullptr;
     // enabled == 2: walk the sample tiles from the END — the layer-1 weight gradient that runs just before this kernel
     // streamed x front to back, so the tail of x is what is still in L2 when the scatter starts re-reading it
     sc.enabled = g_scatter_reverse ? 2 : 1;

@@ -38,6 +38,10 @@ def _side_stream(dev) -> 'torch.cuda.Stream':
 
 # 1 = DeepFM forward as ONE kernel: the layer-1 GEMM gathers its own operand rows (rpb_deepfm_fwd_fused)
 FUSED_GATHER_GEMM = int(__import__('os').environ.get('RPB_FUSED_GATHER_GEMM', '1'))
+# Row-sharded tables (dist.ShardedTables): 1 = DeepFM runs its fused core on them too — the one-kernel forward requests
+# remote rows with the same cp.async over NVLink and the dx GEMM's scatter epilogue reduces into the owners' gradient
+# shards — instead of the separate gather / MLP / dx GEMM / scatter kernels.  Opt-in until measured on >= 2 GPUs.
+SHARDED_FUSED = int(__import__('os').environ.get('RPB_SHARDED_FUSED', '0'))
 _LAUNCHES = 0           # number of librec_pangu_b200 kernels launched (bench.py reports it as gpu_launches)
 
 
@@ -728,7 +732,7 @@ def _tower_fwd(cfg, x, params, addend=None, head=None):
     return logit, [x, y1] + hs, pred, loss
 
 
-def _deepfm_fused_fwd(cfg, tables, idx, dense, params, head, need_grad):
+def _deepfm_fused_fwd(cfg, tables, idx, dense, params, head, need_grad, shards=None):
     """rpb_deepfm_fwd_fused: gather + FM + layer 1 + tower tail (+ sigmoid/BCE) in one launch.  Returns None when the
     shape is outside what that kernel takes, else (logit, acts, pred, loss, fm_s, rows) like _gather_fwd_raw + _tower_fwd."""
     F, Nd, D = len(tables), len(dense), int(tables[0].shape[1])
@@ -741,7 +745,7 @@ def _deepfm_fused_fwd(cfg, tables, idx, dense, params, head, need_grad):
     ldx = feature_row_stride(F, D, Nd)
     x = torch.empty((M, ldx), dtype=torch.float32, device=dev) if need_grad else None
     fm_s = torch.empty((M, D), dtype=torch.float32, device=dev) if need_grad else None
-    rows = [int(t.shape[0]) for t in tables]
+    rows = [int(t.shape[0]) for t in tables] if shards is None else list(shards.rows)      # sharded: GLOBAL row counts
     g = GatherDesc()
     g.B, g.F, g.D, g.Nd, g.ldx, g.ld_lr = M, F, D, Nd, ldx, 0
     keep = [_ptr_list(tables), (C.c_int64 * F)(*rows), _ptr_list(idx)]
@@ -749,6 +753,8 @@ def _deepfm_fused_fwd(cfg, tables, idx, dense, params, head, need_grad):
     if Nd:
         keep.append(_ptr_list(dense))
         g.dense = keep[-1]
+    if shards is not None:
+        g.G, g.shard_tab = shards.world, shards.w_tab.data_ptr()
     g.x, g.fm_s = _ptr(x), _ptr(fm_s)
     g.err = _err_record(dev).data_ptr()
     y1 = torch.empty((M, 64), dtype=torch.float32, device=dev)
@@ -907,8 +913,12 @@ class _DeepFMCore(torch.autograd.Function):
         pred = loss = None
         fused = None
         head = (label, 0.0, 1.0) if label is not None else None
+        st = gcfg.get('shards')
         if ctx.tower and FUSED_GATHER_GEMM and cfg['impl'] != 1:
-            fused = _deepfm_fused_fwd(cfg, tables, idx, dense, params, head, need_grad)
+            fused = _deepfm_fused_fwd(cfg, tables, idx, dense, params, head, need_grad, shards=st)
+        if st is not None and fused is None:
+            raise RuntimeError('fused DeepFM core on row-sharded tables: shape outside rpb_deepfm_fwd_fused (deepfm_core '
+                               'should have declined it)')
         if fused is not None:                          # gather + FM + layer 1 + tail + loss: one kernel
             logit, acts, pred, loss, fm_s, rows = fused
             pre_drop, seeds = [None] * cfg['n_hidden'], [0] * cfg['n_hidden']
@@ -951,7 +961,13 @@ class _DeepFMCore(torch.autograd.Function):
         tables = ctx.tables
         tbl_req = ctx.needs_input_grad[2:2 + F]
         store = gcfg.get('grad_store')
-        if store is not None:
+        st = gcfg.get('shards')
+        if st is not None:
+            # row-sharded: the scatter reduces into the owners' gradient shards (local HBM or NVLink); g_tables are this
+            # rank's own shards and only flag which tables are trainable
+            store = None
+            g_tables = [st.grads[f] if tbl_req[f] else None for f in range(F)]
+        elif store is not None:
             trainable = [tables[f] for f in range(F) if tbl_req[f]]
             if store.pending and all(t.grad is None for t in trainable):
                 store.clean()
@@ -967,6 +983,8 @@ class _DeepFMCore(torch.autograd.Function):
             d.dfm, d.x, d.ldx, d.fm_s = dlogit.data_ptr(), x.data_ptr(), x.stride(0), fm_s.data_ptr()   # dL/dfm = dlogit
             d._keep = (_ptr_list(g_tables), (C.c_int64 * F)(*ctx.rows), _ptr_list(idx), dlogit)
             d.grads, d.rows, d.idx = d._keep[:3]
+            if st is not None:
+                d.G, d.grad_shard_tab = st.world, st.g_tab.data_ptr()
             return d
 
         def hook(dh, lddh, W0, dlogit):
@@ -1010,7 +1028,13 @@ class _DeepFMCore(torch.autograd.Function):
             check(_lib.load().rpb_gather_bwd(C.byref(d), _stream()), 'rpb_gather_bwd')
             _count()
         out: List[Optional[torch.Tensor]] = [None] * ctx.n_inputs
-        if store is not None:
+        if st is not None:
+            st.pending.append(list(idx))
+            st.barrier()                                  # every rank's remote gradient adds have landed
+            for f in range(F):
+                if g_tables[f] is not None:
+                    tables[f].grad = g_tables[f]
+        elif store is not None:
             store.pending.append((g_tables, None, ctx.rows, idx, D))
             for f in range(F):
                 if g_tables[f] is None:
@@ -1054,10 +1078,13 @@ def _gather_fwd_raw(tables, idx, dense, want_fm, need_grad):
 
 
 def deepfm_core(tables, idx, dense, weights, biases, n_hidden, relu, dropout, training, grad_store=None,
-                impl: Optional[int] = None, label: Optional[torch.Tensor] = None):
+                impl: Optional[int] = None, label: Optional[torch.Tensor] = None, shards=None):
     """logit [B,1] of DeepFM (FM second order + MLP over [emb | dense]) as one fused autograd node.  With `label` ([B]
     fp32) and a tower-shaped MLP (see _tower_ok) the node also yields sigmoid(logit) and the mean BCE from the same
-    launch that finishes the MLP: returns (logit, pred [B,1], loss) instead of logit."""
+    launch that finishes the MLP: returns (logit, pred [B,1], loss) instead of logit.
+
+    `shards` (dist.ShardedTables): `tables` are this rank's shard Parameters; the node then needs the one-kernel forward
+    (rpb_deepfm_fwd_fused) and returns None when the shape is outside it (the caller runs the unfused sharded path)."""
     F = len(tables)
     D = int(tables[0].shape[1])
     for t in tables:
@@ -1075,12 +1102,15 @@ def deepfm_core(tables, idx, dense, weights, biases, n_hidden, relu, dropout, tr
     cfg = dict(n_hidden=n_hidden, has_out=True, K=F * D + len(dense_l), relu=list(relu), dropout=list(dropout),
                training=training, impl=_GEMM_IMPL if impl is None else impl)
     tower = _tower_ok(cfg, params)
+    if shards is not None and not (tower and FUSED_GATHER_GEMM and cfg['impl'] != 1 and D == 16 and F % 2 == 0 and
+                                   n_hidden >= 2 and idx_l[0].shape[0] >= 512):
+        return None
     extra = []
     if label is not None and tower:
         _cuda(label, 'label')
         extra = [label.reshape(-1).float().contiguous()]
-    gcfg = dict(F=F, Nd=len(dense_l), D=D, needs_grad=needs_grad, grad_store=grad_store, tower=tower,
-                has_label=bool(extra))
+    gcfg = dict(F=F, Nd=len(dense_l), D=D, needs_grad=needs_grad, grad_store=grad_store if shards is None else None,
+                tower=tower, has_label=bool(extra), shards=shards)
     return _DeepFMCore.apply(cfg, gcfg, *tables, *idx_l, *dense_l, *params, *extra)
 
 

@@ -13,20 +13,21 @@ from rec_pangu_b200 import dist as rdist, ops
 from rec_pangu_b200.models.ranking import DeepFM
 
 
-def check(rank, world, dev, hidden):
+def check(rank, world, dev, hidden, D=8, B=96, fused=False):
     """hidden = [16, 8]: layer-by-layer MLP kernels; [64, 64]: the fused tower-tail kernels (single-GPU reference with the
-    loss fused into the DeepFM core node, sharded model through MLP + the separate sigmoid/BCE head)."""
+    loss fused into the DeepFM core node, sharded model through MLP + the separate sigmoid/BCE head).
+    fused (D = 16, B >= 512, 64-wide tower): the sharded model runs the fused core too (ops.SHARDED_FUSED): one-kernel
+    forward with remote row requests, dx GEMM with the scatter epilogue into the owners' gradient shards."""
     enc = make_enc(6, 3, [101, 57, 33, 200, 17, 64])
-    B = 96
     torch.manual_seed(7)
-    ref = DeepFM(embedding_dim=8, hidden_units=hidden, enc_dict=enc)
+    ref = DeepFM(embedding_dim=D, hidden_units=hidden, enc_dict=enc)
     with torch.no_grad():
         for n, p in ref.named_parameters():
             if 'embedding_layer' in n:
                 p.mul_(0.3)
     sd = {k: v.clone() for k, v in ref.state_dict().items()}
     ref = ref.to(dev)
-    model = DeepFM(embedding_dim=8, hidden_units=hidden, enc_dict=enc)
+    model = DeepFM(embedding_dim=D, hidden_units=hidden, enc_dict=enc)
     model.load_state_dict(sd)
     model = model.to(dev)
     st = rdist.shard_model_tables(model)
@@ -42,10 +43,16 @@ def check(rank, world, dev, hidden):
         ro['loss'].backward()
         # sharded
         model.zero_grad()
+        ops.SHARDED_FUSED = 1 if fused else 0
+        n0 = ops.launch_count()
         out = model(mine)
+        n_fwd = ops.launch_count() - n0
         (out['loss'] / world).backward()
+        ops.SHARDED_FUSED = 0
         bucket.all_reduce()
         ops.check_index_errors(dev)
+        if fused:
+            assert n_fwd == 2, f'fused sharded forward should be weight split + one kernel, saw {n_fwd} launches'
         torch.testing.assert_close(out['pred'], ro['pred'][rank * B:(rank + 1) * B], rtol=1e-5, atol=1e-6)
         for f, c in enumerate(model.embedding_layer.emb_feature):
             g_full = st.full_grad(f)
@@ -130,6 +137,10 @@ def main():
     dev = torch.device('cuda', local)
     for hidden in ([16, 8], [64, 64]):
         check(rank, world, dev, hidden)
+    if os.environ.get('RPB_SHARDED_FUSED', '0') == '1':      # opt-in until measured on >= 2 GPUs (ops.SHARDED_FUSED)
+        check(rank, world, dev, [64, 64], D=16, B=640, fused=True)
+        if rank == 0:
+            print('SHARDED_FUSED_OK world', world, flush=True)
     check_mmoe_sync_bn(rank, world, dev)
     if rank == 0:
         print('SHARDED_OK world', world, flush=True)
