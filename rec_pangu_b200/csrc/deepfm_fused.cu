@@ -26,6 +26,15 @@ constexpr int FG_ROW = TC_BLOCK_K + 4;    // floats per staged row: 144 B, confl
 constexpr int FG_N = 64;                  // layer-1 width
 constexpr int FG_FM_BUF = 4;              // per-tile FM values handed from the split warps to the tail (see kernel)
 constexpr int FG_B_BYTES = 2 * FG_N * TC_BLOCK_K * 4;
+// TCTAIL variant (rpb_set_option("fused_tc_tail", 1); NOT YET RUN ON HARDWARE): the 64x64 tail layers run on tcgen05 too.
+// The epilogue warps turn the layer-1 accumulator into h1 = relu(acc + b1), store it, split it into (hi, lo) and write
+// it back into TENSOR MEMORY as the A operand of the next layer (TS-mode MMA, the same trick the gather warps use for
+// layer 1); the MMA issuer runs 8 k-steps x 2 MMAs against the resident stacked [W hi ; W lo] operand of that layer into
+// the accumulator buffer the tile just vacated, and so on down the tower.  The activations never touch shared memory,
+// which takes the tail's LDS.128 stream off the MIO pipe the gather warps are bound by (profiles/r01_experiments.md).
+// Tensor memory: 2 x 128 accumulator columns | FT_OP x 64 layer-1 operand ring | 128 columns tail operand (hi 64 | lo 64).
+constexpr int FT_OP = 2;
+constexpr int FT_TAIL_B_BYTES = 2 * FG_B_BYTES;     // one tail layer: 2 k-blocks of [W hi ; W lo] (128 rows x 128 B each)
 
 struct FusedFwdParams {
     const float* tables[RPB_MAX_FIELDS];
@@ -72,14 +81,17 @@ __device__ int g_fg_trace_on = 0;
 __device__ unsigned long long g_fg_trace[16];
 #define FG_T() (trace ? clock64() : 0ll)
 
-template <int LA, bool SHARDED>
+template <int LA, bool SHARDED, bool TCTAIL>
 __global__ void __launch_bounds__(FG_THREADS, 1)
 deepfm_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
+                        const __grid_constant__ CUtensorMap tmThi, const __grid_constant__ CUtensorMap tmTlo,
                         const __grid_constant__ FusedFwdParams p, const __grid_constant__ TowerFwdParams tw, int m_tiles) {
+    constexpr int OPN = TCTAIL ? FT_OP : FG_OP;                               // depth of the tensor-memory operand ring
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* b_base = smem;                                                   // FG_LB x 16 KiB, 1 KiB aligned (SWIZZLE_128B)
-    float* a_base = reinterpret_cast<float*>(b_base + FG_LB * FG_B_BYTES);    // LA x 128 rows x FG_ROW floats
+    uint8_t* t_base = b_base + FG_LB * FG_B_BYTES;                            // TCTAIL: n_tail x 32 KiB resident tail operands
+    float* a_base = reinterpret_cast<float*>(t_base + (TCTAIL ? tw.n_tail * FT_TAIL_B_BYTES : 0));   // LA x 128 rows x FG_ROW floats
     long long* id_base = reinterpret_cast<long long*>(a_base + LA * TC_BLOCK_M * FG_ROW);   // LA x 128 x 2 ids
     uint64_t* bars = reinterpret_cast<uint64_t*>(id_base + LA * TC_BLOCK_M * 2);
     uint64_t* full_b = bars;                       // [FG_LB]  weight k-block landed
@@ -89,11 +101,12 @@ deepfm_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_
     uint64_t* tmem_full = empty_op + FG_OP;        // [2]
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
     uint64_t* fm_ready = tmem_empty + 2;           // [FG_FM_BUF]  FM values of a tile written
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(fm_ready + FG_FM_BUF);
+    uint64_t* tail_bars = fm_ready + FG_FM_BUF;    // [4] TCTAIL: [0] tail weights landed, [1] tail operand written, [2] tail MMAs done
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tail_bars + 4);
     float* fm_tile = reinterpret_cast<float*>(tmem_ptr + 4);                  // [FG_FM_BUF][128]
     float* tw_As = fm_tile + FG_FM_BUF * TC_BLOCK_M;                          // 16-byte aligned: every block above is
-    float* tw_Bs = tw_As + TC_BLOCK_M * TW_LDA;
-    float* tw_loss = tw_Bs + tw.n_tail * TW_H * TW_H;
+    float* tw_Bs = tw_As + (TCTAIL ? TC_BLOCK_M : TC_BLOCK_M * TW_LDA);       // TCTAIL: tw_As = 128 head partials only
+    float* tw_loss = tw_Bs + (TCTAIL ? 0 : tw.n_tail * TW_H * TW_H);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = p.nkb;
@@ -101,12 +114,14 @@ deepfm_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_
     const uint32_t G = (uint32_t)my_tiles * (uint32_t)nkb;                    // k-blocks this CTA walks
     constexpr uint32_t ACC_STRIDE = 2 * FG_N;                                 // stacked accumulator: [a.b_hi | a.b_lo]
     constexpr uint32_t A_COL = 2 * ACC_STRIDE;                                // first TMEM column of the operand ring
+    constexpr uint32_t TAIL_A = A_COL + FT_OP * 64u;                          // TCTAIL: tail operand, hi [0,64) | lo [64,128)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < FG_LB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
         for (int s = 0; s < FG_OP; ++s) { mbar_init(&ready_op[s], 128); mbar_init(&empty_op[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], FG_EPI_WARPS); }
         for (int s = 0; s < FG_FM_BUF; ++s) mbar_init(&fm_ready[s], 128);
+        mbar_init(&tail_bars[0], 1); mbar_init(&tail_bars[1], FG_EPI_WARPS * 32); mbar_init(&tail_bars[2], 1); mbar_init(&tail_bars[3], 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr, 512);
@@ -120,6 +135,16 @@ deepfm_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_
     if (warp == 0) {
         // ---------------- weight producer: [B hi ; B lo] of every k-block through a FG_LB-deep ring
         if (lane == 0) {
+            if constexpr (TCTAIL) {
+                // resident tail operands: layer l, k-block kb -> [W_l hi ; W_l lo] columns kb*32 .. kb*32+31 (128 rows x 128 B)
+                mbar_arrive_expect_tx(&tail_bars[0], (uint32_t)(tw.n_tail * FT_TAIL_B_BYTES));
+                for (int l = 0; l < tw.n_tail; ++l)
+                    for (int kb = 0; kb < 2; ++kb) {
+                        uint8_t* st = t_base + (size_t)(l * 2 + kb) * FG_B_BYTES;
+                        tma_load_2d(st, &tmThi, &tail_bars[0], kb * TC_BLOCK_K, l * TW_H);
+                        tma_load_2d(st + FG_B_BYTES / 2, &tmTlo, &tail_bars[0], kb * TC_BLOCK_K, l * TW_H);
+                    }
+            }
             long long w_b = 0;
             for (uint32_t g = 0; g < G; ++g) {
                 const int s = g % FG_LB, kb = g % nkb;
@@ -139,19 +164,43 @@ deepfm_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_
             const uint32_t idesc = make_idesc_tf32(TC_BLOCK_M, 2 * FG_N);
             uint32_t g = 0;
             long long w_fb = 0, w_op = 0, w_acc = 0, w_is = 0;
+            // TCTAIL: tail steps are issued in (tile, layer) order as soon as the epilogue warps have written the operand
+            // (tail_bars[1]); between k-blocks of the running tile without blocking, and blocking before an accumulator
+            // buffer is re-used (tile t + 2 needs tile t's tail finished) and after the last tile.
+            int tl_t = 0, tl_l = 0; uint32_t tl_n = 0;
+            auto tail_step = [&](bool block) -> bool {
+                if (!block && !mbar_test(&tail_bars[1], tl_n & 1u)) return false;
+                mbar_wait(&tail_bars[1], tl_n & 1u);
+                if (tl_n == 0) mbar_wait(&tail_bars[0], 0u);               // resident tail operands have landed
+                tc_fence_after();
+                const uint32_t d_t = tmem_base + ((uint32_t)tl_t & 1u) * ACC_STRIDE;
+                const uint32_t tb = smem_u32(t_base + (size_t)tl_l * FT_TAIL_B_BYTES);
+#pragma unroll
+                for (int k = 0; k < TW_H / TC_UMMA_K; ++k) {
+                    const uint64_t db = make_kmajor_sw128_desc(tb + (uint32_t)(k >> 2) * FG_B_BYTES + (uint32_t)(k & 3) * TC_UMMA_K * 4);
+                    umma_tf32_ts(d_t, tmem_base + TAIL_A + 64u + k * TC_UMMA_K, db, idesc, k > 0 ? 1u : 0u);
+                    umma_tf32_ts(d_t, tmem_base + TAIL_A + k * TC_UMMA_K, db, idesc, 1u);
+                }
+                umma_commit(&tail_bars[2]);
+                ++tl_n;
+                if (++tl_l == tw.n_tail) { tl_l = 0; ++tl_t; }
+                return true;
+            };
             for (int t = 0; t < my_tiles; ++t) {
                 const uint32_t acc = (uint32_t)t & 1u;
                 const long long c0 = FG_T();
+                if constexpr (TCTAIL) { while (tl_t + 2 <= t) tail_step(true); }
                 mbar_wait(&tmem_empty[acc], (((uint32_t)t >> 1) & 1u) ^ 1u);
                 w_acc += FG_T() - c0;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
                 for (int kb = 0; kb < nkb; ++kb, ++g) {
-                    const int s = g % FG_LB, o = g % FG_OP;
+                    const int s = g % FG_LB, o = g % OPN;
+                    if constexpr (TCTAIL) { if (tl_t < t) tail_step(false); }
                     const long long c1 = FG_T();
                     mbar_wait(&full_b[s], (g / FG_LB) & 1u);
                     const long long c2 = FG_T();
-                    mbar_wait(&ready_op[o], (g / FG_OP) & 1u);
+                    mbar_wait(&ready_op[o], (g / OPN) & 1u);
                     const long long c3 = FG_T();
                     w_fb += c2 - c1; w_op += c3 - c2;
                     tc_fence_after();
@@ -169,6 +218,7 @@ deepfm_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_
                 }
                 umma_commit(&tmem_full[acc]);
             }
+            if constexpr (TCTAIL) { while (tl_t < my_tiles) tail_step(true); }
             if (trace) { g_fg_trace[4] = (unsigned long long)w_fb; g_fg_trace[5] = (unsigned long long)w_op; g_fg_trace[6] = (unsigned long long)w_acc; g_fg_trace[7] = (unsigned long long)w_is; }
         }
     } else if (warp < 6) {
@@ -259,9 +309,9 @@ deepfm_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_
                 fg_wait<LA - 2>();                      // group g has landed: A(g) and the ids of k-block g + LA - 1
                 const long long c1 = FG_T();
                 issue();                                // k-block g + LA - 1 (starts with a __syncwarp: rows of group g visible warp-wide)
-                const int o = g % FG_OP;
+                const int o = g % OPN;
                 const long long c2 = FG_T();
-                mbar_wait(&empty_op[o], ((g / FG_OP) & 1u) ^ 1u);
+                mbar_wait(&empty_op[o], ((g / OPN) & 1u) ^ 1u);
                 const long long c3 = FG_T();
                 w_cp += c1 - c0; w_eo += c3 - c2; w_wk += c2 - c1;
                 tc_fence_after();
@@ -334,10 +384,97 @@ deepfm_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_
         const int row = quarter * 32 + lane;
         const int et = threadIdx.x - 6 * 32;
         auto epi_sync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+        float loss_acc = 0.f;
+        if constexpr (TCTAIL) {
+            const float tw_bo = tw.b_out != nullptr ? __ldg(tw.b_out) : 0.f;
+            // Round r = 0 .. n_tail of a tile: read the accumulator of layer r (r = 0: layer 1; both stacked halves), add the
+            // bias, ReLU, store the activation row piece for backward, and either hand it back to the tensor core as the
+            // next layer's operand (hi | lo in tensor memory) or, after the last layer, fold it into the output row-dot.
+            // Thread = (row, half): the two warps of a lane quarter own columns {half*16 .. +15} and {32 + half*16 .. +15}.
+            const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+            const int L = tw.n_tail;
+            uint32_t n_out = 0;                                   // tail_bars[2] phases consumed
+            for (int t = 0; t < my_tiles; ++t) {
+                const int m0 = ((int)blockIdx.x + t * (int)gridDim.x) * TC_BLOCK_M;
+                const uint32_t acc = (uint32_t)t & 1u;
+                const int m = m0 + row;
+                const long long q0 = FG_T();
+                mbar_wait(&tmem_full[acc], ((uint32_t)t >> 1) & 1u);
+                tc_fence_after();
+                const long long q1 = FG_T();
+                const uint32_t d_acc = tmem_base + acc * ACC_STRIDE + lane_addr;
+                float headp = 0.f;
+                for (int r = 0; r <= L; ++r) {
+                    if (r > 0) { mbar_wait(&tail_bars[2], n_out & 1u); ++n_out; tc_fence_after(); }
+                    const float* bias = r == 0 ? p.bias1 : tw.b[r - 1];
+                    float* hout = r == 0 ? p.h1 : tw.h[r - 1];
+                    const long long ldh = r == 0 ? p.ldh1 : (long long)TW_H;
+                    for (int c0 = half * 16; c0 < FG_N; c0 += 32) {
+                        uint32_t a0[16], a1[16];
+                        tmem_ld16(d_acc + (uint32_t)c0, a0);
+                        tmem_ld16(d_acc + (uint32_t)(FG_N + c0), a1);
+                        float v[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            v[j] = fmaxf(__uint_as_float(a1[j]) + __uint_as_float(a0[j]) + __ldg(bias + c0 + j), 0.f);
+                        if (m < p.M) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4)
+                                stg_f4(hout + (size_t)m * ldh + c0 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                        }
+                        if (r < L) {
+                            uint32_t hi[16], lo[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                hi[j] = __float_as_uint(v[j]) & 0xFFFFE000u;
+                                lo[j] = __float_as_uint(v[j] - __uint_as_float(hi[j]));
+                            }
+                            tmem_st16(tmem_base + TAIL_A + lane_addr + (uint32_t)c0, hi);
+                            tmem_st16(tmem_base + TAIL_A + 64u + lane_addr + (uint32_t)c0, lo);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) headp = fmaf(v[j], __ldg(tw.w_out + c0 + j), headp);
+                        }
+                    }
+                    if (r < L) {
+                        tmem_st_wait();
+                        tc_fence_before();
+                        mbar_arrive(&tail_bars[1]);               // 256 arrivals: the operand of tail layer r is complete
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);     // every read of this accumulator buffer is done
+                const long long q2 = FG_T();
+                mbar_wait(&fm_ready[t % FG_FM_BUF], ((uint32_t)t / FG_FM_BUF) & 1u);
+                float* head_part = tw_As;                         // [128] partial row-dots of the half-1 warps
+                if (half == 1) head_part[row] = headp;
+                epi_sync();
+                if (half == 0 && m < p.M) {
+                    const float z = headp + head_part[row] + tw_bo + fm_tile[(t % FG_FM_BUF) * TC_BLOCK_M + row];
+                    tw.logit[m] = z;
+                    if (tw.pred != nullptr) {
+                        const float q = 1.f / (1.f + expf(-z));
+                        tw.pred[m] = q;
+                        if (tw.label != nullptr) {
+                            const float y = __ldg(tw.label + m);
+                            const float pe = q + tw.eps;
+                            const float l1 = fmaxf(logf(pe), -100.f);
+                            const float l0 = fmaxf(logf(1.f - pe), -100.f);
+                            loss_acc += -(y * l1 + (1.f - y) * l0);
+                        }
+                    }
+                }
+                epi_sync();                                       // head_part is free for the next tile
+                if (trace && et == 0) {
+                    g_fg_trace[8] += (unsigned long long)(q1 - q0); g_fg_trace[9] += (unsigned long long)(q2 - q1);
+                    g_fg_trace[10] += (unsigned long long)(FG_T() - q2);
+                }
+            }
+        } else {
         tower_load_weights_t<FG_EPI_WARPS * 32>(tw, tw_Bs, et);
         const float4 tw_wo = ldg_f4(tw.w_out + (et & 15) * 4);
         const float tw_bo = tw.b_out != nullptr ? __ldg(tw.b_out) : 0.f;
-        float loss_acc = 0.f;
         for (int t = 0; t < my_tiles; ++t) {
             const int m0 = ((int)blockIdx.x + t * (int)gridDim.x) * TC_BLOCK_M;
             const uint32_t acc = (uint32_t)t & 1u;
@@ -375,6 +512,7 @@ deepfm_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_
                 g_fg_trace[10] += (unsigned long long)(FG_T() - q2);
             }
         }
+        }
         if (tw.loss != nullptr) tw_loss[et] = loss_acc;
     }
     tc_fence_before();
@@ -407,11 +545,14 @@ deepfm_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_
     }
 }
 
-static size_t fg_smem_bytes(int la, int n_tail) {
-    return (size_t)FG_LB * FG_B_BYTES + (size_t)la * TC_BLOCK_M * FG_ROW * 4 + (size_t)la * TC_BLOCK_M * 16 +
-           (2 * FG_LB + 2 * FG_OP + 4 + FG_FM_BUF) * 8 + 16 + FG_FM_BUF * TC_BLOCK_M * 4 +
-           (size_t)(TC_BLOCK_M * TW_LDA + n_tail * TW_H * TW_H + 256) * 4 + 1024;
+static size_t fg_smem_bytes(int la, int n_tail, bool tctail = false) {
+    return (size_t)FG_LB * FG_B_BYTES + (tctail ? (size_t)n_tail * FT_TAIL_B_BYTES : 0) +
+           (size_t)la * TC_BLOCK_M * FG_ROW * 4 + (size_t)la * TC_BLOCK_M * 16 +
+           (2 * FG_LB + 2 * FG_OP + 4 + FG_FM_BUF + 4) * 8 + 16 + FG_FM_BUF * TC_BLOCK_M * 4 +
+           (tctail ? (size_t)(TC_BLOCK_M + 256) * 4 : (size_t)(TC_BLOCK_M * TW_LDA + n_tail * TW_H * TW_H + 256) * 4) + 1024;
 }
+
+int tc_prepare_tail_weights(const float* const* W, int n_tail, CUtensorMap* tm_hi, CUtensorMap* tm_lo, cudaStream_t st);   // linear_tc.cu
 
 }  // namespace rpb
 
@@ -472,23 +613,29 @@ RPB_API int rpb_deepfm_fwd_fused(const RpbGatherDesc* g, const float* W1, const 
     if (rc != 0) return rc;
     const int m_tiles = ceil_div(d->M, TC_BLOCK_M);
     const int grid = min(m_tiles, 148);
-    auto launch = [&](auto la_tag) -> int {
+    const size_t cap = 227 * 1024;
+    // tail layers on tcgen05 (opt-in, see FT_OP): needs the resident tail operands next to >= 3 gather stages
+    const bool tctail = g_fused_tc_tail != 0 && fg_smem_bytes(3, d->n_tail, true) <= cap;
+    CUtensorMap tmThi = tmBhi, tmTlo = tmBlo;          // placeholders when the tail runs on the CUDA cores
+    if (tctail) {
+        rc = tc_prepare_tail_weights(tw.W, d->n_tail, &tmThi, &tmTlo, st);
+        if (rc != 0) return rc;
+    }
+    auto launch = [&](auto la_tag, auto sh_tag, auto tc_tag) -> int {
         constexpr int LA = decltype(la_tag)::value;
-        const size_t smem = fg_smem_bytes(LA, d->n_tail);
-        if (sharded) {
-            cudaError_t e = cudaFuncSetAttribute(deepfm_fwd_fused_kernel<LA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return (int)e;
-            deepfm_fwd_fused_kernel<LA, true><<<grid, FG_THREADS, smem, st>>>(tmBhi, tmBlo, p, tw, m_tiles);
-            return (int)cudaGetLastError();
-        }
-        cudaError_t e = cudaFuncSetAttribute(deepfm_fwd_fused_kernel<LA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        constexpr bool SH = decltype(sh_tag)::value, TC = decltype(tc_tag)::value;
+        const size_t smem = fg_smem_bytes(LA, d->n_tail, TC);
+        cudaError_t e = cudaFuncSetAttribute(deepfm_fwd_fused_kernel<LA, SH, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        deepfm_fwd_fused_kernel<LA, false><<<grid, FG_THREADS, smem, st>>>(tmBhi, tmBlo, p, tw, m_tiles);
+        deepfm_fwd_fused_kernel<LA, SH, TC><<<grid, FG_THREADS, smem, st>>>(tmBhi, tmBlo, tmThi, tmTlo, p, tw, m_tiles);
         return (int)cudaGetLastError();
     };
-    const size_t cap = 227 * 1024;
-    if (fg_smem_bytes(5, d->n_tail) <= cap) return launch(std::integral_constant<int, 5>{});
-    if (fg_smem_bytes(4, d->n_tail) <= cap) return launch(std::integral_constant<int, 4>{});
-    if (fg_smem_bytes(3, d->n_tail) <= cap) return launch(std::integral_constant<int, 3>{});
+    auto pick = [&](auto la_tag) -> int {
+        if (tctail) return sharded ? launch(la_tag, std::true_type{}, std::true_type{}) : launch(la_tag, std::false_type{}, std::true_type{});
+        return sharded ? launch(la_tag, std::true_type{}, std::false_type{}) : launch(la_tag, std::false_type{}, std::false_type{});
+    };
+    if (fg_smem_bytes(5, d->n_tail, tctail) <= cap) return pick(std::integral_constant<int, 5>{});
+    if (fg_smem_bytes(4, d->n_tail, tctail) <= cap) return pick(std::integral_constant<int, 4>{});
+    if (fg_smem_bytes(3, d->n_tail, tctail) <= cap) return pick(std::integral_constant<int, 3>{});
     return RPB_ERR_UNSUPPORTED;
 }

@@ -1039,6 +1039,37 @@ int tc_prepare_weight(const float* W, long long ldw, int N, int K, CUtensorMap* 
     return rc;
 }
 
+// Pre-split operands of the square 64 x 64 tower-tail layers for the tcgen05 tail of deepfm_fused.cu: hi / lo
+// [n_tail * 64, 64] (layer l = rows l*64 .. l*64+63) in workspace slot 6 + their TMA maps with [64 x 32] boxes.
+struct TailSplitArgs { const float* W[RPB_TOWER_MAX_TAIL]; };
+__global__ void __launch_bounds__(256)
+split_pack_tail_kernel(const TailSplitArgs a, int n_tail, float* __restrict__ hi, float* __restrict__ lo) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tail * 64 * 64) return;
+    const float v = __ldg(a.W[t >> 12] + (t & 4095));
+    const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    hi[t] = h;
+    lo[t] = v - h;
+}
+
+int tc_prepare_tail_weights(const float* const* W, int n_tail, CUtensorMap* tm_hi, CUtensorMap* tm_lo, cudaStream_t st) {
+    if (n_tail < 1 || n_tail > RPB_TOWER_MAX_TAIL) return RPB_ERR_UNSUPPORTED;
+    int werr = 0;
+    float* ws = static_cast<float*>(workspace(6, (size_t)2 * n_tail * 64 * 64 * sizeof(float), &werr));
+    if (ws == nullptr) return werr;
+    float* hi = ws;
+    float* lo = ws + (size_t)n_tail * 64 * 64;
+    TailSplitArgs a{};
+    for (int l = 0; l < n_tail; ++l) {
+        if (W[l] == nullptr) return RPB_ERR_BAD_ARG;
+        a.W[l] = W[l];
+    }
+    split_pack_tail_kernel<<<ceil_div(n_tail * 64 * 64, 256), 256, 0, st>>>(a, n_tail, hi, lo);
+    int rc = make_map(tm_hi, hi, (long long)n_tail * 64, 64, 64, 64);
+    if (rc == 0) rc = make_map(tm_lo, lo, (long long)n_tail * 64, 64, 64, 64);
+    return rc;
+}
+
 // dW[N,K] += dy[M,N]^T @ x[M,K] on tensor cores (see wgrad_tf32x3_kernel).  Returns RPB_ERR_UNSUPPORTED when the
 // operands do not satisfy the TMA constraints (16-byte aligned rows) or N > 256.
 int wgrad_tc(const float* dy, long long lddy, const float* x, long long ldx, float* dW, int M, int N, int K, cudaStream_t st) {

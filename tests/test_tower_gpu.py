@@ -1,5 +1,7 @@
 """GPU parity tests of the fused MLP tower tail (rpb_tower_tail_fwd / rpb_tower_tail_bwd through the C ABI) against
 the oracle's MLP (oracle/restatement.py::mlp, models/layers/deep.py:62-84) + torch.nn.BCELoss on the CPU."""
+import os
+
 import pytest
 import torch
 
@@ -215,6 +217,47 @@ def test_deepfm_one_kernel_forward_equals_separate_kernels(B, F, Nd, hidden):
     with torch.no_grad():
         p_fused = model(data, is_training=False)['pred']
     torch.testing.assert_close(p_fused, res[0][0], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.skipif(os.environ.get('RPB_EXPERIMENTAL', '0') != '1',
+                    reason='tcgen05 tower tail of the one-kernel forward: compiled but not yet run on hardware (opt-in)')
+@pytest.mark.parametrize('B,F,Nd,hidden', [(4096, 26, 13, [64, 64, 64]), (5000, 26, 13, [64, 64]), (1300, 4, 0, [64, 64, 64, 64])])
+def test_deepfm_one_kernel_forward_tc_tail(B, F, Nd, hidden):
+    """rpb_set_option('fused_tc_tail', 1): the 64x64 tail layers of rpb_deepfm_fwd_fused on tcgen05 (3xTF32, operands handed
+    from layer to layer through tensor memory) vs the exact-fp32 CUDA-core tail of the same kernel: logits within 1e-4
+    (north_star tolerance), stored activations and gradients to the tensor-relative tolerance of the other tcgen05 tests."""
+    from helpers import make_enc, make_batch
+    from rec_pangu_b200 import ops, _lib
+    from rec_pangu_b200.models.ranking import DeepFM
+    enc = make_enc(F, Nd, 3000)
+    torch.manual_seed(2)
+    model = DeepFM(embedding_dim=16, hidden_units=hidden, enc_dict=enc)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if 'embedding_layer' in n:
+                p.mul_(0.25)
+            elif p.dim() == 1:
+                p.copy_(torch.randn(p.shape) * 0.05)
+    model = model.cuda().train()
+    data = make_batch(enc, B, seed=21, device='cuda')
+    res = []
+    for flag in (1, 0):
+        _lib.check(_lib.load().rpb_set_option(b'fused_tc_tail', flag), 'rpb_set_option(fused_tc_tail)')
+        try:
+            model.zero_grad()
+            out = model(data)
+            out['loss'].backward()
+            torch.cuda.synchronize()
+            ops.check_index_errors()
+            grads = {n: p.grad.clone() for n, p in model.named_parameters()}
+            res.append((out['pred'].detach().clone(), out['loss'].detach().clone(), model._last_logit.clone(), grads))
+        finally:
+            _lib.check(_lib.load().rpb_set_option(b'fused_tc_tail', 0), 'rpb_set_option(fused_tc_tail)')
+    assert (res[0][2] - res[1][2]).abs().max().item() <= 1e-4
+    torch.testing.assert_close(res[0][1], res[1][1], rtol=1e-5, atol=1e-6)
+    for n in res[0][3]:
+        a, b = res[0][3][n], res[1][3][n]
+        assert (a - b).abs().max().item() <= 5e-4 * max(1e-6, b.abs().max().item()) + 1e-7, n
 
 
 def test_deepfm_one_kernel_reports_bad_index():
