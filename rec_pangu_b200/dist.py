@@ -152,6 +152,54 @@ class ShardedTables:
         return unshard(shards, self.rows[f])
 
 
+def _table_key(col: str) -> str:
+    return f'embedding_layer.embedding_layer.{col}.weight'
+
+
+def gather_state_dict(model) -> Dict[str, torch.Tensor]:
+    """`model.state_dict()` in the REFERENCE's layout from a model whose tables are row-sharded: every table entry
+    (`embedding_layer.embedding_layer.<col>.weight`) is all-gathered and re-interleaved to [vocab_size + 1, D]; all other
+    entries (replicated on every rank) are the local ones.  Collective: every rank of the shard group must call it and
+    every rank gets the full dict, so `RankTrainer.save_model` on rank 0 writes a checkpoint that the reference — or a
+    single-GPU run of this build, or a run sharded over another number of GPUs — loads unchanged (trainer.py:133-150)."""
+    st = model.embedding_layer._shards
+    sd = {k: v for k, v in model.state_dict().items()}
+    if st is None:
+        return sd
+    for f, c in enumerate(st.cols):
+        sd[_table_key(c)] = st.full_table(f)
+    return sd
+
+
+def load_state_dict_sharded(model, state_dict: Dict[str, torch.Tensor], strict: bool = True):
+    """Inverse of gather_state_dict: load a reference-layout state_dict into a model with row-sharded tables.  Each rank
+    copies ITS rows (owner = id mod G) of every full table into its shard in place (the peer mappings stay valid);
+    everything else goes through nn.Module.load_state_dict.  Full-size table entries never touch the device whole."""
+    st = model.embedding_layer._shards
+    if st is None:
+        return model.load_state_dict(state_dict, strict=strict)
+    rest = dict(state_dict)
+    for f, c in enumerate(st.cols):
+        key = _table_key(c)
+        if key not in rest:
+            if strict:
+                raise KeyError(f'missing key in state_dict: {key}')
+            continue
+        full = rest.pop(key)
+        if tuple(full.shape) != (st.rows[f], st.D):
+            raise RuntimeError(f'size mismatch for {key}: checkpoint {tuple(full.shape)}, model {(st.rows[f], st.D)}')
+        with torch.no_grad():
+            st.weights[f].copy_(local_slice(full, st.rank, st.world).to(st.weights[f].device))
+    own = {k: v for k, v in model.state_dict().items() if not any(k == _table_key(c) for c in st.cols)}
+    missing = [k for k in own if k not in rest]
+    unexpected = [k for k in rest if k not in own]
+    if strict and (missing or unexpected):
+        raise RuntimeError(f'load_state_dict_sharded: missing keys {missing}, unexpected keys {unexpected}')
+    res = model.load_state_dict(rest, strict=False)
+    st.barrier()
+    return res
+
+
 def enable_sync_batchnorm(group=None, enabled: bool = True):
     """BatchNorm1d layers of the hot path (multi-task towers) normalise with the statistics of the GLOBAL batch: the
     [sum | sum of squares | count] vector in forward and the [dgamma | dbeta] column sums in backward are all-reduced over

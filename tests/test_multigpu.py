@@ -13,6 +13,60 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+class _HostShards:
+    """dist.ShardedTables without the device part (CPU tensors, gloo collectives): what the checkpoint helpers touch."""
+
+    def __init__(self, emb, rank, world, rdist):
+        self.rank, self.world, self.group = rank, world, None
+        self.cols, self.D = list(emb.emb_feature), emb.embedding_dim
+        self.rows = [int(emb.enc_dict[c]['vocab_size']) + 1 for c in self.cols]
+        self.weights = [rdist.local_slice(emb.embedding_layer[c].weight.data, rank, world) for c in self.cols]
+        self._rdist = rdist
+
+    def full_table(self, f):
+        shards = [torch.empty_like(self.weights[f]) for _ in range(self.world)]
+        dist.all_gather(shards, self.weights[f])
+        return self._rdist.unshard(shards, self.rows[f])
+
+    def barrier(self):
+        dist.barrier()
+
+
+def _check_sharded_checkpoint(rank, world, rdist):
+    """gather_state_dict / load_state_dict_sharded round-trip a reference-layout state_dict through row shards."""
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from helpers import make_enc
+    from rec_pangu_b200.models.ranking import DeepFM
+    enc = make_enc(4, 2, [101, 57, 33, 8])
+    torch.manual_seed(5)
+    model = DeepFM(embedding_dim=8, hidden_units=[16, 8], enc_dict=enc)
+    full_sd = {k: v.clone() for k, v in model.state_dict().items()}
+    model.embedding_layer.attach_shards(_HostShards(model.embedding_layer, rank, world, rdist))
+    assert model.state_dict()['embedding_layer.embedding_layer.C1.weight'].shape[0] == rdist.shard_rows(102, world)
+    got = rdist.gather_state_dict(model)
+    assert set(got) == set(full_sd)
+    for k, v in full_sd.items():
+        assert torch.equal(got[k], v), k
+    torch.manual_seed(6)
+    other = {k: torch.randn_like(v) for k, v in full_sd.items()}
+    rdist.load_state_dict_sharded(model, other)
+    st = model.embedding_layer._shards
+    for f, c in enumerate(st.cols):
+        assert torch.equal(st.weights[f], rdist.local_slice(other[f'embedding_layer.embedding_layer.{c}.weight'], rank, world))
+        assert model.embedding_layer.embedding_layer[c].weight.data_ptr() == st.weights[f].data_ptr()     # loaded in place
+    assert torch.equal(model.dnn.net[0].weight, other['dnn.net.0.weight'])
+    back = rdist.gather_state_dict(model)
+    for k, v in other.items():
+        assert torch.equal(back[k], v), k
+    bad = dict(other)
+    bad.pop('dnn.net.0.bias')
+    try:
+        rdist.load_state_dict_sharded(model, bad)
+        raise AssertionError('strict load accepted a missing key')
+    except RuntimeError:
+        pass
+
+
 def _gloo_worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     sys.path.insert(0, ROOT)
@@ -48,6 +102,7 @@ def _gloo_worker(rank, world, port, q):
         shards = [torch.empty_like(sl) for _ in range(world)]
         dist.all_gather(shards, sl)
         assert torch.equal(rdist.unshard(shards, rows), full)
+        _check_sharded_checkpoint(rank, world, rdist)
         q.put((rank, 'ok'))
     except Exception as e:  # noqa
         q.put((rank, repr(e)))
