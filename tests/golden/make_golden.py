@@ -233,7 +233,7 @@ if __name__ == '__main__':
         run_multitask_all()
         sys.exit(0)
     if '--only-afm' in sys.argv:                  # AFM fixture only (added after the first set)
-        run_model('afm', AFM, {'hidden_units': [16, 8]}, n_sparse=5, n_dense=2, seed=2029)
+        run_model('afm', AFM, {'hidden_units': [16, 8]}, n_sparse=6, seed=2029)
         sys.exit(0)
     run_layers()
     run_model('deepfm', DeepFM, {'hidden_units': [16, 8]})
@@ -243,7 +243,7 @@ if __name__ == '__main__':
     run_model('autoint_l2', AutoInt, {'dnn_hidden_units': [16], 'num_heads': 2, 'attention_dim': 4, 'attention_layers': 2})
     run_model('dcn', DCN, {'crossing_layers': 3})
     run_model('fibinet', FiBiNet, {'hidden_units': [16, 8]}, n_sparse=6)
-    run_model('afm', AFM, {'hidden_units': [16, 8]}, n_sparse=5, n_dense=2, seed=2029)
+    run_model('afm', AFM, {'hidden_units': [16, 8]}, n_sparse=6, seed=2029)
     run_model('fm', FM, {})
     run_model('wdl', WDL, {'hidden_units': [16, 8]})
     run_model('nfm', NFM, {'hidden_units': [16, 8]})
