@@ -419,25 +419,25 @@ def run_ours(args):
     # step counter on the device so the captured graph keeps its bias correction.  Reported beside the headline.
     train_step = None
     if world == 1 and not args.no_train_step:
-      try:
-        from rec_pangu_b200.optim import FusedAdam
-        opt = FusedAdam(model, lr=1e-3)
-        tsteps = [GraphedStep(model, cb, post=opt.step, use_graph=use_graph) for cb in cbs]
-        for i in range(max(3, args.warmup)):
-            tsteps[i % NB].replay()
-        torch.cuda.synchronize()
-        e0.record()
-        for i in range(args.steps):
-            tsteps[i % NB].replay()
-        e1.record()
-        torch.cuda.synchronize()
-        ms_t = e0.elapsed_time(e1)
-        train_step = {'value': B * args.steps / (ms_t * 1e-3), 'unit': 'samples/s', 'ms_per_step': ms_t / args.steps,
-                      'what': 'forward + backward + FusedAdam (row-sparse Adam on the touched table rows, gradient re-zero fused)',
-                      'gpu_launches_per_step': tsteps[0].launches_per_step, 'loss_after': float(tsteps[0].loss.item())}
-        del tsteps, opt
-      except Exception as ex:          # a secondary leg must never cost the headline line
-        train_step = {'error': repr(ex)}
+        try:
+            from rec_pangu_b200.optim import FusedAdam
+            opt = FusedAdam(model, lr=1e-3)
+            tsteps = [GraphedStep(model, cb, post=opt.step, use_graph=use_graph) for cb in cbs]
+            for i in range(max(3, args.warmup)):
+                tsteps[i % NB].replay()
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(args.steps):
+                tsteps[i % NB].replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ms_t = e0.elapsed_time(e1)
+            train_step = {'value': B * args.steps / (ms_t * 1e-3), 'unit': 'samples/s', 'ms_per_step': ms_t / args.steps,
+                          'what': 'forward + backward + FusedAdam (row-sparse Adam on the touched table rows, gradient re-zero fused)',
+                          'gpu_launches_per_step': tsteps[0].launches_per_step, 'loss_after': float(tsteps[0].loss.item())}
+            del tsteps, opt
+        except Exception as ex:          # a secondary leg must never cost the headline line
+            train_step = {'error': repr(ex)}
 
     # ---------------- secondary legs (N = 1 only): Zipf(1.05)-distributed ids and stock PyTorch eager on the
     # same GPU (the oracle's functional restatement of the reference forward run on CUDA tensors = the "existing Blackwell
@@ -445,53 +445,53 @@ def run_ours(args):
     # [V+1, D] table gradients from autograd)
     zipf = eager_gpu = None
     if world == 1 and not args.no_extras:
-      try:
-        import numpy as np
-        rng = np.random.default_rng(SEED)
-        zsteps = []
-        for i in range(2):
-            cb = ColumnarBatch(enc, B, device=dev, pinned_host=False)
-            d = synth_batch(enc, B, gen, device=dev)
-            for c in cb.sparse:
-                d[c] = torch.from_numpy(((rng.zipf(1.05, B) - 1) % (CFG['V'] + 1)).astype('int64')).to(dev)
-            cb.load_device(d)
-            zsteps.append(GraphedStep(model, cb, use_graph=use_graph))
-        for i in range(3):
-            zsteps[i % 2].replay()
-        torch.cuda.synchronize()
-        e0.record()
-        for i in range(args.steps):
-            zsteps[i % 2].replay()
-        e1.record()
-        torch.cuda.synchronize()
-        ms_z = e0.elapsed_time(e1)
-        zipf = {'value': B * args.steps / (ms_z * 1e-3), 'unit': 'samples/s', 'ms_per_step': ms_z / args.steps,
-                'ids': 'zipf(1.05) - 1 mod (V+1) per field'}
-        del zsteps
-        import oracle
-        sd = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
-        dd = cbs[0].as_dict()
-        n_e = 5
-        for it in range(2 + n_e):
-            if it == 2:
-                torch.cuda.synchronize()
-                e0.record()
-            out = oracle.deepfm(sd, enc, dd, hidden_units=tuple(CFG['hidden']))
-            out['loss'].backward()
-            for v in sd.values():
-                v.grad = None
-        e1.record()
-        torch.cuda.synchronize()
-        ms_e = e0.elapsed_time(e1)
-        eager_gpu = {'value': B * n_e / (ms_e * 1e-3), 'unit': 'samples/s', 'ms_per_step': ms_e / n_e,
-                     'what': 'stock PyTorch eager ops of the reference forward + autograd backward on the same B200 (fp32)'}
-        del sd, out
-        torch.cuda.empty_cache()
-      except Exception as ex:
-        if zipf is None:
-            zipf = {'error': repr(ex)}
-        else:
-            eager_gpu = {'error': repr(ex)}
+        try:
+            import numpy as np
+            rng = np.random.default_rng(SEED)
+            zsteps = []
+            for i in range(2):
+                cb = ColumnarBatch(enc, B, device=dev, pinned_host=False)
+                d = synth_batch(enc, B, gen, device=dev)
+                for c in cb.sparse:
+                    d[c] = torch.from_numpy(((rng.zipf(1.05, B) - 1) % (CFG['V'] + 1)).astype('int64')).to(dev)
+                cb.load_device(d)
+                zsteps.append(GraphedStep(model, cb, use_graph=use_graph))
+            for i in range(3):
+                zsteps[i % 2].replay()
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(args.steps):
+                zsteps[i % 2].replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ms_z = e0.elapsed_time(e1)
+            zipf = {'value': B * args.steps / (ms_z * 1e-3), 'unit': 'samples/s', 'ms_per_step': ms_z / args.steps,
+                    'ids': 'zipf(1.05) - 1 mod (V+1) per field'}
+            del zsteps
+            import oracle
+            sd = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+            dd = cbs[0].as_dict()
+            n_e = 5
+            for it in range(2 + n_e):
+                if it == 2:
+                    torch.cuda.synchronize()
+                    e0.record()
+                out = oracle.deepfm(sd, enc, dd, hidden_units=tuple(CFG['hidden']))
+                out['loss'].backward()
+                for v in sd.values():
+                    v.grad = None
+            e1.record()
+            torch.cuda.synchronize()
+            ms_e = e0.elapsed_time(e1)
+            eager_gpu = {'value': B * n_e / (ms_e * 1e-3), 'unit': 'samples/s', 'ms_per_step': ms_e / n_e,
+                         'what': 'stock PyTorch eager ops of the reference forward + autograd backward on the same B200 (fp32)'}
+            del sd, out
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            if zipf is None:
+                zipf = {'error': repr(ex)}
+            else:
+                eager_gpu = {'error': repr(ex)}
 
     line = {
         'metric': 'DeepFM samples/sec (forward+backward hot path)', 'value': value, 'unit': 'samples/s',
