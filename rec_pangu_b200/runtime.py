@@ -61,11 +61,19 @@ class GraphedStep:
     """Captures `out = model(batch); out['loss'].backward(); post(); model.zero_grad()` into one CUDA graph on
     static input buffers.  `post` (e.g. an optimizer step or a gradient collective) runs between backward and
     zero_grad.  ``replay()`` re-launches the whole step with one cudaGraphLaunch; ``loss`` / ``pred`` are the static
-    output tensors."""
+    output tensors.
+
+    ``zero_first`` (experimental, not yet measured): the same K steps with the loop boundary moved — every step starts with
+    the `model.zero_grad()` of the step before it, issued on a side stream so that the sparse re-zero of the table
+    gradients (random 64-byte stores, DRAM-bound) overlaps the forward kernel (shared-memory-pipe-bound) and is joined
+    before backward; the gradients of the last step stay in `.grad` after a replay."""
+
+    _zero_streams = {}
 
     def __init__(self, model: torch.nn.Module, batch: ColumnarBatch, post: Optional[Callable[[], None]] = None,
-                 warmup: int = 3, use_graph: bool = True, loss_scale: float = 1.0):
+                 warmup: int = 3, use_graph: bool = True, loss_scale: float = 1.0, zero_first: bool = False):
         self.model, self.batch, self.post = model, batch, post
+        self.zero_first = zero_first
         self.loss_scale = loss_scale           # data parallel: back-propagate loss / world (dist.DenseGradBucket)
         self.data = batch.as_dict()
         self.graph = None
@@ -90,11 +98,27 @@ class GraphedStep:
         self.launches_per_step = ops.launch_count() - n0
 
     def _eager(self):
+        join = None
+        if self.zero_first:
+            main = torch.cuda.current_stream()
+            key = main.device.index or 0
+            side = self._zero_streams.get(key)
+            if side is None:
+                side = self._zero_streams[key] = torch.cuda.Stream(device=main.device)
+            fork, join = torch.cuda.Event(), torch.cuda.Event()
+            fork.record(main)
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                self.model.zero_grad(set_to_none=True)
+                join.record(side)
         out = self.model(self.data)
+        if join is not None:
+            torch.cuda.current_stream().wait_event(join)
         (out['loss'] if self.loss_scale == 1.0 else out['loss'] * self.loss_scale).backward()
         if self.post is not None:
             self.post()
-        self.model.zero_grad(set_to_none=True)
+        if not self.zero_first:
+            self.model.zero_grad(set_to_none=True)
         self.loss = out['loss'].detach()
         self.pred = out.get('pred', None)
 
