@@ -541,6 +541,7 @@ def run_experiments(args):
 
     * zero_first: GraphedStep(zero_first=True) — the sparse re-zero of the table gradients overlapped with the next forward
       (each replay clears the rows ITS batch touched two replays earlier: same work per step, one step later).
+    * l2_fetch_32B: the default step with cudaLimitMaxL2FetchGranularity = 32 (aimed at the scatter epilogue's line fetches).
     * fused_tc_tail: rpb_set_option('fused_tc_tail', 1) — tower-tail layers of the one-kernel forward on tcgen05: parity
       against the default kernel on the same batch (logit / loss / gradients), then step and forward-only timings."""
     from rec_pangu_b200 import ops, _lib
@@ -606,6 +607,17 @@ def run_experiments(args):
         torch.cuda.synchronize()
     except Exception as ex:
         res['zero_first'] = {'error': repr(ex)}
+    # ---- L2 fetch granularity 32 B (cudaLimitMaxL2FetchGranularity, device-wide hint): the scatter epilogue's `red`s fetch
+    # whole 128-byte lines (340 MB read for 109 MB of reductions, profiles/r01_deepfm_step_ncu_full.md); replays of the
+    # graphs captured above, so only the limit differs
+    try:
+        if base is not None:
+            lib = _lib.load()
+            _lib.check(lib.rpb_set_option(b'l2_fetch_granularity', 32), 'rpb_set_option(l2_fetch_granularity)')
+            res['l2_fetch_32B'] = {'ms_per_step': time_graphs(base)}
+            _lib.check(lib.rpb_set_option(b'l2_fetch_granularity', 128), 'rpb_set_option(l2_fetch_granularity)')
+    except Exception as ex:
+        res['l2_fetch_32B'] = {'error': repr(ex)}
     # ---- tcgen05 tower tail: parity first (eager, same batch), then timings.  LAST: a protocol bug traps the context.
     try:
         lib = _lib.load()
