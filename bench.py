@@ -603,22 +603,17 @@ def run_experiments(args):
         zs = [GraphedStep(model, cb, zero_first=True) for cb in cbs]
         res['zero_first'] = {'ms_per_step': time_graphs(zs), 'launches_per_step': zs[0].launches_per_step}
         del zs
-        model.zero_grad()
-        torch.cuda.synchronize()
     except Exception as ex:
         res['zero_first'] = {'error': repr(ex)}
-    # ---- L2 fetch granularity 32 B (cudaLimitMaxL2FetchGranularity, device-wide hint): the scatter epilogue's `red`s fetch
-    # whole 128-byte lines (340 MB read for 109 MB of reductions, profiles/r01_deepfm_step_ncu_full.md); replays of the
-    # graphs captured above, so only the limit differs
     try:
-        if base is not None:
-            lib = _lib.load()
-            _lib.check(lib.rpb_set_option(b'l2_fetch_granularity', 32), 'rpb_set_option(l2_fetch_granularity)')
-            res['l2_fetch_32B'] = {'ms_per_step': time_graphs(base)}
-            _lib.check(lib.rpb_set_option(b'l2_fetch_granularity', 128), 'rpb_set_option(l2_fetch_granularity)')
+        # the rotated graphs leave the rows of the batch before last populated: start the parity leg from all-zero buffers
+        model.zero_grad()
+        for buf in model.embedding_layer._grad_store.buffers.values():
+            buf.zero_()
+        torch.cuda.synchronize()
     except Exception as ex:
-        res['l2_fetch_32B'] = {'error': repr(ex)}
-    # ---- tcgen05 tower tail: parity first (eager, same batch), then timings.  LAST: a protocol bug traps the context.
+        res['reset_error'] = repr(ex)
+    # ---- tcgen05 tower tail: parity first (eager, same batch), then timings.  A protocol bug traps the context (bounded mbarrier waits).
     try:
         lib = _lib.load()
         d = cbs[0].as_dict()
@@ -651,6 +646,16 @@ def run_experiments(args):
         _lib.check(lib.rpb_set_option(b'fused_tc_tail', 0), 'rpb_set_option(fused_tc_tail)')
     except Exception as ex:
         res.setdefault('fused_tc_tail', {})['error'] = repr(ex)
+    # ---- L2 fetch granularity 32 B (cudaLimitMaxL2FetchGranularity, device-wide hint): the scatter epilogue's `red`s fetch
+    # whole 128-byte lines (340 MB read for 109 MB of reductions, profiles/r01_deepfm_step_ncu_full.md); replays of the
+    # graphs captured above, so only the limit differs (runs after the tail leg; if that one trapped, this reports the error)
+    try:
+        if base is not None:
+            lib = _lib.load()
+            _lib.check(lib.rpb_set_option(b'l2_fetch_granularity', 32), 'rpb_set_option(l2_fetch_granularity)')
+            res['l2_fetch_32B'] = {'ms_per_step': time_graphs(base)}      # last leg: the limit is not restored
+    except Exception as ex:
+        res['l2_fetch_32B'] = {'error': repr(ex)}
     print(json.dumps(res), flush=True)
     sys.stdout.flush()
     os._exit(0)            # a trapped context must not turn teardown into a hang
