@@ -542,8 +542,9 @@ def run_experiments(args):
     * zero_first: GraphedStep(zero_first=True) — the sparse re-zero of the table gradients overlapped with the next forward
       (each replay clears the rows ITS batch touched two replays earlier: same work per step, one step later).
     * l2_fetch_32B: the default step with cudaLimitMaxL2FetchGranularity = 32 (aimed at the scatter epilogue's line fetches).
-    * fused_tc_tail: rpb_set_option('fused_tc_tail', 1) — tower-tail layers of the one-kernel forward on tcgen05: parity
-      against the default kernel on the same batch (logit / loss / gradients), then step and forward-only timings."""
+    * fused_tc_tail / tower_bwd_tc / both_tc: rpb_set_option(...) — the tower-tail layers of the one-kernel forward, and the dz
+      chain of the tower-tail backward, on tcgen05: parity against the default kernels on the same batch (logit / loss /
+      gradients), then step (and forward-only) timings."""
     from rec_pangu_b200 import ops, _lib
     from rec_pangu_b200.models.ranking import DeepFM
     from rec_pangu_b200.runtime import ColumnarBatch, GraphedStep
@@ -613,39 +614,56 @@ def run_experiments(args):
         torch.cuda.synchronize()
     except Exception as ex:
         res['reset_error'] = repr(ex)
-    # ---- tcgen05 tower tail: parity first (eager, same batch), then timings.  A protocol bug traps the context (bounded mbarrier waits).
-    try:
-        lib = _lib.load()
-        d = cbs[0].as_dict()
+    # ---- tcgen05 variants: parity first (eager, same batch, against the default kernels), then timings.  A protocol bug
+    # traps the context (every mbarrier wait is bounded), which ends this process's measurements but nothing else.
+    lib = _lib.load()
+    d0 = cbs[0].as_dict()
 
-        def one(flag):
-            _lib.check(lib.rpb_set_option(b'fused_tc_tail', flag), 'rpb_set_option(fused_tc_tail)')
-            model.zero_grad()
-            out = model(d)
-            out['loss'].backward()
-            torch.cuda.synchronize()
-            ops.check_index_errors(dev)
-            gw = {n: p.grad.detach().clone() for n, p in model.named_parameters() if not n.startswith('embedding_layer.')}
-            gt = model.embedding_layer.tables()[0].grad.detach().clone()
-            return model._last_logit.clone(), float(out['loss'].item()), gw, gt
-
-        l0, loss0, gw0, gt0 = one(0)
-        l1, loss1, gw1, gt1 = one(1)
-        rel = {n: float((gw1[n] - gw0[n]).abs().max() / gw0[n].abs().max().clamp_min(1e-12)) for n in gw0}
-        tc = {'max_abs_dlogit': float((l1 - l0).abs().max()), 'loss_default': loss0, 'loss_tc_tail': loss1,
-              'max_rel_dgrad_dense': max(rel.values()),
-              'max_rel_dgrad_table0': float((gt1 - gt0).abs().max() / gt0.abs().max().clamp_min(1e-12)),
-              'tolerance': 'north_star: |dlogit| <= 1e-4'}
-        tc['parity_ok'] = bool(tc['max_abs_dlogit'] <= 1e-4 and abs(loss1 - loss0) <= 1e-5 and tc['max_rel_dgrad_dense'] <= 5e-4)
-        res['fused_tc_tail'] = tc
+    def eager_step(opts):
+        for k in ('fused_tc_tail', 'tower_bwd_tc'):
+            _lib.check(lib.rpb_set_option(k.encode(), 1 if k in opts else 0), f'rpb_set_option({k})')
         model.zero_grad()
-        ts = [GraphedStep(model, cb) for cb in cbs]          # captured with the option on
-        tc['ms_per_step'] = time_graphs(ts)
-        fg, keep = fwd_graphs()
-        tc['fwd_us'] = 1e3 * time_graphs(fg)
-        _lib.check(lib.rpb_set_option(b'fused_tc_tail', 0), 'rpb_set_option(fused_tc_tail)')
-    except Exception as ex:
-        res.setdefault('fused_tc_tail', {})['error'] = repr(ex)
+        out = model(d0)
+        out['loss'].backward()
+        torch.cuda.synchronize()
+        ops.check_index_errors(dev)
+        gw = {n: p.grad.detach().clone() for n, p in model.named_parameters() if not n.startswith('embedding_layer.')}
+        gt = model.embedding_layer.tables()[0].grad.detach().clone()
+        return model._last_logit.clone(), float(out['loss'].item()), gw, gt
+
+    ref = None
+    for name, opts in (('tower_bwd_tc', ('tower_bwd_tc',)), ('fused_tc_tail', ('fused_tc_tail',)),
+                       ('both_tc', ('fused_tc_tail', 'tower_bwd_tc'))):
+        try:
+            if ref is None:
+                ref = eager_step(())
+            l0, loss0, gw0, gt0 = ref
+            l1, loss1, gw1, gt1 = eager_step(opts)
+            rel = {n: float((gw1[n] - gw0[n]).abs().max() / gw0[n].abs().max().clamp_min(1e-12)) for n in gw0}
+            tc = {'max_abs_dlogit': float((l1 - l0).abs().max()), 'loss_default': loss0, 'loss_variant': loss1,
+                  'max_rel_dgrad_dense': max(rel.values()), 'worst_dense_grad': max(rel, key=rel.get),
+                  'max_rel_dgrad_table0': float((gt1 - gt0).abs().max() / gt0.abs().max().clamp_min(1e-12)),
+                  'tolerance': 'north_star: |dlogit| <= 1e-4; gradients 5e-4 of the tensor maximum'}
+            tc['parity_ok'] = bool(tc['max_abs_dlogit'] <= 1e-4 and abs(loss1 - loss0) <= 1e-5 and
+                                   tc['max_rel_dgrad_dense'] <= 5e-4 and tc['max_rel_dgrad_table0'] <= 5e-4)
+            res[name] = tc
+            model.zero_grad()
+            ts = [GraphedStep(model, cb) for cb in cbs]          # captured with the options on
+            tc['ms_per_step'] = time_graphs(ts)
+            tc['launches_per_step'] = ts[0].launches_per_step
+            if 'fused_tc_tail' in opts:
+                fg, keep = fwd_graphs()
+                tc['fwd_us'] = 1e3 * time_graphs(fg)
+                del fg, keep
+            del ts
+        except Exception as ex:
+            res.setdefault(name, {})['error'] = repr(ex)
+    try:
+        for k in (b'fused_tc_tail', b'tower_bwd_tc'):
+            lib.rpb_set_option(k, 0)
+        model.zero_grad()
+    except Exception:
+        pass
     # ---- L2 fetch granularity 32 B (cudaLimitMaxL2FetchGranularity, device-wide hint): the scatter epilogue's `red`s fetch
     # whole 128-byte lines (340 MB read for 109 MB of reductions, profiles/r01_deepfm_step_ncu_full.md); replays of the
     # graphs captured above, so only the limit differs (runs after the tail leg; if that one trapped, this reports the error)

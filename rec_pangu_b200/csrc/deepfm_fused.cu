@@ -552,7 +552,7 @@ static size_t fg_smem_bytes(int la, int n_tail, bool tctail = false) {
            (tctail ? (size_t)(TC_BLOCK_M + 256) * 4 : (size_t)(TC_BLOCK_M * TW_LDA + n_tail * TW_H * TW_H + 256) * 4) + 1024;
 }
 
-int tc_prepare_tail_weights(const float* const* W, int n_tail, CUtensorMap* tm_hi, CUtensorMap* tm_lo, cudaStream_t st);   // linear_tc.cu
+
 
 }  // namespace rpb
 
@@ -618,7 +618,7 @@ RPB_API int rpb_deepfm_fwd_fused(const RpbGatherDesc* g, const float* W1, const 
     const bool tctail = g_fused_tc_tail != 0 && fg_smem_bytes(3, d->n_tail, true) <= cap;
     CUtensorMap tmThi = tmBhi, tmTlo = tmBlo;          // placeholders when the tail runs on the CUDA cores
     if (tctail) {
-        rc = tc_prepare_tail_weights(tw.W, d->n_tail, &tmThi, &tmTlo, st);
+        rc = tc_prepare_tail_weights(tw.W, d->n_tail, &tmThi, &tmTlo, st, 0, 6);
         if (rc != 0) return rc;
     }
     auto launch = [&](auto la_tag, auto sh_tag, auto tc_tag) -> int {

@@ -1040,22 +1040,25 @@ int tc_prepare_weight(const float* W, long long ldw, int N, int K, CUtensorMap* 
 }
 
 // Pre-split operands of the square 64 x 64 tower-tail layers for the tcgen05 tail of deepfm_fused.cu: hi / lo
-// [n_tail * 64, 64] (layer l = rows l*64 .. l*64+63) in workspace slot 6 + their TMA maps with [64 x 32] boxes.
+// [n_tail * 64, 64] (layer l = rows l*64 .. l*64+63) in workspace `slot` (6: forward, 7: backward with transpose = 1, i.e.
+// W_l^T, the K-major operand of dz . W_l) + their TMA maps with [64 x 32] boxes.
 struct TailSplitArgs { const float* W[RPB_TOWER_MAX_TAIL]; };
 __global__ void __launch_bounds__(256)
-split_pack_tail_kernel(const TailSplitArgs a, int n_tail, float* __restrict__ hi, float* __restrict__ lo) {
+split_pack_tail_kernel(const TailSplitArgs a, int n_tail, int transpose, float* __restrict__ hi, float* __restrict__ lo) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tail * 64 * 64) return;
-    const float v = __ldg(a.W[t >> 12] + (t & 4095));
+    const int i = t & 4095;                              // out[l][r = i >> 6][c = i & 63] = transpose ? W_l[c][r] : W_l[r][c]
+    const float v = __ldg(a.W[t >> 12] + (transpose ? ((i & 63) << 6) + (i >> 6) : i));
     const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
     hi[t] = h;
     lo[t] = v - h;
 }
 
-int tc_prepare_tail_weights(const float* const* W, int n_tail, CUtensorMap* tm_hi, CUtensorMap* tm_lo, cudaStream_t st) {
+int tc_prepare_tail_weights(const float* const* W, int n_tail, CUtensorMap* tm_hi, CUtensorMap* tm_lo, cudaStream_t st,
+                            int transpose, int slot) {
     if (n_tail < 1 || n_tail > RPB_TOWER_MAX_TAIL) return RPB_ERR_UNSUPPORTED;
     int werr = 0;
-    float* ws = static_cast<float*>(workspace(6, (size_t)2 * n_tail * 64 * 64 * sizeof(float), &werr));
+    float* ws = static_cast<float*>(workspace(slot, (size_t)2 * n_tail * 64 * 64 * sizeof(float), &werr));
     if (ws == nullptr) return werr;
     float* hi = ws;
     float* lo = ws + (size_t)n_tail * 64 * 64;
@@ -1064,7 +1067,7 @@ int tc_prepare_tail_weights(const float* const* W, int n_tail, CUtensorMap* tm_h
         if (W[l] == nullptr) return RPB_ERR_BAD_ARG;
         a.W[l] = W[l];
     }
-    split_pack_tail_kernel<<<ceil_div(n_tail * 64 * 64, 256), 256, 0, st>>>(a, n_tail, hi, lo);
+    split_pack_tail_kernel<<<ceil_div(n_tail * 64 * 64, 256), 256, 0, st>>>(a, n_tail, transpose, hi, lo);
     int rc = make_map(tm_hi, hi, (long long)n_tail * 64, 64, 64, 64);
     if (rc == 0) rc = make_map(tm_lo, lo, (long long)n_tail * 64, 64, 64, 64);
     return rc;

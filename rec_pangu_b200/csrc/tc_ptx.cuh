@@ -118,5 +118,7 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int m, int n) {
 }
 
 int tc_prepare_weight(const float* W, long long ldw, int N, int K, CUtensorMap* tm_hi, CUtensorMap* tm_lo, cudaStream_t st);   // linear_tc.cu
+int tc_prepare_tail_weights(const float* const* W, int n_tail, CUtensorMap* tm_hi, CUtensorMap* tm_lo, cudaStream_t st,
+                            int transpose, int slot);                                                                       // linear_tc.cu
 
 }  // namespace rpb

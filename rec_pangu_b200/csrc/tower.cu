@@ -20,16 +20,6 @@ namespace rpb {
 constexpr int TW_ROWS = 64;              // samples per tile of the standalone kernels
 constexpr int TW_THREADS = 128;          // 8 row groups x 16 column groups
 
-struct TowerBwdParams {
-    const float* hin[TW_MAX_TAIL + 1]; long long ldh1;       // hin[0] = h1 (row stride ldh1), hin[j>0] row stride 64
-    const float* W[TW_MAX_TAIL]; const float* w_out;
-    float* dz[TW_MAX_TAIL + 1]; float* db[TW_MAX_TAIL + 1];
-    float* dw_out; float* db_out;
-    const float* pred; const float* label; const float* gloss; float eps, scale;
-    const float* dlogit_in; float* dlogit_out;
-    int M, n_tail;
-};
-
 __global__ void __launch_bounds__(TW_THREADS, 4)
 tower_tail_fwd_kernel(const TowerFwdParams p) {
     extern __shared__ __align__(16) float tw_smem[];
@@ -329,6 +319,10 @@ RPB_API int rpb_tower_tail_bwd(const RpbTowerBwdDesc* d, void* stream) {
     p.pred = d->pred; p.label = d->label; p.gloss = d->gloss; p.eps = d->eps; p.scale = d->scale;
     p.dlogit_in = d->dlogit_in; p.dlogit_out = d->dlogit_out;
     p.M = d->M; p.n_tail = d->n_tail;
+    if (g_tower_bwd_tc) {          // opt-in: the dz chain on tcgen05 (tower_tc.cu); declines shapes it is not built for
+        const int rc = tower_tail_bwd_tc(p, reinterpret_cast<cudaStream_t>(stream));
+        if (rc != RPB_ERR_UNSUPPORTED) return rc;
+    }
     const size_t smem = (size_t)(2 * TW_ROWS * TW_LDA + d->n_tail * TW_H * TW_H) * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(tower_tail_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)      // 4 CTAs x ~50 KiB per SM only fit with the L1/shared split at its shared-memory maximum

@@ -20,6 +20,17 @@ struct TowerFwdParams {
     int M, n_tail, enabled;
 };
 
+struct TowerBwdParams {
+    const float* hin[TW_MAX_TAIL + 1]; long long ldh1;       // hin[0] = h1 (row stride ldh1), hin[j>0] row stride 64
+    const float* W[TW_MAX_TAIL]; const float* w_out;
+    float* dz[TW_MAX_TAIL + 1]; float* db[TW_MAX_TAIL + 1];
+    float* dw_out; float* db_out;
+    const float* pred; const float* label; const float* gloss; float eps, scale;
+    const float* dlogit_in; float* dlogit_out;
+    int M, n_tail;
+};
+int tower_tail_bwd_tc(const TowerBwdParams& p, cudaStream_t st);       // tower_tc.cu (opt-in tcgen05 backward tail)
+
 // NT threads cooperate on a tile of NT/2 rows: thread (ty = t >> 4, tx = t & 15) owns rows ty + (NT/16)*i, i < 8, and
 // columns tx*4 .. tx*4+3.
 // acc[i][c] += sum_k As[ty + RG i][k] * Bs[k][tx * 4 + c]     (As row stride TW_LDA, Bs row stride TW_H)
