@@ -260,6 +260,44 @@ def test_deepfm_one_kernel_forward_tc_tail(B, F, Nd, hidden):
         assert (a - b).abs().max().item() <= 5e-4 * max(1e-6, b.abs().max().item()) + 1e-7, n
 
 
+@pytest.mark.skipif(os.environ.get('RPB_EXPERIMENTAL', '0') != '1',
+                    reason='tcgen05 tower-tail backward: compiled but not yet run on hardware (opt-in)')
+@pytest.mark.parametrize('B,F,Nd,hidden', [(4096, 26, 13, [64, 64, 64]), (5000, 26, 13, [64, 64]), (1300, 4, 0, [64, 64, 64, 64])])
+def test_tower_tail_backward_tc(B, F, Nd, hidden):
+    """rpb_set_option('tower_bwd_tc', 1): the dz chain of rpb_tower_tail_bwd on tcgen05 (3xTF32 through tensor memory) vs the
+    exact-fp32 CUDA-core kernel: identical forward, every gradient within the tensor-relative tolerance."""
+    from helpers import make_enc, make_batch
+    from rec_pangu_b200 import ops, _lib
+    from rec_pangu_b200.models.ranking import DeepFM
+    enc = make_enc(F, Nd, 3000)
+    torch.manual_seed(2)
+    model = DeepFM(embedding_dim=16, hidden_units=hidden, enc_dict=enc)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if 'embedding_layer' in n:
+                p.mul_(0.25)
+            elif p.dim() == 1:
+                p.copy_(torch.randn(p.shape) * 0.05)
+    model = model.cuda().train()
+    data = make_batch(enc, B, seed=21, device='cuda')
+    res = []
+    for flag in (1, 0):
+        _lib.check(_lib.load().rpb_set_option(b'tower_bwd_tc', flag), 'rpb_set_option(tower_bwd_tc)')
+        try:
+            model.zero_grad()
+            out = model(data)
+            out['loss'].backward()
+            torch.cuda.synchronize()
+            ops.check_index_errors()
+            res.append((out['loss'].detach().clone(), {n: p.grad.clone() for n, p in model.named_parameters()}))
+        finally:
+            _lib.check(_lib.load().rpb_set_option(b'tower_bwd_tc', 0), 'rpb_set_option(tower_bwd_tc)')
+    assert torch.equal(res[0][0], res[1][0])
+    for n in res[0][1]:
+        a, b = res[0][1][n], res[1][1][n]
+        assert (a - b).abs().max().item() <= 5e-4 * max(1e-6, b.abs().max().item()) + 1e-7, n
+
+
 def test_deepfm_one_kernel_reports_bad_index():
     from helpers import make_enc, make_batch
     from rec_pangu_b200 import ops
