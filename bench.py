@@ -655,6 +655,16 @@ def run_experiments(args):
                 fg, keep = fwd_graphs()
                 tc['fwd_us'] = 1e3 * time_graphs(fg)
                 del fg, keep
+                if name == 'fused_tc_tail':                  # per-role cycles of CTA 0 (rpb_debug_fused_trace): what bounds it now
+                    import ctypes
+                    lib.rpb_debug_fused_trace(None, 1)
+                    model(d0)
+                    torch.cuda.synchronize()
+                    out16 = (ctypes.c_uint64 * 16)()
+                    lib.rpb_debug_fused_trace(out16, 0)
+                    names = ['kernel', 'gather_cp_wait', 'gather_wait_slot', 'gather_work', 'mma_wait_weights', 'mma_wait_operands',
+                             'mma_wait_acc', 'mma_issue', 'epi_wait_acc', 'epi_rounds', 'epi_head', 'producer_wait']
+                    tc['trace_cycles_cta0'] = {k: int(v) for k, v in zip(names, out16)}
             del ts
         except Exception as ex:
             res.setdefault(name, {})['error'] = repr(ex)
