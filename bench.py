@@ -541,6 +541,8 @@ def run_experiments(args):
 
     * zero_first: GraphedStep(zero_first=True) — the sparse re-zero of the table gradients overlapped with the next forward
       (each replay clears the rows ITS batch touched two replays earlier: same work per step, one step later).
+    * sharded_fused_local: the fused core on row-sharded tables (RPB_SHARDED_FUSED) with all shards on this one GPU
+      (dist.LocalShards): parity of logits and of every gradient against the unsharded model.
     * l2_fetch_32B: the default step with cudaLimitMaxL2FetchGranularity = 32 (aimed at the scatter epilogue's line fetches).
     * fused_tc_tail / tower_bwd_tc / both_tc: rpb_set_option(...) — the tower-tail layers of the one-kernel forward, and the dz
       chain of the tower-tail backward, on tcgen05: parity against the default kernels on the same batch (logit / loss /
@@ -614,6 +616,52 @@ def run_experiments(args):
         torch.cuda.synchronize()
     except Exception as ex:
         res['reset_error'] = repr(ex)
+    # ---- fused core on row-sharded tables, checked on ONE GPU: dist.LocalShards keeps all G shards of every table on this
+    # device, so the sharded variants of the one-kernel forward and of the dx-GEMM scatter epilogue see the same pointer
+    # tables as over NVLink; a smaller vocabulary keeps the second copy of the tables cheap
+    try:
+        from rec_pangu_b200 import dist as rdist
+        G_loc, V_loc, B_loc = 4, 50_000, 8192
+        enc_s = {f'I{i + 1}': {'min': 0.0, 'max': 1.0} for i in range(CFG['Nd'])}
+        enc_s.update({f'C{i + 1}': {'vocab_size': V_loc} for i in range(CFG['F'])})
+        torch.manual_seed(3)
+        with torch.device(dev):
+            ref_m = DeepFM(embedding_dim=D, hidden_units=CFG['hidden'], enc_dict=enc_s)
+            sh_m = DeepFM(embedding_dim=D, hidden_units=CFG['hidden'], enc_dict=enc_s)
+        sh_m.load_state_dict({k: v.clone() for k, v in ref_m.state_dict().items()})
+        ref_m.train()
+        sh_m.train()
+        ls = rdist.LocalShards(sh_m.embedding_layer, G_loc)
+        sh_m.embedding_layer.attach_shards(ls)
+        bt = synth_batch(enc_s, B_loc, gen, device=dev)
+        out_r = ref_m(bt)
+        out_r['loss'].backward()
+        ops.SHARDED_FUSED = 1
+        try:
+            n0 = ops.launch_count()
+            out_s = sh_m(bt)
+            n_fwd = ops.launch_count() - n0
+            out_s['loss'].backward()
+        finally:
+            ops.SHARDED_FUSED = 0
+        torch.cuda.synchronize()
+        ops.check_index_errors(dev)
+        tg = 0.0
+        for f, t in enumerate(ref_m.embedding_layer.tables()):
+            tg = max(tg, float((ls.full_grad(f) - t.grad).abs().max() / t.grad.abs().max().clamp_min(1e-12)))
+        dense_r = {n: p.grad for n, p in ref_m.named_parameters() if not n.startswith('embedding_layer.')}
+        dg = max(float((p.grad - dense_r[n]).abs().max() / dense_r[n].abs().max().clamp_min(1e-12))
+                 for n, p in sh_m.named_parameters() if not n.startswith('embedding_layer.'))
+        sl = {'shards': G_loc, 'forward_launches': n_fwd,
+              'max_abs_dlogit': float((sh_m._last_logit - ref_m._last_logit).abs().max()),
+              'dloss': abs(float(out_s['loss'].item()) - float(out_r['loss'].item())),
+              'max_rel_dgrad_tables': tg, 'max_rel_dgrad_dense': dg}
+        sl['parity_ok'] = bool(n_fwd == 2 and sl['max_abs_dlogit'] <= 1e-6 and sl['dloss'] <= 1e-6 and tg <= 1e-4 and dg <= 1e-4)
+        res['sharded_fused_local'] = sl
+        del ref_m, sh_m, ls, out_r, out_s
+        torch.cuda.empty_cache()
+    except Exception as ex:
+        res.setdefault('sharded_fused_local', {})['error'] = repr(ex)
     # ---- tcgen05 variants: parity first (eager, same batch, against the default kernels), then timings.  A protocol bug
     # traps the context (every mbarrier wait is bounded), which ends this process's measurements but nothing else.
     lib = _lib.load()

@@ -152,6 +152,54 @@ class ShardedTables:
         return unshard(shards, self.rows[f])
 
 
+class LocalShards:
+    """All G row shards of every table on ONE device, with the pointer tables the sharded kernels take — a single-GPU
+    stand-in for ShardedTables (no symmetric memory, no collectives; `barrier()` is a no-op) used to check the sharded
+    address arithmetic of the kernels (owner = id mod G, local row = id div G) without a second GPU: a shard pointer is a
+    shard pointer, local or NVLink.  Acts as rank 0: `weights` / `grads` are rank 0's shards (the autograd anchors and the
+    published `.grad`), `all_weights[f][g]` / `all_grads[f][g]` hold every shard."""
+
+    def __init__(self, emb_layer, world: int):
+        self.world, self.rank, self.group = int(world), 0, None
+        self.cols = list(emb_layer.emb_feature)
+        self.D = emb_layer.embedding_dim
+        self.rows = [int(emb_layer.enc_dict[c]['vocab_size']) + 1 for c in self.cols]
+        F, G = len(self.cols), self.world
+        self.all_weights, self.all_grads = [], []
+        w_ptrs = torch.zeros(F * G, dtype=torch.int64)
+        g_ptrs = torch.zeros(F * G, dtype=torch.int64)
+        dev = None
+        for f, c in enumerate(self.cols):
+            full = emb_layer.embedding_layer[c].weight.data
+            dev = full.device
+            ws = [local_slice(full, g, G) for g in range(G)]
+            gs = [torch.zeros_like(w) for w in ws]
+            for g in range(G):
+                w_ptrs[f * G + g] = ws[g].data_ptr()
+                g_ptrs[f * G + g] = gs[g].data_ptr()
+            self.all_weights.append(ws)
+            self.all_grads.append(gs)
+        self.weights = [ws[0] for ws in self.all_weights]
+        self.grads = [gs[0] for gs in self.all_grads]
+        self.w_tab, self.g_tab = w_ptrs.to(dev), g_ptrs.to(dev)
+        self.pending = []
+
+    def barrier(self):
+        pass
+
+    def full_table(self, f: int) -> torch.Tensor:
+        return unshard(self.all_weights[f], self.rows[f])
+
+    def full_grad(self, f: int) -> torch.Tensor:
+        return unshard(self.all_grads[f], self.rows[f])
+
+    def zero_grads(self):
+        for gs in self.all_grads:
+            for g in gs:
+                g.zero_()
+        self.pending = []
+
+
 def _table_key(col: str) -> str:
     return f'embedding_layer.embedding_layer.{col}.weight'           # SURVEY.md App. C
 

@@ -298,6 +298,52 @@ def test_tower_tail_backward_tc(B, F, Nd, hidden):
         assert (a - b).abs().max().item() <= 5e-4 * max(1e-6, b.abs().max().item()) + 1e-7, n
 
 
+@pytest.mark.skipif(os.environ.get('RPB_EXPERIMENTAL', '0') != '1',
+                    reason='fused DeepFM core on row-sharded tables: compiled but not yet run on hardware (opt-in)')
+@pytest.mark.parametrize('G', [2, 3, 8])
+def test_sharded_fused_core_on_local_shards(G):
+    """ops.SHARDED_FUSED with dist.LocalShards (all G shards of every table on this GPU): the sharded variants of the
+    one-kernel forward and of the dx-GEMM scatter epilogue resolve owner = id mod G / local row = id div G through the same
+    pointer tables they get over NVLink.  Logits equal the unsharded model's, every table gradient (shards re-interleaved)
+    and every dense gradient agree."""
+    from helpers import make_enc, make_batch
+    from rec_pangu_b200 import ops, dist as rdist
+    from rec_pangu_b200.models.ranking import DeepFM
+    enc = make_enc(6, 3, [1001, 577, 333, 2000, 170, 64])
+    torch.manual_seed(4)
+    ref = DeepFM(embedding_dim=16, hidden_units=[64, 64], enc_dict=enc)
+    with torch.no_grad():
+        for n, p in ref.named_parameters():
+            if 'embedding_layer' in n:
+                p.mul_(0.25)
+    sh = DeepFM(embedding_dim=16, hidden_units=[64, 64], enc_dict=enc)
+    sh.load_state_dict({k: v.clone() for k, v in ref.state_dict().items()})
+    ref, sh = ref.cuda().train(), sh.cuda().train()
+    ls = rdist.LocalShards(sh.embedding_layer, G)
+    sh.embedding_layer.attach_shards(ls)
+    data = make_batch(enc, 1500, seed=5, device='cuda')
+    out_r = ref(data)
+    out_r['loss'].backward()
+    ops.SHARDED_FUSED = 1
+    try:
+        n0 = ops.launch_count()
+        out_s = sh(data)
+        assert ops.launch_count() - n0 == 2                      # weight split + the one-kernel forward
+        out_s['loss'].backward()
+    finally:
+        ops.SHARDED_FUSED = 0
+    torch.cuda.synchronize()
+    ops.check_index_errors()
+    torch.testing.assert_close(sh._last_logit, ref._last_logit, rtol=0, atol=1e-6)
+    for f, t in enumerate(ref.embedding_layer.tables()):
+        full = ls.full_grad(f)
+        assert (full - t.grad).abs().max().item() <= 1e-4 * max(1e-6, t.grad.abs().max().item()) + 1e-8, f
+    dense_r = {n: p.grad for n, p in ref.named_parameters() if not n.startswith('embedding_layer.')}
+    for n, p in sh.named_parameters():
+        if not n.startswith('embedding_layer.'):
+            torch.testing.assert_close(p.grad, dense_r[n], rtol=1e-4, atol=1e-6, msg=lambda s: f'{n}: {s}')
+
+
 def test_deepfm_one_kernel_reports_bad_index():
     from helpers import make_enc, make_batch
     from rec_pangu_b200 import ops
