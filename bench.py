@@ -513,7 +513,7 @@ def run_ours(args):
     if rank == 0:
         # opt-in variants not yet measured on hardware: in a child process with a hard timeout, only when this run has been
         # quick so far (a slow box must not be pushed past "minutes"), after every measurement of this process is final
-        if world == 1 and not args.no_experiments and not args.no_extras and time.time() - T_START < 150:
+        if world == 1 and not args.no_experiments and not args.no_extras and time.time() - T_START < 180:
             line['experiments'] = experiments_in_child(args.steps)
         if world == 1 and not args.no_cpu_baseline:
             try:
