@@ -513,8 +513,14 @@ def run_ours(args):
     if rank == 0:
         # opt-in variants not yet measured on hardware: in a child process with a hard timeout, only when this run has been
         # quick so far (a slow box must not be pushed past "minutes"), after every measurement of this process is final
-        if world == 1 and not args.no_experiments and not args.no_extras and time.time() - T_START < 180:
-            line['experiments'] = experiments_in_child(args.steps)
+        t_parent = time.time() - T_START
+        if world == 1 and not args.no_experiments and not args.no_extras:
+            if t_parent < 180:
+                line['experiments'] = experiments_in_child(args.steps)
+                line['experiments']['wall_s'] = round(time.time() - T_START - t_parent, 1)
+            else:
+                line['experiments'] = {'skipped': f'this run had already taken {t_parent:.0f} s'}
+        line['wall_s_before_cpu_baseline'] = round(time.time() - T_START, 1)
         if world == 1 and not args.no_cpu_baseline:
             try:
                 torch.cuda.empty_cache()
