@@ -5,6 +5,7 @@ numerical step of the hot path is a kernel of librec_pangu_b200.so.  CUDA tensor
 fallback, and a missing library raises at first use.
 """
 import ctypes as C
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -15,17 +16,17 @@ from ._lib import GatherDesc, ScatterDesc, TowerFwdDesc, TowerBwdDesc, check
 __all__ = ['GradStore', 'hash_to_row', 'essm_head', 'deepfm_core', 'gather', 'gather_sharded', 'sharded_clean', 'fm_interaction', 'mlp_forward', 'sigmoid_bce', 'linear', 'feature_row_stride',
            'check_index_errors', 'set_gemm_impl', 'get_gemm_impl', 'launch_count', 'reset_launch_count']
 
-_GEMM_IMPL = int(__import__('os').environ.get('RPB_GEMM_IMPL', '0'))   # 0 auto, 1 SIMT fp32, 2 tcgen05 3xTF32
+_GEMM_IMPL = int(os.environ.get('RPB_GEMM_IMPL', '0'))   # 0 auto, 1 SIMT fp32, 2 tcgen05 3xTF32
 # DeepFM backward: 1 = layer-1 dx GEMM scatters table gradients from its epilogue (rpb_linear_dx_scatter),
 # 0 = dx GEMM to HBM followed by rpb_gather_bwd.  Both are bit-for-bit the same sums in a different add order.
-FUSED_DX_SCATTER = int(__import__('os').environ.get('RPB_DX_SCATTER', '1'))
+FUSED_DX_SCATTER = int(os.environ.get('RPB_DX_SCATTER', '1'))
 # MLP tower tail (rpb_tower_tail_fwd/bwd): 1 = every 64-wide hidden layer after the first, the Linear(64->1) output, the
 # logit sum and (DeepFM) sigmoid + BCE run as ONE fp32 kernel per direction; 0 = one GEMM / row-dot / head kernel each.
-TOWER_TAIL = int(__import__('os').environ.get('RPB_TOWER_TAIL', '1'))
+TOWER_TAIL = int(os.environ.get('RPB_TOWER_TAIL', '1'))
 # 1 = the tail runs inside the epilogue of the layer-1 tcgen05 GEMM (rpb_linear_tower_fwd), 0 = as its own kernel
-FUSED_TOWER_EPILOGUE = int(__import__('os').environ.get('RPB_TOWER_EPILOGUE', '1'))
+FUSED_TOWER_EPILOGUE = int(os.environ.get('RPB_TOWER_EPILOGUE', '1'))
 # 1 = the tower's small weight-gradient kernels run on a side stream concurrently with the layer-1 one
-PARALLEL_WGRAD = int(__import__('os').environ.get('RPB_PARALLEL_WGRAD', '1'))
+PARALLEL_WGRAD = int(os.environ.get('RPB_PARALLEL_WGRAD', '1'))
 _SIDE = {}
 
 
@@ -37,11 +38,11 @@ def _side_stream(dev) -> 'torch.cuda.Stream':
 
 
 # 1 = DeepFM forward as ONE kernel: the layer-1 GEMM gathers its own operand rows (rpb_deepfm_fwd_fused)
-FUSED_GATHER_GEMM = int(__import__('os').environ.get('RPB_FUSED_GATHER_GEMM', '1'))
+FUSED_GATHER_GEMM = int(os.environ.get('RPB_FUSED_GATHER_GEMM', '1'))
 # Row-sharded tables (dist.ShardedTables): 1 = DeepFM runs its fused core on them too — the one-kernel forward requests
 # remote rows with the same cp.async over NVLink and the dx GEMM's scatter epilogue reduces into the owners' gradient
 # shards — instead of the separate gather / MLP / dx GEMM / scatter kernels.  Opt-in until measured on >= 2 GPUs.
-SHARDED_FUSED = int(__import__('os').environ.get('RPB_SHARDED_FUSED', '0'))
+SHARDED_FUSED = int(os.environ.get('RPB_SHARDED_FUSED', '0'))
 _LAUNCHES = 0           # number of librec_pangu_b200 kernels launched (bench.py reports it as gpu_launches)
 
 
