@@ -549,6 +549,7 @@ def run_experiments(args):
       (each replay clears the rows ITS batch touched two replays earlier: same work per step, one step later).
     * sharded_fused_local: the fused core on row-sharded tables (RPB_SHARDED_FUSED) with all shards on this one GPU
       (dist.LocalShards): parity of logits and of every gradient against the unsharded model.
+    * autoint_vec: the AutoInt attention kernels with float4 lane I/O at the config-4 shape: bit-identity, step time.
     * l2_fetch_32B: the default step with cudaLimitMaxL2FetchGranularity = 32 (aimed at the scatter epilogue's line fetches).
     * fused_tc_tail / tower_bwd_tc / both_tc: rpb_set_option(...) — the tower-tail layers of the one-kernel forward, and the dz
       chain of the tower-tail backward, on tcgen05: parity against the default kernels on the same batch (logit / loss /
@@ -728,6 +729,59 @@ def run_experiments(args):
         model.zero_grad()
     except Exception:
         pass
+    # ---- AutoInt attention kernels with float4 lane I/O (rpb_set_option('autoint_vec', 1)): BASELINE.json config 4 shape
+    # (B = 32768, 26 fields, D = 32, 3 heads x 8) on a 100k-row vocabulary (the attention kernels do not see the vocabulary).
+    # Same arithmetic in the same order, so everything must be bit-identical; eval() keeps dropout out of the comparison.
+    try:
+        from rec_pangu_b200.models.ranking import AutoInt
+        enc_a = {f'I{i + 1}': {'min': 0.0, 'max': 1.0} for i in range(CFG['Nd'])}
+        enc_a.update({f'C{i + 1}': {'vocab_size': 100_000} for i in range(CFG['F'])})
+        torch.manual_seed(5)
+        with torch.device(dev):
+            am = AutoInt(embedding_dim=32, num_heads=3, enc_dict=enc_a)
+        am.set_grad_mode('persistent')
+        am.eval()
+        B_a = 32768
+        ab = ColumnarBatch(enc_a, B_a, device=dev, pinned_host=False)
+        ab.load_device(synth_batch(enc_a, B_a, gen, device=dev))
+        da = ab.as_dict()
+
+        def a_step(flag):
+            _lib.check(lib.rpb_set_option(b'autoint_vec', flag), 'rpb_set_option(autoint_vec)')
+            am.zero_grad()
+            out = am(da)
+            out['loss'].backward()
+            torch.cuda.synchronize()
+            ops.check_index_errors(dev)
+            return (out['pred'].detach().clone(), float(out['loss'].item()),
+                    {n: p.grad.detach().clone() for n, p in am.named_parameters() if p.grad is not None and p.numel() < 10_000_000})
+
+        p0, l0_, g0 = a_step(0)
+        p1, l1_, g1 = a_step(1)
+        av = {'pred_equal': bool(torch.equal(p0, p1)), 'dloss': abs(l1_ - l0_),
+              'max_rel_dgrad': max(float((g1[n] - g0[n]).abs().max() / g0[n].abs().max().clamp_min(1e-12)) for n in g0)}
+        av['parity_ok'] = bool(av['pred_equal'] and av['dloss'] == 0.0 and av['max_rel_dgrad'] <= 1e-5)
+        res['autoint_vec'] = av
+        am.zero_grad()
+        am.train()
+        for flag, key in ((0, 'default_ms_per_step'), (1, 'ms_per_step')):
+            _lib.check(lib.rpb_set_option(b'autoint_vec', flag), 'rpb_set_option(autoint_vec)')
+            gs = GraphedStep(am, ab)
+            for _ in range(3):
+                gs.replay()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(20):
+                gs.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            av[key] = e0.elapsed_time(e1) / 20
+            del gs
+        lib.rpb_set_option(b'autoint_vec', 0)
+        del am, ab
+        torch.cuda.empty_cache()
+    except Exception as ex:
+        res.setdefault('autoint_vec', {})['error'] = repr(ex)
     # ---- L2 fetch granularity 32 B (cudaLimitMaxL2FetchGranularity, device-wide hint): the scatter epilogue's `red`s fetch
     # whole 128-byte lines (340 MB read for 109 MB of reductions, profiles/r01_deepfm_step_ncu_full.md); replays of the
     # graphs captured above, so only the limit differs (runs after the tail leg; if that one trapped, this reports the error)

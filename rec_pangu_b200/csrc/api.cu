@@ -16,6 +16,7 @@ int g_gemm_stack_n = 1;
 int g_tf32_raw_hi = 1;
 int g_fused_tc_tail = 0;    // opt-in until measured on hardware
 int g_tower_bwd_tc = 0;     // opt-in until measured on hardware
+int g_autoint_vec = 0;      // opt-in until measured on hardware
 
 // Grow-only per-device scratch buffers (slot = call site).  Kernels of one stream that share a slot are ordered by
 // the stream, so reuse is safe for the single-stream execution model of the reference's training loop.  Growth uses
@@ -69,6 +70,7 @@ RPB_API int rpb_set_option(const char* name, int64_t value) {
     if (n == "gemm_a_tmem") { rpb::g_gemm_a_tmem = value != 0; return 0; }
     if (n == "gemm_stack_n") { rpb::g_gemm_stack_n = value != 0; return 0; }
     if (n == "tf32_raw_hi") { rpb::g_tf32_raw_hi = value != 0; return 0; }
+    if (n == "autoint_vec") { rpb::g_autoint_vec = value != 0; return 0; }
     if (n == "tower_bwd_tc") { rpb::g_tower_bwd_tc = value != 0; return 0; }
     if (n == "fused_tc_tail") { rpb::g_fused_tc_tail = value != 0; return 0; }
     if (n == "wgrad_tc") { rpb::g_wgrad_tc = value != 0; return 0; }

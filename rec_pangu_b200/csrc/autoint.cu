@@ -19,7 +19,10 @@ constexpr int AI_MAXF = 32;
 constexpr int AI_WARPS = 4;
 
 // qkvr: [B*F, ldq] with Q at col 0, K at HD, V at 2HD, R at 3HD (R absent when res != nullptr: then res is [B*F, ldres])
-template <int DH>   // attention_dim d
+// VEC (opt-in rpb_set_option("autoint_vec", 1), not yet run on hardware): a lane's DH outputs are contiguous and 16-byte
+// aligned, so they move as DH/4 float4 requests instead of DH scalar ones — the scalar form issues 4x the memory
+// instructions and writes every 32-byte sector of dQ|dK|dV|dR eight times over (ncu: 493 GB/s at 7.6 % of peak in backward).
+template <int DH, bool VEC>   // attention_dim d
 __global__ void __launch_bounds__(AI_WARPS * 32)
 autoint_attn_fwd_kernel(const float* __restrict__ qkvr, long long ldq, const float* __restrict__ res, long long ldres,
                         float* __restrict__ out, int B, int F, int H, int ncols) {
@@ -76,11 +79,21 @@ autoint_attn_fwd_kernel(const float* __restrict__ qkvr, long long ldq, const flo
             }
             if (on) {
                 float* dst = out + ((size_t)b * F + f0) * HD + c0;
+                if constexpr (VEC) {
+#pragma unroll
+                    for (int e = 0; e < DH; e += 4) {
+                        const float4 r = (res != nullptr) ? ldg_f4(res + ((size_t)b * F + f0) * ldres + c0 + e)
+                                                          : *reinterpret_cast<const float4*>(s + f0 * ncols + 3 * HD + c0 + e);
+                        stg_f4(dst + e, make_float4(fmaxf(o[e] + r.x, 0.f), fmaxf(o[e + 1] + r.y, 0.f),
+                                                    fmaxf(o[e + 2] + r.z, 0.f), fmaxf(o[e + 3] + r.w, 0.f)));
+                    }
+                } else {
 #pragma unroll
                 for (int e = 0; e < DH; ++e) {
                     const float r = (res != nullptr) ? __ldg(res + ((size_t)b * F + f0) * ldres + c0 + e)
                                                      : s[f0 * ncols + 3 * HD + c0 + e];
                     dst[e] = fmaxf(o[e] + r, 0.f);
+                }
                 }
             }
         }
@@ -89,7 +102,7 @@ autoint_attn_fwd_kernel(const float* __restrict__ qkvr, long long ldq, const flo
 
 // dqkvr: [B*F, ldq] receives dQ|dK|dV|dR (dR = masked dout; written even when the residual is X itself so that the
 // caller can add it to dX).
-template <int DH>
+template <int DH, bool VEC>
 __global__ void __launch_bounds__(AI_WARPS * 32)
 autoint_attn_bwd_kernel(const float* __restrict__ qkvr, long long ldq, const float* __restrict__ out,
                         const float* __restrict__ dout, float* __restrict__ dqkvr, long long lddq, int B, int F, int H,
@@ -116,6 +129,22 @@ autoint_attn_bwd_kernel(const float* __restrict__ qkvr, long long ldq, const flo
             const bool on = lane < F;
             const int f0 = on ? t / H : 0, c0 = on ? (t % H) * DH : 0;
             float q[DH], g[DH];
+            if constexpr (VEC) {
+#pragma unroll
+                for (int e = 0; e < DH; ++e) { q[e] = s[f0 * ncols + c0 + e]; g[e] = 0.f; }
+                if (on) {
+                    const size_t oi = ((size_t)b * F + f0) * HD + c0;
+#pragma unroll
+                    for (int e = 0; e < DH; e += 4) {
+                        const float4 ov = ldg_f4(out + oi + e), dv4 = ldg_f4(dout + oi + e);
+                        g[e] = ov.x > 0.f ? dv4.x : 0.f; g[e + 1] = ov.y > 0.f ? dv4.y : 0.f;       // ReLU backward
+                        g[e + 2] = ov.z > 0.f ? dv4.z : 0.f; g[e + 3] = ov.w > 0.f ? dv4.w : 0.f;
+                        const float4 gv = make_float4(g[e], g[e + 1], g[e + 2], g[e + 3]);
+                        stg_f4(dqkvr + ((size_t)b * F + f0) * lddq + 3 * HD + c0 + e, gv);            // residual branch grad
+                        *reinterpret_cast<float4*>(DO + lane * DH + e) = gv;
+                    }
+                }
+            } else {
 #pragma unroll
             for (int e = 0; e < DH; ++e) {
                 q[e] = s[f0 * ncols + c0 + e];
@@ -126,6 +155,7 @@ autoint_attn_bwd_kernel(const float* __restrict__ qkvr, long long ldq, const flo
                     dqkvr[((size_t)b * F + f0) * lddq + 3 * HD + c0 + e] = g[e];      // residual branch grad
                     DO[lane * DH + e] = g[e];
                 }
+            }
             }
             float sc[AI_MAXF];
             float mx = -INFINITY;
@@ -178,8 +208,14 @@ autoint_attn_bwd_kernel(const float* __restrict__ qkvr, long long ldq, const flo
                 }
             }
             if (on) {
+                if constexpr (VEC) {
+#pragma unroll
+                    for (int e = 0; e < DH; e += 4)
+                        stg_f4(dqkvr + ((size_t)b * F + f0) * lddq + c0 + e, make_float4(dq[e], dq[e + 1], dq[e + 2], dq[e + 3]));
+                } else {
 #pragma unroll
                 for (int e = 0; e < DH; ++e) dqkvr[((size_t)b * F + f0) * lddq + c0 + e] = dq[e];
+                }
             }
             __syncwarp();
             // transposed reductions: lane = key/value token r2
@@ -197,10 +233,18 @@ autoint_attn_bwd_kernel(const float* __restrict__ qkvr, long long ldq, const flo
                         dv[e] = fmaf(av, DO[r * DH + e], dv[e]);
                     }
                 }
+                if constexpr (VEC) {
+#pragma unroll
+                    for (int e = 0; e < DH; e += 4) {
+                        stg_f4(dqkvr + ((size_t)b * F + f0) * lddq + HD + c0 + e, make_float4(dk[e], dk[e + 1], dk[e + 2], dk[e + 3]));
+                        stg_f4(dqkvr + ((size_t)b * F + f0) * lddq + 2 * HD + c0 + e, make_float4(dv[e], dv[e + 1], dv[e + 2], dv[e + 3]));
+                    }
+                } else {
 #pragma unroll
                 for (int e = 0; e < DH; ++e) {
                     dqkvr[((size_t)b * F + f0) * lddq + HD + c0 + e] = dk[e];
                     dqkvr[((size_t)b * F + f0) * lddq + 2 * HD + c0 + e] = dv[e];
+                }
                 }
             }
             __syncwarp();
@@ -234,10 +278,18 @@ RPB_API int rpb_autoint_attn_fwd(const float* qkvr, int64_t ldq, const float* re
         constexpr int DH = decltype(dt)::value;
         const size_t smem = (size_t)AI_WARPS * F * ncols * sizeof(float);
         if (smem > 200 * 1024) return RPB_ERR_UNSUPPORTED;
-        cudaError_t e = cudaFuncSetAttribute(autoint_attn_fwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
         const int grid = min(ceil_div(B, AI_WARPS), 148 * 8);
-        autoint_attn_fwd_kernel<DH><<<grid, AI_WARPS * 32, smem, st>>>(qkvr, ldq, res, ldres, out, B, F, H, ncols);
+        const bool vec = g_autoint_vec && (HD % 4) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0 &&
+                         (res == nullptr || ((ldres % 4) == 0 && (reinterpret_cast<uintptr_t>(res) & 15u) == 0));
+        if (vec) {
+            cudaError_t ev = cudaFuncSetAttribute(autoint_attn_fwd_kernel<DH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (ev != cudaSuccess) return (int)ev;
+            autoint_attn_fwd_kernel<DH, true><<<grid, AI_WARPS * 32, smem, st>>>(qkvr, ldq, res, ldres, out, B, F, H, ncols);
+            return (int)cudaGetLastError();
+        }
+        cudaError_t e = cudaFuncSetAttribute(autoint_attn_fwd_kernel<DH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        autoint_attn_fwd_kernel<DH, false><<<grid, AI_WARPS * 32, smem, st>>>(qkvr, ldq, res, ldres, out, B, F, H, ncols);
         return (int)cudaGetLastError();
     });
 }
@@ -256,10 +308,19 @@ RPB_API int rpb_autoint_attn_bwd(const float* qkvr, int64_t ldq, int has_res_pro
         constexpr int DH = decltype(dt)::value;
         const size_t smem = (size_t)AI_WARPS * (F * ncols + 2 * F * (F + 1) + F * DH) * sizeof(float);
         if (smem > 200 * 1024) return RPB_ERR_UNSUPPORTED;
-        cudaError_t e = cudaFuncSetAttribute(autoint_attn_bwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
         const int grid = min(ceil_div(B, AI_WARPS), 148 * 6);
-        autoint_attn_bwd_kernel<DH><<<grid, AI_WARPS * 32, smem, st>>>(qkvr, ldq, out, dout, dqkvr, lddq, B, F, H, ncols);
+        const bool vec = g_autoint_vec && (HD % 4) == 0 && (lddq % 4) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0 &&
+                         (reinterpret_cast<uintptr_t>(dout) & 15u) == 0 && (reinterpret_cast<uintptr_t>(dqkvr) & 15u) == 0 &&
+                         ((F * DH) % 4) == 0;
+        if (vec) {
+            cudaError_t ev = cudaFuncSetAttribute(autoint_attn_bwd_kernel<DH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (ev != cudaSuccess) return (int)ev;
+            autoint_attn_bwd_kernel<DH, true><<<grid, AI_WARPS * 32, smem, st>>>(qkvr, ldq, out, dout, dqkvr, lddq, B, F, H, ncols);
+            return (int)cudaGetLastError();
+        }
+        cudaError_t e = cudaFuncSetAttribute(autoint_attn_bwd_kernel<DH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        autoint_attn_bwd_kernel<DH, false><<<grid, AI_WARPS * 32, smem, st>>>(qkvr, ldq, out, dout, dqkvr, lddq, B, F, H, ncols);
         return (int)cudaGetLastError();
     });
 }

@@ -28,6 +28,7 @@ extern int g_wgrad_stages;                           // api.cu: pipeline depth o
 extern int g_wgrad_tc;                               // api.cu: 1 = tcgen05 weight-gradient kernel in auto mode
 extern int g_fused_tc_tail;                          // api.cu: 1 = one-kernel DeepFM forward runs its 64x64 tail layers on tcgen05 (deepfm_fused.cu, TCTAIL)
 extern int g_tower_bwd_tc;                           // api.cu: 1 = tower-tail backward runs its dz chain on tcgen05 (tower_tc.cu)
+extern int g_autoint_vec;                            // api.cu: 1 = AutoInt attention kernels move a lane's outputs as float4 (autoint.cu, VEC)
 extern int g_gather_policy;                          // api.cu: 0 = L1 no-allocate, 1 = + L2::64B, 2 = __ldg
 
 // Fused scatter epilogue of the layer-1 dx GEMM: instead of writing dx[M, F*D+Nd] the epilogue adds every sample's
