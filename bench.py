@@ -529,7 +529,7 @@ def run_ours(args):
             r = cpu_reference_run(steps=60, warmup=1, B=CFG['B'], min_seconds=10.0)   # ~10 s of CPU work, <= 60 steps
             line['cpu_baseline'] = {'value': r['value'], 'unit': 'samples/s', 'cores': r['cores'], 'kind': 'port',
                                     'sample': r['sample']}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(_finite(line), allow_nan=False), flush=True)
     if dist is not None:
         # symmetric-memory + NCCL teardown can block for minutes at interpreter exit; the numbers are out, leave hard
         dist.barrier()
@@ -797,6 +797,17 @@ def run_experiments(args):
     os._exit(0)            # a trapped context must not turn teardown into a hang
 
 
+def _finite(o):
+    """Replace non-finite floats by strings: the headline line must stay strict JSON whatever an experiment produced."""
+    if isinstance(o, float):
+        return o if o == o and o not in (float('inf'), float('-inf')) else str(o)
+    if isinstance(o, dict):
+        return {str(k): _finite(v) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return [_finite(v) for v in o]
+    return o
+
+
 def experiments_in_child(steps, budget_s=120):
     """Run `bench.py --experiment all` in a child process; returns its JSON object or {'error': ...}.  Never raises."""
     import subprocess
@@ -805,7 +816,7 @@ def experiments_in_child(steps, budget_s=120):
                            capture_output=True, text=True, timeout=budget_s)
         for ln in reversed(r.stdout.strip().splitlines()):
             if ln.startswith('{'):
-                return json.loads(ln)
+                return _finite(json.loads(ln))
         return {'error': f'no result (rc {r.returncode}): ' + (r.stderr or '')[-300:]}
     except subprocess.TimeoutExpired:
         return {'error': f'timeout after {budget_s} s'}
