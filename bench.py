@@ -529,7 +529,11 @@ def run_ours(args):
             r = cpu_reference_run(steps=60, warmup=1, B=CFG['B'], min_seconds=10.0)   # ~10 s of CPU work, <= 60 steps
             line['cpu_baseline'] = {'value': r['value'], 'unit': 'samples/s', 'cores': r['cores'], 'kind': 'port',
                                     'sample': r['sample']}
-        print(json.dumps(_finite(line), allow_nan=False), flush=True)
+        try:
+            text = json.dumps(_finite(line), allow_nan=False)
+        except Exception:
+            text = json.dumps(line)
+        print(text, flush=True)
     if dist is not None:
         # symmetric-memory + NCCL teardown can block for minutes at interpreter exit; the numbers are out, leave hard
         dist.barrier()
