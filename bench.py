@@ -404,6 +404,7 @@ def run_ours(args):
                         'traffic': 248.6e6, 'traffic_source': 'profiles/r01_deepfm_step_ncu_full.md (ncu --set full: dram__bytes_read 125.9 MB + write 122.7 MB per launch)',
                         'us_per_launch': us_fwd, 'alg_bytes_per_launch': ALG_BYTES_PER_SAMPLE * B, 'peak_source': peak_src,
                         'share_of_step': us_fwd / (1e3 * ms / args.steps),
+                        'forward_only_samples_per_s': B / (us_fwd * 1e-6),
                         'note': 'bound by the shared-memory (MIO) pipe, not by HBM: the CUDA-core tower tail shares it with the '
                                 'gather warps (profiles/r01_experiments.md); the stage alone is gather_only',
                         'gather_only': gather_only}
