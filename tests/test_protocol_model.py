@@ -38,3 +38,22 @@ def test_model_detects_a_missing_drain():
                 self.pipe.append(('commit', self.tmem_full[t & 1]))
     with pytest.raises(RuntimeError, match='DEADLOCK'):
         NoDrain(3, 2, 2, random.Random(1)).run()
+
+
+def test_colsum16_butterfly_mapping():
+    """numpy restatement of colsum16 (rec_pangu_b200/csrc/tower_tc.cu): after the 4 exchange stages + one xor-16 add, lane l
+    holds the sum over the warp's 32 rows of column (l & 15) — the mapping the bias-gradient reductions rely on."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    V = rng.standard_normal((32, 16))
+    v, lanes = V.copy(), np.arange(32)
+    off = 8
+    while off > 0:
+        up = (lanes & off) != 0
+        new = v.copy()
+        for i in range(off):
+            send = np.where(up, v[:, i], v[:, i + off])
+            new[:, i] = np.where(up, v[:, i + off], v[:, i]) + send[lanes ^ off]
+        v, off = new, off // 2
+    res = v[:, 0] + v[lanes ^ 16, 0]
+    assert np.allclose(res, V.sum(axis=0)[lanes & 15])
