@@ -405,6 +405,11 @@ def run_ours(args):
                         'us_per_launch': us_fwd, 'alg_bytes_per_launch': ALG_BYTES_PER_SAMPLE * B, 'peak_source': peak_src,
                         'share_of_step': us_fwd / (1e3 * ms / args.steps),
                         'forward_only_samples_per_s': B / (us_fwd * 1e-6),
+                        # the same launch against the bytes a TRAINING forward has to move: the algorithmic reads plus what it
+                        # must leave behind for backward (feature row x, h1..h3, fm_s, logit, pred)
+                        'with_saved_activations': (lambda bps: {'bytes_per_sample': bps, 'achieved': bps * B / (us_fwd * 1e-6) / 1e9,
+                                                                'frac': bps * B / (us_fwd * 1e-6) / 1e9 / peak})(
+                            ALG_BYTES_PER_SAMPLE + 4 * ((F * D + Nd + 3) // 4 * 4) + 4 * 64 * len(CFG['hidden']) + 4 * D + 8),
                         'note': 'bound by the shared-memory (MIO) pipe, not by HBM: the CUDA-core tower tail shares it with the '
                                 'gather warps (profiles/r01_experiments.md); the stage alone is gather_only',
                         'gather_only': gather_only}
