@@ -180,3 +180,15 @@ def test_index_routing_restatement_is_self_consistent():
     assert oracle.bounds_check(rows, V + 1) and not oracle.bounds_check(np.array([V + 1]), V + 1)
     # known-answer vector for the splitmix64 finaliser (first outputs of the reference splitmix64 sequence seeded 0)
     assert int(oracle.splitmix64(np.array([0], dtype=np.uint64))[0]) == 0xE220A8397B1DCDAF
+
+
+def test_bench_optional_legs_cannot_break_the_headline_line():
+    """bench.py: whatever the child-process measurements of the opt-in variants return (here: no GPU at all, so the child
+    dies at CUDA initialisation), the parent gets a plain dict back and the line it prints stays strict JSON."""
+    import json
+    import bench
+    r = bench.experiments_in_child(5, budget_s=120)
+    assert isinstance(r, dict) and ('error' in r or 'steps' in r)
+    line = {'value': 1.0, 'experiments': bench._finite({'a': float('nan'), 'b': [float('inf'), 2.0], 'c': r})}
+    text = json.dumps(line, allow_nan=False)
+    assert json.loads(text)['experiments']['a'] == 'nan'
