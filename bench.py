@@ -597,15 +597,18 @@ def run_experiments(args):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / K
 
-    def fwd_graphs():
+    def fwd_graphs(infer=False):
+        """Graph-captured forward per batch: training (grad enabled: x, activations stored) or inference (no_grad, is_training
+        False: nothing materialised)."""
         gs, keep = [], []
         for cb in cbs:
             d = cb.as_dict()
-            keep.append(model(d))
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                keep.append(model(d))
+            with (torch.no_grad() if infer else torch.enable_grad()):
+                keep.append(model(d, is_training=not infer))
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    keep.append(model(d, is_training=not infer))
             gs.append(g)
         return gs, keep
 
@@ -616,6 +619,9 @@ def run_experiments(args):
         res['default_ms_per_step'] = time_graphs(base)
         fg, keep = fwd_graphs()
         res['default_fwd_us'] = 1e3 * time_graphs(fg)
+        del fg, keep
+        fg, keep = fwd_graphs(infer=True)
+        res['default_fwd_infer_us'] = 1e3 * time_graphs(fg)
         del fg, keep
     except Exception as ex:
         res['default_error'] = repr(ex)
@@ -719,6 +725,9 @@ def run_experiments(args):
             if 'fused_tc_tail' in opts:
                 fg, keep = fwd_graphs()
                 tc['fwd_us'] = 1e3 * time_graphs(fg)
+                del fg, keep
+                fg, keep = fwd_graphs(infer=True)
+                tc['fwd_infer_us'] = 1e3 * time_graphs(fg)
                 del fg, keep
                 if name == 'fused_tc_tail':                  # per-role cycles of CTA 0 (rpb_debug_fused_trace): what bounds it now
                     import ctypes
