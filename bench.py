@@ -559,6 +559,8 @@ def run_experiments(args):
       (each replay clears the rows ITS batch touched two replays earlier: same work per step, one step later).
     * sharded_fused_local: the fused core on row-sharded tables (RPB_SHARDED_FUSED) with all shards on this one GPU
       (dist.LocalShards): parity of logits and of every gradient against the unsharded model.
+    * l2_persist / all_on: an L2 persisting access-policy window on the feature row x (hint only), alone and with every
+      variant that passed parity.
     * autoint_vec: the AutoInt attention kernels with float4 lane I/O at the config-4 shape: bit-identity, step time.
     * l2_fetch_32B: the default step with cudaLimitMaxL2FetchGranularity = 32 (aimed at the scatter epilogue's line fetches).
     * fused_tc_tail / tower_bwd_tc / both_tc: rpb_set_option(...) — the tower-tail layers of the one-kernel forward, and the dz
@@ -746,6 +748,34 @@ def run_experiments(args):
         for k in (b'fused_tc_tail', b'tower_bwd_tc'):
             lib.rpb_set_option(k, 0)
         model.zero_grad()
+    except Exception:
+        pass
+    # ---- L2 persisting window on the feature row x (rpb_set_option('l2_persist', 1)): the forward kernel's stores of x and the
+    # re-reads by the layer-1 weight gradient and the scatter epilogue carry an access-policy window (a hint: same results),
+    # alone and then together with everything else that passed parity above
+    try:
+        _lib.check(lib.rpb_set_option(b'l2_persist', 1), 'rpb_set_option(l2_persist)')
+        model.zero_grad()
+        ps = [GraphedStep(model, cb) for cb in cbs]
+        res['l2_persist'] = {'ms_per_step': time_graphs(ps), 'loss': float(ps[0].loss.item()),
+                             'loss_default': float(base[0].loss.item()) if base is not None else None}
+        del ps
+        if res.get('both_tc', {}).get('parity_ok'):
+            for k in (b'fused_tc_tail', b'tower_bwd_tc'):
+                _lib.check(lib.rpb_set_option(k, 1), 'rpb_set_option')
+            model.zero_grad()
+            allon = [GraphedStep(model, cb, zero_first=True) for cb in cbs]
+            res['all_on'] = {'ms_per_step': time_graphs(allon), 'loss': float(allon[0].loss.item()),
+                             'what': 'fused_tc_tail + tower_bwd_tc + l2_persist + zero_first'}
+            del allon
+    except Exception as ex:
+        res.setdefault('l2_persist', {})['error'] = repr(ex)
+    try:
+        for k in (b'fused_tc_tail', b'tower_bwd_tc', b'l2_persist'):
+            lib.rpb_set_option(k, 0)
+        model.zero_grad()
+        for buf in model.embedding_layer._grad_store.buffers.values():
+            buf.zero_()
     except Exception:
         pass
     # ---- AutoInt attention kernels with float4 lane I/O (rpb_set_option('autoint_vec', 1)): BASELINE.json config 4 shape

@@ -17,6 +17,8 @@ int g_tf32_raw_hi = 1;
 int g_fused_tc_tail = 0;    // opt-in until measured on hardware
 int g_tower_bwd_tc = 0;     // opt-in until measured on hardware
 int g_autoint_vec = 0;      // opt-in until measured on hardware
+int g_l2_persist = 0;       // opt-in until measured on hardware
+size_t g_l2_aside = 0, g_l2_max_window = 0;
 
 // Grow-only per-device scratch buffers (slot = call site).  Kernels of one stream that share a slot are ordered by
 // the stream, so reuse is safe for the single-stream execution model of the reference's training loop.  Growth uses
@@ -70,6 +72,21 @@ RPB_API int rpb_set_option(const char* name, int64_t value) {
     if (n == "gemm_a_tmem") { rpb::g_gemm_a_tmem = value != 0; return 0; }
     if (n == "gemm_stack_n") { rpb::g_gemm_stack_n = value != 0; return 0; }
     if (n == "tf32_raw_hi") { rpb::g_tf32_raw_hi = value != 0; return 0; }
+    if (n == "l2_persist") {                    // enable / disable the persisting L2 set-aside of the current device (not during capture)
+        int dev = 0, aside = 0, win = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&aside, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        if (e != cudaSuccess) return (int)e;
+        if (value != 0 && (aside <= 0 || win <= 0)) return RPB_ERR_UNSUPPORTED;
+        e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, value != 0 ? (size_t)aside : 0);
+        if (e != cudaSuccess) return (int)e;
+        if (value == 0) cudaCtxResetPersistingL2Cache();
+        rpb::g_l2_aside = value != 0 ? (size_t)aside : 0;
+        rpb::g_l2_max_window = value != 0 ? (size_t)win : 0;
+        rpb::g_l2_persist = value != 0;
+        return 0;
+    }
     if (n == "autoint_vec") { rpb::g_autoint_vec = value != 0; return 0; }
     if (n == "tower_bwd_tc") { rpb::g_tower_bwd_tc = value != 0; return 0; }
     if (n == "fused_tc_tail") { rpb::g_fused_tc_tail = value != 0; return 0; }

@@ -29,6 +29,8 @@ extern int g_wgrad_tc;                               // api.cu: 1 = tcgen05 weig
 extern int g_fused_tc_tail;                          // api.cu: 1 = one-kernel DeepFM forward runs its 64x64 tail layers on tcgen05 (deepfm_fused.cu, TCTAIL)
 extern int g_tower_bwd_tc;                           // api.cu: 1 = tower-tail backward runs its dz chain on tcgen05 (tower_tc.cu)
 extern int g_autoint_vec;                            // api.cu: 1 = AutoInt attention kernels move a lane's outputs as float4 (autoint.cu, VEC)
+extern int g_l2_persist;                             // api.cu: 1 = launches that write / re-read the feature row x carry an L2 persisting access-policy window on it
+extern size_t g_l2_aside, g_l2_max_window;           // api.cu: persisting L2 set-aside / largest policy window of the device (set by rpb_set_option("l2_persist", 1))
 extern int g_gather_policy;                          // api.cu: 0 = L1 no-allocate, 1 = + L2::64B, 2 = __ldg
 
 // Fused scatter epilogue of the layer-1 dx GEMM: instead of writing dx[M, F*D+Nd] the epilogue adds every sample's
@@ -66,6 +68,32 @@ struct TcEpilogue {
 };
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// Launch with an L2 access-policy window on [wptr, wptr + wbytes): the selected fraction of those lines is kept in the
+// persisting set-aside of the L2, the rest streams.  A pure hint (opt-in g_l2_persist): the feature row x (113 MB at config 2)
+// is written by the forward kernel and read again by the layer-1 weight gradient and by the scatter epilogue, and the L2
+// holds 126 MB.  Launch attributes travel into CUDA-graph kernel nodes, unlike a stream attribute set during capture.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_windowed(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                          const void* wptr, size_t wbytes, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    int na = 0;
+    if (wptr != nullptr && wbytes > 0 && rpb::g_l2_aside > 0 && rpb::g_l2_max_window > 0) {
+        const size_t win = wbytes < rpb::g_l2_max_window ? wbytes : rpb::g_l2_max_window;
+        const float ratio = (float)rpb::g_l2_aside / (float)win;
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = const_cast<void*>(wptr);
+        attr[0].val.accessPolicyWindow.num_bytes = win;
+        attr[0].val.accessPolicyWindow.hitRatio = ratio < 1.f ? ratio : 1.f;
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        na = 1;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 __device__ __forceinline__ float4 ldg_f4(const float* p) {
     return __ldg(reinterpret_cast<const float4*>(p));

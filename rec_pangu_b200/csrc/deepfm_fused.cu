@@ -627,6 +627,9 @@ RPB_API int rpb_deepfm_fwd_fused(const RpbGatherDesc* g, const float* W1, const 
         const size_t smem = fg_smem_bytes(LA, d->n_tail, TC);
         cudaError_t e = cudaFuncSetAttribute(deepfm_fwd_fused_kernel<LA, SH, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
+        if (g_l2_persist && p.x != nullptr)        // opt-in: keep the feature row in the L2 set-aside for the backward kernels
+            return (int)launch_windowed(deepfm_fwd_fused_kernel<LA, SH, TC>, dim3(grid), dim3(FG_THREADS), smem, st, p.x,
+                                        (size_t)p.M * (size_t)p.ldx * sizeof(float), tmBhi, tmBlo, tmThi, tmTlo, p, tw, m_tiles);
         deepfm_fwd_fused_kernel<LA, SH, TC><<<grid, FG_THREADS, smem, st>>>(tmBhi, tmBlo, tmThi, tmTlo, p, tw, m_tiles);
         return (int)cudaGetLastError();
     };

@@ -983,6 +983,10 @@ int gemm_tc(const float* A, long long lda, const float* Bsrc, long long ldb, int
                 }
                 cudaError_t ee = cudaFuncSetAttribute(gemm_tf32x3_v2_kernel<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (ee != cudaSuccess) return (int)ee;
+                if (g_l2_persist && ep.sc != nullptr && ep.sc->x != nullptr)      // opt-in: the FM term re-reads x from the L2 set-aside
+                    return (int)launch_windowed(gemm_tf32x3_v2_kernel<R, false>, dim3(grid), dim3(V2_THREADS), smem, st, ep.sc->x,
+                                                (size_t)M * (size_t)ep.sc->ldx * sizeof(float), tmA, tmBhi, tmBlo, ep, block_n, nkb,
+                                                m_tiles, n_tiles, tmem_cols, b_resident, a_stages, stack_n, *ep.sc, no_tail);
                 gemm_tf32x3_v2_kernel<R, false><<<grid, V2_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, ep, block_n, nkb, m_tiles, n_tiles,
                                                                                tmem_cols, b_resident, a_stages, stack_n,
                                                                                ep.sc != nullptr ? *ep.sc : no_scatter,
@@ -1103,6 +1107,10 @@ int wgrad_tc(const float* dy, long long lddy, const float* x, long long ldx, flo
         const size_t smem = (size_t)S * stage_bytes + (3 * S + 2) * 8 + 1024;
         cudaError_t ee = cudaFuncSetAttribute(wgrad_tf32x3_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (ee != cudaSuccess) return (int)ee;
+        if (g_l2_persist)                          // opt-in: x (the wide operand) is re-read by the scatter epilogue that follows
+            return (int)launch_windowed(wgrad_tf32x3_kernel<S>, dim3(ktiles, slabs), dim3(TC_THREADS), smem, st, x,
+                                        (size_t)M * (size_t)ldx * sizeof(float), tmX, tmDy, dW, N, K, M, block_n, slab, tmem_cols,
+                                        stack_n, g_tf32_raw_hi);
         wgrad_tf32x3_kernel<S><<<dim3(ktiles, slabs), TC_THREADS, smem, st>>>(tmX, tmDy, dW, N, K, M, block_n, slab, tmem_cols, stack_n, g_tf32_raw_hi);
         return (int)cudaGetLastError();
     };
