@@ -615,6 +615,10 @@ def run_experiments(args):
         return gs, keep
 
     res = {'steps': K}
+
+    def emit():                      # one line per finished leg: if the parent's timeout strikes, the last line is what it keeps
+        print(json.dumps(res), flush=True)
+
     base = None
     try:
         base = [GraphedStep(model, cb) for cb in cbs]
@@ -627,6 +631,7 @@ def run_experiments(args):
         del fg, keep
     except Exception as ex:
         res['default_error'] = repr(ex)
+    emit()
     try:
         zs = [GraphedStep(model, cb, zero_first=True) for cb in cbs]
         res['zero_first'] = {'ms_per_step': time_graphs(zs), 'launches_per_step': zs[0].launches_per_step}
@@ -641,6 +646,7 @@ def run_experiments(args):
         torch.cuda.synchronize()
     except Exception as ex:
         res['reset_error'] = repr(ex)
+    emit()
     # ---- fused core on row-sharded tables, checked on ONE GPU: dist.LocalShards keeps all G shards of every table on this
     # device, so the sharded variants of the one-kernel forward and of the dx-GEMM scatter epilogue see the same pointer
     # tables as over NVLink; a smaller vocabulary keeps the second copy of the tables cheap
@@ -687,6 +693,7 @@ def run_experiments(args):
         torch.cuda.empty_cache()
     except Exception as ex:
         res.setdefault('sharded_fused_local', {})['error'] = repr(ex)
+    emit()
     # ---- tcgen05 variants: parity first (eager, same batch, against the default kernels), then timings.  A protocol bug
     # traps the context (every mbarrier wait is bounded), which ends this process's measurements but nothing else.
     lib = _lib.load()
@@ -744,12 +751,14 @@ def run_experiments(args):
             del ts
         except Exception as ex:
             res.setdefault(name, {})['error'] = repr(ex)
+        emit()
     try:
         for k in (b'fused_tc_tail', b'tower_bwd_tc'):
             lib.rpb_set_option(k, 0)
         model.zero_grad()
     except Exception:
         pass
+    emit()
     # ---- L2 persisting window on the feature row x (rpb_set_option('l2_persist', 1)): the forward kernel's stores of x and the
     # re-reads by the layer-1 weight gradient and the scatter epilogue carry an access-policy window (a hint: same results),
     # alone and then together with everything else that passed parity above
@@ -778,6 +787,7 @@ def run_experiments(args):
             buf.zero_()
     except Exception:
         pass
+    emit()
     # ---- AutoInt attention kernels with float4 lane I/O (rpb_set_option('autoint_vec', 1)): BASELINE.json config 4 shape
     # (B = 32768, 26 fields, D = 32, 3 heads x 8) on a 100k-row vocabulary (the attention kernels do not see the vocabulary).
     # Same arithmetic in the same order, so everything must be bit-identical; eval() keeps dropout out of the comparison.
@@ -831,6 +841,7 @@ def run_experiments(args):
         torch.cuda.empty_cache()
     except Exception as ex:
         res.setdefault('autoint_vec', {})['error'] = repr(ex)
+    emit()
     # ---- L2 fetch granularity 32 B (cudaLimitMaxL2FetchGranularity, device-wide hint): the scatter epilogue's `red`s fetch
     # whole 128-byte lines (340 MB read for 109 MB of reductions, profiles/r01_deepfm_step_ncu_full.md); replays of the
     # graphs captured above, so only the limit differs (runs after the tail leg; if that one trapped, this reports the error)
@@ -867,7 +878,16 @@ def experiments_in_child(steps, budget_s=120):
             if ln.startswith('{'):
                 return _finite(json.loads(ln))
         return {'error': f'no result (rc {r.returncode}): ' + (r.stderr or '')[-300:]}
-    except subprocess.TimeoutExpired:
+    except subprocess.TimeoutExpired as ex:            # keep what the child had finished (it prints one line per leg)
+        out = ex.stdout.decode(errors='replace') if isinstance(ex.stdout, bytes) else (ex.stdout or '')
+        for ln in reversed(out.strip().splitlines()):
+            if ln.startswith('{') and ln.endswith('}'):
+                try:
+                    r = _finite(json.loads(ln))
+                    r['timeout'] = f'child killed after {budget_s} s; legs finished until then are kept'
+                    return r
+                except Exception:
+                    continue
         return {'error': f'timeout after {budget_s} s'}
     except Exception as ex:
         return {'error': repr(ex)}
