@@ -314,6 +314,55 @@ def run_ours(args):
     e2e = {'value': world * B * args.steps / (ms_e2e * 1e-3), 'unit': 'samples/s', 'h2d_bytes_per_step': h2d,
            'd2h_bytes_per_step': 4, 'loss': lossv, 'overlap': 'H2D of batch i+1 on a copy stream during step i; loss of step i read by the host during step i+1'}
 
+    line = {
+        'metric': 'DeepFM samples/sec (forward+backward hot path)', 'value': value, 'unit': 'samples/s',
+        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'DeepFM criteo-shape: 26 sparse x 1M-row tables (D=16) + 13 dense, MLP 64-64-64, '
+                               'fwd + bwd (dense per-table grads, sparse re-zero), BASELINE.json configs[1]',
+                   'batch_per_gpu': B, 'global_batch': B * world, 'parallelism': (f'dp{world}: batch-parallel ranks, tables row-sharded in NVLink peer memory (fused P2P gather/scatter), '
+                                   f'dense grads NCCL all-reduce') if world > 1 else 'single',
+                   'launch': launch_mode, 'l2': 'inputs larger than L2: 4 rotating batches over 1.66 GB of tables',
+                   'gemm': {0: 'auto(tcgen05 3xTF32)', 1: 'simt fp32', 2: 'tcgen05 3xTF32'}[ops.get_gemm_impl()],
+                   'grad_mode': 'persistent' if world == 1 else 'sharded',
+                   'sharded_fused_core': bool(ops.SHARDED_FUSED) if world > 1 else None},
+        'e2e': e2e, 'gpu_launches': launches_per_step * args.steps, 'clocks': clocks, 'roofline': None,
+        'train_step': None, 'zipf_ids': None, 'torch_eager_gpu_baseline': None,
+    }
+
+    # Everything below is secondary.  The line exists from here on and is filled in leg by leg; a watchdog prints it as it
+    # stands if the secondary legs ever fail to come back (a hang there must not cost the headline numbers above).
+    _lock, _state = threading.Lock(), {'done': False}
+
+    def emit_line(note=None):
+        with _lock:
+            if _state['done']:
+                return
+            _state['done'] = True
+            if note is not None:
+                line['watchdog'] = note
+            text = None
+            for _ in range(5):
+                try:
+                    try:
+                        text = json.dumps(_finite(line), allow_nan=False)
+                    except (ValueError, TypeError):
+                        text = json.dumps(line)
+                    break
+                except RuntimeError:             # dict touched by the main thread while serialising
+                    time.sleep(0.05)
+            print(text if text is not None else json.dumps({k: line[k] for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step')}), flush=True)
+
+    watchdog = None
+    if world == 1 and rank == 0:
+        def _fire():
+            emit_line('secondary legs did not return within 420 s of the headline measurement; line printed by the watchdog')
+            sys.stdout.flush()
+            os._exit(0)
+        watchdog = threading.Timer(420.0, _fire)
+        watchdog.daemon = True
+        watchdog.start()
+
     roofline = None
     if world == 1:
         # ---------------- roofline of the dominant memory kernel: the fused gather+FM forward (rpb_gather_fwd)
@@ -422,6 +471,8 @@ def run_ours(args):
                 pass
 
 
+    line['roofline'] = roofline
+
     # ---------------- same step + optimizer: FusedAdam between backward and zero_grad — dense
     # parameters in one multi-tensor launch, table rows row-sparsely with the gradient re-zero fused in (rpb_sparse_adam),
     # step counter on the device so the captured graph keeps its bias correction.  Reported beside the headline.
@@ -446,6 +497,8 @@ def run_ours(args):
             del tsteps, opt
         except Exception as ex:          # a secondary leg must never cost the headline line
             train_step = {'error': repr(ex)}
+
+    line['train_step'] = train_step
 
     # ---------------- secondary legs (N = 1 only): Zipf(1.05)-distributed ids and stock PyTorch eager on the
     # same GPU (the oracle's functional restatement of the reference forward run on CUDA tensors = the "existing Blackwell
@@ -501,21 +554,7 @@ def run_ours(args):
             else:
                 eager_gpu = {'error': repr(ex)}
 
-    line = {
-        'metric': 'DeepFM samples/sec (forward+backward hot path)', 'value': value, 'unit': 'samples/s',
-        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'DeepFM criteo-shape: 26 sparse x 1M-row tables (D=16) + 13 dense, MLP 64-64-64, '
-                               'fwd + bwd (dense per-table grads, sparse re-zero), BASELINE.json configs[1]',
-                   'batch_per_gpu': B, 'global_batch': B * world, 'parallelism': (f'dp{world}: batch-parallel ranks, tables row-sharded in NVLink peer memory (fused P2P gather/scatter), '
-                                   f'dense grads NCCL all-reduce') if world > 1 else 'single',
-                   'launch': launch_mode, 'l2': 'inputs larger than L2: 4 rotating batches over 1.66 GB of tables',
-                   'gemm': {0: 'auto(tcgen05 3xTF32)', 1: 'simt fp32', 2: 'tcgen05 3xTF32'}[ops.get_gemm_impl()],
-                   'grad_mode': 'persistent' if world == 1 else 'sharded',
-                   'sharded_fused_core': bool(ops.SHARDED_FUSED) if world > 1 else None},
-        'e2e': e2e, 'gpu_launches': launches_per_step * args.steps, 'clocks': clocks, 'roofline': roofline,
-        'train_step': train_step, 'zipf_ids': zipf, 'torch_eager_gpu_baseline': eager_gpu,
-    }
+    line['zipf_ids'], line['torch_eager_gpu_baseline'] = zipf, eager_gpu
     if rank == 0:
         # opt-in variants not yet measured on hardware: in a child process with a hard timeout, only when this run has been
         # quick so far (a slow box must not be pushed past "minutes"), after every measurement of this process is final
@@ -532,14 +571,15 @@ def run_ours(args):
                 torch.cuda.empty_cache()
             except Exception:
                 pass
-            r = cpu_reference_run(steps=60, warmup=1, B=CFG['B'], min_seconds=10.0)   # ~10 s of CPU work, <= 60 steps
-            line['cpu_baseline'] = {'value': r['value'], 'unit': 'samples/s', 'cores': r['cores'], 'kind': 'port',
-                                    'sample': r['sample']}
-        try:
-            text = json.dumps(_finite(line), allow_nan=False)
-        except Exception:
-            text = json.dumps(line)
-        print(text, flush=True)
+            try:
+                r = cpu_reference_run(steps=60, warmup=1, B=CFG['B'], min_seconds=10.0)   # ~10 s of CPU work, <= 60 steps
+                line['cpu_baseline'] = {'value': r['value'], 'unit': 'samples/s', 'cores': r['cores'], 'kind': 'port',
+                                        'sample': r['sample']}
+            except Exception as ex:
+                line['cpu_baseline'] = {'error': repr(ex), 'kind': 'port'}
+        if watchdog is not None:
+            watchdog.cancel()
+        emit_line()
     if dist is not None:
         # symmetric-memory + NCCL teardown can block for minutes at interpreter exit; the numbers are out, leave hard
         dist.barrier()
