@@ -597,6 +597,7 @@ def run_experiments(args):
 
     * zero_first: GraphedStep(zero_first=True) — the sparse re-zero of the table gradients overlapped with the next forward
       (each replay clears the rows ITS batch touched two replays earlier: same work per step, one step later).
+    * afm_golden: the AFM class against the fixture of the real reference AFM (default kernels).
     * sharded_fused_local: the fused core on row-sharded tables (RPB_SHARDED_FUSED) with all shards on this one GPU
       (dist.LocalShards): parity of logits and of every gradient against the unsharded model.
     * l2_persist / all_on: an L2 persisting access-policy window on the feature row x (hint only), alone and with every
@@ -686,6 +687,31 @@ def run_experiments(args):
         torch.cuda.synchronize()
     except Exception as ex:
         res['reset_error'] = repr(ex)
+    emit()
+    # ---- AFM (the FiBiNet class under the reference's other name, added after the last GPU call): the fixture produced by
+    # the real reference AFM, through the default kernels
+    try:
+        sys.path.insert(0, os.path.join(ROOT, 'tests'))
+        from helpers import load_golden
+        from rec_pangu_b200.models import ranking
+        g_ = load_golden('afm')
+        m_ = g_['meta']
+        afm = getattr(ranking, m_['model'])(embedding_dim=m_['D'], enc_dict=m_['enc_dict'], **m_['kwargs'])
+        afm.load_state_dict(g_['sd'])
+        afm = afm.to(dev).eval()
+        o_ = afm({k: v.to(dev) for k, v in g_['data'].items()})
+        o_['loss'].backward()
+        torch.cuda.synchronize()
+        gr_ = dict(afm.named_parameters())
+        res['afm_golden'] = {
+            'max_abs_dpred': float((o_['pred'].cpu() - g_['out']['pred']).abs().max()),
+            'dloss': abs(float(o_['loss'].item()) - float(g_['out']['loss'])),
+            'max_rel_dgrad': max(float((gr_[k].grad.cpu() - v).abs().max() / v.abs().max().clamp_min(1e-12)) for k, v in g_['grad'].items())}
+        res['afm_golden']['parity_ok'] = bool(res['afm_golden']['max_abs_dpred'] <= 1e-5 and res['afm_golden']['dloss'] <= 1e-5 and
+                                              res['afm_golden']['max_rel_dgrad'] <= 1e-4)
+        del afm, o_, gr_
+    except Exception as ex:
+        res.setdefault('afm_golden', {})['error'] = repr(ex)
     emit()
     # ---- fused core on row-sharded tables, checked on ONE GPU: dist.LocalShards keeps all G shards of every table on this
     # device, so the sharded variants of the one-kernel forward and of the dx-GEMM scatter epilogue see the same pointer
