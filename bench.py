@@ -561,7 +561,7 @@ def run_ours(args):
         t_parent = time.time() - T_START
         if world == 1 and not args.no_experiments and not args.no_extras:
             if t_parent < 180:
-                line['experiments'] = experiments_in_child(args.steps)
+                line['experiments'] = experiments_in_children(args.steps, deadline=T_START + 400)
                 line['experiments']['wall_s'] = round(time.time() - T_START - t_parent, 1)
             else:
                 line['experiments'] = {'skipped': f'this run had already taken {t_parent:.0f} s'}
@@ -591,9 +591,12 @@ def run_ours(args):
 
 # ----------------------------------------------------------------------------------------------- experiments (child process)
 def run_experiments(args):
-    """`bench.py --experiment all` — run by the default bench in a CHILD process (own CUDA context, hard timeout) after all
-    of its own measurements are done, so that nothing here can touch the headline numbers.  Measures two opt-in variants
-    that were written after the last GPU call of round 1 and have not run on hardware yet; prints one JSON object.
+    """`bench.py --experiment safe|tc_fwd|tc_bwd|all` — run by the default bench in CHILD processes (own CUDA context, hard
+    timeout) after all of its own measurements are done, so that nothing here can touch the headline numbers.  Measures the
+    opt-in variants that were written after the last GPU call of round 1 and have not run on hardware yet; prints one JSON
+    object per finished leg (the last line is the result).  Groups: `safe` = everything that cannot trap (default-kernel
+    checks, hints, address arithmetic), `tc_fwd` / `tc_bwd` = one new tcgen05 kernel each, in separate processes because a
+    protocol bug there traps the CUDA context (`tc_bwd` also runs both together and `all_on` when told that `tc_fwd` passed).
 
     * zero_first: GraphedStep(zero_first=True) — the sparse re-zero of the table gradients overlapped with the next forward
       (each replay clears the rows ITS batch touched two replays earlier: same work per step, one step later).
@@ -655,7 +658,8 @@ def run_experiments(args):
             gs.append(g)
         return gs, keep
 
-    res = {'steps': K}
+    which = args.experiment if args.experiment in ('safe', 'tc_fwd', 'tc_bwd') else 'all'
+    res = {'steps': K, 'group': which}
 
     def emit():                      # one line per finished leg: if the parent's timeout strikes, the last line is what it keeps
         print(json.dumps(res), flush=True)
@@ -673,92 +677,95 @@ def run_experiments(args):
     except Exception as ex:
         res['default_error'] = repr(ex)
     emit()
-    try:
-        zs = [GraphedStep(model, cb, zero_first=True) for cb in cbs]
-        res['zero_first'] = {'ms_per_step': time_graphs(zs), 'launches_per_step': zs[0].launches_per_step}
-        del zs
-    except Exception as ex:
-        res['zero_first'] = {'error': repr(ex)}
-    try:
-        # the rotated graphs leave the rows of the batch before last populated: start the parity leg from all-zero buffers
-        model.zero_grad()
-        for buf in model.embedding_layer._grad_store.buffers.values():
-            buf.zero_()
-        torch.cuda.synchronize()
-    except Exception as ex:
-        res['reset_error'] = repr(ex)
-    emit()
-    # ---- AFM (the FiBiNet class under the reference's other name, added after the last GPU call): the fixture produced by
-    # the real reference AFM, through the default kernels
-    try:
-        sys.path.insert(0, os.path.join(ROOT, 'tests'))
-        from helpers import load_golden
-        from rec_pangu_b200.models import ranking
-        g_ = load_golden('afm')
-        m_ = g_['meta']
-        afm = getattr(ranking, m_['model'])(embedding_dim=m_['D'], enc_dict=m_['enc_dict'], **m_['kwargs'])
-        afm.load_state_dict(g_['sd'])
-        afm = afm.to(dev).eval()
-        o_ = afm({k: v.to(dev) for k, v in g_['data'].items()})
-        o_['loss'].backward()
-        torch.cuda.synchronize()
-        gr_ = dict(afm.named_parameters())
-        res['afm_golden'] = {
-            'max_abs_dpred': float((o_['pred'].cpu() - g_['out']['pred']).abs().max()),
-            'dloss': abs(float(o_['loss'].item()) - float(g_['out']['loss'])),
-            'max_rel_dgrad': max(float((gr_[k].grad.cpu() - v).abs().max() / v.abs().max().clamp_min(1e-12)) for k, v in g_['grad'].items())}
-        res['afm_golden']['parity_ok'] = bool(res['afm_golden']['max_abs_dpred'] <= 1e-5 and res['afm_golden']['dloss'] <= 1e-5 and
-                                              res['afm_golden']['max_rel_dgrad'] <= 1e-4)
-        del afm, o_, gr_
-    except Exception as ex:
-        res.setdefault('afm_golden', {})['error'] = repr(ex)
-    emit()
-    # ---- fused core on row-sharded tables, checked on ONE GPU: dist.LocalShards keeps all G shards of every table on this
-    # device, so the sharded variants of the one-kernel forward and of the dx-GEMM scatter epilogue see the same pointer
-    # tables as over NVLink; a smaller vocabulary keeps the second copy of the tables cheap
-    try:
-        from rec_pangu_b200 import dist as rdist
-        G_loc, V_loc, B_loc = 4, 50_000, 8192
-        enc_s = {f'I{i + 1}': {'min': 0.0, 'max': 1.0} for i in range(CFG['Nd'])}
-        enc_s.update({f'C{i + 1}': {'vocab_size': V_loc} for i in range(CFG['F'])})
-        torch.manual_seed(3)
-        with torch.device(dev):
-            ref_m = DeepFM(embedding_dim=D, hidden_units=CFG['hidden'], enc_dict=enc_s)
-            sh_m = DeepFM(embedding_dim=D, hidden_units=CFG['hidden'], enc_dict=enc_s)
-        sh_m.load_state_dict({k: v.clone() for k, v in ref_m.state_dict().items()})
-        ref_m.train()
-        sh_m.train()
-        ls = rdist.LocalShards(sh_m.embedding_layer, G_loc)
-        sh_m.embedding_layer.attach_shards(ls)
-        bt = synth_batch(enc_s, B_loc, gen, device=dev)
-        out_r = ref_m(bt)
-        out_r['loss'].backward()
-        ops.SHARDED_FUSED = 1
+    if which in ('safe', 'all'):
         try:
-            n0 = ops.launch_count()
-            out_s = sh_m(bt)
-            n_fwd = ops.launch_count() - n0
-            out_s['loss'].backward()
-        finally:
-            ops.SHARDED_FUSED = 0
-        torch.cuda.synchronize()
-        ops.check_index_errors(dev)
-        tg = 0.0
-        for f, t in enumerate(ref_m.embedding_layer.tables()):
-            tg = max(tg, float((ls.full_grad(f) - t.grad).abs().max() / t.grad.abs().max().clamp_min(1e-12)))
-        dense_r = {n: p.grad for n, p in ref_m.named_parameters() if not n.startswith('embedding_layer.')}
-        dg = max(float((p.grad - dense_r[n]).abs().max() / dense_r[n].abs().max().clamp_min(1e-12))
-                 for n, p in sh_m.named_parameters() if not n.startswith('embedding_layer.'))
-        sl = {'shards': G_loc, 'forward_launches': n_fwd,
-              'max_abs_dlogit': float((sh_m._last_logit - ref_m._last_logit).abs().max()),
-              'dloss': abs(float(out_s['loss'].item()) - float(out_r['loss'].item())),
-              'max_rel_dgrad_tables': tg, 'max_rel_dgrad_dense': dg}
-        sl['parity_ok'] = bool(n_fwd == 2 and sl['max_abs_dlogit'] <= 1e-6 and sl['dloss'] <= 1e-6 and tg <= 1e-4 and dg <= 1e-4)
-        res['sharded_fused_local'] = sl
-        del ref_m, sh_m, ls, out_r, out_s
-        torch.cuda.empty_cache()
-    except Exception as ex:
-        res.setdefault('sharded_fused_local', {})['error'] = repr(ex)
+            zs = [GraphedStep(model, cb, zero_first=True) for cb in cbs]
+            res['zero_first'] = {'ms_per_step': time_graphs(zs), 'launches_per_step': zs[0].launches_per_step}
+            del zs
+        except Exception as ex:
+            res['zero_first'] = {'error': repr(ex)}
+        try:
+            # the rotated graphs leave the rows of the batch before last populated: start the parity leg from all-zero buffers
+            model.zero_grad()
+            for buf in model.embedding_layer._grad_store.buffers.values():
+                buf.zero_()
+            torch.cuda.synchronize()
+        except Exception as ex:
+            res['reset_error'] = repr(ex)
+    emit()
+    if which in ('safe', 'all'):
+        # ---- AFM (the FiBiNet class under the reference's other name, added after the last GPU call): the fixture produced by
+        # the real reference AFM, through the default kernels
+        try:
+            sys.path.insert(0, os.path.join(ROOT, 'tests'))
+            from helpers import load_golden
+            from rec_pangu_b200.models import ranking
+            g_ = load_golden('afm')
+            m_ = g_['meta']
+            afm = getattr(ranking, m_['model'])(embedding_dim=m_['D'], enc_dict=m_['enc_dict'], **m_['kwargs'])
+            afm.load_state_dict(g_['sd'])
+            afm = afm.to(dev).eval()
+            o_ = afm({k: v.to(dev) for k, v in g_['data'].items()})
+            o_['loss'].backward()
+            torch.cuda.synchronize()
+            gr_ = dict(afm.named_parameters())
+            res['afm_golden'] = {
+                'max_abs_dpred': float((o_['pred'].cpu() - g_['out']['pred']).abs().max()),
+                'dloss': abs(float(o_['loss'].item()) - float(g_['out']['loss'])),
+                'max_rel_dgrad': max(float((gr_[k].grad.cpu() - v).abs().max() / v.abs().max().clamp_min(1e-12)) for k, v in g_['grad'].items())}
+            res['afm_golden']['parity_ok'] = bool(res['afm_golden']['max_abs_dpred'] <= 1e-5 and res['afm_golden']['dloss'] <= 1e-5 and
+                                                  res['afm_golden']['max_rel_dgrad'] <= 1e-4)
+            del afm, o_, gr_
+        except Exception as ex:
+            res.setdefault('afm_golden', {})['error'] = repr(ex)
+    emit()
+    if which in ('safe', 'all'):
+        # ---- fused core on row-sharded tables, checked on ONE GPU: dist.LocalShards keeps all G shards of every table on this
+        # device, so the sharded variants of the one-kernel forward and of the dx-GEMM scatter epilogue see the same pointer
+        # tables as over NVLink; a smaller vocabulary keeps the second copy of the tables cheap
+        try:
+            from rec_pangu_b200 import dist as rdist
+            G_loc, V_loc, B_loc = 4, 50_000, 8192
+            enc_s = {f'I{i + 1}': {'min': 0.0, 'max': 1.0} for i in range(CFG['Nd'])}
+            enc_s.update({f'C{i + 1}': {'vocab_size': V_loc} for i in range(CFG['F'])})
+            torch.manual_seed(3)
+            with torch.device(dev):
+                ref_m = DeepFM(embedding_dim=D, hidden_units=CFG['hidden'], enc_dict=enc_s)
+                sh_m = DeepFM(embedding_dim=D, hidden_units=CFG['hidden'], enc_dict=enc_s)
+            sh_m.load_state_dict({k: v.clone() for k, v in ref_m.state_dict().items()})
+            ref_m.train()
+            sh_m.train()
+            ls = rdist.LocalShards(sh_m.embedding_layer, G_loc)
+            sh_m.embedding_layer.attach_shards(ls)
+            bt = synth_batch(enc_s, B_loc, gen, device=dev)
+            out_r = ref_m(bt)
+            out_r['loss'].backward()
+            ops.SHARDED_FUSED = 1
+            try:
+                n0 = ops.launch_count()
+                out_s = sh_m(bt)
+                n_fwd = ops.launch_count() - n0
+                out_s['loss'].backward()
+            finally:
+                ops.SHARDED_FUSED = 0
+            torch.cuda.synchronize()
+            ops.check_index_errors(dev)
+            tg = 0.0
+            for f, t in enumerate(ref_m.embedding_layer.tables()):
+                tg = max(tg, float((ls.full_grad(f) - t.grad).abs().max() / t.grad.abs().max().clamp_min(1e-12)))
+            dense_r = {n: p.grad for n, p in ref_m.named_parameters() if not n.startswith('embedding_layer.')}
+            dg = max(float((p.grad - dense_r[n]).abs().max() / dense_r[n].abs().max().clamp_min(1e-12))
+                     for n, p in sh_m.named_parameters() if not n.startswith('embedding_layer.'))
+            sl = {'shards': G_loc, 'forward_launches': n_fwd,
+                  'max_abs_dlogit': float((sh_m._last_logit - ref_m._last_logit).abs().max()),
+                  'dloss': abs(float(out_s['loss'].item()) - float(out_r['loss'].item())),
+                  'max_rel_dgrad_tables': tg, 'max_rel_dgrad_dense': dg}
+            sl['parity_ok'] = bool(n_fwd == 2 and sl['max_abs_dlogit'] <= 1e-6 and sl['dloss'] <= 1e-6 and tg <= 1e-4 and dg <= 1e-4)
+            res['sharded_fused_local'] = sl
+            del ref_m, sh_m, ls, out_r, out_s
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            res.setdefault('sharded_fused_local', {})['error'] = repr(ex)
     emit()
     # ---- tcgen05 variants: parity first (eager, same batch, against the default kernels), then timings.  A protocol bug
     # traps the context (every mbarrier wait is bounded), which ends this process's measurements but nothing else.
@@ -778,8 +785,14 @@ def run_experiments(args):
         return model._last_logit.clone(), float(out['loss'].item()), gw, gt
 
     ref = None
-    for name, opts in (('tower_bwd_tc', ('tower_bwd_tc',)), ('fused_tc_tail', ('fused_tc_tail',)),
-                       ('both_tc', ('fused_tc_tail', 'tower_bwd_tc'))):
+    variants = []
+    if which in ('tc_fwd', 'all'):
+        variants.append(('fused_tc_tail', ('fused_tc_tail',)))
+    if which in ('tc_bwd', 'all'):
+        variants.append(('tower_bwd_tc', ('tower_bwd_tc',)))
+    if which == 'all' or (which == 'tc_bwd' and args.tc_fwd_ok):      # together only where the forward variant has passed parity
+        variants.append(('both_tc', ('fused_tc_tail', 'tower_bwd_tc')))
+    for name, opts in variants:
         try:
             if ref is None:
                 ref = eager_step(())
@@ -825,99 +838,102 @@ def run_experiments(args):
     except Exception:
         pass
     emit()
-    # ---- L2 persisting window on the feature row x (rpb_set_option('l2_persist', 1)): the forward kernel's stores of x and the
-    # re-reads by the layer-1 weight gradient and the scatter epilogue carry an access-policy window (a hint: same results),
-    # alone and then together with everything else that passed parity above
-    try:
-        _lib.check(lib.rpb_set_option(b'l2_persist', 1), 'rpb_set_option(l2_persist)')
-        model.zero_grad()
-        ps = [GraphedStep(model, cb) for cb in cbs]
-        res['l2_persist'] = {'ms_per_step': time_graphs(ps), 'loss': float(ps[0].loss.item()),
-                             'loss_default': float(base[0].loss.item()) if base is not None else None}
-        del ps
-        if res.get('both_tc', {}).get('parity_ok'):
-            for k in (b'fused_tc_tail', b'tower_bwd_tc'):
-                _lib.check(lib.rpb_set_option(k, 1), 'rpb_set_option')
+    if which in ('safe', 'all') or res.get('both_tc', {}).get('parity_ok'):
+        # ---- L2 persisting window on the feature row x (rpb_set_option('l2_persist', 1)): the forward kernel's stores of x and the
+        # re-reads by the layer-1 weight gradient and the scatter epilogue carry an access-policy window (a hint: same results),
+        # alone and then together with everything else that passed parity above
+        try:
+            _lib.check(lib.rpb_set_option(b'l2_persist', 1), 'rpb_set_option(l2_persist)')
             model.zero_grad()
-            allon = [GraphedStep(model, cb, zero_first=True) for cb in cbs]
-            res['all_on'] = {'ms_per_step': time_graphs(allon), 'loss': float(allon[0].loss.item()),
-                             'what': 'fused_tc_tail + tower_bwd_tc + l2_persist + zero_first'}
-            del allon
-    except Exception as ex:
-        res.setdefault('l2_persist', {})['error'] = repr(ex)
-    try:
-        for k in (b'fused_tc_tail', b'tower_bwd_tc', b'l2_persist'):
-            lib.rpb_set_option(k, 0)
-        model.zero_grad()
-        for buf in model.embedding_layer._grad_store.buffers.values():
-            buf.zero_()
-    except Exception:
-        pass
+            ps = [GraphedStep(model, cb) for cb in cbs]
+            res['l2_persist'] = {'ms_per_step': time_graphs(ps), 'loss': float(ps[0].loss.item()),
+                                 'loss_default': float(base[0].loss.item()) if base is not None else None}
+            del ps
+            if res.get('both_tc', {}).get('parity_ok') and res.get('tower_bwd_tc', {}).get('parity_ok'):
+                for k in (b'fused_tc_tail', b'tower_bwd_tc'):
+                    _lib.check(lib.rpb_set_option(k, 1), 'rpb_set_option')
+                model.zero_grad()
+                allon = [GraphedStep(model, cb, zero_first=True) for cb in cbs]
+                res['all_on'] = {'ms_per_step': time_graphs(allon), 'loss': float(allon[0].loss.item()),
+                                 'what': 'fused_tc_tail + tower_bwd_tc + l2_persist + zero_first'}
+                del allon
+        except Exception as ex:
+            res.setdefault('l2_persist', {})['error'] = repr(ex)
+        try:
+            for k in (b'fused_tc_tail', b'tower_bwd_tc', b'l2_persist'):
+                lib.rpb_set_option(k, 0)
+            model.zero_grad()
+            for buf in model.embedding_layer._grad_store.buffers.values():
+                buf.zero_()
+        except Exception:
+            pass
     emit()
-    # ---- AutoInt attention kernels with float4 lane I/O (rpb_set_option('autoint_vec', 1)): BASELINE.json config 4 shape
-    # (B = 32768, 26 fields, D = 32, 3 heads x 8) on a 100k-row vocabulary (the attention kernels do not see the vocabulary).
-    # Same arithmetic in the same order, so everything must be bit-identical; eval() keeps dropout out of the comparison.
-    try:
-        from rec_pangu_b200.models.ranking import AutoInt
-        enc_a = {f'I{i + 1}': {'min': 0.0, 'max': 1.0} for i in range(CFG['Nd'])}
-        enc_a.update({f'C{i + 1}': {'vocab_size': 100_000} for i in range(CFG['F'])})
-        torch.manual_seed(5)
-        with torch.device(dev):
-            am = AutoInt(embedding_dim=32, num_heads=3, enc_dict=enc_a)
-        am.set_grad_mode('persistent')
-        am.eval()
-        B_a = 32768
-        ab = ColumnarBatch(enc_a, B_a, device=dev, pinned_host=False)
-        ab.load_device(synth_batch(enc_a, B_a, gen, device=dev))
-        da = ab.as_dict()
+    if which in ('safe', 'all'):
+        # ---- AutoInt attention kernels with float4 lane I/O (rpb_set_option('autoint_vec', 1)): BASELINE.json config 4 shape
+        # (B = 32768, 26 fields, D = 32, 3 heads x 8) on a 100k-row vocabulary (the attention kernels do not see the vocabulary).
+        # Same arithmetic in the same order, so everything must be bit-identical; eval() keeps dropout out of the comparison.
+        try:
+            from rec_pangu_b200.models.ranking import AutoInt
+            enc_a = {f'I{i + 1}': {'min': 0.0, 'max': 1.0} for i in range(CFG['Nd'])}
+            enc_a.update({f'C{i + 1}': {'vocab_size': 100_000} for i in range(CFG['F'])})
+            torch.manual_seed(5)
+            with torch.device(dev):
+                am = AutoInt(embedding_dim=32, num_heads=3, enc_dict=enc_a)
+            am.set_grad_mode('persistent')
+            am.eval()
+            B_a = 32768
+            ab = ColumnarBatch(enc_a, B_a, device=dev, pinned_host=False)
+            ab.load_device(synth_batch(enc_a, B_a, gen, device=dev))
+            da = ab.as_dict()
 
-        def a_step(flag):
-            _lib.check(lib.rpb_set_option(b'autoint_vec', flag), 'rpb_set_option(autoint_vec)')
+            def a_step(flag):
+                _lib.check(lib.rpb_set_option(b'autoint_vec', flag), 'rpb_set_option(autoint_vec)')
+                am.zero_grad()
+                out = am(da)
+                out['loss'].backward()
+                torch.cuda.synchronize()
+                ops.check_index_errors(dev)
+                return (out['pred'].detach().clone(), float(out['loss'].item()),
+                        {n: p.grad.detach().clone() for n, p in am.named_parameters() if p.grad is not None and p.numel() < 10_000_000})
+
+            p0, l0_, g0 = a_step(0)
+            p1, l1_, g1 = a_step(1)
+            av = {'pred_equal': bool(torch.equal(p0, p1)), 'dloss': abs(l1_ - l0_),
+                  'max_rel_dgrad': max(float((g1[n] - g0[n]).abs().max() / g0[n].abs().max().clamp_min(1e-12)) for n in g0)}
+            av['parity_ok'] = bool(av['pred_equal'] and av['dloss'] == 0.0 and av['max_rel_dgrad'] <= 1e-5)
+            res['autoint_vec'] = av
             am.zero_grad()
-            out = am(da)
-            out['loss'].backward()
-            torch.cuda.synchronize()
-            ops.check_index_errors(dev)
-            return (out['pred'].detach().clone(), float(out['loss'].item()),
-                    {n: p.grad.detach().clone() for n, p in am.named_parameters() if p.grad is not None and p.numel() < 10_000_000})
-
-        p0, l0_, g0 = a_step(0)
-        p1, l1_, g1 = a_step(1)
-        av = {'pred_equal': bool(torch.equal(p0, p1)), 'dloss': abs(l1_ - l0_),
-              'max_rel_dgrad': max(float((g1[n] - g0[n]).abs().max() / g0[n].abs().max().clamp_min(1e-12)) for n in g0)}
-        av['parity_ok'] = bool(av['pred_equal'] and av['dloss'] == 0.0 and av['max_rel_dgrad'] <= 1e-5)
-        res['autoint_vec'] = av
-        am.zero_grad()
-        am.train()
-        for flag, key in ((0, 'default_ms_per_step'), (1, 'ms_per_step')):
-            _lib.check(lib.rpb_set_option(b'autoint_vec', flag), 'rpb_set_option(autoint_vec)')
-            gs = GraphedStep(am, ab)
-            for _ in range(3):
-                gs.replay()
-            torch.cuda.synchronize()
-            e0.record()
-            for _ in range(20):
-                gs.replay()
-            e1.record()
-            torch.cuda.synchronize()
-            av[key] = e0.elapsed_time(e1) / 20
-            del gs
-        lib.rpb_set_option(b'autoint_vec', 0)
-        del am, ab
-        torch.cuda.empty_cache()
-    except Exception as ex:
-        res.setdefault('autoint_vec', {})['error'] = repr(ex)
+            am.train()
+            for flag, key in ((0, 'default_ms_per_step'), (1, 'ms_per_step')):
+                _lib.check(lib.rpb_set_option(b'autoint_vec', flag), 'rpb_set_option(autoint_vec)')
+                gs = GraphedStep(am, ab)
+                for _ in range(3):
+                    gs.replay()
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(20):
+                    gs.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                av[key] = e0.elapsed_time(e1) / 20
+                del gs
+            lib.rpb_set_option(b'autoint_vec', 0)
+            del am, ab
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            res.setdefault('autoint_vec', {})['error'] = repr(ex)
     emit()
-    # ---- L2 fetch granularity 32 B (cudaLimitMaxL2FetchGranularity, device-wide hint): the scatter epilogue's `red`s fetch
-    # whole 128-byte lines (340 MB read for 109 MB of reductions, profiles/r01_deepfm_step_ncu_full.md); replays of the
-    # graphs captured above, so only the limit differs (runs after the tail leg; if that one trapped, this reports the error)
-    try:
-        if base is not None:
-            lib = _lib.load()
-            _lib.check(lib.rpb_set_option(b'l2_fetch_granularity', 32), 'rpb_set_option(l2_fetch_granularity)')
-            res['l2_fetch_32B'] = {'ms_per_step': time_graphs(base)}      # last leg: the limit is not restored
-    except Exception as ex:
-        res['l2_fetch_32B'] = {'error': repr(ex)}
+    if which in ('safe', 'all'):
+        # ---- L2 fetch granularity 32 B (cudaLimitMaxL2FetchGranularity, device-wide hint): the scatter epilogue's `red`s fetch
+        # whole 128-byte lines (340 MB read for 109 MB of reductions, profiles/r01_deepfm_step_ncu_full.md); replays of the
+        # graphs captured above, so only the limit differs (runs after the tail leg; if that one trapped, this reports the error)
+        try:
+            if base is not None:
+                lib = _lib.load()
+                _lib.check(lib.rpb_set_option(b'l2_fetch_granularity', 32), 'rpb_set_option(l2_fetch_granularity)')
+                res['l2_fetch_32B'] = {'ms_per_step': time_graphs(base)}      # last leg: the limit is not restored
+        except Exception as ex:
+            res['l2_fetch_32B'] = {'error': repr(ex)}
     print(json.dumps(res), flush=True)
     sys.stdout.flush()
     os._exit(0)            # a trapped context must not turn teardown into a hang
@@ -934,11 +950,26 @@ def _finite(o):
     return o
 
 
-def experiments_in_child(steps, budget_s=120):
-    """Run `bench.py --experiment all` in a child process; returns its JSON object or {'error': ...}.  Never raises."""
+def experiments_in_children(steps, deadline):
+    """The three experiment groups, one child process each, as long as `deadline` (time.time()) allows.  Never raises."""
+    out = {}
+    for name, budget in (('safe', 110), ('tc_fwd', 80), ('tc_bwd', 100)):
+        remaining = deadline - time.time()
+        if remaining < 40:
+            out[name] = {'skipped': 'time budget of the optional legs used up'}
+            continue
+        extra = ['--tc-fwd-ok'] if name == 'tc_bwd' and out.get('tc_fwd', {}).get('fused_tc_tail', {}).get('parity_ok') else []
+        t0 = time.time()
+        out[name] = experiments_in_child(steps, int(min(budget, remaining)), name, extra)
+        out[name]['wall_s'] = round(time.time() - t0, 1)
+    return out
+
+
+def experiments_in_child(steps, budget_s=120, group='all', extra=()):
+    """Run `bench.py --experiment <group>` in a child process; returns its JSON object or {'error': ...}.  Never raises."""
     import subprocess
     try:
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), '--experiment', 'all', '--steps', str(steps)],
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), '--experiment', group, '--steps', str(steps), *extra],
                            capture_output=True, text=True, timeout=budget_s)
         for ln in reversed(r.stdout.strip().splitlines()):
             if ln.startswith('{'):
@@ -970,7 +1001,8 @@ def main():
     ap.add_argument('--no-train-step', action='store_true', help='skip the secondary forward+backward+optimizer timing')
     ap.add_argument('--no-extras', action='store_true', help='skip the Zipf-id and stock-PyTorch-eager-GPU secondary timings')
     ap.add_argument('--no-experiments', action='store_true', help='skip the child-process measurements of the opt-in variants')
-    ap.add_argument('--experiment', default=None, help='internal: run the opt-in variant measurements (child process of the default bench)')
+    ap.add_argument('--experiment', default=None, help='internal: run the opt-in variant measurements (child process of the default bench): safe | tc_fwd | tc_bwd | all')
+    ap.add_argument('--tc-fwd-ok', action='store_true', help='internal: the tc_fwd group passed parity, so tc_bwd may also run both tcgen05 variants together')
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     if args.experiment is not None:

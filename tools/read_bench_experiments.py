@@ -50,9 +50,16 @@ def main(path):
     if not ex:
         print('no experiments object (skipped or old bench)')
         return
+    groups = {g: ex[g] for g in ('safe', 'tc_fwd', 'tc_bwd') if isinstance(ex.get(g), dict)} or {'all': ex}
+    print(f"experiments: wall {ex.get('wall_s')} s in {len(groups)} child process(es)")
+    for gname, grp in groups.items():
+        report(gname, grp)
+
+
+def report(gname, ex):
     base = ex.get('default_ms_per_step')
-    print(f"experiments: wall {ex.get('wall_s')} s, default {base} ms/step, fwd {ex.get('default_fwd_us')} us, "
-          f"infer fwd {ex.get('default_fwd_infer_us')} us; notes: {ex.get('timeout') or ex.get('skipped') or ex.get('error') or '-'}")
+    print(f"[{gname}] wall {ex.get('wall_s')} s, default {base} ms/step, fwd {ex.get('default_fwd_us')} us, "
+          f"infer fwd {ex.get('default_fwd_infer_us')} us; notes: {ex.get('timeout') or ex.get('skipped') or ex.get('error') or ex.get('default_error') or '-'}")
     for k, v in ex.items():
         if not isinstance(v, dict):
             continue
