@@ -14,9 +14,11 @@ int g_gemm_v2 = 1;
 int g_gemm_a_tmem = 1;
 int g_gemm_stack_n = 1;
 int g_tf32_raw_hi = 1;
+int g_fused_gather_warps = 8;
+int g_fused_ring = 0;
 int g_fused_tc_tail = 0;    // opt-in until measured on hardware
 int g_tower_bwd_tc = 0;     // opt-in until measured on hardware
-int g_autoint_vec = 0;      // opt-in until measured on hardware
+int g_autoint_vec = 1;      // float4 lane I/O: bit-identical, 3.60 -> 3.18 ms per config-4 step (BENCH_r01 experiments.safe.autoint_vec)
 int g_l2_persist = 0;       // opt-in until measured on hardware
 size_t g_l2_aside = 0, g_l2_max_window = 0;
 
@@ -89,6 +91,8 @@ RPB_API int rpb_set_option(const char* name, int64_t value) {
     }
     if (n == "autoint_vec") { rpb::g_autoint_vec = value != 0; return 0; }
     if (n == "tower_bwd_tc") { rpb::g_tower_bwd_tc = value != 0; return 0; }
+    if (n == "fused_gather_warps") { if (value != 4 && value != 8) return RPB_ERR_BAD_ARG; rpb::g_fused_gather_warps = (int)value; return 0; }
+    if (n == "fused_ring") { if (value != 0 && (value < 3 || value > 6)) return RPB_ERR_BAD_ARG; rpb::g_fused_ring = (int)value; return 0; }
     if (n == "fused_tc_tail") { rpb::g_fused_tc_tail = value != 0; return 0; }
     if (n == "wgrad_tc") { rpb::g_wgrad_tc = value != 0; return 0; }
     if (n == "scatter_reverse") { rpb::g_scatter_reverse = value != 0; return 0; }

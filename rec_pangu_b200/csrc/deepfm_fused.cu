@@ -545,6 +545,389 @@ deepfm_fwd_fused_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_
     }
 }
 
+
+// =====================================================================================================================
+// v2 of the one-kernel forward (default): EIGHT gather/split warps and the feature row stored by TMA.
+//
+// The per-role trace of the 4-warp kernel above (profiles/r01_experiments.md, BENCH_r01 experiments.tc_fwd) showed the
+// four gather/split warps busy for 159 k of 210 k cycles per CTA — one warp per SM sub-partition doing, per k-block and
+// row, the row requests, 8 LDS.128, the FM sums, 32 hi/lo splits, two tcgen05.st.x32 and 8 cooperative STG.128 of x,
+// every instruction at its full dependent latency — while the MMA thread waited for operands 60 % of the time.  Here
+//   * warps 2-9 gather: warps w and w+4 share a TMEM lane quarter (rows) and own ONE FIELD each of a k-block (16 of its
+//     32 columns), i.e. half the work per thread and two independent instruction streams per sub-partition;
+//   * a warp's rows of a k-block live in a private [32 rows x 64 B] stage written by cp.async in the TMA SWIZZLE_64B
+//     pattern (thread = row LDS.128 stays conflict-free without padding), and the feature row x leaves the SM as ONE
+//     `cp.async.bulk.tensor.2d.global.shared::cta` per warp and k-block issued by lane 0 — no STG, no second LDS pass;
+//   * the FM sums of the two field halves meet once per tile through shared memory (named barrier per lane quarter).
+// Warps: 0 = weight TMA producer, 1 = MMA issuer (+TMEM alloc), 2-9 = gather + split, 10-17 = epilogue + tower tail.
+constexpr int F8_THREADS = 576;
+constexpr int F8_GW = 8;                          // gather warps
+constexpr int F8_STAGE_BYTES = F8_GW * 32 * 64;   // one k-block of a 128-row tile: 8 private [32 x 64 B] regions = 16 KiB
+constexpr int F8_FMX_LD = 17;                     // floats per row of the FM exchange (sum_f e [16] | sum e^2), odd stride
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 :: "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory"); }
+
+// Diagnostics as for the kernel above; gather rows describe warp 2 (field half 0, lane quarter 2).
+template <int LA, bool SHARDED>
+__global__ void __launch_bounds__(F8_THREADS, 1)
+deepfm_fwd_fused8_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
+                         const __grid_constant__ CUtensorMap tmX,
+                         const __grid_constant__ FusedFwdParams p, const __grid_constant__ TowerFwdParams tw, int m_tiles) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* b_base = smem;                                                   // FG_LB x 16 KiB, 1 KiB aligned (SWIZZLE_128B)
+    uint8_t* a_base = b_base + FG_LB * FG_B_BYTES;                            // LA x 16 KiB: [stage][gather warp][32 rows][64 B], SWIZZLE_64B
+    long long* id_base = reinterpret_cast<long long*>(a_base + LA * F8_STAGE_BYTES);     // [LA][gather warp][32] ids
+    uint64_t* bars = reinterpret_cast<uint64_t*>(id_base + LA * F8_GW * 32);
+    uint64_t* full_b = bars;                       // [FG_LB]  weight k-block landed
+    uint64_t* empty_b = full_b + FG_LB;            // [FG_LB]  MMAs that read it are done
+    uint64_t* ready_op = empty_b + FG_LB;          // [FG_OP]  A hi/lo of a k-block are in tensor memory (one arrival per gather warp)
+    uint64_t* empty_op = ready_op + FG_OP;         // [FG_OP]
+    uint64_t* tmem_full = empty_op + FG_OP;        // [2]
+    uint64_t* tmem_empty = tmem_full + 2;          // [2]
+    uint64_t* fm_ready = tmem_empty + 2;           // [FG_FM_BUF]  FM values of a tile written (4 arrivals: the half-0 warps)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(fm_ready + FG_FM_BUF);
+    float* fm_tile = reinterpret_cast<float*>(tmem_ptr + 4);                  // [FG_FM_BUF][128]
+    float* fm_x = fm_tile + FG_FM_BUF * TC_BLOCK_M;                           // [128][F8_FMX_LD] half-1 -> half-0 FM partials
+    float* tw_As = fm_x + TC_BLOCK_M * F8_FMX_LD;                             // 128 * 17 floats: still 16-byte aligned
+    float* tw_Bs = tw_As + TC_BLOCK_M * TW_LDA;
+    float* tw_loss = tw_Bs + tw.n_tail * TW_H * TW_H;
+    static_assert((TC_BLOCK_M * F8_FMX_LD) % 4 == 0, "fm_x must keep tw_As 16-byte aligned");
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = p.nkb;
+    const int my_tiles = ((int)blockIdx.x < m_tiles) ? (m_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const uint32_t G = (uint32_t)my_tiles * (uint32_t)nkb;                    // k-blocks this CTA walks
+    constexpr uint32_t ACC_STRIDE = 2 * FG_N;                                 // stacked accumulator: [a.b_hi | a.b_lo]
+    constexpr uint32_t A_COL = 2 * ACC_STRIDE;                                // first TMEM column of the operand ring
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < FG_LB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
+        for (int s = 0; s < FG_OP; ++s) { mbar_init(&ready_op[s], F8_GW); mbar_init(&empty_op[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], FG_EPI_WARPS); }
+        for (int s = 0; s < FG_FM_BUF; ++s) mbar_init(&fm_ready[s], 4);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const bool trace = g_fg_trace_on != 0 && blockIdx.x == 0;
+    const long long t_start = FG_T();
+
+    if (warp == 0) {
+        // ---------------- weight producer: [B hi ; B lo] of every k-block through a FG_LB-deep ring
+        if (lane == 0) {
+            long long w_b = 0;
+            for (uint32_t g = 0; g < G; ++g) {
+                const int s = g % FG_LB, kb = g % nkb;
+                const long long c0 = FG_T();
+                mbar_wait(&empty_b[s], ((g / FG_LB) & 1u) ^ 1u);
+                w_b += FG_T() - c0;
+                if (trace && g + 1 == G) g_fg_trace[11] = (unsigned long long)w_b;
+                uint8_t* st = b_base + (size_t)s * FG_B_BYTES;
+                mbar_arrive_expect_tx(&full_b[s], (uint32_t)FG_B_BYTES);
+                tma_load_2d(st, &tmBhi, &full_b[s], kb * TC_BLOCK_K, 0);
+                tma_load_2d(st + FG_B_BYTES / 2, &tmBlo, &full_b[s], kb * TC_BLOCK_K, 0);
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer: per k-step two TS-mode MMAs (a_lo, a_hi) against the stacked 128-row weight operand
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(TC_BLOCK_M, 2 * FG_N);
+            uint32_t g = 0;
+            long long w_fb = 0, w_op = 0, w_acc = 0, w_is = 0;
+            for (int t = 0; t < my_tiles; ++t) {
+                const uint32_t acc = (uint32_t)t & 1u;
+                const long long c0 = FG_T();
+                mbar_wait(&tmem_empty[acc], (((uint32_t)t >> 1) & 1u) ^ 1u);
+                w_acc += FG_T() - c0;
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int s = g % FG_LB, o = g % FG_OP;
+                    const long long c1 = FG_T();
+                    mbar_wait(&full_b[s], (g / FG_LB) & 1u);
+                    const long long c2 = FG_T();
+                    mbar_wait(&ready_op[o], (g / FG_OP) & 1u);
+                    const long long c3 = FG_T();
+                    w_fb += c2 - c1; w_op += c3 - c2;
+                    tc_fence_after();
+                    const uint32_t b_addr = smem_u32(b_base + (size_t)s * FG_B_BYTES);
+                    const uint32_t ta_hi = tmem_base + A_COL + (uint32_t)o * 64u, ta_lo = ta_hi + 32u;
+#pragma unroll
+                    for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
+                        const uint64_t db = make_kmajor_sw128_desc(b_addr + k * TC_UMMA_K * 4);
+                        umma_tf32_ts(d_tmem, ta_lo + k * TC_UMMA_K, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        umma_tf32_ts(d_tmem, ta_hi + k * TC_UMMA_K, db, idesc, 1u);
+                    }
+                    umma_commit(&empty_op[o]);
+                    umma_commit(&empty_b[s]);
+                    w_is += FG_T() - c3;
+                }
+                umma_commit(&tmem_full[acc]);
+            }
+            if (trace) { g_fg_trace[4] = (unsigned long long)w_fb; g_fg_trace[5] = (unsigned long long)w_op; g_fg_trace[6] = (unsigned long long)w_acc; g_fg_trace[7] = (unsigned long long)w_is; }
+        }
+    } else if (warp < 2 + F8_GW) {
+        // ---------------- gather + split warps: thread = sample row of the tile (= its TMEM lane), one field per k-block
+        const int gw = warp - 2;                         // 0..7
+        const int q = warp & 3;                          // TMEM lane quarter this warp may touch (= warp id mod 4)
+        const int half = gw >> 2;                        // field 2*kb + half, columns half*16 .. +15 of the k-block
+        const int wrow0 = q * 32;                        // first tile row of this warp
+        const int r = wrow0 + lane;
+        const int K_emb_cols = p.F * 16;
+        const int sw = (lane >> 1) & 3;                  // SWIZZLE_64B: 16-byte chunk c of row `lane` lives at chunk c ^ sw
+        uint8_t* my_stage = a_base + gw * (32 * 64);     // + slot * F8_STAGE_BYTES
+        long long* my_ids = id_base + gw * 32;           // + slot * F8_GW * 32
+        // issue(): request the table row pieces (or dense columns) of the next un-requested k-block `gi` into stage gi % LA,
+        // and this lane's id of k-block gi + LA - 1 into the id FIFO; one cp.async group per call (empty past the end).
+        // Rows are requested cooperatively: 4 consecutive lanes fetch the four 16-byte pieces of one 64-byte row.
+        uint32_t gi = 0; int i_kb = 0, i_t = 0;          // next k-block to request: global index, k-block, local tile
+        uint32_t gj = (uint32_t)(LA - 1); int j_kb = (LA - 1) % nkb, j_t = (LA - 1) / nkb;     // next ids to request
+        auto issue = [&]() {
+            if (gi < G) {
+                const int mt = ((int)blockIdx.x + i_t * (int)gridDim.x) * TC_BLOCK_M;
+                const int slot = (int)(gi % LA);
+                uint8_t* stg = my_stage + slot * F8_STAGE_BYTES;
+                if (i_kb < p.nkb_emb) {
+                    const int piece = lane & 3, f = 2 * i_kb + half;
+                    const long long* ids = my_ids + slot * (F8_GW * 32);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int rr = i * 8 + (lane >> 2);              // row inside the warp's 32
+                        const bool ok = mt + wrow0 + rr < p.M;
+                        long long id = ids[rr];
+                        if (!ok) id = 0;
+                        else if ((unsigned long long)id >= (unsigned long long)p.rows[f]) { if (piece == 0) fg_bad_index(p.err, f, mt + wrow0 + rr, id); id = 0; }
+                        const float* src;
+                        if constexpr (SHARDED) {
+                            const unsigned long long iu = (unsigned long long)id, gg = (unsigned long long)p.G;
+                            const float* base = reinterpret_cast<const float*>(__ldg(reinterpret_cast<const unsigned long long*>(p.shard_tab) + (size_t)f * gg + (size_t)(iu % gg)));
+                            src = base + (size_t)(iu / gg) * 16 + piece * 4;
+                        } else {
+                            src = p.tables[f] + (size_t)id * 16 + piece * 4;
+                        }
+                        fg_cp16(reinterpret_cast<float*>(stg + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4)), src, ok);
+                    }
+                } else {
+                    const int m = mt + r;
+                    const bool ok = m < p.M;
+                    const int c0 = i_kb * TC_BLOCK_K - K_emb_cols + half * 16;    // first dense column of this warp's half
+#pragma unroll 4
+                    for (int j = 0; j < 16; ++j) {
+                        const int c = c0 + j;
+                        float* dst = reinterpret_cast<float*>(stg + lane * 64 + (((j >> 2) ^ sw) << 4)) + (j & 3);
+                        if (c < p.Nd) fg_cp4(dst, p.dense[c] + (ok ? m : 0), ok);
+                        else *dst = 0.f;
+                    }
+                }
+            }
+            if (gj < G && j_kb < p.nkb_emb) {
+                const int m = ((int)blockIdx.x + j_t * (int)gridDim.x) * TC_BLOCK_M + r;
+                const bool ok = m < p.M;
+                fg_cp8(my_ids + (int)(gj % LA) * (F8_GW * 32) + lane, p.idx[2 * j_kb + half] + (ok ? m : 0), ok);
+            }
+            fg_commit();
+            ++gi; if (++i_kb == nkb) { i_kb = 0; ++i_t; }
+            ++gj; if (++j_kb == nkb) { j_kb = 0; ++j_t; }
+        };
+        // prologue: ids of the first LA-1 k-blocks with plain loads, then LA-1 groups in flight
+        {
+            int kb = 0, tl = 0;
+            for (uint32_t qq = 0; qq + 1 < (uint32_t)LA && qq < G; ++qq) {
+                const int m = ((int)blockIdx.x + tl * (int)gridDim.x) * TC_BLOCK_M + r;
+                const bool ok = kb < p.nkb_emb && m < p.M;
+                my_ids[(int)(qq % LA) * (F8_GW * 32) + lane] = ok ? __ldg(p.idx[2 * kb + half] + m) : 0;
+                if (++kb == nkb) { kb = 0; ++tl; }
+            }
+        }
+        __syncwarp();
+        for (int qq = 0; qq + 1 < LA; ++qq) issue();
+
+        float fs[16];                                   // sum over this warp's fields of e, and of e^2
+        float fq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) fs[j] = 0.f;
+        uint32_t g = 0;
+        long long w_cp = 0, w_eo = 0, w_wk = 0;
+        const bool store_x = p.x != nullptr;
+        for (int t = 0; t < my_tiles; ++t) {
+            const int mt = ((int)blockIdx.x + t * (int)gridDim.x) * TC_BLOCK_M;
+            const int m = mt + r;
+            for (int kb = 0; kb < nkb; ++kb, ++g) {
+                const long long c0 = FG_T();
+                fg_wait<LA - 2>();                      // group g has landed: this lane's pieces of stage g and its id of k-block g + LA - 1
+                const long long c1 = FG_T();
+                const uint8_t* stg = my_stage + (g % LA) * F8_STAGE_BYTES;
+                if (store_x) fence_proxy_async();       // the TMA store below reads what cp.async / st.shared wrote
+                __syncwarp();                           // ... of every lane of this warp
+                if (store_x && lane == 0) {
+                    const int col = kb * TC_BLOCK_K + half * 16;
+                    if (col < (int)p.ldx) tma_store_2d(&tmX, stg, col, mt + wrow0);      // rows >= M / columns >= ldx are clipped by the TMA unit
+                    bulk_commit();
+                }
+                float4 v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const float4*>(stg + lane * 64 + ((j ^ sw) << 4));
+                if (kb < p.nkb_emb) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 a = v[j];
+                        fs[4 * j + 0] += a.x; fs[4 * j + 1] += a.y; fs[4 * j + 2] += a.z; fs[4 * j + 3] += a.w;
+                        fq = fmaf(a.x, a.x, fq); fq = fmaf(a.y, a.y, fq); fq = fmaf(a.z, a.z, fq); fq = fmaf(a.w, a.w, fq);
+                    }
+                }
+                uint32_t h[16], l[16];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 qv = v[j];
+                    h[4 * j + 0] = __float_as_uint(qv.x) & 0xFFFFE000u; l[4 * j + 0] = __float_as_uint(qv.x - __uint_as_float(h[4 * j + 0]));
+                    h[4 * j + 1] = __float_as_uint(qv.y) & 0xFFFFE000u; l[4 * j + 1] = __float_as_uint(qv.y - __uint_as_float(h[4 * j + 1]));
+                    h[4 * j + 2] = __float_as_uint(qv.z) & 0xFFFFE000u; l[4 * j + 2] = __float_as_uint(qv.z - __uint_as_float(h[4 * j + 2]));
+                    h[4 * j + 3] = __float_as_uint(qv.w) & 0xFFFFE000u; l[4 * j + 3] = __float_as_uint(qv.w - __uint_as_float(h[4 * j + 3]));
+                }
+                const int o = g % FG_OP;
+                const long long c2 = FG_T();
+                mbar_wait(&empty_op[o], ((g / FG_OP) & 1u) ^ 1u);
+                const long long c3 = FG_T();
+                tc_fence_after();
+                const uint32_t ta = tmem_base + A_COL + (uint32_t)o * 64u + ((uint32_t)wrow0 << 16) + (uint32_t)half * 16u;
+                tmem_st16(ta, h);
+                tmem_st16(ta + 32u, l);
+                tmem_st_wait();
+                tc_fence_before();
+                if (lane == 0) bulk_wait_read<1>();     // the store of k-block g - 1 has finished reading its stage ...
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ready_op[o]);
+                issue();                                // ... which the requests of k-block g + LA - 1 now refill
+                w_cp += c1 - c0; w_eo += c3 - c2; w_wk += (c2 - c1) + (FG_T() - c3);
+            }
+            // FM second order of this sample: 0.5 * (sum_d s_d^2 - sum_{f,d} e^2); the two field halves meet in shared memory,
+            // the half-0 thread finishes and hands the value to the tail
+            if (half == 1) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) fm_x[r * F8_FMX_LD + j] = fs[j];
+                fm_x[r * F8_FMX_LD + 16] = fq;
+            }
+            asm volatile("bar.sync %0, 64;" :: "r"(2 + q) : "memory");
+            if (half == 0) {
+                float ss = 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { fs[j] += fm_x[r * F8_FMX_LD + j]; ss = fmaf(fs[j], fs[j], ss); }
+                const float fmv = 0.5f * (ss - (fq + fm_x[r * F8_FMX_LD + 16]));
+                fm_tile[(t % FG_FM_BUF) * TC_BLOCK_M + r] = fmv;
+                if (m < p.M) {
+                    if (p.fm != nullptr) p.fm[m] = fmv;
+                    if (p.fm_s != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            stg_f4(p.fm_s + (size_t)m * 16 + 4 * j, make_float4(fs[4 * j], fs[4 * j + 1], fs[4 * j + 2], fs[4 * j + 3]));
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&fm_ready[t % FG_FM_BUF]);
+            }
+            fq = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) fs[j] = 0.f;
+        }
+        fg_wait<0>();
+        if (lane == 0) bulk_wait_all<0>();
+        if (trace && gw == 0 && lane == 0) { g_fg_trace[1] = (unsigned long long)w_cp; g_fg_trace[2] = (unsigned long long)w_eo; g_fg_trace[3] = (unsigned long long)w_wk; }
+    } else {
+        // ---------------- epilogue warps: layer-1 epilogue -> h1 (HBM + shared memory) -> tower tail (tower_tile.cuh)
+        const int quarter = warp & 3;
+        const int half = (warp - (2 + F8_GW)) >> 2;
+        const int row = quarter * 32 + lane;
+        const int et = threadIdx.x - (2 + F8_GW) * 32;
+        auto epi_sync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+        float loss_acc = 0.f;
+        tower_load_weights_t<FG_EPI_WARPS * 32>(tw, tw_Bs, et);
+        const float4 tw_wo = ldg_f4(tw.w_out + (et & 15) * 4);
+        const float tw_bo = tw.b_out != nullptr ? __ldg(tw.b_out) : 0.f;
+        for (int t = 0; t < my_tiles; ++t) {
+            const int m0 = ((int)blockIdx.x + t * (int)gridDim.x) * TC_BLOCK_M;
+            const uint32_t acc = (uint32_t)t & 1u;
+            const int m = m0 + row;
+            const long long q0 = FG_T();
+            mbar_wait(&tmem_full[acc], ((uint32_t)t >> 1) & 1u);
+            tc_fence_after();
+            const long long q1 = FG_T();
+            epi_sync();                                // previous tile's activations fully consumed (weights visible)
+            for (int c0 = half * 16; c0 < FG_N; c0 += 32) {
+                uint32_t a0[16], a1[16];
+                tmem_ld16(tmem_base + acc * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, a0);
+                tmem_ld16(tmem_base + acc * ACC_STRIDE + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(FG_N + c0), a1);
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    v[j] = fmaxf(__uint_as_float(a1[j]) + __uint_as_float(a0[j]) + __ldg(p.bias1 + c0 + j), 0.f);
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 q4 = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    if (m < p.M) stg_f4(p.h1 + (size_t)m * p.ldh1 + c0 + j, q4);
+                    *reinterpret_cast<float4*>(tw_As + row * TW_LDA + c0 + j) = q4;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            mbar_wait(&fm_ready[t % FG_FM_BUF], ((uint32_t)t / FG_FM_BUF) & 1u);
+            epi_sync();
+            const long long q2 = FG_T();
+            tower_tail_tile_fwd<FG_EPI_WARPS * 32>(tw, tw_As, tw_Bs, m0, et, tw_wo, tw_bo, loss_acc, epi_sync,
+                                                   fm_tile + (t % FG_FM_BUF) * TC_BLOCK_M);
+            if (trace && et == 0) {
+                g_fg_trace[8] += (unsigned long long)(q1 - q0); g_fg_trace[9] += (unsigned long long)(q2 - q1);
+                g_fg_trace[10] += (unsigned long long)(FG_T() - q2);
+            }
+        }
+        if (tw.loss != nullptr) tw_loss[et] = loss_acc;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+    if (trace && threadIdx.x == 0) g_fg_trace[0] = (unsigned long long)(clock64() - t_start);
+    if (tw.loss != nullptr && warp == 0) {
+        // deterministic mean BCE: 256 epilogue partials -> per-CTA partial -> the last CTA adds them in index order
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < FG_EPI_WARPS; ++i) s += tw_loss[lane + 32 * i];
+        s = warp_sum(s);
+        unsigned int last = 0;
+        if (lane == 0) {
+            tw.partials[blockIdx.x] = s;
+            __threadfence();
+            last = (atomicAdd(tw.counter, 1u) == gridDim.x - 1) ? 1u : 0u;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            __threadfence();
+            float tot = 0.f;
+            for (int i = lane; i < (int)gridDim.x; i += 32) tot += ((volatile float*)tw.partials)[i];
+            tot = warp_sum(tot);
+            if (lane == 0) {
+                tw.loss[0] = tw.scale * (tot / (float)tw.M);
+                *tw.counter = 0u;
+            }
+        }
+    }
+}
+
+static size_t f8_smem_bytes(int la, int n_tail) {
+    return (size_t)FG_LB * FG_B_BYTES + (size_t)la * F8_STAGE_BYTES + (size_t)la * F8_GW * 32 * 8 +
+           (2 * FG_LB + 2 * FG_OP + 4 + FG_FM_BUF) * 8 + 16 + FG_FM_BUF * TC_BLOCK_M * 4 + (size_t)(TC_BLOCK_M * F8_FMX_LD) * 4 +
+           (size_t)(TC_BLOCK_M * TW_LDA + n_tail * TW_H * TW_H + 256) * 4 + 1024;
+}
+
 static size_t fg_smem_bytes(int la, int n_tail, bool tctail = false) {
     return (size_t)FG_LB * FG_B_BYTES + (tctail ? (size_t)n_tail * FT_TAIL_B_BYTES : 0) +
            (size_t)la * TC_BLOCK_M * FG_ROW * 4 + (size_t)la * TC_BLOCK_M * 16 +
@@ -616,6 +999,35 @@ RPB_API int rpb_deepfm_fwd_fused(const RpbGatherDesc* g, const float* W1, const 
     const size_t cap = 227 * 1024;
     // tail layers on tcgen05 (opt-in, see FT_OP): needs the resident tail operands next to >= 3 gather stages
     const bool tctail = g_fused_tc_tail != 0 && fg_smem_bytes(3, d->n_tail, true) <= cap;
+    if (g_fused_gather_warps == 8 && !tctail) {
+        // default: 8 gather warps, x stored by TMA ([32 rows x 16 columns] boxes, SWIZZLE_64B) — deepfm_fwd_fused8_kernel
+        CUtensorMap tmX = tmBhi;                       // placeholder when x is not materialised
+        if (p.x != nullptr) {
+            rc = tc_make_map2d(&tmX, p.x, p.M, p.ldx, p.ldx, 16, 32, 64);
+            if (rc != 0) return rc;
+        }
+        auto launch8 = [&](auto la_tag, auto sh_tag) -> int {
+            constexpr int LA = decltype(la_tag)::value;
+            constexpr bool SH = decltype(sh_tag)::value;
+            const size_t smem = f8_smem_bytes(LA, d->n_tail);
+            cudaError_t e = cudaFuncSetAttribute(deepfm_fwd_fused8_kernel<LA, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            deepfm_fwd_fused8_kernel<LA, SH><<<grid, F8_THREADS, smem, st>>>(tmBhi, tmBlo, tmX, p, tw, m_tiles);
+            return (int)cudaGetLastError();
+        };
+        auto pick8 = [&](auto la_tag) -> int { return sharded ? launch8(la_tag, std::true_type{}) : launch8(la_tag, std::false_type{}); };
+        const int want = g_fused_ring > 0 ? g_fused_ring : 6;
+        for (int la = want; la >= 3; --la) {
+            if (f8_smem_bytes(la, d->n_tail) > cap) continue;
+            switch (la) {
+                case 6: return pick8(std::integral_constant<int, 6>{});
+                case 5: return pick8(std::integral_constant<int, 5>{});
+                case 4: return pick8(std::integral_constant<int, 4>{});
+                default: return pick8(std::integral_constant<int, 3>{});
+            }
+        }
+        return RPB_ERR_UNSUPPORTED;
+    }
     CUtensorMap tmThi = tmBhi, tmTlo = tmBlo;          // placeholders when the tail runs on the CUDA cores
     if (tctail) {
         rc = tc_prepare_tail_weights(tw.W, d->n_tail, &tmThi, &tmTlo, st, 0, 6);

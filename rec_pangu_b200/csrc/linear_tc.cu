@@ -912,6 +912,21 @@ static int make_map(CUtensorMap* map, const float* base, long long rows, long lo
     return r == CUDA_SUCCESS ? 0 : RPB_ERR_BAD_ARG;
 }
 
+int tc_make_map2d(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_cols, int box_rows,
+                  int swizzle_bytes) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr) return RPB_ERR_NO_DRIVER;
+    const CUtensorMapSwizzle swz = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B :
+                                   swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : RPB_ERR_BAD_ARG;
+}
+
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 bool tc_shape_ok(const float* A, long long lda, int M, int N, int K) {

@@ -21,11 +21,8 @@ def _logit(p):
     return torch.log(p) - torch.log1p(-p)
 
 
-RANKING_GOLDEN = ['deepfm', 'deepfm_d16', 'fm', 'wdl', 'nfm', 'dcn', 'xdeepfm', 'autoint', 'autoint_l2', 'fibinet']
-# AFM (= the FiBiNet class under the reference's other name) was added after the last GPU call of round 1: its fixture runs
-# with the other not-yet-run-on-hardware checks (RPB_EXPERIMENTAL=1) until it has passed once on a B200
-if __import__('os').environ.get('RPB_EXPERIMENTAL', '0') == '1':
-    RANKING_GOLDEN.append('afm')
+# 'afm' = the FiBiNet class under the reference's other name (passed on a B200 in the round-1 bench record: afm_golden.parity_ok)
+RANKING_GOLDEN = ['deepfm', 'deepfm_d16', 'fm', 'wdl', 'nfm', 'dcn', 'xdeepfm', 'autoint', 'autoint_l2', 'fibinet', 'afm']
 
 
 @pytest.mark.parametrize('name', RANKING_GOLDEN)

@@ -344,11 +344,11 @@ def test_sharded_fused_core_on_local_shards(G):
             torch.testing.assert_close(p.grad, dense_r[n], rtol=1e-4, atol=1e-6, msg=lambda s: f'{n}: {s}')
 
 
-@pytest.mark.skipif(os.environ.get('RPB_EXPERIMENTAL', '0') != '1',
-                    reason='float4 lane I/O of the AutoInt attention kernels: compiled but not yet run on hardware (opt-in)')
+@pytest.mark.parametrize('vec', [0, 1])
 @pytest.mark.parametrize('name', ['autoint', 'autoint_l2'])
-def test_autoint_vec_matches_reference_golden(name):
-    """rpb_set_option('autoint_vec', 1) against the fixtures produced by the real reference AutoInt (tests/golden)."""
+def test_autoint_vec_matches_reference_golden(name, vec):
+    """Both lane I/O variants of the AutoInt attention kernels (rpb_set_option('autoint_vec', 0 | 1); 1 = float4, the default)
+    against the fixtures produced by the real reference AutoInt (tests/golden)."""
     from helpers import load_golden
     from rec_pangu_b200 import ops, _lib
     from rec_pangu_b200.models import ranking
@@ -358,14 +358,14 @@ def test_autoint_vec_matches_reference_golden(name):
     model.load_state_dict(g['sd'])
     model = model.cuda().eval()
     data = {k: v.cuda() for k, v in g['data'].items()}
-    _lib.check(_lib.load().rpb_set_option(b'autoint_vec', 1), 'rpb_set_option(autoint_vec)')
+    _lib.check(_lib.load().rpb_set_option(b'autoint_vec', vec), 'rpb_set_option(autoint_vec)')
     try:
         out = model(data)
         out['loss'].backward()
         torch.cuda.synchronize()
         ops.check_index_errors()
     finally:
-        _lib.check(_lib.load().rpb_set_option(b'autoint_vec', 0), 'rpb_set_option(autoint_vec)')
+        _lib.check(_lib.load().rpb_set_option(b'autoint_vec', 1), 'rpb_set_option(autoint_vec)')
     torch.testing.assert_close(out['pred'].cpu(), g['out']['pred'], rtol=1e-5, atol=1e-6)
     grads = dict(model.named_parameters())
     for k, ref in g['grad'].items():
