@@ -211,6 +211,9 @@ int rpb_deepfm_fwd_fused(const RpbGatherDesc* g, const float* W1, const float* b
 /* Per-role stall cycles of CTA 0 of the last rpb_deepfm_fwd_fused launch (same protocol as rpb_debug_tc_trace; see
  * deepfm_fused.cu for the 12 counters). */
 int rpb_debug_fused_trace(uint64_t* out16, int enable);
+/* per-CTA record of the last traced launch of the 8-gather-warp kernel: out1024[cta*4 + {0: SM id, 1: start ns, 2: end ns,
+ * 3: tiles}] (globaltimer), 256 CTAs. */
+int rpb_debug_fused_cta_times(uint64_t* out1024);
 /* Backward of rpb_tower_tail_fwd.  hin: HOST array of n_tail+1 device pointers, hin[0] = h1 (row stride ldh1),
  * hin[j] = h[j-1] ([M, H] contiguous).  dlogit[m] = dlogit_in[m] when given, else gloss[0]*scale/M * dBCE/dp * p(1-p)
  * from (pred, label) with ATen's clamps (gloss NULL = 1); it is written to dlogit_out when non-NULL.
@@ -232,10 +235,13 @@ int rpb_tower_tail_bwd(const RpbTowerBwdDesc* d, void* stream);
 /* nn.Dropout of the MLP (models/layers/deep.py:71-72, default p=0.1 for xDeepFM/AutoInt) on a contiguous
  * buffer of n floats.  keep(i) comes from a counter-based generator keyed by (seed, i), so backward recomputes
  * the mask instead of storing it.  Train-mode equivalence with torch's Philox stream is statistical
- * (SURVEY.md §7 hard-part 4).  bwd: dx = dy * keep/(1-p) * (relu_out ? relu_out > 0 : 1). */
-int rpb_dropout_fwd(const float* x, float* y, int64_t n, float p, uint64_t seed, void* stream);
+ * (SURVEY.md §7 hard-part 4).  bwd: dx = dy * keep/(1-p) * (relu_out ? relu_out > 0 : 1).
+ * `epoch` (device pointer or NULL): a step counter in device memory that is mixed into the seed when the kernel RUNS, so a
+ * training step captured once as a CUDA graph draws a fresh mask at every replay (the host-drawn `seed` is baked into the
+ * graph); forward and backward of one step must see the same *epoch. */
+int rpb_dropout_fwd(const float* x, float* y, int64_t n, float p, uint64_t seed, const uint64_t* epoch, void* stream);
 int rpb_dropout_bwd(const float* dy, const float* relu_out, float* dx, int64_t n, float p, uint64_t seed,
-                    void* stream);
+                    const uint64_t* epoch, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * DCN CrossNet, all L (<= 8) layers in one kernel (models/layers/interaction.py:119-141):

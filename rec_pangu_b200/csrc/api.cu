@@ -16,7 +16,7 @@ int g_gemm_stack_n = 1;
 int g_tf32_raw_hi = 1;
 int g_fused_gather_warps = 8;
 int g_fused_ring = 0;
-int g_fused_tc_tail = 0;    // opt-in until measured on hardware
+int g_fused_tc_tail = 1;    // tower-tail layers of the one-kernel forward on tcgen05 (0 = fp32 CUDA-core tail)
 int g_tower_bwd_tc = 0;     // opt-in until measured on hardware
 int g_autoint_vec = 1;      // float4 lane I/O: bit-identical, 3.60 -> 3.18 ms per config-4 step (BENCH_r01 experiments.safe.autoint_vec)
 int g_l2_persist = 0;       // opt-in until measured on hardware

@@ -76,9 +76,14 @@ __device__ __forceinline__ void fg_bad_index(long long* err, int f, int b, long 
 // Diagnostics (rpb_debug_fused_trace): cycles of CTA 0 of the last launch — [0] kernel, [1] split: cp.async wait,
 // [2] split: wait for a free TMEM operand slot, [3] split: work, [4] MMA: wait weights, [5] MMA: wait operands,
 // [6] MMA: wait accumulator, [7] MMA: issue, [8] epilogue: wait accumulator, [9] epilogue: layer-1 part + wait FM,
-// [10] epilogue: tail, [11] weight producer: wait free stage.
+// [10] epilogue: tail, [11] weight producer: wait free stage; 8-warp kernel only: gather phases [12] proxy fence + warp sync +
+// TMA store, [13] operand loads + FM sums + hi/lo split, [14] tcgen05.st + wait, [15] next row requests (issue()).
 __device__ int g_fg_trace_on = 0;
 __device__ unsigned long long g_fg_trace[16];
+// per-CTA record of the last traced launch (8-warp kernel): [cta][0] = SM id, [1] = start, [2] = end (globaltimer, ns), [3] = tiles
+__device__ unsigned long long g_fg_cta[256 * 4];
+__device__ __forceinline__ unsigned long long fg_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned int fg_smid() { unsigned int r; asm volatile("mov.u32 %0, %smid;" : "=r"(r)); return r; }
 #define FG_T() (trace ? clock64() : 0ll)
 
 template <int LA, bool SHARDED, bool TCTAIL>
@@ -574,15 +579,25 @@ template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile
 template <int N> __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory"); }
 
 // Diagnostics as for the kernel above; gather rows describe warp 2 (field half 0, lane quarter 2).
-template <int LA, bool SHARDED>
+// TCTAIL (default): the 64x64 tail layers run on tcgen05 as well — the epilogue warps turn an accumulator into the activation
+// row h = relu(acc + b), store it for backward, split it into (hi, lo) and write it back into TENSOR MEMORY as the A operand
+// of the next layer; the MMA thread issues that layer's 8 k-steps x 2 TS-mode MMAs against the resident stacked
+// [W hi ; W lo] operand (TMA-loaded once per CTA) into the accumulator buffer the tile just vacated, between the k-blocks of
+// the next tile.  Activations never touch shared memory, and the drain after a CTA's last gather shrinks from ~25 k cycles
+// (two fp32 64x64 layers on 8 CUDA-core warps) to the latency of the TMEM round trips.
+// Tensor memory: 2 x 128 accumulator columns | OPN x 64 layer-1 operand ring | TCTAIL: 128 columns tail operand (hi | lo).
+template <int LA, bool SHARDED, bool TCTAIL>
 __global__ void __launch_bounds__(F8_THREADS, 1)
 deepfm_fwd_fused8_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
+                         const __grid_constant__ CUtensorMap tmThi, const __grid_constant__ CUtensorMap tmTlo,
                          const __grid_constant__ CUtensorMap tmX,
                          const __grid_constant__ FusedFwdParams p, const __grid_constant__ TowerFwdParams tw, int m_tiles) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    constexpr int OPN = TCTAIL ? FT_OP : FG_OP;                               // depth of the tensor-memory operand ring
     uint8_t* b_base = smem;                                                   // FG_LB x 16 KiB, 1 KiB aligned (SWIZZLE_128B)
-    uint8_t* a_base = b_base + FG_LB * FG_B_BYTES;                            // LA x 16 KiB: [stage][gather warp][32 rows][64 B], SWIZZLE_64B
+    uint8_t* t_base = b_base + FG_LB * FG_B_BYTES;                            // TCTAIL: n_tail x 32 KiB resident tail operands
+    uint8_t* a_base = t_base + (TCTAIL ? tw.n_tail * FT_TAIL_B_BYTES : 0);    // LA x 16 KiB: [stage][gather warp][32 rows][64 B], SWIZZLE_64B
     long long* id_base = reinterpret_cast<long long*>(a_base + LA * F8_STAGE_BYTES);     // [LA][gather warp][32] ids
     uint64_t* bars = reinterpret_cast<uint64_t*>(id_base + LA * F8_GW * 32);
     uint64_t* full_b = bars;                       // [FG_LB]  weight k-block landed
@@ -592,12 +607,13 @@ deepfm_fwd_fused8_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid
     uint64_t* tmem_full = empty_op + FG_OP;        // [2]
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
     uint64_t* fm_ready = tmem_empty + 2;           // [FG_FM_BUF]  FM values of a tile written (4 arrivals: the half-0 warps)
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(fm_ready + FG_FM_BUF);
+    uint64_t* tail_bars = fm_ready + FG_FM_BUF;    // [4] TCTAIL: [0] tail weights landed, [1] tail operand written, [2] tail MMAs done
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tail_bars + 4);
     float* fm_tile = reinterpret_cast<float*>(tmem_ptr + 4);                  // [FG_FM_BUF][128]
     float* fm_x = fm_tile + FG_FM_BUF * TC_BLOCK_M;                           // [128][F8_FMX_LD] half-1 -> half-0 FM partials
     float* tw_As = fm_x + TC_BLOCK_M * F8_FMX_LD;                             // 128 * 17 floats: still 16-byte aligned
-    float* tw_Bs = tw_As + TC_BLOCK_M * TW_LDA;
-    float* tw_loss = tw_Bs + tw.n_tail * TW_H * TW_H;
+    float* tw_Bs = tw_As + (TCTAIL ? TC_BLOCK_M : TC_BLOCK_M * TW_LDA);       // TCTAIL: tw_As = 128 head partials only
+    float* tw_loss = tw_Bs + (TCTAIL ? 0 : tw.n_tail * TW_H * TW_H);
     static_assert((TC_BLOCK_M * F8_FMX_LD) % 4 == 0, "fm_x must keep tw_As 16-byte aligned");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -606,12 +622,14 @@ deepfm_fwd_fused8_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid
     const uint32_t G = (uint32_t)my_tiles * (uint32_t)nkb;                    // k-blocks this CTA walks
     constexpr uint32_t ACC_STRIDE = 2 * FG_N;                                 // stacked accumulator: [a.b_hi | a.b_lo]
     constexpr uint32_t A_COL = 2 * ACC_STRIDE;                                // first TMEM column of the operand ring
+    constexpr uint32_t TAIL_A = A_COL + FT_OP * 64u;                          // TCTAIL: tail operand, hi [0,64) | lo [64,128)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < FG_LB; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
         for (int s = 0; s < FG_OP; ++s) { mbar_init(&ready_op[s], F8_GW); mbar_init(&empty_op[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], FG_EPI_WARPS); }
         for (int s = 0; s < FG_FM_BUF; ++s) mbar_init(&fm_ready[s], 4);
+        mbar_init(&tail_bars[0], 1); mbar_init(&tail_bars[1], FG_EPI_WARPS); mbar_init(&tail_bars[2], 1); mbar_init(&tail_bars[3], 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr, 512);
@@ -621,10 +639,23 @@ deepfm_fwd_fused8_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid
     const uint32_t tmem_base = *tmem_ptr;
     const bool trace = g_fg_trace_on != 0 && blockIdx.x == 0;
     const long long t_start = FG_T();
+    if (g_fg_trace_on != 0 && threadIdx.x == 0 && blockIdx.x < 256) {
+        g_fg_cta[blockIdx.x * 4 + 0] = fg_smid(); g_fg_cta[blockIdx.x * 4 + 1] = fg_globaltimer(); g_fg_cta[blockIdx.x * 4 + 3] = (unsigned long long)my_tiles;
+    }
 
     if (warp == 0) {
         // ---------------- weight producer: [B hi ; B lo] of every k-block through a FG_LB-deep ring
         if (lane == 0) {
+            if constexpr (TCTAIL) {
+                // resident tail operands: layer l, k-block kb -> [W_l hi ; W_l lo] columns kb*32 .. kb*32+31 (128 rows x 128 B)
+                mbar_arrive_expect_tx(&tail_bars[0], (uint32_t)(tw.n_tail * FT_TAIL_B_BYTES));
+                for (int l = 0; l < tw.n_tail; ++l)
+                    for (int kb = 0; kb < 2; ++kb) {
+                        uint8_t* st = t_base + (size_t)(l * 2 + kb) * FG_B_BYTES;
+                        tma_load_2d(st, &tmThi, &tail_bars[0], kb * TC_BLOCK_K, l * TW_H);
+                        tma_load_2d(st + FG_B_BYTES / 2, &tmTlo, &tail_bars[0], kb * TC_BLOCK_K, l * TW_H);
+                    }
+            }
             long long w_b = 0;
             for (uint32_t g = 0; g < G; ++g) {
                 const int s = g % FG_LB, kb = g % nkb;
@@ -644,19 +675,47 @@ deepfm_fwd_fused8_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid
             const uint32_t idesc = make_idesc_tf32(TC_BLOCK_M, 2 * FG_N);
             uint32_t g = 0;
             long long w_fb = 0, w_op = 0, w_acc = 0, w_is = 0;
+            // TCTAIL: tail steps are issued in (tile, layer) order as soon as the epilogue warps have written the operand
+            // (tail_bars[1]); between k-blocks of the running tile without blocking, and blocking before an accumulator
+            // buffer is re-used (tile t + 2 needs tile t's tail finished) and after the last tile.
+            int tl_t = 0, tl_l = 0; uint32_t tl_n = 0;
+            auto tail_step = [&](bool block) -> bool {
+                if (!block && !mbar_test(&tail_bars[1], tl_n & 1u)) return false;
+                mbar_wait(&tail_bars[1], tl_n & 1u);
+                if (tl_n == 0) mbar_wait(&tail_bars[0], 0u);               // resident tail operands have landed
+                tc_fence_after();
+                const uint32_t d_t = tmem_base + ((uint32_t)tl_t & 1u) * ACC_STRIDE;
+                const uint32_t tb = smem_u32(t_base + (size_t)tl_l * FT_TAIL_B_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < TW_H / TC_UMMA_K; ++kk) {
+                    const uint64_t db = make_kmajor_sw128_desc(tb + (uint32_t)(kk >> 2) * FG_B_BYTES + (uint32_t)(kk & 3) * TC_UMMA_K * 4);
+                    umma_tf32_ts(d_t, tmem_base + TAIL_A + 64u + kk * TC_UMMA_K, db, idesc, kk > 0 ? 1u : 0u);
+                    umma_tf32_ts(d_t, tmem_base + TAIL_A + kk * TC_UMMA_K, db, idesc, 1u);
+                }
+                umma_commit(&tail_bars[2]);
+                ++tl_n;
+                if (++tl_l == tw.n_tail) { tl_l = 0; ++tl_t; }
+                return true;
+            };
             for (int t = 0; t < my_tiles; ++t) {
                 const uint32_t acc = (uint32_t)t & 1u;
                 const long long c0 = FG_T();
+                if constexpr (TCTAIL) { while (tl_t + 2 <= t) tail_step(true); }
                 mbar_wait(&tmem_empty[acc], (((uint32_t)t >> 1) & 1u) ^ 1u);
                 w_acc += FG_T() - c0;
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
                 for (int kb = 0; kb < nkb; ++kb, ++g) {
-                    const int s = g % FG_LB, o = g % FG_OP;
+                    const int s = g % FG_LB, o = g % OPN;
+                    if constexpr (TCTAIL) { if (tl_t < t) tail_step(false); }
                     const long long c1 = FG_T();
                     mbar_wait(&full_b[s], (g / FG_LB) & 1u);
                     const long long c2 = FG_T();
-                    mbar_wait(&ready_op[o], (g / FG_OP) & 1u);
+                    if constexpr (TCTAIL) {
+                        // do not sit on the operand barrier while a tail layer of the previous tile becomes ready
+                        while (!mbar_test(&ready_op[o], (g / OPN) & 1u)) { if (tl_t < t) tail_step(false); }
+                    }
+                    mbar_wait(&ready_op[o], (g / OPN) & 1u);
                     const long long c3 = FG_T();
                     w_fb += c2 - c1; w_op += c3 - c2;
                     tc_fence_after();
@@ -674,6 +733,7 @@ deepfm_fwd_fused8_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid
                 }
                 umma_commit(&tmem_full[acc]);
             }
+            if constexpr (TCTAIL) { while (tl_t < my_tiles) tail_step(true); }
             if (trace) { g_fg_trace[4] = (unsigned long long)w_fb; g_fg_trace[5] = (unsigned long long)w_op; g_fg_trace[6] = (unsigned long long)w_acc; g_fg_trace[7] = (unsigned long long)w_is; }
         }
     } else if (warp < 2 + F8_GW) {
@@ -757,7 +817,7 @@ deepfm_fwd_fused8_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid
 #pragma unroll
         for (int j = 0; j < 16; ++j) fs[j] = 0.f;
         uint32_t g = 0;
-        long long w_cp = 0, w_eo = 0, w_wk = 0;
+        long long w_cp = 0, w_eo = 0, w_wk = 0, w_p0 = 0, w_p1 = 0, w_p2 = 0, w_p3 = 0;
         const bool store_x = p.x != nullptr;
         for (int t = 0; t < my_tiles; ++t) {
             const int mt = ((int)blockIdx.x + t * (int)gridDim.x) * TC_BLOCK_M;
@@ -774,6 +834,7 @@ deepfm_fwd_fused8_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid
                     if (col < (int)p.ldx) tma_store_2d(&tmX, stg, col, mt + wrow0);      // rows >= M / columns >= ldx are clipped by the TMA unit
                     bulk_commit();
                 }
+                const long long c1a = FG_T();
                 float4 v[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const float4*>(stg + lane * 64 + ((j ^ sw) << 4));
@@ -794,9 +855,9 @@ deepfm_fwd_fused8_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid
                     h[4 * j + 2] = __float_as_uint(qv.z) & 0xFFFFE000u; l[4 * j + 2] = __float_as_uint(qv.z - __uint_as_float(h[4 * j + 2]));
                     h[4 * j + 3] = __float_as_uint(qv.w) & 0xFFFFE000u; l[4 * j + 3] = __float_as_uint(qv.w - __uint_as_float(h[4 * j + 3]));
                 }
-                const int o = g % FG_OP;
+                const int o = g % OPN;
                 const long long c2 = FG_T();
-                mbar_wait(&empty_op[o], ((g / FG_OP) & 1u) ^ 1u);
+                mbar_wait(&empty_op[o], ((g / OPN) & 1u) ^ 1u);
                 const long long c3 = FG_T();
                 tc_fence_after();
                 const uint32_t ta = tmem_base + A_COL + (uint32_t)o * 64u + ((uint32_t)wrow0 << 16) + (uint32_t)half * 16u;
@@ -804,11 +865,15 @@ deepfm_fwd_fused8_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid
                 tmem_st16(ta + 32u, l);
                 tmem_st_wait();
                 tc_fence_before();
+                const long long c4 = FG_T();
                 if (lane == 0) bulk_wait_read<1>();     // the store of k-block g - 1 has finished reading its stage ...
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ready_op[o]);
+                const long long c5 = FG_T();
                 issue();                                // ... which the requests of k-block g + LA - 1 now refill
-                w_cp += c1 - c0; w_eo += c3 - c2; w_wk += (c2 - c1) + (FG_T() - c3);
+                const long long c6 = FG_T();
+                w_cp += c1 - c0; w_eo += c3 - c2; w_wk += (c2 - c1) + (c6 - c3);
+                w_p0 += c1a - c1; w_p1 += c2 - c1a; w_p2 += c4 - c3; w_p3 += c6 - c5;
             }
             // FM second order of this sample: 0.5 * (sum_d s_d^2 - sum_{f,d} e^2); the two field halves meet in shared memory,
             // the half-0 thread finishes and hands the value to the tail
@@ -841,7 +906,10 @@ deepfm_fwd_fused8_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid
         }
         fg_wait<0>();
         if (lane == 0) bulk_wait_all<0>();
-        if (trace && gw == 0 && lane == 0) { g_fg_trace[1] = (unsigned long long)w_cp; g_fg_trace[2] = (unsigned long long)w_eo; g_fg_trace[3] = (unsigned long long)w_wk; }
+        if (trace && gw == 0 && lane == 0) {
+            g_fg_trace[1] = (unsigned long long)w_cp; g_fg_trace[2] = (unsigned long long)w_eo; g_fg_trace[3] = (unsigned long long)w_wk;
+            g_fg_trace[12] = (unsigned long long)w_p0; g_fg_trace[13] = (unsigned long long)w_p1; g_fg_trace[14] = (unsigned long long)w_p2; g_fg_trace[15] = (unsigned long long)w_p3;
+        }
     } else {
         // ---------------- epilogue warps: layer-1 epilogue -> h1 (HBM + shared memory) -> tower tail (tower_tile.cuh)
         const int quarter = warp & 3;
@@ -850,6 +918,94 @@ deepfm_fwd_fused8_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid
         const int et = threadIdx.x - (2 + F8_GW) * 32;
         auto epi_sync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
         float loss_acc = 0.f;
+        if constexpr (TCTAIL) {
+            const float tw_bo = tw.b_out != nullptr ? __ldg(tw.b_out) : 0.f;
+            // Round r = 0 .. n_tail of a tile: read the accumulator of layer r (r = 0: layer 1; both stacked halves), add the
+            // bias, ReLU, store the activation row piece for backward, and either hand it back to the tensor core as the
+            // next layer's operand (hi | lo in tensor memory) or, after the last layer, fold it into the output row-dot.
+            // Thread = (row, half): the two warps of a lane quarter own columns {half*16 .. +15} and {32 + half*16 .. +15}.
+            const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+            const int L = tw.n_tail;
+            uint32_t n_out = 0;                                   // tail_bars[2] phases consumed
+            for (int t = 0; t < my_tiles; ++t) {
+                const int m0 = ((int)blockIdx.x + t * (int)gridDim.x) * TC_BLOCK_M;
+                const uint32_t acc = (uint32_t)t & 1u;
+                const int m = m0 + row;
+                const long long q0 = FG_T();
+                mbar_wait(&tmem_full[acc], ((uint32_t)t >> 1) & 1u);
+                tc_fence_after();
+                const long long q1 = FG_T();
+                const uint32_t d_acc = tmem_base + acc * ACC_STRIDE + lane_addr;
+                float headp = 0.f;
+                for (int r = 0; r <= L; ++r) {
+                    if (r > 0) { mbar_wait(&tail_bars[2], n_out & 1u); ++n_out; tc_fence_after(); }
+                    const float* bias = r == 0 ? p.bias1 : tw.b[r - 1];
+                    float* hout = r == 0 ? p.h1 : tw.h[r - 1];
+                    const long long ldh = r == 0 ? p.ldh1 : (long long)TW_H;
+                    for (int c0 = half * 16; c0 < FG_N; c0 += 32) {
+                        uint32_t a0[16], a1[16];
+                        tmem_ld16(d_acc + (uint32_t)c0, a0);
+                        tmem_ld16(d_acc + (uint32_t)(FG_N + c0), a1);
+                        float v[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            v[j] = fmaxf(__uint_as_float(a1[j]) + __uint_as_float(a0[j]) + __ldg(bias + c0 + j), 0.f);
+                        if (m < p.M) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4)
+                                stg_f4(hout + (size_t)m * ldh + c0 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                        }
+                        if (r < L) {
+                            uint32_t hi[16], lo[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                hi[j] = __float_as_uint(v[j]) & 0xFFFFE000u;
+                                lo[j] = __float_as_uint(v[j] - __uint_as_float(hi[j]));
+                            }
+                            tmem_st16(tmem_base + TAIL_A + lane_addr + (uint32_t)c0, hi);
+                            tmem_st16(tmem_base + TAIL_A + 64u + lane_addr + (uint32_t)c0, lo);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) headp = fmaf(v[j], __ldg(tw.w_out + c0 + j), headp);
+                        }
+                    }
+                    if (r < L) {
+                        tmem_st_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tail_bars[1]);    // 8 arrivals: the operand of tail layer r is complete
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);     // every read of this accumulator buffer is done
+                const long long q2 = FG_T();
+                mbar_wait(&fm_ready[t % FG_FM_BUF], ((uint32_t)t / FG_FM_BUF) & 1u);
+                float* head_part = tw_As;                         // [128] partial row-dots of the half-1 warps
+                if (half == 1) head_part[row] = headp;
+                epi_sync();
+                if (half == 0 && m < p.M) {
+                    const float z = headp + head_part[row] + tw_bo + fm_tile[(t % FG_FM_BUF) * TC_BLOCK_M + row];
+                    tw.logit[m] = z;
+                    if (tw.pred != nullptr) {
+                        const float qq = 1.f / (1.f + expf(-z));
+                        tw.pred[m] = qq;
+                        if (tw.label != nullptr) {
+                            const float y = __ldg(tw.label + m);
+                            const float pe = qq + tw.eps;
+                            const float l1 = fmaxf(logf(pe), -100.f);
+                            const float l0 = fmaxf(logf(1.f - pe), -100.f);
+                            loss_acc += -(y * l1 + (1.f - y) * l0);
+                        }
+                    }
+                }
+                epi_sync();                                       // head_part is free for the next tile
+                if (trace && et == 0) {
+                    g_fg_trace[8] += (unsigned long long)(q1 - q0); g_fg_trace[9] += (unsigned long long)(q2 - q1);
+                    g_fg_trace[10] += (unsigned long long)(FG_T() - q2);
+                }
+            }
+        } else {
         tower_load_weights_t<FG_EPI_WARPS * 32>(tw, tw_Bs, et);
         const float4 tw_wo = ldg_f4(tw.w_out + (et & 15) * 4);
         const float tw_bo = tw.b_out != nullptr ? __ldg(tw.b_out) : 0.f;
@@ -890,12 +1046,14 @@ deepfm_fwd_fused8_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid
                 g_fg_trace[10] += (unsigned long long)(FG_T() - q2);
             }
         }
+        }
         if (tw.loss != nullptr) tw_loss[et] = loss_acc;
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
     if (trace && threadIdx.x == 0) g_fg_trace[0] = (unsigned long long)(clock64() - t_start);
+    if (g_fg_trace_on != 0 && threadIdx.x == 0 && blockIdx.x < 256) g_fg_cta[blockIdx.x * 4 + 2] = fg_globaltimer();
     if (tw.loss != nullptr && warp == 0) {
         // deterministic mean BCE: 256 epilogue partials -> per-CTA partial -> the last CTA adds them in index order
         float s = 0.f;
@@ -922,10 +1080,10 @@ deepfm_fwd_fused8_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid
     }
 }
 
-static size_t f8_smem_bytes(int la, int n_tail) {
-    return (size_t)FG_LB * FG_B_BYTES + (size_t)la * F8_STAGE_BYTES + (size_t)la * F8_GW * 32 * 8 +
-           (2 * FG_LB + 2 * FG_OP + 4 + FG_FM_BUF) * 8 + 16 + FG_FM_BUF * TC_BLOCK_M * 4 + (size_t)(TC_BLOCK_M * F8_FMX_LD) * 4 +
-           (size_t)(TC_BLOCK_M * TW_LDA + n_tail * TW_H * TW_H + 256) * 4 + 1024;
+static size_t f8_smem_bytes(int la, int n_tail, bool tctail) {
+    return (size_t)FG_LB * FG_B_BYTES + (tctail ? (size_t)n_tail * FT_TAIL_B_BYTES : 0) + (size_t)la * F8_STAGE_BYTES + (size_t)la * F8_GW * 32 * 8 +
+           (2 * FG_LB + 2 * FG_OP + 4 + FG_FM_BUF + 4) * 8 + 16 + FG_FM_BUF * TC_BLOCK_M * 4 + (size_t)(TC_BLOCK_M * F8_FMX_LD) * 4 +
+           (tctail ? (size_t)(TC_BLOCK_M + 256) * 4 : (size_t)(TC_BLOCK_M * TW_LDA + n_tail * TW_H * TW_H + 256) * 4) + 1024;
 }
 
 static size_t fg_smem_bytes(int la, int n_tail, bool tctail = false) {
@@ -940,6 +1098,11 @@ static size_t fg_smem_bytes(int la, int n_tail, bool tctail = false) {
 }  // namespace rpb
 
 using namespace rpb;
+
+RPB_API int rpb_debug_fused_cta_times(uint64_t* out1024) {
+    if (out1024 == nullptr) return RPB_ERR_BAD_ARG;
+    return (int)cudaMemcpyFromSymbol(out1024, g_fg_cta, sizeof(unsigned long long) * 1024);
+}
 
 RPB_API int rpb_debug_fused_trace(uint64_t* out16, int enable) {
     int on = enable != 0;
@@ -997,28 +1160,36 @@ RPB_API int rpb_deepfm_fwd_fused(const RpbGatherDesc* g, const float* W1, const 
     const int m_tiles = ceil_div(d->M, TC_BLOCK_M);
     const int grid = min(m_tiles, 148);
     const size_t cap = 227 * 1024;
-    // tail layers on tcgen05 (opt-in, see FT_OP): needs the resident tail operands next to >= 3 gather stages
-    const bool tctail = g_fused_tc_tail != 0 && fg_smem_bytes(3, d->n_tail, true) <= cap;
-    if (g_fused_gather_warps == 8 && !tctail) {
-        // default: 8 gather warps, x stored by TMA ([32 rows x 16 columns] boxes, SWIZZLE_64B) — deepfm_fwd_fused8_kernel
+    if (g_fused_gather_warps == 8) {
+        // default: 8 gather warps, x stored by TMA ([32 rows x 16 columns] boxes, SWIZZLE_64B) — deepfm_fwd_fused8_kernel;
+        // tower-tail layers on tcgen05 unless rpb_set_option("fused_tc_tail", 0)
+        const bool tc8 = g_fused_tc_tail != 0 && f8_smem_bytes(3, d->n_tail, true) <= cap;
         CUtensorMap tmX = tmBhi;                       // placeholder when x is not materialised
         if (p.x != nullptr) {
             rc = tc_make_map2d(&tmX, p.x, p.M, p.ldx, p.ldx, 16, 32, 64);
             if (rc != 0) return rc;
         }
-        auto launch8 = [&](auto la_tag, auto sh_tag) -> int {
+        CUtensorMap tmThi = tmBhi, tmTlo = tmBlo;      // placeholders when the tail runs on the CUDA cores
+        if (tc8) {
+            rc = tc_prepare_tail_weights(tw.W, d->n_tail, &tmThi, &tmTlo, st, 0, 6);
+            if (rc != 0) return rc;
+        }
+        auto launch8 = [&](auto la_tag, auto sh_tag, auto tc_tag) -> int {
             constexpr int LA = decltype(la_tag)::value;
-            constexpr bool SH = decltype(sh_tag)::value;
-            const size_t smem = f8_smem_bytes(LA, d->n_tail);
-            cudaError_t e = cudaFuncSetAttribute(deepfm_fwd_fused8_kernel<LA, SH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            constexpr bool SH = decltype(sh_tag)::value, TC = decltype(tc_tag)::value;
+            const size_t smem = f8_smem_bytes(LA, d->n_tail, TC);
+            cudaError_t e = cudaFuncSetAttribute(deepfm_fwd_fused8_kernel<LA, SH, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
-            deepfm_fwd_fused8_kernel<LA, SH><<<grid, F8_THREADS, smem, st>>>(tmBhi, tmBlo, tmX, p, tw, m_tiles);
+            deepfm_fwd_fused8_kernel<LA, SH, TC><<<grid, F8_THREADS, smem, st>>>(tmBhi, tmBlo, tmThi, tmTlo, tmX, p, tw, m_tiles);
             return (int)cudaGetLastError();
         };
-        auto pick8 = [&](auto la_tag) -> int { return sharded ? launch8(la_tag, std::true_type{}) : launch8(la_tag, std::false_type{}); };
+        auto pick8 = [&](auto la_tag) -> int {
+            if (tc8) return sharded ? launch8(la_tag, std::true_type{}, std::true_type{}) : launch8(la_tag, std::false_type{}, std::true_type{});
+            return sharded ? launch8(la_tag, std::true_type{}, std::false_type{}) : launch8(la_tag, std::false_type{}, std::false_type{});
+        };
         const int want = g_fused_ring > 0 ? g_fused_ring : 6;
         for (int la = want; la >= 3; --la) {
-            if (f8_smem_bytes(la, d->n_tail) > cap) continue;
+            if (f8_smem_bytes(la, d->n_tail, tc8) > cap) continue;
             switch (la) {
                 case 6: return pick8(std::integral_constant<int, 6>{});
                 case 5: return pick8(std::integral_constant<int, 5>{});
@@ -1028,6 +1199,8 @@ RPB_API int rpb_deepfm_fwd_fused(const RpbGatherDesc* g, const float* W1, const 
         }
         return RPB_ERR_UNSUPPORTED;
     }
+    // round-1 kernel (rpb_set_option("fused_gather_warps", 4)): tail layers on tcgen05 opt-in, see FT_OP
+    const bool tctail = g_fused_tc_tail != 0 && fg_smem_bytes(3, d->n_tail, true) <= cap;
     CUtensorMap tmThi = tmBhi, tmTlo = tmBlo;          // placeholders when the tail runs on the CUDA cores
     if (tctail) {
         rc = tc_prepare_tail_weights(tw.W, d->n_tail, &tmThi, &tmTlo, st, 0, 6);

@@ -129,18 +129,20 @@ __device__ __forceinline__ float uniform01(unsigned long long seed, unsigned lon
 // y = x * keep / (1-p)  (in place allowed)
 __global__ void __launch_bounds__(256)
 dropout_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float p, float inv_keep,
-                   unsigned long long seed) {
+                   unsigned long long seed, const unsigned long long* __restrict__ epoch) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (epoch != nullptr) seed += __ldg(epoch) * 0xD1B54A32D192ED03ull;      // device-side step counter (CUDA-graph replays)
     y[i] = (uniform01(seed, (unsigned long long)i) >= p) ? x[i] * inv_keep : 0.f;
 }
 
 // dx = dy * keep/(1-p) * (relu_out ? relu_out > 0 : 1)
 __global__ void __launch_bounds__(256)
 dropout_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ relu_out, float* __restrict__ dx,
-                   long long n, float p, float inv_keep, unsigned long long seed) {
+                   long long n, float p, float inv_keep, unsigned long long seed, const unsigned long long* __restrict__ epoch) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (epoch != nullptr) seed += __ldg(epoch) * 0xD1B54A32D192ED03ull;
     float v = (uniform01(seed, (unsigned long long)i) >= p) ? dy[i] * inv_keep : 0.f;
     if (relu_out != nullptr && !(relu_out[i] > 0.f)) v = 0.f;
     dx[i] = v;
@@ -150,19 +152,19 @@ dropout_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ relu_
 
 using namespace rpb;
 
-RPB_API int rpb_dropout_fwd(const float* x, float* y, int64_t n, float p, uint64_t seed, void* stream) {
+RPB_API int rpb_dropout_fwd(const float* x, float* y, int64_t n, float p, uint64_t seed, const uint64_t* epoch, void* stream) {
     if (x == nullptr || y == nullptr || n <= 0 || p < 0.f || p >= 1.f) return RPB_ERR_BAD_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    dropout_fwd_kernel<<<ceil_div(n, 256), 256, 0, st>>>(x, y, n, p, 1.f / (1.f - p), seed);
+    dropout_fwd_kernel<<<ceil_div(n, 256), 256, 0, st>>>(x, y, n, p, 1.f / (1.f - p), seed, reinterpret_cast<const unsigned long long*>(epoch));
     RPB_LAUNCH_CHECK();
     return 0;
 }
 
 RPB_API int rpb_dropout_bwd(const float* dy, const float* relu_out, float* dx, int64_t n, float p, uint64_t seed,
-                            void* stream) {
+                            const uint64_t* epoch, void* stream) {
     if (dy == nullptr || dx == nullptr || n <= 0 || p < 0.f || p >= 1.f) return RPB_ERR_BAD_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    dropout_bwd_kernel<<<ceil_div(n, 256), 256, 0, st>>>(dy, relu_out, dx, n, p, 1.f / (1.f - p), seed);
+    dropout_bwd_kernel<<<ceil_div(n, 256), 256, 0, st>>>(dy, relu_out, dx, n, p, 1.f / (1.f - p), seed, reinterpret_cast<const unsigned long long*>(epoch));
     RPB_LAUNCH_CHECK();
     return 0;
 }

@@ -109,6 +109,37 @@ def _err_record(device) -> torch.Tensor:
     return _ERR[key]
 
 
+_DROPOUT_EPOCH = {}
+_dropout_calls = 0
+
+
+def _dropout_epoch(device) -> torch.Tensor:
+    """Per-device int64 step counter the dropout kernels mix into their seed when they RUN.  The host-drawn seed of a call is
+    baked into a captured CUDA graph; `advance_dropout_epoch()` (inside the captured step: runtime.GraphedStep) makes every
+    replay draw a fresh mask, forward and backward of one step seeing the same value."""
+    global _dropout_calls
+    _dropout_calls += 1
+    key = torch.device(device).index or 0
+    t = _DROPOUT_EPOCH.get(key)
+    if t is None:
+        t = _DROPOUT_EPOCH[key] = torch.zeros(1, dtype=torch.int64, device=device)
+    return t
+
+
+def dropout_calls() -> int:
+    """Number of dropout kernel launches so far (GraphedStep: does the step need the epoch increment?)."""
+    return _dropout_calls
+
+
+def advance_dropout_epoch(device=None):
+    dev = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+    key = dev.index or 0
+    t = _DROPOUT_EPOCH.get(key)
+    if t is None:
+        t = _DROPOUT_EPOCH[key] = torch.zeros(1, dtype=torch.int64, device=dev)
+    t.add_(1)
+
+
 def check_index_errors(device=None, sync: bool = True):
     """Raise IndexError if any gather since the last check saw an index outside [0, vocab_size]
     (the reference raises IndexError from aten::embedding on CPU, models/layers/embedding.py:61-62)."""
@@ -535,7 +566,7 @@ def _mlp_fwd(cfg, x, params, addend=None):
         if p > 0.0:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
             yd = torch.empty_like(y)
-            check(lib.rpb_dropout_fwd(_ptr(y), _ptr(yd), y.numel(), p, seed, st), 'rpb_dropout_fwd')
+            check(lib.rpb_dropout_fwd(_ptr(y), _ptr(yd), y.numel(), p, seed, _dropout_epoch(y.device).data_ptr(), st), 'rpb_dropout_fwd')
             _count()
             pre_drop.append(y)
             seeds.append(seed)
@@ -594,7 +625,7 @@ def _mlp_bwd(cfg, acts, pre_drop, seeds, params, g, need_dx_input, layer0_hook=N
         p = drops[j]
         out = torch.empty_like(dh)
         check(lib.rpb_dropout_bwd(_ptr(dh), _ptr(pre_drop[j]) if relu[j] else None, _ptr(out), dh.numel(), p,
-                                  seeds[j], st), 'rpb_dropout_bwd')
+                                  seeds[j], _dropout_epoch(dh.device).data_ptr(), st), 'rpb_dropout_bwd')
         _count()
         return out
 
@@ -1580,7 +1611,7 @@ class _Dropout(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, p, seed):
         y = torch.empty_like(x)
-        check(_lib.load().rpb_dropout_fwd(_ptr(x), _ptr(y), x.numel(), p, seed, _stream()), 'rpb_dropout_fwd')
+        check(_lib.load().rpb_dropout_fwd(_ptr(x), _ptr(y), x.numel(), p, seed, _dropout_epoch(x.device).data_ptr(), _stream()), 'rpb_dropout_fwd')
         _count()
         ctx.p, ctx.seed = p, seed
         return y
@@ -1589,7 +1620,7 @@ class _Dropout(torch.autograd.Function):
     def backward(ctx, g):
         g = g.contiguous()
         dx = torch.empty_like(g)
-        check(_lib.load().rpb_dropout_bwd(_ptr(g), None, _ptr(dx), g.numel(), ctx.p, ctx.seed, _stream()), 'rpb_dropout_bwd')
+        check(_lib.load().rpb_dropout_bwd(_ptr(g), None, _ptr(dx), g.numel(), ctx.p, ctx.seed, _dropout_epoch(g.device).data_ptr(), _stream()), 'rpb_dropout_bwd')
         _count()
         return dx, None, None
 

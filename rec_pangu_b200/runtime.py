@@ -80,11 +80,16 @@ class GraphedStep:
         self.loss = self.pred = None
         self.launches_per_step = 0
         from . import ops
+        self._advance_epoch = False
+        d0 = ops.dropout_calls()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(warmup):
                 self._eager()
+        # a step that draws dropout masks starts by advancing the device-side epoch the kernels mix into their seeds: the
+        # host-drawn seeds are frozen by the capture, the epoch is not (same trick as FusedAdam's device step counter)
+        self._advance_epoch = ops.dropout_calls() > d0
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         n0 = ops.launch_count()
@@ -98,6 +103,9 @@ class GraphedStep:
         self.launches_per_step = ops.launch_count() - n0
 
     def _eager(self):
+        if self._advance_epoch:
+            from . import ops
+            ops.advance_dropout_epoch(self.batch.idx.device)
         join = None
         if self.zero_first:
             main = torch.cuda.current_stream()

@@ -50,6 +50,42 @@ def make_batch(enc, B, seed=1029, labels=('label',), device='cpu'):
     return {k: v.to(device) for k, v in data.items()}
 
 
+class capture_relu_inputs:
+    """Records the input of every ReLU the oracle evaluates inside the `with` block (oracle/restatement.py uses F.relu only).
+    Entries are CPU tensors whose first dimension is the batch."""
+
+    def __enter__(self):
+        import torch.nn.functional as F
+        self._F, self._orig, self.inputs = F, F.relu, []
+
+        def relu(x, *a, **k):
+            self.inputs.append(x.detach())
+            return self._orig(x, *a, **k)
+        F.relu = relu
+        return self
+
+    def __exit__(self, *exc):
+        self._F.relu = self._orig
+        return False
+
+
+def kink_adjacent_samples(relu_inputs, tau=5e-6):
+    """Samples that have at least one ReLU pre-activation within `tau` of the kink.  The CUDA path reproduces every
+    pre-activation to ~1e-6 or better (3xTF32 products, fp32 sums in another order), so only for these samples can the GPU take the other
+    ReLU branch than the CPU oracle — which flips that ONE sample's whole gradient contribution on and off: an
+    ill-conditioning of the reference's own formulation at that input, not an arithmetic error.  Everything else in the
+    batch is smooth.  Returns a bool mask [B]."""
+    mask = None
+    for z in relu_inputs:
+        m = (z.abs() < tau).reshape(z.shape[0], -1).any(dim=1)
+        mask = m if mask is None else (mask | m)
+    return mask
+
+
+def drop_samples(data, keep):
+    return {k: v[keep.to(v.device)] for k, v in data.items()}
+
+
 def assert_close_rel(a, b, tol, what='', atol=1e-7, outlier_frac=0.0):
     """|a-b| <= tol * max|b| + atol element-wise, for batch-reduced gradients whose fp32 summation order (atomics /
     tiling) differs from the sequential CPU oracle.  `outlier_frac` tolerates a small fraction of elements beyond the

@@ -1,0 +1,403 @@
+// exp_rowfetch — how fast can a persistent kernel (1 CTA / SM, 8 fetch warps) pull 1.7 M random 64-byte table rows into
+// shared memory?  Config-2 shape: 26 tables x 1M rows x 16 fp32, batch 65536 -> 128-row tiles x 26 fields.
+//   V0  LDGSTS (cp.async 16 B), 4 lanes per row, ring of LA field-blocks per warp       (what deepfm_fwd_fused8 does)
+//   V1  TMA tile::gather4 — 4 rows per instruction, 8 lanes of a warp issue one each, mbarrier completion
+//   V2  cp.async.bulk 64 B per row, one per lane, mbarrier completion
+//   V3  LDG.128 (4 lanes per row) into registers, U field-blocks in flight, STS afterwards
+// Each warp owns 32 rows of the tile and one field parity (as in the fused kernel); consumption = LDS.128 of the own row
+// + a running sum (so nothing is optimised away).  Prints microseconds per launch (CUDA events, 20 launches).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/exp/exp_rowfetch tools/exp/exp_rowfetch.cu -lcuda
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+#include <vector>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
+
+constexpr int F = 26, D = 16, V = 1000001, B = 65536, TILE = 128, NT = 256, NW = 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) break;
+        if (clock64() - t0 > 2000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void cp16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global.L2::64B [%0], [%1], 16;" :: "r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ void tma_gather4(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int r0, int r1, int r2, int r3) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+__device__ __forceinline__ void bulk64(void* dst, const void* src, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 64, [%2];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 :: "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* map, const void* smem_src, int c0, int c1, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+                 :: "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp16_hint(void* dst, const void* src, uint64_t pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint.L2::64B [%0], [%1], 16, %2;" :: "r"(smem_u32(dst)), "l"(src), "l"(pol) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+
+struct Params {
+    const CUtensorMap* xmap;    // [B, 432] fp32, box {16, 32}, SWIZZLE_64B (MODE >= 4)
+    const float* tables[F];
+    const long long* idx[F];
+    float* out;                 // [B] sink
+    const CUtensorMap* maps;    // [F] in global memory
+    int m_tiles;
+};
+
+// per warp: ring of LA stages, one stage = its 32 rows x 64 B of one field; the warp walks fields half, half+2, ... of every tile
+template <int MODE, int LA>
+__global__ void __launch_bounds__(NT, 1) fetch_kernel(const __grid_constant__ Params p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* stage_base = smem;                                          // [LA][NW][32][64]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LA * NW * 2048); // [NW][LA]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp & 3, half = warp >> 2;
+    uint8_t* my_stage = stage_base + warp * 2048;
+    uint64_t* my_bar = bars + warp * LA;
+    if (lane == 0) for (int s = 0; s < LA; ++s) mbar_init(&my_bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    const int my_tiles = ((int)blockIdx.x < p.m_tiles) ? (p.m_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    constexpr int NKB = F / 2;
+    const int G = my_tiles * NKB;
+    const int sw = (lane >> 1) & 3;
+    float acc = 0.f;
+    const uint64_t pol_ef = policy_evict_first(), pol_el = policy_evict_last();
+    (void)pol_el;
+    int gi = 0, i_kb = 0, i_t = 0;
+    long long nid[4] = {0, 0, 0, 0};                 // ids of the NEXT field-block to request, loaded one issue() ahead
+    auto prefetch_ids = [&]() {
+        if (gi < G) {
+            const int m0 = ((int)blockIdx.x + i_t * (int)gridDim.x) * TILE + q * 32;
+            const int f = 2 * i_kb + half;
+            if constexpr (MODE == 0 || MODE >= 4) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) nid[i] = __ldg(p.idx[f] + m0 + i * 8 + (lane >> 2));
+            } else if constexpr (MODE == 1) {
+                if (lane < 8) {
+                    const longlong2 a = __ldg(reinterpret_cast<const longlong2*>(p.idx[f] + m0 + lane * 4));
+                    const longlong2 b = __ldg(reinterpret_cast<const longlong2*>(p.idx[f] + m0 + lane * 4 + 2));
+                    nid[0] = a.x; nid[1] = a.y; nid[2] = b.x; nid[3] = b.y;
+                }
+            } else if constexpr (MODE == 2) {
+                nid[0] = __ldg(p.idx[f] + m0 + lane);
+            }
+        }
+    };
+    auto issue = [&]() {
+        if (gi < G) {
+            const int f = 2 * i_kb + half, slot = gi % LA;
+            uint8_t* stg = my_stage + slot * (NW * 2048);
+            if constexpr (MODE == 0 || MODE >= 4) {
+                const int piece = lane & 3;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int rr = i * 8 + (lane >> 2);
+                    if constexpr (MODE == 5) cp16_hint(stg + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4), p.tables[f] + (size_t)nid[i] * 16 + piece * 4, pol_ef);
+                    else cp16(stg + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4), p.tables[f] + (size_t)nid[i] * 16 + piece * 4);
+                }
+            } else if constexpr (MODE == 1) {
+                if (lane == 0) mbar_expect_tx(&my_bar[slot], 2048);
+                __syncwarp();
+                if (lane < 8) tma_gather4(stg + lane * 256, p.maps + f, &my_bar[slot], 0, (int)nid[0], (int)nid[1], (int)nid[2], (int)nid[3]);
+            } else if constexpr (MODE == 2) {
+                if (lane == 0) mbar_expect_tx(&my_bar[slot], 2048);
+                __syncwarp();
+                bulk64(stg + lane * 64, p.tables[f] + (size_t)nid[0] * 16, &my_bar[slot]);
+            }
+        }
+        if constexpr (MODE == 0 || MODE >= 4) cp_commit();
+        ++gi; if (++i_kb == NKB) { i_kb = 0; ++i_t; }
+        prefetch_ids();
+    };
+    if constexpr (MODE != 3) prefetch_ids();
+    if constexpr (MODE == 3) {
+        // registers: U = LA field-blocks in flight, 4 float4 per lane each
+        float4 r[LA][4];
+        auto load = [&](int u, int g) {
+            const int t = g / NKB, kb = g % NKB;
+            const int m0 = ((int)blockIdx.x + t * (int)gridDim.x) * TILE + q * 32;
+            const int f = 2 * kb + half, piece = lane & 3;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int rr = i * 8 + (lane >> 2);
+                const long long id = __ldg(p.idx[f] + m0 + rr);
+                const float* src = p.tables[f] + (size_t)id * 16 + piece * 4;
+                asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.f32 {%0,%1,%2,%3}, [%4];"
+                             : "=f"(r[u][i].x), "=f"(r[u][i].y), "=f"(r[u][i].z), "=f"(r[u][i].w) : "l"(src));
+            }
+        };
+#pragma unroll
+        for (int u = 0; u < LA; ++u) if (u < G) load(u, u);
+        for (int g0 = 0; g0 < G; g0 += LA) {
+#pragma unroll
+            for (int u = 0; u < LA; ++u) {
+                const int g = g0 + u;
+                if (g < G) {
+                    const int piece = lane & 3;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int rr = i * 8 + (lane >> 2);
+                        *reinterpret_cast<float4*>(my_stage + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4)) = r[u][i];
+                    }
+                    if (g + LA < G) load(u, g + LA);
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 v = *reinterpret_cast<const float4*>(my_stage + lane * 64 + ((j ^ sw) << 4));
+                        acc += v.x + v.y + v.z + v.w;
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        for (int s = 0; s + 1 < LA; ++s) issue();
+        for (int g = 0; g < G; ++g) {
+            const int slot = g % LA;
+            if constexpr (MODE == 0) { cp_wait<LA - 2>(); __syncwarp(); }
+            else if constexpr (MODE >= 8) { cp_wait<LA - 2>(); __syncwarp(); }
+            else if constexpr (MODE >= 4) { cp_wait<LA - 2>(); asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); __syncwarp(); }
+            else mbar_wait(&my_bar[slot], (g / LA) & 1);
+            const uint8_t* stg = my_stage + slot * (NW * 2048);
+            if constexpr (MODE >= 4 && MODE < 8) {
+                if (lane == 0) {
+                    const int t = g / NKB, kb = g % NKB;
+                    const int m0 = ((int)blockIdx.x + t * (int)gridDim.x) * TILE + q * 32;
+                    if constexpr (MODE == 6) tma_store_2d_hint(p.xmap, stg, kb * 32 + half * 16, m0, pol_ef);
+                    else if constexpr (MODE == 7) tma_store_2d_hint(p.xmap, stg, kb * 32 + half * 16, m0, pol_el);
+                    else tma_store_2d(p.xmap, stg, kb * 32 + half * 16, m0);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = (MODE == 2) ? j : (j ^ sw);                 // MODE 2: linear rows (4-way bank conflict, measured as is)
+                const float4 v = *reinterpret_cast<const float4*>(stg + lane * 64 + (c << 4));
+                acc += v.x + v.y + v.z + v.w;
+            }
+            if constexpr (MODE >= 4 && MODE < 8) { if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+            if constexpr (MODE >= 8) {
+                float z = acc;
+#pragma unroll 1
+                for (int it = 0; it < (MODE == 8 ? 150 : 300); ++it) z = fmaf(z, 1.0001f, 0.5f);      // ~4 cycles per dependent FMA
+                acc = z;
+            }
+            __syncwarp();
+            issue();
+        }
+        if constexpr (MODE == 0 || MODE >= 4) cp_wait<0>();
+        if constexpr (MODE >= 4 && MODE < 8) { if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+    }
+    if (acc == 123.456f) p.out[blockIdx.x * NT + threadIdx.x] = acc;
+    if (blockIdx.x == 0 && threadIdx.x < 8) p.out[threadIdx.x] = acc;
+}
+
+
+// MODE 11: dedicated fetch warps.  NF warps do nothing but request rows (LDGSTS) for whole k-block stages (128 rows x 2 fields =
+// 16 KiB) and signal completion through cp.async.mbarrier.arrive.noinc; 8 consumer warps wait, read their own row and burn
+// WORK dependent FMAs per round (stand-in for the hi/lo split, tcgen05.st, FM sums ...).
+template <int NF, int LA, int WORK>
+__global__ void __launch_bounds__((NF + 8) * 32, 1) fetch_split_kernel(const __grid_constant__ Params p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* stage_base = smem;                                          // [LA][8][32][64]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + LA * 16384);     // [LA]
+    uint64_t* empty = full + LA;                                         // [LA]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) for (int s = 0; s < LA; ++s) { mbar_init(&full[s], NF * 32); mbar_init(&empty[s], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    const int my_tiles = ((int)blockIdx.x < p.m_tiles) ? (p.m_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    constexpr int NKB = F / 2;
+    const int G = my_tiles * NKB;
+    float acc = 0.f;
+    if (warp < NF) {
+        constexpr int PER = 32 / NF;                                     // LDGSTS instructions per lane and stage
+        long long nid[PER];
+        auto ids_of = [&](int g) {
+            const int t = g / NKB, kb = g % NKB;
+            const int m0 = ((int)blockIdx.x + t * (int)gridDim.x) * TILE;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                const int j = warp * PER + i, gw = j >> 2, rr = (j & 3) * 8 + (lane >> 2);
+                nid[i] = __ldg(p.idx[2 * kb + (gw >> 2)] + m0 + (gw & 3) * 32 + rr);
+            }
+        };
+        if (G > 0) ids_of(0);
+        for (int g = 0; g < G; ++g) {
+            const int slot = g % LA, kb = g % NKB;
+            mbar_wait(&empty[slot], ((g / LA) & 1) ^ 1);
+            uint8_t* stg = stage_base + slot * 16384;
+            const int piece = lane & 3;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                const int j = warp * PER + i, gw = j >> 2, rr = (j & 3) * 8 + (lane >> 2);
+                cp16(stg + gw * 2048 + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4), p.tables[2 * kb + (gw >> 2)] + (size_t)nid[i] * 16 + piece * 4);
+            }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(&full[slot])) : "memory");
+            if (g + 1 < G) ids_of(g + 1);
+        }
+        cp_wait<0>();
+    } else {
+        const int gw = warp - NF;
+        const int sw = (lane >> 1) & 3;
+        for (int g = 0; g < G; ++g) {
+            const int slot = g % LA;
+            mbar_wait(&full[slot], (g / LA) & 1);
+            const uint8_t* stg = stage_base + slot * 16384 + gw * 2048;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 v = *reinterpret_cast<const float4*>(stg + lane * 64 + ((j ^ sw) << 4));
+                acc += v.x + v.y + v.z + v.w;
+            }
+            __syncwarp();
+            if (lane == 0) { asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" :: "r"(smem_u32(&empty[slot])) : "memory"); }
+            float z = acc;
+#pragma unroll 1
+            for (int it = 0; it < WORK; ++it) z = fmaf(z, 1.0001f, 0.5f);
+            acc = z;
+        }
+    }
+    if (acc == 123.456f) p.out[blockIdx.x * 512 + threadIdx.x] = acc;
+    if (blockIdx.x == 0 && threadIdx.x >= NF * 32 && threadIdx.x < NF * 32 + 8) p.out[threadIdx.x - NF * 32] = acc;
+}
+
+template <int NF, int LA, int WORK>
+static void run_split(const Params& p, const char* name) {
+    const size_t smem = (size_t)LA * 16384 + 2 * LA * 8 + 64;
+    CK(cudaFuncSetAttribute(fetch_split_kernel<NF, LA, WORK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) fetch_split_kernel<NF, LA, WORK><<<148, (NF + 8) * 32, smem>>>(p);
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < 20; ++i) fetch_split_kernel<NF, LA, WORK><<<148, (NF + 8) * 32, smem>>>(p);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double us = ms * 1e3 / 20;
+    printf("%-44s NF=%d LA=%d WORK=%d  %7.1f us  (%.2f TB/s of rows+ids)\n", name, NF, LA, WORK, us, (double)B * F * 72 / us / 1e6);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+template <int MODE, int LA>
+static void run(const Params& p, const char* name) {
+    const size_t smem = (size_t)LA * NW * 2048 + NW * LA * 8 + 64;
+    CK(cudaFuncSetAttribute(fetch_kernel<MODE, LA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) fetch_kernel<MODE, LA><<<148, NT, smem>>>(p);
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < 20; ++i) fetch_kernel<MODE, LA><<<148, NT, smem>>>(p);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double us = ms * 1e3 / 20;
+    float h[8];
+    CK(cudaMemcpy(h, p.out, sizeof(h), cudaMemcpyDeviceToHost));
+    printf("%-44s LA=%d  %7.1f us  (%.2f TB/s of rows+ids)  acc0=%g\n", name, LA, us, (double)B * F * 72 / us / 1e6, h[0]);
+}
+
+int main() {
+    Params p{};
+    std::vector<float*> tabs(F);
+    std::vector<long long*> idxs(F);
+    std::vector<long long> h(B);
+    srand(1);
+    for (int f = 0; f < F; ++f) {
+        CK(cudaMalloc(&tabs[f], (size_t)V * D * 4));
+        CK(cudaMemset(tabs[f], 0, (size_t)V * D * 4));
+        std::vector<float> ones(16 * 1024, 1.0f);
+        CK(cudaMemcpy(tabs[f], ones.data(), ones.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&idxs[f], (size_t)B * 8));
+        for (int i = 0; i < B; ++i) h[i] = (long long)(((unsigned long long)rand() * 2147483648ull + rand()) % V);
+        CK(cudaMemcpy(idxs[f], h.data(), (size_t)B * 8, cudaMemcpyHostToDevice));
+        p.tables[f] = tabs[f]; p.idx[f] = idxs[f];
+    }
+    CK(cudaMalloc(&p.out, 148 * NT * 4 + 64));
+    p.m_tiles = B / TILE;
+    // tensor maps for gather4: [V rows, 16 cols], box {16, 1}, SWIZZLE_64B
+    void* fnp = nullptr; cudaDriverEntryPointQueryResult qr;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fnp, cudaEnableDefault, &qr));
+    EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(fnp);
+    std::vector<CUtensorMap> maps(F);
+    for (int f = 0; f < F; ++f) {
+        cuuint64_t gdim[2] = {16, (cuuint64_t)V}; cuuint64_t gstr[1] = {64}; cuuint32_t box[2] = {16, 1}; cuuint32_t es[2] = {1, 1};
+        CUresult r = enc(&maps[f], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, tabs[f], gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); return 1; }
+    }
+    float* xbuf;
+    CK(cudaMalloc(&xbuf, (size_t)B * 432 * 4));
+    CUtensorMap xm;
+    {
+        cuuint64_t gdim[2] = {432, (cuuint64_t)B}; cuuint64_t gstr[1] = {432 * 4}; cuuint32_t box[2] = {16, 32}; cuuint32_t es[2] = {1, 1};
+        CUresult r = enc(&xm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, xbuf, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { printf("encode x failed %d\n", (int)r); return 1; }
+    }
+    CUtensorMap* dxm;
+    CK(cudaMalloc(&dxm, sizeof(CUtensorMap)));
+    CK(cudaMemcpy(dxm, &xm, sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    p.xmap = dxm;
+    CUtensorMap* dmaps;
+    CK(cudaMalloc(&dmaps, F * sizeof(CUtensorMap)));
+    CK(cudaMemcpy(dmaps, maps.data(), F * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    p.maps = dmaps;
+    run<0, 3>(p, "V0 LDGSTS 16 B x 4 lanes/row");
+    run<0, 5>(p, "V0 LDGSTS 16 B x 4 lanes/row");
+    run<0, 8>(p, "V0 LDGSTS 16 B x 4 lanes/row");
+    run<4, 3>(p, "V4 LDGSTS + TMA x store (64 B boxes)");
+    run<4, 5>(p, "V4 LDGSTS + TMA x store (64 B boxes)");
+    run<6, 5>(p, "V6 = V4, x store evict_first");
+    run<7, 5>(p, "V7 = V4, x store evict_last");
+    run<8, 5>(p, "V8 = V0 + ~600 cycles of dependent ALU work per round");
+    run<9, 5>(p, "V9 = V0 + ~1200 cycles of dependent ALU work per round");
+    run<9, 8>(p, "V9 = V0 + ~1200 cycles of dependent ALU work per round");
+    run_split<4, 4, 0>(p, "V11 dedicated fetch warps");
+    run_split<4, 4, 150>(p, "V11 dedicated fetch warps");
+    run_split<4, 8, 150>(p, "V11 dedicated fetch warps");
+    run_split<2, 8, 150>(p, "V11 dedicated fetch warps");
+    run_split<8, 8, 150>(p, "V11 dedicated fetch warps");
+    run_split<8, 8, 75>(p, "V11 dedicated fetch warps");
+    run_split<4, 8, 75>(p, "V11 dedicated fetch warps");
+    run_split<4, 3, 75>(p, "V11 dedicated fetch warps");
+    run<3, 2>(p, "V3 LDG.128 -> regs -> STS");
+    run<2, 5>(p, "V2 cp.async.bulk 64 B per row");
+    run<1, 5>(p, "V1 TMA gather4");
+    return 0;
+}

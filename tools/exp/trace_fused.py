@@ -11,7 +11,8 @@ from rec_pangu_b200.models.ranking import DeepFM
 
 NAMES = ['kernel', 'split: cp.async wait', 'split: wait TMEM slot', 'split: work', 'mma: wait weights', 'mma: wait operands',
          'mma: wait accumulator', 'mma: issue', 'epi: wait accumulator', 'epi: layer-1 part + FM wait', 'epi: tail',
-         'weight producer: wait stage']
+         'weight producer: wait stage', 'gather: fence+sync+TMA store', 'gather: LDS+FM+split', 'gather: tcgen05.st+wait',
+         'gather: issue() next requests']
 
 
 def main():
@@ -41,6 +42,18 @@ def main():
         print(f'materialise x = {need_grad}  (event {e0.elapsed_time(e1) * 1e3:.1f} us incl. split_pack + launch overhead)')
         for n, v in zip(NAMES, out):
             print(f'   {n:32s} {v:10d}')
+        ct = (C.c_uint64 * 1024)()
+        lib.rpb_debug_fused_cta_times(ct)
+        recs = [(ct[4 * i], ct[4 * i + 1], ct[4 * i + 2], ct[4 * i + 3]) for i in range(148)]
+        t0 = min(r[1] for r in recs)
+        print('   per-CTA (globaltimer): first start 0, last start %.1f us, first end %.1f us, last end %.1f us' % (
+            (max(r[1] for r in recs) - t0) / 1e3, (min(r[2] for r in recs) - t0) / 1e3, (max(r[2] for r in recs) - t0) / 1e3))
+        for nt in sorted(set(r[3] for r in recs)):
+            d = sorted((r[2] - r[1]) / 1e3 for r in recs if r[3] == nt)
+            print(f'   CTAs with {nt} tiles: n={len(d)} duration us min {d[0]:.1f} median {d[len(d) // 2]:.1f} max {d[-1]:.1f}')
+        by_sm = sorted(recs, key=lambda r: r[2] - r[1])
+        print('   slowest CTAs (sm, tiles, us):', [(int(r[0]), int(r[3]), round((r[2] - r[1]) / 1e3, 1)) for r in by_sm[-8:]])
+        print('   fastest CTAs (sm, tiles, us):', [(int(r[0]), int(r[3]), round((r[2] - r[1]) / 1e3, 1)) for r in by_sm[:8]])
 
 
 if __name__ == '__main__':
