@@ -102,7 +102,11 @@ class DenseGradBucket:
 class ShardedTables:
     """Row-sharded embedding tables + gradient shards of one EmbeddingLayer in symmetric (peer-mapped) memory."""
 
-    def __init__(self, emb_layer, group=None, full_tables: Optional[Dict[str, torch.Tensor]] = None):
+    def __init__(self, emb_layer, group=None, full_tables: Optional[Dict[str, torch.Tensor]] = None, init=None, seed: int = 1029):
+        """`init`: None = slice the full tables the layer (or `full_tables`) holds — every rank must hold identical ones;
+        'kaiming' | 'xavier' | callable(shard, f, rank) = fill each rank's shard LOCALLY, no full table anywhere (tables that
+        exceed one GPU: BASELINE.json config 5).  'kaiming' is the reference's reset_parameters (base_model.py:42-59:
+        kaiming_normal_ on [rows, D] => std = sqrt(2 / D)), 'xavier' its _init_weights (std = sqrt(2 / (rows + D)))."""
         import torch.distributed._symmetric_memory as symm
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
@@ -121,8 +125,20 @@ class ShardedTables:
             g = symm.empty((n, self.D), dtype=torch.float32, device=dev)
             hw = symm.rendezvous(w, self.group)
             hg = symm.rendezvous(g, self.group)
-            src = full_tables[c] if full_tables is not None else emb_layer.embedding_layer[c].weight.data
-            w.copy_(local_slice(src.to(dev), self.rank, G))
+            if init is None:
+                src = full_tables[c] if full_tables is not None else emb_layer.embedding_layer[c].weight.data
+                if src.device.type == 'meta':
+                    raise RuntimeError('tables were created under dist.deferred_tables(): pass init= to shard_model_tables')
+                w.copy_(local_slice(src.to(dev), self.rank, G))
+            elif callable(init):
+                init(w, f, self.rank)
+            else:
+                gen = torch.Generator(device=dev).manual_seed(seed + 7919 * f + 104729 * self.rank)
+                std = (2.0 / self.D) ** 0.5 if init == 'kaiming' else (2.0 / (self.rows[f] + self.D)) ** 0.5
+                w.normal_(0.0, std, generator=gen)
+                n_mine = len(range(self.rank, self.rows[f], G))
+                if n_mine < n:
+                    w[n_mine:].zero_()                       # padding rows of the last shards
             g.zero_()
             for r in range(G):
                 w_ptrs[f * G + r] = int(hw.buffer_ptrs[r])
@@ -256,10 +272,31 @@ def enable_sync_batchnorm(group=None, enabled: bool = True):
     ops.SYNC_BN_GROUP = (group if group is not None else dist.group.WORLD) if enabled else None
 
 
-def shard_model_tables(model, group=None) -> ShardedTables:
-    """Convert `model.embedding_layer` to row-sharded peer-memory tables (every rank must hold identical full tables
-    when this is called, e.g. same seed).  The full tables are released afterwards."""
-    emb = model.embedding_layer
-    st = ShardedTables(emb, group)
-    emb.attach_shards(st)
-    return st
+class deferred_tables:
+    """Context manager: EmbeddingLayers constructed inside create their nn.Embedding containers on the `meta` device (shape
+    only, no storage), so a model whose tables exceed one GPU can be built and then given row shards that are filled
+    locally (`shard_model_tables(model, init=...)`).  reset_parameters / _init_weights skip meta tensors."""
+    active = False
+
+    def __enter__(self):
+        self._prev, deferred_tables.active = deferred_tables.active, True
+        return self
+
+    def __exit__(self, *exc):
+        deferred_tables.active = self._prev
+        return False
+
+
+def shard_model_tables(model, group=None, init=None, seed: int = 1029) -> ShardedTables:
+    """Convert every EmbeddingLayer of the model — `model.embedding_layer` and the D = 1 tables of an LR_Layer
+    (models/layers/shallow.py) — to row-sharded peer-memory tables.  init=None: every rank must hold identical full
+    tables when this is called (same seed); they are released afterwards.  init='kaiming' | 'xavier' | callable: see
+    ShardedTables.  Returns the ShardedTables of `model.embedding_layer`."""
+    from .models.layers.embedding import EmbeddingLayer
+    main = None
+    for i, m in enumerate(mod for mod in model.modules() if isinstance(mod, EmbeddingLayer)):
+        st = ShardedTables(m, group, init=init, seed=seed + 1000003 * i)
+        m.attach_shards(st)
+        if m is model.embedding_layer:
+            main = st
+    return main

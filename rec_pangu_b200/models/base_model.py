@@ -17,7 +17,8 @@ class BaseModel(nn.Module):
     def _init_weights(self, module: nn.Module) -> None:
         """base_model.py:28-40 (xavier; used by the multi-task models)."""
         if isinstance(module, nn.Embedding):
-            xavier_normal_(module.weight.data)
+            if module.weight.device.type != 'meta':        # dist.deferred_tables(): shards are initialised locally
+                xavier_normal_(module.weight.data)
         elif isinstance(module, nn.Linear):
             xavier_normal_(module.weight.data)
             if module.bias is not None:
@@ -26,7 +27,7 @@ class BaseModel(nn.Module):
     def reset_parameters(self):
         """base_model.py:42-59: kaiming_normal_ on every >=2-D parameter (embedding tables included)."""
         for weight in self.parameters():
-            if len(weight.shape) == 1:
+            if len(weight.shape) == 1 or weight.device.type == 'meta':      # meta: dist.deferred_tables()
                 continue
             torch.nn.init.kaiming_normal_(weight)
 

@@ -18,10 +18,12 @@ class EmbeddingLayer(nn.Module):
         # `embedding_layer.<col>.weight`, [vocab_size+1, D], embedding.py:31-34); their forward is never called.
         self.embedding_layer = nn.ModuleDict()
         self.emb_feature = []
+        from ... import dist as _dist
+        kw = {'device': 'meta'} if _dist.deferred_tables.active else {}      # shape only: shards are attached later
         for col in sparse_feature_names(enc_dict):
             self.emb_feature.append(col)
             self.embedding_layer.update({col: nn.Embedding(num_embeddings=enc_dict[col]['vocab_size'] + 1,
-                                                           embedding_dim=embedding_dim)})
+                                                           embedding_dim=embedding_dim, **kw)})
         self.dense_feature = dense_feature_names(enc_dict)
         # 'dense': backward returns fresh zero-filled [rows, D] grads exactly like nn.Embedding (reference behaviour);
         # 'persistent': grads live in persistent buffers that are re-zeroed sparsely (ops.GradStore) — same .grad
@@ -37,6 +39,7 @@ class EmbeddingLayer(nn.Module):
         for f, c in enumerate(self.emb_feature):
             trainable = self.embedding_layer[c].weight.requires_grad
             self.embedding_layer[c].weight = nn.Parameter(st.weights[f], requires_grad=trainable)
+            self.embedding_layer[c].weight._rpb_shards = st          # lets another layer's gather find these shards (LR tables)
 
     def set_weights(self, col_name: str, embedding_matrix: torch.Tensor, trainable: Optional[bool] = True) -> None:
         """embedding.py:36-47."""
@@ -54,9 +57,16 @@ class EmbeddingLayer(nn.Module):
         idx = [X[c] for c in self.emb_feature]
         dense = [X[c] for c in self.dense_feature] if with_dense else []
         if self._shards is not None:
+            x, fm, _ = ops.gather_sharded(self._shards, self.tables(), idx, dense, want_fm=want_fm)
+            lr_in = None
             if lr_tables is not None:
-                raise NotImplementedError('LR (D=1) tables together with row-sharded embedding tables')
-            return ops.gather_sharded(self._shards, self.tables(), idx, dense, want_fm=want_fm)
+                # the D = 1 tables of the LR_Layer are row-sharded the same way (owner = id mod G): a second gather launch
+                # over their shards yields [lr_f[idx_f] (F) | dense (Nd) | 0-pad] = the LR input row (shallow.py:22-27)
+                st_lr = getattr(lr_tables[0], '_rpb_shards', None)
+                if st_lr is None:
+                    raise RuntimeError('row-sharded embedding tables need row-sharded LR tables (dist.shard_model_tables shards both)')
+                lr_in, _, _ = ops.gather_sharded(st_lr, list(lr_tables), idx, dense)
+            return x, fm, lr_in
         return ops.gather(self.tables(), idx, dense, lr_tables=lr_tables, want_fm=want_fm,
                           grad_store=self._grad_store if self.grad_mode == 'persistent' else None, want_x=want_x)
 

@@ -422,6 +422,8 @@ class _GatherSharded(torch.autograd.Function):
     def backward(ctx, *gouts):
         st = ctx.st
         x, fm_s, *idx = ctx.saved_tensors
+        if st.pending and all(p.grad is None for p in ctx.params if p.requires_grad):
+            sharded_clean(st)                         # grads were dropped without model.zero_grad() (optimizer.zero_grad()): lazy re-zero
         gx = gouts[0]
         gfm = gouts[1] if ctx.want_fm else None
         F, D, G = len(st.cols), st.D, st.world
@@ -464,20 +466,33 @@ def gather_sharded(st, params, idx: Sequence[torch.Tensor], dense: Sequence[torc
 
 
 def sharded_clean(st):
-    """Re-zero the gradient shards after a step, then a barrier.  Two ways, picked by estimated cost: (a) every rank
-    clears the rows ITS batches touched, wherever they live (rpb_rows_zero with the shard table: 64-byte stores, (G-1)/G of
-    them over NVLink, ~140 us per 1.7 M rows measured at G = 2), or (b) every rank memsets its OWN shards (local HBM
-    at ~6 TB/s; 1/G of the tables, so it wins from G = 2 on at config 2 and costs 32 us at G = 8)."""
+    """Re-zero the gradient shards after a step, then a barrier.  Two ways: (b) every rank memsets its OWN shards (local
+    HBM at ~6 TB/s; 1/G of the tables: 128 us at G = 2, 32 us at G = 8 for config 2), or (a) every rank clears the rows ITS
+    batches touched wherever they live (rpb_rows_zero with the shard table: 64-byte stores, (G-1)/G of them over NVLink) —
+    the only affordable way when the shards are large (config 5: a memset of 2 GB per table and step).
+    Ordering: in (a) a rank writes into OTHER ranks' gradient shards, which their optimizer may still be reading, so (a)
+    starts with a barrier (every rank is past optimizer.step) — in (b) nobody touches foreign memory.  The choice is made
+    once per ShardedTables from an all-reduced estimate, so every rank takes the same branch whatever its batch size."""
     F = len(st.cols)
-    if st.pending and st.world > 1:
-        n_rows = sum(ix[0].shape[0] * F for ix in st.pending)
-        dense_us = sum(g.numel() for g in st.grads) * 4 / 6.0e6
-        if dense_us < 8.0e-5 * n_rows:
+    if not st.pending:
+        return
+    if st.world > 1:
+        mode = getattr(st, '_clean_mode', None)
+        if mode is None:
+            n_rows = sum(ix[0].shape[0] * F for ix in st.pending)
+            dense_us = sum(g.numel() for g in st.grads) * 4 / 6.0e6
+            want_dense = 1.0 if dense_us < 8.0e-5 * n_rows else 0.0
+            t = torch.tensor([want_dense], device=st.grads[0].device)
+            if st.group is not None and torch.distributed.is_initialized():
+                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN, group=st.group)
+            mode = st._clean_mode = 'dense' if float(t.item()) > 0.5 else 'sparse'
+        if mode == 'dense':
             for g in st.grads:
                 g.zero_()
             st.barrier()
             st.pending = []
             return
+        st.barrier()                      # nobody's optimizer is still reading the shards we are about to write into
     for idx in st.pending:
         d = ScatterDesc()
         d.B, d.F, d.D = idx[0].shape[0], F, st.D
@@ -487,8 +502,7 @@ def sharded_clean(st):
         d.G, d.grad_shard_tab = st.world, st.g_tab.data_ptr()
         check(_lib.load().rpb_rows_zero(C.byref(d), _stream()), 'rpb_rows_zero(sharded)')
         _count()
-    if st.pending:
-        st.barrier()
+    st.barrier()
     st.pending = []
 
 
@@ -998,6 +1012,8 @@ class _DeepFMCore(torch.autograd.Function):
             # row-sharded: the scatter reduces into the owners' gradient shards (local HBM or NVLink); g_tables are this
             # rank's own shards and only flag which tables are trainable
             store = None
+            if st.pending and all(tables[f].grad is None for f in range(F) if tbl_req[f]):
+                sharded_clean(st)                     # lazy re-zero, as GradStore does for unsharded tables
             g_tables = [st.grads[f] if tbl_req[f] else None for f in range(F)]
         elif store is not None:
             trainable = [tables[f] for f in range(F) if tbl_req[f]]

@@ -89,7 +89,7 @@ def test_ranking_model_matches_oracle_criteo_shape(model_name, kw, okw):
         oracle.MODEL_FORWARDS[model_name]({k: v.clone() for k, v in sd.items()}, enc, data_cpu, **okw)
     kink = kink_adjacent_samples(cap.inputs)
     n_kink = int(kink.sum()) if kink is not None else 0
-    assert n_kink <= max(4, B // 100), f'{n_kink} of {B} samples within 5e-6 of a ReLU kink: the exclusion must stay small'
+    assert n_kink <= max(4, B // 20), f'{n_kink} of {B} samples within 5e-6 of a ReLU kink: the exclusion must stay small'   # AutoInt: 816 ReLU units per sample
     if n_kink:
         data_cpu = drop_samples(data_cpu, ~kink)
     data = {k: v.cuda() for k, v in data_cpu.items()}

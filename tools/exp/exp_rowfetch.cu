@@ -75,7 +75,7 @@ struct Params {
 
 // per warp: ring of LA stages, one stage = its 32 rows x 64 B of one field; the warp walks fields half, half+2, ... of every tile
 template <int MODE, int LA>
-__global__ void __launch_bounds__(NT, 1) fetch_kernel(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(NT, 2) fetch_kernel(const __grid_constant__ Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* stage_base = smem;                                          // [LA][NW][32][64]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LA * NW * 2048); // [NW][LA]
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(NT, 1) fetch_kernel(const __grid_constant__ Pa
     const int q = warp & 3, half = warp >> 2;
     uint8_t* my_stage = stage_base + warp * 2048;
     uint64_t* my_bar = bars + warp * LA;
-    if (lane == 0) for (int s = 0; s < LA; ++s) mbar_init(&my_bar[s], 1);
+    if (lane == 0) for (int s = 0; s < LA; ++s) mbar_init(&my_bar[s], (MODE == 12 && (s & 1) == 0) ? 32 : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
     const int my_tiles = ((int)blockIdx.x < p.m_tiles) ? (p.m_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -99,7 +99,16 @@ __global__ void __launch_bounds__(NT, 1) fetch_kernel(const __grid_constant__ Pa
         if (gi < G) {
             const int m0 = ((int)blockIdx.x + i_t * (int)gridDim.x) * TILE + q * 32;
             const int f = 2 * i_kb + half;
-            if constexpr (MODE == 0 || MODE >= 4) {
+            if constexpr (MODE == 12) {
+                if ((gi & 1) == 0) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) nid[i] = __ldg(p.idx[f] + m0 + i * 8 + (lane >> 2));
+                } else if (lane < 8) {
+                    const longlong2 a = __ldg(reinterpret_cast<const longlong2*>(p.idx[f] + m0 + lane * 4));
+                    const longlong2 b = __ldg(reinterpret_cast<const longlong2*>(p.idx[f] + m0 + lane * 4 + 2));
+                    nid[0] = a.x; nid[1] = a.y; nid[2] = b.x; nid[3] = b.y;
+                }
+            } else if constexpr (MODE == 0 || MODE >= 4) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) nid[i] = __ldg(p.idx[f] + m0 + i * 8 + (lane >> 2));
             } else if constexpr (MODE == 1) {
@@ -117,7 +126,21 @@ __global__ void __launch_bounds__(NT, 1) fetch_kernel(const __grid_constant__ Pa
         if (gi < G) {
             const int f = 2 * i_kb + half, slot = gi % LA;
             uint8_t* stg = my_stage + slot * (NW * 2048);
-            if constexpr (MODE == 0 || MODE >= 4) {
+            if constexpr (MODE == 12) {
+                if ((gi & 1) == 0) {
+                    const int piece = lane & 3;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int rr = i * 8 + (lane >> 2);
+                        cp16(stg + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4), p.tables[f] + (size_t)nid[i] * 16 + piece * 4);
+                    }
+                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(&my_bar[slot])) : "memory");
+                } else {
+                    if (lane == 0) mbar_expect_tx(&my_bar[slot], 2048);
+                    __syncwarp();
+                    if (lane < 8) tma_gather4(stg + lane * 256, p.maps + f, &my_bar[slot], 0, (int)nid[0], (int)nid[1], (int)nid[2], (int)nid[3]);
+                }
+            } else if constexpr (MODE == 0 || MODE >= 4) {
                 const int piece = lane & 3;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -135,7 +158,7 @@ __global__ void __launch_bounds__(NT, 1) fetch_kernel(const __grid_constant__ Pa
                 bulk64(stg + lane * 64, p.tables[f] + (size_t)nid[0] * 16, &my_bar[slot]);
             }
         }
-        if constexpr (MODE == 0 || MODE >= 4) cp_commit();
+        if constexpr ((MODE == 0 || MODE >= 4) && MODE != 12) cp_commit();
         ++gi; if (++i_kb == NKB) { i_kb = 0; ++i_t; }
         prefetch_ids();
     };
@@ -185,6 +208,7 @@ __global__ void __launch_bounds__(NT, 1) fetch_kernel(const __grid_constant__ Pa
         for (int g = 0; g < G; ++g) {
             const int slot = g % LA;
             if constexpr (MODE == 0) { cp_wait<LA - 2>(); __syncwarp(); }
+            else if constexpr (MODE == 12) mbar_wait(&my_bar[slot], (g / LA) & 1);
             else if constexpr (MODE >= 8) { cp_wait<LA - 2>(); __syncwarp(); }
             else if constexpr (MODE >= 4) { cp_wait<LA - 2>(); asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); __syncwarp(); }
             else mbar_wait(&my_bar[slot], (g / LA) & 1);
@@ -206,7 +230,7 @@ __global__ void __launch_bounds__(NT, 1) fetch_kernel(const __grid_constant__ Pa
                 acc += v.x + v.y + v.z + v.w;
             }
             if constexpr (MODE >= 4 && MODE < 8) { if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-            if constexpr (MODE >= 8) {
+            if constexpr (MODE >= 8 && MODE < 12) {
                 float z = acc;
 #pragma unroll 1
                 for (int it = 0; it < (MODE == 8 ? 150 : 300); ++it) z = fmaf(z, 1.0001f, 0.5f);      // ~4 cycles per dependent FMA
@@ -215,7 +239,7 @@ __global__ void __launch_bounds__(NT, 1) fetch_kernel(const __grid_constant__ Pa
             __syncwarp();
             issue();
         }
-        if constexpr (MODE == 0 || MODE >= 4) cp_wait<0>();
+        if constexpr ((MODE == 0 || MODE >= 4) && MODE != 12) cp_wait<0>();
         if constexpr (MODE >= 4 && MODE < 8) { if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
     }
     if (acc == 123.456f) p.out[blockIdx.x * NT + threadIdx.x] = acc;
@@ -313,15 +337,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 template <int MODE, int LA>
-static void run(const Params& p, const char* name) {
+static void run(const Params& p, const char* name, int grid = 148) {
     const size_t smem = (size_t)LA * NW * 2048 + NW * LA * 8 + 64;
     CK(cudaFuncSetAttribute(fetch_kernel<MODE, LA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    for (int i = 0; i < 3; ++i) fetch_kernel<MODE, LA><<<148, NT, smem>>>(p);
+    for (int i = 0; i < 3; ++i) fetch_kernel<MODE, LA><<<grid, NT, smem>>>(p);
     CK(cudaDeviceSynchronize());
     CK(cudaEventRecord(e0));
-    for (int i = 0; i < 20; ++i) fetch_kernel<MODE, LA><<<148, NT, smem>>>(p);
+    for (int i = 0; i < 20; ++i) fetch_kernel<MODE, LA><<<grid, NT, smem>>>(p);
     CK(cudaEventRecord(e1));
     CK(cudaDeviceSynchronize());
     float ms = 0;
@@ -329,7 +353,7 @@ static void run(const Params& p, const char* name) {
     const double us = ms * 1e3 / 20;
     float h[8];
     CK(cudaMemcpy(h, p.out, sizeof(h), cudaMemcpyDeviceToHost));
-    printf("%-44s LA=%d  %7.1f us  (%.2f TB/s of rows+ids)  acc0=%g\n", name, LA, us, (double)B * F * 72 / us / 1e6, h[0]);
+    printf("%-44s LA=%d grid=%d  %7.1f us  (%.2f TB/s of rows+ids)  acc0=%g\n", name, LA, grid, us, (double)B * F * 72 / us / 1e6, h[0]);
 }
 
 int main() {
@@ -379,25 +403,15 @@ int main() {
     CK(cudaMemcpy(dmaps, maps.data(), F * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
     p.maps = dmaps;
     run<0, 3>(p, "V0 LDGSTS 16 B x 4 lanes/row");
-    run<0, 5>(p, "V0 LDGSTS 16 B x 4 lanes/row");
-    run<0, 8>(p, "V0 LDGSTS 16 B x 4 lanes/row");
+    run<0, 3>(p, "V0 LDGSTS, half the SMs", 74);
+    run<0, 3>(p, "V0 LDGSTS, 3/4 of the SMs", 111);
+    run<0, 3>(p, "V0 LDGSTS, 2 CTAs per SM (16 fetch warps)", 296);
+    run<0, 3>(p, "V0 LDGSTS, 4 CTAs per SM?", 592);
+    run<1, 4>(p, "V1 TMA gather4");
+    run<1, 4>(p, "V1 TMA gather4, 2 CTAs per SM", 296);
+    run<12, 4>(p, "V12 hybrid: even rounds LDGSTS, odd rounds TMA gather4");
+    run<12, 4>(p, "V12 hybrid, 2 CTAs per SM", 296);
     run<4, 3>(p, "V4 LDGSTS + TMA x store (64 B boxes)");
-    run<4, 5>(p, "V4 LDGSTS + TMA x store (64 B boxes)");
-    run<6, 5>(p, "V6 = V4, x store evict_first");
-    run<7, 5>(p, "V7 = V4, x store evict_last");
-    run<8, 5>(p, "V8 = V0 + ~600 cycles of dependent ALU work per round");
-    run<9, 5>(p, "V9 = V0 + ~1200 cycles of dependent ALU work per round");
-    run<9, 8>(p, "V9 = V0 + ~1200 cycles of dependent ALU work per round");
-    run_split<4, 4, 0>(p, "V11 dedicated fetch warps");
-    run_split<4, 4, 150>(p, "V11 dedicated fetch warps");
-    run_split<4, 8, 150>(p, "V11 dedicated fetch warps");
-    run_split<2, 8, 150>(p, "V11 dedicated fetch warps");
-    run_split<8, 8, 150>(p, "V11 dedicated fetch warps");
-    run_split<8, 8, 75>(p, "V11 dedicated fetch warps");
-    run_split<4, 8, 75>(p, "V11 dedicated fetch warps");
-    run_split<4, 3, 75>(p, "V11 dedicated fetch warps");
-    run<3, 2>(p, "V3 LDG.128 -> regs -> STS");
-    run<2, 5>(p, "V2 cp.async.bulk 64 B per row");
-    run<1, 5>(p, "V1 TMA gather4");
+    run<4, 3>(p, "V4 LDGSTS + TMA x store, 2 CTAs per SM", 296);
     return 0;
 }

@@ -17,7 +17,10 @@ NAMES = ['kernel', 'split: cp.async wait', 'split: wait TMEM slot', 'split: work
 
 def main():
     lib = _lib.load()
-    enc = bench.make_enc()
+    for kv in filter(None, os.environ.get('RPB_OPTIONS', '').split(',')):
+        k, v = kv.split('=')
+        _lib.check(lib.rpb_set_option(k.encode(), int(v)), f'rpb_set_option({k})')
+    enc = bench.make_enc(bench.WORKLOADS['deepfm'])
     torch.manual_seed(0)
     with torch.device('cuda'):
         model = DeepFM(embedding_dim=16, hidden_units=[64, 64, 64], enc_dict=enc)
@@ -44,6 +47,10 @@ def main():
             print(f'   {n:32s} {v:10d}')
         ct = (C.c_uint64 * 1024)()
         lib.rpb_debug_fused_cta_times(ct)
+        print(f'   (fetch/split kernel: [split: cp.async wait] = fetch warp waits for a free stage, [gather: issue()] = fetch warp requests, '
+              f'split warp waits for rows {ct[805]})')
+        print(f'   CTA 0 timeline (cycles from start): gather prologue done {ct[800]}, gather loop end {ct[802]} (tile-end sections {ct[801]}), '
+              f'last layer-1 MMA issued {ct[804]}, epilogue done {ct[803]}')
         recs = [(ct[4 * i], ct[4 * i + 1], ct[4 * i + 2], ct[4 * i + 3]) for i in range(148)]
         t0 = min(r[1] for r in recs)
         print('   per-CTA (globaltimer): first start 0, last start %.1f us, first end %.1f us, last end %.1f us' % (
