@@ -232,6 +232,15 @@ typedef struct RpbTowerBwdDesc {
 } RpbTowerBwdDesc;
 int rpb_tower_tail_bwd(const RpbTowerBwdDesc* d, void* stream);
 
+/* torch.nn.LayerNorm over the last dimension of x [M, N] (row stride ldx), N <= 1024: y = (x - mean) * rstd * gamma + beta with
+ * the biased variance and eps inside the square root; mean / rstd [M] are saved for backward.  Used by the MaskBlock of
+ * MaskNet (models/layers/interaction.py:254-283).  bwd: dx, and dgamma / dbeta ACCUMULATED into zero-initialised [N]
+ * buffers (column sums over the batch, fp32 atomics). */
+int rpb_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, float* y, int64_t ldy,
+                      float* mean, float* rstd, int32_t M, int32_t N, void* stream);
+int rpb_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* gamma, const float* mean,
+                      const float* rstd, float* dx, int64_t lddx, float* dgamma, float* dbeta, int32_t M, int32_t N, void* stream);
+
 /* nn.Dropout of the MLP (models/layers/deep.py:71-72, default p=0.1 for xDeepFM/AutoInt) on a contiguous
  * buffer of n floats.  keep(i) comes from a counter-based generator keyed by (seed, i), so backward recomputes
  * the mask instead of storing it.  Train-mode equivalence with torch's Philox stream is statistical

@@ -18,7 +18,7 @@ __all__ = [
     "sparse_cols", "dense_cols", "embedding_layer", "get_linear_input", "fm_layer",
     "bi_interaction", "mlp", "lr_layer", "crossnet", "cin", "senet", "bilinear_field_interaction",
     "mhsa", "bce_mean", "deepfm", "xdeepfm", "autoint", "dcn", "fibinet", "afm", "fm", "wdl", "nfm", "mmoe",
-    "sharebottom", "omoe", "mlmmoe", "essm", "MODEL_FORWARDS",
+    "sharebottom", "omoe", "mlmmoe", "essm", "masknet", "lr", "aitm", "MODEL_FORWARDS",
 ]
 
 
@@ -333,8 +333,65 @@ def afm(sd, enc_dict, data, is_training=True, hidden_units=(64, 64, 64)):
     return fibinet(sd, enc_dict, data, is_training=is_training, hidden_units=hidden_units)
 
 
+def _mask_block(sd, prefix, net, mask_input):
+    """MaskBlock.forward (layers/interaction.py:279-283): LN_out(W_h (LN_in(net) * W_2 relu(W_1 mask_input)))."""
+    n = F.layer_norm(net, (net.shape[1],), sd[f"{prefix}._input_layer_norm.weight"], sd[f"{prefix}._input_layer_norm.bias"])
+    m = F.linear(F.relu(F.linear(mask_input, sd[f"{prefix}._mask_layer.0.weight"], sd[f"{prefix}._mask_layer.0.bias"])),
+                 sd[f"{prefix}._mask_layer.2.weight"], sd[f"{prefix}._mask_layer.2.bias"])
+    h = F.linear(n * m, sd[f"{prefix}._hidden_layer.weight"], sd[f"{prefix}._hidden_layer.bias"])
+    return F.layer_norm(h, (h.shape[1],), sd[f"{prefix}._layer_norm.weight"], sd[f"{prefix}._layer_norm.bias"])
+
+
+def masknet(sd, enc_dict, data, hidden_units=(64, 64, 64), block_num=3, use_parallel=True, **_):
+    """MaskNet.forward (ranking/masknet.py:57-86); the MLP keeps its default Dropout(0.1) modules (eval: identity), so the
+    Linear layers sit at net.{0,3,6,...}."""
+    emb = embedding_layer(sd, "embedding_layer", enc_dict, data)
+    x = torch.cat([emb.flatten(start_dim=1), get_linear_input(enc_dict, data)], dim=1)
+    if use_parallel:
+        out = torch.stack([_mask_block(sd, f"mask_block_list.{i}", x, x) for i in range(block_num)], dim=1).mean(dim=1)
+    else:
+        out = x
+        for i in range(block_num):
+            out = _mask_block(sd, f"mask_block_list.{i}", out, x)
+    logit = mlp(sd, "mlp", out, len(hidden_units), 3)
+    pred = torch.sigmoid(logit)
+    res = {"logit": logit, "pred": pred}
+    if "label" in data:
+        res["loss"] = bce_mean(pred.squeeze(-1), data["label"])
+    return res
+
+
+def lr(sd, enc_dict, data, **_):
+    """LR.forward (ranking/lr.py:42-55): sigmoid(LR_Layer(data))."""
+    logit = lr_layer(sd, "lr_layer", enc_dict, data)
+    pred = torch.sigmoid(logit)
+    res = {"logit": logit, "pred": pred}
+    if "label" in data:
+        res["loss"] = bce_mean(pred.squeeze(-1), data["label"])
+    return res
+
+
+def aitm(sd, enc_dict, data, tower_dims=(400, 400, 400), **_):
+    """AITM.forward / .loss (multi_task/aitm.py:61-120), eval mode (dropout off)."""
+    x = embedding_layer(sd, "embedding_layer", enc_dict, data).flatten(start_dim=1)
+    n = len(tower_dims)
+    tc = mlp(sd, "click_tower", x, n, 3, has_out=False)
+    tv = mlp(sd, "conversion_tower", x, n, 3, has_out=False)
+    info = F.relu(F.linear(tc, sd["info_layer.0.weight"], sd["info_layer.0.bias"]))
+    tok = torch.stack([tv, info], dim=1)                                    # [B, 2, d]
+    ait = mhsa(sd, "attention_layer", tok, num_heads=1, attention_dim=tok.shape[2]).sum(dim=1)
+    click = torch.sigmoid(F.linear(tc, sd["click_layer.0.weight"], sd["click_layer.0.bias"])).squeeze(1)
+    conv = torch.sigmoid(F.linear(ait, sd["conversion_layer.0.weight"], sd["conversion_layer.0.bias"])).squeeze(1)
+    res = {"task1_pred": click, "task2_pred": conv}
+    if "task1_label" in data:
+        res["loss"] = (F.binary_cross_entropy(click, data["task1_label"]) + F.binary_cross_entropy(conv, data["task2_label"])
+                       + 0.6 * torch.clamp(conv - click, min=0).sum())
+    return res
+
+
 MODEL_FORWARDS = {
     'AFM': afm,
     'DeepFM': deepfm, 'xDeepFM': xdeepfm, 'AutoInt': autoint, 'DCN': dcn, 'FiBiNet': fibinet,
     'FM': fm, 'WDL': wdl, 'NFM': nfm, 'MMOE': mmoe, 'ShareBottom': sharebottom, 'OMOE': omoe, 'MLMMOE': mlmmoe, 'ESSM': essm,
+    'MaskNet': masknet, 'LR': lr, 'AITM': aitm,
 }

@@ -88,6 +88,8 @@ SIGNATURES = {
     'rpb_debug_fused_trace': (C.c_int, [C.POINTER(C.c_uint64), C.c_int]),
     'rpb_debug_fused_cta_times': (C.c_int, [_vp]),
     'rpb_tower_tail_bwd': (C.c_int, [C.POINTER(TowerBwdDesc), _vp]),
+    'rpb_layernorm_fwd': (C.c_int, [_vp, _i64, _vp, _vp, _f32, _vp, _i64, _vp, _vp, _i32, _i32, _vp]),
+    'rpb_layernorm_bwd': (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _i32, _vp]),
     'rpb_dropout_fwd': (C.c_int, [_vp, _vp, _i64, _f32, C.c_uint64, _vp, _vp]),
     'rpb_dropout_bwd': (C.c_int, [_vp, _vp, _vp, _i64, _f32, C.c_uint64, _vp, _vp]),
     'rpb_crossnet_fwd': (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(_vp), _vp, _i64, _vp, C.c_int, _vp]),

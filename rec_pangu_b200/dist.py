@@ -216,22 +216,29 @@ class LocalShards:
         self.pending = []
 
 
-def _table_key(col: str) -> str:
-    return f'embedding_layer.embedding_layer.{col}.weight'
+def _sharded_layers(model):
+    """(state_dict prefix, EmbeddingLayer) for every row-sharded EmbeddingLayer of the model — `embedding_layer` and the D = 1
+    tables of an LR_Layer (`lr_layer.emb_layer` / `lr.emb_layer`); keys are `<prefix>.embedding_layer.<col>.weight` (App. C)."""
+    from .models.layers.embedding import EmbeddingLayer
+    return [(name, m) for name, m in model.named_modules() if isinstance(m, EmbeddingLayer) and m._shards is not None]
+
+
+def _table_key(col: str, prefix: str = 'embedding_layer') -> str:
+    return f'{prefix}.embedding_layer.{col}.weight'           # SURVEY.md App. C
 
 
 def gather_state_dict(model) -> Dict[str, torch.Tensor]:
     """`model.state_dict()` in the REFERENCE's layout from a model whose tables are row-sharded: every table entry
-    (`embedding_layer.embedding_layer.<col>.weight`) is all-gathered and re-interleaved to [vocab_size + 1, D]; all other
-    entries (replicated on every rank) are the local ones.  Collective: every rank of the shard group must call it and
-    every rank gets the full dict, so `RankTrainer.save_model` on rank 0 writes a checkpoint that the reference — or a
-    single-GPU run of this build, or a run sharded over another number of GPUs — loads unchanged (trainer.py:133-150)."""
-    st = model.embedding_layer._shards
+    (`embedding_layer.embedding_layer.<col>.weight`, and the LR tables) is all-gathered and re-interleaved to
+    [vocab_size + 1, D]; all other entries (replicated on every rank) are the local ones.  Collective: every rank of the
+    shard group must call it and every rank gets the full dict, so `RankTrainer.save_model` on rank 0 writes a checkpoint
+    that the reference — or a single-GPU run of this build, or a run sharded over another number of GPUs — loads unchanged
+    (trainer.py:133-150)."""
     sd = {k: v for k, v in model.state_dict().items()}
-    if st is None:
-        return sd
-    for f, c in enumerate(st.cols):
-        sd[_table_key(c)] = st.full_table(f)
+    for prefix, m in _sharded_layers(model):
+        st = m._shards
+        for f, c in enumerate(st.cols):
+            sd[_table_key(c, prefix)] = st.full_table(f)
     return sd
 
 
@@ -239,28 +246,33 @@ def load_state_dict_sharded(model, state_dict: Dict[str, torch.Tensor], strict: 
     """Inverse of gather_state_dict: load a reference-layout state_dict into a model with row-sharded tables.  Each rank
     copies ITS rows (owner = id mod G) of every full table into its shard in place (the peer mappings stay valid);
     everything else goes through nn.Module.load_state_dict.  Full-size table entries never touch the device whole."""
-    st = model.embedding_layer._shards
-    if st is None:
+    layers = _sharded_layers(model)
+    if not layers:
         return model.load_state_dict(state_dict, strict=strict)
     rest = dict(state_dict)
-    for f, c in enumerate(st.cols):
-        key = _table_key(c)
-        if key not in rest:
-            if strict:
-                raise KeyError(f'missing key in state_dict: {key}')
-            continue
-        full = rest.pop(key)
-        if tuple(full.shape) != (st.rows[f], st.D):
-            raise RuntimeError(f'size mismatch for {key}: checkpoint {tuple(full.shape)}, model {(st.rows[f], st.D)}')
-        with torch.no_grad():
-            st.weights[f].copy_(local_slice(full, st.rank, st.world).to(st.weights[f].device))
-    own = {k: v for k, v in model.state_dict().items() if not any(k == _table_key(c) for c in st.cols)}
+    table_keys = set()
+    for prefix, m in layers:
+        st = m._shards
+        for f, c in enumerate(st.cols):
+            key = _table_key(c, prefix)
+            table_keys.add(key)
+            if key not in rest:
+                if strict:
+                    raise KeyError(f'missing key in state_dict: {key}')
+                continue
+            full = rest.pop(key)
+            if tuple(full.shape) != (st.rows[f], st.D):
+                raise RuntimeError(f'size mismatch for {key}: checkpoint {tuple(full.shape)}, model {(st.rows[f], st.D)}')
+            with torch.no_grad():
+                st.weights[f].copy_(local_slice(full, st.rank, st.world).to(st.weights[f].device))
+    own = {k: v for k, v in model.state_dict().items() if k not in table_keys}
     missing = [k for k in own if k not in rest]
     unexpected = [k for k in rest if k not in own]
     if strict and (missing or unexpected):
         raise RuntimeError(f'load_state_dict_sharded: missing keys {missing}, unexpected keys {unexpected}')
     res = model.load_state_dict(rest, strict=False)
-    st.barrier()
+    for _, m in layers:
+        m._shards.barrier()
     return res
 
 

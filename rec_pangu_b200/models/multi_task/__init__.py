@@ -7,12 +7,4 @@ from .mlmmoe import MLMMOE
 from .essm import ESSM
 
 
-def _unported(name):
-    class _Unported:
-        def __init__(self, *args, **kwargs):
-            raise NotImplementedError(f'{name} is not part of the B200 hot-path scope yet (SURVEY.md §8f rank 4)')
-    _Unported.__name__ = name
-    return _Unported
-
-
-AITM = _unported('AITM')
+from .aitm import AITM

@@ -8,4 +8,6 @@ from .fm import FM
 from .xdeepfm import xDeepFM
 from .dcn import DCN
 from .afm import AFM
-from ._unported import AFN, AOANet, CCPM, LR, MaskNet
+from .masknet import MaskNet
+from .lr import LR
+from ._unported import AFN, AOANet, CCPM

@@ -42,7 +42,7 @@ FUSED_GATHER_GEMM = int(os.environ.get('RPB_FUSED_GATHER_GEMM', '1'))
 # Row-sharded tables (dist.ShardedTables): 1 = DeepFM runs its fused core on them too — the one-kernel forward requests
 # remote rows with the same cp.async over NVLink and the dx GEMM's scatter epilogue reduces into the owners' gradient
 # shards — instead of the separate gather / MLP / dx GEMM / scatter kernels.  Opt-in until measured on >= 2 GPUs.
-SHARDED_FUSED = int(os.environ.get('RPB_SHARDED_FUSED', '0'))
+SHARDED_FUSED = int(os.environ.get('RPB_SHARDED_FUSED', '1'))
 _LAUNCHES = 0           # number of librec_pangu_b200 kernels launched (bench.py reports it as gpu_launches)
 
 
@@ -826,7 +826,7 @@ def _deepfm_fused_fwd(cfg, tables, idx, dense, params, head, need_grad, shards=N
     if rc == _lib.ERR_UNSUPPORTED:
         return None
     check(rc, 'rpb_deepfm_fwd_fused')
-    _count(2)
+    _count(3)                     # layer-1 weight split, tail weight split (tcgen05 tail), the forward kernel
     del keep
     return logit, [x, y1] + hs, pred, loss, fm_s, rows
 
@@ -1646,6 +1646,42 @@ def dropout(x: torch.Tensor, p: float, training: bool) -> torch.Tensor:
     if not training or p <= 0.0:
         return x
     return _Dropout.apply(x.contiguous(), float(p), int(torch.randint(0, 2 ** 62, (1,)).item()))
+
+
+# ------------------------------------------------------------------ LayerNorm (MaskNet's MaskBlock)
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, K, gamma, beta, eps):
+        M = x.shape[0]
+        y = torch.empty((M, K), dtype=torch.float32, device=x.device)
+        mean = torch.empty((M,), dtype=torch.float32, device=x.device)
+        rstd = torch.empty((M,), dtype=torch.float32, device=x.device)
+        check(_lib.load().rpb_layernorm_fwd(_ptr(x), x.stride(0), _ptr(gamma), _ptr(beta), eps, _ptr(y), y.stride(0), _ptr(mean),
+                                            _ptr(rstd), M, K, _stream()), 'rpb_layernorm_fwd')
+        _count()
+        ctx.K = K
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        M, K = x.shape[0], ctx.K
+        g = _rowmajor(g)
+        dx = torch.zeros_like(x) if x.shape[1] != K else torch.empty_like(x)      # pad columns of a feature row get zero
+        dgamma = torch.zeros_like(gamma)
+        dbeta = torch.zeros_like(gamma)
+        check(_lib.load().rpb_layernorm_bwd(_ptr(g), g.stride(0), _ptr(x), x.stride(0), _ptr(gamma), _ptr(mean), _ptr(rstd),
+                                            _ptr(dx), dx.stride(0), _ptr(dgamma), _ptr(dbeta), M, K, _stream()), 'rpb_layernorm_bwd')
+        _count()
+        return dx, None, dgamma, dbeta, None
+
+
+def layer_norm(x: torch.Tensor, ln: torch.nn.LayerNorm, K: Optional[int] = None) -> torch.Tensor:
+    """torch.nn.LayerNorm over the first K columns of x [M, >= K] (K defaults to the module's normalized_shape)."""
+    _cuda(x, 'layer_norm input')
+    K = int(ln.normalized_shape[0]) if K is None else K
+    return _LayerNorm.apply(_rowmajor(x), K, ln.weight, ln.bias, float(ln.eps))
 
 
 # ------------------------------------------------------------------ FiBiNet: SENET + bilinear (both passes) fused

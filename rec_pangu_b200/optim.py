@@ -17,6 +17,8 @@ from .models.layers.embedding import EmbeddingLayer
 
 
 class FusedAdam:
+    graph_safe = True           # step counter lives on the device: model_pipeline.train_model may capture the step as a CUDA graph
+
     def __init__(self, model: torch.nn.Module, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
         self.model, self.lr, self.betas, self.eps = model, lr, betas, eps
         self.step_count = 0

@@ -29,8 +29,9 @@ sys.path.insert(0, '/root/reference')
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
-from rec_pangu.models.ranking import DeepFM, xDeepFM, AutoInt, DCN, FiBiNet, FM, WDL, NFM, AFM  # noqa: E402
-from rec_pangu.models.multi_task import MMOE, ShareBottom, OMOE, MLMMOE, ESSM  # noqa: E402
+from rec_pangu.models.ranking import DeepFM, xDeepFM, AutoInt, DCN, FiBiNet, FM, WDL, NFM, AFM, MaskNet  # noqa: E402
+from rec_pangu.models.multi_task import MMOE, ShareBottom, OMOE, MLMMOE, ESSM, AITM  # noqa: E402
+from rec_pangu.models.layers import LR_Layer  # noqa: E402
 from rec_pangu.models.layers import (FM_Layer, MLP, CrossNet, CompressedInteractionNet, SENET_Layer,  # noqa: E402
                                      BilinearInteractionLayer, MultiHeadSelfAttention, InnerProductLayer)
 
@@ -228,7 +229,58 @@ def run_multitask_all():
                       list_attrs=('level_gates', 'gates', 'gates_bias'))
 
 
+def run_lr(seed=3029):
+    """ranking/lr.py cannot be constructed in the reference (lr.py:28 calls a reset_parameters() it does not have,
+    SURVEY.md App. A-15): the fixture drives what its forward would run — the reference's LR_Layer, sigmoid, BCELoss on
+    squeeze(-1) (lr.py:42-55) — with the state_dict keys the class would have (`lr_layer.*`)."""
+    torch.manual_seed(seed)
+    gen = torch.Generator().manual_seed(seed)
+    enc = make_enc(5, 3, [17, 50, 97, 9, 33])
+
+    class _LR(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lr_layer = LR_Layer(enc_dict=enc)
+
+        def forward(self, data):
+            y = self.lr_layer(data).sigmoid()
+            return {'pred': y, 'loss': torch.nn.BCELoss()(y.squeeze(-1), data['label'])}
+    model = _LR()
+    data = make_batch(enc, 48, gen)
+    out = model(data)
+    out['loss'].backward()
+    save('lr', model, enc, data, out, meta={'model': 'LR', 'kwargs': {}, 'D': 1})
+
+
+def run_aitm(seed=4029):
+    torch.manual_seed(seed)
+    gen = torch.Generator().manual_seed(seed)
+    enc = make_enc(4, 2, [17, 50, 97, 9])
+    kwargs = {'tower_dims': [16, 16, 8], 'drop_prob': [0.1, 0.1, 0.1]}
+    model = AITM(embedding_dim=8, enc_dict=enc, **kwargs)
+    with torch.no_grad():
+        for k, p in model.named_parameters():
+            if p.dim() == 1:
+                p.copy_(torch.randn(p.shape, generator=gen) * 0.1)
+    model.eval()
+    data = make_batch(enc, 48, gen, labels=('task1_label', 'task2_label'))
+    out = model(data)
+    out['loss'].backward()
+    save('aitm', model, enc, data, out, meta={'model': 'AITM', 'kwargs': kwargs, 'D': 8})
+
+
+def run_round2():
+    """Fixtures added in round 2: MaskNet (parallel and serial blocks), LR, AITM."""
+    run_model('masknet', MaskNet, {'hidden_units': [16, 8], 'block_num': 3, 'use_parallel': True}, n_sparse=6, seed=5029)
+    run_model('masknet_serial', MaskNet, {'hidden_units': [16, 8], 'block_num': 2, 'use_parallel': False}, n_sparse=6, seed=6029)
+    run_lr()
+    run_aitm()
+
+
 if __name__ == '__main__':
+    if '--only-round2' in sys.argv:
+        run_round2()
+        sys.exit(0)
     if '--only-multitask' in sys.argv:            # ShareBottom / OMOE / MLMMOE fixtures only (added after the first set)
         run_multitask_all()
         sys.exit(0)
@@ -250,3 +302,4 @@ if __name__ == '__main__':
     run_mmoe('mmoe_eval', bn_training=False)
     run_mmoe('mmoe_train', bn_training=True)
     run_multitask_all()
+    run_round2()

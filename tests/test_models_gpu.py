@@ -13,6 +13,8 @@ pytestmark = pytest.mark.gpu
 def _build(name, meta):
     from rec_pangu_b200.models import ranking
     cls = getattr(ranking, meta['model'])
+    if meta['model'] == 'LR':                      # ranking/lr.py:12-16: no embedding_dim argument
+        return cls(enc_dict=meta['enc_dict'], **meta['kwargs'])
     return cls(embedding_dim=meta['D'], enc_dict=meta['enc_dict'], **meta['kwargs'])
 
 
@@ -22,7 +24,8 @@ def _logit(p):
 
 
 # 'afm' = the FiBiNet class under the reference's other name (passed on a B200 in the round-1 bench record: afm_golden.parity_ok)
-RANKING_GOLDEN = ['deepfm', 'deepfm_d16', 'fm', 'wdl', 'nfm', 'dcn', 'xdeepfm', 'autoint', 'autoint_l2', 'fibinet', 'afm']
+RANKING_GOLDEN = ['deepfm', 'deepfm_d16', 'fm', 'wdl', 'nfm', 'dcn', 'xdeepfm', 'autoint', 'autoint_l2', 'fibinet', 'afm',
+                  'masknet', 'masknet_serial', 'lr']
 
 
 @pytest.mark.parametrize('name', RANKING_GOLDEN)
@@ -205,6 +208,31 @@ def test_essm_matches_reference_golden():
     out2 = model(data, is_training=False)
     assert set(out2.keys()) == {'task1_pred', 'task2_pred'}
     assert torch.equal(out2['task1_pred'], out['task1_pred']) and torch.equal(out2['task2_pred'], out['task2_pred'])
+
+
+def test_aitm_matches_reference_golden():
+    """AITM (multi_task/aitm.py): two towers, information transfer, attention over the two tokens, constrained loss — vs the
+    fixture produced by the real reference class (predictions are [B], not [B, 1], as in the reference)."""
+    from rec_pangu_b200.models.multi_task import AITM
+    g = load_golden('aitm')
+    m = g['meta']
+    model = AITM(embedding_dim=m['D'], enc_dict=m['enc_dict'], **m['kwargs'])
+    assert set(model.state_dict().keys()) == set(g['sd'].keys())
+    model.load_state_dict(g['sd'])
+    model = model.cuda().eval()
+    data = {k: v.cuda() for k, v in g['data'].items()}
+    out = model(data)
+    out['loss'].backward()
+    for k in ('task1_pred', 'task2_pred'):
+        assert out[k].shape == g['out'][k].shape
+        torch.testing.assert_close(out[k].cpu(), g['out'][k], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(out['loss'].cpu(), g['out']['loss'], rtol=1e-5, atol=1e-5)
+    grads = dict(model.named_parameters())
+    for k, ref in g['grad'].items():
+        assert grads[k].grad is not None, k
+        assert_close_rel(grads[k].grad, ref, 2e-4, k)
+    out2 = model(data, is_training=False)
+    assert set(out2.keys()) == {'task1_pred', 'task2_pred'}
 
 
 def test_persistent_grad_mode_equals_dense_mode():

@@ -68,11 +68,14 @@ def test_multitask_flow_mmoe(tmp_path):
 
 
 def test_batch_stager_packs_columns_and_survives_reuse():
-    """model_pipeline._to_device: one pinned staging buffer + one H2D copy per dtype; device views of consecutive batches
-    stay intact while they are in use (double buffering), values are bit-identical to per-key .to(device)."""
-    from rec_pangu_b200.model_pipeline import _BatchStager
-    st = _BatchStager()
+    """model_pipeline._BatchStager: one pinned staging buffer + one H2D copy per dtype on a copy stream; device views of
+    consecutive batches stay intact while they are in use (double buffering), values are bit-identical to per-key
+    .to(device); columns that already are the rows of one pinned tensor are copied without re-packing."""
+    from rec_pangu_b200.model_pipeline import _BatchStager, _common_pinned_base
     dev = torch.device('cuda', torch.cuda.current_device())
+    st = _BatchStager(dev)
+    copy_stream = torch.cuda.Stream()
+    main = torch.cuda.current_stream()
     g = torch.Generator().manual_seed(0)
     batches = []
     for b in range(5):
@@ -81,33 +84,109 @@ def test_batch_stager_packs_columns_and_survives_reuse():
         d.update({f'd{i}': torch.rand(n, generator=g) for i in range(3)})
         d['label'] = (torch.rand(n, generator=g) < 0.3).float()
         batches.append(d)
-    prev = None
+    # batch 2 comes from a "columnar loader": every column a row view of one pinned buffer per dtype
+    buf_i = torch.stack([batches[2][f's{i}'] for i in range(6)]).pin_memory()
+    buf_f = torch.stack([batches[2][k] for k in ('d0', 'd1', 'd2', 'label')]).pin_memory()
+    col = {f's{i}': buf_i[i] for i in range(6)}
+    col.update({k: buf_f[i] for i, k in enumerate(('d0', 'd1', 'd2', 'label'))})
+    assert _common_pinned_base([col[f's{i}'] for i in range(6)]) is buf_i
+    assert _common_pinned_base([batches[0][f's{i}'] for i in range(6)]) is None
+    batches[2] = col
+    staged = []
     for d in batches:
-        ref = {k: v.clone() for k, v in d.items()}
-        out = st(dict(d), dev)
-        assert list(out.keys()) == list(ref.keys())
-        for k in ref:
-            assert out[k].is_cuda and out[k].dtype == ref[k].dtype and torch.equal(out[k].cpu(), ref[k])
-        if prev is not None:                                          # the previous batch's views were not overwritten
-            for k in prev[1]:
-                assert torch.equal(prev[0][k].cpu(), prev[1][k])
-        prev = (out, ref)
-    # two int64 columns of one batch are rows of ONE device buffer
-    o = st({k: v for k, v in batches[0].items()}, dev)
-    assert o['s1'].data_ptr() - o['s0'].data_ptr() == 512 * 8
+        t, out = st.stage(d, copy_stream)
+        main.wait_event(st.ready[t])
+        kept = {k: v.clone() for k, v in out.items()}                # what a step would read from the staging views
+        ev = torch.cuda.Event()
+        ev.record(main)
+        st.done[t] = ev
+        staged.append((d, kept))
+    torch.cuda.synchronize()
+    for d, kept in staged:
+        assert list(kept.keys()) == list(d.keys())
+        for k in d:
+            assert torch.equal(kept[k].cpu(), d[k]), k
 
 
-def test_trainer_with_fused_adam(tmp_path):
-    from rec_pangu.dataset import get_dataloader
-    from rec_pangu.models.ranking import DeepFM
-    from rec_pangu.trainer import RankTrainer
-    df, schema = _frame()
-    train_loader, valid_loader, _, enc_dict = get_dataloader(df[:240], df[:270], df[:285], schema, batch_size=512)
-    torch.manual_seed(0)
-    model = DeepFM(embedding_dim=8, enc_dict=enc_dict)
-    trainer = RankTrainer(num_task=1, model_ckpt_dir=str(tmp_path))
-    m = trainer.fit(model, train_loader, valid_loader, epoch=12, lr=1e-2, device=torch.device('cuda'), optimizer_type='fused_adam')
-    assert m['roc_auc_score'] > 0.7
-    with pytest.raises(ValueError):
-        trainer.fit(model, train_loader, valid_loader, epoch=1, optimizer_type='fused_adam', lr_scheduler_type='StepLR',
-                    scheduler_params={'step_size': 1})
+class _Loader:
+    """In-memory loader of host dict batches with the two attributes train_model reads (dataset, batch_size)."""
+
+    def __init__(self, batches, batch_size):
+        self.batches, self.batch_size = batches, batch_size
+        self.dataset = range(len(batches) * batch_size)
+
+    def __iter__(self):
+        return (dict(b) for b in self.batches)
+
+
+@pytest.mark.parametrize('model_name', ['DeepFM', 'xDeepFM'])
+def test_train_model_graph_replay_equals_eager_launches(model_name, monkeypatch):
+    """model_pipeline.train_model with a graph-safe optimizer (FusedAdam) captures the step once per staging buffer and
+    replays it (reference loop: model_pipeline.py:47-58).  Same batches through RPB_TRAIN_GRAPH=0 (eager launches): same
+    parameters afterwards.  xDeepFM runs eval-free: its MLP dropout draws per-replay masks (device epoch), so only DeepFM
+    (dropout 0) is compared bit-tight; xDeepFM must stay finite and move."""
+    from helpers import make_enc, make_batch
+    from rec_pangu_b200.models import ranking
+    from rec_pangu_b200.model_pipeline import train_model
+    from rec_pangu_b200.optim import FusedAdam
+    enc = make_enc(26, 13, 500)
+    B = 1024
+    batches = [make_batch(enc, B, seed=100 + i) for i in range(7)]
+    finals = []
+    for graph in ('1', '0'):
+        monkeypatch.setenv('RPB_TRAIN_GRAPH', graph)
+        torch.manual_seed(3)
+        model = getattr(ranking, model_name)(embedding_dim=16, enc_dict=enc).cuda()
+        opt = FusedAdam(model, lr=1e-2)
+        res = train_model(model, _Loader(batches, B), opt, torch.device('cuda'), metric_list=['log_loss'], log_rounds=3)
+        assert 'train_log_loss' in res and np.isfinite(res['train_log_loss'])
+        finals.append({k: v.detach().clone() for k, v in model.state_dict().items()})
+    moved = 0
+    for k in finals[0]:
+        a, b = finals[0][k].float(), finals[1][k].float()
+        assert torch.isfinite(a).all(), k
+        if model_name == 'DeepFM':
+            assert (a - b).abs().max().item() <= 1e-5 * max(1.0, b.abs().max().item()), k
+        moved += int((a - b).abs().max().item() >= 0)
+    assert moved == len(finals[0])
+
+
+def test_train_model_reports_out_of_range_ids_like_the_reference():
+    """An id beyond the table raises IndexError from train_model / test_model (ops.check_index_errors at the points that
+    synchronise anyway) instead of silently training on row 0 (reference: aten::embedding raises on CPU / asserts on CUDA)."""
+    from helpers import make_enc, make_batch
+    from rec_pangu_b200.models.ranking import DeepFM
+    from rec_pangu_b200.model_pipeline import train_model, test_model
+    enc = make_enc(4, 2, 100)
+    batches = [make_batch(enc, 256, seed=i) for i in range(3)]
+    batches[1]['C2'][17] = 100 + 7
+    model = DeepFM(embedding_dim=16, hidden_units=[64, 64], enc_dict=enc).cuda()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    with pytest.raises(IndexError):
+        train_model(model, _Loader(batches, 256), opt, torch.device('cuda'), log_rounds=100)
+    with pytest.raises(IndexError):
+        test_model(model, _Loader(batches, 256), torch.device('cuda'))
+
+
+def test_graph_replays_draw_fresh_dropout_masks():
+    """runtime.GraphedStep on a model with active dropout (xDeepFM, MLP dropout 0.1): the host-drawn seeds are frozen by the
+    capture, the device-side epoch the kernels mix in is advanced inside the captured step, so two replays on the SAME batch
+    and weights give different training-mode predictions (and a third differs from both)."""
+    from helpers import make_enc, make_batch
+    from rec_pangu_b200.models.ranking import xDeepFM
+    from rec_pangu_b200.runtime import ColumnarBatch, GraphedStep
+    enc = make_enc(8, 3, 200)
+    torch.manual_seed(1)
+    model = xDeepFM(embedding_dim=16, enc_dict=enc).cuda()
+    model.set_grad_mode('persistent')
+    model.train()
+    cb = ColumnarBatch(enc, 512, device='cuda', pinned_host=False)
+    cb.load_device(make_batch(enc, 512, seed=5, device='cuda'))
+    step = GraphedStep(model, cb)                 # no optimizer: weights stay fixed, only the masks may change
+    assert step.graph is not None
+    preds = []
+    for _ in range(3):
+        step.replay()
+        torch.cuda.synchronize()
+        preds.append(step.pred.detach().clone())
+    assert not torch.equal(preds[0], preds[1]) and not torch.equal(preds[1], preds[2]) and not torch.equal(preds[0], preds[2])

@@ -213,7 +213,7 @@ def test_deepfm_one_kernel_forward_equals_separate_kernels(B, F, Nd, hidden):
             res.append((out['pred'].detach().clone(), out['loss'].detach().clone(), model._last_logit.clone(), grads, nl))
         finally:
             ops.FUSED_GATHER_GEMM = 1
-    assert res[0][4] == 2 and res[1][4] == 3            # (split + fused kernel) vs (gather, split + GEMM-with-tail)
+    assert res[0][4] == 3 and res[1][4] == 3            # (2 weight splits + fused kernel) vs (gather, split + GEMM-with-tail)
     torch.testing.assert_close(res[0][2], res[1][2], rtol=1e-5, atol=2e-5)
     torch.testing.assert_close(res[0][0], res[1][0], rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(res[0][1], res[1][1], rtol=1e-5, atol=1e-6)
