@@ -715,7 +715,7 @@ def train_model_leg(w, model, enc, opt, dev, labels, steps):
         return {k: out[k] for k in d}
     host = [columnar(synth_batch(enc, B, gen, labels=labels)) for _ in range(4)]
     loader = _MemLoader([host[i % 4] for i in range(n)], B)
-    warm = _MemLoader([host[i % 4] for i in range(4)], B)
+    warm = _MemLoader([host[i % 4] for i in range(8)], B)          # 2 eager runs + the graph capture per staging buffer happen here
     num_task = 1 if w['kind'] == 'ranking' else 2
     train_model(model, warm, opt, dev, metric_list=[], num_task=num_task, log_rounds=10 ** 9)
     torch.cuda.synchronize()

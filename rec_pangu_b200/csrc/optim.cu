@@ -97,6 +97,26 @@ sparse_adam_kernel(const __grid_constant__ SparseAdamParams p) {
     }
 }
 
+// D = 1 tables (the LR_Layer's wide part, models/layers/shallow.py:14-27): one thread per sample walks the fields; the row is
+// claimed with the same stamp exchange, so the step stays graph-safe (no torch.unique, step number read on the device).
+__global__ void __launch_bounds__(256)
+sparse_adam_scalar_kernel(const __grid_constant__ SparseAdamParams p) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B) return;
+    const int step = p.step_dev != nullptr ? *p.step_dev : p.step;
+    const AdamHyper hy = p.step_dev != nullptr ? make_hyper(p.h.lr, p.h.b1, p.h.b2, p.h.eps, step) : p.h;
+    for (int f = 0; f < p.F; ++f) {
+        if (p.w[f] == nullptr) continue;
+        long long row = __ldg(p.idx[f] + b);
+        if ((unsigned long long)row >= (unsigned long long)p.rows[f]) row = 0;
+        if (atomicExch(p.stamp[f] + row, step) == step) continue;          // another sample of this batch already updated the row
+        float w = p.w[f][row], m = p.m[f][row], v = p.v[f][row];
+        adam_update(w, m, v, p.g[f][row], hy);
+        p.w[f][row] = w; p.m[f][row] = m; p.v[f][row] = v;
+        p.g[f][row] = 0.f;                                                  // fused sparse zero_grad
+    }
+}
+
 }  // namespace rpb
 
 using namespace rpb;
@@ -134,7 +154,7 @@ RPB_API int rpb_adam_multi(const RpbAdamMultiDesc* d, void* stream) {
 
 RPB_API int rpb_sparse_adam(const RpbSparseAdamDesc* d, void* stream) {
     if (d == nullptr || d->B <= 0 || d->F <= 0 || d->D <= 0 || (d->step_dev == nullptr && d->step < 1)) return RPB_ERR_BAD_ARG;
-    if (d->F > RPB_MAX_FIELDS || d->D % 4 != 0 || d->D > 128) return RPB_ERR_UNSUPPORTED;
+    if (d->F > RPB_MAX_FIELDS || (d->D != 1 && d->D % 4 != 0) || d->D > 128) return RPB_ERR_UNSUPPORTED;
     SparseAdamParams p{};
     for (int f = 0; f < d->F; ++f) {
         p.w[f] = d->weights[f]; p.g[f] = d->grads[f]; p.m[f] = d->exp_avg[f]; p.v[f] = d->exp_avg_sq[f];
@@ -146,6 +166,10 @@ RPB_API int rpb_sparse_adam(const RpbSparseAdamDesc* d, void* stream) {
     p.step_dev = d->step_dev;
     p.h = make_hyper(d->lr, d->beta1, d->beta2, d->eps, d->step_dev != nullptr ? 1 : d->step);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (d->D == 1) {
+        sparse_adam_scalar_kernel<<<ceil_div(p.B, 256), 256, 0, st>>>(p);
+        return (int)cudaGetLastError();
+    }
     const int dv = d->D / 4;
     auto launch = [&](auto lt) -> int {
         constexpr int LPR = decltype(lt)::value;

@@ -38,7 +38,7 @@ class AITM(BaseModel):
     def _two_token_attention(self, t0: torch.Tensor, t1: torch.Tensor):
         """MultiHeadSelfAttention on the token pair (t0, t1), each [B, d]: out_i = relu(sum_j softmax_j(q_i . k_j) v_j + t_i)."""
         att = self.attention_layer
-        if att.num_heads != 1 or att.W_res is not None or att.layer_norm is not None or getattr(att, 'scale', None):
+        if att.num_heads != 1 or att.W_res is not None:
             raise NotImplementedError('AITM attention: only the MultiHeadSelfAttention defaults of the reference are wired')
         q = [ops.linear(t, att.W_q.weight, None) for t in (t0, t1)]
         k = [ops.linear(t, att.W_k.weight, None) for t in (t0, t1)]

@@ -1175,8 +1175,19 @@ def mlp_forward(x: torch.Tensor, K: int, weights: Sequence[torch.Tensor], biases
         params += [W if W.is_contiguous() else W.contiguous(), b]
     cfg = dict(n_hidden=n_hidden, has_out=has_out, K=K, relu=list(relu), dropout=list(dropout), training=training,
                impl=_GEMM_IMPL if impl is None else impl)
-    if not has_out or n_hidden < 1:
-        raise NotImplementedError('MLP needs >= 1 hidden layer and an output layer (deep.py:40-41)')
+    if n_hidden < 1:
+        raise NotImplementedError('MLP needs >= 1 hidden layer (deep.py:40-41)')
+    if not has_out:
+        # towers without an output layer (AITM click / conversion towers, deep.py:79-84 with output_dim=None): layer by layer
+        # through the single-Linear op (same tcgen05 GEMM), ReLU and dropout in between
+        h, k = x, K
+        for i in range(n_hidden):
+            h = linear(h, params[2 * i], params[2 * i + 1], K=k, impl=impl)
+            if relu[i]:
+                h = torch.relu(h)
+            h = globals()['dropout'](h, dropout[i], training)
+            k = None
+        return h
     return _MLP.apply(cfg, x, *params)
 
 

@@ -86,12 +86,12 @@ class FusedAdam:
         d = SparseAdamDesc()
         d.B, d.F, d.D, d.step = idx[0].shape[0], F, D, self.step_count
         d.lr, d.beta1, d.beta2, d.eps = self.lr, self.betas[0], self.betas[1], self.eps
-        states = [self._st(p) if g is not None else None for p, g in zip(params, grads)]
+        states = [self._st(p) if (g is not None and p is not None) else None for p, g in zip(params, grads)]
         for p, s in zip(params, states):
             if s is not None and 'stamp' not in s:
                 s['stamp'] = torch.zeros(p.shape[0], dtype=torch.int32, device=p.device)
         arr = lambda ts: (C.c_void_p * F)(*[t.data_ptr() if t is not None else 0 for t in ts])  # noqa: E731
-        w_arr = arr([p if g is not None else None for p, g in zip(params, grads)])
+        w_arr = arr([p if (g is not None and s is not None) else None for p, g, s in zip(params, grads, states)])
         g_arr = arr(grads)
         m_arr = arr([s['m'] if s else None for s in states])
         v_arr = arr([s['v'] if s else None for s in states])
@@ -104,20 +104,8 @@ class FusedAdam:
         ops._count()
 
     def _sparse_scalar(self, params, grads, rows, idx):
-        # D=1 tables: tiny rows; update them densely over the touched rows with index ops (plumbing on [B]-sized data)
-        b1, b2 = self.betas
-        bc1 = 1 - b1 ** self.step_count
-        bc2 = 1 - b2 ** self.step_count
-        for p, g, ix in zip(params, grads, idx):
-            if p is None or g is None:
-                continue
-            s = self._st(p)
-            rows_u = torch.unique(ix)
-            gr = g[rows_u]
-            s['m'][rows_u] = b1 * s['m'][rows_u] + (1 - b1) * gr
-            s['v'][rows_u] = b2 * s['v'][rows_u] + (1 - b2) * gr * gr
-            p[rows_u] -= (self.lr / bc1) * s['m'][rows_u] / (s['v'][rows_u].sqrt() / bc2 ** 0.5 + self.eps)
-            g[rows_u] = 0
+        """D = 1 tables (LR_Layer): the scalar variant of rpb_sparse_adam — same stamp claim, graph-safe."""
+        self._sparse(_lib.load(), C.c_void_p(torch.cuda.current_stream().cuda_stream), params, grads, rows, idx, 1)
 
     def zero_grad(self, set_to_none: bool = True):
         self.model.zero_grad(set_to_none=set_to_none)
