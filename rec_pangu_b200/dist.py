@@ -78,25 +78,23 @@ class DenseGradBucket:
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
 
     def all_reduce(self, average: bool = False):
+        """Three launches around the collective whatever the number of parameters: pack (one multi-tensor copy), all-reduce,
+        unpack (one multi-tensor copy) — a per-parameter loop costs two tiny kernels per tensor (18 for DeepFM's tower)."""
         if self.world == 1 or not self.params:
             return
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            if p.grad is not None:
-                self.flat[off:off + n].copy_(p.grad.reshape(-1))
-            else:
-                self.flat[off:off + n].zero_()
-            off += n
+        views = list(self.flat.split([p.numel() for p in self.params]))
+        live = [(v, p) for v, p in zip(views, self.params) if p.grad is not None]
+        dead = [v for v, p in zip(views, self.params) if p.grad is None]
+        if dead:
+            torch._foreach_zero_(dead)
+        if live:
+            torch._foreach_copy_([v for v, _ in live], [p.grad.reshape(-1) for _, p in live])
         dist.all_reduce(self.flat, group=self.group)
         if average:
             self.flat.mul_(1.0 / self.world)
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            if p.grad is not None:
-                p.grad.copy_(self.flat[off:off + n].view_as(p.grad))
-            off += n
+        if live:
+            torch._foreach_copy_([p.grad.reshape(-1) if p.grad.is_contiguous() else p.grad for _, p in live],
+                                 [v if p.grad.is_contiguous() else v.view_as(p.grad) for v, p in live])
 
 
 class ShardedTables:

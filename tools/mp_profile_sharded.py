@@ -1,62 +1,72 @@
-"""torchrun diagnostic: per-phase device time of the row-sharded (NVLink peer memory) gather / scatter / re-zero at
-config-2 shape, max over ranks."""
+"""torchrun diagnostic: per-kernel device time of the N-GPU DeepFM step (config-2 shape, tables row-sharded in NVLink peer
+memory): torch.profiler (CUPTI) around eager steps on every rank, kernel durations averaged per step, MAX over ranks.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/mp_profile_sharded.py
+
+Prints a markdown table on rank 0 (kept as profiles/r02_scale<N>_kernels.md).  Device times are per kernel; the step replayed
+as a CUDA graph (bench.py) is their sum minus overlap plus launch gaps."""
 import os
 import sys
+from collections import defaultdict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 import torch.distributed as dist
+from torch.profiler import profile, ProfilerActivity
 
 import bench
-from rec_pangu_b200 import dist as rdist, ops
-from rec_pangu_b200.models.ranking import DeepFM
+from rec_pangu_b200 import dist as rdist
 
 
 def main():
     rank, world, local = rdist.init_from_env('nccl')
     dev = torch.device('cuda', local)
-    enc = bench.make_enc()
-    B, D = bench.CFG['B'], bench.CFG['D']
-    torch.manual_seed(1029)
-    with torch.device(dev):
-        model = DeepFM(embedding_dim=D, hidden_units=bench.CFG['hidden'], enc_dict=enc)
-    st = rdist.shard_model_tables(model)
+    w = bench.WORKLOADS[os.environ.get('WORKLOAD', 'deepfm')]
+    model, enc, st = bench.build_model(w, dev, world)
     torch.cuda.empty_cache()
+    bucket = rdist.DenseGradBucket([p for n, p in model.named_parameters() if 'embedding_layer.' not in n])
     gen = torch.Generator(device=dev).manual_seed(1 + rank)
-    data = bench.synth_batch(enc, B, gen, device=dev)
-    emb = model.embedding_layer
-    idx = [data[c] for c in emb.emb_feature]
-    dn = [data[c] for c in emb.dense_feature]
+    labels = bench.label_names(w)
+    data = bench.synth_batch(enc, w['B'], gen, device=dev, labels=labels)
 
-    def timed(fn, iters=10):
-        for _ in range(2):
-            fn()
-        dist.barrier()
+    def step():
+        out = model(data)
+        (out['loss'] / world).backward()
+        bucket.all_reduce()
+        model.zero_grad()
+
+    for _ in range(3):
+        step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    n_steps = 4
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(n_steps):
+            step()
         torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda._sleep(int(4e7))
-        a.record()
-        for _ in range(iters):
-            fn()
-        b.record()
-        torch.cuda.synchronize()
-        t = torch.tensor([a.elapsed_time(b) * 1e3 / iters], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    res = {}
-    with torch.no_grad():
-        res['gather_fwd_sharded_us'] = timed(lambda: ops.gather_sharded(st, emb.tables(), idx, dn, want_fm=True))
-    res['barrier_us'] = timed(lambda: st.barrier())
-
-    def fwd_bwd():
-        x, fm, _ = ops.gather_sharded(st, emb.tables(), idx, dn, want_fm=True)
-        (x.sum() * 1e-6 + fm.sum() * 1e-6).backward()
-    res['gather_fwd+bwd(scatter+barrier)_us'] = timed(fwd_bwd, iters=5)
-    res['clean(rows_zero+barrier)_us'] = timed(lambda: (st.pending.append(idx), ops.sharded_clean(st)), iters=5)
+    per = defaultdict(float)
+    cnt = defaultdict(int)
+    for ev in prof.events():
+        if ev.device_type == torch.autograd.DeviceType.CUDA:
+            name = ev.name.split('(')[0].replace('void ', '').replace('rpb::', '')[:70]
+            per[name] += ev.device_time_total if hasattr(ev, 'device_time_total') else ev.cuda_time_total
+            cnt[name] += 1
+    names = sorted(per, key=lambda k: -per[k])[:24]
+    # same kernel set on every rank (same code path): max over ranks of the per-step time
+    vals = torch.tensor([per[n] / n_steps for n in names], device=dev, dtype=torch.float64)
+    obj = [names]
+    dist.broadcast_object_list(obj, src=0)
+    vals = torch.tensor([per.get(n, 0.0) / n_steps for n in obj[0]], device=dev, dtype=torch.float64)
+    vmax = vals.clone()
+    dist.all_reduce(vmax, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print('SHARDED_PROFILE', world, res, flush=True)
+        print(f'SHARDED_PROFILE world={world} workload={w["model"]} batch_per_gpu={w["B"]}')
+        print('| kernel | launches / step | us / step (rank 0) | us / step (max over ranks) |')
+        print('|---|---|---|---|')
+        for n, a, b in zip(obj[0], vals.tolist(), vmax.tolist()):
+            print(f'| `{n}` | {cnt[n] / n_steps:.1f} | {a:.1f} | {b:.1f} |')
+        print(f'| sum of the listed kernels | | {sum(vals.tolist()):.1f} | {sum(vmax.tolist()):.1f} |', flush=True)
     torch.cuda.synchronize()
     os._exit(0)
 
