@@ -372,6 +372,14 @@ typedef struct RpbSparseAdamDesc {
     const int32_t* step_dev;        /* optional DEVICE int32 step number (overrides `step`; see rpb_adam_multi) */
 } RpbSparseAdamDesc;
 int rpb_sparse_adam(const RpbSparseAdamDesc* d, void* stream);
+/* Exact-lazy Adam (results equal the reference's DENSE torch.optim.Adam, trainer.py:75, although only touched rows are ever
+ * accessed): stamps[f][row] = last optimizer step applied to the row.  rpb_sparse_adam_catchup replays, for the rows of the
+ * batch `idx` that is about to be READ, the zero-gradient steps they missed (moments decay, weight walks by its momentum) up
+ * to the current step (*step_dev, or `step`); `grads` is ignored.  rpb_sparse_adam_flush does the same for every row of one
+ * table (before a state_dict is taken).  rpb_sparse_adam then applies the step with gradients as before. */
+int rpb_sparse_adam_catchup(const RpbSparseAdamDesc* d, void* stream);
+int rpb_sparse_adam_flush(float* w, float* m, float* v, int32_t* stamp, int64_t rows, int32_t D, float lr, float beta1,
+                          float beta2, float eps, const int32_t* step_dev, int32_t step, void* stream);
 
 #ifdef __cplusplus
 }

@@ -115,6 +115,8 @@ SIGNATURES = {
     'rpb_adam_dense': (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, C.c_int, _vp]),
     'rpb_adam_multi': (C.c_int, [C.POINTER(AdamMultiDesc), _vp]),
     'rpb_sparse_adam': (C.c_int, [C.POINTER(SparseAdamDesc), _vp]),
+    'rpb_sparse_adam_catchup': (C.c_int, [C.POINTER(SparseAdamDesc), _vp]),
+    'rpb_sparse_adam_flush': (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _f32, _f32, _vp, _i32, _vp]),
     'rpb_autoint_attn_fwd': (C.c_int, [_vp, _i64, _vp, _i64, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     'rpb_autoint_attn_bwd': (C.c_int, [_vp, _i64, C.c_int, _vp, _vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
 }

@@ -117,6 +117,112 @@ sparse_adam_scalar_kernel(const __grid_constant__ SparseAdamParams p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Exact-lazy Adam (FusedAdam(exact=True)): results equal the reference's DENSE torch.optim.Adam (trainer.py:75), which moves
+// every row at every step — a row without gradient still decays its moments and walks by its momentum — while only rows a
+// batch touches are ever read or written.  stamp[row] = the last optimizer step whose update the row has received.  Before
+// a forward reads a row (catch-up kernel, launched from a forward pre-hook with the batch ids) and before a state_dict is
+// taken (flush kernel over all rows), the missed zero-gradient steps stamp+1 .. cur are replayed:
+//     m <- b1 m,  v <- b2 v,  w <- w - lr / (1 - b1^s) * m / (sqrt(v) / sqrt(1 - b2^s) + eps)        for s = stamp+1 .. cur
+// The walk terms shrink like 0.9^k, so after CATCHUP_ITERS steps the remaining ones are below fp32 resolution of the sum;
+// the moments of the rest of the gap decay in closed form (b^gap).
+constexpr int CATCHUP_ITERS = 320;
+
+__device__ __forceinline__ void catchup4(float4& w, float4& m, float4& v, int old, int cur, const AdamHyper& hy) {
+    const int gap = cur - old;
+    if (gap <= 0) return;
+    const bool zero = m.x == 0.f && m.y == 0.f && m.z == 0.f && m.w == 0.f;       // never-touched row: nothing moves
+    if (!zero) {
+        float pb1 = powf(hy.b1, (float)old), pb2 = powf(hy.b2, (float)old);
+        const int n = min(gap, CATCHUP_ITERS);
+        for (int k = 0; k < n; ++k) {
+            pb1 *= hy.b1; pb2 *= hy.b2;
+            const float a = hy.lr / (1.f - pb1), c = rsqrtf(1.f - pb2);
+            m.x *= hy.b1; m.y *= hy.b1; m.z *= hy.b1; m.w *= hy.b1;
+            v.x *= hy.b2; v.y *= hy.b2; v.z *= hy.b2; v.w *= hy.b2;
+            w.x -= a * (m.x / (sqrtf(v.x) * c + hy.eps)); w.y -= a * (m.y / (sqrtf(v.y) * c + hy.eps));
+            w.z -= a * (m.z / (sqrtf(v.z) * c + hy.eps)); w.w -= a * (m.w / (sqrtf(v.w) * c + hy.eps));
+        }
+        if (gap > n) {
+            const float d1 = powf(hy.b1, (float)(gap - n)), d2 = powf(hy.b2, (float)(gap - n));
+            m.x *= d1; m.y *= d1; m.z *= d1; m.w *= d1;
+            v.x *= d2; v.y *= d2; v.z *= d2; v.w *= d2;
+        }
+    }
+}
+
+// rows of the batch about to be read; lane 0 of a row group claims the row (stamp exchange), so a row hit by several samples is
+// caught up once.  `cur` = *step_dev = optimizer steps taken so far.
+template <int LPR>
+__global__ void __launch_bounds__(256)
+sparse_adam_catchup_kernel(const __grid_constant__ SparseAdamParams p) {
+    const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int cur = p.step_dev != nullptr ? *p.step_dev : p.step;
+    const int b_raw = (int)(gt / LPR), l = (int)(gt % LPR);
+    const bool valid = b_raw < p.B;
+    const int b = valid ? b_raw : p.B - 1;
+    const int DV = p.D >= 4 ? p.D / 4 : 1;
+    for (int f = 0; f < p.F; ++f) {
+        if (p.w[f] == nullptr) continue;
+        long long row = __ldg(p.idx[f] + b);
+        if ((unsigned long long)row >= (unsigned long long)p.rows[f]) row = 0;
+        int old = cur;
+        if (l == 0 && valid) old = atomicExch(p.stamp[f] + row, cur);
+        old = __shfl_sync(0xffffffffu, old, (threadIdx.x & 31) / LPR * LPR);
+        if (old < cur && l < DV) {
+            if (p.D >= 4) {
+                const size_t off = (size_t)row * p.D + l * 4;
+                float4 w = *reinterpret_cast<const float4*>(p.w[f] + off);
+                float4 m = *reinterpret_cast<const float4*>(p.m[f] + off);
+                float4 v = *reinterpret_cast<const float4*>(p.v[f] + off);
+                catchup4(w, m, v, old, cur, p.h);
+                *reinterpret_cast<float4*>(p.w[f] + off) = w;
+                *reinterpret_cast<float4*>(p.m[f] + off) = m;
+                *reinterpret_cast<float4*>(p.v[f] + off) = v;
+            } else {                                               // D = 1 (LR tables): lane 0 only (DV = 1)
+                float4 w = make_float4(p.w[f][row], 0.f, 0.f, 0.f), m = make_float4(p.m[f][row], 0.f, 0.f, 0.f);
+                float4 v = make_float4(p.v[f][row], 0.f, 0.f, 0.f);
+                catchup4(w, m, v, old, cur, p.h);
+                p.w[f][row] = w.x; p.m[f][row] = m.x; p.v[f][row] = v.x;
+            }
+        }
+    }
+}
+
+// every row of one table (state_dict / evaluation of the whole table): thread = (row, 4-float piece)
+__global__ void __launch_bounds__(256)
+sparse_adam_flush_kernel(float* __restrict__ w, float* __restrict__ m, float* __restrict__ v, int* __restrict__ stamp, long long rows,
+                         int D, AdamHyper hy, const int* __restrict__ step_dev, int step) {
+    const int DV = D >= 4 ? D / 4 : 1;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long row = t / DV;
+    const int l = (int)(t % DV);
+    if (row >= rows) return;
+    const int cur = step_dev != nullptr ? *step_dev : step;
+    const int old = stamp[row];
+    if (old < cur) {
+        if (D >= 4) {
+            const size_t off = (size_t)row * D + l * 4;
+            float4 ww = *reinterpret_cast<const float4*>(w + off), mm = *reinterpret_cast<const float4*>(m + off);
+            float4 vv = *reinterpret_cast<const float4*>(v + off);
+            catchup4(ww, mm, vv, old, cur, hy);
+            *reinterpret_cast<float4*>(w + off) = ww; *reinterpret_cast<float4*>(m + off) = mm; *reinterpret_cast<float4*>(v + off) = vv;
+        } else {
+            float4 ww = make_float4(w[row], 0.f, 0.f, 0.f), mm = make_float4(m[row], 0.f, 0.f, 0.f), vv = make_float4(v[row], 0.f, 0.f, 0.f);
+            catchup4(ww, mm, vv, old, cur, hy);
+            w[row] = ww.x; m[row] = mm.x; v[row] = vv.x;
+        }
+    }
+}
+// second pass: the stamps (a separate launch: every piece of a row must have read the old stamp first)
+__global__ void __launch_bounds__(256)
+sparse_adam_flush_stamp_kernel(int* __restrict__ stamp, long long rows, const int* __restrict__ step_dev, int step) {
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    const int cur = step_dev != nullptr ? *step_dev : step;
+    if (stamp[row] < cur) stamp[row] = cur;
+}
+
 }  // namespace rpb
 
 using namespace rpb;
@@ -182,4 +288,52 @@ RPB_API int rpb_sparse_adam(const RpbSparseAdamDesc* d, void* stream) {
     if (dv <= 8) return launch(std::integral_constant<int, 8>{});
     if (dv <= 16) return launch(std::integral_constant<int, 16>{});
     return launch(std::integral_constant<int, 32>{});
+}
+
+static int fill_sparse_params(const RpbSparseAdamDesc* d, SparseAdamParams& p) {
+    if (d == nullptr || d->B <= 0 || d->F <= 0 || d->D <= 0 || (d->step_dev == nullptr && d->step < 0)) return RPB_ERR_BAD_ARG;
+    if (d->F > RPB_MAX_FIELDS || (d->D != 1 && d->D % 4 != 0) || d->D > 128) return RPB_ERR_UNSUPPORTED;
+    for (int f = 0; f < d->F; ++f) {
+        p.w[f] = d->weights[f]; p.g[f] = nullptr; p.m[f] = d->exp_avg[f]; p.v[f] = d->exp_avg_sq[f];
+        p.stamp[f] = d->stamps[f];
+        p.idx[f] = reinterpret_cast<const long long*>(d->idx[f]);
+        p.rows[f] = d->rows[f];
+    }
+    p.B = d->B; p.F = d->F; p.D = d->D; p.step = d->step;
+    p.step_dev = d->step_dev;
+    p.h = make_hyper(d->lr, d->beta1, d->beta2, d->eps, 1);
+    return 0;
+}
+
+RPB_API int rpb_sparse_adam_catchup(const RpbSparseAdamDesc* d, void* stream) {
+    SparseAdamParams p{};
+    const int rc = fill_sparse_params(d, p);
+    if (rc != 0) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int dv = d->D >= 4 ? d->D / 4 : 1;
+    auto launch = [&](auto lt) -> int {
+        constexpr int LPR = decltype(lt)::value;
+        sparse_adam_catchup_kernel<LPR><<<ceil_div((long long)p.B * LPR, 256), 256, 0, st>>>(p);
+        return (int)cudaGetLastError();
+    };
+    if (dv <= 1) return launch(std::integral_constant<int, 1>{});
+    if (dv <= 2) return launch(std::integral_constant<int, 2>{});
+    if (dv <= 4) return launch(std::integral_constant<int, 4>{});
+    if (dv <= 8) return launch(std::integral_constant<int, 8>{});
+    if (dv <= 16) return launch(std::integral_constant<int, 16>{});
+    return launch(std::integral_constant<int, 32>{});
+}
+
+RPB_API int rpb_sparse_adam_flush(float* w, float* m, float* v, int32_t* stamp, int64_t rows, int32_t D, float lr, float beta1,
+                                  float beta2, float eps, const int32_t* step_dev, int32_t step, void* stream) {
+    if (w == nullptr || m == nullptr || v == nullptr || stamp == nullptr || rows <= 0 || D <= 0) return RPB_ERR_BAD_ARG;
+    if ((D != 1 && D % 4 != 0) || D > 128) return RPB_ERR_UNSUPPORTED;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int dv = D >= 4 ? D / 4 : 1;
+    const AdamHyper hy = make_hyper(lr, beta1, beta2, eps, 1);
+    sparse_adam_flush_kernel<<<ceil_div(rows * dv, 256), 256, 0, st>>>(w, m, v, stamp, rows, D, hy, step_dev, step);
+    RPB_LAUNCH_CHECK();
+    sparse_adam_flush_stamp_kernel<<<ceil_div(rows, 256), 256, 0, st>>>(stamp, rows, step_dev, step);
+    RPB_LAUNCH_CHECK();
+    return 0;
 }

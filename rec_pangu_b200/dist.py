@@ -117,12 +117,20 @@ class ShardedTables:
         self.weights, self.grads, self._handles = [], [], []
         w_ptrs = torch.zeros(F * G, dtype=torch.int64)
         g_ptrs = torch.zeros(F * G, dtype=torch.int64)
+        # all gradient shards of the layer live in ONE symmetric allocation: the per-step re-zero is one memset instead of F
+        # fill launches (26 x ~2.3 us at config 2), one rendezvous instead of F
+        ns = [shard_rows(r, G) for r in self.rows]
+        seg = [(n * self.D + 3) // 4 * 4 for n in ns]             # floats per table, 16-byte aligned segments (D = 1 tables)
+        offs = [sum(seg[:f]) for f in range(F)]
+        self.grad_flat = symm.empty((sum(seg),), dtype=torch.float32, device=dev)
+        hgf = symm.rendezvous(self.grad_flat, self.group)
+        self.grad_flat.zero_()
+        self._handles.append(hgf)
         for f, c in enumerate(self.cols):
-            n = shard_rows(self.rows[f], G)
+            n = ns[f]
             w = symm.empty((n, self.D), dtype=torch.float32, device=dev)
-            g = symm.empty((n, self.D), dtype=torch.float32, device=dev)
+            g = self.grad_flat[offs[f]:offs[f] + n * self.D].view(n, self.D)
             hw = symm.rendezvous(w, self.group)
-            hg = symm.rendezvous(g, self.group)
             if init is None:
                 src = full_tables[c] if full_tables is not None else emb_layer.embedding_layer[c].weight.data
                 if src.device.type == 'meta':
@@ -137,13 +145,12 @@ class ShardedTables:
                 n_mine = len(range(self.rank, self.rows[f], G))
                 if n_mine < n:
                     w[n_mine:].zero_()                       # padding rows of the last shards
-            g.zero_()
             for r in range(G):
                 w_ptrs[f * G + r] = int(hw.buffer_ptrs[r])
-                g_ptrs[f * G + r] = int(hg.buffer_ptrs[r])
+                g_ptrs[f * G + r] = int(hgf.buffer_ptrs[r]) + offs[f] * 4
             self.weights.append(w)
             self.grads.append(g)
-            self._handles += [hw, hg]
+            self._handles.append(hw)
         self.w_tab = w_ptrs.to(dev)
         self.g_tab = g_ptrs.to(dev)
         self._one = torch.zeros(1, device=dev)

@@ -487,8 +487,12 @@ def sharded_clean(st):
                 torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN, group=st.group)
             mode = st._clean_mode = 'dense' if float(t.item()) > 0.5 else 'sparse'
         if mode == 'dense':
-            for g in st.grads:
-                g.zero_()
+            flat = getattr(st, 'grad_flat', None)
+            if flat is not None:
+                flat.zero_()                      # every gradient shard of the layer in one memset
+            else:
+                for g in st.grads:
+                    g.zero_()
             st.barrier()
             st.pending = []
             return

@@ -224,9 +224,11 @@ def check_optimizer_then_zero_grad(rank, world, dev):
         w_full = st.full_table(f)
         r = ref.embedding_layer.embedding_layer[c].weight.data
         err = (w_full - r).abs().max().item()
-        assert err <= 2e-5, (c, err)
+        # Adam's update is lr * m / sqrt(v): a row whose gradient is summed in another order moves by a slightly different
+        # fraction of lr = 1e-2 (2.3e-5 at N = 8); a LOST gradient row (the race this guards against) moves by ~lr
+        assert err <= 2e-4, (c, err)
     for (n, p), (_, q) in zip(model.dnn.named_parameters(), ref.dnn.named_parameters()):
-        assert (p - q).abs().max().item() <= 2e-5, n
+        assert (p - q).abs().max().item() <= 2e-4, n
     dist.barrier()
 
 
