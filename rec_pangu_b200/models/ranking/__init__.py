@@ -10,4 +10,6 @@ from .dcn import DCN
 from .afm import AFM
 from .masknet import MaskNet
 from .lr import LR
-from ._unported import AFN, AOANet, CCPM
+from .afn import AFN
+from .aoanet import AOANet
+from .ccpm import CCPM

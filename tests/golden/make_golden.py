@@ -29,7 +29,7 @@ sys.path.insert(0, '/root/reference')
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
-from rec_pangu.models.ranking import DeepFM, xDeepFM, AutoInt, DCN, FiBiNet, FM, WDL, NFM, AFM, MaskNet  # noqa: E402
+from rec_pangu.models.ranking import DeepFM, xDeepFM, AutoInt, DCN, FiBiNet, FM, WDL, NFM, AFM, MaskNet, AFN, AOANet, CCPM  # noqa: E402
 from rec_pangu.models.multi_task import MMOE, ShareBottom, OMOE, MLMMOE, ESSM, AITM  # noqa: E402
 from rec_pangu.models.layers import LR_Layer  # noqa: E402
 from rec_pangu.models.layers import (FM_Layer, MLP, CrossNet, CompressedInteractionNet, SENET_Layer,  # noqa: E402
@@ -275,6 +275,9 @@ def run_round2():
     run_model('masknet_serial', MaskNet, {'hidden_units': [16, 8], 'block_num': 2, 'use_parallel': False}, n_sparse=6, seed=6029)
     run_lr()
     run_aitm()
+    run_model('afn', AFN, {'dnn_hidden_units': [16, 8], 'afn_hidden_units': [16, 8], 'logarithmic_neurons': 3}, n_sparse=6, seed=7029)
+    run_model('aoanet', AOANet, {'dnn_hidden_units': [16, 8], 'num_interaction_layers': 2, 'num_subspaces': 3}, n_sparse=6, seed=8029)
+    run_model('ccpm', CCPM, {'channels': [3, 2], 'kernel_heights': [4, 3]}, n_sparse=6, seed=9029)
 
 
 if __name__ == '__main__':

@@ -25,7 +25,7 @@ def _logit(p):
 
 # 'afm' = the FiBiNet class under the reference's other name (passed on a B200 in the round-1 bench record: afm_golden.parity_ok)
 RANKING_GOLDEN = ['deepfm', 'deepfm_d16', 'fm', 'wdl', 'nfm', 'dcn', 'xdeepfm', 'autoint', 'autoint_l2', 'fibinet', 'afm',
-                  'masknet', 'masknet_serial', 'lr']
+                  'masknet', 'masknet_serial', 'lr', 'afn', 'aoanet', 'ccpm']
 
 
 @pytest.mark.parametrize('name', RANKING_GOLDEN)
