@@ -19,6 +19,7 @@ int g_fused_fetch_warps = 8;
 int g_fused_ring = 0;
 int g_fused_tc_tail = 1;    // tower-tail layers of the one-kernel forward on tcgen05 (0 = fp32 CUDA-core tail)
 int g_tower_bwd_tc = 0;     // opt-in until measured on hardware
+int g_cin_tc = 1;
 int g_autoint_vec = 1;      // float4 lane I/O: bit-identical, 3.60 -> 3.18 ms per config-4 step (BENCH_r01 experiments.safe.autoint_vec)
 int g_l2_persist = 0;       // opt-in until measured on hardware
 size_t g_l2_aside = 0, g_l2_max_window = 0;
@@ -27,7 +28,7 @@ size_t g_l2_aside = 0, g_l2_max_window = 0;
 // the stream, so reuse is safe for the single-stream execution model of the reference's training loop.  Growth uses
 // cudaMalloc and therefore must not happen inside CUDA-graph capture: run one eager warm-up step first.
 void* workspace(int slot, size_t bytes, int* err) {
-    constexpr int kMaxDev = 16, kSlots = 8;
+    constexpr int kMaxDev = 16, kSlots = 12;
     static void* ptr[kMaxDev][kSlots] = {};
     static size_t cap[kMaxDev][kSlots] = {};
     int dev = 0;
@@ -90,6 +91,7 @@ RPB_API int rpb_set_option(const char* name, int64_t value) {
         rpb::g_l2_persist = value != 0;
         return 0;
     }
+    if (n == "cin_tc") { rpb::g_cin_tc = value != 0; return 0; }
     if (n == "autoint_vec") { rpb::g_autoint_vec = value != 0; return 0; }
     if (n == "tower_bwd_tc") { rpb::g_tower_bwd_tc = value != 0; return 0; }
     if (n == "fused_gather_warps") { if (value != 4 && value != 8) return RPB_ERR_BAD_ARG; rpb::g_fused_gather_warps = (int)value; return 0; }

@@ -371,12 +371,37 @@ static int pack_weights(const CinMeta& meta, const CinPtrs& ptrs, float** Wt_out
 
 using namespace rpb;
 
+namespace rpb {
+bool cin_tc_shape_ok(int F, int D, int L, const int* units);                                                   // cin_tc.cu
+int cin_layer_fwd_tc(int F, int M, int U, int D, const float* W, const float* bias, const float* x0, long long ld0, const float* xk,
+                     long long ldk, float* xout, long long ldo, float* pooled, long long ldp, int B, cudaStream_t st);
+int cin_layer_bwd_tc_c(int F, int M, const float* W, const float* x0, long long ld0, const float* xk, long long ldk, const float* dpooled,
+                       long long lddp, const float* gx, long long ldgx, float* gout, long long ldgo, float* db, float* dxk, long long lddxk,
+                       float* de, long long ldde, int de_accumulate, int B, cudaStream_t st);
+}
+
 RPB_API int rpb_cin_fwd(const float* e, int64_t lde, int B, int F, int D, int L, const int32_t* units,
                         const float* const* W, const float* const* bias, float* pooled, int64_t ldp, void* stream) {
     if (e == nullptr || pooled == nullptr || W == nullptr || bias == nullptr || B <= 0) return RPB_ERR_BAD_ARG;
     CinHost h = cin_meta(F, L, units);
     if (!h.ok) return RPB_ERR_UNSUPPORTED;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (cin_tc_shape_ok(F, D, L, units)) {
+        // tensor-core path (cin_tc.cu): one launch per layer, X_{k+1} [B, U, D] ping-pongs through workspace slot 3
+        int werr = 0;
+        const size_t per = (size_t)B * units[0] * D;
+        float* xs = L > 1 ? static_cast<float*>(workspace(3, 2 * per * sizeof(float), &werr)) : nullptr;
+        if (L > 1 && xs == nullptr) return werr;
+        const float* xk = e; long long ldk = lde;
+        for (int k = 0; k < L; ++k) {
+            float* xout = k + 1 < L ? xs + (size_t)(k & 1) * per : nullptr;
+            const int rc = cin_layer_fwd_tc(F, h.meta.M[k], units[k], D, W[k], bias[k], e, lde, xk, ldk, xout, (long long)units[k] * D,
+                                            pooled + h.meta.p_off[k], ldp, B, st);
+            if (rc != 0) return rc;
+            xk = xout; ldk = (long long)units[k] * D;
+        }
+        return 0;
+    }
     int maxu = 0;
     for (int k = 0; k < L; ++k) maxu = max(maxu, units[k]);
     float *Wt = nullptr, *bcat = nullptr;
@@ -423,9 +448,34 @@ RPB_API int rpb_cin_bwd(const float* e, int64_t lde, int B, int F, int D, int L,
     if (spill == nullptr) return werr;
     float* Gout = spill;
     float* Xout = spill + per;
+    bool tc_done = false;
+    if (cin_tc_shape_ok(F, D, L, units)) {
+        // tensor-core path (cin_tc.cu): recompute X_1 .. X_{L-1} (one launch per layer), then per layer, top down, the dZ GEMM
+        // with the gradient contraction in its epilogue; G_k and X_k are spilled in the layout the weight-gradient kernel reads
+        const long long ldu = (long long)h.meta.u_total * D;
+        float* dxb = static_cast<float*>(workspace(3, 2 * (size_t)B * units[0] * D * sizeof(float), &werr));
+        if (dxb == nullptr) return werr;
+        const size_t dper = (size_t)B * units[0] * D;
+        for (int k = 0; k + 1 < L; ++k) {
+            rc = cin_layer_fwd_tc(F, h.meta.M[k], units[k], D, W[k], bias ? bias[k] : nullptr, e, lde,
+                                  k == 0 ? e : Xout + (size_t)h.meta.p_off[k - 1] * D, k == 0 ? lde : ldu,
+                                  Xout + (size_t)h.meta.p_off[k] * D, ldu, nullptr, 0, B, st);
+            if (rc != 0) return rc;
+        }
+        for (int k = L - 1; k >= 0; --k) {
+            rc = cin_layer_bwd_tc_c(F, h.meta.M[k], W[k], e, lde, k == 0 ? e : Xout + (size_t)h.meta.p_off[k - 1] * D, k == 0 ? lde : ldu,
+                                    dpooled + h.meta.p_off[k], lddp, k == L - 1 ? nullptr : dxb + (size_t)((k + 1) & 1) * dper,
+                                    (long long)units[k] * D, Gout + (size_t)h.meta.p_off[k] * D, ldu, nullptr /* db: the weight-gradient kernel sums it */,
+                                    k > 0 ? dxb + (size_t)(k & 1) * dper : nullptr, (long long)h.meta.M[k] * D, de, ldde,
+                                    k == L - 1 ? accumulate : 1, B, st);
+            if (rc != 0) return rc;
+        }
+        tc_done = true;
+    }
     rc = cin_dispatch(D, maxu, [&](auto dt, auto ut) -> int {
         constexpr int DD = decltype(dt)::value, MU = decltype(ut)::value;
         constexpr int SPC = 256 / DD;
+        if (!tc_done) {
         const size_t smem = ((size_t)h.meta.w_total + ((h.meta.u_total + 3) & ~3) + (size_t)SPC * F * DD * 2 +
                              (size_t)SPC * h.meta.u_total * DD) * sizeof(float);
         if (smem > 220 * 1024) return RPB_ERR_UNSUPPORTED;
@@ -436,6 +486,7 @@ RPB_API int rpb_cin_bwd(const float* e, int64_t lde, int B, int F, int D, int L,
                                                                accumulate, Gout, Xout);
         int r2 = (int)cudaGetLastError();
         if (r2 != 0) return r2;
+        }
         // weight gradients
         const int slabs = max(1, min(ceil_div(B, 8), (148 * 2) / L));
         int slab = ceil_div(B, slabs);

@@ -1,0 +1,482 @@
+// xDeepFM Compressed Interaction Network on tcgen05 (reference: models/layers/interaction.py:144-171).
+//
+// One CIN layer is a GEMM whose A operand does not exist in memory:
+//     X_{k+1}[(b,d), u] = sum_j Z[(b,d), j] * W_k[u, j] + bias[u],      Z[(b,d), h*M + m] = X0[b,h,d] * Xk[b,m,d]
+// rows = (sample, embedding dim) pairs (1 M rows at config 3), K = F*M (676 / 416), N = U = 16.  The fp32 CUDA-core kernels
+// of cin.cu form Z in registers and pay 4 LDS.128 of weights per 17 FP instructions (3.6 ms forward, 14 ms backward at
+// config 3, ~1 % of the HBM roofline, 0 % tensor pipe: profiles/r01_kernels.md).  Here the outer product is formed in
+// registers by "split" warps — thread = row (b,d) = tensor-memory lane, X0[b,:,d] and Xk[b,:,d] live in its registers for the
+// whole tile, every (h, m) of a k-block is a compile-time constant — split into (hi, lo) and written straight into tensor
+// memory as the TS-mode A operand, exactly like the split warps of deepfm_fwd_fs_kernel; the pre-split weights
+// [W hi ; W lo] (stacked N = 32) stay resident in shared memory; 3xTF32 keeps the 1e-4 parity bound.
+//
+// cin_fwd_tc_kernel<F, M>: warps 0 = weight TMA (once per CTA), 1 = MMA issuer, 2-9 = split (warps w and w+4 share a lane
+// quarter and take columns 0-15 / 16-31 of every k-block), 10-13 = epilogue (accumulator -> + bias -> X_{k+1}[b,u,d] and the
+// pooled sums over d).  Persistent: one CTA per SM walks tiles of 128 rows = 8 samples.
+#include "tc_ptx.cuh"
+
+namespace rpb {
+
+constexpr int CT_D = 16;                 // embedding dim these kernels are built for (one 64-byte row per field)
+constexpr int CT_U = 16;                 // units per layer
+constexpr int CT_THREADS = 14 * 32;
+constexpr int CT_OPN = 6;                // tensor-memory operand ring: 6 x 64 columns (A hi 32 | A lo 32)
+constexpr int CT_ACC = 2 * CT_U;         // accumulator columns: [A.Whi^T | A.Wlo^T]
+constexpr int CT_A_COL = 2 * CT_ACC;     // two accumulator buffers, then the operand ring
+constexpr int CT_KB_BYTES = 2 * CT_U * TC_BLOCK_K * 4;     // one resident weight k-block: 32 rows x 128 B = 4 KiB
+
+struct CinTcParams {
+    const float* x0; long long ld0;      // X0[b,h,d] = x0[b * ld0 + h * 16 + d]            (feature row of the gather)
+    const float* xk; long long ldk;      // Xk[b,m,d] = xk[b * ldk + m * 16 + d]            (layer 0: = x0)
+    const float* bias;                   // [16] or null
+    float* xout; long long ldo;          // X_{k+1}[b,u,d] = xout[b * ldo + u * 16 + d], or null
+    float* pooled; long long ldp;        // pooled[b * ldp + u] = sum_d X_{k+1}[b,u,d], or null
+    int B, m_tiles;
+};
+
+// z columns of k-block KB, half HF, for the thread's row: compile-time (h, m) per column
+template <int F, int M, int KB, int HF>
+__device__ __forceinline__ void cin_zcols(const float (&x0)[F], const float (&xk)[M], uint32_t (&hi)[16], uint32_t (&lo)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        constexpr int dummy = 0; (void)dummy;
+        const int j = KB * TC_BLOCK_K + HF * 16 + i;
+        float z = 0.f;
+        if (j < F * M) z = x0[j / M] * xk[j % M];                 // j, M, F are compile-time after unrolling
+        hi[i] = __float_as_uint(z) & 0xFFFFE000u;
+        lo[i] = __float_as_uint(z - __uint_as_float(hi[i]));
+    }
+}
+
+template <int F, int M, int HF, int KB, int NKB>
+struct CinSplitLoop {
+    static __device__ __forceinline__ void run(const float (&x0)[F], const float (&xk)[M], uint32_t tmem_base, uint32_t lane_addr,
+                                               uint64_t* ready_op, uint64_t* empty_op, uint32_t g0, int lane) {
+        uint32_t hi[16], lo[16];
+        cin_zcols<F, M, KB, HF>(x0, xk, hi, lo);
+        const uint32_t g = g0 + KB;
+        const int o = g % CT_OPN;
+        mbar_wait(&empty_op[o], ((g / CT_OPN) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t ta = tmem_base + CT_A_COL + (uint32_t)o * 64u + lane_addr + (uint32_t)HF * 16u;
+        tmem_st16(ta, hi);
+        tmem_st16(ta + 32u, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ready_op[o]);
+        CinSplitLoop<F, M, HF, KB + 1, NKB>::run(x0, xk, tmem_base, lane_addr, ready_op, empty_op, g0, lane);
+    }
+};
+template <int F, int M, int HF, int NKB>
+struct CinSplitLoop<F, M, HF, NKB, NKB> {
+    static __device__ __forceinline__ void run(const float (&)[F], const float (&)[M], uint32_t, uint32_t, uint64_t*, uint64_t*, uint32_t, int) {}
+};
+
+template <int F, int M>
+__global__ void __launch_bounds__(CT_THREADS, 1)
+cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo, const __grid_constant__ CinTcParams p) {
+    constexpr int NKB = (F * M + TC_BLOCK_K - 1) / TC_BLOCK_K;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* w_base = smem;                                               // NKB x 4 KiB resident [W hi ; W lo] k-blocks
+    uint64_t* bars = reinterpret_cast<uint64_t*>(w_base + NKB * CT_KB_BYTES);
+    uint64_t* w_full = bars;                       // [1] weights landed
+    uint64_t* ready_op = w_full + 1;               // [CT_OPN] operand written (8 arrivals: one per split warp)
+    uint64_t* empty_op = ready_op + CT_OPN;        // [CT_OPN]
+    uint64_t* tmem_full = empty_op + CT_OPN;       // [2]
+    uint64_t* tmem_empty = tmem_full + 2;          // [2] 4 arrivals
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int my_tiles = ((int)blockIdx.x < p.m_tiles) ? (p.m_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    if (threadIdx.x == 0) {
+        mbar_init(w_full, 1);
+        for (int s = 0; s < CT_OPN; ++s) { mbar_init(&ready_op[s], 8); mbar_init(&empty_op[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(w_full, (uint32_t)(NKB * CT_KB_BYTES));
+            for (int kb = 0; kb < NKB; ++kb) {
+                tma_load_2d(w_base + (size_t)kb * CT_KB_BYTES, &tmWhi, w_full, kb * TC_BLOCK_K, 0);
+                tma_load_2d(w_base + (size_t)kb * CT_KB_BYTES + CT_KB_BYTES / 2, &tmWlo, w_full, kb * TC_BLOCK_K, 0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(TC_BLOCK_M, CT_ACC);
+            mbar_wait(w_full, 0u);
+            uint32_t g = 0;
+            for (int t = 0; t < my_tiles; ++t) {
+                const uint32_t acc = (uint32_t)t & 1u;
+                mbar_wait(&tmem_empty[acc], (((uint32_t)t >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * CT_ACC;
+                for (int kb = 0; kb < NKB; ++kb, ++g) {
+                    const int o = g % CT_OPN;
+                    mbar_wait(&ready_op[o], (g / CT_OPN) & 1u);
+                    tc_fence_after();
+                    const uint32_t b_addr = smem_u32(w_base + (size_t)kb * CT_KB_BYTES);
+                    const uint32_t ta_hi = tmem_base + CT_A_COL + (uint32_t)o * 64u, ta_lo = ta_hi + 32u;
+#pragma unroll
+                    for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
+                        const uint64_t db = make_kmajor_sw128_desc(b_addr + k * TC_UMMA_K * 4);
+                        umma_tf32_ts(d_tmem, ta_lo + k * TC_UMMA_K, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        umma_tf32_ts(d_tmem, ta_hi + k * TC_UMMA_K, db, idesc, 1u);
+                    }
+                    umma_commit(&empty_op[o]);
+                }
+                umma_commit(&tmem_full[acc]);
+            }
+        }
+    } else if (warp < 10) {
+        // ---------------- split warps: thread = row (b, d) of the tile; X0[b,:,d] and Xk[b,:,d] in registers
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        uint32_t g0 = 0;
+        for (int t = 0; t < my_tiles; ++t, g0 += NKB) {
+            const long long b = (long long)((int)blockIdx.x + t * (int)gridDim.x) * 8 + (row >> 4);
+            const int d = row & 15;
+            float x0[F], xk[M];
+            if (b < p.B) {
+                const float* r0 = p.x0 + (size_t)b * p.ld0 + d;
+                const float* rk = p.xk + (size_t)b * p.ldk + d;
+#pragma unroll
+                for (int h = 0; h < F; ++h) x0[h] = __ldg(r0 + h * CT_D);
+#pragma unroll
+                for (int m = 0; m < M; ++m) xk[m] = __ldg(rk + m * CT_D);
+            } else {
+#pragma unroll
+                for (int h = 0; h < F; ++h) x0[h] = 0.f;
+#pragma unroll
+                for (int m = 0; m < M; ++m) xk[m] = 0.f;
+            }
+            if (half == 0) CinSplitLoop<F, M, 0, 0, NKB>::run(x0, xk, tmem_base, lane_addr, ready_op, empty_op, g0, lane);
+            else CinSplitLoop<F, M, 1, 0, NKB>::run(x0, xk, tmem_base, lane_addr, ready_op, empty_op, g0, lane);
+        }
+    } else {
+        // ---------------- epilogue warps: accumulator (both stacked halves) + bias -> X_{k+1}, pooled sums over d
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        float bv[CT_U];
+#pragma unroll
+        for (int u = 0; u < CT_U; ++u) bv[u] = p.bias != nullptr ? __ldg(p.bias + u) : 0.f;
+        for (int t = 0; t < my_tiles; ++t) {
+            const uint32_t acc = (uint32_t)t & 1u;
+            const long long b = (long long)((int)blockIdx.x + t * (int)gridDim.x) * 8 + (row >> 4);
+            const int d = row & 15;
+            mbar_wait(&tmem_full[acc], ((uint32_t)t >> 1) & 1u);
+            tc_fence_after();
+            uint32_t a0[16], a1[16];
+            tmem_ld16(tmem_base + acc * CT_ACC + lane_addr, a0);
+            tmem_ld16(tmem_base + acc * CT_ACC + lane_addr + CT_U, a1);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            const bool valid = b < p.B;
+#pragma unroll
+            for (int u = 0; u < CT_U; ++u) {
+                const float v = __uint_as_float(a0[u]) + __uint_as_float(a1[u]) + bv[u];
+                if (valid && p.xout != nullptr) p.xout[(size_t)b * p.ldo + u * CT_D + d] = v;
+                if (p.pooled != nullptr) {
+                    const float s = group_sum<CT_D>(v);
+                    if (valid && d == 0) p.pooled[(size_t)b * p.ldp + u] = s;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+template <int F, int M>
+static int cin_fwd_tc_launch(const float* W, const CinTcParams& p, cudaStream_t st) {
+    constexpr int NKB = (F * M + TC_BLOCK_K - 1) / TC_BLOCK_K;
+    CUtensorMap tmWhi, tmWlo;
+    int rc = tc_prepare_weight(W, F * M, CT_U, F * M, &tmWhi, &tmWlo, st);
+    if (rc != 0) return rc;
+    const size_t smem = (size_t)NKB * CT_KB_BYTES + (1 + 2 * CT_OPN + 4) * 8 + 16 + 1024;
+    cudaError_t e = cudaFuncSetAttribute(cin_fwd_tc_kernel<F, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    cin_fwd_tc_kernel<F, M><<<min(p.m_tiles, 148), CT_THREADS, smem, st>>>(tmWhi, tmWlo, p);
+    return (int)cudaGetLastError();
+}
+
+// One CIN layer forward on tensor cores.  Returns RPB_ERR_UNSUPPORTED for shapes outside the instantiated (F, M) pairs.
+int cin_layer_fwd_tc(int F, int M, int U, int D, const float* W, const float* bias, const float* x0, long long ld0, const float* xk,
+                     long long ldk, float* xout, long long ldo, float* pooled, long long ldp, int B, cudaStream_t st) {
+    if (D != CT_D || U != CT_U || !g_gemm_v2) return RPB_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(W) & 15u) != 0) return RPB_ERR_UNSUPPORTED;
+    CinTcParams p{};
+    p.x0 = x0; p.ld0 = ld0; p.xk = xk; p.ldk = ldk; p.bias = bias; p.xout = xout; p.ldo = ldo; p.pooled = pooled; p.ldp = ldp;
+    p.B = B; p.m_tiles = ceil_div(B, 8);
+    if (F == 26 && M == 26) return cin_fwd_tc_launch<26, 26>(W, p, st);
+    if (F == 26 && M == 16) return cin_fwd_tc_launch<26, 16>(W, p, st);
+    return RPB_ERR_UNSUPPORTED;
+}
+
+// =====================================================================================================================
+// Backward of one layer, part A (per-sample gradients):  dZ[(b,d), j] = sum_u G[(b,d), u] * W_k[u, j]  (rows x 16 x F*M GEMM),
+// consumed straight out of the accumulator:  dXk[b,m,d] += dZ[., h*M+m] * X0[b,h,d],   dX0[b,h,d] += dZ[., h*M+m] * Xk[b,m,d].
+// G = dL/dX_{k+1} = dpooled (broadcast over d) + the dXk the layer above produced.  Thread = row (b, d) on both sides of the
+// tensor core: "G" warps form G, spill it for the weight-gradient kernel, split it into the TS-mode A operand (K = 16);
+// epilogue warps hold X0[b,:,d], Xk[b,:,d] and the two gradient vectors in registers and read dZ 16 columns at a time; every
+// (h, m) is a compile-time constant.  W_k^T hi / lo ([F*M rows, 16 -> 32 zero-padded columns], SWIZZLE_128B) resident in smem;
+// 3 MMAs per k-step (hi.hi + lo.hi + hi.lo) into NT-column accumulators, double buffered.
+constexpr int CB_THREADS = 10 * 32;      // 0 weights, 1 MMA, 2-5 G warps, 6-9 epilogue warps
+
+struct CinBwdParams {
+    const float* x0; long long ld0;
+    const float* xk; long long ldk;
+    const float* dpooled; long long lddp;        // + p_off_k already applied
+    const float* gx; long long ldgx;             // dXk of the layer above [B, 16, 16] or null (top layer)
+    float* gout; long long ldgo;                 // G spill for the weight gradient: gout[b * ldgo + u * 16 + d]
+    float* db;                                   // [16] accumulated (atomics), or null
+    float* dxk; long long lddxk;                 // k > 0: dXk[b,m,d] written (-> gx of the layer below); k == 0: null
+    float* de; long long ldde; int de_accumulate;    // dX0 (+ dXk when k == 0) added into / written to de[b,h,d]
+    int B, m_tiles;
+};
+
+template <int F, int M, int NT, int NTI, int C0>
+struct CinDzCols {
+    // columns C0 .. C0+15 of N-tile NTI (global j = NTI*NT + C0 + i): dxk[m] += dz * x0[h], dx0[h] += dz * xk[m]
+    static __device__ __forceinline__ void run(uint32_t acc_addr, const float (&x0)[F], const float (&xk)[M], float (&dx0)[F], float (&dxk)[M]) {
+        if constexpr (C0 < NT && NTI * NT + C0 < F * M) {
+            uint32_t a[16];
+            tmem_ld16(acc_addr + (uint32_t)C0, a);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int j = NTI * NT + C0 + i;
+                if (j < F * M) {
+                    const float dz = __uint_as_float(a[i]);
+                    dxk[j % M] = fmaf(dz, x0[j / M], dxk[j % M]);
+                    dx0[j / M] = fmaf(dz, xk[j % M], dx0[j / M]);
+                }
+            }
+            CinDzCols<F, M, NT, NTI, C0 + 16>::run(acc_addr, x0, xk, dx0, dxk);
+        }
+    }
+};
+
+template <int F, int M, int NT, int NTILES>
+__global__ void __launch_bounds__(CB_THREADS, 1)
+cin_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo, const __grid_constant__ CinBwdParams p) {
+    constexpr int NP = NT * NTILES;                                       // padded F*M
+    constexpr uint32_t ACC0 = 0, A_COL = 2 * NT;                          // two NT-column accumulators, then 2 x 32 operand columns
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* w_hi = smem;                                                 // [NP rows][128 B]: W^T hi (16 valid columns, 16 zero)
+    uint8_t* w_lo = w_hi + (size_t)NP * 128;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(w_lo + (size_t)NP * 128);
+    uint64_t* w_full = bars;                       // [1]
+    uint64_t* a_ready = w_full + 1;                // [2] G operand of a tile written (4 arrivals)
+    uint64_t* a_empty = a_ready + 2;               // [2] its MMAs are done
+    uint64_t* acc_full = a_empty + 2;              // [2]
+    uint64_t* acc_empty = acc_full + 2;            // [2] 4 arrivals
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float* db_part = reinterpret_cast<float*>(tmem_ptr + 4);              // [4 warps][16]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int my_tiles = ((int)blockIdx.x < p.m_tiles) ? (p.m_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    if (threadIdx.x == 0) {
+        mbar_init(w_full, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&a_ready[s], 4); mbar_init(&a_empty[s], 1); mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(w_full, (uint32_t)(2 * NP * 128));
+            for (int nt = 0; nt < NTILES; ++nt) {
+                tma_load_2d(w_hi + (size_t)nt * NT * 128, &tmWhi, w_full, 0, nt * NT);
+                tma_load_2d(w_lo + (size_t)nt * NT * 128, &tmWlo, w_full, 0, nt * NT);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(TC_BLOCK_M, NT);
+            mbar_wait(w_full, 0u);
+            uint32_t n_acc = 0;
+            for (int t = 0; t < my_tiles; ++t) {
+                const uint32_t ab = (uint32_t)t & 1u;
+                mbar_wait(&a_ready[ab], ((uint32_t)t >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t ta_hi = tmem_base + A_COL + ab * 32u, ta_lo = ta_hi + 16u;
+                for (int nt = 0; nt < NTILES; ++nt, ++n_acc) {
+                    const uint32_t buf = n_acc & 1u;
+                    mbar_wait(&acc_empty[buf], ((n_acc >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + ACC0 + buf * NT;
+                    const uint32_t bh = smem_u32(w_hi + (size_t)nt * NT * 128), bl = smem_u32(w_lo + (size_t)nt * NT * 128);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {                          // K = 16 = 2 k-steps of 8
+                        const uint64_t dh = make_kmajor_sw128_desc(bh + k * TC_UMMA_K * 4), dl = make_kmajor_sw128_desc(bl + k * TC_UMMA_K * 4);
+                        umma_tf32_ts(d_tmem, ta_lo + k * TC_UMMA_K, dh, idesc, k > 0 ? 1u : 0u);
+                        umma_tf32_ts(d_tmem, ta_hi + k * TC_UMMA_K, dl, idesc, 1u);
+                        umma_tf32_ts(d_tmem, ta_hi + k * TC_UMMA_K, dh, idesc, 1u);
+                    }
+                    umma_commit(&acc_full[buf]);
+                }
+                umma_commit(&a_empty[ab]);
+            }
+        }
+    } else if (warp < 6) {
+        // ---------------- G warps: thread = row (b, d): G[u] = dpooled[b, u] + gx[b, u, d]; spill, bias gradient, A operand
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        float dbs[CT_U];
+#pragma unroll
+        for (int u = 0; u < CT_U; ++u) dbs[u] = 0.f;
+        for (int t = 0; t < my_tiles; ++t) {
+            const long long b = (long long)((int)blockIdx.x + t * (int)gridDim.x) * 8 + (row >> 4);
+            const int d = row & 15;
+            float g[CT_U];
+            if (b < p.B) {
+#pragma unroll
+                for (int u = 0; u < CT_U; ++u) {
+                    float v = __ldg(p.dpooled + (size_t)b * p.lddp + u);
+                    if (p.gx != nullptr) v += __ldg(p.gx + (size_t)b * p.ldgx + u * CT_D + d);
+                    g[u] = v;
+                    dbs[u] += v;
+                    if (p.gout != nullptr) p.gout[(size_t)b * p.ldgo + u * CT_D + d] = v;
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < CT_U; ++u) g[u] = 0.f;
+            }
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int u = 0; u < CT_U; ++u) {
+                hi[u] = __float_as_uint(g[u]) & 0xFFFFE000u;
+                lo[u] = __float_as_uint(g[u] - __uint_as_float(hi[u]));
+            }
+            const uint32_t ab = (uint32_t)t & 1u;
+            mbar_wait(&a_empty[ab], (((uint32_t)t >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t ta = tmem_base + A_COL + ab * 32u + lane_addr;
+            tmem_st16(ta, hi);
+            tmem_st16(ta + 16u, lo);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_ready[ab]);
+        }
+        if (p.db != nullptr) {
+#pragma unroll
+            for (int u = 0; u < CT_U; ++u) {
+                const float s = warp_sum(dbs[u]);
+                if (lane == 0) db_part[(warp - 2) * CT_U + u] = s;
+            }
+        }
+    } else {
+        // ---------------- epilogue warps: thread = row (b, d); X0[b,:,d], Xk[b,:,d], dX0, dXk in registers
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        uint32_t n_acc = 0;
+        for (int t = 0; t < my_tiles; ++t) {
+            const long long b = (long long)((int)blockIdx.x + t * (int)gridDim.x) * 8 + (row >> 4);
+            const int d = row & 15;
+            const bool valid = b < p.B;
+            float x0[F], xk[M], dx0[F], dxk[M];
+#pragma unroll
+            for (int h = 0; h < F; ++h) { x0[h] = valid ? __ldg(p.x0 + (size_t)b * p.ld0 + h * CT_D + d) : 0.f; dx0[h] = 0.f; }
+#pragma unroll
+            for (int m = 0; m < M; ++m) { xk[m] = valid ? __ldg(p.xk + (size_t)b * p.ldk + m * CT_D + d) : 0.f; dxk[m] = 0.f; }
+            // N-tiles unrolled by hand (NTILES <= 4): every column index must be a compile-time constant
+            auto one_tile = [&](auto nti_tag) {
+                constexpr int NTI = decltype(nti_tag)::value;
+                if constexpr (NTI < NTILES) {
+                    const uint32_t buf = n_acc & 1u;
+                    mbar_wait(&acc_full[buf], (n_acc >> 1) & 1u);
+                    tc_fence_after();
+                    CinDzCols<F, M, NT, NTI, 0>::run(tmem_base + ACC0 + buf * NT + lane_addr, x0, xk, dx0, dxk);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                    ++n_acc;
+                }
+            };
+            one_tile(std::integral_constant<int, 0>{});
+            one_tile(std::integral_constant<int, 1>{});
+            one_tile(std::integral_constant<int, 2>{});
+            one_tile(std::integral_constant<int, 3>{});
+            if (valid) {
+                if (p.dxk != nullptr) {
+#pragma unroll
+                    for (int m = 0; m < M; ++m) p.dxk[(size_t)b * p.lddxk + m * CT_D + d] = dxk[m];
+                }
+#pragma unroll
+                for (int h = 0; h < F; ++h) {
+                    float v = dx0[h];
+                    if constexpr (M == F) { if (p.dxk == nullptr) v += dxk[h]; }          // layer 0: Xk is X0
+                    float* dst = p.de + (size_t)b * p.ldde + h * CT_D + d;
+                    *dst = p.de_accumulate ? *dst + v : v;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+    if (p.db != nullptr && threadIdx.x < CT_U) {
+        const float s = db_part[threadIdx.x] + db_part[CT_U + threadIdx.x] + db_part[2 * CT_U + threadIdx.x] + db_part[3 * CT_U + threadIdx.x];
+        red_add_f1(p.db + threadIdx.x, s);
+    }
+}
+
+template <int F, int M, int NT, int NTILES>
+static int cin_bwd_tc_launch(const float* W, const CinBwdParams& p, cudaStream_t st) {
+    static_assert(NTILES <= 4 && NT % 16 == 0 && NT * NTILES >= F * M && 2 * NT + 64 <= 512, "tile plan");
+    CUtensorMap tmWhi, tmWlo;
+    // W_k [16, F*M] -> W_k^T [NT*NTILES rows, 32 columns] hi / lo (columns 16.. and rows F*M.. are zero)
+    int rc = tc_prepare_operand(W, F * M, CT_U, F * M, 1, NT * NTILES, TC_BLOCK_K, NT, 8, &tmWhi, &tmWlo, st);
+    if (rc != 0) return rc;
+    const size_t smem = (size_t)2 * NT * NTILES * 128 + 9 * 8 + 16 + 4 * CT_U * 4 + 1024;
+    cudaError_t e = cudaFuncSetAttribute(cin_bwd_tc_kernel<F, M, NT, NTILES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    cin_bwd_tc_kernel<F, M, NT, NTILES><<<min(p.m_tiles, 148), CB_THREADS, smem, st>>>(tmWhi, tmWlo, p);
+    return (int)cudaGetLastError();
+}
+
+int cin_layer_bwd_tc(int F, int M, const float* W, const CinBwdParams& p, cudaStream_t st) {
+    if (F == 26 && M == 26) return cin_bwd_tc_launch<26, 26, 176, 4>(W, p, st);
+    if (F == 26 && M == 16) return cin_bwd_tc_launch<26, 16, 208, 2>(W, p, st);
+    return RPB_ERR_UNSUPPORTED;
+}
+
+int cin_layer_bwd_tc_c(int F, int M, const float* W, const float* x0, long long ld0, const float* xk, long long ldk, const float* dpooled,
+                       long long lddp, const float* gx, long long ldgx, float* gout, long long ldgo, float* db, float* dxk, long long lddxk,
+                       float* de, long long ldde, int de_accumulate, int B, cudaStream_t st) {
+    CinBwdParams p{};
+    p.x0 = x0; p.ld0 = ld0; p.xk = xk; p.ldk = ldk; p.dpooled = dpooled; p.lddp = lddp; p.gx = gx; p.ldgx = ldgx;
+    p.gout = gout; p.ldgo = ldgo; p.db = db; p.dxk = dxk; p.lddxk = lddxk; p.de = de; p.ldde = ldde; p.de_accumulate = de_accumulate;
+    p.B = B; p.m_tiles = ceil_div(B, 8);
+    return cin_layer_bwd_tc(F, M, W, p, st);
+}
+
+// (F, M, U, D) combinations the tensor-core kernels are instantiated for: the Criteo shape of BASELINE.json config 3
+bool cin_tc_shape_ok(int F, int D, int L, const int* units) {
+    if (!g_cin_tc || !g_gemm_v2 || F != 26 || D != CT_D || L < 1) return false;
+    for (int k = 0; k < L; ++k) if (units[k] != CT_U) return false;
+    return true;
+}
+
+}  // namespace rpb

@@ -1058,6 +1058,21 @@ int tc_prepare_weight(const float* W, long long ldw, int N, int K, CUtensorMap* 
     return rc;
 }
 
+// General pre-split K-major operand for kernels outside this file (cin_tc.cu): out(r, c) = transpose ? src[c, r] : src[r, c],
+// zero padded to [Rp, Cp], hi / lo in workspace `slot`, TMA maps with [box_rows x 32] boxes (SWIZZLE_128B).
+int tc_prepare_operand(const float* src, long long ld, int rows_in, int cols_in, int transpose, int Rp, int Cp, int box_rows,
+                       int slot, CUtensorMap* tm_hi, CUtensorMap* tm_lo, cudaStream_t st) {
+    int werr = 0;
+    float* ws = static_cast<float*>(workspace(slot, (size_t)2 * Rp * Cp * sizeof(float), &werr));
+    if (ws == nullptr) return werr;
+    float* hi = ws;
+    float* lo = ws + (size_t)Rp * Cp;
+    split_pack_kernel<<<ceil_div((long long)Rp * Cp, 256), 256, 0, st>>>(src, ld, rows_in, cols_in, transpose, hi, lo, Rp, Cp);
+    int rc = make_map(tm_hi, hi, Rp, Cp, Cp, box_rows);
+    if (rc == 0) rc = make_map(tm_lo, lo, Rp, Cp, Cp, box_rows);
+    return rc;
+}
+
 // Pre-split operands of the square 64 x 64 tower-tail layers for the tcgen05 tail of deepfm_fused.cu: hi / lo
 // [n_tail * 64, 64] (layer l = rows l*64 .. l*64+63) in workspace `slot` (6: forward, 7: backward with transpose = 1, i.e.
 // W_l^T, the K-major operand of dz . W_l) + their TMA maps with [64 x 32] boxes.

@@ -121,6 +121,8 @@ int tc_prepare_weight(const float* W, long long ldw, int N, int K, CUtensorMap* 
 // general 2-D fp32 map: [rows, cols] with row stride ld (floats), box [box_rows x box_cols], swizzle span 0 / 32 / 64 / 128 bytes
 int tc_make_map2d(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_cols, int box_rows,
                   int swizzle_bytes);                                                                                      // linear_tc.cu
+int tc_prepare_operand(const float* src, long long ld, int rows_in, int cols_in, int transpose, int Rp, int Cp, int box_rows,
+                       int slot, CUtensorMap* tm_hi, CUtensorMap* tm_lo, cudaStream_t st);                                 // linear_tc.cu
 int tc_prepare_tail_weights(const float* const* W, int n_tail, CUtensorMap* tm_hi, CUtensorMap* tm_lo, cudaStream_t st,
                             int transpose, int slot);                                                                       // linear_tc.cu
 
