@@ -378,6 +378,8 @@ int cin_layer_fwd_tc(int F, int M, int U, int D, const float* W, const float* bi
 int cin_layer_bwd_tc_c(int F, int M, const float* W, const float* x0, long long ld0, const float* xk, long long ldk, const float* dpooled,
                        long long lddp, const float* gx, long long ldgx, float* gout, long long ldgo, float* db, float* dxk, long long lddxk,
                        float* de, long long ldde, int de_accumulate, int B, cudaStream_t st);
+int cin_layer_wgrad_tc(int F, int M, const float* x0, long long ld0, const float* xk, long long ldk, const float* g, long long ldg,
+                       float* dW, int B, cudaStream_t st);
 }
 
 RPB_API int rpb_cin_fwd(const float* e, int64_t lde, int B, int F, int D, int L, const int32_t* units,
@@ -448,7 +450,6 @@ RPB_API int rpb_cin_bwd(const float* e, int64_t lde, int B, int F, int D, int L,
     if (spill == nullptr) return werr;
     float* Gout = spill;
     float* Xout = spill + per;
-    bool tc_done = false;
     if (cin_tc_shape_ok(F, D, L, units)) {
         // tensor-core path (cin_tc.cu): recompute X_1 .. X_{L-1} (one launch per layer), then per layer, top down, the dZ GEMM
         // with the gradient contraction in its epilogue; G_k and X_k are spilled in the layout the weight-gradient kernel reads
@@ -465,17 +466,23 @@ RPB_API int rpb_cin_bwd(const float* e, int64_t lde, int B, int F, int D, int L,
         for (int k = L - 1; k >= 0; --k) {
             rc = cin_layer_bwd_tc_c(F, h.meta.M[k], W[k], e, lde, k == 0 ? e : Xout + (size_t)h.meta.p_off[k - 1] * D, k == 0 ? lde : ldu,
                                     dpooled + h.meta.p_off[k], lddp, k == L - 1 ? nullptr : dxb + (size_t)((k + 1) & 1) * dper,
-                                    (long long)units[k] * D, Gout + (size_t)h.meta.p_off[k] * D, ldu, nullptr /* db: the weight-gradient kernel sums it */,
+                                    (long long)units[k] * D, Gout + (size_t)h.meta.p_off[k] * D, ldu, db ? db[k] : nullptr,
                                     k > 0 ? dxb + (size_t)(k & 1) * dper : nullptr, (long long)h.meta.M[k] * D, de, ldde,
                                     k == L - 1 ? accumulate : 1, B, st);
             if (rc != 0) return rc;
         }
-        tc_done = true;
+        // weight gradients: dW_k = P^T . X_k over the rows (b, d), P = G_k x X_0 formed in registers (cin_wgrad_tc_kernel)
+        for (int k = 0; k < L; ++k) {
+            rc = cin_layer_wgrad_tc(F, h.meta.M[k], e, lde, k == 0 ? e : Xout + (size_t)h.meta.p_off[k - 1] * D, k == 0 ? lde : ldu,
+                                    Gout + (size_t)h.meta.p_off[k] * D, ldu, dW[k], B, st);
+            if (rc != 0) return rc;
+        }
+        return 0;
     }
     rc = cin_dispatch(D, maxu, [&](auto dt, auto ut) -> int {
         constexpr int DD = decltype(dt)::value, MU = decltype(ut)::value;
         constexpr int SPC = 256 / DD;
-        if (!tc_done) {
+        {
         const size_t smem = ((size_t)h.meta.w_total + ((h.meta.u_total + 3) & ~3) + (size_t)SPC * F * DD * 2 +
                              (size_t)SPC * h.meta.u_total * DD) * sizeof(float);
         if (smem > 220 * 1024) return RPB_ERR_UNSUPPORTED;

@@ -462,6 +462,215 @@ int cin_layer_bwd_tc(int F, int M, const float* W, const CinBwdParams& p, cudaSt
     return RPB_ERR_UNSUPPORTED;
 }
 
+// =====================================================================================================================
+// Backward of one layer, part B (weight gradient):  dW_k[u, h*M + m] = sum_{(b,d)} G[(b,d),u] * X0[(b,d),h] * Xk[(b,d),m].
+// Written as a GEMM over the rows r = (b, d):   D[(u,h), m] = sum_r P[(u,h), r] * Xk[r, m],   P[(u,h), r] = G[r,u] * X0[r,h].
+//   * A = P^T in tensor memory (TS mode): lane = (u, h) pair (416 pairs = 4 M-tiles of 128), columns = the 32 rows of a k-block
+//     (2 samples x 16 d).  A thread reads the two 64-byte rows G[b,u,:] and X0[b,h,:] it needs — contiguous in the G spill and
+//     in the feature row — multiplies them element-wise, splits and stores: no outer product, no transposition.
+//   * B = Xk [m, r] K-major: row m of a k-block = Xk[b0,m,:] | Xk[b1,m,:], fetched with cp.async into a SWIZZLE_128B tile; the
+//     raw fp32 tile is the "hi" operand (the tensor core ignores the low 13 mantissa bits), the loader warp writes lo = x - hi
+//     below it: stacked [raw ; lo] operand of 64 rows (rows m >= M are zero), two TS-mode MMAs (a_lo, a_hi) per k-step.
+//   * the four accumulators (64 columns each) live in tensor memory for the CTA's whole slab of rows; the epilogue adds the two
+//     halves and reduces into dW with fp32 `red`.
+constexpr int CW_THREADS = 10 * 32;      // 0 = Xk loader, 1 = MMA, 2-9 = operand warps (w, w+4: sample 0 / 1 of the k-block), 2-5 also epilogue
+constexpr int CW_BST = 4;                // B tile ring
+constexpr int CW_OPN = 4;                // A operand ring (64 columns each)
+constexpr int CW_B_BYTES = 64 * 128;     // stacked [raw 32 rows ; lo 32 rows] x 128 B
+
+struct CinWgParams {
+    const float* x0; long long ld0;
+    const float* xk; long long ldk;
+    const float* g; long long ldg;       // G spill: g[b * ldg + u * 16 + d]
+    float* dW;                           // [16, F*M] accumulated
+    int B, n_kb;                         // k-blocks = ceil(B / 2)
+};
+
+template <int F, int M>
+__global__ void __launch_bounds__(CW_THREADS, 1)
+cin_wgrad_tc_kernel(const __grid_constant__ CinWgParams p) {
+    constexpr int NPAIR = CT_U * F;                                      // (u, h) pairs
+    constexpr int MT = (NPAIR + 127) / 128;                              // M-tiles
+    static_assert(MT <= 4 && M <= 32, "accumulator plan");
+    constexpr uint32_t A_COL = 4 * 64;                                   // after the four 64-column accumulators
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* b_base = smem;                                              // CW_BST x 8 KiB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + CW_BST * CW_B_BYTES);
+    uint64_t* b_full = bars;                       // [CW_BST]
+    uint64_t* b_empty = b_full + CW_BST;           // [CW_BST]
+    uint64_t* a_ready = b_empty + CW_BST;          // [CW_OPN] 8 arrivals
+    uint64_t* a_empty = a_ready + CW_OPN;          // [CW_OPN]
+    uint64_t* acc_done = a_empty + CW_OPN;         // [1]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_done + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // slab of k-blocks of this CTA
+    const int per = (p.n_kb + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int kb0 = (int)blockIdx.x * per, kb1 = min(p.n_kb, kb0 + per);
+    const int nkb = max(0, kb1 - kb0);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < CW_BST; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < CW_OPN; ++s) { mbar_init(&a_ready[s], 8); mbar_init(&a_empty[s], 1); }
+        mbar_init(acc_done, 1);
+        fence_barrier_init();
+    }
+    // rows m >= M of every stacked tile stay zero for the whole kernel
+    for (int i = threadIdx.x; i < CW_BST * CW_B_BYTES / 16; i += blockDim.x) reinterpret_cast<float4*>(b_base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (warp == 1) tmem_alloc(tmem_ptr, 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ---------------- Xk loader: raw rows by cp.async (16-byte pieces, SWIZZLE_128B positions), then the lo tile
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % CW_BST;
+            mbar_wait(&b_empty[s], ((i / CW_BST) & 1u) ^ 1u);
+            uint8_t* tile = b_base + (size_t)s * CW_B_BYTES;
+            const long long bA = (long long)(kb0 + i) * 2;
+            for (int e = lane; e < M * 8; e += 32) {                      // (row m, chunk c): c < 4 sample 0, c >= 4 sample 1
+                const int m = e >> 3, c = e & 7;
+                const long long b = bA + (c >> 2);
+                const bool ok = b < p.B;
+                const float* src = p.xk + (size_t)(ok ? b : 0) * p.ldk + m * CT_D + (c & 3) * 4;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_u32(tile + m * 128 + ((c ^ (m & 7)) << 4))), "l"(src), "r"(ok ? 16 : 0) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            for (int e = lane; e < M * 8; e += 32) {
+                const int m = e >> 3, c = e & 7;
+                const uint32_t off = m * 128 + ((c ^ (m & 7)) << 4);
+                const float4 v = *reinterpret_cast<const float4*>(tile + off);
+                float4 l;
+                l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                *reinterpret_cast<float4*>(tile + 32 * 128 + off) = l;   // rows 32.. of the stacked tile (same swizzle phase: 32 % 8 == 0)
+            }
+            fence_proxy_async();                                          // generic-proxy writes -> the MMA's async-proxy reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&b_full[s]);
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(TC_BLOCK_M, 64);
+            uint32_t ga = 0;
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % CW_BST;
+                mbar_wait(&b_full[s], (i / CW_BST) & 1u);
+                tc_fence_after();
+                const uint32_t b_addr = smem_u32(b_base + (size_t)s * CW_B_BYTES);
+                for (int mt = 0; mt < MT; ++mt, ++ga) {
+                    const int o = ga % CW_OPN;
+                    mbar_wait(&a_ready[o], (ga / CW_OPN) & 1u);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)mt * 64u;
+                    const uint32_t ta_hi = tmem_base + A_COL + (uint32_t)o * 64u, ta_lo = ta_hi + 32u;
+#pragma unroll
+                    for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
+                        const uint64_t db = make_kmajor_sw128_desc(b_addr + k * TC_UMMA_K * 4);
+                        umma_tf32_ts(d_tmem, ta_lo + k * TC_UMMA_K, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                        umma_tf32_ts(d_tmem, ta_hi + k * TC_UMMA_K, db, idesc, 1u);
+                    }
+                    umma_commit(&a_empty[o]);
+                }
+                umma_commit(&b_empty[s]);
+            }
+            umma_commit(acc_done);
+        }
+    } else {
+        // ---------------- operand warps: lane = (u, h) pair of the M-tile, `half` = which sample of the k-block
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        uint32_t ga = 0;
+        for (int i = 0; i < nkb; ++i) {
+            const long long b = (long long)(kb0 + i) * 2 + half;
+            const bool okb = b < p.B;
+            for (int mt = 0; mt < MT; ++mt, ++ga) {
+                const int pr = mt * 128 + q * 32 + lane;
+                const bool ok = okb && pr < NPAIR;
+                const int u = pr / F, h = pr - u * F;
+                uint32_t hi[16], lo[16];
+                if (ok) {
+                    const float4* gr = reinterpret_cast<const float4*>(p.g + (size_t)b * p.ldg + u * CT_D);
+                    const float4* xr = reinterpret_cast<const float4*>(p.x0 + (size_t)b * p.ld0 + h * CT_D);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float4 a = __ldg(gr + c), x = __ldg(xr + c);
+                        const float z[4] = {a.x * x.x, a.y * x.y, a.z * x.z, a.w * x.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            hi[4 * c + e] = __float_as_uint(z[e]) & 0xFFFFE000u;
+                            lo[4 * c + e] = __float_as_uint(z[e] - __uint_as_float(hi[4 * c + e]));
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) { hi[e] = 0u; lo[e] = 0u; }
+                }
+                const int o = ga % CW_OPN;
+                mbar_wait(&a_empty[o], ((ga / CW_OPN) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t ta = tmem_base + A_COL + (uint32_t)o * 64u + lane_addr + (uint32_t)half * 16u;
+                tmem_st16(ta, hi);
+                tmem_st16(ta + 32u, lo);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_ready[o]);
+            }
+        }
+        // ---------------- epilogue (first four operand warps): acc[mt] = a.b_raw | a.b_lo  ->  dW[u, h*M + m] += sum
+        if (half == 0 && nkb > 0) {
+            mbar_wait(acc_done, 0u);
+            tc_fence_after();
+            for (int mt = 0; mt < MT; ++mt) {
+                const int pr = mt * 128 + q * 32 + lane;
+                uint32_t a0[16], a1[16], c0[16], c1[16];
+                tmem_ld16(tmem_base + (uint32_t)mt * 64u + lane_addr, a0);
+                tmem_ld16(tmem_base + (uint32_t)mt * 64u + lane_addr + 16u, a1);
+                tmem_ld16(tmem_base + (uint32_t)mt * 64u + lane_addr + 32u, c0);
+                tmem_ld16(tmem_base + (uint32_t)mt * 64u + lane_addr + 48u, c1);
+                if (pr < NPAIR) {
+                    const int u = pr / F, h = pr - u * F;
+                    float* dst = p.dW + (size_t)u * (F * M) + h * M;
+#pragma unroll
+                    for (int m = 0; m < 16; ++m) if (m < M) red_add_f1(dst + m, __uint_as_float(a0[m]) + __uint_as_float(c0[m]));
+#pragma unroll
+                    for (int m = 16; m < 32; ++m) if (m < M) red_add_f1(dst + m, __uint_as_float(a1[m - 16]) + __uint_as_float(c1[m - 16]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+template <int F, int M>
+static int cin_wgrad_tc_launch(const CinWgParams& p, cudaStream_t st) {
+    const size_t smem = (size_t)CW_BST * CW_B_BYTES + (2 * CW_BST + 2 * CW_OPN + 1) * 8 + 16 + 1024;
+    cudaError_t e = cudaFuncSetAttribute(cin_wgrad_tc_kernel<F, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    cin_wgrad_tc_kernel<F, M><<<min(p.n_kb, 148), CW_THREADS, smem, st>>>(p);
+    return (int)cudaGetLastError();
+}
+
+int cin_layer_wgrad_tc(int F, int M, const float* x0, long long ld0, const float* xk, long long ldk, const float* g, long long ldg,
+                       float* dW, int B, cudaStream_t st) {
+    if ((ld0 & 3) || (ldk & 3) || (ldg & 3) || (reinterpret_cast<uintptr_t>(x0) & 15u) || (reinterpret_cast<uintptr_t>(xk) & 15u) ||
+        (reinterpret_cast<uintptr_t>(g) & 15u))
+        return RPB_ERR_UNSUPPORTED;
+    CinWgParams p{};
+    p.x0 = x0; p.ld0 = ld0; p.xk = xk; p.ldk = ldk; p.g = g; p.ldg = ldg; p.dW = dW; p.B = B; p.n_kb = ceil_div(B, 2);
+    if (F == 26 && M == 26) return cin_wgrad_tc_launch<26, 26>(p, st);
+    if (F == 26 && M == 16) return cin_wgrad_tc_launch<26, 16>(p, st);
+    return RPB_ERR_UNSUPPORTED;
+}
+
 int cin_layer_bwd_tc_c(int F, int M, const float* W, const float* x0, long long ld0, const float* xk, long long ldk, const float* dpooled,
                        long long lddp, const float* gx, long long ldgx, float* gout, long long ldgo, float* db, float* dxk, long long lddxk,
                        float* de, long long ldde, int de_accumulate, int B, cudaStream_t st) {
