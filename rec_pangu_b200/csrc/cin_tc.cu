@@ -20,6 +20,9 @@ namespace rpb {
 constexpr int CT_D = 16;                 // embedding dim these kernels are built for (one 64-byte row per field)
 constexpr int CT_U = 16;                 // units per layer
 constexpr int CT_THREADS = 14 * 32;
+// registers are re-dealt between the warpgroups of the 384-thread kernels (168 per thread at launch)
+#define RPB_REG_DEC(n) asm volatile("setmaxnreg.dec.sync.aligned.u32 " #n ";")
+#define RPB_REG_INC(n) asm volatile("setmaxnreg.inc.sync.aligned.u32 " #n ";")
 constexpr int CT_OPN = 6;                // tensor-memory operand ring: 6 x 64 columns (A hi 32 | A lo 32)
 constexpr int CT_ACC = 2 * CT_U;         // accumulator columns: [A.Whi^T | A.Wlo^T]
 constexpr int CT_A_COL = 2 * CT_ACC;     // two accumulator buffers, then the operand ring
@@ -213,6 +216,216 @@ static int cin_fwd_tc_launch(const float* W, const CinTcParams& p, cudaStream_t 
     return (int)cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Forward, second formulation (the default): contract over m on the tensor core, over h in the epilogue.
+//     T[(b,d), (u,h)] = sum_m Xk[b,m,d] * W_k[u, h*M + m]           (rows x M x 16*F GEMM; A = Xk rows, K = M)
+//     X_{k+1}[b,u,d]  = sum_h X0[b,h,d] * T[(b,d), (u,h)] + bias[u]  (epilogue, straight out of the accumulator)
+// Same flops on the tensor core as the outer-product form, but the A operand is M values per row instead of F*M products
+// (26 splits instead of 676: the split warps were the bound, profiles/r02_cin_ncu.md), W_k is its own K-major operand
+// ([(u,h) rows, M contiguous columns]: no transposition), and the epilogue is one FMA per accumulator column.
+constexpr int C2_THREADS = 12 * 32;      // warpgroups: [0 weights, 1 MMA, 2-3 idle] [4-7 operand warps] [8-11 epilogue warps]
+
+template <int F, int NT, int NTI, int C0>
+struct CinTCols {
+    // columns C0 .. C0+15 of N-tile NTI (global j = NTI*NT + C0 + i = u*F + h): out[u] += T * x0[h]
+    static __device__ __forceinline__ void run(uint32_t acc_addr, const float (&x0)[F], float (&out)[CT_U]) {
+        if constexpr (C0 < NT && NTI * NT + C0 < CT_U * F) {
+            uint32_t a[16];
+            tmem_ld16(acc_addr + (uint32_t)C0, a);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int j = NTI * NT + C0 + i;
+                if (j < CT_U * F) out[j / F] = fmaf(__uint_as_float(a[i]), x0[j % F], out[j / F]);
+            }
+            CinTCols<F, NT, NTI, C0 + 16>::run(acc_addr, x0, out);
+        }
+    }
+};
+
+template <int F, int NT, int NTILES, int NTI>
+struct CinTTiles {
+    static __device__ __forceinline__ void run(uint32_t acc0, uint64_t* acc_full, uint64_t* acc_empty, uint32_t& n_acc, int lane,
+                                               const float (&x0)[F], float (&out)[CT_U]) {
+        if constexpr (NTI < NTILES) {
+            const uint32_t buf = n_acc & 1u;
+            mbar_wait(&acc_full[buf], (n_acc >> 1) & 1u);
+            tc_fence_after();
+            CinTCols<F, NT, NTI, 0>::run(acc0 + buf * NT, x0, out);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            ++n_acc;
+            CinTTiles<F, NT, NTILES, NTI + 1>::run(acc0, acc_full, acc_empty, n_acc, lane, x0, out);
+        }
+    }
+};
+
+template <int F, int M, int NT, int NTILES>
+__global__ void __launch_bounds__(C2_THREADS, 1)
+cin_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo, const __grid_constant__ CinTcParams p) {
+    constexpr int KP = M <= 16 ? 16 : 32;                                 // K padded to whole k-steps (zero columns)
+    constexpr int KS = KP / TC_UMMA_K;
+    constexpr int NP = NT * NTILES;                                       // padded 16*F
+    constexpr uint32_t ACC0 = 0, A_COL = 2 * NT;                          // two NT-column accumulators, then 2 x (hi KP | lo KP)
+    static_assert(A_COL + 4 * KP <= 512 && NP >= CT_U * F && NT % 16 == 0 && NT <= 256 && NTILES <= 4, "tile plan");
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* w_hi = smem;                                                 // [NP rows (u,h)][128 B]: W hi (M valid columns, rest zero)
+    uint8_t* w_lo = w_hi + (size_t)NP * 128;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(w_lo + (size_t)NP * 128);
+    uint64_t* w_full = bars;                       // [1]
+    uint64_t* a_ready = w_full + 1;                // [2] Xk operand of a tile written (4 arrivals)
+    uint64_t* a_empty = a_ready + 2;               // [2] its MMAs are done
+    uint64_t* acc_full = a_empty + 2;              // [2]
+    uint64_t* acc_empty = acc_full + 2;            // [2] 4 arrivals
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int my_tiles = ((int)blockIdx.x < p.m_tiles) ? (p.m_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    if (threadIdx.x == 0) {
+        mbar_init(w_full, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&a_ready[s], 4); mbar_init(&a_empty[s], 1); mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    // roles by WARPGROUP: setmaxnreg is executed by all four warps of a warpgroup at the same instruction
+    if (warp < 4) {
+        RPB_REG_DEC(56);
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(w_full, (uint32_t)(2 * NP * 128));
+            for (int nt = 0; nt < NTILES; ++nt) {
+                tma_load_2d(w_hi + (size_t)nt * NT * 128, &tmWhi, w_full, 0, nt * NT);
+                tma_load_2d(w_lo + (size_t)nt * NT * 128, &tmWlo, w_full, 0, nt * NT);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(TC_BLOCK_M, NT);
+            mbar_wait(w_full, 0u);
+            uint32_t n_acc = 0;
+            for (int t = 0; t < my_tiles; ++t) {
+                const uint32_t ab = (uint32_t)t & 1u;
+                mbar_wait(&a_ready[ab], ((uint32_t)t >> 1) & 1u);
+                tc_fence_after();
+                const uint32_t ta_hi = tmem_base + A_COL + ab * (2 * KP), ta_lo = ta_hi + KP;
+                for (int nt = 0; nt < NTILES; ++nt, ++n_acc) {
+                    const uint32_t buf = n_acc & 1u;
+                    mbar_wait(&acc_empty[buf], ((n_acc >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + ACC0 + buf * NT;
+                    const uint32_t bh = smem_u32(w_hi + (size_t)nt * NT * 128), bl = smem_u32(w_lo + (size_t)nt * NT * 128);
+#pragma unroll
+                    for (int k = 0; k < KS; ++k) {
+                        const uint64_t dh = make_kmajor_sw128_desc(bh + k * TC_UMMA_K * 4), dl = make_kmajor_sw128_desc(bl + k * TC_UMMA_K * 4);
+                        umma_tf32_ts(d_tmem, ta_lo + k * TC_UMMA_K, dh, idesc, k > 0 ? 1u : 0u);
+                        umma_tf32_ts(d_tmem, ta_hi + k * TC_UMMA_K, dl, idesc, 1u);
+                        umma_tf32_ts(d_tmem, ta_hi + k * TC_UMMA_K, dh, idesc, 1u);
+                    }
+                    umma_commit(&acc_full[buf]);
+                }
+                umma_commit(&a_empty[ab]);
+            }
+        }
+    }
+    } else if (warp < 8) {
+        RPB_REG_DEC(96);
+        // ---------------- operand warps: thread = row (b, d): Xk[b,:,d] -> (hi, lo) -> tensor memory
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        for (int t = 0; t < my_tiles; ++t) {
+            const long long b = (long long)((int)blockIdx.x + t * (int)gridDim.x) * 8 + (row >> 4);
+            const int d = row & 15;
+            float xv[KP];
+#pragma unroll
+            for (int m = 0; m < KP; ++m) xv[m] = (m < M && b < p.B) ? __ldg(p.xk + (size_t)b * p.ldk + m * CT_D + d) : 0.f;
+            const uint32_t ab = (uint32_t)t & 1u;
+            mbar_wait(&a_empty[ab], (((uint32_t)t >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t ta = tmem_base + A_COL + ab * (2 * KP) + lane_addr;
+#pragma unroll
+            for (int c = 0; c < KP; c += 16) {
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    hi[i] = __float_as_uint(xv[c + i]) & 0xFFFFE000u;
+                    lo[i] = __float_as_uint(xv[c + i] - __uint_as_float(hi[i]));
+                }
+                tmem_st16(ta + c, hi);
+                tmem_st16(ta + KP + c, lo);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_ready[ab]);
+        }
+    } else {
+        RPB_REG_INC(240);
+        // ---------------- epilogue warps: thread = row (b, d); X0[b,:,d] (prefetched one tile ahead) and the 16 outputs in registers
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const int d = row & 15;
+        float bv[CT_U];
+#pragma unroll
+        for (int u = 0; u < CT_U; ++u) bv[u] = p.bias != nullptr ? __ldg(p.bias + u) : 0.f;
+        uint32_t n_acc = 0;
+        float x0n[F];
+        {
+            const long long b = (long long)(int)blockIdx.x * 8 + (row >> 4);
+#pragma unroll
+            for (int h = 0; h < F; ++h) x0n[h] = (my_tiles > 0 && b < p.B) ? __ldg(p.x0 + (size_t)b * p.ld0 + h * CT_D + d) : 0.f;
+        }
+        for (int t = 0; t < my_tiles; ++t) {
+            const long long b = (long long)((int)blockIdx.x + t * (int)gridDim.x) * 8 + (row >> 4);
+            const bool valid = b < p.B;
+            float x0[F], out[CT_U];
+#pragma unroll
+            for (int h = 0; h < F; ++h) x0[h] = x0n[h];
+            {
+                const long long bn = (long long)((int)blockIdx.x + (t + 1) * (int)gridDim.x) * 8 + (row >> 4);
+                const bool okn = t + 1 < my_tiles && bn < p.B;
+#pragma unroll
+                for (int h = 0; h < F; ++h) x0n[h] = okn ? __ldg(p.x0 + (size_t)bn * p.ld0 + h * CT_D + d) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < CT_U; ++u) out[u] = bv[u];
+            CinTTiles<F, NT, NTILES, 0>::run(tmem_base + ACC0 + lane_addr, acc_full, acc_empty, n_acc, lane, x0, out);
+#pragma unroll
+            for (int u = 0; u < CT_U; ++u) {
+                const float v = out[u];
+                if (valid && p.xout != nullptr) p.xout[(size_t)b * p.ldo + u * CT_D + d] = v;
+                if (p.pooled != nullptr) {
+                    const float s = group_sum<CT_D>(v);
+                    if (valid && d == 0) p.pooled[(size_t)b * p.ldp + u] = s;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+template <int F, int M, int NT, int NTILES>
+static int cin_fwd2_tc_launch(const float* W, const CinTcParams& p, cudaStream_t st) {
+    CUtensorMap tmWhi, tmWlo;
+    // W_k [16, F*M] read as [(u,h) = 16*F rows, M columns] -> hi / lo [NT*NTILES rows, 32 columns] (zero padded), [NT x 32] boxes
+    int rc = tc_prepare_operand(W, M, CT_U * F, M, 0, NT * NTILES, TC_BLOCK_K, NT, 9, &tmWhi, &tmWlo, st);
+    if (rc != 0) return rc;
+    const size_t smem = (size_t)2 * NT * NTILES * 128 + 9 * 8 + 32 + 1024;
+    cudaError_t e = cudaFuncSetAttribute(cin_fwd2_tc_kernel<F, M, NT, NTILES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    cin_fwd2_tc_kernel<F, M, NT, NTILES><<<min(p.m_tiles, 148), C2_THREADS, smem, st>>>(tmWhi, tmWlo, p);
+    return (int)cudaGetLastError();
+}
+
 // One CIN layer forward on tensor cores.  Returns RPB_ERR_UNSUPPORTED for shapes outside the instantiated (F, M) pairs.
 int cin_layer_fwd_tc(int F, int M, int U, int D, const float* W, const float* bias, const float* x0, long long ld0, const float* xk,
                      long long ldk, float* xout, long long ldo, float* pooled, long long ldp, int B, cudaStream_t st) {
@@ -221,8 +434,13 @@ int cin_layer_fwd_tc(int F, int M, int U, int D, const float* W, const float* bi
     CinTcParams p{};
     p.x0 = x0; p.ld0 = ld0; p.xk = xk; p.ldk = ldk; p.bias = bias; p.xout = xout; p.ldo = ldo; p.pooled = pooled; p.ldp = ldp;
     p.B = B; p.m_tiles = ceil_div(B, 8);
-    if (F == 26 && M == 26) return cin_fwd_tc_launch<26, 26>(W, p, st);
-    if (F == 26 && M == 16) return cin_fwd_tc_launch<26, 16>(W, p, st);
+    if (g_cin_tc == 2) {                                                  // first formulation (outer product in registers), kept for A/B
+        if (F == 26 && M == 26) return cin_fwd_tc_launch<26, 26>(W, p, st);
+        if (F == 26 && M == 16) return cin_fwd_tc_launch<26, 16>(W, p, st);
+        return RPB_ERR_UNSUPPORTED;
+    }
+    if (F == 26 && M == 26) return cin_fwd2_tc_launch<26, 26, 144, 3>(W, p, st);
+    if (F == 26 && M == 16) return cin_fwd2_tc_launch<26, 16, 208, 2>(W, p, st);
     return RPB_ERR_UNSUPPORTED;
 }
 
@@ -234,7 +452,7 @@ int cin_layer_fwd_tc(int F, int M, int U, int D, const float* W, const float* bi
 // epilogue warps hold X0[b,:,d], Xk[b,:,d] and the two gradient vectors in registers and read dZ 16 columns at a time; every
 // (h, m) is a compile-time constant.  W_k^T hi / lo ([F*M rows, 16 -> 32 zero-padded columns], SWIZZLE_128B) resident in smem;
 // 3 MMAs per k-step (hi.hi + lo.hi + hi.lo) into NT-column accumulators, double buffered.
-constexpr int CB_THREADS = 10 * 32;      // 0 weights, 1 MMA, 2-5 G warps, 6-9 epilogue warps
+constexpr int CB_THREADS = 12 * 32;      // warpgroups: [0 weights, 1 MMA, 2-3 idle] [4-7 G warps] [8-11 epilogue warps]; registers re-dealt by setmaxnreg
 
 struct CinBwdParams {
     const float* x0; long long ld0;
@@ -300,6 +518,9 @@ cin_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
+    // roles by WARPGROUP: setmaxnreg is executed by all four warps of a warpgroup at the same instruction
+    if (warp < 4) {
+        RPB_REG_DEC(56);
     if (warp == 0) {
         if (lane == 0) {
             mbar_arrive_expect_tx(w_full, (uint32_t)(2 * NP * 128));
@@ -336,7 +557,9 @@ cin_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_consta
                 umma_commit(&a_empty[ab]);
             }
         }
-    } else if (warp < 6) {
+    }
+    } else if (warp < 8) {
+        RPB_REG_DEC(96);
         // ---------------- G warps: thread = row (b, d): G[u] = dpooled[b, u] + gx[b, u, d]; spill, bias gradient, A operand
         const int q = warp & 3;
         const int row = q * 32 + lane;
@@ -382,10 +605,11 @@ cin_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_consta
 #pragma unroll
             for (int u = 0; u < CT_U; ++u) {
                 const float s = warp_sum(dbs[u]);
-                if (lane == 0) db_part[(warp - 2) * CT_U + u] = s;
+                if (lane == 0) db_part[(warp - 4) * CT_U + u] = s;
             }
         }
     } else {
+        RPB_REG_INC(240);
         // ---------------- epilogue warps: thread = row (b, d); X0[b,:,d], Xk[b,:,d], dX0, dXk in registers
         const int q = warp & 3;
         const int row = q * 32 + lane;
@@ -423,12 +647,16 @@ cin_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_consta
 #pragma unroll
                     for (int m = 0; m < M; ++m) p.dxk[(size_t)b * p.lddxk + m * CT_D + d] = dxk[m];
                 }
+                // old values first, all loads in flight together (x0 / xk are dead here: their registers are free)
+                float* dst = p.de + (size_t)b * p.ldde + d;
+                float old[F];
+#pragma unroll
+                for (int h = 0; h < F; ++h) old[h] = p.de_accumulate ? __ldcg(dst + h * CT_D) : 0.f;
 #pragma unroll
                 for (int h = 0; h < F; ++h) {
-                    float v = dx0[h];
+                    float v = dx0[h] + old[h];
                     if constexpr (M == F) { if (p.dxk == nullptr) v += dxk[h]; }          // layer 0: Xk is X0
-                    float* dst = p.de + (size_t)b * p.ldde + h * CT_D + d;
-                    *dst = p.de_accumulate ? *dst + v : v;
+                    dst[h * CT_D] = v;
                 }
             }
         }
@@ -465,18 +693,19 @@ int cin_layer_bwd_tc(int F, int M, const float* W, const CinBwdParams& p, cudaSt
 // =====================================================================================================================
 // Backward of one layer, part B (weight gradient):  dW_k[u, h*M + m] = sum_{(b,d)} G[(b,d),u] * X0[(b,d),h] * Xk[(b,d),m].
 // Written as a GEMM over the rows r = (b, d):   D[(u,h), m] = sum_r P[(u,h), r] * Xk[r, m],   P[(u,h), r] = G[r,u] * X0[r,h].
-//   * A = P^T in tensor memory (TS mode): lane = (u, h) pair (416 pairs = 4 M-tiles of 128), columns = the 32 rows of a k-block
-//     (2 samples x 16 d).  A thread reads the two 64-byte rows G[b,u,:] and X0[b,h,:] it needs — contiguous in the G spill and
-//     in the feature row — multiplies them element-wise, splits and stores: no outer product, no transposition.
-//   * B = Xk [m, r] K-major: row m of a k-block = Xk[b0,m,:] | Xk[b1,m,:], fetched with cp.async into a SWIZZLE_128B tile; the
-//     raw fp32 tile is the "hi" operand (the tensor core ignores the low 13 mantissa bits), the loader warp writes lo = x - hi
-//     below it: stacked [raw ; lo] operand of 64 rows (rows m >= M are zero), two TS-mode MMAs (a_lo, a_hi) per k-step.
-//   * the four accumulators (64 columns each) live in tensor memory for the CTA's whole slab of rows; the epilogue adds the two
+//   * a loader warp stages, per k-block of 32 rows (2 samples x 16 d) and CW_BST k-blocks ahead (cp.async): the Xk rows as the
+//     K-major B tile (row m = Xk[b0,m,:] | Xk[b1,m,:], SWIZZLE_128B positions), the G rows [2][16 u][16 d] and the X0 rows
+//     [2][F][16 d] (chunks XOR-swizzled by (h >> 1) & 3 so that a quarter warp of consecutive h reads conflict-free).  The raw
+//     fp32 Xk tile is the "hi" operand (the tensor core ignores the low 13 mantissa bits); the loader writes lo = x - hi below
+//     it: stacked [raw ; lo] operand of 2*NB rows (rows m >= M are zero), two TS-mode MMAs (a_lo, a_hi) per k-step.
+//   * A = P^T in tensor memory (TS mode): lane = (u, h) pair (416 pairs = 4 M-tiles of 128), columns = the 32 rows of the
+//     k-block.  An operand thread reads its two 64-byte rows G[b,u,:] and X0[b,h,:] from the stage (LDS.128), multiplies them
+//     element-wise, splits and stores: no outer product, no transposition, no exposed DRAM latency.
+//   * the four accumulators (2*NB columns each) live in tensor memory for the CTA's whole slab of rows; the epilogue adds the two
 //     halves and reduces into dW with fp32 `red`.
-constexpr int CW_THREADS = 10 * 32;      // 0 = Xk loader, 1 = MMA, 2-9 = operand warps (w, w+4: sample 0 / 1 of the k-block), 2-5 also epilogue
-constexpr int CW_BST = 4;                // B tile ring
+constexpr int CW_THREADS = 10 * 32;      // 0 = loader, 1 = MMA, 2-9 = operand warps (w, w+4: sample 0 / 1 of the k-block), 2-5 also epilogue
+constexpr int CW_BST = 4;                // stage ring
 constexpr int CW_OPN = 4;                // A operand ring (64 columns each)
-constexpr int CW_B_BYTES = 64 * 128;     // stacked [raw 32 rows ; lo 32 rows] x 128 B
 
 struct CinWgParams {
     const float* x0; long long ld0;
@@ -487,18 +716,30 @@ struct CinWgParams {
 };
 
 template <int F, int M>
+struct CwLayout {
+    static constexpr int NB = M <= 16 ? 16 : 32;                          // rows of one half of the stacked B tile
+    static constexpr int B_BYTES = 2 * NB * 128;
+    static constexpr int G_OFF = B_BYTES;                                 // [2][16][64 B]
+    static constexpr int X_OFF = G_OFF + 2 * CT_U * 64;                   // [2][F][64 B], chunk-swizzled
+    static constexpr int STAGE = (X_OFF + 2 * F * 64 + 1023) / 1024 * 1024;
+};
+
+template <int F, int M>
 __global__ void __launch_bounds__(CW_THREADS, 1)
 cin_wgrad_tc_kernel(const __grid_constant__ CinWgParams p) {
+    using L = CwLayout<F, M>;
+    constexpr int NB = L::NB;
     constexpr int NPAIR = CT_U * F;                                      // (u, h) pairs
     constexpr int MT = (NPAIR + 127) / 128;                              // M-tiles
     static_assert(MT <= 4 && M <= 32, "accumulator plan");
-    constexpr uint32_t A_COL = 4 * 64;                                   // after the four 64-column accumulators
+    constexpr uint32_t ACCW = 2 * NB;
+    constexpr uint32_t A_COL = 4 * ACCW;                                 // after the accumulators
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* b_base = smem;                                              // CW_BST x 8 KiB
-    uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + CW_BST * CW_B_BYTES);
-    uint64_t* b_full = bars;                       // [CW_BST]
-    uint64_t* b_empty = b_full + CW_BST;           // [CW_BST]
+    uint8_t* st_base = smem;                                             // CW_BST stages
+    uint64_t* bars = reinterpret_cast<uint64_t*>(st_base + CW_BST * L::STAGE);
+    uint64_t* b_full = bars;                       // [CW_BST] loader -> MMA thread and operand warps
+    uint64_t* b_empty = b_full + CW_BST;           // [CW_BST] 1 commit + 8 operand warps
     uint64_t* a_ready = b_empty + CW_BST;          // [CW_OPN] 8 arrivals
     uint64_t* a_empty = a_ready + CW_OPN;          // [CW_OPN]
     uint64_t* acc_done = a_empty + CW_OPN;         // [1]
@@ -510,13 +751,13 @@ cin_wgrad_tc_kernel(const __grid_constant__ CinWgParams p) {
     const int kb0 = (int)blockIdx.x * per, kb1 = min(p.n_kb, kb0 + per);
     const int nkb = max(0, kb1 - kb0);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < CW_BST; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < CW_BST; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 9); }
         for (int s = 0; s < CW_OPN; ++s) { mbar_init(&a_ready[s], 8); mbar_init(&a_empty[s], 1); }
         mbar_init(acc_done, 1);
         fence_barrier_init();
     }
     // rows m >= M of every stacked tile stay zero for the whole kernel
-    for (int i = threadIdx.x; i < CW_BST * CW_B_BYTES / 16; i += blockDim.x) reinterpret_cast<float4*>(b_base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = threadIdx.x; i < CW_BST * L::STAGE / 16; i += blockDim.x) reinterpret_cast<float4*>(st_base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (warp == 1) tmem_alloc(tmem_ptr, 512);
     fence_proxy_async();
     tc_fence_before();
@@ -525,11 +766,11 @@ cin_wgrad_tc_kernel(const __grid_constant__ CinWgParams p) {
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp == 0) {
-        // ---------------- Xk loader: raw rows by cp.async (16-byte pieces, SWIZZLE_128B positions), then the lo tile
+        // ---------------- loader: Xk / G / X0 rows of the k-block by cp.async (16-byte pieces), then the lo half of the B tile
         for (int i = 0; i < nkb; ++i) {
             const int s = i % CW_BST;
             mbar_wait(&b_empty[s], ((i / CW_BST) & 1u) ^ 1u);
-            uint8_t* tile = b_base + (size_t)s * CW_B_BYTES;
+            uint8_t* tile = st_base + (size_t)s * L::STAGE;
             const long long bA = (long long)(kb0 + i) * 2;
             for (int e = lane; e < M * 8; e += 32) {                      // (row m, chunk c): c < 4 sample 0, c >= 4 sample 1
                 const int m = e >> 3, c = e & 7;
@@ -537,6 +778,20 @@ cin_wgrad_tc_kernel(const __grid_constant__ CinWgParams p) {
                 const bool ok = b < p.B;
                 const float* src = p.xk + (size_t)(ok ? b : 0) * p.ldk + m * CT_D + (c & 3) * 4;
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_u32(tile + m * 128 + ((c ^ (m & 7)) << 4))), "l"(src), "r"(ok ? 16 : 0) : "memory");
+            }
+            for (int e = lane; e < 2 * CT_U * 4; e += 32) {               // G[half][u] chunk c
+                const int half = e >> 6, u = (e >> 2) & 15, c = e & 3;
+                const long long b = bA + half;
+                const bool ok = b < p.B;
+                const float* src = p.g + (size_t)(ok ? b : 0) * p.ldg + u * CT_D + c * 4;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_u32(tile + L::G_OFF + (half * CT_U + u) * 64 + (c << 4))), "l"(src), "r"(ok ? 16 : 0) : "memory");
+            }
+            for (int e = lane; e < 2 * F * 4; e += 32) {                  // X0[half][h] chunk c at position c ^ ((h >> 1) & 3)
+                const int half = e / (F * 4), r = e - half * (F * 4), h = r >> 2, c = r & 3;
+                const long long b = bA + half;
+                const bool ok = b < p.B;
+                const float* src = p.x0 + (size_t)(ok ? b : 0) * p.ld0 + h * CT_D + c * 4;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_u32(tile + L::X_OFF + (half * F + h) * 64 + ((c ^ ((h >> 1) & 3)) << 4))), "l"(src), "r"(ok ? 16 : 0) : "memory");
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -548,7 +803,7 @@ cin_wgrad_tc_kernel(const __grid_constant__ CinWgParams p) {
                 float4 l;
                 l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
                 l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-                *reinterpret_cast<float4*>(tile + 32 * 128 + off) = l;   // rows 32.. of the stacked tile (same swizzle phase: 32 % 8 == 0)
+                *reinterpret_cast<float4*>(tile + NB * 128 + off) = l;   // lower half of the stacked tile (same swizzle phase: NB % 8 == 0)
             }
             fence_proxy_async();                                          // generic-proxy writes -> the MMA's async-proxy reads
             __syncwarp();
@@ -556,18 +811,18 @@ cin_wgrad_tc_kernel(const __grid_constant__ CinWgParams p) {
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(TC_BLOCK_M, 64);
+            const uint32_t idesc = make_idesc_tf32(TC_BLOCK_M, 2 * NB);
             uint32_t ga = 0;
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % CW_BST;
                 mbar_wait(&b_full[s], (i / CW_BST) & 1u);
                 tc_fence_after();
-                const uint32_t b_addr = smem_u32(b_base + (size_t)s * CW_B_BYTES);
+                const uint32_t b_addr = smem_u32(st_base + (size_t)s * L::STAGE);
                 for (int mt = 0; mt < MT; ++mt, ++ga) {
                     const int o = ga % CW_OPN;
                     mbar_wait(&a_ready[o], (ga / CW_OPN) & 1u);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)mt * 64u;
+                    const uint32_t d_tmem = tmem_base + (uint32_t)mt * ACCW;
                     const uint32_t ta_hi = tmem_base + A_COL + (uint32_t)o * 64u, ta_lo = ta_hi + 32u;
 #pragma unroll
                     for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
@@ -585,21 +840,30 @@ cin_wgrad_tc_kernel(const __grid_constant__ CinWgParams p) {
         // ---------------- operand warps: lane = (u, h) pair of the M-tile, `half` = which sample of the k-block
         const int q = warp & 3, half = (warp - 2) >> 2;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        uint32_t g_off[MT], x_off[MT], x_sw[MT];
+        bool okp[MT];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            const int pr = mt * 128 + q * 32 + lane;
+            okp[mt] = pr < NPAIR;
+            const int u = okp[mt] ? pr / F : 0, h = okp[mt] ? pr - u * F : 0;
+            g_off[mt] = L::G_OFF + (half * CT_U + u) * 64;
+            x_off[mt] = L::X_OFF + (half * F + h) * 64;
+            x_sw[mt] = (h >> 1) & 3;
+        }
         uint32_t ga = 0;
         for (int i = 0; i < nkb; ++i) {
-            const long long b = (long long)(kb0 + i) * 2 + half;
-            const bool okb = b < p.B;
+            const int s = i % CW_BST;
+            const uint8_t* tile = st_base + (size_t)s * L::STAGE;
+            mbar_wait(&b_full[s], (i / CW_BST) & 1u);
+#pragma unroll
             for (int mt = 0; mt < MT; ++mt, ++ga) {
-                const int pr = mt * 128 + q * 32 + lane;
-                const bool ok = okb && pr < NPAIR;
-                const int u = pr / F, h = pr - u * F;
                 uint32_t hi[16], lo[16];
-                if (ok) {
-                    const float4* gr = reinterpret_cast<const float4*>(p.g + (size_t)b * p.ldg + u * CT_D);
-                    const float4* xr = reinterpret_cast<const float4*>(p.x0 + (size_t)b * p.ld0 + h * CT_D);
+                if (okp[mt]) {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        const float4 a = __ldg(gr + c), x = __ldg(xr + c);
+                        const float4 a = *reinterpret_cast<const float4*>(tile + g_off[mt] + (c << 4));
+                        const float4 x = *reinterpret_cast<const float4*>(tile + x_off[mt] + ((c ^ x_sw[mt]) << 4));
                         const float z[4] = {a.x * x.x, a.y * x.y, a.z * x.z, a.w * x.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
@@ -622,6 +886,7 @@ cin_wgrad_tc_kernel(const __grid_constant__ CinWgParams p) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_ready[o]);
             }
+            if (lane == 0) mbar_arrive(&b_empty[s]);                      // this warp has read the stage's G / X0 rows (syncwarp above)
         }
         // ---------------- epilogue (first four operand warps): acc[mt] = a.b_raw | a.b_lo  ->  dW[u, h*M + m] += sum
         if (half == 0 && nkb > 0) {
@@ -629,18 +894,18 @@ cin_wgrad_tc_kernel(const __grid_constant__ CinWgParams p) {
             tc_fence_after();
             for (int mt = 0; mt < MT; ++mt) {
                 const int pr = mt * 128 + q * 32 + lane;
-                uint32_t a0[16], a1[16], c0[16], c1[16];
-                tmem_ld16(tmem_base + (uint32_t)mt * 64u + lane_addr, a0);
-                tmem_ld16(tmem_base + (uint32_t)mt * 64u + lane_addr + 16u, a1);
-                tmem_ld16(tmem_base + (uint32_t)mt * 64u + lane_addr + 32u, c0);
-                tmem_ld16(tmem_base + (uint32_t)mt * 64u + lane_addr + 48u, c1);
-                if (pr < NPAIR) {
-                    const int u = pr / F, h = pr - u * F;
-                    float* dst = p.dW + (size_t)u * (F * M) + h * M;
+                const int u = pr / F, h = pr - u * F;
+                float* dst = p.dW + (size_t)u * (F * M) + h * M;
 #pragma unroll
-                    for (int m = 0; m < 16; ++m) if (m < M) red_add_f1(dst + m, __uint_as_float(a0[m]) + __uint_as_float(c0[m]));
+                for (int c = 0; c < NB; c += 16) {
+                    uint32_t a[16], l[16];
+                    tmem_ld16(tmem_base + (uint32_t)mt * ACCW + lane_addr + (uint32_t)c, a);
+                    tmem_ld16(tmem_base + (uint32_t)mt * ACCW + lane_addr + (uint32_t)(NB + c), l);
+                    if (pr < NPAIR) {
 #pragma unroll
-                    for (int m = 16; m < 32; ++m) if (m < M) red_add_f1(dst + m, __uint_as_float(a1[m - 16]) + __uint_as_float(c1[m - 16]));
+                        for (int e = 0; e < 16; ++e)
+                            if (c + e < M) red_add_f1(dst + c + e, __uint_as_float(a[e]) + __uint_as_float(l[e]));
+                    }
                 }
             }
         }
@@ -652,7 +917,7 @@ cin_wgrad_tc_kernel(const __grid_constant__ CinWgParams p) {
 
 template <int F, int M>
 static int cin_wgrad_tc_launch(const CinWgParams& p, cudaStream_t st) {
-    const size_t smem = (size_t)CW_BST * CW_B_BYTES + (2 * CW_BST + 2 * CW_OPN + 1) * 8 + 16 + 1024;
+    const size_t smem = (size_t)CW_BST * CwLayout<F, M>::STAGE + (2 * CW_BST + 2 * CW_OPN + 1) * 8 + 16 + 1024;
     cudaError_t e = cudaFuncSetAttribute(cin_wgrad_tc_kernel<F, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     cin_wgrad_tc_kernel<F, M><<<min(p.n_kb, 148), CW_THREADS, smem, st>>>(p);
