@@ -28,6 +28,51 @@ constexpr int CT_ACC = 2 * CT_U;         // accumulator columns: [A.Whi^T | A.Wl
 constexpr int CT_A_COL = 2 * CT_ACC;     // two accumulator buffers, then the operand ring
 constexpr int CT_KB_BYTES = 2 * CT_U * TC_BLOCK_K * 4;     // one resident weight k-block: 32 rows x 128 B = 4 KiB
 
+// one lane of a converged warp (the same lane every time: MMA issue and the commits that track it must come from one thread)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// Pre-split K-major weight operands with PERMUTED rows, so that consecutive accumulator columns feed different register
+// accumulators in the epilogues (a chain of dependent FMAs per output otherwise: profiles/r02_cin_ncu.md).
+//   mode 0 (forward):  row h*16 + u            = W[u, h*M + 0..M-1]                      (K = M columns, zero padded to 32)
+//   mode 1 (backward): row s*F + h, m=(h+s)%M  = W[0..15, h*M + m]  (W^T, K = 16 columns, zero padded to 32)
+__global__ void __launch_bounds__(256)
+cin_pack_operand_kernel(const float* __restrict__ W, int F, int M, int mode, int rows_valid, int Rp, float* __restrict__ hi, float* __restrict__ lo) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= Rp * TC_BLOCK_K) return;
+    const int r = t / TC_BLOCK_K, c = t - r * TC_BLOCK_K;
+    float v = 0.f;
+    if (r < rows_valid) {
+        if (mode == 0) {
+            const int h = r / CT_U, u = r - h * CT_U;
+            if (c < M) v = __ldg(W + (size_t)u * F * M + h * M + c);
+        } else {
+            const int sft = r / F, h = r - sft * F, m = (h + sft) % M;
+            if (c < CT_U) v = __ldg(W + (size_t)c * F * M + h * M + m);
+        }
+    }
+    const float hv = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    hi[t] = hv;
+    lo[t] = v - hv;
+}
+
+static int cin_prepare_operand(const float* W, int F, int M, int mode, int Rp, int box_rows, int slot, CUtensorMap* tm_hi, CUtensorMap* tm_lo,
+                               cudaStream_t st) {
+    int werr = 0;
+    float* ws = static_cast<float*>(workspace(slot, (size_t)2 * Rp * TC_BLOCK_K * sizeof(float), &werr));
+    if (ws == nullptr) return werr;
+    float* hi = ws;
+    float* lo = ws + (size_t)Rp * TC_BLOCK_K;
+    const int rows_valid = mode == 0 ? CT_U * F : F * M;
+    cin_pack_operand_kernel<<<ceil_div(Rp * TC_BLOCK_K, 256), 256, 0, st>>>(W, F, M, mode, rows_valid, Rp, hi, lo);
+    int rc = tc_make_map2d(tm_hi, hi, Rp, TC_BLOCK_K, TC_BLOCK_K, TC_BLOCK_K, box_rows, 128);
+    if (rc == 0) rc = tc_make_map2d(tm_lo, lo, Rp, TC_BLOCK_K, TC_BLOCK_K, TC_BLOCK_K, box_rows, 128);
+    return rc;
+}
+
 struct CinTcParams {
     const float* x0; long long ld0;      // X0[b,h,d] = x0[b * ld0 + h * 16 + d]            (feature row of the gather)
     const float* xk; long long ldk;      // Xk[b,m,d] = xk[b * ldk + m * 16 + d]            (layer 0: = x0)
@@ -218,7 +263,7 @@ static int cin_fwd_tc_launch(const float* W, const CinTcParams& p, cudaStream_t 
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Forward, second formulation (the default): contract over m on the tensor core, over h in the epilogue.
-//     T[(b,d), (u,h)] = sum_m Xk[b,m,d] * W_k[u, h*M + m]           (rows x M x 16*F GEMM; A = Xk rows, K = M)
+//     T[(b,d), (h,u)] = sum_m Xk[b,m,d] * W_k[u, h*M + m]           (rows x M x 16*F GEMM; A = Xk rows, K = M)
 //     X_{k+1}[b,u,d]  = sum_h X0[b,h,d] * T[(b,d), (u,h)] + bias[u]  (epilogue, straight out of the accumulator)
 // Same flops on the tensor core as the outer-product form, but the A operand is M values per row instead of F*M products
 // (26 splits instead of 676: the split warps were the bound, profiles/r02_cin_ncu.md), W_k is its own K-major operand
@@ -227,7 +272,7 @@ constexpr int C2_THREADS = 12 * 32;      // warpgroups: [0 weights, 1 MMA, 2-3 i
 
 template <int F, int NT, int NTI, int C0>
 struct CinTCols {
-    // columns C0 .. C0+15 of N-tile NTI (global j = NTI*NT + C0 + i = u*F + h): out[u] += T * x0[h]
+    // columns C0 .. C0+15 of N-tile NTI (global j = NTI*NT + C0 + i = h*16 + u, cin_pack_operand_kernel mode 0): out[u] += T * x0[h]
     static __device__ __forceinline__ void run(uint32_t acc_addr, const float (&x0)[F], float (&out)[CT_U]) {
         if constexpr (C0 < NT && NTI * NT + C0 < CT_U * F) {
             uint32_t a[16];
@@ -235,7 +280,7 @@ struct CinTCols {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const int j = NTI * NT + C0 + i;
-                if (j < CT_U * F) out[j / F] = fmaf(__uint_as_float(a[i]), x0[j % F], out[j / F]);
+                if (j < CT_U * F) out[j % CT_U] = fmaf(__uint_as_float(a[i]), x0[j / CT_U], out[j % CT_U]);
             }
             CinTCols<F, NT, NTI, C0 + 16>::run(acc_addr, x0, out);
         }
@@ -305,32 +350,36 @@ cin_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_const
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(TC_BLOCK_M, NT);
-            mbar_wait(w_full, 0u);
-            uint32_t n_acc = 0;
-            for (int t = 0; t < my_tiles; ++t) {
-                const uint32_t ab = (uint32_t)t & 1u;
-                mbar_wait(&a_ready[ab], ((uint32_t)t >> 1) & 1u);
+        // MMA issue: warp-uniform control flow, one elected lane issues; descriptors advance by additions
+        const uint32_t idesc = make_idesc_tf32(TC_BLOCK_M, NT);
+        const uint64_t dh0 = make_kmajor_sw128_desc(smem_u32(w_hi)), dl0 = make_kmajor_sw128_desc(smem_u32(w_lo));
+        mbar_wait(w_full, 0u);
+        uint32_t n_acc = 0;
+        for (int t = 0; t < my_tiles; ++t) {
+            const uint32_t ab = (uint32_t)t & 1u;
+            mbar_wait(&a_ready[ab], ((uint32_t)t >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t ta_hi = tmem_base + A_COL + ab * (2 * KP), ta_lo = ta_hi + KP;
+#pragma unroll
+            for (int nt = 0; nt < NTILES; ++nt, ++n_acc) {
+                const uint32_t buf = n_acc & 1u;
+                mbar_wait(&acc_empty[buf], ((n_acc >> 1) & 1u) ^ 1u);
                 tc_fence_after();
-                const uint32_t ta_hi = tmem_base + A_COL + ab * (2 * KP), ta_lo = ta_hi + KP;
-                for (int nt = 0; nt < NTILES; ++nt, ++n_acc) {
-                    const uint32_t buf = n_acc & 1u;
-                    mbar_wait(&acc_empty[buf], ((n_acc >> 1) & 1u) ^ 1u);
-                    tc_fence_after();
+                if (elect_one()) {
                     const uint32_t d_tmem = tmem_base + ACC0 + buf * NT;
-                    const uint32_t bh = smem_u32(w_hi + (size_t)nt * NT * 128), bl = smem_u32(w_lo + (size_t)nt * NT * 128);
 #pragma unroll
                     for (int k = 0; k < KS; ++k) {
-                        const uint64_t dh = make_kmajor_sw128_desc(bh + k * TC_UMMA_K * 4), dl = make_kmajor_sw128_desc(bl + k * TC_UMMA_K * 4);
-                        umma_tf32_ts(d_tmem, ta_lo + k * TC_UMMA_K, dh, idesc, k > 0 ? 1u : 0u);
-                        umma_tf32_ts(d_tmem, ta_hi + k * TC_UMMA_K, dl, idesc, 1u);
-                        umma_tf32_ts(d_tmem, ta_hi + k * TC_UMMA_K, dh, idesc, 1u);
+                        const uint64_t off = (uint64_t)((nt * NT * 128 + k * TC_UMMA_K * 4) >> 4);
+                        umma_tf32_ts(d_tmem, ta_lo + k * TC_UMMA_K, dh0 + off, idesc, k > 0 ? 1u : 0u);
+                        umma_tf32_ts(d_tmem, ta_hi + k * TC_UMMA_K, dl0 + off, idesc, 1u);
+                        umma_tf32_ts(d_tmem, ta_hi + k * TC_UMMA_K, dh0 + off, idesc, 1u);
                     }
                     umma_commit(&acc_full[buf]);
                 }
-                umma_commit(&a_empty[ab]);
+                __syncwarp();
             }
+            if (elect_one()) umma_commit(&a_empty[ab]);
+            __syncwarp();
         }
     }
     } else if (warp < 8) {
@@ -416,8 +465,8 @@ cin_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_const
 template <int F, int M, int NT, int NTILES>
 static int cin_fwd2_tc_launch(const float* W, const CinTcParams& p, cudaStream_t st) {
     CUtensorMap tmWhi, tmWlo;
-    // W_k [16, F*M] read as [(u,h) = 16*F rows, M columns] -> hi / lo [NT*NTILES rows, 32 columns] (zero padded), [NT x 32] boxes
-    int rc = tc_prepare_operand(W, M, CT_U * F, M, 0, NT * NTILES, TC_BLOCK_K, NT, 9, &tmWhi, &tmWlo, st);
+    // W_k [16, F*M] -> rows (h, u), M columns -> hi / lo [NT*NTILES rows, 32 columns] (zero padded), [NT x 32] boxes
+    int rc = cin_prepare_operand(W, F, M, 0, NT * NTILES, NT, 9, &tmWhi, &tmWlo, st);
     if (rc != 0) return rc;
     const size_t smem = (size_t)2 * NT * NTILES * 128 + 9 * 8 + 32 + 1024;
     cudaError_t e = cudaFuncSetAttribute(cin_fwd2_tc_kernel<F, M, NT, NTILES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -468,7 +517,9 @@ struct CinBwdParams {
 
 template <int F, int M, int NT, int NTI, int C0>
 struct CinDzCols {
-    // columns C0 .. C0+15 of N-tile NTI (global j = NTI*NT + C0 + i): dxk[m] += dz * x0[h], dx0[h] += dz * xk[m]
+    // columns C0 .. C0+15 of N-tile NTI; global column j = NTI*NT + C0 + i = s*F + h stands for (h, m = (h + s) % M)
+    // (cin_pack_operand_kernel mode 1: neighbouring columns differ in h AND m, so no two consecutive FMAs share an accumulator):
+    // dxk[m] += dz * x0[h], dx0[h] += dz * xk[m]
     static __device__ __forceinline__ void run(uint32_t acc_addr, const float (&x0)[F], const float (&xk)[M], float (&dx0)[F], float (&dxk)[M]) {
         if constexpr (C0 < NT && NTI * NT + C0 < F * M) {
             uint32_t a[16];
@@ -477,9 +528,10 @@ struct CinDzCols {
             for (int i = 0; i < 16; ++i) {
                 const int j = NTI * NT + C0 + i;
                 if (j < F * M) {
+                    const int h = j % F, m = (h + j / F) % M;
                     const float dz = __uint_as_float(a[i]);
-                    dxk[j % M] = fmaf(dz, x0[j / M], dxk[j % M]);
-                    dx0[j / M] = fmaf(dz, xk[j % M], dx0[j / M]);
+                    dxk[m] = fmaf(dz, x0[h], dxk[m]);
+                    dx0[h] = fmaf(dz, xk[m], dx0[h]);
                 }
             }
             CinDzCols<F, M, NT, NTI, C0 + 16>::run(acc_addr, x0, xk, dx0, dxk);
@@ -530,32 +582,36 @@ cin_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(TC_BLOCK_M, NT);
-            mbar_wait(w_full, 0u);
-            uint32_t n_acc = 0;
-            for (int t = 0; t < my_tiles; ++t) {
-                const uint32_t ab = (uint32_t)t & 1u;
-                mbar_wait(&a_ready[ab], ((uint32_t)t >> 1) & 1u);
+        // MMA issue: warp-uniform control flow, one elected lane issues; descriptors advance by additions
+        const uint32_t idesc = make_idesc_tf32(TC_BLOCK_M, NT);
+        const uint64_t dh0 = make_kmajor_sw128_desc(smem_u32(w_hi)), dl0 = make_kmajor_sw128_desc(smem_u32(w_lo));
+        mbar_wait(w_full, 0u);
+        uint32_t n_acc = 0;
+        for (int t = 0; t < my_tiles; ++t) {
+            const uint32_t ab = (uint32_t)t & 1u;
+            mbar_wait(&a_ready[ab], ((uint32_t)t >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t ta_hi = tmem_base + A_COL + ab * 32u, ta_lo = ta_hi + 16u;
+#pragma unroll
+            for (int nt = 0; nt < NTILES; ++nt, ++n_acc) {
+                const uint32_t buf = n_acc & 1u;
+                mbar_wait(&acc_empty[buf], ((n_acc >> 1) & 1u) ^ 1u);
                 tc_fence_after();
-                const uint32_t ta_hi = tmem_base + A_COL + ab * 32u, ta_lo = ta_hi + 16u;
-                for (int nt = 0; nt < NTILES; ++nt, ++n_acc) {
-                    const uint32_t buf = n_acc & 1u;
-                    mbar_wait(&acc_empty[buf], ((n_acc >> 1) & 1u) ^ 1u);
-                    tc_fence_after();
+                if (elect_one()) {
                     const uint32_t d_tmem = tmem_base + ACC0 + buf * NT;
-                    const uint32_t bh = smem_u32(w_hi + (size_t)nt * NT * 128), bl = smem_u32(w_lo + (size_t)nt * NT * 128);
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {                          // K = 16 = 2 k-steps of 8
-                        const uint64_t dh = make_kmajor_sw128_desc(bh + k * TC_UMMA_K * 4), dl = make_kmajor_sw128_desc(bl + k * TC_UMMA_K * 4);
-                        umma_tf32_ts(d_tmem, ta_lo + k * TC_UMMA_K, dh, idesc, k > 0 ? 1u : 0u);
-                        umma_tf32_ts(d_tmem, ta_hi + k * TC_UMMA_K, dl, idesc, 1u);
-                        umma_tf32_ts(d_tmem, ta_hi + k * TC_UMMA_K, dh, idesc, 1u);
+                        const uint64_t off = (uint64_t)((nt * NT * 128 + k * TC_UMMA_K * 4) >> 4);
+                        umma_tf32_ts(d_tmem, ta_lo + k * TC_UMMA_K, dh0 + off, idesc, k > 0 ? 1u : 0u);
+                        umma_tf32_ts(d_tmem, ta_hi + k * TC_UMMA_K, dl0 + off, idesc, 1u);
+                        umma_tf32_ts(d_tmem, ta_hi + k * TC_UMMA_K, dh0 + off, idesc, 1u);
                     }
                     umma_commit(&acc_full[buf]);
                 }
-                umma_commit(&a_empty[ab]);
+                __syncwarp();
             }
+            if (elect_one()) umma_commit(&a_empty[ab]);
+            __syncwarp();
         }
     }
     } else if (warp < 8) {
@@ -674,8 +730,8 @@ template <int F, int M, int NT, int NTILES>
 static int cin_bwd_tc_launch(const float* W, const CinBwdParams& p, cudaStream_t st) {
     static_assert(NTILES <= 4 && NT % 16 == 0 && NT * NTILES >= F * M && 2 * NT + 64 <= 512, "tile plan");
     CUtensorMap tmWhi, tmWlo;
-    // W_k [16, F*M] -> W_k^T [NT*NTILES rows, 32 columns] hi / lo (columns 16.. and rows F*M.. are zero)
-    int rc = tc_prepare_operand(W, F * M, CT_U, F * M, 1, NT * NTILES, TC_BLOCK_K, NT, 8, &tmWhi, &tmWlo, st);
+    // W_k [16, F*M] -> W_k^T with permuted rows (s, h) [NT*NTILES rows, 32 columns] hi / lo (columns 16.. and rows F*M.. are zero)
+    int rc = cin_prepare_operand(W, F, M, 1, NT * NTILES, NT, 8, &tmWhi, &tmWlo, st);
     if (rc != 0) return rc;
     const size_t smem = (size_t)2 * NT * NTILES * 128 + 9 * 8 + 16 + 4 * CT_U * 4 + 1024;
     cudaError_t e = cudaFuncSetAttribute(cin_bwd_tc_kernel<F, M, NT, NTILES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -704,7 +760,8 @@ int cin_layer_bwd_tc(int F, int M, const float* W, const CinBwdParams& p, cudaSt
 //   * the four accumulators (2*NB columns each) live in tensor memory for the CTA's whole slab of rows; the epilogue adds the two
 //     halves and reduces into dW with fp32 `red`.
 constexpr int CW_THREADS = 10 * 32;      // 0 = loader, 1 = MMA, 2-9 = operand warps (w, w+4: sample 0 / 1 of the k-block), 2-5 also epilogue
-constexpr int CW_BST = 4;                // stage ring
+constexpr int CW_BST = 6;                // stage ring
+constexpr int CW_AHEAD = 4;              // k-blocks whose cp.async groups are in flight (< CW_BST)
 constexpr int CW_OPN = 4;                // A operand ring (64 columns each)
 
 struct CinWgParams {
@@ -766,12 +823,13 @@ cin_wgrad_tc_kernel(const __grid_constant__ CinWgParams p) {
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp == 0) {
-        // ---------------- loader: Xk / G / X0 rows of the k-block by cp.async (16-byte pieces), then the lo half of the B tile
-        for (int i = 0; i < nkb; ++i) {
-            const int s = i % CW_BST;
-            mbar_wait(&b_empty[s], ((i / CW_BST) & 1u) ^ 1u);
+        // ---------------- loader: Xk / G / X0 rows of a k-block by cp.async (16-byte pieces), CW_AHEAD k-blocks in flight (one
+        // cp.async group per k-block), then the lo half of the B tile once the group has landed
+        auto issue = [&](int j) {
+            const int s = j % CW_BST;
+            mbar_wait(&b_empty[s], ((j / CW_BST) & 1u) ^ 1u);
             uint8_t* tile = st_base + (size_t)s * L::STAGE;
-            const long long bA = (long long)(kb0 + i) * 2;
+            const long long bA = (long long)(kb0 + j) * 2;
             for (int e = lane; e < M * 8; e += 32) {                      // (row m, chunk c): c < 4 sample 0, c >= 4 sample 1
                 const int m = e >> 3, c = e & 7;
                 const long long b = bA + (c >> 2);
@@ -793,8 +851,15 @@ cin_wgrad_tc_kernel(const __grid_constant__ CinWgParams p) {
                 const float* src = p.x0 + (size_t)(ok ? b : 0) * p.ld0 + h * CT_D + c * 4;
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_u32(tile + L::X_OFF + (half * F + h) * 64 + ((c ^ ((h >> 1) & 3)) << 4))), "l"(src), "r"(ok ? 16 : 0) : "memory");
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        };
+        for (int j = 0; j < CW_AHEAD; ++j) {
+            if (j < nkb) issue(j);
+            asm volatile("cp.async.commit_group;" ::: "memory");          // (possibly empty) group j
+        }
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % CW_BST;
+            uint8_t* tile = st_base + (size_t)s * L::STAGE;
+            asm volatile("cp.async.wait_group %0;" :: "n"(CW_AHEAD - 1) : "memory");      // group i has landed
             __syncwarp();
             for (int e = lane; e < M * 8; e += 32) {
                 const int m = e >> 3, c = e & 7;
@@ -808,34 +873,44 @@ cin_wgrad_tc_kernel(const __grid_constant__ CinWgParams p) {
             fence_proxy_async();                                          // generic-proxy writes -> the MMA's async-proxy reads
             __syncwarp();
             if (lane == 0) mbar_arrive(&b_full[s]);
+            if (i + CW_AHEAD < nkb) issue(i + CW_AHEAD);
+            asm volatile("cp.async.commit_group;" ::: "memory");
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(TC_BLOCK_M, 2 * NB);
-            uint32_t ga = 0;
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % CW_BST;
-                mbar_wait(&b_full[s], (i / CW_BST) & 1u);
+        // ---------------- MMA issue: warp-uniform control flow, one elected lane issues (no per-instruction waterfall: with 32 small
+        // MMAs per k-block the issue loop was the bound, profiles/r02_cin_ncu.md); descriptors advance by additions
+        const uint32_t idesc = make_idesc_tf32(TC_BLOCK_M, 2 * NB);
+        const uint64_t desc0 = make_kmajor_sw128_desc(smem_u32(st_base));
+        uint32_t ga = 0;
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % CW_BST;
+            mbar_wait(&b_full[s], (i / CW_BST) & 1u);
+            tc_fence_after();
+            const uint64_t dbs = desc0 + (uint64_t)(((uint32_t)s * (uint32_t)L::STAGE) >> 4);
+            const uint32_t acc_on = i > 0 ? 1u : 0u;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt, ++ga) {
+                const uint32_t o = ga % CW_OPN;
+                mbar_wait(&a_ready[o], (ga / CW_OPN) & 1u);
                 tc_fence_after();
-                const uint32_t b_addr = smem_u32(st_base + (size_t)s * L::STAGE);
-                for (int mt = 0; mt < MT; ++mt, ++ga) {
-                    const int o = ga % CW_OPN;
-                    mbar_wait(&a_ready[o], (ga / CW_OPN) & 1u);
-                    tc_fence_after();
+                if (elect_one()) {
                     const uint32_t d_tmem = tmem_base + (uint32_t)mt * ACCW;
-                    const uint32_t ta_hi = tmem_base + A_COL + (uint32_t)o * 64u, ta_lo = ta_hi + 32u;
+                    const uint32_t ta_hi = tmem_base + A_COL + o * 64u, ta_lo = ta_hi + 32u;
 #pragma unroll
                     for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
-                        const uint64_t db = make_kmajor_sw128_desc(b_addr + k * TC_UMMA_K * 4);
-                        umma_tf32_ts(d_tmem, ta_lo + k * TC_UMMA_K, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                        const uint64_t db = dbs + (uint64_t)(k * TC_UMMA_K * 4 >> 4);
+                        umma_tf32_ts(d_tmem, ta_lo + k * TC_UMMA_K, db, idesc, k > 0 ? 1u : acc_on);
                         umma_tf32_ts(d_tmem, ta_hi + k * TC_UMMA_K, db, idesc, 1u);
                     }
                     umma_commit(&a_empty[o]);
                 }
-                umma_commit(&b_empty[s]);
+                __syncwarp();
             }
-            umma_commit(acc_done);
+            if (elect_one()) umma_commit(&b_empty[s]);
+            __syncwarp();
         }
+        if (elect_one()) umma_commit(acc_done);
+        __syncwarp();
     } else {
         // ---------------- operand warps: lane = (u, h) pair of the M-tile, `half` = which sample of the k-block
         const int q = warp & 3, half = (warp - 2) >> 2;
