@@ -28,13 +28,6 @@ constexpr int CT_ACC = 2 * CT_U;         // accumulator columns: [A.Whi^T | A.Wl
 constexpr int CT_A_COL = 2 * CT_ACC;     // two accumulator buffers, then the operand ring
 constexpr int CT_KB_BYTES = 2 * CT_U * TC_BLOCK_K * 4;     // one resident weight k-block: 32 rows x 128 B = 4 KiB
 
-// one lane of a converged warp (the same lane every time: MMA issue and the commits that track it must come from one thread)
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-
 // Pre-split K-major weight operands with PERMUTED rows, so that consecutive accumulator columns feed different register
 // accumulators in the epilogues (a chain of dependent FMAs per output otherwise: profiles/r02_cin_ncu.md).
 //   mode 0 (forward):  row h*16 + u            = W[u, h*M + 0..M-1]                      (K = M columns, zero padded to 32)
@@ -759,7 +752,7 @@ int cin_layer_bwd_tc(int F, int M, const float* W, const CinBwdParams& p, cudaSt
 //     element-wise, splits and stores: no outer product, no transposition, no exposed DRAM latency.
 //   * the four accumulators (2*NB columns each) live in tensor memory for the CTA's whole slab of rows; the epilogue adds the two
 //     halves and reduces into dW with fp32 `red`.
-constexpr int CW_THREADS = 10 * 32;      // 0 = loader, 1 = MMA, 2-9 = operand warps (w, w+4: sample 0 / 1 of the k-block), 2-5 also epilogue
+constexpr int CW_THREADS = 11 * 32;      // 0 = Xk loader, 1 = MMA, 2-9 = operand warps (w, w+4: sample 0 / 1 of the k-block; 2-5 also epilogue), 10 = G / X0 loader
 constexpr int CW_BST = 6;                // stage ring
 constexpr int CW_AHEAD = 4;              // k-blocks whose cp.async groups are in flight (< CW_BST)
 constexpr int CW_OPN = 4;                // A operand ring (64 columns each)
@@ -795,9 +788,11 @@ cin_wgrad_tc_kernel(const __grid_constant__ CinWgParams p) {
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* st_base = smem;                                             // CW_BST stages
     uint64_t* bars = reinterpret_cast<uint64_t*>(st_base + CW_BST * L::STAGE);
-    uint64_t* b_full = bars;                       // [CW_BST] loader -> MMA thread and operand warps
-    uint64_t* b_empty = b_full + CW_BST;           // [CW_BST] 1 commit + 8 operand warps
-    uint64_t* a_ready = b_empty + CW_BST;          // [CW_OPN] 8 arrivals
+    uint64_t* b_full = bars;                       // [CW_BST] Xk tile (+ lo half) written          -> MMA thread
+    uint64_t* b_empty = b_full + CW_BST;           // [CW_BST] its MMAs are done (commit)          -> Xk loader
+    uint64_t* g_full = b_empty + CW_BST;           // [CW_BST] G / X0 rows written                  -> operand warps
+    uint64_t* g_empty = g_full + CW_BST;           // [CW_BST] 8 operand warps have read them       -> G / X0 loader
+    uint64_t* a_ready = g_empty + CW_BST;          // [CW_OPN] 8 arrivals
     uint64_t* a_empty = a_ready + CW_OPN;          // [CW_OPN]
     uint64_t* acc_done = a_empty + CW_OPN;         // [1]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_done + 1);
@@ -808,7 +803,7 @@ cin_wgrad_tc_kernel(const __grid_constant__ CinWgParams p) {
     const int kb0 = (int)blockIdx.x * per, kb1 = min(p.n_kb, kb0 + per);
     const int nkb = max(0, kb1 - kb0);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < CW_BST; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 9); }
+        for (int s = 0; s < CW_BST; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); mbar_init(&g_full[s], 1); mbar_init(&g_empty[s], 8); }
         for (int s = 0; s < CW_OPN; ++s) { mbar_init(&a_ready[s], 8); mbar_init(&a_empty[s], 1); }
         mbar_init(acc_done, 1);
         fence_barrier_init();
@@ -823,33 +818,31 @@ cin_wgrad_tc_kernel(const __grid_constant__ CinWgParams p) {
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp == 0) {
-        // ---------------- loader: Xk / G / X0 rows of a k-block by cp.async (16-byte pieces), CW_AHEAD k-blocks in flight (one
-        // cp.async group per k-block), then the lo half of the B tile once the group has landed
-        auto issue = [&](int j) {
-            const int s = j % CW_BST;
-            mbar_wait(&b_empty[s], ((j / CW_BST) & 1u) ^ 1u);
-            uint8_t* tile = st_base + (size_t)s * L::STAGE;
-            const long long bA = (long long)(kb0 + j) * 2;
-            for (int e = lane; e < M * 8; e += 32) {                      // (row m, chunk c): c < 4 sample 0, c >= 4 sample 1
-                const int m = e >> 3, c = e & 7;
-                const long long b = bA + (c >> 2);
+        // ---------------- Xk loader: rows of a k-block by cp.async (16-byte pieces, SWIZZLE_128B positions), CW_AHEAD k-blocks in
+        // flight (one cp.async group each), then the lo half of the tile once the group has landed.  Per-lane piece offsets are
+        // fixed for the whole kernel (the loaders were instruction-bound with the index arithmetic in the loop).
+        constexpr int NE = (M * 8 + 31) / 32;
+        uint32_t src_off[NE], dst_off[NE], hf[NE];
+#pragma unroll
+        for (int j = 0; j < NE; ++j) {
+            const int e = lane + 32 * j, m = e >> 3, c = e & 7;           // (row m, chunk c): c < 4 sample 0, c >= 4 sample 1
+            hf[j] = e < M * 8 ? (uint32_t)(c >> 2) : 0x40000000u;         // out-of-range pieces: "sample" beyond any batch
+            src_off[j] = m * CT_D + (c & 3) * 4;
+            dst_off[j] = m * 128 + ((c ^ (m & 7)) << 4);
+        }
+        auto issue = [&](int j2) {
+            const int s = j2 % CW_BST;
+            mbar_wait(&b_empty[s], ((j2 / CW_BST) & 1u) ^ 1u);
+            const uint32_t tile = smem_u32(st_base + (size_t)s * L::STAGE);
+            const long long bA = (long long)(kb0 + j2) * 2;
+#pragma unroll
+            for (int j = 0; j < NE; ++j) {
+                const long long b = bA + hf[j];
                 const bool ok = b < p.B;
-                const float* src = p.xk + (size_t)(ok ? b : 0) * p.ldk + m * CT_D + (c & 3) * 4;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_u32(tile + m * 128 + ((c ^ (m & 7)) << 4))), "l"(src), "r"(ok ? 16 : 0) : "memory");
-            }
-            for (int e = lane; e < 2 * CT_U * 4; e += 32) {               // G[half][u] chunk c
-                const int half = e >> 6, u = (e >> 2) & 15, c = e & 3;
-                const long long b = bA + half;
-                const bool ok = b < p.B;
-                const float* src = p.g + (size_t)(ok ? b : 0) * p.ldg + u * CT_D + c * 4;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_u32(tile + L::G_OFF + (half * CT_U + u) * 64 + (c << 4))), "l"(src), "r"(ok ? 16 : 0) : "memory");
-            }
-            for (int e = lane; e < 2 * F * 4; e += 32) {                  // X0[half][h] chunk c at position c ^ ((h >> 1) & 3)
-                const int half = e / (F * 4), r = e - half * (F * 4), h = r >> 2, c = r & 3;
-                const long long b = bA + half;
-                const bool ok = b < p.B;
-                const float* src = p.x0 + (size_t)(ok ? b : 0) * p.ld0 + h * CT_D + c * 4;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_u32(tile + L::X_OFF + (half * F + h) * 64 + ((c ^ ((h >> 1) & 3)) << 4))), "l"(src), "r"(ok ? 16 : 0) : "memory");
+                if (hf[j] < 2u) {
+                    const float* src = p.xk + (size_t)(ok ? b : 0) * p.ldk + src_off[j];
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(tile + dst_off[j]), "l"(src), "r"(ok ? 16 : 0) : "memory");
+                }
             }
         };
         for (int j = 0; j < CW_AHEAD; ++j) {
@@ -861,18 +854,63 @@ cin_wgrad_tc_kernel(const __grid_constant__ CinWgParams p) {
             uint8_t* tile = st_base + (size_t)s * L::STAGE;
             asm volatile("cp.async.wait_group %0;" :: "n"(CW_AHEAD - 1) : "memory");      // group i has landed
             __syncwarp();
-            for (int e = lane; e < M * 8; e += 32) {
-                const int m = e >> 3, c = e & 7;
-                const uint32_t off = m * 128 + ((c ^ (m & 7)) << 4);
-                const float4 v = *reinterpret_cast<const float4*>(tile + off);
-                float4 l;
-                l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-                l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-                *reinterpret_cast<float4*>(tile + NB * 128 + off) = l;   // lower half of the stacked tile (same swizzle phase: NB % 8 == 0)
+#pragma unroll
+            for (int j = 0; j < NE; ++j) {
+                if (hf[j] < 2u) {
+                    const float4 v = *reinterpret_cast<const float4*>(tile + dst_off[j]);
+                    float4 l;
+                    l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                    l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                    *reinterpret_cast<float4*>(tile + NB * 128 + dst_off[j]) = l;       // lower half of the stacked tile (same swizzle phase)
+                }
             }
             fence_proxy_async();                                          // generic-proxy writes -> the MMA's async-proxy reads
             __syncwarp();
             if (lane == 0) mbar_arrive(&b_full[s]);
+            if (i + CW_AHEAD < nkb) issue(i + CW_AHEAD);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+    } else if (warp == 10) {
+        // ---------------- G / X0 loader: [2][16 u][64 B] and [2][F][64 B] (chunks XOR-swizzled by (h >> 1) & 3) per k-block
+        constexpr int NG = (2 * CT_U * 4) / 32, NX = (2 * F * 4 + 31) / 32;
+        uint32_t src_off[NG + NX], dst_off[NG + NX], hf[NG + NX];
+#pragma unroll
+        for (int j = 0; j < NG; ++j) {
+            const int e = lane + 32 * j, half = e >> 6, u = (e >> 2) & 15, c = e & 3;
+            hf[j] = (uint32_t)half;
+            src_off[j] = u * CT_D + c * 4;
+            dst_off[j] = L::G_OFF + (half * CT_U + u) * 64 + (c << 4);
+        }
+#pragma unroll
+        for (int j = 0; j < NX; ++j) {
+            const int e = lane + 32 * j, half = e / (F * 4), r = e - half * (F * 4), h = r >> 2, c = r & 3;
+            hf[NG + j] = e < 2 * F * 4 ? (uint32_t)half : 0x40000000u;
+            src_off[NG + j] = h * CT_D + c * 4;
+            dst_off[NG + j] = L::X_OFF + (half * F + h) * 64 + ((c ^ ((h >> 1) & 3)) << 4);
+        }
+        auto issue = [&](int j2) {
+            const int s = j2 % CW_BST;
+            mbar_wait(&g_empty[s], ((j2 / CW_BST) & 1u) ^ 1u);
+            const uint32_t tile = smem_u32(st_base + (size_t)s * L::STAGE);
+            const long long bA = (long long)(kb0 + j2) * 2;
+#pragma unroll
+            for (int j = 0; j < NG + NX; ++j) {
+                const long long b = bA + hf[j];
+                const bool ok = b < p.B;
+                if (hf[j] < 2u) {
+                    const float* src = (j < NG ? p.g + (size_t)(ok ? b : 0) * p.ldg : p.x0 + (size_t)(ok ? b : 0) * p.ld0) + src_off[j];
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(tile + dst_off[j]), "l"(src), "r"(ok ? 16 : 0) : "memory");
+                }
+            }
+        };
+        for (int j = 0; j < CW_AHEAD; ++j) {
+            if (j < nkb) issue(j);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        for (int i = 0; i < nkb; ++i) {
+            asm volatile("cp.async.wait_group %0;" :: "n"(CW_AHEAD - 1) : "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&g_full[i % CW_BST]);
             if (i + CW_AHEAD < nkb) issue(i + CW_AHEAD);
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
@@ -930,7 +968,7 @@ cin_wgrad_tc_kernel(const __grid_constant__ CinWgParams p) {
         for (int i = 0; i < nkb; ++i) {
             const int s = i % CW_BST;
             const uint8_t* tile = st_base + (size_t)s * L::STAGE;
-            mbar_wait(&b_full[s], (i / CW_BST) & 1u);
+            mbar_wait(&g_full[s], (i / CW_BST) & 1u);
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt, ++ga) {
                 uint32_t hi[16], lo[16];
@@ -961,7 +999,7 @@ cin_wgrad_tc_kernel(const __grid_constant__ CinWgParams p) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_ready[o]);
             }
-            if (lane == 0) mbar_arrive(&b_empty[s]);                      // this warp has read the stage's G / X0 rows (syncwarp above)
+            if (lane == 0) mbar_arrive(&g_empty[s]);                      // this warp has read the stage's G / X0 rows (syncwarp above)
         }
         // ---------------- epilogue (first four operand warps): acc[mt] = a.b_raw | a.b_lo  ->  dW[u, h*M + m] += sum
         if (half == 0 && nkb > 0) {
@@ -992,7 +1030,7 @@ cin_wgrad_tc_kernel(const __grid_constant__ CinWgParams p) {
 
 template <int F, int M>
 static int cin_wgrad_tc_launch(const CinWgParams& p, cudaStream_t st) {
-    const size_t smem = (size_t)CW_BST * CwLayout<F, M>::STAGE + (2 * CW_BST + 2 * CW_OPN + 1) * 8 + 16 + 1024;
+    const size_t smem = (size_t)CW_BST * CwLayout<F, M>::STAGE + (4 * CW_BST + 2 * CW_OPN + 1) * 8 + 16 + 1024;
     cudaError_t e = cudaFuncSetAttribute(cin_wgrad_tc_kernel<F, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     cin_wgrad_tc_kernel<F, M><<<min(p.n_kb, 148), CW_THREADS, smem, st>>>(p);

@@ -318,7 +318,9 @@ gemm_tf32x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             if (trace) { g_tc_trace[1] = (unsigned long long)w_raw; g_tc_trace[10] = g; }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        // warp-uniform control flow, one elected lane issues (an `if (lane == 0)` region makes ptxas wrap every tcgen05
+        // instruction in a per-thread waterfall loop)
+        {
             const uint32_t idesc = make_idesc_tf32(TC_BLOCK_M, block_n);
             uint32_t g = 0, t = 0;
             long long w_ready = 0, w_acc = 0, w_issue = 0;
@@ -342,6 +344,7 @@ gemm_tf32x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     const uint32_t b_hi = b_resident ? smem_u32(bres_base + (size_t)kb * 2 * b_bytes)
                                                      : smem_u32(raw_base + (size_t)s * raw_bytes + TC_A_BYTES);
                     const uint32_t b_lo = b_hi + b_bytes;
+                    if (elect_one()) {
                     if (stack_n) {
                         const uint32_t ta_hi = tmem_base + a_col + (uint32_t)o * 64u, ta_lo = ta_hi + 32u;
                         const uint32_t idesc2 = make_idesc_tf32(TC_BLOCK_M, 2 * block_n);
@@ -374,11 +377,14 @@ gemm_tf32x3_v2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     }
                     umma_commit(&empty_op[o]);
                     if (!b_resident) umma_commit(&empty_raw[s]);
+                    }
+                    __syncwarp();
                     w_issue += TC_TRACE_T() - c2;
                 }
-                umma_commit(&tmem_full[acc]);
+                if (elect_one()) umma_commit(&tmem_full[acc]);
+                __syncwarp();
             }
-            if (trace) { g_tc_trace[2] = (unsigned long long)w_ready; g_tc_trace[3] = (unsigned long long)w_acc; g_tc_trace[4] = (unsigned long long)w_issue; }
+            if (trace && lane == 0) { g_tc_trace[2] = (unsigned long long)w_ready; g_tc_trace[3] = (unsigned long long)w_acc; g_tc_trace[4] = (unsigned long long)w_issue; }
         }
     } else if (warp < 6) {
         // ---------------- split warps: raw A -> (hi, lo) operand stage
@@ -743,28 +749,31 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // stack_n: [B hi ; B lo] (adjacent 32-float chunks, LBO apart) as ONE operand of 2*block_n columns — two MMAs per
-            // 8-sample group instead of three; accumulator columns [0, block_n) = a.b_hi, [block_n, 2*block_n) = a.b_lo.
-            const uint32_t idesc = make_idesc_tf32_mn(128, stack_n ? 2 * block_n : block_n);
-            long long w_ready = 0, w_issue = 0;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t ph = (uint32_t)((kb / kStages) & 1);
-                const long long c1 = TC_TRACE_T();
-                mbar_wait(&ready_bar[s], ph);
-                const long long c2 = TC_TRACE_T();
-                w_ready += c2 - c1;
-                tc_fence_after();
-                const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
+        // Warp-uniform control flow, one elected lane issues: inside an `if (lane == 0)` region ptxas wraps every tcgen05
+        // instruction in a per-thread waterfall loop (~14 instructions per MMA), which made this thread co-critical.
+        // stack_n: [B hi ; B lo] (adjacent 32-float chunks, LBO apart) as ONE operand of 2*block_n columns — two MMAs per
+        // 8-sample group instead of three; accumulator columns [0, block_n) = a.b_hi, [block_n, 2*block_n) = a.b_lo.
+        const uint32_t idesc = make_idesc_tf32_mn(128, stack_n ? 2 * block_n : block_n);
+        const uint64_t d0 = make_mnmajor_sw128_desc(smem_u32(smem));
+        long long w_ready = 0, w_issue = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % kStages;
+            const uint32_t ph = (uint32_t)((kb / kStages) & 1);
+            const long long c1 = TC_TRACE_T();
+            mbar_wait(&ready_bar[s], ph);
+            const long long c2 = TC_TRACE_T();
+            w_ready += c2 - c1;
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t a_hi = (uint32_t)(s * stage_bytes);             // byte offsets from the stage ring's base
                 const uint32_t a_lo = a_hi + a_bytes;
                 const uint32_t b_hi = a_hi + 2 * a_bytes;
                 const uint32_t b_lo = b_hi + b_bytes;
 #pragma unroll
                 for (int g = 0; g < WG_ROWS / TC_UMMA_K; ++g) {
                     const uint32_t koff = g * 1024;                         // one 8-sample K group
-                    const uint64_t da_hi = make_mnmajor_sw128_desc(a_hi + koff), da_lo = make_mnmajor_sw128_desc(a_lo + koff);
-                    const uint64_t db_hi = make_mnmajor_sw128_desc(b_hi + koff), db_lo = make_mnmajor_sw128_desc(b_lo + koff);
+                    const uint64_t da_hi = d0 + ((a_hi + koff) >> 4), da_lo = d0 + ((a_lo + koff) >> 4);
+                    const uint64_t db_hi = d0 + ((b_hi + koff) >> 4), db_lo = d0 + ((b_lo + koff) >> 4);
                     if (stack_n) {
                         umma_tf32(tmem_base, da_lo, db_hi, idesc, (kb > 0 || g > 0) ? 1u : 0u);
                         umma_tf32(tmem_base, da_hi, db_hi, idesc, 1u);
@@ -775,11 +784,13 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                     umma_tf32(tmem_base, da_hi, db_hi, idesc, 1u);
                 }
                 umma_commit(&empty_bar[s]);
-                w_issue += TC_TRACE_T() - c2;
             }
-            umma_commit(tmem_full_bar);
-            if (trace) { g_tc_trace[2] = (unsigned long long)w_ready; g_tc_trace[4] = (unsigned long long)w_issue; }
+            __syncwarp();
+            w_issue += TC_TRACE_T() - c2;
         }
+        if (elect_one()) umma_commit(tmem_full_bar);
+        __syncwarp();
+        if (trace && lane == 0) { g_tc_trace[2] = (unsigned long long)w_ready; g_tc_trace[4] = (unsigned long long)w_issue; }
     } else {
         const int t = threadIdx.x - 64;
         const int b_vec = b_bytes / 16;
