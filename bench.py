@@ -324,15 +324,17 @@ def run_ours(args, w):
         cbs.append(cb)
     use_graph = not args.eager
     launch_mode = 'cuda_graph' if use_graph else 'eager'
+    # one GPU: the step opens with zero_grad (where the reference's loop has it), its sparse re-zero running next to the forward
+    # kernel; N > 1: the sharded gradient tables are cleaned lazily by the next backward (ops.sharded_clean), step order unchanged
+    zero_first = bool(args.zero_first) and world == 1
     try:
-        for cb in cbs:
-            steps_g.append(GraphedStep(model, cb, post=post, use_graph=use_graph, loss_scale=loss_scale))
+        steps_g = GraphedStep.ring(model, cbs, post=post, use_graph=use_graph, loss_scale=loss_scale, zero_first=zero_first)
     except Exception as e:      # capture not possible: time the eager path instead (still the same kernels)
         if rank == 0:
             print(f'[bench] CUDA-graph capture failed ({e!r}); falling back to eager launches', file=sys.stderr)
         launch_mode = 'eager'
         torch.cuda.synchronize()
-        steps_g = [GraphedStep(model, cb, post=post, use_graph=False, loss_scale=loss_scale) for cb in cbs]
+        steps_g = GraphedStep.ring(model, cbs, post=post, use_graph=False, loss_scale=loss_scale, zero_first=zero_first)
     ops.check_index_errors(dev)
     launches_per_step = steps_g[0].launches_per_step
 
@@ -363,12 +365,21 @@ def run_ours(args, w):
     # ---------------- timed region: K steps, inputs resident in HBM, rotating over NB batches (tables >> L2).  N > 1: the
     # window is repeated (NVLink contention makes a single 10-30 ms window noisy) and the MEDIAN window is reported.
     repeats = args.repeats if args.repeats > 0 else (1 if world == 1 else 5)
+    # the steps are replayed strictly in ring order (with zero_first step j re-zeroes what step j-1 touched)
+    ring = {'pos': 0}
+
+    def step_next():
+        j = ring['pos']
+        steps_g[j].replay()
+        ring['pos'] = (j + 1) % NB
+        return j
+
     for i in range(args.warmup):
-        steps_g[i % NB].replay()
+        step_next()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    windows = [timed_window(lambda i: steps_g[i % NB].replay(), args.steps) for _ in range(repeats)]
+    windows = [timed_window(lambda i: step_next(), args.steps) for _ in range(repeats)]
     clocks = sampler.stop()
     ms = _median(windows)
     value = world * B * args.steps / (ms * 1e-3)
@@ -376,7 +387,7 @@ def run_ours(args, w):
     # ---------------- e2e: every step's inputs start in pinned HOST memory: H2D (3 copies) -> step -> D2H read of the loss.
     # Double-buffered: the copy of batch i+1 runs on a copy stream while batch i computes (each batch is still copied
     # exactly once per step inside the timed region).
-    for cb in cbs[:2]:
+    for cb in cbs:
         if cb.h_idx is None:
             cb.h_idx = torch.zeros_like(cb.idx, device='cpu').pin_memory()
             cb.h_dns = torch.zeros_like(cb.dns, device='cpu').pin_memory()
@@ -386,8 +397,8 @@ def run_ours(args, w):
         cb.h_lab.copy_(cb.lab)
     main_stream = torch.cuda.current_stream()
     copy_stream = torch.cuda.Stream()
-    ev_copied = [torch.cuda.Event(), torch.cuda.Event()]
-    ev_done = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_copied = [torch.cuda.Event() for _ in range(NB)]
+    ev_done = [torch.cuda.Event() for _ in range(NB)]
     loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()          # D2H landing zone of the per-step loss
     ev_loss = [torch.cuda.Event(), torch.cuda.Event()]
     e2e_state = {'h2d': 0, 'loss': 0.0}
@@ -396,25 +407,27 @@ def run_ours(args, w):
         """Every step: H2D of its batch from pinned memory (3 copies), the graph replay, and a D2H copy of its loss that the
         host reads.  The loss of step i is read while step i+1 runs (async metrics: the copy is queued right behind the
         step, the host waits for its event one iteration later), so the device never idles on a host round trip; the last
-        loss is read before the timed region closes."""
+        loss is read before the timed region closes.  Batches follow the ring order of the steps."""
+        main_stream.synchronize()
         with torch.cuda.stream(copy_stream):
-            e2e_state['h2d'] = cbs[0].h2d()
-            ev_copied[0].record(copy_stream)
+            e2e_state['h2d'] = cbs[ring['pos']].h2d()
+            ev_copied[ring['pos']].record(copy_stream)
         for i in range(n):
-            cur, nxt = i % 2, (i + 1) % 2
-            if i >= 1:
-                copy_stream.wait_event(ev_done[nxt])            # buffer `nxt` was last read by step i-1
+            cur = ring['pos']
+            nxt = (cur + 1) % NB
+            copy_stream.wait_event(ev_done[nxt])                # buffer `nxt` was last read NB-1 steps ago (no-op before its first use)
             with torch.cuda.stream(copy_stream):
                 cbs[nxt].h2d()
                 ev_copied[nxt].record(copy_stream)
             main_stream.wait_event(ev_copied[cur])
-            steps_g[cur].replay()
+            step_next()
             ev_done[cur].record(main_stream)
-            loss_host[cur:cur + 1].copy_(steps_g[cur].loss.reshape(1), non_blocking=True)     # D2H of this step's result
-            ev_loss[cur].record(main_stream)
+            lh = i % 2
+            loss_host[lh:lh + 1].copy_(steps_g[cur].loss.reshape(1), non_blocking=True)       # D2H of this step's result
+            ev_loss[lh].record(main_stream)
             if i >= 1:
-                ev_loss[nxt].synchronize()                       # loss of step i-1 has landed
-                e2e_state['loss'] = float(loss_host[nxt])
+                ev_loss[1 - lh].synchronize()                    # loss of step i-1 has landed
+                e2e_state['loss'] = float(loss_host[1 - lh])
         ev_loss[(n - 1) % 2].synchronize()
         e2e_state['loss'] = float(loss_host[(n - 1) % 2])
 
@@ -428,6 +441,14 @@ def run_ours(args, w):
         barrier()
         e2e_windows.append(max_over_ranks(e0.elapsed_time(e1)))
     ms_e2e = _median(e2e_windows)
+    # leave the ring at its start: the last step replayed is the last one captured, so the host-side list of touched rows
+    # matches the device again and a plain zero_grad() cleans exactly what is dirty before the secondary legs run
+    while ring['pos'] != 0:
+        step_next()
+    torch.cuda.synchronize()
+    if zero_first:
+        model.zero_grad(set_to_none=True)
+        torch.cuda.synchronize()
     e2e = {'value': world * B * args.steps / (ms_e2e * 1e-3), 'unit': 'samples/s', 'h2d_bytes_per_step': e2e_state['h2d'],
            'd2h_bytes_per_step': 4, 'loss': e2e_state['loss'], 'ms_per_step': ms_e2e / args.steps,
            'overlap': 'H2D of batch i+1 on a copy stream during step i; loss of step i read by the host during step i+1'}
@@ -442,6 +463,8 @@ def run_ours(args, w):
                 'CUDA events, barrier + synchronize on both sides, max over ranks',
                 'gemm': {0: 'auto(tcgen05 3xTF32)', 1: 'simt fp32', 2: 'tcgen05 3xTF32'}[ops.get_gemm_impl()],
                 'grad_mode': 'persistent' if world == 1 else 'sharded',
+                'zero_grad': ('opens the step (side stream, 148 x 128-thread blocks next to the forward kernel), joined before backward'
+                              if zero_first else 'closes the step'),
                 'sharded_fused_core': bool(ops.SHARDED_FUSED) if world > 1 else None,
                 'tables_per_gpu_bytes': sum(p.numel() * 4 for n, p in model.named_parameters() if 'embedding_layer' in n)},
         'e2e': e2e, 'gpu_launches': launches_per_step * args.steps, 'clocks': clocks, 'roofline': None,
@@ -765,6 +788,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='deepfm', choices=sorted(WORKLOADS))
     ap.add_argument('--repeats', type=int, default=0, help='timed windows of `steps` steps (median reported); 0 = 1 at N=1, 5 at N>1')
+    ap.add_argument('--zero-first', type=int, default=0, help='1 GPU: 1 = the step opens with zero_grad on a side stream next to the forward kernel (measured slower: the two kernels do not share an SM, profiles/r02_zero_first.md); 0 = zero_grad closes the step')
     ap.add_argument('--eager', action='store_true', help='time eager launches instead of CUDA-graph replays')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-train-step', action='store_true', help='skip the secondary forward+backward+optimizer timings')

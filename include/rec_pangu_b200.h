@@ -275,6 +275,17 @@ int rpb_cin_fwd(const float* e, int64_t lde, int B, int F, int D, int L, const i
 int rpb_cin_bwd(const float* e, int64_t lde, int B, int F, int D, int L, const int32_t* units,
                 const float* const* W, const float* const* bias, const float* dpooled, int64_t lddp,
                 float* de, int64_t ldde, int accumulate, float* const* dW, float* const* db, void* stream);
+/* Training variants (tensor-core shapes only: F = 26, D = 16, U_k = 16; RPB_ERR_UNSUPPORTED otherwise — fall back to the pair
+ * above): the forward keeps X_1 .. X_{L-1} in xsave [B, ldx] (layer k+1 at column (U_0 + .. + U_{k-1}) * D, ldx >= that sum over
+ * the first L-1 layers, 16-byte aligned) — what autograd keeps alive in the reference (interaction.py:160-168) — and the
+ * backward reads them instead of recomputing the forward. */
+int rpb_cin_fwd_save(const float* e, int64_t lde, int B, int F, int D, int L, const int32_t* units,
+                     const float* const* W, const float* const* bias, float* pooled, int64_t ldp,
+                     float* xsave, int64_t ldx, void* stream);
+int rpb_cin_bwd_saved(const float* e, int64_t lde, int B, int F, int D, int L, const int32_t* units,
+                      const float* const* W, const float* const* bias, const float* dpooled, int64_t lddp,
+                      float* de, int64_t ldde, int accumulate, float* const* dW, float* const* db,
+                      const float* xsaved, int64_t ldx, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * AutoInt interacting-layer core (models/layers/attention.py:12-32,63-95) on projected inputs.

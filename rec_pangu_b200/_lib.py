@@ -99,6 +99,10 @@ SIGNATURES = {
                               C.POINTER(_vp), _vp, _i64, _vp]),
     'rpb_cin_bwd': (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_i32), C.POINTER(_vp),
                               C.POINTER(_vp), _vp, _i64, _vp, _i64, C.c_int, C.POINTER(_vp), C.POINTER(_vp), _vp]),
+    'rpb_cin_fwd_save': (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_i32), C.POINTER(_vp),
+                                   C.POINTER(_vp), _vp, _i64, _vp, _i64, _vp]),
+    'rpb_cin_bwd_saved': (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_i32), C.POINTER(_vp),
+                                    C.POINTER(_vp), _vp, _i64, _vp, _i64, C.c_int, C.POINTER(_vp), C.POINTER(_vp), _vp, _i64, _vp]),
     'rpb_matmul_kn_fwd': (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     'rpb_matmul_kn_bwd': (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, C.c_int, C.c_int, C.c_int,
                                     C.c_int, _vp]),

@@ -20,6 +20,7 @@ int g_fused_ring = 0;
 int g_fused_tc_tail = 1;    // tower-tail layers of the one-kernel forward on tcgen05 (0 = fp32 CUDA-core tail)
 int g_tower_bwd_tc = 0;     // opt-in until measured on hardware
 int g_cin_tc = 1;
+int g_rows_zero_blocks = 0;
 int g_autoint_vec = 1;      // float4 lane I/O: bit-identical, 3.60 -> 3.18 ms per config-4 step (BENCH_r01 experiments.safe.autoint_vec)
 int g_l2_persist = 0;       // opt-in until measured on hardware
 size_t g_l2_aside = 0, g_l2_max_window = 0;
@@ -91,6 +92,7 @@ RPB_API int rpb_set_option(const char* name, int64_t value) {
         rpb::g_l2_persist = value != 0;
         return 0;
     }
+    if (n == "rows_zero_blocks") { if (value < 0 || value > 65535) return RPB_ERR_BAD_ARG; rpb::g_rows_zero_blocks = (int)value; return 0; }
     if (n == "cin_tc") { if (value < 0 || value > 2) return RPB_ERR_BAD_ARG; rpb::g_cin_tc = (int)value; return 0; }
     if (n == "autoint_vec") { rpb::g_autoint_vec = value != 0; return 0; }
     if (n == "tower_bwd_tc") { rpb::g_tower_bwd_tc = value != 0; return 0; }

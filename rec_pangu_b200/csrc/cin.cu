@@ -382,28 +382,34 @@ int cin_layer_wgrad_tc(int F, int M, const float* x0, long long ld0, const float
                        float* dW, int B, cudaStream_t st);
 }
 
-RPB_API int rpb_cin_fwd(const float* e, int64_t lde, int B, int F, int D, int L, const int32_t* units,
-                        const float* const* W, const float* const* bias, float* pooled, int64_t ldp, void* stream) {
+static int cin_fwd_impl(const float* e, int64_t lde, int B, int F, int D, int L, const int32_t* units,
+                        const float* const* W, const float* const* bias, float* pooled, int64_t ldp, float* xsave, int64_t ldx, void* stream) {
     if (e == nullptr || pooled == nullptr || W == nullptr || bias == nullptr || B <= 0) return RPB_ERR_BAD_ARG;
     CinHost h = cin_meta(F, L, units);
     if (!h.ok) return RPB_ERR_UNSUPPORTED;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (cin_tc_shape_ok(F, D, L, units)) {
-        // tensor-core path (cin_tc.cu): one launch per layer, X_{k+1} [B, U, D] ping-pongs through workspace slot 3
+        // tensor-core path (cin_tc.cu): one launch per layer; X_{k+1} [B, U, D] ping-pongs through workspace slot 3, or goes to
+        // the caller's xsave ([B, ldx], layer k at column p_off[k] * D: the layout the backward kernels read) when training
         int werr = 0;
         const size_t per = (size_t)B * units[0] * D;
-        float* xs = L > 1 ? static_cast<float*>(workspace(3, 2 * per * sizeof(float), &werr)) : nullptr;
-        if (L > 1 && xs == nullptr) return werr;
+        float* xs = (L > 1 && xsave == nullptr) ? static_cast<float*>(workspace(3, 2 * per * sizeof(float), &werr)) : nullptr;
+        if (L > 1 && xsave == nullptr && xs == nullptr) return werr;
         const float* xk = e; long long ldk = lde;
         for (int k = 0; k < L; ++k) {
-            float* xout = k + 1 < L ? xs + (size_t)(k & 1) * per : nullptr;
-            const int rc = cin_layer_fwd_tc(F, h.meta.M[k], units[k], D, W[k], bias[k], e, lde, xk, ldk, xout, (long long)units[k] * D,
+            float* xout = nullptr; long long ldo = (long long)units[k] * D;
+            if (k + 1 < L) {
+                if (xsave != nullptr) { xout = xsave + (size_t)h.meta.p_off[k] * D; ldo = ldx; }
+                else xout = xs + (size_t)(k & 1) * per;
+            }
+            const int rc = cin_layer_fwd_tc(F, h.meta.M[k], units[k], D, W[k], bias[k], e, lde, xk, ldk, xout, ldo,
                                             pooled + h.meta.p_off[k], ldp, B, st);
             if (rc != 0) return rc;
-            xk = xout; ldk = (long long)units[k] * D;
+            xk = xout; ldk = ldo;
         }
         return 0;
     }
+    if (xsave != nullptr) return RPB_ERR_UNSUPPORTED;                      // only the tensor-core path keeps X_k
     int maxu = 0;
     for (int k = 0; k < L; ++k) maxu = max(maxu, units[k]);
     float *Wt = nullptr, *bcat = nullptr;
@@ -427,9 +433,25 @@ RPB_API int rpb_cin_fwd(const float* e, int64_t lde, int B, int F, int D, int L,
     return rc;
 }
 
-RPB_API int rpb_cin_bwd(const float* e, int64_t lde, int B, int F, int D, int L, const int32_t* units,
+RPB_API int rpb_cin_fwd(const float* e, int64_t lde, int B, int F, int D, int L, const int32_t* units,
+                        const float* const* W, const float* const* bias, float* pooled, int64_t ldp, void* stream) {
+    return cin_fwd_impl(e, lde, B, F, D, L, units, W, bias, pooled, ldp, nullptr, 0, stream);
+}
+
+RPB_API int rpb_cin_fwd_save(const float* e, int64_t lde, int B, int F, int D, int L, const int32_t* units,
+                             const float* const* W, const float* const* bias, float* pooled, int64_t ldp,
+                             float* xsave, int64_t ldx, void* stream) {
+    if (xsave == nullptr || L < 2) return RPB_ERR_BAD_ARG;
+    int64_t need = 0;
+    for (int k = 0; k + 1 < L; ++k) need += (int64_t)units[k] * D;
+    if (ldx < need || (ldx & 3) || (reinterpret_cast<uintptr_t>(xsave) & 15u)) return RPB_ERR_BAD_ARG;
+    return cin_fwd_impl(e, lde, B, F, D, L, units, W, bias, pooled, ldp, xsave, ldx, stream);
+}
+
+static int cin_bwd_impl(const float* e, int64_t lde, int B, int F, int D, int L, const int32_t* units,
                         const float* const* W, const float* const* bias, const float* dpooled, int64_t lddp,
-                        float* de, int64_t ldde, int accumulate, float* const* dW, float* const* db, void* stream) {
+                        float* de, int64_t ldde, int accumulate, float* const* dW, float* const* db,
+                        const float* xsaved, int64_t ldx, void* stream) {
     if (e == nullptr || dpooled == nullptr || de == nullptr || W == nullptr || dW == nullptr || B <= 0) return RPB_ERR_BAD_ARG;
     CinHost h = cin_meta(F, L, units);
     if (!h.ok) return RPB_ERR_UNSUPPORTED;
@@ -457,14 +479,18 @@ RPB_API int rpb_cin_bwd(const float* e, int64_t lde, int B, int F, int D, int L,
         float* dxb = static_cast<float*>(workspace(3, 2 * (size_t)B * units[0] * D * sizeof(float), &werr));
         if (dxb == nullptr) return werr;
         const size_t dper = (size_t)B * units[0] * D;
-        for (int k = 0; k + 1 < L; ++k) {
-            rc = cin_layer_fwd_tc(F, h.meta.M[k], units[k], D, W[k], bias ? bias[k] : nullptr, e, lde,
-                                  k == 0 ? e : Xout + (size_t)h.meta.p_off[k - 1] * D, k == 0 ? lde : ldu,
-                                  Xout + (size_t)h.meta.p_off[k] * D, ldu, nullptr, 0, B, st);
-            if (rc != 0) return rc;
+        const float* Xs = Xout; long long ldxs = ldu;                      // X_1 .. X_{L-1}: recomputed here, or kept by the forward
+        if (xsaved != nullptr) { Xs = xsaved; ldxs = ldx; }
+        else {
+            for (int k = 0; k + 1 < L; ++k) {
+                rc = cin_layer_fwd_tc(F, h.meta.M[k], units[k], D, W[k], bias ? bias[k] : nullptr, e, lde,
+                                      k == 0 ? e : Xout + (size_t)h.meta.p_off[k - 1] * D, k == 0 ? lde : ldu,
+                                      Xout + (size_t)h.meta.p_off[k] * D, ldu, nullptr, 0, B, st);
+                if (rc != 0) return rc;
+            }
         }
         for (int k = L - 1; k >= 0; --k) {
-            rc = cin_layer_bwd_tc_c(F, h.meta.M[k], W[k], e, lde, k == 0 ? e : Xout + (size_t)h.meta.p_off[k - 1] * D, k == 0 ? lde : ldu,
+            rc = cin_layer_bwd_tc_c(F, h.meta.M[k], W[k], e, lde, k == 0 ? e : Xs + (size_t)h.meta.p_off[k - 1] * D, k == 0 ? lde : ldxs,
                                     dpooled + h.meta.p_off[k], lddp, k == L - 1 ? nullptr : dxb + (size_t)((k + 1) & 1) * dper,
                                     (long long)units[k] * D, Gout + (size_t)h.meta.p_off[k] * D, ldu, db ? db[k] : nullptr,
                                     k > 0 ? dxb + (size_t)(k & 1) * dper : nullptr, (long long)h.meta.M[k] * D, de, ldde,
@@ -473,12 +499,13 @@ RPB_API int rpb_cin_bwd(const float* e, int64_t lde, int B, int F, int D, int L,
         }
         // weight gradients: dW_k = P^T . X_k over the rows (b, d), P = G_k x X_0 formed in registers (cin_wgrad_tc_kernel)
         for (int k = 0; k < L; ++k) {
-            rc = cin_layer_wgrad_tc(F, h.meta.M[k], e, lde, k == 0 ? e : Xout + (size_t)h.meta.p_off[k - 1] * D, k == 0 ? lde : ldu,
+            rc = cin_layer_wgrad_tc(F, h.meta.M[k], e, lde, k == 0 ? e : Xs + (size_t)h.meta.p_off[k - 1] * D, k == 0 ? lde : ldxs,
                                     Gout + (size_t)h.meta.p_off[k] * D, ldu, dW[k], B, st);
             if (rc != 0) return rc;
         }
         return 0;
     }
+    if (xsaved != nullptr) return RPB_ERR_UNSUPPORTED;
     rc = cin_dispatch(D, maxu, [&](auto dt, auto ut) -> int {
         constexpr int DD = decltype(dt)::value, MU = decltype(ut)::value;
         constexpr int SPC = 256 / DD;
@@ -513,4 +540,18 @@ RPB_API int rpb_cin_bwd(const float* e, int64_t lde, int B, int F, int D, int L,
         return launch(std::integral_constant<int, 4>{});
     });
     return rc;
+}
+
+RPB_API int rpb_cin_bwd(const float* e, int64_t lde, int B, int F, int D, int L, const int32_t* units,
+                        const float* const* W, const float* const* bias, const float* dpooled, int64_t lddp,
+                        float* de, int64_t ldde, int accumulate, float* const* dW, float* const* db, void* stream) {
+    return cin_bwd_impl(e, lde, B, F, D, L, units, W, bias, dpooled, lddp, de, ldde, accumulate, dW, db, nullptr, 0, stream);
+}
+
+RPB_API int rpb_cin_bwd_saved(const float* e, int64_t lde, int B, int F, int D, int L, const int32_t* units,
+                              const float* const* W, const float* const* bias, const float* dpooled, int64_t lddp,
+                              float* de, int64_t ldde, int accumulate, float* const* dW, float* const* db,
+                              const float* xsaved, int64_t ldx, void* stream) {
+    if (xsaved == nullptr) return RPB_ERR_BAD_ARG;
+    return cin_bwd_impl(e, lde, B, F, D, L, units, W, bias, dpooled, lddp, de, ldde, accumulate, dW, db, xsaved, ldx, stream);
 }

@@ -439,14 +439,43 @@ cin_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_const
 #pragma unroll
             for (int u = 0; u < CT_U; ++u) out[u] = bv[u];
             CinTTiles<F, NT, NTILES, 0>::run(tmem_base + ACC0 + lane_addr, acc_full, acc_empty, n_acc, lane, x0, out);
+            if (valid && p.xout != nullptr) {
+                float* xo = p.xout + (size_t)b * p.ldo + d;
 #pragma unroll
-            for (int u = 0; u < CT_U; ++u) {
-                const float v = out[u];
-                if (valid && p.xout != nullptr) p.xout[(size_t)b * p.ldo + u * CT_D + d] = v;
-                if (p.pooled != nullptr) {
-                    const float s = group_sum<CT_D>(v);
-                    if (valid && d == 0) p.pooled[(size_t)b * p.ldp + u] = s;
+                for (int u = 0; u < CT_U; ++u) xo[u * CT_D] = out[u];
+            }
+            if (p.pooled != nullptr) {
+                // sums over the 16 lanes (d) of a sample for all 16 units at once: recursive halving, 8 + 4 + 2 + 1 shuffles instead
+                // of 16 four-step butterflies; lane d ends up with the total of unit u = d -> one 64-byte store per sample
+                float r8[8], r4[4], r2[2];
+                {
+                    const bool up = (d & 8) != 0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float recv = __shfl_xor_sync(0xffffffffu, up ? out[i] : out[i + 8], 8);
+                        r8[i] = (up ? out[i + 8] : out[i]) + recv;
+                    }
                 }
+                {
+                    const bool up = (d & 4) != 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float recv = __shfl_xor_sync(0xffffffffu, up ? r8[i] : r8[i + 4], 4);
+                        r4[i] = (up ? r8[i + 4] : r8[i]) + recv;
+                    }
+                }
+                {
+                    const bool up = (d & 2) != 0;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const float recv = __shfl_xor_sync(0xffffffffu, up ? r4[i] : r4[i + 2], 2);
+                        r2[i] = (up ? r4[i + 2] : r4[i]) + recv;
+                    }
+                }
+                const bool up = (d & 1) != 0;
+                const float recv = __shfl_xor_sync(0xffffffffu, up ? r2[0] : r2[1], 1);
+                const float tot = (up ? r2[1] : r2[0]) + recv;
+                if (valid) p.pooled[(size_t)b * p.ldp + d] = tot;
             }
         }
     }

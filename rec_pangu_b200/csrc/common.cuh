@@ -31,6 +31,7 @@ extern int g_fused_gather_warps;                     // api.cu: 8 = one-kernel D
 extern int g_fused_fetch_warps;                      // api.cu: 4 = one-kernel DeepFM forward with dedicated fetch warps (default), 0 = every gather warp fetches its own rows
 extern int g_fused_ring;                             // api.cu: gather ring depth of the 8-warp forward (0 = deepest that fits)
 extern int g_tower_bwd_tc;                           // api.cu: 1 = tower-tail backward runs its dz chain on tcgen05 (tower_tc.cu)
+extern int g_rows_zero_blocks;                      // api.cu: > 0 = sparse re-zero launched as that many 128-thread blocks (co-resident with the forward kernel)
 extern int g_cin_tc;                                 // api.cu: 1 = CIN layers on tcgen05 (cin_tc.cu) where the shape is instantiated
 extern int g_autoint_vec;                            // api.cu: 1 = AutoInt attention kernels move a lane's outputs as float4 (autoint.cu, VEC)
 extern int g_l2_persist;                             // api.cu: 1 = launches that write / re-read the feature row x carry an L2 persisting access-policy window on it

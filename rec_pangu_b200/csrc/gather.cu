@@ -345,20 +345,31 @@ gather_bwd_kernel(const __grid_constant__ ScatterParams p) {
 template <int VEC, int LPR>
 __global__ void __launch_bounds__(256)
 rows_zero_kernel(const __grid_constant__ ScatterParams p) {
-    const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = (int)(gt / LPR), l = (int)(gt % LPR);
-    if (b >= p.B) return;
-    const bool lane_on = l < p.D / VEC;
+    // grid-stride: the default launch covers every (sample, lane) once; the co-resident launch (option rows_zero_blocks: a few
+    // 128-thread blocks per SM, 24 registers) is sized to fit NEXT TO the one-CTA-per-SM forward kernel it overlaps with
+    const long long total = (long long)p.B * LPR, stride = (long long)gridDim.x * blockDim.x;
     Vec<VEC> z;
     z.zero();
-    for (int f = 0; f < p.F; ++f) {
-        long long v = __ldg(p.idx[f] + b);
-        if ((unsigned long long)v >= (unsigned long long)p.rows[f]) v = 0;
-        if (lane_on) {
-            float* gr = grad_row(p, f, v, p.D);
-            if (gr != nullptr) z.store(gr + l * VEC);
+    for (long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x; gt < total; gt += stride) {
+        const int b = (int)(gt / LPR), l = (int)(gt % LPR);
+        const bool lane_on = l < p.D / VEC;
+        for (int f0 = 0; f0 < p.F; f0 += 8) {                             // eight index loads in flight, then their stores
+            long long v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = f0 + j < p.F ? __ldg(p.idx[f0 + j] + b) : 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int f = f0 + j;
+                if (f < p.F) {
+                    if ((unsigned long long)v[j] >= (unsigned long long)p.rows[f]) v[j] = 0;
+                    if (lane_on) {
+                        float* gr = grad_row(p, f, v[j], p.D);
+                        if (gr != nullptr) z.store(gr + l * VEC);
+                    }
+                    if ((f % LPR) == l && p.lr_grads[f] != nullptr) p.lr_grads[f][v[j]] = 0.f;
+                }
+            }
         }
-        if ((f % LPR) == l && p.lr_grads[f] != nullptr) p.lr_grads[f][v] = 0.f;
     }
 }
 
@@ -563,7 +574,12 @@ RPB_API int rpb_rows_zero(const RpbScatterDesc* d, void* stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     return dispatch_shape(d->D, aligned, [&](auto vec, auto lpr) -> int {
         constexpr int VEC = decltype(vec)::value, LPR = decltype(lpr)::value;
-        rows_zero_kernel<VEC, LPR><<<ceil_div((long long)p.B * LPR, 256), 256, 0, st>>>(p);
+        if (g_rows_zero_blocks > 0) {
+            // same L1 / shared-memory split as the forward kernel it is meant to run next to (an SM is not re-configured while busy)
+            cudaFuncSetAttribute(rows_zero_kernel<VEC, LPR>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            rows_zero_kernel<VEC, LPR><<<g_rows_zero_blocks, 128, 0, st>>>(p);
+        }
+        else rows_zero_kernel<VEC, LPR><<<ceil_div((long long)p.B * LPR, 256), 256, 0, st>>>(p);
         RPB_LAUNCH_CHECK();
         return 0;
     });

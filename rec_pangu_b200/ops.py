@@ -1402,6 +1402,10 @@ def crossnet(x0: torch.Tensor, K: int, weights, biases) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------ xDeepFM CIN
+# 1: the CIN forward keeps X_1..X_{L-1} for backward when the tensor-core kernels take the shape (RPB_CIN_SAVE_X=0: recompute)
+CIN_SAVE_X = int(os.environ.get('RPB_CIN_SAVE_X', '1'))
+
+
 class _CIN(torch.autograd.Function):
     @staticmethod
     def forward(ctx, e, L, *params):                # params = W_0..W_{L-1} ([U,Cin,1]), b_0..b_{L-1}
@@ -1411,16 +1415,38 @@ class _CIN(torch.autograd.Function):
         tot = sum(units)
         pooled = torch.empty((B, tot), dtype=torch.float32, device=e.device)
         u_arr = (C.c_int32 * L)(*units)
-        check(_lib.load().rpb_cin_fwd(_ptr(e), e.stride(0), B, F, D, L, u_arr, _ptr_array(Ws), _ptr_array(bs),
-                                      _ptr(pooled), tot, _stream()), 'rpb_cin_fwd')
+        # training: keep X_1 .. X_{L-1} (what autograd keeps in the reference) so that backward does not recompute the forward —
+        # tensor-core shapes only; RPB_ERR_UNSUPPORTED means "use the recomputing pair"
+        xsave = None
+        needs_grad = any(ctx.needs_input_grad)           # (grad mode is off inside Function.forward: ask the context)
+        if needs_grad and L > 1 and CIN_SAVE_X:
+            ldx = (tot - units[-1]) * D
+            xsave = torch.empty((B, ldx), dtype=torch.float32, device=e.device)
+            rc = _lib.load().rpb_cin_fwd_save(_ptr(e), e.stride(0), B, F, D, L, u_arr, _ptr_array(Ws), _ptr_array(bs),
+                                              _ptr(pooled), tot, _ptr(xsave), ldx, _stream())
+            if rc == _lib.ERR_UNSUPPORTED:
+                xsave = None
+            else:
+                check(rc, 'rpb_cin_fwd_save')
+        if xsave is None:
+            check(_lib.load().rpb_cin_fwd(_ptr(e), e.stride(0), B, F, D, L, u_arr, _ptr_array(Ws), _ptr_array(bs),
+                                          _ptr(pooled), tot, _stream()), 'rpb_cin_fwd')
         _count(2)
         ctx.L, ctx.units = L, units
-        ctx.save_for_backward(e, *params)
+        ctx.has_x = xsave is not None
+        if xsave is not None:
+            ctx.save_for_backward(e, xsave, *params)
+        else:
+            ctx.save_for_backward(e, *params)
         return pooled
 
     @staticmethod
     def backward(ctx, g):
-        e, *params = ctx.saved_tensors
+        if ctx.has_x:
+            e, xsave, *params = ctx.saved_tensors
+        else:
+            e, *params = ctx.saved_tensors
+            xsave = None
         L, units = ctx.L, ctx.units
         Ws, bs = params[:L], params[L:]
         B, F, D = e.shape
@@ -1429,9 +1455,14 @@ class _CIN(torch.autograd.Function):
         dWs = [torch.zeros_like(w) for w in Ws]
         dbs = [torch.zeros_like(b) for b in bs]
         u_arr = (C.c_int32 * L)(*units)
-        check(_lib.load().rpb_cin_bwd(_ptr(e), e.stride(0), B, F, D, L, u_arr, _ptr_array(Ws), _ptr_array(bs), _ptr(g),
-                                      g.stride(0), _ptr(de), F * D, 0, _ptr_array(dWs), _ptr_array(dbs), _stream()),
-              'rpb_cin_bwd')
+        if xsave is not None:
+            check(_lib.load().rpb_cin_bwd_saved(_ptr(e), e.stride(0), B, F, D, L, u_arr, _ptr_array(Ws), _ptr_array(bs), _ptr(g),
+                                                g.stride(0), _ptr(de), F * D, 0, _ptr_array(dWs), _ptr_array(dbs),
+                                                _ptr(xsave), xsave.stride(0), _stream()), 'rpb_cin_bwd_saved')
+        else:
+            check(_lib.load().rpb_cin_bwd(_ptr(e), e.stride(0), B, F, D, L, u_arr, _ptr_array(Ws), _ptr_array(bs), _ptr(g),
+                                          g.stride(0), _ptr(de), F * D, 0, _ptr_array(dWs), _ptr_array(dbs), _stream()),
+                  'rpb_cin_bwd')
         _count(3)
         return (de, None, *dWs, *dbs)
 

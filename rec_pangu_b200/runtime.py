@@ -63,37 +63,50 @@ class GraphedStep:
     zero_grad.  ``replay()`` re-launches the whole step with one cudaGraphLaunch; ``loss`` / ``pred`` are the static
     output tensors.
 
-    ``zero_first`` (experimental, not yet measured): the same K steps with the loop boundary moved — every step starts with
-    the `model.zero_grad()` of the step before it, issued on a side stream so that the sparse re-zero of the table
-    gradients (random 64-byte stores, DRAM-bound) overlaps the forward kernel (shared-memory-pipe-bound) and is joined
-    before backward; the gradients of the last step stay in `.grad` after a replay."""
+    ``zero_first``: the same K steps with the loop boundary where the reference's loop has it (`optimizer.zero_grad()` opens
+    the iteration, model_pipeline.py:44): every step starts with the `model.zero_grad()` of the step before it, issued on a
+    side stream AFTER the forward kernel has been launched and as a few small blocks per SM (`rows_zero_blocks`), so that the
+    sparse re-zero of the table gradients (random 64-byte stores, DRAM-bound) runs next to the one-CTA-per-SM forward kernel
+    (latency-bound, 20 % of the HBM roofline) instead of after backward; joined before backward.  The gradients of the last
+    step stay in `.grad` after a replay."""
 
     _zero_streams = {}
 
     def __init__(self, model: torch.nn.Module, batch: ColumnarBatch, post: Optional[Callable[[], None]] = None,
-                 warmup: int = 3, use_graph: bool = True, loss_scale: float = 1.0, zero_first: bool = False):
+                 warmup: int = 3, use_graph: bool = True, loss_scale: float = 1.0, zero_first: bool = False,
+                 zero_blocks: int = 148, defer_capture: bool = False):
         self.model, self.batch, self.post = model, batch, post
         self.zero_first = zero_first
+        self.zero_blocks = int(zero_blocks)
         self.loss_scale = loss_scale           # data parallel: back-propagate loss / world (dist.DenseGradBucket)
         self.data = batch.as_dict()
         self.graph = None
         self.loss = self.pred = None
+        self.grads = None
         self.launches_per_step = 0
         from . import ops
         self._advance_epoch = False
+        self._use_graph = use_graph
         d0 = ops.dropout_calls()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(warmup):
-                self._eager()
+                self._eager(zero_first=False)
         # a step that draws dropout masks starts by advancing the device-side epoch the kernels mix into their seeds: the
         # host-drawn seeds are frozen by the capture, the epoch is not (same trick as FusedAdam's device step counter)
         self._advance_epoch = ops.dropout_calls() > d0
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        if not defer_capture:
+            if zero_first:
+                raise ValueError('zero_first steps re-zero what the step BEFORE them touched: build them with GraphedStep.ring()')
+            self._capture()
+
+    def _capture(self):
+        from . import ops
         n0 = ops.launch_count()
-        if use_graph:
+        if self._use_graph:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._eager()
@@ -102,12 +115,32 @@ class GraphedStep:
             self._eager()
         self.launches_per_step = ops.launch_count() - n0
 
-    def _eager(self):
+    @classmethod
+    def ring(cls, model, batches, post=None, warmup: int = 3, use_graph: bool = True, loss_scale: float = 1.0,
+             zero_first: bool = True, zero_blocks: int = 148):
+        """One step per batch, to be replayed round-robin in this order.  With ``zero_first`` step i opens with the re-zero of
+        the rows step i-1 touched (the last one for i = 0): the captures therefore follow one eager backward of the last
+        batch, in ring order, each leaving its own touched-row list for the next capture to pick up."""
+        steps = [cls(model, b, post=post, warmup=warmup, use_graph=use_graph, loss_scale=loss_scale, zero_first=zero_first,
+                     zero_blocks=zero_blocks, defer_capture=True) for b in batches]
+        if zero_first:
+            last = steps[-1]
+            out = model(last.data)
+            (out['loss'] if loss_scale == 1.0 else out['loss'] * loss_scale).backward()
+            if post is not None:
+                post()
+            torch.cuda.synchronize()
+        for st in steps:
+            st._capture()
+        return steps
+
+    def _eager(self, zero_first=None):
+        zero_first = self.zero_first if zero_first is None else zero_first
         if self._advance_epoch:
             from . import ops
             ops.advance_dropout_epoch(self.batch.idx.device)
         join = None
-        if self.zero_first:
+        if zero_first:
             main = torch.cuda.current_stream()
             key = main.device.index or 0
             side = self._zero_streams.get(key)
@@ -115,20 +148,27 @@ class GraphedStep:
                 side = self._zero_streams[key] = torch.cuda.Stream(device=main.device)
             fork, join = torch.cuda.Event(), torch.cuda.Event()
             fork.record(main)
-            side.wait_event(fork)
-            with torch.cuda.stream(side):
-                self.model.zero_grad(set_to_none=True)
-                join.record(side)
         out = self.model(self.data)
         if join is not None:
+            from . import _lib
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                _lib.check(_lib.load().rpb_set_option(b'rows_zero_blocks', self.zero_blocks), 'rpb_set_option(rows_zero_blocks)')
+                try:
+                    self.model.zero_grad(set_to_none=True)
+                finally:
+                    _lib.check(_lib.load().rpb_set_option(b'rows_zero_blocks', 0), 'rpb_set_option(rows_zero_blocks)')
+                join.record(side)
             torch.cuda.current_stream().wait_event(join)
         (out['loss'] if self.loss_scale == 1.0 else out['loss'] * self.loss_scale).backward()
         if self.post is not None:
             self.post()
-        if not self.zero_first:
+        if not zero_first:
             self.model.zero_grad(set_to_none=True)
         self.loss = out['loss'].detach()
         self.pred = out.get('pred', None)
+        if zero_first:      # this step's gradient tensors (dense ones are re-created by every captured step: `.grad` follows the last CAPTURE)
+            self.grads = {n: p.grad for n, p in self.model.named_parameters() if p.grad is not None}
 
     def replay(self):
         if self.graph is not None:

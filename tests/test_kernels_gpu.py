@@ -301,6 +301,39 @@ def test_cin_forward_backward(B, F, D, units):
         assert (p.grad.cpu().double() - r).abs().max().item() <= 1e-4 * max(1.0, r.abs().max().item()), k
 
 
+@pytest.mark.parametrize('B,save_x', [(1003, 1), (1003, 0), (8, 1), (1, 0)])
+def test_cin_tensor_core_ragged_batches_and_both_backward_modes(B, save_x, monkeypatch):
+    """cin_tc.cu at the Criteo shape (F = 26, D = 16, units 16-16-16) on batches that are not multiples of the 8-sample tile or
+    the 2-sample k-block, with the forward keeping X_1..X_{L-1} (rpb_cin_fwd_save / rpb_cin_bwd_saved) and with the backward
+    recomputing them (rpb_cin_fwd / rpb_cin_bwd)."""
+    from rec_pangu_b200 import ops
+    from rec_pangu_b200.models.layers import CompressedInteractionNet
+    monkeypatch.setattr(ops, 'CIN_SAVE_X', save_x)
+    F, D, units = 26, 16, [16, 16, 16]
+    torch.manual_seed(B + save_x)
+    m = CompressedInteractionNet(F, units)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.copy_(torch.randn(p.shape) * (0.3 if p.dim() > 1 else 0.1))
+    sd = {'p.' + k: v.detach().clone().double().requires_grad_(True) for k, v in m.state_dict().items()}
+    m = m.cuda()
+    e0 = torch.randn(B, F, D) * 0.5
+    e = e0.cuda().requires_grad_(True)
+    out = m(e)
+    w = torch.randn(B, 1)
+    (out * w.cuda()).sum().backward()
+    ed = e0.double().requires_grad_(True)
+    ref = oracle.cin(sd, 'p', ed, units)
+    (ref * w.double()).sum().backward()
+    scale = max(1.0, ref.abs().max().item())
+    assert (out.cpu().double() - ref).abs().max().item() <= 2e-5 * scale
+    gs = max(1.0, ed.grad.abs().max().item())
+    assert (e.grad.cpu().double() - ed.grad).abs().max().item() <= 5e-5 * gs
+    for k, p in m.named_parameters():
+        r = sd['p.' + k].grad
+        assert (p.grad.cpu().double() - r).abs().max().item() <= 1e-4 * max(1.0, r.abs().max().item()), k
+
+
 @pytest.mark.parametrize('B,F,D,H,d', [(100, 26, 32, 3, 8), (33, 6, 8, 3, 4), (64, 6, 12, 3, 4), (50, 32, 16, 1, 16)])
 def test_autoint_attention_forward_backward(B, F, D, H, d):
     from rec_pangu_b200.models.layers import MultiHeadSelfAttention

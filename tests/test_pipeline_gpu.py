@@ -190,3 +190,44 @@ def test_graph_replays_draw_fresh_dropout_masks():
         torch.cuda.synchronize()
         preds.append(step.pred.detach().clone())
     assert not torch.equal(preds[0], preds[1]) and not torch.equal(preds[1], preds[2]) and not torch.equal(preds[0], preds[2])
+
+
+def test_graphed_ring_zero_first_leaves_exactly_the_last_steps_gradients():
+    """GraphedStep.ring(zero_first=True): step j opens with the sparse re-zero of the rows step j-1 touched, on a side stream
+    next to the forward kernel.  After any number of ring-ordered replays the table and dense gradients must be exactly those
+    of the LAST step alone (nothing stale from earlier batches, nothing zeroed that the last step wrote)."""
+    from helpers import make_enc, make_batch
+    from rec_pangu_b200.models.ranking import DeepFM
+    from rec_pangu_b200.runtime import ColumnarBatch, GraphedStep
+    enc = make_enc(8, 3, 5000)
+    torch.manual_seed(3)
+    model = DeepFM(embedding_dim=16, hidden_units=[64, 64, 64], enc_dict=enc).cuda()
+    model.set_grad_mode('persistent')
+    model.train()
+    B, NB = 2048, 3
+    cbs = []
+    for i in range(NB):
+        cb = ColumnarBatch(enc, B, device='cuda', pinned_host=False)
+        cb.load_device(make_batch(enc, B, seed=20 + i, device='cuda'))
+        cbs.append(cb)
+    steps = GraphedStep.ring(model, cbs, zero_first=True)
+    assert all(s.graph is not None for s in steps)
+    for k in range(2 * NB + 2):                       # ends on ring position 1
+        steps[k % NB].replay()
+    torch.cuda.synchronize()
+    last = (2 * NB + 1) % NB
+    got = {n: g.detach().clone() for n, g in steps[last].grads.items()}      # the step's own tensors (tables: the persistent buffers)
+    # reference: the same step alone, eagerly, on zeroed gradients
+    for p in model.parameters():
+        if p.grad is not None:
+            p.grad.zero_()
+    model.embedding_layer._grad_store.pending = []      # host-side list of touched rows: stale after graph replays, all rows are clean now
+    out = model(cbs[last].as_dict())
+    out['loss'].backward()
+    torch.cuda.synchronize()
+    n_tables = 0
+    for n, p in model.named_parameters():
+        assert n in got, n
+        n_tables += 'embedding_layer' in n
+        torch.testing.assert_close(got[n], p.grad, rtol=1e-5, atol=1e-7, msg=lambda m, n=n: f'{n}: {m}')
+    assert n_tables >= 8
