@@ -93,7 +93,7 @@ RPB_API int rpb_set_option(const char* name, int64_t value) {
         return 0;
     }
     if (n == "rows_zero_blocks") { if (value < 0 || value > 65535) return RPB_ERR_BAD_ARG; rpb::g_rows_zero_blocks = (int)value; return 0; }
-    if (n == "cin_tc") { if (value < 0 || value > 2) return RPB_ERR_BAD_ARG; rpb::g_cin_tc = (int)value; return 0; }
+    if (n == "cin_tc") { rpb::g_cin_tc = value != 0; return 0; }
     if (n == "autoint_vec") { rpb::g_autoint_vec = value != 0; return 0; }
     if (n == "tower_bwd_tc") { rpb::g_tower_bwd_tc = value != 0; return 0; }
     if (n == "fused_gather_warps") { if (value != 4 && value != 8) return RPB_ERR_BAD_ARG; rpb::g_fused_gather_warps = (int)value; return 0; }

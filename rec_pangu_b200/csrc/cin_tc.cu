@@ -1,32 +1,27 @@
 // xDeepFM Compressed Interaction Network on tcgen05 (reference: models/layers/interaction.py:144-171).
 //
-// One CIN layer is a GEMM whose A operand does not exist in memory:
-//     X_{k+1}[(b,d), u] = sum_j Z[(b,d), j] * W_k[u, j] + bias[u],      Z[(b,d), h*M + m] = X0[b,h,d] * Xk[b,m,d]
-// rows = (sample, embedding dim) pairs (1 M rows at config 3), K = F*M (676 / 416), N = U = 16.  The fp32 CUDA-core kernels
-// of cin.cu form Z in registers and pay 4 LDS.128 of weights per 17 FP instructions (3.6 ms forward, 14 ms backward at
-// config 3, ~1 % of the HBM roofline, 0 % tensor pipe: profiles/r01_kernels.md).  Here the outer product is formed in
-// registers by "split" warps — thread = row (b,d) = tensor-memory lane, X0[b,:,d] and Xk[b,:,d] live in its registers for the
-// whole tile, every (h, m) of a k-block is a compile-time constant — split into (hi, lo) and written straight into tensor
-// memory as the TS-mode A operand, exactly like the split warps of deepfm_fwd_fs_kernel; the pre-split weights
-// [W hi ; W lo] (stacked N = 32) stay resident in shared memory; 3xTF32 keeps the 1e-4 parity bound.
-//
-// cin_fwd_tc_kernel<F, M>: warps 0 = weight TMA (once per CTA), 1 = MMA issuer, 2-9 = split (warps w and w+4 share a lane
-// quarter and take columns 0-15 / 16-31 of every k-block), 10-13 = epilogue (accumulator -> + bias -> X_{k+1}[b,u,d] and the
-// pooled sums over d).  Persistent: one CTA per SM walks tiles of 128 rows = 8 samples.
+//     X_{k+1}[b,u,d] = sum_{h,m} W_k[u, h*M + m] * X0[b,h,d] * Xk[b,m,d] + bias[u]        pooled[b,u] = sum_d X_{k+1}[b,u,d]
+// rows = (sample, embedding dim) pairs (1 M rows at config 3).  The fp32 CUDA-core kernels of cin.cu form the outer product
+// Z = X0 x Xk in registers and pay 4 LDS.128 of weights per 17 FP instructions (3.6 ms forward, 14 ms backward at config 3,
+// ~1 % of the HBM roofline, 0 % tensor pipe: profiles/r01_kernels.md).  Here every part is a tensor-core GEMM whose row operand
+// is written by the warps that own the rows (thread = row (b,d) = tensor-memory lane, TS-mode MMA, 3xTF32 for the 1e-4 parity
+// bound) and whose other contraction is done by the epilogue straight out of the accumulator, every index a compile-time
+// constant:
+//   forward   cin_fwd2_tc_kernel   T[(b,d),(h,u)] = sum_m Xk[m] W_k[u,h,m]     (K = M),  epilogue  X_{k+1}[u] = sum_h X0[h] T[(h,u)]
+//   backward  cin_bwd_tc_kernel    dZ[(b,d),(h,m)] = sum_u G[u] W_k[u,h,m]     (K = 16), epilogue  dXk[m] += dZ X0[h], dX0[h] += dZ Xk[m]
+//   weights   cin_wgrad_tc_kernel  dW_k[(u,h),m]  = sum_(b,d) (G[u] X0[h]) Xk[m]   (K = rows; P = G x X0 formed element-wise)
+// A first forward that fed the outer product itself to the tensor core (676 splits per row) was bound by its split warps
+// (562 us per layer against 250 us for the form above); the steps from 18.6 ms to 2.65 ms per xDeepFM step are listed in
+// profiles/r02_cin_ncu.md.  All kernels are persistent (one CTA per SM) and walk tiles of 128 rows = 8 samples.
 #include "tc_ptx.cuh"
 
 namespace rpb {
 
 constexpr int CT_D = 16;                 // embedding dim these kernels are built for (one 64-byte row per field)
 constexpr int CT_U = 16;                 // units per layer
-constexpr int CT_THREADS = 14 * 32;
 // registers are re-dealt between the warpgroups of the 384-thread kernels (168 per thread at launch)
 #define RPB_REG_DEC(n) asm volatile("setmaxnreg.dec.sync.aligned.u32 " #n ";")
 #define RPB_REG_INC(n) asm volatile("setmaxnreg.inc.sync.aligned.u32 " #n ";")
-constexpr int CT_OPN = 6;                // tensor-memory operand ring: 6 x 64 columns (A hi 32 | A lo 32)
-constexpr int CT_ACC = 2 * CT_U;         // accumulator columns: [A.Whi^T | A.Wlo^T]
-constexpr int CT_A_COL = 2 * CT_ACC;     // two accumulator buffers, then the operand ring
-constexpr int CT_KB_BYTES = 2 * CT_U * TC_BLOCK_K * 4;     // one resident weight k-block: 32 rows x 128 B = 4 KiB
 
 // Pre-split K-major weight operands with PERMUTED rows, so that consecutive accumulator columns feed different register
 // accumulators in the epilogues (a chain of dependent FMAs per output otherwise: profiles/r02_cin_ncu.md).
@@ -75,192 +70,12 @@ struct CinTcParams {
     int B, m_tiles;
 };
 
-// z columns of k-block KB, half HF, for the thread's row: compile-time (h, m) per column
-template <int F, int M, int KB, int HF>
-__device__ __forceinline__ void cin_zcols(const float (&x0)[F], const float (&xk)[M], uint32_t (&hi)[16], uint32_t (&lo)[16]) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        constexpr int dummy = 0; (void)dummy;
-        const int j = KB * TC_BLOCK_K + HF * 16 + i;
-        float z = 0.f;
-        if (j < F * M) z = x0[j / M] * xk[j % M];                 // j, M, F are compile-time after unrolling
-        hi[i] = __float_as_uint(z) & 0xFFFFE000u;
-        lo[i] = __float_as_uint(z - __uint_as_float(hi[i]));
-    }
-}
-
-template <int F, int M, int HF, int KB, int NKB>
-struct CinSplitLoop {
-    static __device__ __forceinline__ void run(const float (&x0)[F], const float (&xk)[M], uint32_t tmem_base, uint32_t lane_addr,
-                                               uint64_t* ready_op, uint64_t* empty_op, uint32_t g0, int lane) {
-        uint32_t hi[16], lo[16];
-        cin_zcols<F, M, KB, HF>(x0, xk, hi, lo);
-        const uint32_t g = g0 + KB;
-        const int o = g % CT_OPN;
-        mbar_wait(&empty_op[o], ((g / CT_OPN) & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t ta = tmem_base + CT_A_COL + (uint32_t)o * 64u + lane_addr + (uint32_t)HF * 16u;
-        tmem_st16(ta, hi);
-        tmem_st16(ta + 32u, lo);
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ready_op[o]);
-        CinSplitLoop<F, M, HF, KB + 1, NKB>::run(x0, xk, tmem_base, lane_addr, ready_op, empty_op, g0, lane);
-    }
-};
-template <int F, int M, int HF, int NKB>
-struct CinSplitLoop<F, M, HF, NKB, NKB> {
-    static __device__ __forceinline__ void run(const float (&)[F], const float (&)[M], uint32_t, uint32_t, uint64_t*, uint64_t*, uint32_t, int) {}
-};
-
-template <int F, int M>
-__global__ void __launch_bounds__(CT_THREADS, 1)
-cin_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo, const __grid_constant__ CinTcParams p) {
-    constexpr int NKB = (F * M + TC_BLOCK_K - 1) / TC_BLOCK_K;
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* w_base = smem;                                               // NKB x 4 KiB resident [W hi ; W lo] k-blocks
-    uint64_t* bars = reinterpret_cast<uint64_t*>(w_base + NKB * CT_KB_BYTES);
-    uint64_t* w_full = bars;                       // [1] weights landed
-    uint64_t* ready_op = w_full + 1;               // [CT_OPN] operand written (8 arrivals: one per split warp)
-    uint64_t* empty_op = ready_op + CT_OPN;        // [CT_OPN]
-    uint64_t* tmem_full = empty_op + CT_OPN;       // [2]
-    uint64_t* tmem_empty = tmem_full + 2;          // [2] 4 arrivals
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int my_tiles = ((int)blockIdx.x < p.m_tiles) ? (p.m_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    if (threadIdx.x == 0) {
-        mbar_init(w_full, 1);
-        for (int s = 0; s < CT_OPN; ++s) { mbar_init(&ready_op[s], 8); mbar_init(&empty_op[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
-        fence_barrier_init();
-    }
-    if (warp == 1) tmem_alloc(tmem_ptr, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            mbar_arrive_expect_tx(w_full, (uint32_t)(NKB * CT_KB_BYTES));
-            for (int kb = 0; kb < NKB; ++kb) {
-                tma_load_2d(w_base + (size_t)kb * CT_KB_BYTES, &tmWhi, w_full, kb * TC_BLOCK_K, 0);
-                tma_load_2d(w_base + (size_t)kb * CT_KB_BYTES + CT_KB_BYTES / 2, &tmWlo, w_full, kb * TC_BLOCK_K, 0);
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(TC_BLOCK_M, CT_ACC);
-            mbar_wait(w_full, 0u);
-            uint32_t g = 0;
-            for (int t = 0; t < my_tiles; ++t) {
-                const uint32_t acc = (uint32_t)t & 1u;
-                mbar_wait(&tmem_empty[acc], (((uint32_t)t >> 1) & 1u) ^ 1u);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * CT_ACC;
-                for (int kb = 0; kb < NKB; ++kb, ++g) {
-                    const int o = g % CT_OPN;
-                    mbar_wait(&ready_op[o], (g / CT_OPN) & 1u);
-                    tc_fence_after();
-                    const uint32_t b_addr = smem_u32(w_base + (size_t)kb * CT_KB_BYTES);
-                    const uint32_t ta_hi = tmem_base + CT_A_COL + (uint32_t)o * 64u, ta_lo = ta_hi + 32u;
-#pragma unroll
-                    for (int k = 0; k < TC_BLOCK_K / TC_UMMA_K; ++k) {
-                        const uint64_t db = make_kmajor_sw128_desc(b_addr + k * TC_UMMA_K * 4);
-                        umma_tf32_ts(d_tmem, ta_lo + k * TC_UMMA_K, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                        umma_tf32_ts(d_tmem, ta_hi + k * TC_UMMA_K, db, idesc, 1u);
-                    }
-                    umma_commit(&empty_op[o]);
-                }
-                umma_commit(&tmem_full[acc]);
-            }
-        }
-    } else if (warp < 10) {
-        // ---------------- split warps: thread = row (b, d) of the tile; X0[b,:,d] and Xk[b,:,d] in registers
-        const int q = warp & 3, half = (warp - 2) >> 2;
-        const int row = q * 32 + lane;
-        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        uint32_t g0 = 0;
-        for (int t = 0; t < my_tiles; ++t, g0 += NKB) {
-            const long long b = (long long)((int)blockIdx.x + t * (int)gridDim.x) * 8 + (row >> 4);
-            const int d = row & 15;
-            float x0[F], xk[M];
-            if (b < p.B) {
-                const float* r0 = p.x0 + (size_t)b * p.ld0 + d;
-                const float* rk = p.xk + (size_t)b * p.ldk + d;
-#pragma unroll
-                for (int h = 0; h < F; ++h) x0[h] = __ldg(r0 + h * CT_D);
-#pragma unroll
-                for (int m = 0; m < M; ++m) xk[m] = __ldg(rk + m * CT_D);
-            } else {
-#pragma unroll
-                for (int h = 0; h < F; ++h) x0[h] = 0.f;
-#pragma unroll
-                for (int m = 0; m < M; ++m) xk[m] = 0.f;
-            }
-            if (half == 0) CinSplitLoop<F, M, 0, 0, NKB>::run(x0, xk, tmem_base, lane_addr, ready_op, empty_op, g0, lane);
-            else CinSplitLoop<F, M, 1, 0, NKB>::run(x0, xk, tmem_base, lane_addr, ready_op, empty_op, g0, lane);
-        }
-    } else {
-        // ---------------- epilogue warps: accumulator (both stacked halves) + bias -> X_{k+1}, pooled sums over d
-        const int q = warp & 3;
-        const int row = q * 32 + lane;
-        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        float bv[CT_U];
-#pragma unroll
-        for (int u = 0; u < CT_U; ++u) bv[u] = p.bias != nullptr ? __ldg(p.bias + u) : 0.f;
-        for (int t = 0; t < my_tiles; ++t) {
-            const uint32_t acc = (uint32_t)t & 1u;
-            const long long b = (long long)((int)blockIdx.x + t * (int)gridDim.x) * 8 + (row >> 4);
-            const int d = row & 15;
-            mbar_wait(&tmem_full[acc], ((uint32_t)t >> 1) & 1u);
-            tc_fence_after();
-            uint32_t a0[16], a1[16];
-            tmem_ld16(tmem_base + acc * CT_ACC + lane_addr, a0);
-            tmem_ld16(tmem_base + acc * CT_ACC + lane_addr + CT_U, a1);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-            const bool valid = b < p.B;
-#pragma unroll
-            for (int u = 0; u < CT_U; ++u) {
-                const float v = __uint_as_float(a0[u]) + __uint_as_float(a1[u]) + bv[u];
-                if (valid && p.xout != nullptr) p.xout[(size_t)b * p.ldo + u * CT_D + d] = v;
-                if (p.pooled != nullptr) {
-                    const float s = group_sum<CT_D>(v);
-                    if (valid && d == 0) p.pooled[(size_t)b * p.ldp + u] = s;
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
-}
-
-template <int F, int M>
-static int cin_fwd_tc_launch(const float* W, const CinTcParams& p, cudaStream_t st) {
-    constexpr int NKB = (F * M + TC_BLOCK_K - 1) / TC_BLOCK_K;
-    CUtensorMap tmWhi, tmWlo;
-    int rc = tc_prepare_weight(W, F * M, CT_U, F * M, &tmWhi, &tmWlo, st);
-    if (rc != 0) return rc;
-    const size_t smem = (size_t)NKB * CT_KB_BYTES + (1 + 2 * CT_OPN + 4) * 8 + 16 + 1024;
-    cudaError_t e = cudaFuncSetAttribute(cin_fwd_tc_kernel<F, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    cin_fwd_tc_kernel<F, M><<<min(p.m_tiles, 148), CT_THREADS, smem, st>>>(tmWhi, tmWlo, p);
-    return (int)cudaGetLastError();
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
-// Forward, second formulation (the default): contract over m on the tensor core, over h in the epilogue.
+// Forward: contract over m on the tensor core, over h in the epilogue.
 //     T[(b,d), (h,u)] = sum_m Xk[b,m,d] * W_k[u, h*M + m]           (rows x M x 16*F GEMM; A = Xk rows, K = M)
 //     X_{k+1}[b,u,d]  = sum_h X0[b,h,d] * T[(b,d), (u,h)] + bias[u]  (epilogue, straight out of the accumulator)
-// Same flops on the tensor core as the outer-product form, but the A operand is M values per row instead of F*M products
-// (26 splits instead of 676: the split warps were the bound, profiles/r02_cin_ncu.md), W_k is its own K-major operand
-// ([(u,h) rows, M contiguous columns]: no transposition), and the epilogue is one FMA per accumulator column.
+// The A operand is M values per row (not the F*M products of the outer product), W_k is its own K-major operand
+// ([(h,u) rows, M contiguous columns]: no transposition), and the epilogue is one FMA per accumulator column.
 constexpr int C2_THREADS = 12 * 32;      // warpgroups: [0 weights, 1 MMA, 2-3 idle] [4-7 operand warps] [8-11 epilogue warps]
 
 template <int F, int NT, int NTI, int C0>
@@ -505,11 +320,6 @@ int cin_layer_fwd_tc(int F, int M, int U, int D, const float* W, const float* bi
     CinTcParams p{};
     p.x0 = x0; p.ld0 = ld0; p.xk = xk; p.ldk = ldk; p.bias = bias; p.xout = xout; p.ldo = ldo; p.pooled = pooled; p.ldp = ldp;
     p.B = B; p.m_tiles = ceil_div(B, 8);
-    if (g_cin_tc == 2) {                                                  // first formulation (outer product in registers), kept for A/B
-        if (F == 26 && M == 26) return cin_fwd_tc_launch<26, 26>(W, p, st);
-        if (F == 26 && M == 16) return cin_fwd_tc_launch<26, 16>(W, p, st);
-        return RPB_ERR_UNSUPPORTED;
-    }
     if (F == 26 && M == 26) return cin_fwd2_tc_launch<26, 26, 144, 3>(W, p, st);
     if (F == 26 && M == 16) return cin_fwd2_tc_launch<26, 16, 208, 2>(W, p, st);
     return RPB_ERR_UNSUPPORTED;
