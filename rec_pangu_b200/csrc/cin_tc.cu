@@ -458,6 +458,21 @@ cin_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_consta
         for (int t = 0; t < my_tiles; ++t) {
             const long long b = (long long)((int)blockIdx.x + t * (int)gridDim.x) * 8 + (row >> 4);
             const int d = row & 15;
+            {
+                // these warps run one to two tiles ahead of the epilogue: pull the rows it will read (X0, Xk, the dE rows it
+                // accumulates into) of the NEXT tile into L2, one 64-byte row per lane and step, so that its loads at the top and
+                // bottom of a tile are L2 hits instead of DRAM round trips
+                const long long bn = (long long)((int)blockIdx.x + (t + 1) * (int)gridDim.x) * 8 + (row >> 4);
+                if (t + 1 < my_tiles && bn < p.B) {
+                    for (int h = d; h < F; h += CT_D) {
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(p.x0 + (size_t)bn * p.ld0 + h * CT_D));
+                        if (p.de_accumulate) asm volatile("prefetch.global.L2 [%0];" :: "l"(p.de + (size_t)bn * p.ldde + h * CT_D));
+                    }
+                    if (p.xk != p.x0) {
+                        for (int m = d; m < M; m += CT_D) asm volatile("prefetch.global.L2 [%0];" :: "l"(p.xk + (size_t)bn * p.ldk + m * CT_D));
+                    }
+                }
+            }
             float g[CT_U];
             if (b < p.B) {
 #pragma unroll
@@ -803,42 +818,61 @@ cin_wgrad_tc_kernel(const __grid_constant__ CinWgParams p) {
             x_off[mt] = L::X_OFF + (half * F + h) * 64;
             x_sw[mt] = (h >> 1) & 3;
         }
+        static_assert(MT == 4, "the operand loop below is unrolled over four M-tiles with two register sets");
+        // P columns of M-tile mt for this thread's (u, h) pair and sample: G[b,u,:] * X0[b,h,:], split into (hi, lo)
+        auto compute = [&](const uint8_t* tile, int mt, uint32_t (&hi)[16], uint32_t (&lo)[16]) {
+            if (okp[mt]) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float4 a = *reinterpret_cast<const float4*>(tile + g_off[mt] + (c << 4));
+                    const float4 x = *reinterpret_cast<const float4*>(tile + x_off[mt] + ((c ^ x_sw[mt]) << 4));
+                    const float z[4] = {a.x * x.x, a.y * x.y, a.z * x.z, a.w * x.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        hi[4 * c + e] = __float_as_uint(z[e]) & 0xFFFFE000u;
+                        lo[4 * c + e] = __float_as_uint(z[e] - __uint_as_float(hi[4 * c + e]));
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) { hi[e] = 0u; lo[e] = 0u; }
+            }
+        };
+        // software pipeline: the tcgen05.st of operand g is in flight while the products of operand g+1 are formed
+        auto put = [&](uint32_t g, const uint32_t (&hi)[16], const uint32_t (&lo)[16]) {
+            const uint32_t o = g % CW_OPN;
+            mbar_wait(&a_empty[o], ((g / CW_OPN) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t ta = tmem_base + A_COL + o * 64u + lane_addr + (uint32_t)half * 16u;
+            tmem_st16(ta, hi);
+            tmem_st16(ta + 32u, lo);
+        };
+        auto publish = [&](uint32_t g) {
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_ready[g % CW_OPN]);
+        };
+        uint32_t hA[16], lA[16], hB[16], lB[16];
         uint32_t ga = 0;
+        if (nkb > 0) {
+            mbar_wait(&g_full[0], 0u);
+            compute(st_base, 0, hA, lA);
+        }
         for (int i = 0; i < nkb; ++i) {
             const int s = i % CW_BST;
             const uint8_t* tile = st_base + (size_t)s * L::STAGE;
-            mbar_wait(&g_full[s], (i / CW_BST) & 1u);
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt, ++ga) {
-                uint32_t hi[16], lo[16];
-                if (okp[mt]) {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const float4 a = *reinterpret_cast<const float4*>(tile + g_off[mt] + (c << 4));
-                        const float4 x = *reinterpret_cast<const float4*>(tile + x_off[mt] + ((c ^ x_sw[mt]) << 4));
-                        const float z[4] = {a.x * x.x, a.y * x.y, a.z * x.z, a.w * x.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            hi[4 * c + e] = __float_as_uint(z[e]) & 0xFFFFE000u;
-                            lo[4 * c + e] = __float_as_uint(z[e] - __uint_as_float(hi[4 * c + e]));
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) { hi[e] = 0u; lo[e] = 0u; }
-                }
-                const int o = ga % CW_OPN;
-                mbar_wait(&a_empty[o], ((ga / CW_OPN) & 1u) ^ 1u);
-                tc_fence_after();
-                const uint32_t ta = tmem_base + A_COL + (uint32_t)o * 64u + lane_addr + (uint32_t)half * 16u;
-                tmem_st16(ta, hi);
-                tmem_st16(ta + 32u, lo);
-                tmem_st_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&a_ready[o]);
+            put(ga, hA, lA); compute(tile, 1, hB, lB); publish(ga); ++ga;
+            put(ga, hB, lB); compute(tile, 2, hA, lA); publish(ga); ++ga;
+            put(ga, hA, lA); compute(tile, 3, hB, lB); publish(ga); ++ga;
+            if (lane == 0) mbar_arrive(&g_empty[s]);                      // every lane has read the stage's G / X0 rows (syncwarp in publish)
+            put(ga, hB, lB);
+            if (i + 1 < nkb) {
+                const int s2 = (i + 1) % CW_BST;
+                mbar_wait(&g_full[s2], ((i + 1) / CW_BST) & 1u);
+                compute(st_base + (size_t)s2 * L::STAGE, 0, hA, lA);
             }
-            if (lane == 0) mbar_arrive(&g_empty[s]);                      // this warp has read the stage's G / X0 rows (syncwarp above)
+            publish(ga); ++ga;
         }
         // ---------------- epilogue (first four operand warps): acc[mt] = a.b_raw | a.b_lo  ->  dW[u, h*M + m] += sum
         if (half == 0 && nkb > 0) {
