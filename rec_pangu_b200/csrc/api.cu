@@ -16,6 +16,7 @@ int g_gemm_stack_n = 1;
 int g_tf32_raw_hi = 1;
 int g_fused_gather_warps = 8;
 int g_fused_fetch_warps = 8;
+int g_fused_l2_prefetch = 0;
 int g_fused_ring = 0;
 int g_fused_tc_tail = 1;    // tower-tail layers of the one-kernel forward on tcgen05 (0 = fp32 CUDA-core tail)
 int g_tower_bwd_tc = 0;     // opt-in until measured on hardware
@@ -97,6 +98,7 @@ RPB_API int rpb_set_option(const char* name, int64_t value) {
     if (n == "autoint_vec") { rpb::g_autoint_vec = value != 0; return 0; }
     if (n == "tower_bwd_tc") { rpb::g_tower_bwd_tc = value != 0; return 0; }
     if (n == "fused_gather_warps") { if (value != 4 && value != 8) return RPB_ERR_BAD_ARG; rpb::g_fused_gather_warps = (int)value; return 0; }
+    if (n == "fused_l2_prefetch") { if (value < 0 || value > 8) return RPB_ERR_BAD_ARG; rpb::g_fused_l2_prefetch = (int)value; return 0; }
     if (n == "fused_fetch_warps") { if (value != 0 && value != 4 && value != 8 && value != 16) return RPB_ERR_BAD_ARG; rpb::g_fused_fetch_warps = (int)value; return 0; }
     if (n == "fused_ring") { if (value != 0 && (value < 3 || value > 6)) return RPB_ERR_BAD_ARG; rpb::g_fused_ring = (int)value; return 0; }
     if (n == "fused_tc_tail") { rpb::g_fused_tc_tail = value != 0; return 0; }

@@ -28,6 +28,7 @@ extern int g_wgrad_stages;                           // api.cu: pipeline depth o
 extern int g_wgrad_tc;                               // api.cu: 1 = tcgen05 weight-gradient kernel in auto mode
 extern int g_fused_tc_tail;                          // api.cu: 1 = one-kernel DeepFM forward runs its 64x64 tail layers on tcgen05 (deepfm_fused.cu, TCTAIL)
 extern int g_fused_gather_warps;                     // api.cu: 8 = one-kernel DeepFM forward with eight gather warps + TMA x store (default), 4 = the round-1 kernel
+extern int g_fused_l2_prefetch;                     // api.cu: tiles by which the FS kernel's L2 prefetch warp runs ahead (0 = off, the default: measured 133 vs 99 us)
 extern int g_fused_fetch_warps;                      // api.cu: 4 = one-kernel DeepFM forward with dedicated fetch warps (default), 0 = every gather warp fetches its own rows
 extern int g_fused_ring;                             // api.cu: gather ring depth of the 8-warp forward (0 = deepest that fits)
 extern int g_tower_bwd_tc;                           // api.cu: 1 = tower-tail backward runs its dz chain on tcgen05 (tower_tc.cu)

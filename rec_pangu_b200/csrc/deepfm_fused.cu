@@ -50,6 +50,7 @@ struct FusedFwdParams {
     // array = rank g's shard of table f, local or mapped over NVLink (the row request is the same cp.async either way)
     int G;
     const float* const* shard_tab;
+    int l2_prefetch;                      // FS kernel, unsharded: tiles by which the L2 prefetch warp runs ahead of the fetch warps (0 = off)
 };
 
 // table rows: 16-byte pieces of a 64-byte row; the L2 fetch is capped at 64 B so that a row does not drag the other half
@@ -1185,6 +1186,7 @@ deepfm_fwd_fs_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_con
         for (int s = 0; s < FG_FM_BUF; ++s) mbar_init(&fm_ready[s], 4);
         mbar_init(&tail_bars[0], 1); mbar_init(&tail_bars[1], FG_EPI_WARPS); mbar_init(&tail_bars[2], 1); mbar_init(&tail_bars[3], 1);
         for (int s = 0; s < LA * 4; ++s) { mbar_init(&full_a[s], NF * 8); mbar_init(&empty_a[s], p.x != nullptr ? 2 : 1); }
+        tmem_ptr[1] = 0u;                          // tile the fetch warps are on (read by the L2 prefetch warp)
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_ptr, 512);
@@ -1324,6 +1326,39 @@ deepfm_fwd_fs_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_con
             bulk_wait_all<0>();
             if (trace) g_fg_trace[12] = (unsigned long long)w_st;
         }
+    } else if (warp == 3) {
+        // ---------------- L2 prefetch warp (the fourth warp of this warpgroup was idle): asks L2 for the table rows of the tile(s)
+        // AHEAD of the one the fetch warps are on, so that their cp.async requests — whose acceptance rate is what bounds the
+        // kernel — are answered by L2.  prefetch.global.L2 returns nothing to the SM.  MEASURED SLOWER (132.7 vs 98.9 us, the same
+        // for 1, 2 and 4 tiles ahead: profiles/r02_rowfetch.md): the prefetches travel the same SM request path as the row
+        // requests, and that path — not DRAM latency — is what the fetch warps wait for.  Off by default (fused_l2_prefetch = 0).
+        if constexpr (!SHARDED) {
+            if (p.l2_prefetch > 0) {
+                volatile uint32_t* prog = reinterpret_cast<volatile uint32_t*>(tmem_ptr + 1);
+                for (int t = 0; t < my_tiles; ++t) {
+                    while ((int)*prog + p.l2_prefetch < t) __nanosleep(256);
+                    const int m0 = tile_m0(t), nr = tile_rows(t);
+                    for (int r0 = 0; r0 < nr; r0 += 32) {
+                        const int r = r0 + lane;
+                        const bool ok = r < nr;
+                        for (int f0 = 0; f0 < p.F; f0 += 13) {
+                            long long id[13];
+#pragma unroll
+                            for (int j = 0; j < 13; ++j) id[j] = (ok && f0 + j < p.F) ? __ldg(p.idx[f0 + j] + m0 + r) : -1;
+#pragma unroll
+                            for (int j = 0; j < 13; ++j) {
+                                const int f = f0 + j;
+                                if (f < p.F && id[j] >= 0 && (unsigned long long)id[j] < (unsigned long long)p.rows[f]) {
+                                    const float* src = p.tables[f] + (size_t)id[j] * 16;
+                                    asm volatile("prefetch.global.L2 [%0];" :: "l"(src));
+                                    asm volatile("prefetch.global.L2 [%0];" :: "l"(src + 8));
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
     }
     } else if (warp >= FS_FETCH_WARP0 && warp < FS_SPLIT_WARP0) {
         if constexpr (NF == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -1365,6 +1400,7 @@ deepfm_fwd_fs_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_con
         __syncwarp();
         for (uint32_t g = 0; g < G; ++g) {
             const int slot = (int)(g % LA);
+            if (kb == 0 && fw == 0 && lane == 0) *reinterpret_cast<volatile uint32_t*>(tmem_ptr + 1) = (uint32_t)t;
             fg_wait<FS_IDD - 1>();                          // the id copies of round g (requested FS_IDD rounds ago) have landed
             __syncwarp();
             const long long c0 = FG_T();
@@ -1712,6 +1748,7 @@ RPB_API int rpb_deepfm_fwd_fused(const RpbGatherDesc* g, const float* W1, const 
     p.M = d->M; p.F = g->F; p.Nd = g->Nd;
     p.G = sharded ? g->G : 1;
     p.shard_tab = sharded ? g->shard_tab : nullptr;
+    p.l2_prefetch = sharded ? 0 : g_fused_l2_prefetch;
     p.nkb_emb = g->F / 2;
     p.nkb = p.nkb_emb + ceil_div(g->Nd, TC_BLOCK_K);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
