@@ -265,8 +265,6 @@ def test_deepfm_one_kernel_forward_tc_tail(B, F, Nd, hidden):
         assert (a - b).abs().max().item() <= 5e-4 * max(1e-6, b.abs().max().item()) + 1e-7, n
 
 
-@pytest.mark.skipif(os.environ.get('RPB_EXPERIMENTAL', '0') != '1',
-                    reason='tcgen05 tower-tail backward: compiled but not yet run on hardware (opt-in)')
 @pytest.mark.parametrize('B,F,Nd,hidden', [(4096, 26, 13, [64, 64, 64]), (5000, 26, 13, [64, 64]), (1300, 4, 0, [64, 64, 64, 64])])
 def test_tower_tail_backward_tc(B, F, Nd, hidden):
     """rpb_set_option('tower_bwd_tc', 1): the dz chain of rpb_tower_tail_bwd on tcgen05 (3xTF32 through tensor memory) vs the
@@ -303,8 +301,6 @@ def test_tower_tail_backward_tc(B, F, Nd, hidden):
         assert (a - b).abs().max().item() <= 5e-4 * max(1e-6, b.abs().max().item()) + 1e-7, n
 
 
-@pytest.mark.skipif(os.environ.get('RPB_EXPERIMENTAL', '0') != '1',
-                    reason='fused DeepFM core on row-sharded tables: compiled but not yet run on hardware (opt-in)')
 @pytest.mark.parametrize('G', [2, 3, 8])
 def test_sharded_fused_core_on_local_shards(G):
     """ops.SHARDED_FUSED with dist.LocalShards (all G shards of every table on this GPU): the sharded variants of the
@@ -329,14 +325,15 @@ def test_sharded_fused_core_on_local_shards(G):
     data = make_batch(enc, 1500, seed=5, device='cuda')
     out_r = ref(data)
     out_r['loss'].backward()
+    old = ops.SHARDED_FUSED
     ops.SHARDED_FUSED = 1
     try:
         n0 = ops.launch_count()
         out_s = sh(data)
-        assert ops.launch_count() - n0 == 2                      # weight split + the one-kernel forward
+        assert ops.launch_count() - n0 == 3                      # two weight splits (layer 1, tower tail) + the one-kernel forward
         out_s['loss'].backward()
     finally:
-        ops.SHARDED_FUSED = 0
+        ops.SHARDED_FUSED = old
     torch.cuda.synchronize()
     ops.check_index_errors()
     torch.testing.assert_close(sh._last_logit, ref._last_logit, rtol=0, atol=1e-6)
