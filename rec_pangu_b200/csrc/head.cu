@@ -126,26 +126,49 @@ __device__ __forceinline__ float uniform01(unsigned long long seed, unsigned lon
     return (float)(z >> 40) * (1.0f / 16777216.0f);
 }
 
-// y = x * keep / (1-p)  (in place allowed)
+// y = x * keep / (1-p)  (in place allowed).  VEC = 4: one float4 per thread (16-byte aligned pointers, n % 4 == 0) — the mask of
+// element i depends on (seed, epoch, i) only, so both forms draw the same masks; the scalar form moved 33 MB in 17 us.
+template <int VEC>
 __global__ void __launch_bounds__(256)
 dropout_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float p, float inv_keep,
                    unsigned long long seed, const unsigned long long* __restrict__ epoch) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     if (i >= n) return;
     if (epoch != nullptr) seed += __ldg(epoch) * 0xD1B54A32D192ED03ull;      // device-side step counter (CUDA-graph replays)
-    y[i] = (uniform01(seed, (unsigned long long)i) >= p) ? x[i] * inv_keep : 0.f;
+    if constexpr (VEC == 4) {
+        float4 v = *reinterpret_cast<const float4*>(x + i);
+        v.x = (uniform01(seed, (unsigned long long)i) >= p) ? v.x * inv_keep : 0.f;
+        v.y = (uniform01(seed, (unsigned long long)i + 1ull) >= p) ? v.y * inv_keep : 0.f;
+        v.z = (uniform01(seed, (unsigned long long)i + 2ull) >= p) ? v.z * inv_keep : 0.f;
+        v.w = (uniform01(seed, (unsigned long long)i + 3ull) >= p) ? v.w * inv_keep : 0.f;
+        *reinterpret_cast<float4*>(y + i) = v;
+    } else {
+        y[i] = (uniform01(seed, (unsigned long long)i) >= p) ? x[i] * inv_keep : 0.f;
+    }
 }
 
 // dx = dy * keep/(1-p) * (relu_out ? relu_out > 0 : 1)
+template <int VEC>
 __global__ void __launch_bounds__(256)
 dropout_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ relu_out, float* __restrict__ dx,
                    long long n, float p, float inv_keep, unsigned long long seed, const unsigned long long* __restrict__ epoch) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     if (i >= n) return;
     if (epoch != nullptr) seed += __ldg(epoch) * 0xD1B54A32D192ED03ull;
-    float v = (uniform01(seed, (unsigned long long)i) >= p) ? dy[i] * inv_keep : 0.f;
-    if (relu_out != nullptr && !(relu_out[i] > 0.f)) v = 0.f;
-    dx[i] = v;
+    if constexpr (VEC == 4) {
+        float4 v = *reinterpret_cast<const float4*>(dy + i);
+        float4 r = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (relu_out != nullptr) r = *reinterpret_cast<const float4*>(relu_out + i);
+        v.x = (uniform01(seed, (unsigned long long)i) >= p && r.x > 0.f) ? v.x * inv_keep : 0.f;
+        v.y = (uniform01(seed, (unsigned long long)i + 1ull) >= p && r.y > 0.f) ? v.y * inv_keep : 0.f;
+        v.z = (uniform01(seed, (unsigned long long)i + 2ull) >= p && r.z > 0.f) ? v.z * inv_keep : 0.f;
+        v.w = (uniform01(seed, (unsigned long long)i + 3ull) >= p && r.w > 0.f) ? v.w * inv_keep : 0.f;
+        *reinterpret_cast<float4*>(dx + i) = v;
+    } else {
+        float v = (uniform01(seed, (unsigned long long)i) >= p) ? dy[i] * inv_keep : 0.f;
+        if (relu_out != nullptr && !(relu_out[i] > 0.f)) v = 0.f;
+        dx[i] = v;
+    }
 }
 
 }  // namespace rpb
@@ -155,7 +178,11 @@ using namespace rpb;
 RPB_API int rpb_dropout_fwd(const float* x, float* y, int64_t n, float p, uint64_t seed, const uint64_t* epoch, void* stream) {
     if (x == nullptr || y == nullptr || n <= 0 || p < 0.f || p >= 1.f) return RPB_ERR_BAD_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    dropout_fwd_kernel<<<ceil_div(n, 256), 256, 0, st>>>(x, y, n, p, 1.f / (1.f - p), seed, reinterpret_cast<const unsigned long long*>(epoch));
+    const unsigned long long* ep = reinterpret_cast<const unsigned long long*>(epoch);
+    if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15u) == 0)
+        dropout_fwd_kernel<4><<<ceil_div(n / 4, 256), 256, 0, st>>>(x, y, n, p, 1.f / (1.f - p), seed, ep);
+    else
+        dropout_fwd_kernel<1><<<ceil_div(n, 256), 256, 0, st>>>(x, y, n, p, 1.f / (1.f - p), seed, ep);
     RPB_LAUNCH_CHECK();
     return 0;
 }
@@ -164,7 +191,11 @@ RPB_API int rpb_dropout_bwd(const float* dy, const float* relu_out, float* dx, i
                             const uint64_t* epoch, void* stream) {
     if (dy == nullptr || dx == nullptr || n <= 0 || p < 0.f || p >= 1.f) return RPB_ERR_BAD_ARG;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    dropout_bwd_kernel<<<ceil_div(n, 256), 256, 0, st>>>(dy, relu_out, dx, n, p, 1.f / (1.f - p), seed, reinterpret_cast<const unsigned long long*>(epoch));
+    const unsigned long long* ep = reinterpret_cast<const unsigned long long*>(epoch);
+    if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(relu_out)) & 15u) == 0)
+        dropout_bwd_kernel<4><<<ceil_div(n / 4, 256), 256, 0, st>>>(dy, relu_out, dx, n, p, 1.f / (1.f - p), seed, ep);
+    else
+        dropout_bwd_kernel<1><<<ceil_div(n, 256), 256, 0, st>>>(dy, relu_out, dx, n, p, 1.f / (1.f - p), seed, ep);
     RPB_LAUNCH_CHECK();
     return 0;
 }

@@ -423,3 +423,38 @@ def test_gather_without_materialisation_matches():
                                 want_x=False)
     assert x2.numel() == 0
     torch.testing.assert_close(fm2, fm, rtol=1e-6, atol=1e-6)
+
+
+def test_dropout_vector_and_scalar_kernels_draw_the_same_masks():
+    """rpb_dropout_fwd / _bwd pick a float4 kernel for 16-byte aligned buffers with n % 4 == 0 and a scalar one otherwise; the
+    keep decision of element i depends on (seed, i) only, so both must keep exactly the same elements — checked through the C
+    ABI with an explicit seed on an aligned buffer and on the same values shifted by one float (misaligned -> scalar path)."""
+    from rec_pangu_b200 import _lib
+    lib = _lib.load()
+    n, p, seed = 4096 * 4, 0.3, 123456789
+    torch.manual_seed(0)
+    base = torch.rand(n + 4, device='cuda') + 0.5                   # strictly positive: y != 0 <=> kept
+    xa = base[:n].clone()                                           # aligned
+    shifted = torch.empty(n + 4, device='cuda')
+    shifted[1:n + 1].copy_(xa)
+    xs = shifted[1:n + 1]                                           # data pointer + 4 bytes
+    assert xa.data_ptr() % 16 == 0 and xs.data_ptr() % 16 == 4
+    ya, ys = torch.empty_like(xa), torch.empty(n + 4, device='cuda')[1:n + 1]
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.rpb_dropout_fwd(xa.data_ptr(), ya.data_ptr(), n, p, seed, None, st), 'rpb_dropout_fwd')
+    _lib.check(lib.rpb_dropout_fwd(xs.data_ptr(), ys.data_ptr(), n, p, seed, None, st), 'rpb_dropout_fwd')
+    torch.cuda.synchronize()
+    assert torch.equal(ya, ys)
+    keep = (ya != 0).float().mean().item()
+    assert abs(keep - (1 - p)) < 0.02
+    torch.testing.assert_close(ya[ya != 0], xa[ya != 0] / (1 - p), rtol=1e-6, atol=0)
+    # backward with a ReLU output mask: same two paths
+    relu = (torch.rand(n, device='cuda') - 0.4).clamp_min(0)
+    relu_s = torch.empty(n + 4, device='cuda')[1:n + 1]
+    relu_s.copy_(relu)
+    da, ds = torch.empty_like(xa), torch.empty(n + 4, device='cuda')[1:n + 1]
+    _lib.check(lib.rpb_dropout_bwd(xa.data_ptr(), relu.data_ptr(), da.data_ptr(), n, p, seed, None, st), 'rpb_dropout_bwd')
+    _lib.check(lib.rpb_dropout_bwd(xs.data_ptr(), relu_s.data_ptr(), ds.data_ptr(), n, p, seed, None, st), 'rpb_dropout_bwd')
+    torch.cuda.synchronize()
+    assert torch.equal(da, ds)
+    assert torch.equal(da != 0, (ya != 0) & (relu > 0))
