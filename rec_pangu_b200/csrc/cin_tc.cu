@@ -11,7 +11,7 @@
 //   backward  cin_bwd_tc_kernel    dZ[(b,d),(h,m)] = sum_u G[u] W_k[u,h,m]     (K = 16), epilogue  dXk[m] += dZ X0[h], dX0[h] += dZ Xk[m]
 //   weights   cin_wgrad_tc_kernel  dW_k[(u,h),m]  = sum_(b,d) (G[u] X0[h]) Xk[m]   (K = rows; P = G x X0 formed element-wise)
 // A first forward that fed the outer product itself to the tensor core (676 splits per row) was bound by its split warps
-// (562 us per layer against 250 us for the form above); the steps from 18.6 ms to 2.65 ms per xDeepFM step are listed in
+// (562 us per layer against 250 us for the form above); the steps from 18.6 ms to 2.54 ms per xDeepFM step are listed in
 // profiles/r02_cin_ncu.md.  All kernels are persistent (one CTA per SM) and walk tiles of 128 rows = 8 samples.
 #include "tc_ptx.cuh"
 
@@ -73,7 +73,7 @@ struct CinTcParams {
 // ---------------------------------------------------------------------------------------------------------------------
 // Forward: contract over m on the tensor core, over h in the epilogue.
 //     T[(b,d), (h,u)] = sum_m Xk[b,m,d] * W_k[u, h*M + m]           (rows x M x 16*F GEMM; A = Xk rows, K = M)
-//     X_{k+1}[b,u,d]  = sum_h X0[b,h,d] * T[(b,d), (u,h)] + bias[u]  (epilogue, straight out of the accumulator)
+//     X_{k+1}[b,u,d]  = sum_h X0[b,h,d] * T[(b,d), (h,u)] + bias[u]  (epilogue, straight out of the accumulator)
 // The A operand is M values per row (not the F*M products of the outer product), W_k is its own K-major operand
 // ([(h,u) rows, M contiguous columns]: no transposition), and the epilogue is one FMA per accumulator column.
 constexpr int C2_THREADS = 12 * 32;      // warpgroups: [0 weights, 1 MMA, 2-3 idle] [4-7 operand warps] [8-11 epilogue warps]
@@ -123,7 +123,7 @@ cin_fwd2_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_const
     static_assert(A_COL + 4 * KP <= 512 && NP >= CT_U * F && NT % 16 == 0 && NT <= 256 && NTILES <= 4, "tile plan");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* w_hi = smem;                                                 // [NP rows (u,h)][128 B]: W hi (M valid columns, rest zero)
+    uint8_t* w_hi = smem;                                                 // [NP rows (h,u)][128 B]: W hi (M valid columns, rest zero)
     uint8_t* w_lo = w_hi + (size_t)NP * 128;
     uint64_t* bars = reinterpret_cast<uint64_t*>(w_lo + (size_t)NP * 128);
     uint64_t* w_full = bars;                       // [1]
@@ -596,10 +596,10 @@ int cin_layer_bwd_tc(int F, int M, const float* W, const CinBwdParams& p, cudaSt
 // =====================================================================================================================
 // Backward of one layer, part B (weight gradient):  dW_k[u, h*M + m] = sum_{(b,d)} G[(b,d),u] * X0[(b,d),h] * Xk[(b,d),m].
 // Written as a GEMM over the rows r = (b, d):   D[(u,h), m] = sum_r P[(u,h), r] * Xk[r, m],   P[(u,h), r] = G[r,u] * X0[r,h].
-//   * a loader warp stages, per k-block of 32 rows (2 samples x 16 d) and CW_BST k-blocks ahead (cp.async): the Xk rows as the
+//   * two loader warps stage, per k-block of 32 rows (2 samples x 16 d) and CW_AHEAD k-blocks ahead (cp.async): the Xk rows as the
 //     K-major B tile (row m = Xk[b0,m,:] | Xk[b1,m,:], SWIZZLE_128B positions), the G rows [2][16 u][16 d] and the X0 rows
 //     [2][F][16 d] (chunks XOR-swizzled by (h >> 1) & 3 so that a quarter warp of consecutive h reads conflict-free).  The raw
-//     fp32 Xk tile is the "hi" operand (the tensor core ignores the low 13 mantissa bits); the loader writes lo = x - hi below
+//     fp32 Xk tile is the "hi" operand (the tensor core ignores the low 13 mantissa bits); its loader writes lo = x - hi below
 //     it: stacked [raw ; lo] operand of 2*NB rows (rows m >= M are zero), two TS-mode MMAs (a_lo, a_hi) per k-step.
 //   * A = P^T in tensor memory (TS mode): lane = (u, h) pair (416 pairs = 4 M-tiles of 128), columns = the 32 rows of the
 //     k-block.  An operand thread reads its two 64-byte rows G[b,u,:] and X0[b,h,:] from the stage (LDS.128), multiplies them
