@@ -639,7 +639,7 @@ def cpu_baseline_child(workload):
 def roofline_leg(w, model, cbs, ms_step, steps, graph_time):
     """`roofline` of the dominant memory kernel of the step's forward, on the ALGORITHMIC bytes of the embedding + interaction
     stage over the measured HBM copy bandwidth.  DeepFM: the one-kernel training forward the step launches
-    (deepfm_fwd_fused8_kernel: gather + dense pack + FM + layer-1 tcgen05 GEMM + tcgen05 tower tail + BCE; the 2 weight-split
+    (deepfm_fwd_fs_kernel: gather + dense pack + FM + layer-1 tcgen05 GEMM + tcgen05 tower tail + BCE; the 2 weight-split
     launches in front of it are inside the interval).  Other models: their gather launch (multi-table gather + dense pack +
     LR rows), timed alone."""
     from rec_pangu_b200 import ops
@@ -677,10 +677,10 @@ def roofline_leg(w, model, cbs, ms_step, steps, graph_time):
             us_f = graph_time(lambda cb: model(cb.as_dict()), steps)
             ach = alg * B / (us_f * 1e-6) / 1e9
             saved = alg + 4 * ((w['F'] * w['D'] + w['Nd'] + 3) // 4 * 4) + 4 * 64 * len(w['kw']['hidden_units']) + 4 * w['D'] + 8
-            out = {'kernel': 'deepfm_fwd_fused8_kernel (gather + dense pack + FM + layer-1 tcgen05 GEMM + tcgen05 tower tail + BCE in one '
+            out = {'kernel': 'deepfm_fwd_fs_kernel (gather + dense pack + FM + layer-1 tcgen05 GEMM + tcgen05 tower tail + BCE in one '
                              'launch, training variant: x and activations stored), the forward of the timed step',
                    'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
-                   'traffic': 248.9e6, 'traffic_source': 'profiles/r02_fused8_ncu.md (ncu --set full: dram__bytes_read 126.5 MB + write 122.3 MB per launch)',
+                   'traffic': 250.5e6, 'traffic_source': 'profiles/r02_deepfm_step_ncu.md (ncu --set full of deepfm_fwd_fs_kernel<6, 0, 8>: dram__bytes_read 127.7 MB + write 122.8 MB per launch)',
                    'us_per_launch': us_f, 'alg_bytes_per_launch': alg * B, 'peak_source': peak_src,
                    'share_of_step': us_f / (1e3 * ms_step), 'forward_only_samples_per_s': B / (us_f * 1e-6),
                    # the same launch against the bytes a TRAINING forward has to move: the algorithmic reads plus what it must
