@@ -687,9 +687,10 @@ def roofline_leg(w, model, cbs, ms_step, steps, graph_time):
                    # leave behind for backward (feature row x, h1..h3, fm_s, logit, pred)
                    'with_saved_activations': {'bytes_per_sample': saved, 'achieved': saved * B / (us_f * 1e-6) / 1e9,
                                               'frac': saved * B / (us_f * 1e-6) / 1e9 / peak},
-                   'floor_note': 'random 64-byte rows are bound by DRAM row activations, not bytes: 1.7 M row reads alone take 49.5 us '
-                                 '(tools/exp/exp_rowfetch.cu: LDGSTS, LDG, TMA gather4, cp.async.bulk all >= 49 us), with the x store '
-                                 '74 us; the kernel adds h1..h3 (profiles/r02_rowfetch.md)',
+                   'floor_note': 'random 64-byte rows are not bound by bytes: 1.7 M row reads alone take 49.5 us with 8 requesting warps '
+                                 'per SM (tools/exp/exp_rowfetch.cu: LDGSTS, LDG, TMA gather4, cp.async.bulk all >= 49 us), with the x store '
+                                 '74 us; the kernel adds h1..h3.  The limit is the rate at which an SM gets row requests accepted, not DRAM '
+                                 'latency: an L2 prefetch warp running ahead made the kernel 34 us slower (profiles/r02_rowfetch.md)',
                    'gather_only': gather}
     except Exception as ex:
         out = dict(out or {}, error=repr(ex))
