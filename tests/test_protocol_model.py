@@ -57,3 +57,47 @@ def test_colsum16_butterfly_mapping():
         v, off = new, off // 2
     res = v[:, 0] + v[lanes ^ 16, 0]
     assert np.allclose(res, V.sum(axis=0)[lanes & 15])
+
+
+# ---------------------------------------------------------------- cin_wgrad_tc_kernel (tools/sim/cin_wgrad_protocol.py)
+spec2 = importlib.util.spec_from_file_location('cin_wgrad_protocol', os.path.join(ROOT, 'tools', 'sim', 'cin_wgrad_protocol.py'))
+wg = importlib.util.module_from_spec(spec2)
+spec2.loader.exec_module(wg)
+
+
+@pytest.mark.parametrize('nkb', [0, 1, 2, 3, 4, 5, 6, 7, 13, 40])
+def test_cin_wgrad_protocol_is_live_and_hazard_free(nkb):
+    """Two cp.async loader warps (4 groups in flight over 6 stages), 8 software-pipelined operand warps, MMA issuer, asynchronous
+    tensor pipe and copy completion of cin_wgrad_tc_kernel: no deadlock, every read sees completely landed data of the right
+    k-block, for any number of k-blocks relative to the ring depths."""
+    for seed in range(12):
+        wg.Sim(nkb, random.Random(1000 * nkb + seed)).run()
+
+
+def _fails(make, seeds=40):
+    for seed in range(seeds):
+        try:
+            make(random.Random(seed)).run()
+        except (AssertionError, RuntimeError):
+            return True
+    return False
+
+
+def test_cin_wgrad_model_detects_protocol_mutations():
+    """The model is only evidence if it can fail: (a) waiting for one cp.async group too few lets the lo pass / the operand
+    warps read a stage that has not landed; (b) releasing the G / X0 stage before the last read lets the loader refill it under
+    a reader; (c) more groups in flight than stages: the prologue waits for a stage nobody can have consumed yet."""
+    def slack(rng):
+        s = wg.Sim(13, rng)
+        s.wait_slack = 1
+        return s
+
+    def early(rng):
+        s = wg.Sim(13, rng)
+        s.early_release = True
+        return s
+    assert _fails(slack)
+    assert _fails(early)
+    assert _fails(lambda rng: wg.Sim(13, rng, bst=4, ahead=5))
+    assert not _fails(lambda rng: wg.Sim(13, rng, bst=4, ahead=4), seeds=10)      # as many as stages is legal (no slack, no hazard)
+    assert not _fails(lambda rng: wg.Sim(13, rng), seeds=10)
