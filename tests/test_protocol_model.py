@@ -101,3 +101,27 @@ def test_cin_wgrad_model_detects_protocol_mutations():
     assert _fails(lambda rng: wg.Sim(13, rng, bst=4, ahead=5))
     assert not _fails(lambda rng: wg.Sim(13, rng, bst=4, ahead=4), seeds=10)      # as many as stages is legal (no slack, no hazard)
     assert not _fails(lambda rng: wg.Sim(13, rng), seeds=10)
+
+
+# ---------------------------------------------------------------- cin_fwd2_tc_kernel / cin_bwd_tc_kernel (tools/sim/cin_tile_protocol.py)
+spec3 = importlib.util.spec_from_file_location('cin_tile_protocol', os.path.join(ROOT, 'tools', 'sim', 'cin_tile_protocol.py'))
+tp = importlib.util.module_from_spec(spec3)
+spec3.loader.exec_module(tp)
+
+
+@pytest.mark.parametrize('ntiles', [2, 3, 4])
+def test_cin_tile_protocol_is_live_and_hazard_free(ntiles):
+    """Operand double buffer + accumulator ping-pong with a counter that runs across tiles (NTILES = 3: cin_fwd2 at M = 26;
+    2 / 4: the other instantiations), four operand and four epilogue warps, asynchronous tensor pipe."""
+    for tiles in (0, 1, 2, 3, 5, 8):
+        for seed in range(10):
+            tp.Sim(tiles, ntiles, random.Random(97 * tiles + 7 * ntiles + seed)).run()
+
+
+def test_cin_tile_model_detects_an_early_operand_release():
+    def early(rng):
+        s = tp.Sim(6, 3, rng)
+        s.early_a_release = True
+        return s
+    assert _fails(early, seeds=60)
+    assert not _fails(lambda rng: tp.Sim(6, 3, rng), seeds=10)
